@@ -1,0 +1,131 @@
+"""Generate tests/golden/*.npz by running the REAL reference (/root/reference,
+imported read-only with stub modules — see tests/refimport.py) on the seeded
+inputs of tests/golden/cases.py.  Run in the build container only:
+
+    python -m tests.golden.make_golden
+
+The reference has no golden vectors of its own, so these
+files are what pins both the oracle and the CUDA path.  Torch 2.11 CPU fp32,
+NumPy 2.3.
+"""
+import contextlib
+import os
+
+import numpy as np
+import torch
+
+from tests import refimport
+from tests.golden import cases
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@contextlib.contextmanager
+def injected(M, perms, rands):
+    """Feed the reference the permutations / random coordinates of the case
+    instead of its own RNG draws (same call order: rand(coords1), rand(coords2),
+    then one super_perm per negative; src/modules.py:1320-1321, :1341)."""
+    perm_it, rand_it = iter(perms), iter(rands)
+    old_perm, old_rand = M.super_perm, torch.rand
+    M.super_perm = lambda size, device: next(perm_it).clone()
+    torch.rand = lambda shape, device=None: next(rand_it).clone()
+    try:
+        yield
+    finally:
+        M.super_perm, torch.rand = old_perm, old_rand
+
+
+def run_loss_case(M, name):
+    cfg, t = cases.make_loss_inputs(name)
+    S = cfg.feature_samples
+    code = t["code"].clone().requires_grad_(True)
+    code_pos = t["code_pos"].clone().requires_grad_(True)
+    loss_fn = M.ContrastiveCorrelationLoss(cfg)
+    with injected(M, list(t["perms"]), [t["rand1"], t["rand2"]]):
+        out = loss_fn(t["feats"], t["feats_pos"], None, None, code, code_pos, t["depth"], t["depth_pos"])
+    w = cases.LOSS_WEIGHTS
+    L = w["pos_intra"] * out[0] + w["pos_inter"] * out[2] + w["neg_inter"] * out[4].mean()
+    if cfg.depth_feat_correlation_loss:
+        L = L + w["depth_feat"] * out[6]
+    L.backward()
+    if cfg.depth_sampling == "fps":
+        c1 = M.farthest_point_sampling_depth(t["feats"], t["depth"], S) * 2 - 1
+        c2 = M.farthest_point_sampling_depth(t["feats_pos"], t["depth_pos"], S) * 2 - 1
+    else:
+        c1, c2 = t["rand1"] * 2 - 1, t["rand2"] * 2 - 1
+    g = dict(coords1=c1.numpy(), coords2=c2.numpy(),
+             scalars=np.array([out[0].item(), out[2].item(), out[4].mean().item(),
+                               out[6].item() if len(out) == 8 else np.nan], np.float64),
+             cd_means=np.array([out[1].mean().item(), out[3].mean().item(), out[5].mean().item(),
+                                out[7].mean().item() if len(out) == 8 else np.nan], np.float64),
+             total=np.float64(L.item()), d_code=code.grad.numpy(), d_code_pos=code_pos.grad.numpy())
+    if S <= 8:
+        g.update(intra_cd=out[1].detach().numpy(), inter_cd=out[3].detach().numpy(),
+                 neg_loss=out[4].detach().numpy(), neg_cd=out[5].detach().numpy())
+        if len(out) == 8:
+            g["depth_dd"] = out[7].detach().numpy()
+    np.savez_compressed(os.path.join(HERE, f"loss_{name}.npz"), **g)
+    print(name, g["scalars"], g["cd_means"], float(np.linalg.norm(g["d_code"])), float(np.linalg.norm(g["d_code_pos"])))
+
+
+def run_fps(M):
+    out = {}
+    for pat in cases.FPS_PATTERNS:
+        depth = cases.make_fps_depth(pat)
+        t = torch.zeros(depth.shape[0], 1, 28, 28)
+        for S in cases.FPS_S:
+            coords = M.farthest_point_sampling_depth(t, depth, S)          # [B,S,S,2] in [0,1)
+            rc = torch.round(coords.reshape(depth.shape[0], S * S, 2) * 28).long()
+            out[f"{pat}_S{S}"] = (rc[..., 0] * 28 + rc[..., 1]).numpy().astype(np.int32)
+            out[f"{pat}_S{S}_coords"] = coords.numpy()
+    np.savez_compressed(os.path.join(HERE, "fps_index_sets.npz"), **out)
+    print("fps:", len(out), "arrays")
+
+
+def run_misc(M):
+    """Small known-answer vectors for the free functions."""
+    rs = np.random.RandomState(77)
+    t = torch.from_numpy(rs.standard_normal((2, 5, 28, 28)).astype(np.float32))
+    coords = torch.from_numpy((rs.random_sample((2, 4, 4, 2)) * 2.4 - 1.2).astype(np.float32))  # some out of range
+    depth = torch.from_numpy(rs.randint(0, 256, (2, 1, 224, 224)).astype(np.float32))
+    depth[0, 0, :100] = 0
+    d7 = torch.nn.functional.interpolate(depth, size=(7, 7), mode="bilinear", align_corners=True)
+    pts = M.depth2points(torch.nn.functional.adaptive_avg_pool2d(depth, (28, 28))[1, 0], fov=90)
+    np.savez_compressed(os.path.join(HERE, "misc.npz"),
+                        sample_out=M.sample(t, coords).numpy(), norm_out=M.norm(t).numpy(),
+                        corr_out=M.tensor_correlation(t[:, :, :3, :3], t[:, :, 5:9, 5:9]).numpy(),
+                        depth_sign7=M.norm(d7).numpy(), points=pts.numpy())
+
+
+def run_knn():
+    """precompute_knns.py cannot be imported (hydra/lightning absent); its loop
+    (src/precompute_knns.py:99-113) is stock torch and is restated verbatim here."""
+    out = {}
+    for name in cases.KNN_CASES:
+        normed_feats, k, n_batches = cases.make_knn_feats(name)
+        all_nns = []
+        step = normed_feats.shape[0] // n_batches
+        for i in range(0, normed_feats.shape[0], step):
+            batch_feats = normed_feats[i:i + step, :]
+            pairwise_sims = torch.einsum("nf,mf->nm", batch_feats, normed_feats)
+            all_nns.append(torch.topk(pairwise_sims, k)[1])
+        nn_idx = torch.cat(all_nns, dim=0)
+        out[name] = nn_idx.numpy()
+        out[name + "_vals"] = torch.gather(normed_feats @ normed_feats.T, 1, nn_idx).numpy()
+    np.savez_compressed(os.path.join(HERE, "knn.npz"), **out)
+    print("knn:", {k: v.shape for k, v in out.items()})
+
+
+def main():
+    assert refimport.have_reference(), "run in the build container (needs /root/reference)"
+    torch.set_num_threads(8)
+    M = refimport.load_reference_modules()
+    for name in cases.LOSS_CASES:
+        run_loss_case(M, name)
+    run_fps(M)
+    run_misc(M)
+    run_knn()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,49 @@
+"""Shared test plumbing: golden loading and running the oracle on a case."""
+import os
+
+import numpy as np
+import torch
+
+from oracle import depthg_oracle as O
+from tests.golden import cases
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def golden(name):
+    return dict(np.load(os.path.join(GOLDEN, name + ".npz")))
+
+
+def weighted_total(out, depth_term):
+    w = cases.LOSS_WEIGHTS
+    L = w["pos_intra"] * out[0] + w["pos_inter"] * out[2] + w["neg_inter"] * out[4].mean()
+    if depth_term:
+        L = L + w["depth_feat"] * out[6]
+    return L
+
+
+def run_oracle_loss(name):
+    """Oracle forward+backward on a golden case with the case's perms / random coords injected."""
+    cfg, t = cases.make_loss_inputs(name)
+    code = t["code"].clone().requires_grad_(True)
+    code_pos = t["code_pos"].clone().requires_grad_(True)
+    fn = O.ContrastiveCorrelationLoss(cfg)
+    perm_it, rand_it = iter(t["perms"]), iter([t["rand1"], t["rand2"]])
+    fn.perm_fn = lambda B, device: next(perm_it).clone()
+    fn.rand_fn = lambda shape, device: next(rand_it).clone()
+    out = fn(t["feats"], t["feats_pos"], None, None, code, code_pos, t["depth"], t["depth_pos"])
+    depth_term = cfg.depth_feat_correlation_loss
+    L = weighted_total(out, depth_term)
+    L.backward()
+    res = dict(coords1=fn.last_coords[0].numpy(), coords2=fn.last_coords[1].numpy(),
+               scalars=np.array([out[0].item(), out[2].item(), out[4].mean().item(),
+                                 out[6].item() if depth_term else np.nan]),
+               cd_means=np.array([out[1].mean().item(), out[3].mean().item(), out[5].mean().item(),
+                                  out[7].mean().item() if depth_term else np.nan]),
+               total=L.item(), d_code=code.grad.numpy(), d_code_pos=code_pos.grad.numpy(), out=out)
+    return cfg, t, res
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))

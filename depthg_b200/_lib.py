@@ -1,0 +1,116 @@
+"""ctypes binding of libdepthg_b200.so (the C ABI declared in include/depthg_b200.h).
+
+The library is built in-tree by ``__graft_entry__.build()`` (or ``make -C
+depthg_b200/csrc``).  There is no CPU or PyTorch fallback: if the shared
+object is missing, or a tensor is not a CUDA fp32 tensor, the call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdepthg_b200.so")
+
+DG_MAX_PAIRS = 32
+DG_MAX_SETS = 32
+GROUP_INTRA, GROUP_INTER, GROUP_NEG, GROUP_DEPTH = 0, 1, 2, 3
+FLAG_POINTWISE, FLAG_ZERO_CLAMP, FLAG_STABALIZE = 1, 2, 4
+
+_c_i32p = C.POINTER(C.c_int32)
+_c_i64p = C.POINTER(C.c_int64)
+_c_f32p = C.POINTER(C.c_float)
+_vp = C.c_void_p
+
+# name -> (restype, argtypes); must list every symbol include/depthg_b200.h declares
+SIGNATURES = {
+    "dg_version": (C.c_int, []),
+    "dg_last_error_string": (C.c_char_p, []),
+    "dg_kernel_launches": (C.c_ulonglong, []),
+    "dg_panel_ld": (C.c_int, [C.c_int]),
+    "dg_panel_rows": (C.c_int, [C.c_int]),
+    "dg_fps_coords": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
+                                C.c_int, _vp, _vp, _vp]),
+    "dg_depth_sign": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, _vp, _vp]),
+    "dg_gather_norm": (C.c_int, [_vp, _c_i64p, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_int, C.c_int, _c_i32p,
+                                 _c_i32p, _vp, C.c_float, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
+    "dg_gather_norm_bwd": (C.c_int, [_vp, _c_i64p, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_int, C.c_int, _c_i32p,
+                                     _c_i32p, _vp, C.c_float, C.c_int, C.c_int, _vp, _vp, _vp, _vp, C.c_int, _c_i32p,
+                                     _c_f32p, C.c_int, _vp, _vp]),
+    "dg_corr_loss_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "dg_corr_loss": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                               C.c_int, _c_f32p, _c_i32p, C.c_float, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                               C.c_size_t, _vp]),
+    "dg_knn_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "dg_knn_topk": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, C.c_size_t, _vp]),
+    "dg_pool_normalize": (C.c_int, [_vp, _c_i64p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _vp, _vp]),
+}
+
+_lib = None
+
+
+class DepthgB200Error(RuntimeError):
+    pass
+
+
+def lib():
+    """Load (once) and return the shared library; raise loudly if it is absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise DepthgB200Error(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(or `make -C depthg_b200/csrc`). depthg_b200 has no CPU / PyTorch fallback.")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = lib().dg_last_error_string().decode(errors="replace")
+        if rc in (-1, -2):
+            raise ValueError(f"{what}: {msg} (code {rc})")
+        raise DepthgB200Error(f"{what}: {msg} (code {rc})")
+
+
+def require_cuda_f32(t: torch.Tensor, name: str):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor, got {type(t).__name__}")
+    if not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor: depthg_b200 has no CPU path (got device {t.device})")
+    if t.dtype != torch.float32:
+        raise ValueError(f"{name} must be float32 (the reference computes in fp32), got {t.dtype}")
+
+
+def ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def i32_array(vals):
+    return (C.c_int32 * len(vals))(*[int(v) for v in vals])
+
+
+def i64_array(vals):
+    return (C.c_int64 * len(vals))(*[int(v) for v in vals])
+
+
+def f32_array(vals):
+    return (C.c_float * len(vals))(*[float(v) for v in vals])
+
+
+def panel_ld(channels: int) -> int:
+    return (channels + 31) // 32 * 32
+
+
+def panel_rows(P: int) -> int:
+    return (P + 63) // 64 * 64

@@ -1,0 +1,84 @@
+// Shared helpers for the depthg_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/depthg_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "depthg_b200 kernels are written for sm_100a (B200) only"
+#endif
+
+namespace dg {
+
+void set_error(const char* fmt, ...);
+void count_launch();  // bumps the process-wide kernel-launch counter (dg_kernel_launches)
+
+#define DG_REQUIRE(cond, code, ...)     \
+  do {                                  \
+    if (!(cond)) {                      \
+      ::dg::set_error(__VA_ARGS__);     \
+      return (code);                    \
+    }                                   \
+  } while (0)
+
+#define DG_CUDA_OK(expr)                                                                        \
+  do {                                                                                          \
+    cudaError_t e_ = (expr);                                                                    \
+    if (e_ != cudaSuccess) {                                                                    \
+      ::dg::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+      return DG_ERR_CUDA;                                                                       \
+    }                                                                                           \
+  } while (0)
+
+#define DG_LAUNCH_OK(name)                                                                   \
+  do {                                                                                       \
+    cudaError_t e_ = cudaGetLastError();                                                     \
+    if (e_ != cudaSuccess) {                                                                 \
+      ::dg::set_error("launch of %s failed: %s", name, cudaGetErrorString(e_));              \
+      return DG_ERR_CUDA;                                                                    \
+    }                                                                                        \
+    ::dg::count_launch();                                                                    \
+  } while (0)
+
+__host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+__host__ __device__ inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Bilinear corner set of torch.grid_sample(padding_mode='border', align_corners=True)
+// for one normalised coordinate pair; weights in ATen's nw/ne/sw/se order.
+struct Corners {
+  int x0, y0, x1, y1;      // x1/y1 may equal W/H (out of range) -> weight is dropped
+  float w00, w01, w10, w11;  // (y0,x0) (y0,x1) (y1,x0) (y1,x1)
+  bool x1_ok, y1_ok;
+};
+
+__device__ __forceinline__ Corners bilinear_corners(float gx, float gy, int H, int W) {
+  float ix = ((gx + 1.f) / 2.f) * (float)(W - 1);
+  float iy = ((gy + 1.f) / 2.f) * (float)(H - 1);
+  ix = fminf((float)(W - 1), fmaxf(ix, 0.f));
+  iy = fminf((float)(H - 1), fmaxf(iy, 0.f));
+  float fx = floorf(ix), fy = floorf(iy);
+  Corners c;
+  c.x0 = (int)fx;
+  c.y0 = (int)fy;
+  c.x1 = c.x0 + 1;
+  c.y1 = c.y0 + 1;
+  float ex = (fx + 1.f) - ix, ey = (fy + 1.f) - iy;  // distance to the se corner
+  float dx = ix - fx, dy = iy - fy;
+  c.w00 = ex * ey;
+  c.w01 = dx * ey;
+  c.w10 = ex * dy;
+  c.w11 = dx * dy;
+  c.x1_ok = c.x1 < W;
+  c.y1_ok = c.y1 < H;
+  return c;
+}
+
+}  // namespace dg

@@ -1,0 +1,230 @@
+// Depth-guided farthest point sampling, one CTA per image.
+//
+// Replaces farthest_point_sampling_depth / depth2points / fps of the reference
+// (/root/reference/src/modules.py:999-1037, :988-996, :939-985), which pools on
+// the device, copies every image to the host and runs a 120-round NumPy loop.
+// Here the whole chain stays in one kernel:
+//   1. adaptive average pooling of the [Hd,Wd] depth to [H,W]: each thread owns
+//      pooled pixels and sums its window row-major with sequential fp32 adds
+//      (128-bit loads when the window is 8 wide), then ATen's sum / kh / kw;
+//   2. lifting to 3-D with one explicit rounding per operation (no FMA);
+//   3. S*S-1 rounds of (distance to last pick, running min, block argmax).  The
+//      candidate key is the int view of the non-negative fp32 distance (-1 once a
+//      point is taken), so a warp argmax is two redux.sync instructions (max of
+//      the key, then min of the index among the maxima = NumPy's first-argmax);
+//      eight warp results meet in shared memory behind ONE barrier per round;
+//   4. the selection ORDER is discarded like the reference does: a block scan of
+//      the taken flags emits the picks in raster order as indices and as
+//      normalised (row/H, col/W) coordinates.
+#include "common.cuh"
+
+namespace dg {
+
+constexpr int FPS_THREADS = 256;
+constexpr int FPS_WARPS = FPS_THREADS / 32;
+
+template <int PPT>
+__global__ void __launch_bounds__(FPS_THREADS) fps_kernel(const float* __restrict__ depth_a,
+                                                          const float* __restrict__ depth_b, int B, int Hd, int Wd,
+                                                          int H, int W, int nsel, float factor, float far_plane,
+                                                          int affine, float* __restrict__ coords,
+                                                          int32_t* __restrict__ idx_out) {
+  extern __shared__ float fps_smem[];
+  const int npts = H * W;
+  float* sX = fps_smem;
+  float* sY = sX + npts;
+  float* sZ = sY + npts;
+  unsigned char* sTaken = reinterpret_cast<unsigned char*>(sZ + npts);
+  __shared__ int s_key[2][FPS_WARPS];
+  __shared__ int s_idx[2][FPS_WARPS];
+  __shared__ int s_scan[FPS_WARPS];
+
+  const int img = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* depth = (img < B ? depth_a + (size_t)img * Hd * Wd : depth_b + (size_t)(img - B) * Hd * Wd);
+
+  float X[PPT], Y[PPT], Z[PPT];
+  int key[PPT];  // int view of the running min distance; -1 once taken
+  const float halfH = (float)H / 2.0f, halfW = (float)W / 2.0f;
+
+#pragma unroll
+  for (int j = 0; j < PPT; ++j) {
+    const int i = j * FPS_THREADS + tid;
+    X[j] = Y[j] = Z[j] = 0.f;
+    key[j] = -1;
+    if (i < npts) {
+      const int py = i / W, px = i - py * W;
+      const int ys = (py * Hd) / H, ye = ((py + 1) * Hd + H - 1) / H;
+      const int xs = (px * Wd) / W, xe = ((px + 1) * Wd + W - 1) / W;
+      float acc = 0.f;
+      if (xe - xs == 8 && (Wd & 3) == 0 && (xs & 3) == 0) {
+        for (int y = ys; y < ye; ++y) {
+          const float4* row = reinterpret_cast<const float4*>(depth + (size_t)y * Wd + xs);
+          const float4 a = __ldg(row), b = __ldg(row + 1);
+          acc = __fadd_rn(acc, a.x); acc = __fadd_rn(acc, a.y); acc = __fadd_rn(acc, a.z); acc = __fadd_rn(acc, a.w);
+          acc = __fadd_rn(acc, b.x); acc = __fadd_rn(acc, b.y); acc = __fadd_rn(acc, b.z); acc = __fadd_rn(acc, b.w);
+        }
+      } else {
+        for (int y = ys; y < ye; ++y)
+          for (int x = xs; x < xe; ++x) acc = __fadd_rn(acc, __ldg(depth + (size_t)y * Wd + x));
+      }
+      const float pooled = __fdiv_rn(__fdiv_rn(acc, (float)(ye - ys)), (float)(xe - xs));  // ATen: sum / kh / kw
+      const float fd = __fmul_rn(factor, pooled);
+      X[j] = __fdiv_rn(__fmul_rn(fd, __fsub_rn((float)px, halfW)), (float)W);
+      Y[j] = __fdiv_rn(__fmul_rn(fd, __fsub_rn((float)py, halfH)), (float)H);
+      Z[j] = __fmul_rn(-pooled, far_plane);
+      key[j] = 0x7f800000;  // +inf
+      sX[i] = X[j];
+      sY[i] = Y[j];
+      sZ[i] = Z[j];
+      sTaken[i] = 0;
+    }
+  }
+  if (tid == 0) key[0] = -1;  // point 0 is the first pick (its smem flag is set below)
+  __syncthreads();
+  if (tid == 0) sTaken[0] = 1;
+
+  int last = 0;
+  for (int r = 1; r < nsel; ++r) {
+    const float lx = sX[last], ly = sY[last], lz = sZ[last];
+    int bk = -1, bi = 0x7fffffff;
+#pragma unroll
+    for (int j = 0; j < PPT; ++j) {
+      if (key[j] >= 0) {
+        const float dx = __fsub_rn(lx, X[j]), dy = __fsub_rn(ly, Y[j]), dz = __fsub_rn(lz, Z[j]);
+        const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+        const int k = min(key[j], __float_as_int(d));  // both non-negative floats -> int order == float order
+        key[j] = k;
+        if (k > bk) {  // strict: the lowest index wins ties inside a thread (j ascending)
+          bk = k;
+          bi = j * FPS_THREADS + tid;
+        }
+      }
+    }
+    const int wk = __reduce_max_sync(0xffffffffu, bk);
+    const int wi = __reduce_min_sync(0xffffffffu, bk == wk ? bi : 0x7fffffff);
+    const int buf = r & 1;
+    if (lane == 0) {
+      s_key[buf][warp] = wk;
+      s_idx[buf][warp] = wi;
+    }
+    __syncthreads();
+    int gk = -1, gi = 0x7fffffff;
+#pragma unroll
+    for (int w = 0; w < FPS_WARPS; ++w) {
+      const int k = s_key[buf][w], i = s_idx[buf][w];
+      if (k > gk || (k == gk && i < gi)) {
+        gk = k;
+        gi = i;
+      }
+    }
+    last = gi;
+    if ((last % FPS_THREADS) == tid) {
+      const int j = last / FPS_THREADS;
+#pragma unroll
+      for (int jj = 0; jj < PPT; ++jj)
+        if (jj == j) key[jj] = -1;
+      sTaken[last] = 1;
+    }
+  }
+  __syncthreads();
+
+  // Raster-order emission: each thread scans a contiguous chunk of point indices.
+  const int chunk = (npts + FPS_THREADS - 1) / FPS_THREADS;
+  const int beg = tid * chunk, end = min(beg + chunk, npts);
+  int cnt = 0;
+  for (int i = beg; i < end; ++i) cnt += sTaken[i];
+  int incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) s_scan[warp] = incl;
+  __syncthreads();
+  int base = 0;
+  for (int w = 0; w < warp; ++w) base += s_scan[w];
+  int rank = base + incl - cnt;
+  float* cimg = coords + (size_t)img * nsel * 2;
+  for (int i = beg; i < end; ++i) {
+    if (sTaken[i]) {
+      const int py = i / W, px = i - py * W;
+      float cy = __fdiv_rn((float)py, (float)H), cx = __fdiv_rn((float)px, (float)W);
+      if (affine) {
+        cy = __fsub_rn(__fmul_rn(cy, 2.0f), 1.0f);
+        cx = __fsub_rn(__fmul_rn(cx, 2.0f), 1.0f);
+      }
+      cimg[2 * rank + 0] = cy;
+      cimg[2 * rank + 1] = cx;
+      if (idx_out) idx_out[(size_t)img * nsel + rank] = i;
+      ++rank;
+    }
+  }
+}
+
+// s = d / max(|d|, eps) of the align_corners=True bilinear resample of depth to SxS.
+__global__ void depth_sign_kernel(const float* __restrict__ depth, int B, int Hd, int Wd, int S, float eps,
+                                  int out_pitch, float* __restrict__ out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= B * out_pitch) return;
+  const int b = t / out_pitch, p = t - b * out_pitch;
+  if (p >= S * S) {
+    out[t] = 0.f;
+    return;
+  }
+  const int h = p / S, w = p - h * S;
+  const float sy = S > 1 ? __fdiv_rn((float)(Hd - 1), (float)(S - 1)) : 0.f;
+  const float sx = S > 1 ? __fdiv_rn((float)(Wd - 1), (float)(S - 1)) : 0.f;
+  const float fy = __fmul_rn(sy, (float)h), fx = __fmul_rn(sx, (float)w);
+  const int y0 = min((int)fy, Hd - 1), x0 = min((int)fx, Wd - 1);
+  const int y1 = y0 + (y0 < Hd - 1 ? 1 : 0), x1 = x0 + (x0 < Wd - 1 ? 1 : 0);
+  const float ly = fminf(fmaxf(fy - (float)y0, 0.f), 1.f), lx = fminf(fmaxf(fx - (float)x0, 0.f), 1.f);
+  const float* d = depth + (size_t)b * Hd * Wd;
+  const float v00 = __ldg(d + (size_t)y0 * Wd + x0), v01 = __ldg(d + (size_t)y0 * Wd + x1);
+  const float v10 = __ldg(d + (size_t)y1 * Wd + x0), v11 = __ldg(d + (size_t)y1 * Wd + x1);
+  const float v = (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
+  out[t] = v / fmaxf(fabsf(v), eps);
+}
+
+}  // namespace dg
+
+extern "C" int dg_fps_coords(const float* depth_a, const float* depth_b, int B, int Hd, int Wd, int H, int W, int S,
+                             float factor, float far_plane, int affine, float* coords, int32_t* idx,
+                             dg_stream_t stream) {
+  using namespace dg;
+  DG_REQUIRE(depth_a && coords, DG_ERR_INVALID, "dg_fps_coords: null pointer");
+  DG_REQUIRE(B > 0 && Hd > 0 && Wd > 0 && H > 0 && W > 0 && S > 0, DG_ERR_INVALID, "dg_fps_coords: bad sizes");
+  DG_REQUIRE(H <= Hd && W <= Wd, DG_ERR_UNSUPPORTED, "dg_fps_coords: pooling must not upsample (%dx%d -> %dx%d)", Hd,
+             Wd, H, W);
+  const int npts = H * W;
+  DG_REQUIRE(S * S <= npts, DG_ERR_INVALID, "dg_fps_coords: S*S=%d exceeds H*W=%d points", S * S, npts);
+  DG_REQUIRE(npts <= 4096, DG_ERR_UNSUPPORTED, "dg_fps_coords: H*W=%d > 4096 not supported", npts);
+  const int nimg = depth_b ? 2 * B : B;
+  const size_t smem = (size_t)npts * (3 * sizeof(float) + 1);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (npts <= 4 * FPS_THREADS) {
+    fps_kernel<4><<<nimg, FPS_THREADS, smem, st>>>(depth_a, depth_b, B, Hd, Wd, H, W, S * S, factor, far_plane,
+                                                   affine, coords, idx);
+  } else if (npts <= 8 * FPS_THREADS) {
+    fps_kernel<8><<<nimg, FPS_THREADS, smem, st>>>(depth_a, depth_b, B, Hd, Wd, H, W, S * S, factor, far_plane,
+                                                   affine, coords, idx);
+  } else {
+    DG_CUDA_OK(cudaFuncSetAttribute(fps_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fps_kernel<16><<<nimg, FPS_THREADS, smem, st>>>(depth_a, depth_b, B, Hd, Wd, H, W, S * S, factor, far_plane,
+                                                    affine, coords, idx);
+  }
+  DG_LAUNCH_OK("fps_kernel");
+  return DG_OK;
+}
+
+extern "C" int dg_depth_sign(const float* depth, int B, int Hd, int Wd, int S, float eps, int out_pitch, float* out,
+                             dg_stream_t stream) {
+  using namespace dg;
+  DG_REQUIRE(depth && out, DG_ERR_INVALID, "dg_depth_sign: null pointer");
+  DG_REQUIRE(B > 0 && Hd > 0 && Wd > 0 && S > 0 && out_pitch >= S * S, DG_ERR_INVALID, "dg_depth_sign: bad sizes");
+  const int n = B * out_pitch;
+  depth_sign_kernel<<<ceil_div(n, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(depth, B, Hd, Wd, S, eps,
+                                                                                          out_pitch, out);
+  DG_LAUNCH_OK("depth_sign_kernel");
+  return DG_OK;
+}

@@ -1,0 +1,340 @@
+// Fused bilinear gather + L2 normalise (forward) and its scatter-add backward.
+//
+// Forward replaces sample() + norm() of the reference
+// (/root/reference/src/modules.py:822-825, :789-790) and the orig_feats[perm]
+// copies it makes for every negative (:1342-1343): one launch gathers ALL the
+// coordinate sets that read the same source tensor (own coords + one set per
+// negative), straight from the tensor's own strides (NCHW or channels-last),
+// and writes K-major row panels [slot][b][p][ld] ready for the correlation
+// kernel, plus 1/||x|| per row and the per-image mean row (pointwise centring).
+//
+// One CTA per (set, image); a warp owns a sample point at a time, lanes run over
+// channels (128-bit loads when the channel stride is 1), so a channels-last
+// source is read in whole 128-byte lines and every panel row is written once,
+// coalesced.  HBM-bound: no data reuse beyond the four bilinear corners.
+#include "common.cuh"
+
+namespace dg {
+
+constexpr int GATHER_THREADS = 512;
+constexpr int GATHER_WARPS = GATHER_THREADS / 32;
+
+struct SetTable {
+  int32_t coord[DG_MAX_SETS];
+  int32_t slot[DG_MAX_SETS];
+};
+
+// dynamic smem: row staging [GATHER_WARPS][ld] + mean accumulators [GATHER_WARPS][ld]
+__global__ void __launch_bounds__(GATHER_THREADS)
+    gather_norm_kernel(const float* __restrict__ t, int64_t sb, int64_t sc, int64_t sh, int64_t sw, int B, int C, int H,
+                       int W, const float* __restrict__ coords, int S, SetTable sets, const int64_t* __restrict__ perm,
+                       float eps, int Prows, int ld, float* __restrict__ out, float* __restrict__ rnorm,
+                       float* __restrict__ meanvec) {
+  extern __shared__ float gsm[];
+  const int set = blockIdx.x / B, b = blockIdx.x - set * B;
+  const int P = S * S;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* row = gsm + (size_t)warp * ld;
+  float* macc = gsm + (size_t)(GATHER_WARPS + warp) * ld;
+  const int slot = sets.slot[set];
+  const int64_t src = perm ? perm[(size_t)set * B + b] : (int64_t)b;
+  const float* timg = t + src * sb;
+  const float* cset = coords + ((size_t)sets.coord[set] * B + b) * P * 2;
+  float* opanel = out + ((size_t)slot * B + b) * Prows * ld;
+  float* rpanel = rnorm + ((size_t)slot * B + b) * Prows;
+
+  for (int c = lane; c < ld; c += 32) macc[c] = 0.f;
+  const bool vec = (sc == 1) && ((C & 3) == 0) && ((sb & 3) == 0) && ((sh & 3) == 0) && ((sw & 3) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(t) & 15) == 0);
+
+  for (int p = warp; p < Prows; p += GATHER_WARPS) {
+    float* orow = opanel + (size_t)p * ld;
+    if (p >= P) {  // zero padding rows
+      for (int c = lane; c < ld; c += 32) orow[c] = 0.f;
+      if (lane == 0) rpanel[p] = 0.f;
+      continue;
+    }
+    const int h = p / S, w = p - h * S;
+    const float* cc = cset + 2 * (w * S + h);  // the reference's S-axis swap (coords.permute(0,2,1,3))
+    const Corners k = bilinear_corners(__ldg(cc), __ldg(cc + 1), H, W);
+    const float* p00 = timg + k.y0 * sh + k.x0 * sw;
+    const float* p01 = k.x1_ok ? p00 + sw : p00;
+    const float* p10 = k.y1_ok ? p00 + sh : p00;
+    const float* p11 = p10 + (k.x1_ok ? sw : 0);
+    const float w00 = k.w00, w01 = k.x1_ok ? k.w01 : 0.f, w10 = k.y1_ok ? k.w10 : 0.f,
+                w11 = (k.x1_ok && k.y1_ok) ? k.w11 : 0.f;
+    float ss = 0.f;
+    if (vec) {
+      for (int c = lane * 4; c < C; c += 128) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(p00 + c));
+        const float4 bq = __ldg(reinterpret_cast<const float4*>(p01 + c));
+        const float4 cq = __ldg(reinterpret_cast<const float4*>(p10 + c));
+        const float4 d = __ldg(reinterpret_cast<const float4*>(p11 + c));
+        float4 v;
+        v.x = a.x * w00 + bq.x * w01 + cq.x * w10 + d.x * w11;
+        v.y = a.y * w00 + bq.y * w01 + cq.y * w10 + d.y * w11;
+        v.z = a.z * w00 + bq.z * w01 + cq.z * w10 + d.z * w11;
+        v.w = a.w * w00 + bq.w * w01 + cq.w * w10 + d.w * w11;
+        ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+        *reinterpret_cast<float4*>(row + c) = v;
+      }
+    } else {
+      for (int c = lane; c < C; c += 32) {
+        const int64_t o = (int64_t)c * sc;
+        const float v = __ldg(p00 + o) * w00 + __ldg(p01 + o) * w01 + __ldg(p10 + o) * w10 + __ldg(p11 + o) * w11;
+        ss += v * v;
+        row[c] = v;
+      }
+    }
+    ss = warp_sum(ss);
+    const float r = 1.f / fmaxf(sqrtf(ss), eps);
+    __syncwarp();
+    if (vec) {
+      for (int c = lane * 4; c < ld; c += 128) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < C) {
+          v = *reinterpret_cast<const float4*>(row + c);
+          v.x *= r; v.y *= r; v.z *= r; v.w *= r;
+          float4 m = *reinterpret_cast<float4*>(macc + c);
+          m.x += v.x; m.y += v.y; m.z += v.z; m.w += v.w;
+          *reinterpret_cast<float4*>(macc + c) = m;
+        }
+        *reinterpret_cast<float4*>(orow + c) = v;
+      }
+    } else {
+      for (int c = lane; c < ld; c += 32) {
+        float v = 0.f;
+        if (c < C) {
+          v = row[c] * r;
+          macc[c] += v;
+        }
+        orow[c] = v;
+      }
+    }
+    if (lane == 0) rpanel[p] = r;
+    __syncwarp();
+  }
+  if (meanvec == nullptr) return;
+  __syncthreads();
+  float* mv = meanvec + ((size_t)slot * B + b) * ld;
+  const float invP = 1.f / (float)P;
+  for (int c = threadIdx.x; c < ld; c += GATHER_THREADS) {
+    float s = 0.f;
+#pragma unroll
+    for (int wdx = 0; wdx < GATHER_WARPS; ++wdx) s += gsm[(size_t)(GATHER_WARPS + wdx) * ld + c];
+    mv[c] = s * invP;
+  }
+}
+
+struct PairTable {
+  int32_t group[DG_MAX_PAIRS + 1];
+  float scale[DG_MAX_PAIRS + 1];
+};
+
+// One warp per panel row: compose the row's gradient from the unit gradients,
+// back through x/max(||x||,eps), then atomically scatter through the 4 corners.
+__global__ void __launch_bounds__(256)
+    gather_norm_bwd_kernel(float* __restrict__ grad, int64_t sb, int64_t sc, int64_t sh, int64_t sw, int B, int C, int H,
+                           int W, const float* __restrict__ coords, int S, SetTable sets,
+                           const int64_t* __restrict__ perm, float eps, int Prows, int ld, const float* __restrict__ cn,
+                           const float* __restrict__ rnorm, const float* __restrict__ dC1, const float* __restrict__ dC2,
+                           int npairs, PairTable pairs, int has_depth, const float* __restrict__ group_w, int nsets) {
+  const int P = S * S;
+  const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp_global >= nsets * B * P) return;
+  const int set = warp_global / (B * P);
+  const int rem = warp_global - set * B * P;
+  const int b = rem / P, p = rem - b * P;
+  const int slot = sets.slot[set];
+  const size_t panel = (size_t)B * Prows * ld;
+  const size_t rowoff = ((size_t)b * Prows + p) * ld;
+  const int R = ld / 32;  // ld is a multiple of 32, <= 8 chunks handled in registers
+  float g[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) g[j] = 0.f;
+  if (slot == 0) {
+    for (int k = 0; k < npairs; ++k) {
+      const float wk = __ldg(group_w + pairs.group[k]) * pairs.scale[k];
+      const float* a = dC1 + (size_t)k * panel + rowoff;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j < R) g[j] += wk * __ldg(a + lane + 32 * j);
+    }
+    {
+      const float w0 = __ldg(group_w + pairs.group[0]) * pairs.scale[0];
+      const float* a = dC2 + rowoff;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j < R) g[j] += w0 * __ldg(a + lane + 32 * j);
+    }
+    if (has_depth) {
+      const float wd = __ldg(group_w + DG_GROUP_DEPTH);
+      const float* a1 = dC1 + (size_t)npairs * panel + rowoff;
+      const float* a2 = dC2 + (size_t)npairs * panel + rowoff;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j < R) g[j] += wd * (__ldg(a1 + lane + 32 * j) + __ldg(a2 + lane + 32 * j));
+    }
+  } else {
+    const float ws = __ldg(group_w + pairs.group[slot]) * pairs.scale[slot];
+    const float* a = dC2 + (size_t)slot * panel + rowoff;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (j < R) g[j] = ws * __ldg(a + lane + 32 * j);
+  }
+  const float* xh = cn + (size_t)slot * panel + rowoff;
+  const float r = __ldg(rnorm + ((size_t)slot * B + b) * Prows + p);
+  float x[8];
+  float dot = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    x[j] = (j < R) ? __ldg(xh + lane + 32 * j) : 0.f;
+    dot += g[j] * x[j];
+  }
+  dot = warp_sum(dot);
+  const bool clamped = r * eps >= 0.9999f;  // ||x|| <= eps: the denominator was the constant eps
+  if (clamped) dot = 0.f;
+
+  const int h = p / S, w = p - h * S;
+  const float* cc = coords + (((size_t)sets.coord[set] * B + b) * P + (w * S + h)) * 2;
+  const Corners k = bilinear_corners(__ldg(cc), __ldg(cc + 1), H, W);
+  const int64_t src = perm ? perm[(size_t)set * B + b] : (int64_t)b;
+  float* g00 = grad + src * sb + k.y0 * sh + k.x0 * sw;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = lane + 32 * j;
+    if (j < R && c < C) {
+      const float dx = (g[j] - x[j] * dot) * r;
+      float* q = g00 + (int64_t)c * sc;
+      atomicAdd(q, dx * k.w00);
+      if (k.x1_ok) atomicAdd(q + sw, dx * k.w01);
+      if (k.y1_ok) atomicAdd(q + sh, dx * k.w10);
+      if (k.x1_ok && k.y1_ok) atomicAdd(q + sh + sw, dx * k.w11);
+    }
+  }
+}
+
+// get_feats pooling: mean over H,W then L2 normalise (src/precompute_knns.py:19).
+__global__ void __launch_bounds__(256) pool_normalize_kernel(const float* __restrict__ t, int64_t sb, int64_t sc,
+                                                             int64_t sh, int64_t sw, int C, int H, int W, float eps,
+                                                             float* __restrict__ out) {
+  extern __shared__ float psm[];  // [C]
+  __shared__ float red[8];
+  const float* timg = t + (int64_t)blockIdx.x * sb;
+  const int HW = H * W;
+  const float inv = 1.f / (float)HW;
+  float ss = 0.f;
+  if (sc == 1) {  // channels-last: threads over channels, loop over pixels (coalesced)
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      float s = 0.f;
+      for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x) s += __ldg(timg + y * sh + x * sw + c);
+      s *= inv;
+      psm[c] = s;
+      ss += s * s;
+    }
+  } else {  // NCHW: a warp per channel plane, lanes over pixels
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int c = warp; c < C; c += nw) {
+      float s = 0.f;
+      for (int i = lane; i < HW; i += 32) {
+        const int y = i / W, x = i - y * W;
+        s += __ldg(timg + (int64_t)c * sc + y * sh + x * sw);
+      }
+      s = warp_sum(s) * inv;
+      if (lane == 0) {
+        psm[c] = s;
+        ss += s * s;
+      }
+    }
+  }
+  ss = warp_sum(ss);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  float tot = 0.f;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tot += red[i];
+  const float r = 1.f / fmaxf(sqrtf(tot), eps);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) out[(size_t)blockIdx.x * C + c] = psm[c] * r;
+}
+
+static int check_sets(const char* fn, int nsets, const int32_t* set_coord, const int32_t* set_slot, SetTable* tab) {
+  DG_REQUIRE(nsets > 0 && nsets <= DG_MAX_SETS, DG_ERR_INVALID, "%s: nsets=%d out of range", fn, nsets);
+  DG_REQUIRE(set_coord && set_slot, DG_ERR_INVALID, "%s: null set tables", fn);
+  for (int s = 0; s < nsets; ++s) {
+    DG_REQUIRE(set_coord[s] >= 0 && set_slot[s] >= 0, DG_ERR_INVALID, "%s: negative set entry", fn);
+    tab->coord[s] = set_coord[s];
+    tab->slot[s] = set_slot[s];
+  }
+  return DG_OK;
+}
+
+}  // namespace dg
+
+extern "C" int dg_panel_ld(int channels) { return dg::round_up(channels, 32); }
+extern "C" int dg_panel_rows(int P) { return dg::round_up(P, 64); }
+
+extern "C" int dg_gather_norm(const float* t, const int64_t* strides, int B, int C, int H, int W, const float* coords,
+                              int S, int nsets, const int32_t* set_coord, const int32_t* set_slot, const int64_t* perm,
+                              float eps, int Prows, int ld, float* out, float* rnorm, float* meanvec,
+                              dg_stream_t stream) {
+  using namespace dg;
+  DG_REQUIRE(t && strides && coords && out && rnorm, DG_ERR_INVALID, "dg_gather_norm: null pointer");
+  DG_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && S > 0, DG_ERR_INVALID, "dg_gather_norm: bad sizes");
+  DG_REQUIRE(ld >= C && (ld % 32) == 0, DG_ERR_INVALID, "dg_gather_norm: ld=%d must be a multiple of 32 >= C=%d", ld, C);
+  DG_REQUIRE(Prows >= S * S, DG_ERR_INVALID, "dg_gather_norm: Prows=%d < S*S=%d", Prows, S * S);
+  SetTable tab;
+  int rc = check_sets("dg_gather_norm", nsets, set_coord, set_slot, &tab);
+  if (rc != DG_OK) return rc;
+  const size_t smem = (size_t)2 * GATHER_WARPS * ld * sizeof(float);
+  DG_REQUIRE(smem <= 200 * 1024, DG_ERR_UNSUPPORTED, "dg_gather_norm: C=%d too large for the row staging buffer", C);
+  DG_CUDA_OK(cudaFuncSetAttribute(gather_norm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  gather_norm_kernel<<<nsets * B, GATHER_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+      t, strides[0], strides[1], strides[2], strides[3], B, C, H, W, coords, S, tab, perm, eps, Prows, ld, out, rnorm,
+      meanvec);
+  DG_LAUNCH_OK("gather_norm_kernel");
+  return DG_OK;
+}
+
+extern "C" int dg_gather_norm_bwd(float* grad, const int64_t* strides, int B, int C, int H, int W, const float* coords,
+                                  int S, int nsets, const int32_t* set_coord, const int32_t* set_slot,
+                                  const int64_t* perm, float eps, int Prows, int ld, const float* cn,
+                                  const float* rnorm, const float* dC1, const float* dC2, int npairs,
+                                  const int32_t* pair_group, const float* pair_scale, int has_depth,
+                                  const float* group_w, dg_stream_t stream) {
+  using namespace dg;
+  DG_REQUIRE(grad && strides && coords && cn && rnorm && dC1 && dC2 && group_w && pair_group && pair_scale,
+             DG_ERR_INVALID, "dg_gather_norm_bwd: null pointer");
+  DG_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && S > 0, DG_ERR_INVALID, "dg_gather_norm_bwd: bad sizes");
+  DG_REQUIRE(ld >= C && (ld % 32) == 0 && ld <= 256, DG_ERR_UNSUPPORTED,
+             "dg_gather_norm_bwd: ld=%d must be a multiple of 32 in [C,256]", ld);
+  DG_REQUIRE(npairs > 0 && npairs <= DG_MAX_PAIRS, DG_ERR_INVALID, "dg_gather_norm_bwd: npairs=%d", npairs);
+  SetTable tab;
+  int rc = check_sets("dg_gather_norm_bwd", nsets, set_coord, set_slot, &tab);
+  if (rc != DG_OK) return rc;
+  PairTable pt;
+  for (int k = 0; k < npairs; ++k) {
+    DG_REQUIRE(pair_group[k] >= 0 && pair_group[k] < DG_NUM_GROUPS, DG_ERR_INVALID, "dg_gather_norm_bwd: bad group");
+    pt.group[k] = pair_group[k];
+    pt.scale[k] = pair_scale[k];
+  }
+  for (int s = 0; s < nsets; ++s)
+    DG_REQUIRE(set_slot[s] < npairs, DG_ERR_INVALID, "dg_gather_norm_bwd: slot %d >= npairs", set_slot[s]);
+  const long long rows = (long long)nsets * B * S * S;
+  const int blocks = (int)((rows * 32 + 255) / 256);
+  gather_norm_bwd_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      grad, strides[0], strides[1], strides[2], strides[3], B, C, H, W, coords, S, tab, perm, eps, Prows, ld, cn, rnorm,
+      dC1, dC2, npairs, pt, has_depth, group_w, nsets);
+  DG_LAUNCH_OK("gather_norm_bwd_kernel");
+  return DG_OK;
+}
+
+extern "C" int dg_pool_normalize(const float* t, const int64_t* strides, int N, int C, int H, int W, float eps,
+                                 float* out, dg_stream_t stream) {
+  using namespace dg;
+  DG_REQUIRE(t && strides && out, DG_ERR_INVALID, "dg_pool_normalize: null pointer");
+  DG_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0 && C <= 12288, DG_ERR_INVALID, "dg_pool_normalize: bad sizes");
+  pool_normalize_kernel<<<N, 256, (size_t)C * sizeof(float), reinterpret_cast<cudaStream_t>(stream)>>>(
+      t, strides[0], strides[1], strides[2], strides[3], C, H, W, eps, out);
+  DG_LAUNCH_OK("pool_normalize_kernel");
+  return DG_OK;
+}

@@ -1,0 +1,77 @@
+"""KNN build of the reference's ``precompute_knns.py`` on sm_100a kernels.
+
+The reference (/root/reference/src/precompute_knns.py:94-115) pools + normalises
+backbone features, then on the CPU computes a [N/64, N] similarity block per chunk
+and takes ``topk(…, 30)``.  Here the similarity GEMM and the running top-k are one
+kernel (``dg_knn_topk``); the similarity matrix is never materialised.  Query rows
+shard across GPUs; the database is all-gathered (``depthg_b200.distributed``).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, ptr, require_cuda_f32, stream_ptr
+
+TOPK = 30          # src/precompute_knns.py:108
+N_BATCHES = 64     # src/precompute_knns.py:51 (chunking of the reference loop; the kernel streams instead)
+
+
+def knn_topk(queries: torch.Tensor, db: torch.Tensor, k: int = TOPK, return_sims: bool = False):
+    """Top-k database rows by fp32 dot product for every query row.
+
+    queries [Nq,F], db [N,F] CUDA fp32 (unit-norm rows for cosine similarity).
+    Returns int64 [Nq,k] sorted by descending similarity (and the similarities)."""
+    require_cuda_f32(queries, "queries")
+    require_cuda_f32(db, "db")
+    if queries.dim() != 2 or db.dim() != 2 or queries.shape[1] != db.shape[1]:
+        raise ValueError(f"queries {tuple(queries.shape)} / db {tuple(db.shape)} must be [Nq,F] and [N,F]")
+    if not 1 <= k <= 32:
+        raise ValueError(f"k={k} must be in [1,32] (the reference uses 30)")
+    if k > db.shape[0]:
+        raise ValueError(f"k={k} exceeds the database size {db.shape[0]}")
+    queries, db = queries.contiguous(), db.contiguous()
+    Nq, F = queries.shape
+    N = db.shape[0]
+    if Nq == 0:
+        return torch.empty((0, k), device=db.device, dtype=torch.int64)
+    idx = torch.empty((Nq, k), device=db.device, dtype=torch.int64)
+    sims = torch.empty((Nq, k), device=db.device, dtype=torch.float32) if return_sims else None
+    lib = _lib.lib()
+    ws_bytes = lib.dg_knn_workspace_bytes(Nq, N, F, k)
+    ws = torch.empty(ws_bytes, device=db.device, dtype=torch.uint8)
+    check(lib.dg_knn_topk(ptr(queries), ptr(db), Nq, N, F, k, ptr(idx), ptr(sims), ptr(ws), ws_bytes, stream_ptr()),
+          "dg_knn_topk")
+    return (idx, sims) if return_sims else idx
+
+
+def build_knn_index(normed_feats: torch.Tensor, k: int = TOPK, n_batches: int = N_BATCHES) -> torch.Tensor:
+    """The whole loop of src/precompute_knns.py:99-113 as one call: int64 [N,k].
+    ``n_batches`` is accepted for signature parity; chunking does not change the
+    result and the kernel streams the database tile by tile instead."""
+    del n_batches
+    return knn_topk(normed_feats, normed_feats, k)
+
+
+def pool_normalize(feat_maps: torch.Tensor, eps: float = 1e-12) -> torch.Tensor:
+    """get_feats' ``F.normalize(model(img).mean([2,3]), dim=1)`` (src/precompute_knns.py:19)
+    as one kernel.  feat_maps [N,C,H,W] (any strides) -> [N,C]."""
+    require_cuda_f32(feat_maps, "feat_maps")
+    if feat_maps.dim() != 4:
+        raise ValueError("feat_maps must be [N,C,H,W]")
+    N, Cdim, H, W = feat_maps.shape
+    out = torch.empty((N, Cdim), device=feat_maps.device, dtype=torch.float32)
+    check(_lib.lib().dg_pool_normalize(ptr(feat_maps), _lib.i64_array(feat_maps.stride()), N, Cdim, H, W, eps,
+                                       ptr(out), stream_ptr()), "dg_pool_normalize")
+    return out
+
+
+def nns_filename(model_type, dataset_name, image_set, crop_type, res) -> str:
+    """File name contract of src/precompute_knns.py:71-72 / src/data.py:1056-1057."""
+    return "nns_{}_{}_{}_{}_{}.npz".format(model_type, dataset_name, image_set, crop_type, res)
+
+
+def save_nns(path: str, nearest_neighbors: torch.Tensor) -> None:
+    """np.savez_compressed(file, nns=int64[N,k]) (src/precompute_knns.py:115)."""
+    np.savez_compressed(path, nns=nearest_neighbors.to("cpu", torch.int64).numpy())

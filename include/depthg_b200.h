@@ -1,0 +1,177 @@
+/* depthg_b200 — C ABI of the B200-native DepthG hot path.
+ *
+ * This is the drop-in boundary.  Every entry point
+ *   - is extern "C", takes plain pointers and sizes, no torch / C++ types;
+ *   - takes DEVICE pointers unless the parameter is documented "host";
+ *   - enqueues its kernels on `stream` and returns without synchronising;
+ *   - never allocates: the caller owns every buffer including workspaces
+ *     (sizes come from the dg_*_workspace_bytes helpers);
+ *   - returns DG_OK (0) or a negative DG_ERR_* code; the text of the last
+ *     failure on the calling thread is available from dg_last_error_string().
+ * Kernels are compiled for sm_100a only; there is no CPU path.
+ *
+ * The reference (leonsick/depthg) is pure Python: what each entry point
+ * replaces is a function of /root/reference/src/modules.py or
+ * src/precompute_knns.py, cited per declaration.
+ */
+#ifndef DEPTHG_B200_H_
+#define DEPTHG_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* dg_stream_t; /* == cudaStream_t */
+
+#if defined(__GNUC__)
+#define DG_API __attribute__((visibility("default")))
+#else
+#define DG_API
+#endif
+
+enum {
+  DG_OK = 0,
+  DG_ERR_INVALID = -1,     /* bad argument (null pointer, non-positive size, bad pitch) */
+  DG_ERR_UNSUPPORTED = -2, /* shape outside what the kernels are built for            */
+  DG_ERR_WORKSPACE = -3,   /* workspace too small                                     */
+  DG_ERR_CUDA = -4         /* a CUDA runtime call / launch failed                     */
+};
+
+#define DG_MAX_PAIRS 32 /* helper() calls per forward: 1 intra + 1 inter + neg_samples */
+#define DG_MAX_SETS 32  /* coordinate sets gathered from one source tensor per launch  */
+
+/* Pair groups: which scalar of the reference's output tuple a pair feeds. */
+enum { DG_GROUP_INTRA = 0, DG_GROUP_INTER = 1, DG_GROUP_NEG = 2, DG_GROUP_DEPTH = 3, DG_NUM_GROUPS = 4 };
+
+/* Flags of ContrastiveCorrelationLoss.helper (src/modules.py:1231-1254). */
+enum { DG_FLAG_POINTWISE = 1, DG_FLAG_ZERO_CLAMP = 2, DG_FLAG_STABALIZE = 4 };
+
+DG_API int dg_version(void);
+DG_API const char* dg_last_error_string(void);
+/* Number of kernels this library has launched in this process (for launch accounting). */
+DG_API unsigned long long dg_kernel_launches(void);
+
+/* Pitch (in floats) of a panel row holding `channels` values: rounded up to a
+ * multiple of 32 so a row is a whole number of 128-byte lines. */
+DG_API int dg_panel_ld(int channels);
+/* Rows of a panel holding P sample points: rounded up to a multiple of 64. */
+DG_API int dg_panel_rows(int P);
+
+/* ---------------------------------------------------------------------------
+ * Depth-guided farthest point sampling.
+ * Replaces farthest_point_sampling_depth + depth2points + fps
+ * (src/modules.py:999-1037, :988-996, :939-985) for up to two depth tensors in
+ * one launch (one CTA per image, nothing leaves the device).
+ *
+ *   depth_a, depth_b : [B,1,Hd,Wd] fp32 contiguous; depth_b may be NULL.
+ *   H, W             : feature-grid size the depth is average-pooled to
+ *                      (adaptive_avg_pool2d window rule); H*W <= 4096.
+ *   S                : feature_samples; S*S <= H*W points are selected.
+ *   factor, far_plane: 2*tan(fov/2) as an fp32 value computed by the caller
+ *                      (the reference feeds 90 to tan in radians) and 5.0.
+ *   affine           : 0 -> coords in [0,1) as the reference function returns
+ *                      them; 1 -> coords*2-1 as the loss consumes them.
+ *   coords           : out [nimg,S,S,2] (row/H, col/W), raster order.
+ *   idx              : out [nimg,S*S] int32 flat indices row*W+col, ascending
+ *                      (may be NULL).   nimg = B or 2B (depth_a then depth_b).
+ * Arithmetic is fp32 with one rounding per operation and no FMA contraction, so
+ * index sets are bit-identical to the reference's NumPy path. */
+DG_API int dg_fps_coords(const float* depth_a, const float* depth_b, int B, int Hd, int Wd, int H, int W, int S,
+                  float factor, float far_plane, int affine, float* coords, int32_t* idx, dg_stream_t stream);
+
+/* norm(interpolate(depth,(S,S),bilinear,align_corners=True)) of
+ * depth_feature_correlation (src/modules.py:1261-1265): s = d / max(|d|, eps).
+ *   depth [B,1,Hd,Wd] -> out [B, out_pitch] (first S*S entries per image, rest zeroed). */
+DG_API int dg_depth_sign(const float* depth, int B, int Hd, int Wd, int S, float eps, int out_pitch, float* out,
+                  dg_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * Fused bilinear gather + L2 normalise.  Replaces sample() + norm()
+ * (src/modules.py:822-825, :789-790) and the orig_feats[perm] copies (:1342).
+ *
+ *   t        : source tensor, logical shape [B,C,H,W], element strides
+ *              strides[4] = (b,c,h,w) (host array) — NCHW and channels-last
+ *              both work without a copy.
+ *   coords   : [ncoord,B,S*S,2] in [-1,1]; (.,0) addresses x/width, (.,1) y/height
+ *              (grid_sample convention, padding 'border', align_corners=True).
+ *   nsets    : number of output panels; for set s (host arrays of length nsets)
+ *                set_coord[s] : which coordinate block to use,
+ *                set_slot[s]  : which panel slot of `out` to write,
+ *              and row b of the panel samples image perm[s*B+b] (perm NULL -> b).
+ *   out      : [nslots,B,Prows,ld]; row p = h*S+w holds the sample at coordinate
+ *              index w*S+h (the reference's axis swap), L2-normalised over C
+ *              with eps; rows >= S*S and columns >= C are zero-filled.
+ *   rnorm    : [nslots,B,Prows]  1/max(||x||,eps) per row (needed by backward).
+ *   meanvec  : [nslots,B,ld]     mean over the S*S rows of the normalised panel
+ *              (NULL to skip; needed for pointwise centring). */
+DG_API int dg_gather_norm(const float* t, const int64_t* strides, int B, int C, int H, int W, const float* coords, int S,
+                   int nsets, const int32_t* set_coord, const int32_t* set_slot, const int64_t* perm, float eps,
+                   int Prows, int ld, float* out, float* rnorm, float* meanvec, dg_stream_t stream);
+
+/* Backward of dg_gather_norm for the code tensors: combines the unit
+ * gradients of dg_corr_loss with the upstream scalars, goes back through the
+ * normalisation and scatter-adds through the bilinear weights (atomicAdd; the
+ * caller zero-initialises `grad`).
+ *
+ *   grad     : gradient w.r.t. the source tensor, same logical shape/strides as t.
+ *   cn,rnorm : the code panels / reciprocal norms written by the forward gather.
+ *   dC1,dC2  : [npairs+1,B,Prows,ld] unit gradients from dg_corr_loss.
+ *   group_w  : device [DG_NUM_GROUPS] upstream gradients of the four scalar losses.
+ *   pair_group (host [npairs]) / pair_scale (host [npairs]): group of pair k and
+ *              the factor that turns its mean into the group's mean (1/neg_samples
+ *              for negatives, 1 otherwise).  Pair k reads code slot k as its
+ *              second operand and slot 0 as its first; index npairs is the depth term.
+ * Slot 0 rows receive sum_k w_k dC1[k] + w_0 dC2[0] (+ depth), slot s>0 rows w_s dC2[s]. */
+DG_API int dg_gather_norm_bwd(float* grad, const int64_t* strides, int B, int C, int H, int W, const float* coords, int S,
+                       int nsets, const int32_t* set_coord, const int32_t* set_slot, const int64_t* perm, float eps,
+                       int Prows, int ld, const float* cn, const float* rnorm, const float* dC1, const float* dC2,
+                       int npairs, const int32_t* pair_group, const float* pair_scale, int has_depth,
+                       const float* group_w, dg_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * Fused correlation loss, forward + unit gradients.  Replaces helper() for
+ * every pair and depth_feature_correlation() (src/modules.py:1231-1278) plus the
+ * einsum of tensor_correlation (:797-809) without materialising fd/cd.
+ *
+ *   fn  : [npairs,B,Prows,ldf] normalised backbone-feature panels; pair k
+ *         correlates slot 0 (first operand) with slot k (k = 0 is the intra pair).
+ *   cn  : [npairs,B,Prows,ldc] normalised code panels, same slot convention.
+ *   fmean : [npairs,B,ldf] panel row means (only read with DG_FLAG_POINTWISE).
+ *   dsign : [B,Prows] depth signs from dg_depth_sign, or NULL for no depth term.
+ *   pair_shift / pair_group : host [npairs].
+ *   out8  : device [8] = (intra loss, intra cd mean, inter loss, inter cd mean,
+ *           neg loss mean, neg cd mean, depth loss, depth dd mean).
+ *   dC1,dC2 : out [npairs+1,B,Prows,ldc] unit gradients of each pair's MEAN loss
+ *           w.r.t. its first / second normalised code operand (index npairs = depth).
+ *   cd_out, loss_out : optional dense [npairs,B,P,P] (NULL to skip) — the
+ *           reference's 5-D tensors, [b,h,w,i,j] flattened; dd_out optional [B,P,P].
+ *   ws : workspace of dg_corr_loss_workspace_bytes(). */
+DG_API size_t dg_corr_loss_workspace_bytes(int npairs, int B, int P);
+DG_API int dg_corr_loss(const float* fn, const float* cn, const float* fmean, const float* dsign, int npairs, int B, int P,
+                 int Prows, int C, int ldf, int D, int ldc, const float* pair_shift, const int32_t* pair_group,
+                 float depth_shift, int flags, float* out8, float* dC1, float* dC2, float* cd_out, float* loss_out,
+                 float* dd_out, void* ws, size_t ws_bytes, dg_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * Cosine-similarity k-nearest-neighbour build.  Replaces the einsum + topk
+ * loop of src/precompute_knns.py:99-113 for a block of query rows.
+ *
+ *   q  : [Nq,F] query rows, db : [N,F] database rows (both unit-norm fp32, row pitch F).
+ *   idx : out [Nq,k] int64, sorted by descending fp32 similarity (k <= 32).
+ *   sims: optional out [Nq,k] fp32 similarities. */
+DG_API size_t dg_knn_workspace_bytes(int Nq, int N, int F, int k);
+DG_API int dg_knn_topk(const float* q, const float* db, int Nq, int N, int F, int k, int64_t* idx, float* sims, void* ws,
+                size_t ws_bytes, dg_stream_t stream);
+
+/* Mean-pool + L2-normalise of get_feats (src/precompute_knns.py:19):
+ * t [N,C,H,W] with element strides (host) -> out [N,C], eps = 1e-12. */
+DG_API int dg_pool_normalize(const float* t, const int64_t* strides, int N, int C, int H, int W, float eps, float* out,
+                      dg_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEPTHG_B200_H_ */

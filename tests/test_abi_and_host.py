@@ -1,0 +1,130 @@
+"""CPU tests: the C-ABI library loads and exports every symbol the header
+declares, argument validation works without a GPU, the Python host layer refuses
+CPU tensors (no fallback), and the sharding helpers are right (gloo, world 2)."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "depthg_b200.h")).read()
+    return sorted(set(re.findall(r"DG_API\s+[\w\s\*]+?\b(dg_\w+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from depthg_b200 import _lib
+    names = header_symbols()
+    assert len(names) >= 13
+    assert sorted(_lib.SIGNATURES) == names, "ctypes table and header disagree"
+    lib = _lib.lib()
+    for n in names:
+        assert hasattr(lib, n), n
+    assert lib.dg_version() >= 100
+    assert lib.dg_panel_ld(90) == 96 and lib.dg_panel_ld(768) == 768 and lib.dg_panel_rows(121) == 128
+    assert lib.dg_corr_loss_workspace_bytes(7, 32, 121) > 0
+
+
+def test_header_compiles_as_plain_c(tmp_path):
+    src = tmp_path / "t.c"
+    src.write_text('#include "depthg_b200.h"\nint main(void){return DG_OK + (int)sizeof(dg_stream_t)*0;}\n')
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-c", str(src), "-o",
+                    str(tmp_path / "t.o")], check=True)
+
+
+def test_argument_validation_needs_no_gpu():
+    from depthg_b200 import _lib
+    lib = _lib.lib()
+    assert lib.dg_fps_coords(None, None, 1, 8, 8, 4, 4, 2, 1.0, 5.0, 0, None, None, None) == -1
+    assert b"null pointer" in lib.dg_last_error_string()
+    assert lib.dg_knn_topk(None, None, 4, 4, 4, 2, None, None, None, 0, None) == -1
+    with pytest.raises(ValueError):
+        _lib.check(-1, "x")
+    with pytest.raises(_lib.DepthgB200Error):
+        _lib.check(-4, "x")
+
+
+def test_host_layer_refuses_cpu_tensors_and_bad_modes():
+    """No CPU fallback by design (SURVEY.md 8b error conventions)."""
+    from depthg_b200 import modules as M
+    from depthg_b200.precompute_knns import knn_topk
+    from tests.golden import cases
+    cfg = cases.loss_cfg(feature_samples=3)
+    fn = M.ContrastiveCorrelationLoss(cfg)
+    assert len(fn.state_dict()) == 0
+    f = torch.zeros(2, 8, 28, 28)
+    d = torch.zeros(2, 1, 224, 224)
+    with pytest.raises(ValueError, match="CUDA"):
+        fn(f, f, None, None, f, f, d, d)
+    with pytest.raises(ValueError, match="CUDA"):
+        M.farthest_point_sampling_depth(f, d, 3)
+    with pytest.raises(ValueError, match="CUDA"):
+        knn_topk(torch.zeros(4, 8), torch.zeros(4, 8), 2)
+    with pytest.raises(TypeError):
+        M._lib.require_cuda_f32(np.zeros(3), "x")
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    from depthg_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libdepthg_b200.so")
+    with pytest.raises(_lib.DepthgB200Error, match="no CPU"):
+        _lib.lib()
+
+
+def test_shard_bounds_cover_everything():
+    from depthg_b200.distributed import shard_bounds
+    for n in (1, 7, 64, 49629):
+        for w in (1, 2, 3, 8):
+            spans = [shard_bounds(n, w, r) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+
+
+_WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r})
+import numpy as np, torch, torch.distributed as dist
+from depthg_b200.distributed import shard_bounds, shard_batch, allreduce_mean_, sharded_knn, allgather_rows
+from oracle import depthg_oracle as O
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+rs = np.random.RandomState(0)
+feats = torch.nn.functional.normalize(torch.from_numpy(rs.standard_normal((301, 32)).astype(np.float32)), dim=1)
+lo, hi = shard_bounds(301, world, rank)
+cpu_topk = lambda q, db, k: O.knn_rows(q, db, k)[1]
+full = sharded_knn(feats[lo:hi], 301, 5, cpu_topk, gather_result=True)
+assert torch.equal(full, O.knn_rows(feats, feats, 5)[1]), "sharded KNN != single-process KNN"
+even = allgather_rows(feats[rank * 100:(rank + 1) * 100], 200)
+assert torch.equal(even, feats[:200])
+g = [torch.full((3, 2), float(rank + 1)), None, torch.arange(4.0) * (rank + 1)]
+allreduce_mean_(g)
+assert torch.allclose(g[0], torch.full((3, 2), 1.5)) and torch.allclose(g[2], torch.arange(4.0) * 1.5)
+x = torch.arange(10).view(5, 2)
+(part,) = shard_batch([x], world, rank)
+assert part.shape[0] == (3 if rank == 0 else 2)
+dist.barrier(); dist.destroy_process_group()
+print("rank", rank, "ok")
+"""
+
+
+def test_distributed_sharding_world2_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER.format(root=ROOT))
+    port = 29500 + (os.getpid() % 2000)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
+                   OMP_NUM_THREADS="1")
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    for p in procs:
+        out, _ = p.communicate(timeout=180)
+        assert p.returncode == 0, out

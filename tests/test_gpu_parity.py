@@ -1,0 +1,277 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the committed
+golden vectors of the REAL reference and against the CPU oracle on seeded inputs.
+
+Tolerances (BASELINE.json north_star): FPS index sets and KNN indices bit-exact
+(KNN ties allowed only where fp32 similarities differ by < 1e-6); loss values and
+gradients within 1e-4 relative.  The scalar losses are means of +-O(0.1) terms that
+cancel to O(1e-3), so a 2e-7 absolute floor is allowed next to the relative bound.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import depthg_oracle as O
+from tests.golden import cases
+from tests.helpers import golden, rel_err, run_oracle_loss
+
+pytestmark = pytest.mark.gpu
+RTOL, ATOL = 1e-4, 2e-7
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+# ------------------------------------------------------------------ FPS (a5-a7)
+@pytest.mark.parametrize("pattern", list(cases.FPS_PATTERNS))
+@pytest.mark.parametrize("S", cases.FPS_S)
+def test_fps_index_sets_bit_exact_vs_reference_golden(pattern, S):
+    from depthg_b200.modules import farthest_point_sampling_depth, fps_index_sets
+    g = golden("fps_index_sets")
+    depth = cases.make_fps_depth(pattern).to(dev())
+    idx = fps_index_sets(depth, 28, 28, S).cpu().numpy()
+    assert np.array_equal(idx, g[f"{pattern}_S{S}"])
+    coords = farthest_point_sampling_depth(torch.zeros(depth.shape[0], 1, 28, 28, device=dev()), depth, S)
+    assert tuple(coords.shape) == (depth.shape[0], S, S, 2)
+    assert np.array_equal(coords.cpu().numpy(), g[f"{pattern}_S{S}_coords"])
+
+
+def test_fps_full_batch_matches_oracle_and_is_raster_sorted():
+    from depthg_b200.modules import fps_index_sets
+    rs = np.random.RandomState(5)
+    depth = torch.from_numpy(rs.randint(0, 256, (32, 1, 224, 224)).astype(np.float32))
+    idx = fps_index_sets(depth.to(dev()), 28, 28, 11).cpu().numpy()
+    assert idx.shape == (32, 121)
+    assert (np.diff(idx, axis=1) > 0).all() and idx.min() >= 0 and idx.max() < 784
+    want = O.fps_index_sets((1, 1, 28, 28), depth[:6], 11)
+    assert np.array_equal(idx[:6], want)
+
+
+def test_fps_non_divisible_pooling_and_other_grid():
+    """adaptive_avg_pool2d window rule when Hd/H is not an integer, and a 14x14 grid."""
+    from depthg_b200.modules import fps_index_sets
+    rs = np.random.RandomState(9)
+    depth = torch.from_numpy(rs.randint(0, 256, (2, 1, 100, 120)).astype(np.float32))
+    for (H, W, S) in ((28, 28, 6), (14, 14, 5), (40, 40, 7)):
+        if H > 100:
+            continue
+        got = fps_index_sets(depth.to(dev()), H, W, S).cpu().numpy()
+        want = O.fps_index_sets((1, 1, H, W), depth, S)
+        assert np.array_equal(got, want), (H, W, S)
+
+
+# ------------------------------------------------------------------ gather / norm / correlation (a1-a4)
+def _misc_inputs():
+    rs = np.random.RandomState(77)
+    t = torch.from_numpy(rs.standard_normal((2, 5, 28, 28)).astype(np.float32))
+    coords = torch.from_numpy((rs.random_sample((2, 4, 4, 2)) * 2.4 - 1.2).astype(np.float32))
+    return t, coords
+
+
+@pytest.mark.parametrize("channels_last", [False, True])
+def test_sample_and_norm_match_reference_golden(channels_last):
+    from depthg_b200.modules import norm, sample, sample_norm
+    g = golden("misc")
+    t, coords = _misc_inputs()
+    tc = t.to(dev())
+    if channels_last:
+        tc = tc.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+    got = sample(tc, coords.to(dev())).cpu().numpy()
+    np.testing.assert_allclose(got, g["sample_out"], rtol=1e-4, atol=2e-5)
+    want_n = O.norm(torch.from_numpy(g["sample_out"])).numpy()
+    np.testing.assert_allclose(sample_norm(tc, coords.to(dev())).cpu().numpy(), want_n, rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(norm(tc).cpu().numpy(), g["norm_out"], rtol=1e-4, atol=1e-5)
+
+
+def test_sample_wide_channels_vector_path():
+    """C multiple of 4, channels-last: exercises the 128-bit path; C=90: scalar path."""
+    from depthg_b200.modules import sample_norm
+    rs = np.random.RandomState(3)
+    for C in (768, 90):
+        t = torch.from_numpy(rs.standard_normal((3, C, 28, 28)).astype(np.float32))
+        coords = torch.from_numpy((rs.random_sample((3, 11, 11, 2)) * 2 - 1).astype(np.float32))
+        want = O.norm(O.sample(t, coords)).numpy()
+        for cl in (False, True):
+            tc = t.to(dev())
+            if cl:
+                tc = tc.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+            got = sample_norm(tc, coords.to(dev())).cpu().numpy()
+            assert rel_err(got, want) < 1e-5, (C, cl)
+
+
+def test_tensor_correlation_matches_reference_golden():
+    from depthg_b200.modules import tensor_correlation
+    rs = np.random.RandomState(21)
+    a = torch.from_numpy(rs.standard_normal((3, 70, 6, 6)).astype(np.float32))
+    b = torch.from_numpy(rs.standard_normal((3, 70, 6, 6)).astype(np.float32))
+    got = tensor_correlation(a.to(dev()), b.to(dev())).cpu()
+    want = O.tensor_correlation(a, b)
+    assert got.shape == want.shape
+    assert rel_err(got.numpy(), want.numpy()) < 1e-5
+
+
+def test_depth_sign_matches_reference_golden():
+    import ctypes
+    from depthg_b200 import _lib
+    g = golden("misc")
+    rs = np.random.RandomState(77)
+    rs.standard_normal((2, 5, 28, 28)); rs.random_sample((2, 4, 4, 2))
+    depth = torch.from_numpy(rs.randint(0, 256, (2, 1, 224, 224)).astype(np.float32))
+    depth[0, 0, :100] = 0
+    d = depth.to(dev())
+    out = torch.empty((2, 64), device=dev())
+    _lib.check(_lib.lib().dg_depth_sign(_lib.ptr(d), 2, 224, 224, 7, 1e-10, 64, _lib.ptr(out), _lib.stream_ptr()), "x")
+    np.testing.assert_allclose(out[:, :49].cpu().numpy().reshape(2, 7, 7), g["depth_sign7"][:, 0], atol=1e-6)
+    assert (out[:, 49:] == 0).all()
+
+
+# ------------------------------------------------------------------ the loss (a9-a11)
+def _check_loss(r, g, cfg):
+    assert np.array_equal(r["coords1"], g["coords1"]) and np.array_equal(r["coords2"], g["coords2"])
+    np.testing.assert_allclose(r["scalars"], g["scalars"], rtol=RTOL, atol=ATOL, equal_nan=True)
+    np.testing.assert_allclose(r["cd_means"], g["cd_means"], rtol=RTOL, atol=ATOL, equal_nan=True)
+    np.testing.assert_allclose(r["total"], g["total"], rtol=RTOL, atol=ATOL)
+    assert rel_err(r["d_code"], g["d_code"]) < RTOL
+    assert rel_err(r["d_code_pos"], g["d_code_pos"]) < RTOL
+
+
+@pytest.mark.parametrize("name", list(cases.LOSS_CASES))
+@pytest.mark.parametrize("channels_last", [False, True])
+def test_loss_and_grads_match_reference_golden(name, channels_last):
+    from tests.gpu_helpers import run_cuda_loss
+    g = golden("loss_" + name)
+    cfg, t, r = run_cuda_loss(name, channels_last=channels_last)
+    _check_loss(r, g, cfg)
+    assert r["grad_strides"][0] == r["grad_strides"][1]  # gradient comes back in the input's layout
+    for o in r["out"]:
+        assert o.dim() == 0  # fast mode: 0-dim means, nothing 5-D in HBM
+
+
+@pytest.mark.parametrize("name", ["small_fps", "small_random", "small_fps_nodepthterm", "small_fps_stabalize"])
+def test_materialized_5d_outputs_match_reference_golden(name):
+    from tests.gpu_helpers import run_cuda_loss
+    g = golden("loss_" + name)
+    cfg, t, r = run_cuda_loss(name, materialize=True)
+    _check_loss(r, g, cfg)
+    out = r["out"]
+    B, S = t["feats"].shape[0], cfg.feature_samples
+    assert tuple(out[1].shape) == (B, S, S, S, S) and tuple(out[4].shape) == (cfg.neg_samples * B, S, S, S, S)
+    np.testing.assert_allclose(out[1].detach().cpu().numpy(), g["intra_cd"], rtol=1e-4, atol=2e-6)
+    np.testing.assert_allclose(out[3].detach().cpu().numpy(), g["inter_cd"], rtol=1e-4, atol=2e-6)
+    np.testing.assert_allclose(out[4].detach().cpu().numpy(), g["neg_loss"], rtol=1e-4, atol=2e-6)
+    np.testing.assert_allclose(out[5].detach().cpu().numpy(), g["neg_cd"], rtol=1e-4, atol=2e-6)
+    if cfg.depth_feat_correlation_loss:
+        np.testing.assert_allclose(out[7].detach().cpu().numpy(), g["depth_dd"], rtol=1e-4, atol=2e-6)
+
+
+def test_cfg2_full_size_matches_oracle():
+    """cocostuff27 ViT-B/8 training shape (B=32, C=768, D=90, S=11) against the oracle run on the host."""
+    from tests.gpu_helpers import run_cuda_loss
+    cases.LOSS_CASES["_cfg2"] = (32, 768, 90, dict(feature_samples=11, pos_intra_shift=0.2103, pos_inter_shift=0.1233,
+                                                    neg_inter_shift=0.9748, depth_feat_shift=0.0359), 99)
+    try:
+        inputs = cases.make_loss_inputs("_cfg2")
+        cfg, t, r = run_cuda_loss("_cfg2", channels_last=True, inputs=inputs)
+        _, _, want = run_oracle_loss("_cfg2")
+    finally:
+        del cases.LOSS_CASES["_cfg2"]
+    _check_loss(r, want, cfg)
+
+
+def test_loss_rng_stream_follows_reference_call_order():
+    """Without hooks the module draws rand, rand, randperm x N on the device, like the reference."""
+    from depthg_b200.modules import ContrastiveCorrelationLoss, super_perm
+    cfg = cases.loss_cfg(feature_samples=5, depth_sampling="none", neg_samples=3)
+    B = 4
+    g = torch.Generator().manual_seed(0)
+    f, fp = torch.randn(B, 32, 28, 28, generator=g).to(dev()), torch.randn(B, 32, 28, 28, generator=g).to(dev())
+    c, cp = torch.randn(B, 16, 28, 28, generator=g).to(dev()), torch.randn(B, 16, 28, 28, generator=g).to(dev())
+    d = torch.randint(0, 256, (B, 1, 224, 224), generator=g).float().to(dev())
+    fn = ContrastiveCorrelationLoss(cfg)
+    torch.manual_seed(123)
+    out = fn(f, fp, None, None, c, cp, d, d)
+    torch.manual_seed(123)
+    c1 = torch.rand([B, 5, 5, 2], device=dev()) * 2 - 1
+    c2 = torch.rand([B, 5, 5, 2], device=dev()) * 2 - 1
+    perms = [super_perm(B, dev()) for _ in range(3)]
+    assert torch.equal(fn.last_coords[0], c1) and torch.equal(fn.last_coords[1], c2)
+    # replay on the oracle with the same draws
+    ofn = O.ContrastiveCorrelationLoss(cfg)
+    pit, rit = iter([p.cpu() for p in perms]), iter([((c1 + 1) / 2).cpu(), ((c2 + 1) / 2).cpu()])
+    ofn.perm_fn = lambda n, device: next(pit)
+    ofn.rand_fn = lambda shape, device: next(rit)
+    want = ofn(f.cpu(), fp.cpu(), None, None, c.cpu(), cp.cpu(), d.cpu(), d.cpu())
+    for i in (0, 2, 6):
+        np.testing.assert_allclose(out[i].item(), want[i].item(), rtol=1e-3, atol=1e-6)
+    np.testing.assert_allclose(out[4].item(), want[4].mean().item(), rtol=1e-3, atol=1e-6)
+
+
+def test_module_has_no_state_and_rereads_cfg():
+    from depthg_b200.modules import ContrastiveCorrelationLoss
+    cfg = cases.loss_cfg(feature_samples=4)
+    fn = ContrastiveCorrelationLoss(cfg)
+    assert len(fn.state_dict()) == 0 and len(list(fn.parameters())) == 0
+    _, t = cases.make_loss_inputs("small_fps")
+    a = [t[k].to(dev()) for k in ("feats", "feats_pos", "code", "code_pos", "depth", "depth_pos")]
+    fn(a[0], a[1], None, None, a[2], a[3], depth=a[4], depth_pos=a[5])
+    assert fn.last_coords.shape[2] == 4
+    cfg.feature_samples = 6          # the trainer mutates cfg between steps (train_segmentation.py:356-375)
+    cfg.depth_sampling = "none"
+    fn(a[0], a[1], None, None, a[2], a[3], depth=a[4], depth_pos=a[5])
+    assert fn.last_coords.shape[2] == 6
+
+
+# ------------------------------------------------------------------ KNN (a12-a14)
+def _check_knn(idx, feats, want_idx, k):
+    sims = feats @ feats.T
+    got_v = torch.gather(sims, 1, torch.from_numpy(idx)).numpy()
+    want_v = torch.gather(sims, 1, torch.from_numpy(want_idx)).numpy()
+    mism = idx != want_idx
+    # ties: positions may differ only where the fp32 similarities differ by < 1e-6
+    assert np.all(np.abs(got_v - want_v)[mism] < 1e-6), f"{mism.sum()} slots differ beyond the tie rule"
+    assert (np.diff(got_v, axis=1) <= 1e-6).all()
+    for r in np.nonzero(mism.any(1))[0][:50]:
+        assert len(set(idx[r].tolist())) == k
+    return int(mism.sum())
+
+
+@pytest.mark.parametrize("name", list(cases.KNN_CASES))
+def test_knn_indices_match_reference_golden(name):
+    from depthg_b200.precompute_knns import build_knn_index, knn_topk
+    g = golden("knn")
+    feats, k, n_batches = cases.make_knn_feats(name)
+    idx = build_knn_index(feats.to(dev()), k, n_batches)
+    assert idx.dtype == torch.int64 and tuple(idx.shape) == g[name].shape
+    nm = _check_knn(idx.cpu().numpy(), feats, g[name], k)
+    assert nm <= 0.001 * idx.numel()
+    # query-row shard against the full database == the same rows of the full build
+    lo, hi = 130, 517
+    part, sims = knn_topk(feats[lo:hi].to(dev()), feats.to(dev()), k, return_sims=True)
+    assert torch.equal(part, idx[lo:hi])
+    np.testing.assert_allclose(sims.cpu().numpy(), g[name + "_vals"][lo:hi], atol=2e-6)
+
+
+def test_knn_larger_unaligned_problem_vs_oracle():
+    from depthg_b200.precompute_knns import knn_topk
+    rs = np.random.RandomState(31)
+    x = torch.nn.functional.normalize(torch.from_numpy(rs.standard_normal((5003, 768)).astype(np.float32)), dim=1)
+    idx = knn_topk(x[:777].to(dev()), x.to(dev()), 30).cpu().numpy()
+    _, want = O.knn_rows(x[:777], x, 30)
+    sims = x[:777] @ x.T
+    gv = torch.gather(sims, 1, torch.from_numpy(idx)).numpy()
+    wv = torch.gather(sims, 1, want).numpy()
+    mism = idx != want.numpy()
+    assert np.all(np.abs(gv - wv)[mism] < 1e-6)
+    assert (idx[:, 0] == np.arange(777)).all()  # every image is its own nearest neighbour
+
+
+def test_pool_normalize_matches_get_feats():
+    from depthg_b200.precompute_knns import pool_normalize
+    rs = np.random.RandomState(8)
+    fm = torch.from_numpy(rs.standard_normal((5, 96, 7, 7)).astype(np.float32))
+    want = O.pooled_normed_feats(fm).numpy()
+    for cl in (False, True):
+        x = fm.to(dev())
+        if cl:
+            x = x.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+        assert rel_err(pool_normalize(x).cpu().numpy(), want) < 1e-6

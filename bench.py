@@ -1,0 +1,459 @@
+#!/usr/bin/env python
+"""Benchmark of the DepthG hot path on B200 (see the contract in DESIGN.md section "Measurement").
+
+    python bench.py --gpus N --steps K --warmup W            # our sm_100a path
+    python bench.py --impl reference --gpus N --steps K ...   # the reference algorithm on the host CPU
+
+One "step" = ContrastiveCorrelationLoss forward + backward (depth-guided FPS, bilinear
+gathers, fused correlation loss, scatter backward) on one batch of the cocostuff27
+ViT-B/8 training shape (BASELINE.json configs[1]): B=32 per GPU, C=768, 28x28, dim=90,
+feature_samples=11, fps sampling, pointwise, depth term on.  Prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "corr_loss_fwd_bwd_samples_per_s"
+UNIT = "samples/s"
+# cocostuff27 ViT-B/8 (paper_reproduction.sh:8): shifts and loss weights of the paper run
+CFG2 = dict(B=32, C=768, D=90, H=28, W=28, Hd=224, Wd=224, S=11, neg_samples=5,
+            pos_intra_shift=0.2103, pos_inter_shift=0.1233, neg_inter_shift=0.9748, depth_feat_shift=0.0359)
+WEIGHTS = dict(pos_inter=1.0501, pos_intra=0.2305, neg_inter=0.2485, depth_feat=0.1603)
+HEAD_GRAD_FLOATS = 729_012   # trainable 1x1-conv head of ViT-B / dim 90: the DDP all-reduce payload
+KNN = dict(N=49_629, F=768, k=30)
+
+
+def make_cfg(S=CFG2["S"]):
+    from types import SimpleNamespace
+    return SimpleNamespace(feature_samples=S, use_salience=False, depth_sampling="fps", fps_gpu=False, pointwise=True,
+                           zero_clamp=True, stabalize=False, neg_samples=CFG2["neg_samples"],
+                           pos_intra_shift=CFG2["pos_intra_shift"], pos_inter_shift=CFG2["pos_inter_shift"],
+                           neg_inter_shift=CFG2["neg_inter_shift"], depth_feat_correlation_loss=True,
+                           depth_feat_shift=CFG2["depth_feat_shift"])
+
+
+def algorithmic_bytes(B, C=CFG2["C"], D=CFG2["D"], HW=784, Hd=224, Wd=224):
+    """inputs read once, code gradients written once, no 5-D tensors."""
+    return 4 * (2 * B * C * HW + 2 * B * D * HW + 2 * B * D * HW + 2 * B * Hd * Wd)
+
+
+def algorithmic_flops(B, S=CFG2["S"], C=CFG2["C"], D=CFG2["D"], N=CFG2["neg_samples"]):
+    P = S * S
+    return (N + 2) * B * P * P * 2 * (C + 3 * D)
+
+
+def weighted(out):
+    return (WEIGHTS["pos_intra"] * out[0] + WEIGHTS["pos_inter"] * out[2] + WEIGHTS["neg_inter"] * out[4].mean()
+            + WEIGHTS["depth_feat"] * out[6])
+
+
+def synth_inputs(B, gen, device, channels_last=True):
+    """Synthetic batch of the cfg2 shape.  Features arrive channels-last on the live path
+    (permuted [B,HW,C] views, SURVEY.md 7 hard part 6); depth is integer-valued like the uint8 PNGs."""
+    c = CFG2
+
+    def feat(ch):
+        x = torch.randn((B, c["H"], c["W"], ch), generator=gen, device=device)
+        return x.permute(0, 3, 1, 2) if channels_last else x.permute(0, 3, 1, 2).contiguous()
+
+    depth = lambda: torch.randint(0, 256, (B, 1, c["Hd"], c["Wd"]), generator=gen, device=device).float()  # noqa: E731
+    return dict(feats=feat(c["C"]), feats_pos=feat(c["C"]), code=feat(c["D"]), code_pos=feat(c["D"]), depth=depth(),
+                depth_pos=depth())
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz, self._stop = [], set(), None, threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # noqa: BLE001
+            self.nv, self.err = None, repr(e)
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    _NAMES = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+              0x80: "hw_power_brake", 0x2: "applications_clocks", 0x10: "sync_boost", 0x100: "display_clocks"}
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:  # noqa: BLE001
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self._NAMES.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(0.005)
+
+    def __enter__(self):
+        if self.nv:
+            self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self.nv:
+            self.t.join()
+
+    def summary(self):
+        if not self.nv or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml_unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return d["hbm_gbs"], d.get("bf16_tflops", 1590.0), d.get("bf16_tflops_sustained", 1400.0), "measured"
+    return 6650.0, 1590.0, 1400.0, "fallback"
+
+
+# ----------------------------------------------------------------------------- reference arm (CPU)
+def run_reference(args):
+    """The reference algorithm (oracle port: torch-CPU fp32 + NumPy FPS, the reference's own
+    libraries) on the host cores.  /root/reference is not on the GPU box, so the committed
+    restatement (pinned bit-for-bit to the real reference, tests/test_oracle.py) is what runs."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import depthg_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = make_cfg()
+    gen = torch.Generator().manual_seed(0)
+
+    def one_step(inp):
+        code = inp["code"].detach().requires_grad_(True)
+        code_pos = inp["code_pos"].detach().requires_grad_(True)
+        out = O.ContrastiveCorrelationLoss(cfg)(inp["feats"], inp["feats_pos"], None, None, code, code_pos,
+                                                inp["depth"], inp["depth_pos"])
+        weighted(out).backward()
+        return out[0].item()
+
+    B = CFG2["B"]
+    inp = synth_inputs(B, gen, "cpu")
+    t0 = time.perf_counter()
+    one_step(inp)
+    first = time.perf_counter() - t0
+    budget = 150.0
+    while B > 2 and first * (B / CFG2["B"]) * (args.steps + args.warmup) > budget:
+        B //= 2
+    if B != CFG2["B"]:
+        inp = synth_inputs(B, gen, "cpu")
+    for _ in range(args.warmup):
+        one_step(inp)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        one_step(inp)
+    dt = time.perf_counter() - t0
+    value = B * args.steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(B, args.gpus, extra={"device": "cpu"}),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{args.steps} steps of {B} samples of the cfg2 shape (fwd+bwd incl. NumPy FPS)"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(B, n_gpus, extra=None):
+    c = {"workload": "cocostuff27 ViT-B/8 ContrastiveCorrelationLoss fwd+bwd (BASELINE configs[1])",
+         "per_gpu_batch": B, "global_batch": B * n_gpus, "C": CFG2["C"], "dim": CFG2["D"], "grid": "28x28",
+         "feature_samples": CFG2["S"], "neg_samples": CFG2["neg_samples"], "depth_sampling": "fps", "pointwise": True,
+         "depth_term": True, "layout": "channels_last (live trainer layout)", "parallelism": f"dp{n_gpus}"}
+    if extra:
+        c.update(extra)
+    return c
+
+
+# ----------------------------------------------------------------------------- our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-knn", action="store_true", help="skip the KNN-build side measurement")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--nchw", action="store_true", help="NCHW-contiguous inputs instead of channels-last")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch.distributed as dist
+    from depthg_b200 import _lib
+    from depthg_b200.modules import ContrastiveCorrelationLoss
+    from depthg_b200.precompute_knns import knn_topk
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    lib = _lib.lib()
+    hbm_peak, tf_burst, tf_sust, peak_src = peaks()
+
+    B = CFG2["B"]
+    cfg = make_cfg()
+    loss_fn = ContrastiveCorrelationLoss(cfg)
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    # rotate over input sets totalling > L2 (126 MB) so no step finds its inputs cached
+    NSETS = 3
+    sets = [synth_inputs(B, gen, dev, channels_last=not args.nchw) for _ in range(NSETS)]
+    for s in sets:
+        s["code"].requires_grad_(True)
+        s["code_pos"].requires_grad_(True)
+    head_grad = torch.zeros(HEAD_GRAD_FLOATS, device=dev) if world > 1 else None
+
+    def step(i):
+        s = sets[i % NSETS]
+        s["code"].grad = None
+        s["code_pos"].grad = None
+        out = loss_fn(s["feats"], s["feats_pos"], None, None, s["code"], s["code_pos"], s["depth"], s["depth_pos"])
+        weighted(out).backward()
+        if world > 1:   # DDP semantics: the only exchange is the head-gradient all-reduce
+            dist.all_reduce(head_grad)
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    l0 = lib.dg_kernel_launches()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        ev0.record()
+        for i in range(args.steps):
+            step(i)
+        ev1.record()
+        barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = lib.dg_kernel_launches() - l0
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = world * B * args.steps / (ms / 1e3)
+
+    # ---- per-ABI-call breakdown (same inputs, CUDA events on the launching stream around each C-ABI call)
+    breakdown = {}
+    pending = []
+    # wrap each library function so events bracket it
+    wrapped = {}
+    for name in ("dg_fps_coords", "dg_gather_norm", "dg_depth_sign", "dg_corr_loss", "dg_gather_norm_bwd"):
+        fn = getattr(lib, name)
+
+        def make(fn=fn, name=name):
+            def call(*a):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                rc = fn(*a)
+                e1.record()
+                pending.append((name, e0, e1))
+                return rc
+            return call
+        wrapped[name] = make()
+
+    class LibProxy:
+        def __getattr__(self, n):
+            return wrapped.get(n) or getattr(lib, n)
+
+    real_lib_fn = _lib.lib
+    _lib.lib = lambda: LibProxy()
+    try:
+        reps = min(args.steps, 20)
+        for i in range(reps):
+            step(i)
+        torch.cuda.synchronize()
+    finally:
+        _lib.lib = real_lib_fn
+    for name, e0, e1 in pending:
+        breakdown[name] = breakdown.get(name, 0.0) + e0.elapsed_time(e1) * 1e3 / reps
+    calls = {n: sum(1 for p in pending if p[0] == n) // reps for n in breakdown}
+
+    # dominant call and its roofline (algorithmic bytes it is responsible for; DESIGN.md "Roofline accounting")
+    HW = CFG2["H"] * CFG2["W"]
+    P, Prows = CFG2["S"] ** 2, 128
+    npairs = 2 + CFG2["neg_samples"]
+    alg = {
+        "dg_fps_coords": 4 * 2 * B * CFG2["Hd"] * CFG2["Wd"],
+        "dg_gather_norm": 4 * (2 * B * CFG2["C"] * HW + 2 * B * CFG2["D"] * HW),          # sources read once
+        "dg_corr_loss": 4 * npairs * B * Prows * (CFG2["C"] + 2 * 96 + 2 * 96),                 # panels in, unit grads out
+        "dg_gather_norm_bwd": 4 * 2 * B * CFG2["D"] * HW,                                     # code grads written once
+        "dg_depth_sign": 4 * B * P * 4,
+    }
+    dom = max(breakdown, key=breakdown.get)
+    dom_us = breakdown[dom]
+    achieved = alg[dom] / (dom_us * 1e-6) / 1e9
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "us_per_step": dom_us, "calls_per_step": calls.get(dom)}
+    step_bytes = algorithmic_bytes(B)
+    roofline_step = {"bound": "hbm", "algorithmic_bytes": step_bytes, "achieved": step_bytes / (ms_per_step * 1e-3) / 1e9,
+                     "peak": hbm_peak, "unit": "GB/s", "frac": step_bytes / (ms_per_step * 1e-3) / 1e9 / hbm_peak,
+                     "tensor_flops": algorithmic_flops(B),
+                     "tensor_frac_bf16_sustained": algorithmic_flops(B) / (ms_per_step * 1e-3) / 1e12 / tf_sust}
+
+    # ---- end-to-end through the public API with HOST buffers (pinned), H2D + D2H inside the timed region
+    feat_keys = ("feats", "feats_pos", "code", "code_pos")
+
+    def to_host(k, v):
+        v = v.detach()
+        if k in feat_keys and not args.nchw:
+            v = v.permute(0, 2, 3, 1)          # the NHWC-contiguous base of the channels-last view
+        return v.contiguous().cpu().pin_memory()
+
+    host = {k: to_host(k, v) for k, v in sets[0].items()}
+    h2d = sum(v.numel() * 4 for v in host.values())
+    res_host = torch.empty(4, dtype=torch.float32).pin_memory()
+    gh = [torch.empty_like(host["code"]).pin_memory(), torch.empty_like(host["code_pos"]).pin_memory()]
+    d2h = res_host.numel() * 4 + sum(g.numel() * 4 for g in gh)
+
+    def e2e_step():
+        d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        if not args.nchw:
+            for k in feat_keys:
+                d[k] = d[k].permute(0, 3, 1, 2)
+        code = d["code"].requires_grad_(True)
+        code_pos = d["code_pos"].requires_grad_(True)
+        out = loss_fn(d["feats"], d["feats_pos"], None, None, code, code_pos, d["depth"], d["depth_pos"])
+        weighted(out).backward()
+        res_host.copy_(torch.stack([out[0], out[2], out[4], out[6]]).detach(), non_blocking=True)
+        g0, g1 = code.grad, code_pos.grad
+        if not args.nchw:
+            g0, g1 = g0.permute(0, 2, 3, 1), g1.permute(0, 2, 3, 1)
+        gh[0].copy_(g0, non_blocking=True)
+        gh[1].copy_(g1, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    e2e_steps = max(3, min(args.steps, 20))
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    ev0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    ev1.record()
+    barrier()
+    e2e_ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e = {"value": world * B * e2e_steps / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps,
+           "note": "pinned host buffers -> H2D -> FPS/gather/loss/backward -> D2H of 4 losses + both code gradients"}
+
+    # ---- KNN build side metric (query-row sharded; all-gather of the database when N > 1)
+    knn = None
+    if not args.no_knn:
+        from depthg_b200.distributed import allgather_rows, shard_bounds
+        N, F, k = KNN["N"], KNN["F"], KNN["k"]
+        g2 = torch.Generator(device=dev).manual_seed(7)
+        allf = torch.nn.functional.normalize(torch.randn((N, F), generator=g2, device=dev), dim=1)
+        lo, hi = shard_bounds(N, world, rank)
+        local = allf[lo:hi].contiguous()
+        del allf
+
+        def knn_step():
+            db = allgather_rows(local, N) if world > 1 else local
+            return knn_topk(local, db, k)
+
+        knn_step()
+        barrier()
+        ev0.record()
+        reps_k = 2
+        for _ in range(reps_k):
+            knn_step()
+        ev1.record()
+        barrier()
+        kms = ev0.elapsed_time(ev1) / reps_k
+        if world > 1:
+            t = torch.tensor([kms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            kms = float(t.item())
+        flops = 2.0 * N * N * F
+        knn = {"metric": "knn_build_img_per_s", "value": N / (kms / 1e3), "unit": "img/s", "ms": kms, "N": N, "F": F,
+               "k": k, "scaling": "strong", "sharding": "query rows; all-gather of the feature database",
+               "roofline": {"bound": "tensor", "achieved": flops / (kms / 1e3) / 1e12, "peak": tf_burst,
+                            "unit": "TFLOP/s", "frac": flops / (kms / 1e3) / 1e12 / tf_burst,
+                            "note": "fp32 CUDA-core similarity in this round; peak is the bf16 tensor burst figure"}}
+
+    # ---- CPU baseline (oracle port) on this box's host cores, rank 0 at N=1 only
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import depthg_oracle as O
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        cin = {k: v.detach().cpu().contiguous() for k, v in sets[0].items()}
+        times = []
+        for _ in range(3):
+            code = cin["code"].clone().requires_grad_(True)
+            code_pos = cin["code_pos"].clone().requires_grad_(True)
+            t0 = time.perf_counter()
+            out = O.ContrastiveCorrelationLoss(cfg)(cin["feats"], cin["feats_pos"], None, None, code, code_pos,
+                                                    cin["depth"], cin["depth_pos"])
+            weighted(out).backward()
+            times.append(time.perf_counter() - t0)
+            if sum(times) > 25:
+                break
+        cpu_baseline = {"value": B / min(times), "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": f"{len(times)} full steps of the same cfg2 batch (32 samples), best time; "
+                                  f"torch-CPU fp32 + NumPy FPS as the reference runs it",
+                        "ms_per_step": min(times) * 1e3}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": workload_config(B, world, extra={
+                    "l2_policy": f"rotating {NSETS} input sets ({NSETS * step_bytes / 1e6:.0f} MB) > 126 MB L2",
+                    "allreduce_floats_per_step": HEAD_GRAD_FLOATS if world > 1 else 0,
+                    "layout": "nchw" if args.nchw else "channels_last (live trainer layout)"}),
+                "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches),
+                "launches_per_step": launches / args.steps, "roofline": roofline, "roofline_step": roofline_step,
+                "breakdown_us": {k: round(v, 2) for k, v in breakdown.items()}, "cpu_baseline": cpu_baseline,
+                "knn": knn}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

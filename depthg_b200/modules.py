@@ -64,11 +64,19 @@ def fps_index_sets(depth: torch.Tensor, H: int, W: int, n_samples: int) -> torch
 
 
 def super_perm(size: int, device) -> torch.Tensor:
-    """src/modules.py:1184-1188, kept as the same torch calls so a shared seed gives
-    the reference's RNG stream."""
+    """src/modules.py:1184-1188: randperm with fixed points bumped by one, mod size.
+    ``randperm`` is the same torch call (same RNG stream for a shared seed); the bump is
+    written as an add of the fixed-point mask instead of the reference's boolean-mask
+    ``perm[perm == arange] += 1`` — identical values, but no nonzero() and therefore no
+    device->host sync."""
     perm = torch.randperm(size, device=device, dtype=torch.long)
-    perm[perm == torch.arange(size, device=device)] += 1
-    return perm % size
+    return (perm + (perm == torch.arange(size, device=device))) % size
+
+
+def super_perms(n: int, size: int, device) -> torch.Tensor:
+    """``n`` successive super_perm draws as one [n,size] tensor (one fix-up for all)."""
+    perm = torch.stack([torch.randperm(size, device=device, dtype=torch.long) for _ in range(n)])
+    return (perm + (perm == torch.arange(size, device=device))) % size
 
 
 def _strides(t: torch.Tensor):
@@ -331,7 +339,12 @@ class ContrastiveCorrelationLoss(nn.Module):
             c2 = self.rand_fn(shape, dev) * 2 - 1
             coords = torch.stack([c1, c2]).float().contiguous()
         self.last_coords = coords
-        perms = torch.stack([self.perm_fn(B, dev) for _ in range(nneg)]) if nneg else None
+        if not nneg:
+            perms = None
+        elif self.perm_fn is super_perm:
+            perms = super_perms(nneg, B, dev)
+        else:
+            perms = torch.stack([self.perm_fn(B, dev) for _ in range(nneg)])
 
         depth_term = bool(cfg.depth_feat_correlation_loss)
         if depth_term:

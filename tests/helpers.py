@@ -22,9 +22,11 @@ def weighted_total(out, depth_term):
     return L
 
 
-def run_oracle_loss(name):
+def run_oracle_loss(name, dtype=torch.float32):
     """Oracle forward+backward on a golden case with the case's perms / random coords injected."""
     cfg, t = cases.make_loss_inputs(name)
+    if dtype != torch.float32:  # higher-precision evaluation of the same algorithm (noise-floor checks)
+        t = {k: (v.to(dtype) if v.is_floating_point() and k not in ("rand1", "rand2") else v) for k, v in t.items()}
     code = t["code"].clone().requires_grad_(True)
     code_pos = t["code_pos"].clone().requires_grad_(True)
     fn = O.ContrastiveCorrelationLoss(cfg)

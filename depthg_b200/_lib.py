@@ -35,18 +35,32 @@ SIGNATURES = {
                                 C.c_int, _vp, _vp, _vp]),
     "dg_depth_sign": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, _vp, _vp]),
     "dg_gather_norm": (C.c_int, [_vp, _c_i64p, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_int, C.c_int, _c_i32p,
-                                 _c_i32p, _vp, C.c_float, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
+                                 _c_i32p, _vp, C.c_float, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "dg_gather_norm_bwd": (C.c_int, [_vp, _c_i64p, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_int, C.c_int, _c_i32p,
-                                     _c_i32p, _vp, C.c_float, C.c_int, C.c_int, _vp, _vp, _vp, _vp, C.c_int, _c_i32p,
-                                     _c_f32p, C.c_int, _vp, _vp]),
+                                     _c_i32p, _vp, C.c_float, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, C.c_int,
+                                     _c_i32p, _c_f32p, C.c_int, _vp, _vp]),
     "dg_corr_loss_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
-    "dg_corr_loss": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
-                               C.c_int, _c_f32p, _c_i32p, C.c_float, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+    "dg_corr_loss": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                               C.c_int, _c_f32p, _c_i32p, C.c_float, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                C.c_size_t, _vp]),
     "dg_knn_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "dg_knn_topk": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, C.c_size_t, _vp]),
     "dg_pool_normalize": (C.c_int, [_vp, _c_i64p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _vp, _vp]),
 }
+
+PANEL_F32, PANEL_FEATS_SPLIT, PANEL_CODE_SPLIT = 0, 1, 2
+
+
+class Panels(C.Structure):
+    """dg_panels_t of include/depthg_b200.h."""
+    _fields_ = [("format", C.c_int), ("f_hi", _vp), ("f_lo", _vp), ("c_hi", _vp), ("c_lo", _vp), ("ct_hi", _vp),
+                ("ct_lo", _vp)]
+
+
+def make_panels(fmt, f_hi, f_lo, c_hi, c_lo, ct_hi, ct_lo):
+    dp = lambda t: None if t is None else t.data_ptr()  # noqa: E731
+    return Panels(fmt, dp(f_hi), dp(f_lo), dp(c_hi), dp(c_lo), dp(ct_hi), dp(ct_lo))
+
 
 _lib = None
 

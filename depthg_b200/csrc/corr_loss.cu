@@ -329,19 +329,26 @@ __global__ void __launch_bounds__(CORR_THREADS) corr_tile_kernel(const __grid_co
   }
 }
 
+struct FinalizeParams {
+  int npairs, B, P, has_depth, n_pt;
+  int32_t group[DG_MAX_PAIRS];
+};
+
 // One block: fold the per-CTA partial sums into the 8 scalars of the output tuple.
-__global__ void __launch_bounds__(256) corr_finalize_kernel(const __grid_constant__ CorrParams prm, int n_pt) {
+__global__ void __launch_bounds__(256) corr_finalize_kernel(const float* __restrict__ partials,
+                                                            const int* __restrict__ err, float* __restrict__ out8,
+                                                            const __grid_constant__ FinalizeParams prm) {
   __shared__ float red[8][8];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   float acc[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-  const int per_pair = prm.B * n_pt;
+  const int per_pair = prm.B * prm.n_pt;
   const int total = prm.npairs * per_pair;
   for (int e = tid; e < total; e += 256) {
     const int k = e / per_pair;
     const int g = prm.group[k];
-    const float* s = prm.partials + (size_t)e * 4;
+    const float* s = partials + (size_t)e * 4;
     const float l = s[0], c = s[1];
     if (g == DG_GROUP_INTRA) { acc[0] += l; acc[1] += c; }
     else if (g == DG_GROUP_INTER) { acc[2] += l; acc[3] += c; }
@@ -362,9 +369,26 @@ __global__ void __launch_bounds__(256) corr_finalize_kernel(const __grid_constan
     const float elems = (float)prm.B * (float)prm.P * (float)prm.P;
     const int g = tid >> 1;
     const float n = (g < 3) ? (float)cnt[g] : (prm.has_depth ? 1.f : 0.f);
-    prm.out8[tid] = n > 0.f ? t / (n * elems) : 0.f;
+    float r = n > 0.f ? t / (n * elems) : 0.f;
+    if (err && *err != 0) r = __int_as_float(0x7fc00000);  // a pipeline wait timed out: poison the result
+    out8[tid] = r;
   }
 }
+
+int launch_corr_finalize(const float* partials, int npairs, int B, int P, const int32_t* group, int has_depth,
+                         const int* err, float* out8, int n_pt, cudaStream_t st) {
+  FinalizeParams fp;
+  fp.npairs = npairs; fp.B = B; fp.P = P; fp.has_depth = has_depth; fp.n_pt = n_pt;
+  for (int k = 0; k < npairs; ++k) fp.group[k] = group[k];
+  corr_finalize_kernel<<<1, 256, 0, st>>>(partials, err, out8, fp);
+  DG_LAUNCH_OK("corr_finalize_kernel");
+  return DG_OK;
+}
+
+int corr_loss_umma(const dg_panels_t* pan, const float* fmean, const float* dsign, int npairs, int B, int P, int ldf,
+                   int ldc, const float* pair_shift, const int32_t* pair_group, float depth_shift, int flags,
+                   float* out8, float* dC1, float* dC2, float* cd_out, float* loss_out, float* dd_out, float* fd_dbg,
+                   void* ws, cudaStream_t st);
 
 }  // namespace dg
 
@@ -373,27 +397,42 @@ extern "C" size_t dg_corr_loss_workspace_bytes(int npairs, int B, int P) {
   const size_t Prows = (size_t)dg::round_up(P, 64);
   const size_t n_pt = Prows / dg::TM;
   size_t floats = (size_t)npairs * B * Prows + (size_t)npairs * B + (size_t)npairs * B * n_pt * 4;
-  return (floats * sizeof(float) + 255) / 256 * 256;
+  size_t bytes = floats * sizeof(float) + 1024;  // covers the tcgen05 path too (512 B header + partials)
+  return (bytes + 255) / 256 * 256;
 }
 
-extern "C" int dg_corr_loss(const float* fn, const float* cn, const float* fmean, const float* dsign, int npairs, int B,
-                            int P, int Prows, int C, int ldf, int D, int ldc, const float* pair_shift,
+extern "C" int dg_corr_loss(const dg_panels_t* pan, const float* fmean, const float* dsign, int npairs, int B, int P,
+                            int Prows, int C, int ldf, int D, int ldc, const float* pair_shift,
                             const int32_t* pair_group, float depth_shift, int flags, float* out8, float* dC1,
-                            float* dC2, float* cd_out, float* loss_out, float* dd_out, void* ws, size_t ws_bytes,
-                            dg_stream_t stream) {
+                            float* dC2, float* cd_out, float* loss_out, float* dd_out, float* fd_dbg, void* ws,
+                            size_t ws_bytes, dg_stream_t stream) {
   using namespace dg;
-  DG_REQUIRE(fn && cn && pair_shift && pair_group && out8 && dC1 && dC2 && ws, DG_ERR_INVALID,
+  DG_REQUIRE(pan && pan->f_hi && pan->c_hi && pair_shift && pair_group && out8 && dC1 && dC2 && ws, DG_ERR_INVALID,
              "dg_corr_loss: null pointer");
   DG_REQUIRE(npairs > 0 && npairs <= DG_MAX_PAIRS, DG_ERR_INVALID, "dg_corr_loss: npairs=%d out of range", npairs);
   DG_REQUIRE(B > 0 && P > 0 && C > 0 && D > 0, DG_ERR_INVALID, "dg_corr_loss: bad sizes");
-  DG_REQUIRE(Prows == round_up(P, 64), DG_ERR_INVALID, "dg_corr_loss: Prows must be dg_panel_rows(P)");
   DG_REQUIRE(ldf >= C && ldf % 32 == 0 && ldc >= D && ldc % 32 == 0, DG_ERR_INVALID, "dg_corr_loss: bad panel pitch");
   DG_REQUIRE(ldc <= 128, DG_ERR_UNSUPPORTED, "dg_corr_loss: code dim %d > 128 not supported", D);
   DG_REQUIRE(!(flags & DG_FLAG_POINTWISE) || fmean, DG_ERR_INVALID, "dg_corr_loss: pointwise needs fmean");
   DG_REQUIRE(ws_bytes >= dg_corr_loss_workspace_bytes(npairs, B, P), DG_ERR_WORKSPACE,
              "dg_corr_loss: workspace too small");
   DG_REQUIRE(pair_group[0] == DG_GROUP_INTRA, DG_ERR_INVALID, "dg_corr_loss: pair 0 must be the intra pair");
+  for (int k = 0; k < npairs; ++k)
+    DG_REQUIRE(pair_group[k] >= 0 && pair_group[k] <= DG_GROUP_NEG, DG_ERR_INVALID, "dg_corr_loss: bad pair group");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+
+  if (pan->format == DG_PANEL_FEATS_SPLIT || pan->format == DG_PANEL_CODE_SPLIT) {
+    DG_REQUIRE(Prows == 128 && P <= 128, DG_ERR_UNSUPPORTED,
+               "dg_corr_loss: the tcgen05 path needs S*S <= 128 and 128-row panels (got P=%d, Prows=%d)", P, Prows);
+    DG_REQUIRE(pan->f_lo && pan->c_lo && pan->ct_hi && pan->ct_lo, DG_ERR_INVALID,
+               "dg_corr_loss: split panel format needs f_lo, c_lo, ct_hi, ct_lo");
+    return corr_loss_umma(pan, fmean, dsign, npairs, B, P, ldf, ldc, pair_shift, pair_group, depth_shift, flags, out8,
+                          dC1, dC2, cd_out, loss_out, dd_out, fd_dbg, ws, st);
+  }
+  DG_REQUIRE(pan->format == DG_PANEL_F32, DG_ERR_INVALID, "dg_corr_loss: unknown panel format %d", pan->format);
+  DG_REQUIRE(Prows == round_up(P, 64), DG_ERR_INVALID, "dg_corr_loss: Prows must be dg_panel_rows(P)");
+  const float* fn = static_cast<const float*>(pan->f_hi);
+  const float* cn = static_cast<const float*>(pan->c_hi);
   const int n_pt = Prows / TM;
   CorrParams prm;
   prm.fn = fn;
@@ -410,7 +449,6 @@ extern "C" int dg_corr_loss(const float* fn, const float* cn, const float* fmean
   prm.depth_shift = depth_shift;
   prm.inv_cnt = 1.0f / ((float)B * (float)P * (float)P);
   for (int k = 0; k < npairs; ++k) {
-    DG_REQUIRE(pair_group[k] >= 0 && pair_group[k] <= DG_GROUP_NEG, DG_ERR_INVALID, "dg_corr_loss: bad pair group");
     prm.shift[k] = pair_shift[k];
     prm.group[k] = pair_group[k];
   }
@@ -426,7 +464,5 @@ extern "C" int dg_corr_loss(const float* fn, const float* cn, const float* fmean
   DG_CUDA_OK(cudaFuncSetAttribute(corr_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   corr_tile_kernel<<<dim3(n_pt, npairs * B), CORR_THREADS, smem, st>>>(prm);
   DG_LAUNCH_OK("corr_tile_kernel");
-  corr_finalize_kernel<<<1, 256, 0, st>>>(prm, n_pt);
-  DG_LAUNCH_OK("corr_finalize_kernel");
-  return DG_OK;
+  return launch_corr_finalize(prm.partials, npairs, B, P, pair_group, prm.has_depth, nullptr, out8, n_pt, st);
 }

@@ -1,0 +1,460 @@
+// Fused correlation loss on the 5th-gen tensor cores (tcgen05 + TMEM + TMA), P <= 128.
+//
+// Same contract as corr_tile_kernel (corr_loss.cu) — replaces helper() for every pair
+// and depth_feature_correlation (/root/reference/src/modules.py:1231-1278) — but one
+// CTA owns a whole (pair k, image b) tile and nothing P x P ever leaves the SM:
+//
+//   warp 0   TMA producer : streams K-chunks of the split panels into a 4 x 32 KB smem ring
+//   warp 1   MMA issuer   : one elected lane issues tcgen05.mma; accumulators live in TMEM
+//              fd[128x128]  = F1 . F2^T   bf16 hi/lo split, 3 products per K-step (hh + hl + lh)
+//              cd[128x128]  = C1 . C2^T   tf32 hi/lo split, 3 products (fp32-grade: the clamp
+//                                          indicator must not flip, see DESIGN.md "Precision")
+//   warps 2-5 epilogue    : one thread per row p reads its fd / cd rows from TMEM, forms
+//              rowmean (pointwise centring), clamp, loss sums and the unit-gradient factor
+//              U[p,q] = -(fd' - shift) 1[clamp passes] / (B P^2), writes U as bf16 hi/lo into
+//              smem in the canonical 128B-swizzled layout, then
+//   warp 1   again        : dC1[p,:]  = U . C2n        (A = U K-major,  B = C2n^T K-major)
+//                           dC2^T[:,q] = C1n^T . U      (A = C1n^T K-major, B = U MN-major)
+//   warps 2-5 drain dC1 / dC2^T from TMEM to HBM.  For the intra pair the depth term repeats
+//   the last two steps with U_d = -(s_p s_q - depth_shift) 1[..] / (B P^2).
+//
+// Every mbarrier wait is bounded; on a timeout the CTA raises an error flag (the losses
+// come back NaN) instead of hanging the GPU.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace dg {
+
+using namespace umma;
+
+constexpr int UM_THREADS = 192;
+constexpr int UM_NSTAGE = 4;
+constexpr int UM_STAGE = 32768;
+constexpr int UM_UBYTES = 65536;  // U hi (32 KB) + U lo (32 KB), bf16 [2 q-atoms][128 p][64 q]
+constexpr int UM_SMEM = UM_NSTAGE * UM_STAGE + UM_UBYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr uint32_t TM_FD = 0, TM_CD = 128, TM_D1 = 256, TM_D2 = 384;
+
+struct UmmaParams {
+  CUtensorMap tm_fhi, tm_flo;  // bf16 [npairs*B*128, ldf]   box 32 x 128, SWIZZLE_64B
+  CUtensorMap tm_chi, tm_clo;  // f32  [npairs*B*128, ldc]   box 32 x 128, SWIZZLE_128B
+  CUtensorMap tm_thi, tm_tlo;  // bf16 [npairs*B*128, 128]   box 64 x 128, SWIZZLE_128B (transposed code)
+  const float* dsign;          // [B,128] or null
+  const float* old_mean;       // [npairs] (pointwise) or null
+  int npairs, B, P, ldf, ldc, flags, has_depth;
+  float depth_shift, inv_cnt;
+  float shift[DG_MAX_PAIRS];
+  float* dC1;       // [npairs+1,B,128,ldc]
+  float* dC2;       // [npairs+1,B,128,ldc]
+  float* partials;  // [npairs*B][4]
+  float* cd_out;    // optional dense [npairs,B,P,P]
+  float* loss_out;
+  float* dd_out;
+  float* fd_dbg;    // optional raw fd accumulators [npairs,B,128,128] (tests)
+  int* err;         // error flag (0 = ok)
+};
+
+__device__ __forceinline__ void raise(int* err, int code) {
+  if (err) atomicCAS(err, 0, code);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) {
+  return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+
+// Write 32 consecutive q-values of row p (as bf16 hi and lo) into the swizzled U tiles.
+__device__ __forceinline__ void store_u_chunk(uint8_t* u_hi, uint8_t* u_lo, int p, int cc, const float* u) {
+  const uint32_t atom = cc >> 1;
+  uint8_t* row_hi = u_hi + atom * 16384 + p * 128;
+  uint8_t* row_lo = u_lo + atom * 16384 + p * 128;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float a = u[8 * i + 2 * e], b = u[8 * i + 2 * e + 1];
+      const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
+      const __nv_bfloat16 al = __float2bfloat16_rn(a - __bfloat162float(ah));
+      const __nv_bfloat16 bl = __float2bfloat16_rn(b - __bfloat162float(bh));
+      h[e] = pack_bf16(ah, bh);
+      l[e] = pack_bf16(al, bl);
+    }
+    const uint32_t chunk = ((cc & 1) * 4 + i) ^ (p & 7);  // Swizzle<3,4,3>: 16-byte chunk ^= row % 8
+    *reinterpret_cast<uint4*>(row_hi + chunk * 16) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(row_lo + chunk * 16) = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+}
+
+__global__ void __launch_bounds__(UM_THREADS, 1) corr_umma_kernel(const __grid_constant__ UmmaParams prm) {
+  extern __shared__ uint8_t um_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(um_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* ring = smem;
+  uint8_t* u_hi = smem + UM_NSTAGE * UM_STAGE;
+  uint8_t* u_lo = u_hi + 32768;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(u_lo + 32768);
+  uint64_t* full = bars;                  // [UM_NSTAGE]
+  uint64_t* empty = bars + UM_NSTAGE;     // [UM_NSTAGE]
+  uint64_t* acc_full = bars + 2 * UM_NSTAGE;
+  uint64_t* u_ready = acc_full + 1;
+  uint64_t* grad_full = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 3);
+  __shared__ float s_red[4][4];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kb = blockIdx.x;
+  const int k = kb / prm.B, b = kb - k * prm.B;
+  const int nfd = prm.ldf / 32, ncd = prm.ldc / 32;
+  const int njobs = nfd + 2 * ncd + 4;
+  const int row1 = b * 128, row2 = (k * prm.B + b) * 128;  // panel rows of the first / second operand
+  const bool depth_round = prm.has_depth && k == 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < UM_NSTAGE; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(acc_full, 1);
+    mbar_init(u_ready, 128);
+    mbar_init(grad_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      prefetch_tmap(&prm.tm_fhi); prefetch_tmap(&prm.tm_flo); prefetch_tmap(&prm.tm_chi);
+      prefetch_tmap(&prm.tm_clo); prefetch_tmap(&prm.tm_thi); prefetch_tmap(&prm.tm_tlo);
+      for (int j = 0; j < njobs; ++j) {
+        const int s = j % UM_NSTAGE;
+        const uint32_t ph = (j / UM_NSTAGE) & 1;
+        if (!mbar_wait(&empty[s], ph ^ 1)) { raise(prm.err, 1); break; }
+        uint8_t* st = ring + s * UM_STAGE;
+        mbar_arrive_expect_tx(&full[s], UM_STAGE);
+        if (j < nfd) {                       // fd chunk: 4 tiles of [128 rows x 32 bf16]
+          const int c0 = j * 32;
+          tma_load_2d(st, &prm.tm_fhi, &full[s], c0, row1);
+          tma_load_2d(st + 8192, &prm.tm_flo, &full[s], c0, row1);
+          tma_load_2d(st + 16384, &prm.tm_fhi, &full[s], c0, row2);
+          tma_load_2d(st + 24576, &prm.tm_flo, &full[s], c0, row2);
+        } else if (j < nfd + 2 * ncd) {      // cd chunk: job A = first operand hi/lo, job B = second operand
+          const int jj = j - nfd, c0 = (jj >> 1) * 32, r = (jj & 1) ? row2 : row1;
+          tma_load_2d(st, &prm.tm_chi, &full[s], c0, r);
+          tma_load_2d(st + 16384, &prm.tm_clo, &full[s], c0, r);
+        } else {                             // gradient operands: transposed code tiles [128 d x 128 p]
+          const int g = j - nfd - 2 * ncd;   // 0: T2 hi, 1: T2 lo, 2: T1 hi, 3: T1 lo
+          const CUtensorMap* m = (g & 1) ? &prm.tm_tlo : &prm.tm_thi;
+          const int r = (g < 2) ? row2 : row1;
+          tma_load_2d(st, m, &full[s], 0, r);
+          tma_load_2d(st + 16384, m, &full[s], 64, r);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    if (lane == 0) {
+      const uint32_t id_f = instr_desc(FMT_BF16, 128, 128, 0, 0);
+      const uint32_t id_c = instr_desc(FMT_TF32, 128, 128, 0, 0);
+      const uint32_t id_g1 = instr_desc(FMT_BF16, 128, (uint32_t)prm.ldc, 0, 0);
+      const uint32_t id_g2 = instr_desc(FMT_BF16, 128, 128, 0, 1);
+      bool ok = true;
+      int j = 0;
+      for (; j < nfd && ok; ++j) {
+        const int s = j % UM_NSTAGE;
+        ok = mbar_wait(&full[s], (j / UM_NSTAGE) & 1);
+        tc_fence_after_sync();
+        const uint32_t st = smem_u32(ring + s * UM_STAGE);
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          const uint64_t ah = smem_desc(st + ks * 32, 16, 512, SW_64B), al = smem_desc(st + 8192 + ks * 32, 16, 512, SW_64B);
+          const uint64_t bh = smem_desc(st + 16384 + ks * 32, 16, 512, SW_64B),
+                         bl = smem_desc(st + 24576 + ks * 32, 16, 512, SW_64B);
+          mma_f16(tmem + TM_FD, ah, bh, id_f, (j | ks) != 0);
+          mma_f16(tmem + TM_FD, ah, bl, id_f, 1);
+          mma_f16(tmem + TM_FD, al, bh, id_f, 1);
+        }
+        mma_commit(&empty[s]);
+      }
+      for (int c = 0; c < ncd && ok; ++c, j += 2) {
+        const int sa = j % UM_NSTAGE, sb = (j + 1) % UM_NSTAGE;
+        ok = mbar_wait(&full[sa], (j / UM_NSTAGE) & 1) && mbar_wait(&full[sb], ((j + 1) / UM_NSTAGE) & 1);
+        tc_fence_after_sync();
+        const uint32_t a0 = smem_u32(ring + sa * UM_STAGE), b0 = smem_u32(ring + sb * UM_STAGE);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint64_t ah = smem_desc(a0 + ks * 32, 16, 1024, SW_128B), al = smem_desc(a0 + 16384 + ks * 32, 16, 1024, SW_128B);
+          const uint64_t bh = smem_desc(b0 + ks * 32, 16, 1024, SW_128B), bl = smem_desc(b0 + 16384 + ks * 32, 16, 1024, SW_128B);
+          mma_tf32(tmem + TM_CD, ah, bh, id_c, (c | ks) != 0);
+          mma_tf32(tmem + TM_CD, ah, bl, id_c, 1);
+          mma_tf32(tmem + TM_CD, al, bh, id_c, 1);
+        }
+        mma_commit(&empty[sa]);
+        mma_commit(&empty[sb]);
+      }
+      mma_commit(acc_full);
+      // gradient operands: jobs j..j+3 (T2 hi, T2 lo, T1 hi, T1 lo), one ring stage each
+      uint32_t gst[4];
+      for (int g = 0; g < 4 && ok; ++g) {
+        const int s = (j + g) % UM_NSTAGE;
+        ok = mbar_wait(&full[s], ((j + g) / UM_NSTAGE) & 1);
+        gst[g] = smem_u32(ring + s * UM_STAGE);
+      }
+      const uint32_t uh = smem_u32(u_hi), ul = smem_u32(u_lo);
+      const int rounds = depth_round ? 2 : 1;
+      for (int rd = 0; rd < rounds && ok; ++rd) {
+        ok = mbar_wait(u_ready, rd & 1);
+        tc_fence_after_sync();
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {  // dC1[p, d] += U[p, q-block] . C2n^T[d, q-block]^T
+          const uint32_t off = (ks >> 2) * 16384 + (ks & 3) * 32;
+          const uint64_t a_h = smem_desc(uh + off, 16, 1024, SW_128B), a_l = smem_desc(ul + off, 16, 1024, SW_128B);
+          const uint64_t b_h = smem_desc(gst[0] + off, 16, 1024, SW_128B), b_l = smem_desc(gst[1] + off, 16, 1024, SW_128B);
+          mma_f16(tmem + TM_D1, a_h, b_h, id_g1, ks != 0);
+          mma_f16(tmem + TM_D1, a_h, b_l, id_g1, 1);
+          mma_f16(tmem + TM_D1, a_l, b_h, id_g1, 1);
+        }
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {  // dC2^T[d, q] += C1n^T[d, p-block] . U[p-block, q]
+          const uint32_t aoff = (ks >> 2) * 16384 + (ks & 3) * 32;
+          const uint64_t a_h = smem_desc(gst[2] + aoff, 16, 1024, SW_128B), a_l = smem_desc(gst[3] + aoff, 16, 1024, SW_128B);
+          // U as MN-major B: 16 k-rows (p) per step = 2048 B; atoms of 64 q are 16384 B apart (LBO), 8-row groups 1024 B (SBO)
+          const uint64_t b_h = smem_desc(uh + ks * 2048, 16384, 1024, SW_128B), b_l = smem_desc(ul + ks * 2048, 16384, 1024, SW_128B);
+          mma_f16(tmem + TM_D2, a_h, b_h, id_g2, ks != 0);
+          mma_f16(tmem + TM_D2, a_l, b_h, id_g2, 1);
+          mma_f16(tmem + TM_D2, a_h, b_l, id_g2, 1);
+        }
+        mma_commit(grad_full);
+      }
+      if (!ok) raise(prm.err, 2);
+    }
+  } else {
+    // ================================ epilogue (warps 2..5) ================================
+    const int lg = warp & 3;                 // TMEM lane group this warp may access
+    const int p = 32 * lg + lane;            // row of fd / cd / dC1; row (= channel d) of dC2^T
+    const uint32_t tlane = tmem + ((uint32_t)(32 * lg) << 16);
+    const int P = prm.P;
+    const bool pointwise = prm.flags & DG_FLAG_POINTWISE;
+    const float lo = (prm.flags & DG_FLAG_ZERO_CLAMP) ? 0.f : -9999.f;
+    const float hi = (prm.flags & DG_FLAG_STABALIZE) ? 0.8f : __int_as_float(0x7f800000);
+    const float shift = prm.shift[k];
+    const float old_mean = (pointwise && prm.old_mean) ? __ldg(prm.old_mean + k) : 0.f;
+    const float sp = depth_round ? __ldg(prm.dsign + (size_t)b * 128 + p) : 0.f;
+    float sum_loss = 0.f, sum_cd = 0.f, sum_dloss = 0.f, sum_dd = 0.f;
+    float v[32], c[32];
+
+    bool ok = mbar_wait(acc_full, 0);
+    tc_fence_after_sync();
+    float rowmean = 0.f;
+    if (pointwise) {
+      float s = 0.f;
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        tmem_ld_32x32(tlane + TM_FD + 32 * cc, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (32 * cc + i < P) s += v[i];
+      }
+      rowmean = s / (float)P;
+    }
+    const size_t obase = (((size_t)k * prm.B + b) * P + p) * P;
+#pragma unroll 1
+    for (int cc = 0; cc < 4; ++cc) {
+      tmem_ld_32x32(tlane + TM_FD + 32 * cc, v);
+      tmem_ld_32x32(tlane + TM_CD + 32 * cc, c);
+      tmem_ld_wait();
+      if (prm.fd_dbg) {
+        float* dst = prm.fd_dbg + ((size_t)kb * 128 + p) * 128 + 32 * cc;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) dst[i] = v[i];
+      }
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int q = 32 * cc + i;
+        const bool valid = (p < P) && (q < P);
+        const float cdv = c[i];
+        const float cl = fminf(fmaxf(cdv, lo), hi);
+        const bool pass = valid && (cdv >= lo) && (cdv <= hi);
+        const float f = v[i] - rowmean + old_mean - shift;
+        if (valid) {
+          sum_loss += -cl * f;
+          sum_cd += cdv;
+          if (prm.cd_out) prm.cd_out[obase + q] = cdv;
+          if (prm.loss_out) prm.loss_out[obase + q] = -cl * f;
+          if (depth_round) {
+            const float dd = sp * __ldg(prm.dsign + (size_t)b * 128 + q);
+            sum_dloss += -cl * (dd - prm.depth_shift);
+            sum_dd += dd;
+            if (prm.dd_out) prm.dd_out[((size_t)b * P + p) * P + q] = dd;
+          }
+        }
+        v[i] = pass ? -f * prm.inv_cnt : 0.f;
+      }
+      store_u_chunk(u_hi, u_lo, p, cc, v);
+    }
+    const int rounds = depth_round ? 2 : 1;
+    for (int rd = 0; rd < rounds; ++rd) {
+      fence_proxy_async_smem();
+      tc_fence_before_sync();
+      mbar_arrive(u_ready);
+      ok = ok && mbar_wait(grad_full, rd & 1);
+      tc_fence_after_sync();
+      const size_t slab = (size_t)prm.B * 128 * prm.ldc;
+      const size_t which = (rd == 0) ? (size_t)k : (size_t)prm.npairs;
+      float* d1 = prm.dC1 + which * slab + ((size_t)b * 128 + p) * prm.ldc;
+      for (int cc = 0; cc < ncd; ++cc) {  // dC1 row p: ldc contiguous floats
+        tmem_ld_32x32(tlane + TM_D1 + 32 * cc, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          *reinterpret_cast<float4*>(d1 + 32 * cc + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      }
+      if (32 * lg < prm.ldc) {  // dC2^T row = channel d (this thread), columns = q: lanes write consecutive d
+        float* d2 = prm.dC2 + which * slab + (size_t)b * 128 * prm.ldc + p;
+        for (int cc = 0; cc < 4; ++cc) {
+          tmem_ld_32x32(tlane + TM_D2 + 32 * cc, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) d2[(size_t)(32 * cc + i) * prm.ldc] = v[i];
+        }
+      }
+      if (rd + 1 < rounds) {  // depth term: U_d = -(s_p s_q - depth_shift) 1[clamp passes] / (B P^2)
+        tc_fence_before_sync();
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // all epilogue warps have drained D1 / D2 of round 0
+        tc_fence_after_sync();
+#pragma unroll 1
+        for (int cc = 0; cc < 4; ++cc) {
+          tmem_ld_32x32(tlane + TM_CD + 32 * cc, c);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int q = 32 * cc + i;
+            const bool pass = (p < P) && (q < P) && (c[i] >= lo) && (c[i] <= hi);
+            const float dd = sp * __ldg(prm.dsign + (size_t)b * 128 + q);
+            v[i] = pass ? -(dd - prm.depth_shift) * prm.inv_cnt : 0.f;
+          }
+          store_u_chunk(u_hi, u_lo, p, cc, v);
+        }
+      }
+    }
+    if (!ok) raise(prm.err, 3);
+    sum_loss = warp_sum(sum_loss);
+    sum_cd = warp_sum(sum_cd);
+    sum_dloss = warp_sum(sum_dloss);
+    sum_dd = warp_sum(sum_dd);
+    if (lane == 0) {
+      s_red[lg][0] = sum_loss; s_red[lg][1] = sum_cd; s_red[lg][2] = sum_dloss; s_red[lg][3] = sum_dd;
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (warp == 2 && lane < 4)
+      prm.partials[(size_t)kb * 4 + lane] = s_red[0][lane] + s_red[1][lane] + s_red[2][lane] + s_red[3][lane];
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// old_mean[k] = mean_b < mean_p F1n[b,p,:], mean_q F2n[k,b,q,:] >   (= mean of fd over b,p,q)
+__global__ void __launch_bounds__(256) pair_oldmean_kernel(const float* __restrict__ fmean, int B, int ldf,
+                                                           float* __restrict__ old_mean) {
+  __shared__ float red[8];
+  const int k = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float acc = 0.f;
+  for (int b = warp; b < B; b += 8) {
+    const float* m1 = fmean + (size_t)b * ldf;
+    const float* m2 = fmean + ((size_t)k * B + b) * ldf;
+    float s = 0.f;
+    for (int c = lane; c < ldf; c += 32) s += __ldg(m1 + c) * __ldg(m2 + c);
+    acc += warp_sum(s);
+  }
+  if (lane == 0) red[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    old_mean[k] = t / (float)B;
+  }
+}
+
+// ------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+static int make_map_2d(CUtensorMap* m, CUtensorMapDataType dt, int elt_bytes, const void* base, uint64_t cols,
+                       uint64_t rows, uint32_t box_cols, uint32_t box_rows, CUtensorMapSwizzle sw) {
+  EncodeTiledFn fn = get_encode_fn();
+  DG_REQUIRE(fn, DG_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * (uint64_t)elt_bytes};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DG_REQUIRE(r == CUDA_SUCCESS, DG_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return DG_OK;
+}
+
+// declared in corr_loss.cu: folds partial sums into out8 (n_pt = 1 here)
+int launch_corr_finalize(const float* partials, int npairs, int B, int P, const int32_t* group, int has_depth,
+                         const int* err, float* out8, int n_pt, cudaStream_t st);
+
+int corr_loss_umma(const dg_panels_t* pan, const float* fmean, const float* dsign, int npairs, int B, int P, int ldf,
+                   int ldc, const float* pair_shift, const int32_t* pair_group, float depth_shift, int flags,
+                   float* out8, float* dC1, float* dC2, float* cd_out, float* loss_out, float* dd_out, float* fd_dbg,
+                   void* ws, cudaStream_t st) {
+  UmmaParams prm;
+  const uint64_t rows = (uint64_t)npairs * B * 128;
+  int rc;
+  if ((rc = make_map_2d(&prm.tm_fhi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, pan->f_hi, ldf, rows, 32, 128, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+  if ((rc = make_map_2d(&prm.tm_flo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, pan->f_lo, ldf, rows, 32, 128, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+  if ((rc = make_map_2d(&prm.tm_chi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, pan->c_hi, ldc, rows, 32, 128, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if ((rc = make_map_2d(&prm.tm_clo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, pan->c_lo, ldc, rows, 32, 128, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if ((rc = make_map_2d(&prm.tm_thi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, pan->ct_hi, 128, rows, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if ((rc = make_map_2d(&prm.tm_tlo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, pan->ct_lo, 128, rows, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  // workspace: [err int (256 B)][old_mean npairs floats (256 B)][partials npairs*B*4 floats]
+  int* err = static_cast<int*>(ws);
+  float* old_mean = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + 256);
+  float* partials = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + 512);
+  DG_CUDA_OK(cudaMemsetAsync(ws, 0, 512, st));
+  prm.dsign = dsign;
+  prm.old_mean = (flags & DG_FLAG_POINTWISE) ? old_mean : nullptr;
+  prm.npairs = npairs; prm.B = B; prm.P = P; prm.ldf = ldf; prm.ldc = ldc; prm.flags = flags;
+  prm.has_depth = dsign != nullptr;
+  prm.depth_shift = depth_shift;
+  prm.inv_cnt = 1.0f / ((float)B * (float)P * (float)P);
+  for (int k = 0; k < npairs; ++k) prm.shift[k] = pair_shift[k];
+  prm.dC1 = dC1; prm.dC2 = dC2; prm.partials = partials;
+  prm.cd_out = cd_out; prm.loss_out = loss_out; prm.dd_out = dd_out; prm.fd_dbg = fd_dbg; prm.err = err;
+  if (flags & DG_FLAG_POINTWISE) {
+    pair_oldmean_kernel<<<npairs, 256, 0, st>>>(fmean, B, ldf, old_mean);
+    DG_LAUNCH_OK("pair_oldmean_kernel");
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    DG_CUDA_OK(cudaFuncSetAttribute(corr_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, UM_SMEM));
+    attr_set = true;
+  }
+  corr_umma_kernel<<<npairs * B, UM_THREADS, UM_SMEM, st>>>(prm);
+  DG_LAUNCH_OK("corr_umma_kernel");
+  return launch_corr_finalize(partials, npairs, B, P, pair_group, prm.has_depth, err, out8, 1, st);
+}
+
+}  // namespace dg

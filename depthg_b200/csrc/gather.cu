@@ -12,9 +12,17 @@
 // channels (128-bit loads when the channel stride is 1), so a channels-last
 // source is read in whole 128-byte lines and every panel row is written once,
 // coalesced.  HBM-bound: no data reuse beyond the four bilinear corners.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace dg {
+
+__device__ __forceinline__ float umma_tf32(float x) {  // round-to-nearest tf32 (10-bit mantissa) in an fp32 container
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
 
 constexpr int GATHER_THREADS = 512;
 constexpr int GATHER_WARPS = GATHER_THREADS / 32;
@@ -24,82 +32,123 @@ struct SetTable {
   int32_t slot[DG_MAX_SETS];
 };
 
+enum { FMT_F32 = 0, FMT_FEATS_SPLIT = 1, FMT_CODE_SPLIT = 2 };
+
+struct GatherOut {
+  // FMT_F32        : out (fp32 [slot,b,Prows,ld])
+  // FMT_FEATS_SPLIT: hi16/lo16 (bf16 [slot,b,Prows,ld]) : x ~= hi + lo
+  // FMT_CODE_SPLIT : out = tf32-rounded hi, out_lo = x - hi (fp32 [slot,b,Prows,ld]);
+  //                  t_hi16/t_lo16 (bf16 [slot,b,128,128]) transposed: row = channel, col = point
+  float* out;
+  float* out_lo;
+  __nv_bfloat16* hi16;
+  __nv_bfloat16* lo16;
+  __nv_bfloat16* t_hi16;
+  __nv_bfloat16* t_lo16;
+  float* rnorm;
+  float* meanvec;
+};
+
+__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& h, __nv_bfloat16& l) {
+  h = __float2bfloat16_rn(v);
+  l = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+
 // dynamic smem: row staging [GATHER_WARPS][ld] + mean accumulators [GATHER_WARPS][ld]
+//               (+ FMT_CODE_SPLIT: normalised tile [128][ld+1] for the transposed write-out)
+template <int FMT>
 __global__ void __launch_bounds__(GATHER_THREADS)
     gather_norm_kernel(const float* __restrict__ t, int64_t sb, int64_t sc, int64_t sh, int64_t sw, int B, int C, int H,
                        int W, const float* __restrict__ coords, int S, SetTable sets, const int64_t* __restrict__ perm,
-                       float eps, int Prows, int ld, float* __restrict__ out, float* __restrict__ rnorm,
-                       float* __restrict__ meanvec) {
+                       float eps, int Prows, int ld, GatherOut o) {
   extern __shared__ float gsm[];
   const int set = blockIdx.x / B, b = blockIdx.x - set * B;
   const int P = S * S;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* row = gsm + (size_t)warp * ld;
   float* macc = gsm + (size_t)(GATHER_WARPS + warp) * ld;
+  float* tile = gsm + (size_t)2 * GATHER_WARPS * ld;  // FMT_CODE_SPLIT only: [128][ld+1]
   const int slot = sets.slot[set];
   const int64_t src = perm ? perm[(size_t)set * B + b] : (int64_t)b;
   const float* timg = t + src * sb;
   const float* cset = coords + ((size_t)sets.coord[set] * B + b) * P * 2;
-  float* opanel = out + ((size_t)slot * B + b) * Prows * ld;
-  float* rpanel = rnorm + ((size_t)slot * B + b) * Prows;
+  const size_t pbase = ((size_t)slot * B + b) * Prows;
+  float* rpanel = o.rnorm + pbase;
 
   for (int c = lane; c < ld; c += 32) macc[c] = 0.f;
   const bool vec = (sc == 1) && ((C & 3) == 0) && ((sb & 3) == 0) && ((sh & 3) == 0) && ((sw & 3) == 0) &&
                    ((reinterpret_cast<uintptr_t>(t) & 15) == 0);
 
   for (int p = warp; p < Prows; p += GATHER_WARPS) {
-    float* orow = opanel + (size_t)p * ld;
-    if (p >= P) {  // zero padding rows
-      for (int c = lane; c < ld; c += 32) orow[c] = 0.f;
-      if (lane == 0) rpanel[p] = 0.f;
-      continue;
-    }
-    const int h = p / S, w = p - h * S;
-    const float* cc = cset + 2 * (w * S + h);  // the reference's S-axis swap (coords.permute(0,2,1,3))
-    const Corners k = bilinear_corners(__ldg(cc), __ldg(cc + 1), H, W);
-    const float* p00 = timg + k.y0 * sh + k.x0 * sw;
-    const float* p01 = k.x1_ok ? p00 + sw : p00;
-    const float* p10 = k.y1_ok ? p00 + sh : p00;
-    const float* p11 = p10 + (k.x1_ok ? sw : 0);
-    const float w00 = k.w00, w01 = k.x1_ok ? k.w01 : 0.f, w10 = k.y1_ok ? k.w10 : 0.f,
-                w11 = (k.x1_ok && k.y1_ok) ? k.w11 : 0.f;
-    float ss = 0.f;
-    if (vec) {
-      for (int c = lane * 4; c < C; c += 128) {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(p00 + c));
-        const float4 bq = __ldg(reinterpret_cast<const float4*>(p01 + c));
-        const float4 cq = __ldg(reinterpret_cast<const float4*>(p10 + c));
-        const float4 d = __ldg(reinterpret_cast<const float4*>(p11 + c));
-        float4 v;
-        v.x = a.x * w00 + bq.x * w01 + cq.x * w10 + d.x * w11;
-        v.y = a.y * w00 + bq.y * w01 + cq.y * w10 + d.y * w11;
-        v.z = a.z * w00 + bq.z * w01 + cq.z * w10 + d.z * w11;
-        v.w = a.w * w00 + bq.w * w01 + cq.w * w10 + d.w * w11;
-        ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-        *reinterpret_cast<float4*>(row + c) = v;
+    const size_t ro = (pbase + p) * ld;
+    float r = 0.f;
+    if (p < P) {
+      const int h = p / S, w = p - h * S;
+      const float* cc = cset + 2 * (w * S + h);  // the reference's S-axis swap (coords.permute(0,2,1,3))
+      const Corners k = bilinear_corners(__ldg(cc), __ldg(cc + 1), H, W);
+      const float* p00 = timg + k.y0 * sh + k.x0 * sw;
+      const float* p01 = k.x1_ok ? p00 + sw : p00;
+      const float* p10 = k.y1_ok ? p00 + sh : p00;
+      const float* p11 = p10 + (k.x1_ok ? sw : 0);
+      const float w00 = k.w00, w01 = k.x1_ok ? k.w01 : 0.f, w10 = k.y1_ok ? k.w10 : 0.f,
+                  w11 = (k.x1_ok && k.y1_ok) ? k.w11 : 0.f;
+      float ss = 0.f;
+      if (vec) {
+#pragma unroll 2
+        for (int c = lane * 4; c < C; c += 128) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(p00 + c));
+          const float4 bq = __ldg(reinterpret_cast<const float4*>(p01 + c));
+          const float4 cq = __ldg(reinterpret_cast<const float4*>(p10 + c));
+          const float4 d = __ldg(reinterpret_cast<const float4*>(p11 + c));
+          float4 v;
+          v.x = a.x * w00 + bq.x * w01 + cq.x * w10 + d.x * w11;
+          v.y = a.y * w00 + bq.y * w01 + cq.y * w10 + d.y * w11;
+          v.z = a.z * w00 + bq.z * w01 + cq.z * w10 + d.z * w11;
+          v.w = a.w * w00 + bq.w * w01 + cq.w * w10 + d.w * w11;
+          ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+          *reinterpret_cast<float4*>(row + c) = v;
+        }
+      } else {
+        for (int c = lane; c < C; c += 32) {
+          const int64_t off = (int64_t)c * sc;
+          const float v =
+              __ldg(p00 + off) * w00 + __ldg(p01 + off) * w01 + __ldg(p10 + off) * w10 + __ldg(p11 + off) * w11;
+          ss += v * v;
+          row[c] = v;
+        }
       }
-    } else {
-      for (int c = lane; c < C; c += 32) {
-        const int64_t o = (int64_t)c * sc;
-        const float v = __ldg(p00 + o) * w00 + __ldg(p01 + o) * w01 + __ldg(p10 + o) * w10 + __ldg(p11 + o) * w11;
-        ss += v * v;
-        row[c] = v;
-      }
+      ss = warp_sum(ss);
+      r = 1.f / fmaxf(sqrtf(ss), eps);
     }
-    ss = warp_sum(ss);
-    const float r = 1.f / fmaxf(sqrtf(ss), eps);
     __syncwarp();
-    if (vec) {
+    // normalise, accumulate the panel mean, write the row in the requested format (zeros for padding)
+    if (vec || p >= P) {
       for (int c = lane * 4; c < ld; c += 128) {
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (c < C) {
+        if (p < P && c < C) {
           v = *reinterpret_cast<const float4*>(row + c);
           v.x *= r; v.y *= r; v.z *= r; v.w *= r;
           float4 m = *reinterpret_cast<float4*>(macc + c);
           m.x += v.x; m.y += v.y; m.z += v.z; m.w += v.w;
           *reinterpret_cast<float4*>(macc + c) = m;
         }
-        *reinterpret_cast<float4*>(orow + c) = v;
+        if (FMT == FMT_F32) {
+          *reinterpret_cast<float4*>(o.out + ro + c) = v;
+        } else if (FMT == FMT_FEATS_SPLIT) {
+          __nv_bfloat16 h[4], l[4];
+          split_bf16(v.x, h[0], l[0]); split_bf16(v.y, h[1], l[1]);
+          split_bf16(v.z, h[2], l[2]); split_bf16(v.w, h[3], l[3]);
+          *reinterpret_cast<uint2*>(o.hi16 + ro + c) = *reinterpret_cast<uint2*>(h);
+          *reinterpret_cast<uint2*>(o.lo16 + ro + c) = *reinterpret_cast<uint2*>(l);
+        } else {
+          float4 hi = make_float4(umma_tf32(v.x), umma_tf32(v.y), umma_tf32(v.z), umma_tf32(v.w));
+          *reinterpret_cast<float4*>(o.out + ro + c) = hi;
+          *reinterpret_cast<float4*>(o.out_lo + ro + c) = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
+          if (p < 128) {
+            tile[p * (ld + 1) + c] = v.x; tile[p * (ld + 1) + c + 1] = v.y;
+            tile[p * (ld + 1) + c + 2] = v.z; tile[p * (ld + 1) + c + 3] = v.w;
+          }
+        }
       }
     } else {
       for (int c = lane; c < ld; c += 32) {
@@ -108,21 +157,58 @@ __global__ void __launch_bounds__(GATHER_THREADS)
           v = row[c] * r;
           macc[c] += v;
         }
-        orow[c] = v;
+        if (FMT == FMT_F32) {
+          o.out[ro + c] = v;
+        } else if (FMT == FMT_FEATS_SPLIT) {
+          __nv_bfloat16 h, l;
+          split_bf16(v, h, l);
+          o.hi16[ro + c] = h;
+          o.lo16[ro + c] = l;
+        } else {
+          const float hi = umma_tf32(v);
+          o.out[ro + c] = hi;
+          o.out_lo[ro + c] = v - hi;
+          if (p < 128) tile[p * (ld + 1) + c] = v;
+        }
       }
     }
     if (lane == 0) rpanel[p] = r;
     __syncwarp();
   }
-  if (meanvec == nullptr) return;
+  if (o.meanvec == nullptr && FMT != FMT_CODE_SPLIT) return;
   __syncthreads();
-  float* mv = meanvec + ((size_t)slot * B + b) * ld;
-  const float invP = 1.f / (float)P;
-  for (int c = threadIdx.x; c < ld; c += GATHER_THREADS) {
-    float s = 0.f;
+  if (o.meanvec != nullptr) {
+    float* mv = o.meanvec + ((size_t)slot * B + b) * ld;
+    const float invP = 1.f / (float)P;
+    for (int c = threadIdx.x; c < ld; c += GATHER_THREADS) {
+      float s = 0.f;
 #pragma unroll
-    for (int wdx = 0; wdx < GATHER_WARPS; ++wdx) s += gsm[(size_t)(GATHER_WARPS + wdx) * ld + c];
-    mv[c] = s * invP;
+      for (int wdx = 0; wdx < GATHER_WARPS; ++wdx) s += gsm[(size_t)(GATHER_WARPS + wdx) * ld + c];
+      mv[c] = s * invP;
+    }
+  }
+  if (FMT == FMT_CODE_SPLIT) {
+    // transposed bf16 hi/lo panels [channel 0..127][point 0..127] (zero outside C x P) for the gradient GEMMs
+    __nv_bfloat16* th = o.t_hi16 + ((size_t)slot * B + b) * 128 * 128;
+    __nv_bfloat16* tl = o.t_lo16 + ((size_t)slot * B + b) * 128 * 128;
+    for (int d = warp; d < 128; d += GATHER_WARPS) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int p2 = 2 * (lane + 32 * j);  // two adjacent points per lane -> 4-byte stores
+        float v0 = 0.f, v1 = 0.f;
+        if (d < C) {
+          if (p2 < P) v0 = tile[p2 * (ld + 1) + d];
+          if (p2 + 1 < P) v1 = tile[(p2 + 1) * (ld + 1) + d];
+        }
+        __nv_bfloat16 h0, l0, h1, l1;
+        split_bf16(v0, h0, l0);
+        split_bf16(v1, h1, l1);
+        __nv_bfloat162 hh, ll;
+        hh.x = h0; hh.y = h1; ll.x = l0; ll.y = l1;
+        *reinterpret_cast<__nv_bfloat162*>(th + d * 128 + p2) = hh;
+        *reinterpret_cast<__nv_bfloat162*>(tl + d * 128 + p2) = ll;
+      }
+    }
   }
 }
 
@@ -137,7 +223,7 @@ __global__ void __launch_bounds__(256)
     gather_norm_bwd_kernel(float* __restrict__ grad, int64_t sb, int64_t sc, int64_t sh, int64_t sw, int B, int C, int H,
                            int W, const float* __restrict__ coords, int S, SetTable sets,
                            const int64_t* __restrict__ perm, float eps, int Prows, int ld, const float* __restrict__ cn,
-                           const float* __restrict__ rnorm, const float* __restrict__ dC1, const float* __restrict__ dC2,
+                           const float* __restrict__ cn_lo, const float* __restrict__ rnorm, const float* __restrict__ dC1, const float* __restrict__ dC2,
                            int npairs, PairTable pairs, int has_depth, const float* __restrict__ group_w, int nsets) {
   const int P = S * S;
   const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -183,12 +269,14 @@ __global__ void __launch_bounds__(256)
       if (j < R) g[j] = ws * __ldg(a + lane + 32 * j);
   }
   const float* xh = cn + (size_t)slot * panel + rowoff;
+  const float* xl = cn_lo ? cn_lo + (size_t)slot * panel + rowoff : nullptr;  // split panels: x = hi + lo exactly
   const float r = __ldg(rnorm + ((size_t)slot * B + b) * Prows + p);
   float x[8];
   float dot = 0.f;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     x[j] = (j < R) ? __ldg(xh + lane + 32 * j) : 0.f;
+    if (xl && j < R) x[j] += __ldg(xl + lane + 32 * j);
     dot += g[j] * x[j];
   }
   dot = warp_sum(dot);
@@ -275,22 +363,43 @@ extern "C" int dg_panel_rows(int P) { return dg::round_up(P, 64); }
 
 extern "C" int dg_gather_norm(const float* t, const int64_t* strides, int B, int C, int H, int W, const float* coords,
                               int S, int nsets, const int32_t* set_coord, const int32_t* set_slot, const int64_t* perm,
-                              float eps, int Prows, int ld, float* out, float* rnorm, float* meanvec,
-                              dg_stream_t stream) {
+                              float eps, int Prows, int ld, int format, void* out, void* out_lo, void* outT_hi,
+                              void* outT_lo, float* rnorm, float* meanvec, dg_stream_t stream) {
   using namespace dg;
   DG_REQUIRE(t && strides && coords && out && rnorm, DG_ERR_INVALID, "dg_gather_norm: null pointer");
   DG_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && S > 0, DG_ERR_INVALID, "dg_gather_norm: bad sizes");
   DG_REQUIRE(ld >= C && (ld % 32) == 0, DG_ERR_INVALID, "dg_gather_norm: ld=%d must be a multiple of 32 >= C=%d", ld, C);
   DG_REQUIRE(Prows >= S * S, DG_ERR_INVALID, "dg_gather_norm: Prows=%d < S*S=%d", Prows, S * S);
+  DG_REQUIRE(format >= DG_PANEL_F32 && format <= DG_PANEL_CODE_SPLIT, DG_ERR_INVALID, "dg_gather_norm: bad format");
+  DG_REQUIRE(format == DG_PANEL_F32 || out_lo, DG_ERR_INVALID, "dg_gather_norm: split formats need out_lo");
+  DG_REQUIRE(format != DG_PANEL_CODE_SPLIT || (outT_hi && outT_lo && Prows == 128 && ld <= 128), DG_ERR_INVALID,
+             "dg_gather_norm: code-split format needs transposed outputs, Prows == 128 and ld <= 128");
   SetTable tab;
   int rc = check_sets("dg_gather_norm", nsets, set_coord, set_slot, &tab);
   if (rc != DG_OK) return rc;
-  const size_t smem = (size_t)2 * GATHER_WARPS * ld * sizeof(float);
+  size_t smem = (size_t)2 * GATHER_WARPS * ld * sizeof(float);
+  if (format == DG_PANEL_CODE_SPLIT) smem += (size_t)128 * (ld + 1) * sizeof(float);
   DG_REQUIRE(smem <= 200 * 1024, DG_ERR_UNSUPPORTED, "dg_gather_norm: C=%d too large for the row staging buffer", C);
-  DG_CUDA_OK(cudaFuncSetAttribute(gather_norm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  gather_norm_kernel<<<nsets * B, GATHER_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
-      t, strides[0], strides[1], strides[2], strides[3], B, C, H, W, coords, S, tab, perm, eps, Prows, ld, out, rnorm,
-      meanvec);
+  GatherOut o;
+  o.out = static_cast<float*>(out);
+  o.out_lo = static_cast<float*>(out_lo);
+  o.hi16 = static_cast<__nv_bfloat16*>(out);
+  o.lo16 = static_cast<__nv_bfloat16*>(out_lo);
+  o.t_hi16 = static_cast<__nv_bfloat16*>(outT_hi);
+  o.t_lo16 = static_cast<__nv_bfloat16*>(outT_lo);
+  o.rnorm = rnorm;
+  o.meanvec = meanvec;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+#define DG_GATHER_LAUNCH(F)                                                                                          \
+  do {                                                                                                               \
+    DG_CUDA_OK(cudaFuncSetAttribute(gather_norm_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    gather_norm_kernel<F><<<nsets * B, GATHER_THREADS, smem, st>>>(t, strides[0], strides[1], strides[2], strides[3], \
+                                                                    B, C, H, W, coords, S, tab, perm, eps, Prows, ld, o); \
+  } while (0)
+  if (format == DG_PANEL_F32) DG_GATHER_LAUNCH(FMT_F32);
+  else if (format == DG_PANEL_FEATS_SPLIT) DG_GATHER_LAUNCH(FMT_FEATS_SPLIT);
+  else DG_GATHER_LAUNCH(FMT_CODE_SPLIT);
+#undef DG_GATHER_LAUNCH
   DG_LAUNCH_OK("gather_norm_kernel");
   return DG_OK;
 }
@@ -298,7 +407,7 @@ extern "C" int dg_gather_norm(const float* t, const int64_t* strides, int B, int
 extern "C" int dg_gather_norm_bwd(float* grad, const int64_t* strides, int B, int C, int H, int W, const float* coords,
                                   int S, int nsets, const int32_t* set_coord, const int32_t* set_slot,
                                   const int64_t* perm, float eps, int Prows, int ld, const float* cn,
-                                  const float* rnorm, const float* dC1, const float* dC2, int npairs,
+                                  const float* cn_lo, const float* rnorm, const float* dC1, const float* dC2, int npairs,
                                   const int32_t* pair_group, const float* pair_scale, int has_depth,
                                   const float* group_w, dg_stream_t stream) {
   using namespace dg;
@@ -322,8 +431,8 @@ extern "C" int dg_gather_norm_bwd(float* grad, const int64_t* strides, int B, in
   const long long rows = (long long)nsets * B * S * S;
   const int blocks = (int)((rows * 32 + 255) / 256);
   gather_norm_bwd_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      grad, strides[0], strides[1], strides[2], strides[3], B, C, H, W, coords, S, tab, perm, eps, Prows, ld, cn, rnorm,
-      dC1, dC2, npairs, pt, has_depth, group_w, nsets);
+      grad, strides[0], strides[1], strides[2], strides[3], B, C, H, W, coords, S, tab, perm, eps, Prows, ld, cn, cn_lo,
+      rnorm, dC1, dC2, npairs, pt, has_depth, group_w, nsets);
   DG_LAUNCH_OK("gather_norm_bwd_kernel");
   return DG_OK;
 }

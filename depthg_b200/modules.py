@@ -10,6 +10,7 @@ the CPU and there is no PyTorch fallback for the kernels.
 """
 from __future__ import annotations
 
+import ctypes as C
 import struct
 
 import torch
@@ -83,11 +84,22 @@ def _strides(t: torch.Tensor):
     return _lib.i64_array(t.stride())
 
 
-def _gather(t, coords, S, set_coord, set_slot, perm, eps, Prows, ld, out, rnorm, meanvec):
+def _gather(t, coords, S, set_coord, set_slot, perm, eps, Prows, ld, out, rnorm, meanvec, fmt=_lib.PANEL_F32,
+            out_lo=None, outT_hi=None, outT_lo=None):
     B, Cdim, H, W = t.shape
     check(_lib.lib().dg_gather_norm(ptr(t), _strides(t), B, Cdim, H, W, ptr(coords), S, len(set_coord),
                                     _lib.i32_array(set_coord), _lib.i32_array(set_slot), ptr(perm), eps, Prows, ld,
-                                    ptr(out), ptr(rnorm), ptr(meanvec), stream_ptr()), "dg_gather_norm")
+                                    fmt, ptr(out), ptr(out_lo), ptr(outT_hi), ptr(outT_lo), ptr(rnorm), ptr(meanvec),
+                                    stream_ptr()), "dg_gather_norm")
+
+
+def corr_kernel_choice(P: int, D: int) -> str:
+    """Which correlation kernel a shape gets: the tcgen05 kernel needs S*S <= 128 and dim <= 128;
+    everything else runs the generic CUDA-core kernel.  DEPTHG_B200_CORR=simt forces the generic one."""
+    import os
+    if os.environ.get("DEPTHG_B200_CORR", "") == "simt":
+        return "simt"
+    return "umma" if (P <= 128 and _lib.panel_ld(D) <= 128) else "simt"
 
 
 def _check_coords(coords, B):
@@ -166,9 +178,10 @@ def tensor_correlation(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     cd = torch.empty((2, n, P, P), device=dev, dtype=torch.float32)
     ws_bytes = _lib.lib().dg_corr_loss_workspace_bytes(2, n, P)
     ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
-    check(_lib.lib().dg_corr_loss(ptr(fn), ptr(cn), None, None, 2, n, P, Prows, 32, 32, c, ld,
+    pan = _lib.make_panels(_lib.PANEL_F32, fn, None, cn, None, None, None)
+    check(_lib.lib().dg_corr_loss(C.byref(pan), None, None, 2, n, P, Prows, 32, 32, c, ld,
                                   _lib.f32_array([0.0, 0.0]), _lib.i32_array([_lib.GROUP_INTRA, _lib.GROUP_INTER]),
-                                  0.0, 0, ptr(out8), ptr(dC1), ptr(dC2), ptr(cd), None, None, ptr(ws), ws_bytes,
+                                  0.0, 0, ptr(out8), ptr(dC1), ptr(dC2), ptr(cd), None, None, None, ptr(ws), ws_bytes,
                                   stream_ptr()), "dg_corr_loss")
     return cd[1].reshape(n, h, w, h, w)
 
@@ -178,6 +191,10 @@ class _CorrLossFn(torch.autograd.Function):
     """forward: FPS/gather/normalise -> fused correlation loss (values + unit
     gradients); backward: weight the unit gradients by the upstream scalars and
     scatter them back through normalise + bilinear gather into the code tensors."""
+
+    debug_fd = False        # tests: also dump the raw feature correlations of the tcgen05 kernel
+    last_fd = None
+    last_unit_grads = None
 
     @staticmethod
     def forward(ctx, feats, feats_pos, code, code_pos, depth, coords, perms, S, shifts, depth_shift, flags,
@@ -194,10 +211,12 @@ class _CorrLossFn(torch.autograd.Function):
         has_depth = depth is not None
 
         f32 = dict(device=dev, dtype=torch.float32)
-        fpan = torch.empty((npairs, B, Prows, ldf), **f32)
+        bf16 = dict(device=dev, dtype=torch.bfloat16)
+        kind = corr_kernel_choice(P, D)
+        if kind == "umma":
+            Prows = 128   # the tcgen05 kernel works on whole 128 x 128 tiles
         frn = torch.empty((npairs, B, Prows), **f32)
         fmean = torch.empty((npairs, B, ldf), **f32) if pointwise else None
-        cpan = torch.empty((npairs, B, Prows, ldc), **f32)
         crn = torch.empty((npairs, B, Prows), **f32)
 
         # sets gathered from the "own" tensors: slot 0 at coords1, one slot per negative at coords2
@@ -208,10 +227,22 @@ class _CorrLossFn(torch.autograd.Function):
             perm_all = torch.cat([ident, perms.to(torch.long)], 0).contiguous()
         else:
             perm_all = None
-        _gather(feats, coords, S, own_coord, own_slot, perm_all, NORM_EPS, Prows, ldf, fpan, frn, fmean)
-        _gather(feats_pos, coords, S, [1], [1], None, NORM_EPS, Prows, ldf, fpan, frn, fmean)
-        _gather(code, coords, S, own_coord, own_slot, perm_all, NORM_EPS, Prows, ldc, cpan, crn, None)
-        _gather(code_pos, coords, S, [1], [1], None, NORM_EPS, Prows, ldc, cpan, crn, None)
+        if kind == "umma":
+            f_hi, f_lo = torch.empty((npairs, B, Prows, ldf), **bf16), torch.empty((npairs, B, Prows, ldf), **bf16)
+            c_hi, c_lo = torch.empty((npairs, B, Prows, ldc), **f32), torch.empty((npairs, B, Prows, ldc), **f32)
+            ct_hi, ct_lo = torch.empty((npairs, B, 128, 128), **bf16), torch.empty((npairs, B, 128, 128), **bf16)
+            fk = dict(fmt=_lib.PANEL_FEATS_SPLIT, out_lo=f_lo)
+            ck = dict(fmt=_lib.PANEL_CODE_SPLIT, out_lo=c_lo, outT_hi=ct_hi, outT_lo=ct_lo)
+            pan = _lib.make_panels(_lib.PANEL_CODE_SPLIT, f_hi, f_lo, c_hi, c_lo, ct_hi, ct_lo)
+        else:
+            f_hi, c_hi = torch.empty((npairs, B, Prows, ldf), **f32), torch.empty((npairs, B, Prows, ldc), **f32)
+            c_lo = None
+            fk, ck = {}, {}
+            pan = _lib.make_panels(_lib.PANEL_F32, f_hi, None, c_hi, None, None, None)
+        _gather(feats, coords, S, own_coord, own_slot, perm_all, NORM_EPS, Prows, ldf, f_hi, frn, fmean, **fk)
+        _gather(feats_pos, coords, S, [1], [1], None, NORM_EPS, Prows, ldf, f_hi, frn, fmean, **fk)
+        _gather(code, coords, S, own_coord, own_slot, perm_all, NORM_EPS, Prows, ldc, c_hi, crn, None, **ck)
+        _gather(code_pos, coords, S, [1], [1], None, NORM_EPS, Prows, ldc, c_hi, crn, None, **ck)
 
         dsign = None
         if has_depth:
@@ -229,12 +260,17 @@ class _CorrLossFn(torch.autograd.Function):
         dd_out = torch.empty((B, P, P), **f32) if (materialize and has_depth) else None
         ws_bytes = lib.dg_corr_loss_workspace_bytes(npairs, B, P)
         ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
-        check(lib.dg_corr_loss(ptr(fpan), ptr(cpan), ptr(fmean), ptr(dsign), npairs, B, P, Prows, Cdim, ldf, D, ldc,
+        fd_dbg = None
+        if _CorrLossFn.debug_fd and kind == "umma":
+            fd_dbg = torch.zeros((npairs, B, 128, 128), **f32)
+            _CorrLossFn.last_fd = fd_dbg
+        check(lib.dg_corr_loss(C.byref(pan), ptr(fmean), ptr(dsign), npairs, B, P, Prows, Cdim, ldf, D, ldc,
                                _lib.f32_array(shifts), _lib.i32_array(groups), float(depth_shift), int(flags),
-                               ptr(out8), ptr(dC1), ptr(dC2), ptr(cd_out), ptr(loss_out), ptr(dd_out), ptr(ws),
-                               ws_bytes, stream_ptr()), "dg_corr_loss")
+                               ptr(out8), ptr(dC1), ptr(dC2), ptr(cd_out), ptr(loss_out), ptr(dd_out), ptr(fd_dbg),
+                               ptr(ws), ws_bytes, stream_ptr()), "dg_corr_loss")
+        _CorrLossFn.last_unit_grads = (dC1, dC2)
 
-        ctx.save_for_backward(coords, perm_all, cpan, crn, dC1, dC2)
+        ctx.save_for_backward(coords, perm_all, c_hi, c_lo, crn, dC1, dC2)
         ctx.meta = (S, Prows, ldc, npairs, nneg, groups, has_depth, code.shape, code_pos.shape,
                     code.stride(), code_pos.stride())
         ctx.code_like = (code, code_pos)  # only for zeros_like layout; no extra memory
@@ -245,7 +281,7 @@ class _CorrLossFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_intra, g_inter, g_neg, g_depth, *unused):
-        coords, perm_all, cpan, crn, dC1, dC2 = ctx.saved_tensors
+        coords, perm_all, cpan, cpan_lo, crn, dC1, dC2 = ctx.saved_tensors
         S, Prows, ldc, npairs, nneg, groups, has_depth, shp, shp_pos, _, _ = ctx.meta
         code, code_pos = ctx.code_like
         dev = cpan.device
@@ -256,7 +292,8 @@ class _CorrLossFn(torch.autograd.Function):
         B, D, H, W = shp
         need = ctx.needs_input_grad
         d_code = d_code_pos = None
-        common = (NORM_EPS, Prows, ldc, ptr(cpan), ptr(crn), ptr(dC1), ptr(dC2), npairs, _lib.i32_array(groups),
+        common = (NORM_EPS, Prows, ldc, ptr(cpan), ptr(cpan_lo), ptr(crn), ptr(dC1), ptr(dC2), npairs,
+                  _lib.i32_array(groups),
                   _lib.f32_array(scales), 1 if has_depth else 0, ptr(gw), stream_ptr())
         if need[2]:
             d_code = torch.zeros_like(code)

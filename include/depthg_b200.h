@@ -46,6 +46,13 @@ enum {
 /* Pair groups: which scalar of the reference's output tuple a pair feeds. */
 enum { DG_GROUP_INTRA = 0, DG_GROUP_INTER = 1, DG_GROUP_NEG = 2, DG_GROUP_DEPTH = 3, DG_NUM_GROUPS = 4 };
 
+/* Panel formats written by dg_gather_norm and consumed by dg_corr_loss.
+ *   F32         : fp32 rows (generic CUDA-core correlation kernel).
+ *   FEATS_SPLIT : two bf16 panels hi/lo with x ~= hi + lo (tcgen05 kind::f16, 3-term product).
+ *   CODE_SPLIT  : fp32 hi (tf32-rounded) and lo = x - hi (tcgen05 kind::tf32, 3-term product)
+ *                 plus transposed bf16 hi/lo panels [channel 128][point 128] for the gradient GEMMs. */
+enum { DG_PANEL_F32 = 0, DG_PANEL_FEATS_SPLIT = 1, DG_PANEL_CODE_SPLIT = 2 };
+
 /* Flags of ContrastiveCorrelationLoss.helper (src/modules.py:1231-1254). */
 enum { DG_FLAG_POINTWISE = 1, DG_FLAG_ZERO_CLAMP = 2, DG_FLAG_STABALIZE = 4 };
 
@@ -104,12 +111,15 @@ DG_API int dg_depth_sign(const float* depth, int B, int Hd, int Wd, int S, float
  *   out      : [nslots,B,Prows,ld]; row p = h*S+w holds the sample at coordinate
  *              index w*S+h (the reference's axis swap), L2-normalised over C
  *              with eps; rows >= S*S and columns >= C are zero-filled.
+ *   format   : DG_PANEL_*; element type / meaning of out, out_lo, outT_hi, outT_lo
+ *              as described at the enum (unused ones NULL).
  *   rnorm    : [nslots,B,Prows]  1/max(||x||,eps) per row (needed by backward).
  *   meanvec  : [nslots,B,ld]     mean over the S*S rows of the normalised panel
  *              (NULL to skip; needed for pointwise centring). */
 DG_API int dg_gather_norm(const float* t, const int64_t* strides, int B, int C, int H, int W, const float* coords, int S,
                    int nsets, const int32_t* set_coord, const int32_t* set_slot, const int64_t* perm, float eps,
-                   int Prows, int ld, float* out, float* rnorm, float* meanvec, dg_stream_t stream);
+                   int Prows, int ld, int format, void* out, void* out_lo, void* outT_hi, void* outT_lo,
+                   float* rnorm, float* meanvec, dg_stream_t stream);
 
 /* Backward of dg_gather_norm for the code tensors: combines the unit
  * gradients of dg_corr_loss with the upstream scalars, goes back through the
@@ -117,7 +127,8 @@ DG_API int dg_gather_norm(const float* t, const int64_t* strides, int B, int C, 
  * caller zero-initialises `grad`).
  *
  *   grad     : gradient w.r.t. the source tensor, same logical shape/strides as t.
- *   cn,rnorm : the code panels / reciprocal norms written by the forward gather.
+ *   cn,cn_lo,rnorm : the code panels (cn_lo NULL for DG_PANEL_F32; hi + lo for CODE_SPLIT) and
+ *              reciprocal norms written by the forward gather.
  *   dC1,dC2  : [npairs+1,B,Prows,ld] unit gradients from dg_corr_loss.
  *   group_w  : device [DG_NUM_GROUPS] upstream gradients of the four scalar losses.
  *   pair_group (host [npairs]) / pair_scale (host [npairs]): group of pair k and
@@ -127,7 +138,8 @@ DG_API int dg_gather_norm(const float* t, const int64_t* strides, int B, int C, 
  * Slot 0 rows receive sum_k w_k dC1[k] + w_0 dC2[0] (+ depth), slot s>0 rows w_s dC2[s]. */
 DG_API int dg_gather_norm_bwd(float* grad, const int64_t* strides, int B, int C, int H, int W, const float* coords, int S,
                        int nsets, const int32_t* set_coord, const int32_t* set_slot, const int64_t* perm, float eps,
-                       int Prows, int ld, const float* cn, const float* rnorm, const float* dC1, const float* dC2,
+                       int Prows, int ld, const float* cn, const float* cn_lo, const float* rnorm, const float* dC1,
+                       const float* dC2,
                        int npairs, const int32_t* pair_group, const float* pair_scale, int has_depth,
                        const float* group_w, dg_stream_t stream);
 
@@ -136,24 +148,39 @@ DG_API int dg_gather_norm_bwd(float* grad, const int64_t* strides, int B, int C,
  * every pair and depth_feature_correlation() (src/modules.py:1231-1278) plus the
  * einsum of tensor_correlation (:797-809) without materialising fd/cd.
  *
- *   fn  : [npairs,B,Prows,ldf] normalised backbone-feature panels; pair k
- *         correlates slot 0 (first operand) with slot k (k = 0 is the intra pair).
- *   cn  : [npairs,B,Prows,ldc] normalised code panels, same slot convention.
+ *   pan : the normalised panels written by dg_gather_norm, slot k = second operand of
+ *         pair k, slot 0 = first operand of every pair (k = 0 is the intra pair):
+ *           format DG_PANEL_F32   : f_hi = fp32 [npairs,B,Prows,ldf], c_hi = fp32 [npairs,B,Prows,ldc]
+ *                                   (generic CUDA-core kernel, any S);
+ *           split formats         : f_hi/f_lo bf16 [npairs,B,128,ldf]; c_hi/c_lo fp32 [npairs,B,128,ldc];
+ *                                   ct_hi/ct_lo bf16 [npairs,B,128,128] (tcgen05 kernel, S*S <= 128).
  *   fmean : [npairs,B,ldf] panel row means (only read with DG_FLAG_POINTWISE).
  *   dsign : [B,Prows] depth signs from dg_depth_sign, or NULL for no depth term.
  *   pair_shift / pair_group : host [npairs].
  *   out8  : device [8] = (intra loss, intra cd mean, inter loss, inter cd mean,
- *           neg loss mean, neg cd mean, depth loss, depth dd mean).
+ *           neg loss mean, neg cd mean, depth loss, depth dd mean); NaN if the tcgen05
+ *           pipeline reported a timeout.
  *   dC1,dC2 : out [npairs+1,B,Prows,ldc] unit gradients of each pair's MEAN loss
  *           w.r.t. its first / second normalised code operand (index npairs = depth).
  *   cd_out, loss_out : optional dense [npairs,B,P,P] (NULL to skip) — the
  *           reference's 5-D tensors, [b,h,w,i,j] flattened; dd_out optional [B,P,P].
+ *   fd_dbg : optional [npairs,B,128,128] raw feature correlations (tcgen05 path; tests).
  *   ws : workspace of dg_corr_loss_workspace_bytes(). */
+typedef struct dg_panels {
+  int format; /* DG_PANEL_F32, or DG_PANEL_FEATS_SPLIT / DG_PANEL_CODE_SPLIT for the split set */
+  const void* f_hi;
+  const void* f_lo;
+  const void* c_hi;
+  const void* c_lo;
+  const void* ct_hi;
+  const void* ct_lo;
+} dg_panels_t;
+
 DG_API size_t dg_corr_loss_workspace_bytes(int npairs, int B, int P);
-DG_API int dg_corr_loss(const float* fn, const float* cn, const float* fmean, const float* dsign, int npairs, int B, int P,
-                 int Prows, int C, int ldf, int D, int ldc, const float* pair_shift, const int32_t* pair_group,
-                 float depth_shift, int flags, float* out8, float* dC1, float* dC2, float* cd_out, float* loss_out,
-                 float* dd_out, void* ws, size_t ws_bytes, dg_stream_t stream);
+DG_API int dg_corr_loss(const dg_panels_t* pan, const float* fmean, const float* dsign, int npairs, int B, int P,
+                        int Prows, int C, int ldf, int D, int ldc, const float* pair_shift, const int32_t* pair_group,
+                        float depth_shift, int flags, float* out8, float* dC1, float* dC2, float* cd_out,
+                        float* loss_out, float* dd_out, float* fd_dbg, void* ws, size_t ws_bytes, dg_stream_t stream);
 
 /* ---------------------------------------------------------------------------
  * Cosine-similarity k-nearest-neighbour build.  Replaces the einsum + topk

@@ -290,3 +290,68 @@ def test_pool_normalize_matches_get_feats():
         if cl:
             x = x.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
         assert rel_err(pool_normalize(x).cpu().numpy(), want) < 1e-6
+
+
+# ------------------------------------------------------------------ tcgen05 kernel vs the generic CUDA-core kernel
+def _run_both_kernels(name, monkeypatch):
+    """Same inputs through the tcgen05 kernel and (DEPTHG_B200_CORR=simt) the generic kernel."""
+    from depthg_b200 import modules as M
+    from tests.gpu_helpers import run_cuda_loss
+    res = {}
+    for kind in ("umma", "simt"):
+        if kind == "simt":
+            monkeypatch.setenv("DEPTHG_B200_CORR", "simt")
+        else:
+            monkeypatch.delenv("DEPTHG_B200_CORR", raising=False)
+        M._CorrLossFn.debug_fd = (kind == "umma")
+        try:
+            cfg, t, r = run_cuda_loss(name, materialize=True)
+        finally:
+            M._CorrLossFn.debug_fd = False
+        r["dC1"], r["dC2"] = [x.clone() for x in M._CorrLossFn.last_unit_grads]
+        r["fd"] = M._CorrLossFn.last_fd.clone() if kind == "umma" else None
+        res[kind] = r
+    monkeypatch.delenv("DEPTHG_B200_CORR", raising=False)
+    return cfg, t, res
+
+
+@pytest.mark.parametrize("name", ["small_fps", "small_random_pointwise", "cfg1_vits", "small_fps_noclamp"])
+def test_tcgen05_kernel_matches_generic_kernel_stage_by_stage(name, monkeypatch):
+    from depthg_b200.modules import corr_kernel_choice
+    cfg, t, res = _run_both_kernels(name, monkeypatch)
+    S, D = cfg.feature_samples, t["code"].shape[1]
+    assert corr_kernel_choice(S * S, D) == "umma"
+    u, s = res["umma"], res["simt"]
+    P = S * S
+    # (1) feature correlations straight out of TMEM vs an fp64 product of the oracle's normalised samples
+    c1, c2 = torch.from_numpy(u["coords1"]), torch.from_numpy(u["coords2"])
+    f1 = O.norm(O.sample(t["feats"], c1)).double().flatten(2)            # [B,C,P]
+    f2 = O.norm(O.sample(t["feats_pos"], c2)).double().flatten(2)
+    fd_inter = torch.einsum("bcp,bcq->bpq", f1, f2).numpy()
+    fd_intra = torch.einsum("bcp,bcq->bpq", f1, f1).numpy()
+    got = u["fd"].cpu().numpy()
+    np.testing.assert_allclose(got[0][:, :P, :P], fd_intra, atol=2e-5)
+    np.testing.assert_allclose(got[1][:, :P, :P], fd_inter, atol=2e-5)
+    assert np.abs(got[:, :, P:, :]).max() == 0 and np.abs(got[:, :, :, P:]).max() == 0   # zero padding rows
+    # (2) code correlations (tf32 x3 split must be fp32-grade) and the dense loss tensors
+    for i, atol in ((1, 1e-6), (3, 1e-6), (5, 1e-6), (4, 1e-5)):   # cd tensors fp32-grade; loss carries the bf16x3 fd error
+        np.testing.assert_allclose(u["out"][i].detach().cpu().numpy(), s["out"][i].detach().cpu().numpy(),
+                                   rtol=1e-4, atol=atol)
+    # (3) unit gradients of every pair (and the depth term) from the tensor-core GEMMs
+    for key in ("dC1", "dC2"):
+        a, b_ = u[key].cpu().numpy()[:, :, :P], s[key].cpu().numpy()[:, :, :P]
+        assert np.abs(u[key].cpu().numpy()[:-1, :, P:]).max() == 0
+        for k in range(a.shape[0]):
+            if np.linalg.norm(b_[k]) > 0:
+                assert rel_err(a[k], b_[k]) < 5e-5, (key, k, rel_err(a[k], b_[k]))
+    # (4) end results
+    np.testing.assert_allclose(u["scalars"], s["scalars"], rtol=RTOL, atol=ATOL, equal_nan=True)
+    assert rel_err(u["d_code"], s["d_code"]) < RTOL and rel_err(u["d_code_pos"], s["d_code_pos"]) < RTOL
+
+
+def test_generic_kernel_still_matches_reference_golden(monkeypatch):
+    from tests.gpu_helpers import run_cuda_loss
+    monkeypatch.setenv("DEPTHG_B200_CORR", "simt")
+    for name in ("small_fps", "cfg1_vits", "small_random"):
+        cfg, t, r = run_cuda_loss(name)
+        _check_loss(r, golden("loss_" + name), cfg)

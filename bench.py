@@ -271,59 +271,47 @@ def main():
     ms_per_step = ms / args.steps
     value = world * B * args.steps / (ms / 1e3)
 
-    # ---- per-ABI-call breakdown (same inputs, CUDA events on the launching stream around each C-ABI call)
-    breakdown = {}
-    pending = []
-    # wrap each library function so events bracket it
-    wrapped = {}
-    for name in ("dg_fps_coords", "dg_gather_norm", "dg_depth_sign", "dg_corr_loss", "dg_gather_norm_bwd"):
-        fn = getattr(lib, name)
+    # ---- per-kernel breakdown: the library brackets each of its kernels with CUDA events on the launching stream
+    import ctypes
+    reps = min(args.steps, 20)
+    lib.dg_profile_enable(1)
+    for i in range(reps):
+        step(i)
+    need = lib.dg_profile_collect(None, 0)
+    buf = ctypes.create_string_buffer(need + 16)
+    lib.dg_profile_collect(buf, need + 16)
+    lib.dg_profile_enable(0)
+    breakdown, calls = {}, {}
+    for ln in buf.value.decode().strip().split("\n"):
+        if ln:
+            name, n, us = ln.split("\t")
+            breakdown[name] = float(us) / reps
+            calls[name] = int(n) / reps
 
-        def make(fn=fn, name=name):
-            def call(*a):
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                rc = fn(*a)
-                e1.record()
-                pending.append((name, e0, e1))
-                return rc
-            return call
-        wrapped[name] = make()
-
-    class LibProxy:
-        def __getattr__(self, n):
-            return wrapped.get(n) or getattr(lib, n)
-
-    real_lib_fn = _lib.lib
-    _lib.lib = lambda: LibProxy()
-    try:
-        reps = min(args.steps, 20)
-        for i in range(reps):
-            step(i)
-        torch.cuda.synchronize()
-    finally:
-        _lib.lib = real_lib_fn
-    for name, e0, e1 in pending:
-        breakdown[name] = breakdown.get(name, 0.0) + e0.elapsed_time(e1) * 1e3 / reps
-    calls = {n: sum(1 for p in pending if p[0] == n) // reps for n in breakdown}
-
-    # dominant call and its roofline (algorithmic bytes it is responsible for; DESIGN.md "Roofline accounting")
+    # dominant kernel and its roofline.  Algorithmic bytes per kernel = the part of SURVEY 8(d)'s per-step figure
+    # that kernel is responsible for, plus (for the correlation kernel) the panels it must read once
+    # (DESIGN.md "Roofline accounting").
     HW = CFG2["H"] * CFG2["W"]
-    P, Prows = CFG2["S"] ** 2, 128
     npairs = 2 + CFG2["neg_samples"]
+    Cc, Dd = CFG2["C"], 96
     alg = {
-        "dg_fps_coords": 4 * 2 * B * CFG2["Hd"] * CFG2["Wd"],
-        "dg_gather_norm": 4 * (2 * B * CFG2["C"] * HW + 2 * B * CFG2["D"] * HW),          # sources read once
-        "dg_corr_loss": 4 * npairs * B * Prows * (CFG2["C"] + 2 * 96 + 2 * 96),                 # panels in, unit grads out
-        "dg_gather_norm_bwd": 4 * 2 * B * CFG2["D"] * HW,                                     # code grads written once
-        "dg_depth_sign": 4 * B * P * 4,
+        "fps_kernel": 4 * 2 * B * CFG2["Hd"] * CFG2["Wd"],
+        "gather_norm_kernel": 4 * (2 * B * Cc * HW + 2 * B * CFG2["D"] * HW) + 4 * npairs * B * 128 * (Cc + 3 * Dd),
+        "corr_umma_kernel": 4 * npairs * B * 128 * (2 * Cc + 3 * 2 * Dd) + 4 * 2 * npairs * B * 128 * Dd,
+        "corr_tile_kernel": 4 * npairs * B * 128 * (2 * Cc + 2 * Dd) + 4 * 2 * npairs * B * 128 * Dd,
+        "gather_norm_bwd_kernel": 4 * 2 * B * CFG2["D"] * HW + 4 * 3 * npairs * B * 128 * Dd,
     }
-    dom = max(breakdown, key=breakdown.get)
+    dom = max((k for k in breakdown if k in alg), key=breakdown.get)
     dom_us = breakdown[dom]
     achieved = alg[dom] / (dom_us * 1e-6) / 1e9
     roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
-                "us_per_step": dom_us, "calls_per_step": calls.get(dom)}
+                "us_per_step": dom_us, "launches_per_step": calls.get(dom), "algorithmic_bytes_per_step": alg[dom]}
+    if dom == "corr_umma_kernel":
+        fl = algorithmic_flops(B)
+        roofline["tensor"] = {"flops": fl, "achieved_tflops": fl / (dom_us * 1e-6) / 1e12,
+                              "frac_of_bf16_sustained_div3": fl / (dom_us * 1e-6) / 1e12 / (tf_sust / 3.0),
+                              "note": "fd runs as a 3-product bf16 split, cd as a 3-product tf32 split"}
     step_bytes = algorithmic_bytes(B)
     roofline_step = {"bound": "hbm", "algorithmic_bytes": step_bytes, "achieved": step_bytes / (ms_per_step * 1e-3) / 1e9,
                      "peak": hbm_peak, "unit": "GB/s", "frac": step_bytes / (ms_per_step * 1e-3) / 1e9 / hbm_peak,

@@ -29,6 +29,8 @@ SIGNATURES = {
     "dg_version": (C.c_int, []),
     "dg_last_error_string": (C.c_char_p, []),
     "dg_kernel_launches": (C.c_ulonglong, []),
+    "dg_profile_enable": (C.c_int, [C.c_int]),
+    "dg_profile_collect": (C.c_size_t, [C.c_char_p, C.c_size_t]),
     "dg_panel_ld": (C.c_int, [C.c_int]),
     "dg_panel_rows": (C.c_int, [C.c_int]),
     "dg_fps_coords": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
@@ -43,6 +45,9 @@ SIGNATURES = {
     "dg_corr_loss": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                C.c_int, _c_f32p, _c_i32p, C.c_float, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                C.c_size_t, _vp]),
+    "dg_loss_plan": (C.c_int, [_vp, _vp]),
+    "dg_loss_forward": (C.c_int, [_vp, _vp, _vp]),
+    "dg_loss_backward": (C.c_int, [_vp, _vp, _vp, _vp]),
     "dg_knn_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "dg_knn_topk": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, C.c_size_t, _vp]),
     "dg_pool_normalize": (C.c_int, [_vp, _c_i64p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _vp, _vp]),
@@ -60,6 +65,37 @@ class Panels(C.Structure):
 def make_panels(fmt, f_hi, f_lo, c_hi, c_lo, ct_hi, ct_lo):
     dp = lambda t: None if t is None else t.data_ptr()  # noqa: E731
     return Panels(fmt, dp(f_hi), dp(f_lo), dp(c_hi), dp(c_lo), dp(ct_hi), dp(ct_lo))
+
+
+FLAG_DEPTH_TERM, FLAG_FPS, FLAG_FORCE_SIMT = 8, 16, 32
+_i64x4 = C.c_int64 * 4
+
+
+class LossDesc(C.Structure):
+    """dg_loss_desc_t"""
+    _fields_ = [(n, C.c_int) for n in ("B", "C", "D", "H", "W", "Hd", "Wd", "S", "neg_samples", "flags")] + \
+               [(n, C.c_float) for n in ("pos_intra_shift", "pos_inter_shift", "neg_inter_shift", "depth_feat_shift")]
+
+
+class LossPlan(C.Structure):
+    """dg_loss_plan_t"""
+    _fields_ = [(n, C.c_size_t) for n in ("total", "coords", "frn", "fmean", "crn", "f_hi", "f_lo", "c_hi", "c_lo",
+                                          "ct_hi", "ct_lo", "dsign", "dC1", "dC2", "ws", "ws_bytes")] + \
+               [(n, C.c_int) for n in ("kernel", "Prows", "ldf", "ldc", "npairs")]
+
+
+class LossIO(C.Structure):
+    """dg_loss_io_t"""
+    _fields_ = [("feats", _vp), ("feats_pos", _vp), ("code", _vp), ("code_pos", _vp),
+                ("feats_strides", _i64x4), ("feats_pos_strides", _i64x4), ("code_strides", _i64x4),
+                ("code_pos_strides", _i64x4), ("depth", _vp), ("depth_pos", _vp), ("coords", _vp), ("perms", _vp),
+                ("arena", _vp), ("out8", _vp), ("cd_out", _vp), ("loss_out", _vp), ("dd_out", _vp), ("fd_dbg", _vp)]
+
+
+class LossGrads(C.Structure):
+    """dg_loss_grads_t"""
+    _fields_ = [("g", _vp * 4), ("d_code", _vp), ("d_code_pos", _vp), ("d_code_strides", _i64x4),
+                ("d_code_pos_strides", _i64x4)]
 
 
 _lib = None

@@ -1,7 +1,11 @@
 // Library-level entry points: version and the per-thread error text.
 #include <stdarg.h>
+#include <string.h>
 
 #include <atomic>
+#include <map>
+#include <string>
+#include <vector>
 
 #include "common.cuh"
 
@@ -16,8 +20,69 @@ void set_error(const char* fmt, ...) {
 }
 static std::atomic<unsigned long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+// ---- optional per-kernel event timing (diagnostics for bench.py; single-threaded use) ----
+struct ProfRec {
+  const char* name;
+  cudaEvent_t a, b;
+};
+static bool g_prof = false;
+static std::vector<ProfRec> g_recs;
+static cudaEvent_t g_pending = nullptr;
+static cudaStream_t g_pending_stream = nullptr;
+
+void profile_pre(cudaStream_t st) {
+  if (!g_prof) return;
+  cudaEventCreate(&g_pending);
+  cudaEventRecord(g_pending, st);
+  g_pending_stream = st;
+}
+void profile_post(const char* name) {
+  if (!g_prof || !g_pending) return;
+  cudaEvent_t b;
+  cudaEventCreate(&b);
+  cudaEventRecord(b, g_pending_stream);
+  g_recs.push_back({name, g_pending, b});
+  g_pending = nullptr;
+}
 }  // namespace dg
 
 extern "C" int dg_version(void) { return 100; }
 extern "C" const char* dg_last_error_string(void) { return dg::g_err; }
 extern "C" unsigned long long dg_kernel_launches(void) { return dg::g_launches.load(std::memory_order_relaxed); }
+
+extern "C" int dg_profile_enable(int on) {
+  for (auto& r : dg::g_recs) {
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  dg::g_recs.clear();
+  dg::g_prof = on != 0;
+  return DG_OK;
+}
+
+// Synchronises, then writes "name<TAB>launches<TAB>total_us\n" per kernel into buf; returns the bytes needed.
+extern "C" size_t dg_profile_collect(char* buf, size_t buf_bytes) {
+  std::map<std::string, std::pair<int, double>> agg;
+  for (auto& r : dg::g_recs) {
+    cudaEventSynchronize(r.b);
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      auto& e = agg[r.name];
+      e.first += 1;
+      e.second += (double)ms * 1e3;
+    }
+  }
+  std::string out;
+  for (auto& kv : agg) {
+    char line[256];
+    snprintf(line, sizeof line, "%s\t%d\t%.3f\n", kv.first.c_str(), kv.second.first, kv.second.second);
+    out += line;
+  }
+  if (buf && buf_bytes > 0) {
+    size_t n = out.size() < buf_bytes - 1 ? out.size() : buf_bytes - 1;
+    memcpy(buf, out.data(), n);
+    buf[n] = 0;
+  }
+  return out.size() + 1;
+}

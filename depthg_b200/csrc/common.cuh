@@ -14,6 +14,11 @@ namespace dg {
 
 void set_error(const char* fmt, ...);
 void count_launch();  // bumps the process-wide kernel-launch counter (dg_kernel_launches)
+// optional per-kernel CUDA-event timing (dg_profile_enable / dg_profile_collect): no-ops unless enabled
+void profile_pre(cudaStream_t st);
+void profile_post(const char* name);
+
+#define DG_PRE(st) ::dg::profile_pre(st)
 
 #define DG_REQUIRE(cond, code, ...)     \
   do {                                  \
@@ -40,6 +45,7 @@ void count_launch();  // bumps the process-wide kernel-launch counter (dg_kernel
       return DG_ERR_CUDA;                                                                    \
     }                                                                                        \
     ::dg::count_launch();                                                                    \
+    ::dg::profile_post(name);                                                                \
   } while (0)
 
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }

@@ -16,7 +16,7 @@
 // its mean over images) so no second pass over fd is needed; the reference's extra
 // "- fd.mean()" after centring is float noise (~1e-10) and is dropped.
 // This generic-shape kernel computes on the fp32 CUDA cores.
-#include "common.cuh"
+#include "kernels.cuh"
 
 namespace dg {
 
@@ -380,26 +380,68 @@ int launch_corr_finalize(const float* partials, int npairs, int B, int P, const 
   FinalizeParams fp;
   fp.npairs = npairs; fp.B = B; fp.P = P; fp.has_depth = has_depth; fp.n_pt = n_pt;
   for (int k = 0; k < npairs; ++k) fp.group[k] = group[k];
+  DG_PRE(st);
   corr_finalize_kernel<<<1, 256, 0, st>>>(partials, err, out8, fp);
   DG_LAUNCH_OK("corr_finalize_kernel");
   return DG_OK;
 }
 
-int corr_loss_umma(const dg_panels_t* pan, const float* fmean, const float* dsign, int npairs, int B, int P, int ldf,
-                   int ldc, const float* pair_shift, const int32_t* pair_group, float depth_shift, int flags,
-                   float* out8, float* dC1, float* dC2, float* cd_out, float* loss_out, float* dd_out, float* fd_dbg,
-                   void* ws, cudaStream_t st);
+size_t corr_workspace_bytes(int npairs, int B, int P) {
+  if (npairs <= 0 || B <= 0 || P <= 0) return 0;
+  const size_t Prows = (size_t)round_up(P, 64);
+  const size_t n_pt = Prows / TM;
+  size_t floats = (size_t)npairs * B * Prows + (size_t)npairs * B + (size_t)npairs * B * n_pt * 4;
+  size_t bytes = floats * sizeof(float) + 1024;  // covers the tcgen05 path too (header + dots + partials)
+  return (bytes + 255) / 256 * 256;
+}
+
+int corr_loss_simt(const float* fn, const float* cn, const float* fmean, const float* dsign, int npairs, int B, int P,
+                   int Prows, int ldf, int ldc, const float* pair_shift, const int32_t* pair_group, float depth_shift,
+                   int flags, float* out8, float* dC1, float* dC2, float* cd_out, float* loss_out, float* dd_out,
+                   void* ws, cudaStream_t st) {
+  const int n_pt = Prows / TM;
+  CorrParams prm;
+  prm.fn = fn;
+  prm.cn = cn;
+  prm.dsign = dsign;
+  float* wsf = static_cast<float*>(ws);
+  float* rowmean = wsf;
+  float* bsum = rowmean + (size_t)npairs * B * Prows;
+  prm.rowmean = rowmean;
+  prm.bsum = bsum;
+  prm.partials = bsum + (size_t)npairs * B;
+  prm.npairs = npairs; prm.B = B; prm.P = P; prm.Prows = Prows; prm.ldf = ldf; prm.ldc = ldc; prm.flags = flags;
+  prm.has_depth = dsign != nullptr;
+  prm.depth_shift = depth_shift;
+  prm.inv_cnt = 1.0f / ((float)B * (float)P * (float)P);
+  for (int k = 0; k < npairs; ++k) {
+    prm.shift[k] = pair_shift[k];
+    prm.group[k] = pair_group[k];
+  }
+  prm.dC1 = dC1; prm.dC2 = dC2; prm.cd_out = cd_out; prm.loss_out = loss_out; prm.dd_out = dd_out; prm.out8 = out8;
+
+  if (flags & DG_FLAG_POINTWISE) {
+    DG_PRE(st);
+    pair_means_kernel<<<npairs * B, 256, (size_t)ldf * sizeof(float), st>>>(fn, fmean, B, P, Prows, ldf, rowmean, bsum);
+    DG_LAUNCH_OK("pair_means_kernel");
+  }
+  const size_t slab = (size_t)B * Prows * ldc * sizeof(float);
+  DG_CUDA_OK(cudaMemsetAsync(dC2, 0, slab * (npairs + 1), st));
+  const size_t smem = ((size_t)2 * KC * ASTR + (size_t)TM * USTR + (size_t)2 * TM * (ldc + 1)) * sizeof(float);
+  static size_t configured = 0;
+  if (smem > configured) {
+    DG_CUDA_OK(cudaFuncSetAttribute(corr_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  DG_PRE(st);
+  corr_tile_kernel<<<dim3(n_pt, npairs * B), CORR_THREADS, smem, st>>>(prm);
+  DG_LAUNCH_OK("corr_tile_kernel");
+  return launch_corr_finalize(prm.partials, npairs, B, P, pair_group, prm.has_depth, nullptr, out8, n_pt, st);
+}
 
 }  // namespace dg
 
-extern "C" size_t dg_corr_loss_workspace_bytes(int npairs, int B, int P) {
-  if (npairs <= 0 || B <= 0 || P <= 0) return 0;
-  const size_t Prows = (size_t)dg::round_up(P, 64);
-  const size_t n_pt = Prows / dg::TM;
-  size_t floats = (size_t)npairs * B * Prows + (size_t)npairs * B + (size_t)npairs * B * n_pt * 4;
-  size_t bytes = floats * sizeof(float) + 1024;  // covers the tcgen05 path too (512 B header + partials)
-  return (bytes + 255) / 256 * 256;
-}
+extern "C" size_t dg_corr_loss_workspace_bytes(int npairs, int B, int P) { return dg::corr_workspace_bytes(npairs, B, P); }
 
 extern "C" int dg_corr_loss(const dg_panels_t* pan, const float* fmean, const float* dsign, int npairs, int B, int P,
                             int Prows, int C, int ldf, int D, int ldc, const float* pair_shift,
@@ -431,38 +473,7 @@ extern "C" int dg_corr_loss(const dg_panels_t* pan, const float* fmean, const fl
   }
   DG_REQUIRE(pan->format == DG_PANEL_F32, DG_ERR_INVALID, "dg_corr_loss: unknown panel format %d", pan->format);
   DG_REQUIRE(Prows == round_up(P, 64), DG_ERR_INVALID, "dg_corr_loss: Prows must be dg_panel_rows(P)");
-  const float* fn = static_cast<const float*>(pan->f_hi);
-  const float* cn = static_cast<const float*>(pan->c_hi);
-  const int n_pt = Prows / TM;
-  CorrParams prm;
-  prm.fn = fn;
-  prm.cn = cn;
-  prm.dsign = dsign;
-  float* wsf = static_cast<float*>(ws);
-  float* rowmean = wsf;
-  float* bsum = rowmean + (size_t)npairs * B * Prows;
-  prm.rowmean = rowmean;
-  prm.bsum = bsum;
-  prm.partials = bsum + (size_t)npairs * B;
-  prm.npairs = npairs; prm.B = B; prm.P = P; prm.Prows = Prows; prm.ldf = ldf; prm.ldc = ldc; prm.flags = flags;
-  prm.has_depth = dsign != nullptr;
-  prm.depth_shift = depth_shift;
-  prm.inv_cnt = 1.0f / ((float)B * (float)P * (float)P);
-  for (int k = 0; k < npairs; ++k) {
-    prm.shift[k] = pair_shift[k];
-    prm.group[k] = pair_group[k];
-  }
-  prm.dC1 = dC1; prm.dC2 = dC2; prm.cd_out = cd_out; prm.loss_out = loss_out; prm.dd_out = dd_out; prm.out8 = out8;
-
-  if (flags & DG_FLAG_POINTWISE) {
-    pair_means_kernel<<<npairs * B, 256, (size_t)ldf * sizeof(float), st>>>(fn, fmean, B, P, Prows, ldf, rowmean, bsum);
-    DG_LAUNCH_OK("pair_means_kernel");
-  }
-  const size_t slab = (size_t)B * Prows * ldc * sizeof(float);
-  DG_CUDA_OK(cudaMemsetAsync(dC2, 0, slab * (npairs + 1), st));
-  const size_t smem = ((size_t)2 * KC * ASTR + (size_t)TM * USTR + (size_t)2 * TM * (ldc + 1)) * sizeof(float);
-  DG_CUDA_OK(cudaFuncSetAttribute(corr_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  corr_tile_kernel<<<dim3(n_pt, npairs * B), CORR_THREADS, smem, st>>>(prm);
-  DG_LAUNCH_OK("corr_tile_kernel");
-  return launch_corr_finalize(prm.partials, npairs, B, P, pair_group, prm.has_depth, nullptr, out8, n_pt, st);
+  return corr_loss_simt(static_cast<const float*>(pan->f_hi), static_cast<const float*>(pan->c_hi), fmean, dsign, npairs,
+                        B, P, Prows, ldf, ldc, pair_shift, pair_group, depth_shift, flags, out8, dC1, dC2, cd_out,
+                        loss_out, dd_out, ws, st);
 }

@@ -20,9 +20,7 @@
 //
 // Every mbarrier wait is bounded; on a timeout the CTA raises an error flag (the losses
 // come back NaN) instead of hanging the GPU.
-#include <cuda_bf16.h>
-
-#include "common.cuh"
+#include "kernels.cuh"
 #include "umma.cuh"
 
 namespace dg {
@@ -41,7 +39,7 @@ struct UmmaParams {
   CUtensorMap tm_chi, tm_clo;  // f32  [npairs*B*128, ldc]   box 32 x 128, SWIZZLE_128B
   CUtensorMap tm_thi, tm_tlo;  // bf16 [npairs*B*128, 128]   box 64 x 128, SWIZZLE_128B (transposed code)
   const float* dsign;          // [B,128] or null
-  const float* old_mean;       // [npairs] (pointwise) or null
+  const float* dots;           // [npairs,B] <mean row of F1[b], mean row of F2[k,b]> (pointwise) or null
   int npairs, B, P, ldf, ldc, flags, has_depth;
   float depth_shift, inv_cnt;
   float shift[DG_MAX_PAIRS];
@@ -242,7 +240,11 @@ __global__ void __launch_bounds__(UM_THREADS, 1) corr_umma_kernel(const __grid_c
     const float lo = (prm.flags & DG_FLAG_ZERO_CLAMP) ? 0.f : -9999.f;
     const float hi = (prm.flags & DG_FLAG_STABALIZE) ? 0.8f : __int_as_float(0x7f800000);
     const float shift = prm.shift[k];
-    const float old_mean = (pointwise && prm.old_mean) ? __ldg(prm.old_mean + k) : 0.f;
+    float old_mean = 0.f;  // mean of fd over (b,p,q) of this pair = mean_b <mean row F1[b], mean row F2[k,b]>
+    if (pointwise && prm.dots) {
+      for (int bb = 0; bb < prm.B; ++bb) old_mean += __ldg(prm.dots + (size_t)k * prm.B + bb);
+      old_mean /= (float)prm.B;
+    }
     const float sp = depth_round ? __ldg(prm.dsign + (size_t)b * 128 + p) : 0.f;
     float sum_loss = 0.f, sum_cd = 0.f, sum_dloss = 0.f, sum_dd = 0.f;
     float v[32], c[32];
@@ -359,26 +361,19 @@ __global__ void __launch_bounds__(UM_THREADS, 1) corr_umma_kernel(const __grid_c
   if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
-// old_mean[k] = mean_b < mean_p F1n[b,p,:], mean_q F2n[k,b,q,:] >   (= mean of fd over b,p,q)
-__global__ void __launch_bounds__(256) pair_oldmean_kernel(const float* __restrict__ fmean, int B, int ldf,
-                                                           float* __restrict__ old_mean) {
-  __shared__ float red[8];
-  const int k = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float acc = 0.f;
-  for (int b = warp; b < B; b += 8) {
-    const float* m1 = fmean + (size_t)b * ldf;
-    const float* m2 = fmean + ((size_t)k * B + b) * ldf;
-    float s = 0.f;
-    for (int c = lane; c < ldf; c += 32) s += __ldg(m1 + c) * __ldg(m2 + c);
-    acc += warp_sum(s);
-  }
-  if (lane == 0) red[warp] = acc;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float t = 0.f;
-    for (int w = 0; w < 8; ++w) t += red[w];
-    old_mean[k] = t / (float)B;
-  }
+// dots[k,b] = < mean_p F1n[b,p,:], mean_q F2n[k,b,q,:] >  (one warp each); block 0 also clears the error flag
+__global__ void __launch_bounds__(256) pair_dots_kernel(const float* __restrict__ fmean, int npairs, int B, int ldf,
+                                                        float* __restrict__ dots, int* __restrict__ err) {
+  if (blockIdx.x == 0 && threadIdx.x == 0 && err) *err = 0;
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= npairs * B || fmean == nullptr) return;
+  const int k = w / B, b = w - k * B;
+  const float* m1 = fmean + (size_t)b * ldf;
+  const float* m2 = fmean + ((size_t)k * B + b) * ldf;
+  float s = 0.f;
+  for (int c = lane; c < ldf; c += 32) s += __ldg(m1 + c) * __ldg(m2 + c);
+  s = warp_sum(s);
+  if (lane == 0) dots[w] = s;
 }
 
 // ------------------------------------------------------------------------ host side
@@ -412,10 +407,6 @@ static int make_map_2d(CUtensorMap* m, CUtensorMapDataType dt, int elt_bytes, co
   return DG_OK;
 }
 
-// declared in corr_loss.cu: folds partial sums into out8 (n_pt = 1 here)
-int launch_corr_finalize(const float* partials, int npairs, int B, int P, const int32_t* group, int has_depth,
-                         const int* err, float* out8, int n_pt, cudaStream_t st);
-
 int corr_loss_umma(const dg_panels_t* pan, const float* fmean, const float* dsign, int npairs, int B, int P, int ldf,
                    int ldc, const float* pair_shift, const int32_t* pair_group, float depth_shift, int flags,
                    float* out8, float* dC1, float* dC2, float* cd_out, float* loss_out, float* dd_out, float* fd_dbg,
@@ -429,13 +420,13 @@ int corr_loss_umma(const dg_panels_t* pan, const float* fmean, const float* dsig
   if ((rc = make_map_2d(&prm.tm_clo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, pan->c_lo, ldc, rows, 32, 128, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   if ((rc = make_map_2d(&prm.tm_thi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, pan->ct_hi, 128, rows, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   if ((rc = make_map_2d(&prm.tm_tlo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, pan->ct_lo, 128, rows, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
-  // workspace: [err int (256 B)][old_mean npairs floats (256 B)][partials npairs*B*4 floats]
+  // workspace: [err int (256 B)][dots npairs*B floats, padded to 256 B][partials npairs*B*4 floats]
   int* err = static_cast<int*>(ws);
-  float* old_mean = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + 256);
-  float* partials = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + 512);
-  DG_CUDA_OK(cudaMemsetAsync(ws, 0, 512, st));
+  float* dots = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + 256);
+  const size_t dots_bytes = ((size_t)npairs * B * sizeof(float) + 255) / 256 * 256;
+  float* partials = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + 256 + dots_bytes);
   prm.dsign = dsign;
-  prm.old_mean = (flags & DG_FLAG_POINTWISE) ? old_mean : nullptr;
+  prm.dots = (flags & DG_FLAG_POINTWISE) ? dots : nullptr;
   prm.npairs = npairs; prm.B = B; prm.P = P; prm.ldf = ldf; prm.ldc = ldc; prm.flags = flags;
   prm.has_depth = dsign != nullptr;
   prm.depth_shift = depth_shift;
@@ -443,15 +434,18 @@ int corr_loss_umma(const dg_panels_t* pan, const float* fmean, const float* dsig
   for (int k = 0; k < npairs; ++k) prm.shift[k] = pair_shift[k];
   prm.dC1 = dC1; prm.dC2 = dC2; prm.partials = partials;
   prm.cd_out = cd_out; prm.loss_out = loss_out; prm.dd_out = dd_out; prm.fd_dbg = fd_dbg; prm.err = err;
-  if (flags & DG_FLAG_POINTWISE) {
-    pair_oldmean_kernel<<<npairs, 256, 0, st>>>(fmean, B, ldf, old_mean);
-    DG_LAUNCH_OK("pair_oldmean_kernel");
+  {
+    const float* fm = (flags & DG_FLAG_POINTWISE) ? fmean : nullptr;
+    DG_PRE(st);
+    pair_dots_kernel<<<ceil_div(npairs * B * 32, 256), 256, 0, st>>>(fm, npairs, B, ldf, dots, err);
+    DG_LAUNCH_OK("pair_dots_kernel");
   }
   static bool attr_set = false;
   if (!attr_set) {
     DG_CUDA_OK(cudaFuncSetAttribute(corr_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, UM_SMEM));
     attr_set = true;
   }
+  DG_PRE(st);
   corr_umma_kernel<<<npairs * B, UM_THREADS, UM_SMEM, st>>>(prm);
   DG_LAUNCH_OK("corr_umma_kernel");
   return launch_corr_finalize(partials, npairs, B, P, pair_group, prm.has_depth, err, out8, 1, st);

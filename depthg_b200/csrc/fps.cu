@@ -16,7 +16,7 @@
 //   4. the selection ORDER is discarded like the reference does: a block scan of
 //      the taken flags emits the picks in raster order as indices and as
 //      normalised (row/H, col/W) coordinates.
-#include "common.cuh"
+#include "kernels.cuh"
 
 namespace dg {
 
@@ -186,12 +186,8 @@ __global__ void depth_sign_kernel(const float* __restrict__ depth, int B, int Hd
   out[t] = v / fmaxf(fabsf(v), eps);
 }
 
-}  // namespace dg
-
-extern "C" int dg_fps_coords(const float* depth_a, const float* depth_b, int B, int Hd, int Wd, int H, int W, int S,
-                             float factor, float far_plane, int affine, float* coords, int32_t* idx,
-                             dg_stream_t stream) {
-  using namespace dg;
+int launch_fps(const float* depth_a, const float* depth_b, int B, int Hd, int Wd, int H, int W, int S, float factor,
+               float far_plane, int affine, float* coords, int32_t* idx, cudaStream_t st) {
   DG_REQUIRE(depth_a && coords, DG_ERR_INVALID, "dg_fps_coords: null pointer");
   DG_REQUIRE(B > 0 && Hd > 0 && Wd > 0 && H > 0 && W > 0 && S > 0, DG_ERR_INVALID, "dg_fps_coords: bad sizes");
   DG_REQUIRE(H <= Hd && W <= Wd, DG_ERR_UNSUPPORTED, "dg_fps_coords: pooling must not upsample (%dx%d -> %dx%d)", Hd,
@@ -201,15 +197,17 @@ extern "C" int dg_fps_coords(const float* depth_a, const float* depth_b, int B, 
   DG_REQUIRE(npts <= 4096, DG_ERR_UNSUPPORTED, "dg_fps_coords: H*W=%d > 4096 not supported", npts);
   const int nimg = depth_b ? 2 * B : B;
   const size_t smem = (size_t)npts * (3 * sizeof(float) + 1);
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (npts <= 4 * FPS_THREADS) {
+    DG_PRE(st);
     fps_kernel<4><<<nimg, FPS_THREADS, smem, st>>>(depth_a, depth_b, B, Hd, Wd, H, W, S * S, factor, far_plane,
                                                    affine, coords, idx);
   } else if (npts <= 8 * FPS_THREADS) {
+    DG_PRE(st);
     fps_kernel<8><<<nimg, FPS_THREADS, smem, st>>>(depth_a, depth_b, B, Hd, Wd, H, W, S * S, factor, far_plane,
                                                    affine, coords, idx);
   } else {
     DG_CUDA_OK(cudaFuncSetAttribute(fps_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DG_PRE(st);
     fps_kernel<16><<<nimg, FPS_THREADS, smem, st>>>(depth_a, depth_b, B, Hd, Wd, H, W, S * S, factor, far_plane,
                                                     affine, coords, idx);
   }
@@ -217,14 +215,27 @@ extern "C" int dg_fps_coords(const float* depth_a, const float* depth_b, int B, 
   return DG_OK;
 }
 
-extern "C" int dg_depth_sign(const float* depth, int B, int Hd, int Wd, int S, float eps, int out_pitch, float* out,
-                             dg_stream_t stream) {
-  using namespace dg;
+int launch_depth_sign(const float* depth, int B, int Hd, int Wd, int S, float eps, int out_pitch, float* out,
+                      cudaStream_t st) {
   DG_REQUIRE(depth && out, DG_ERR_INVALID, "dg_depth_sign: null pointer");
   DG_REQUIRE(B > 0 && Hd > 0 && Wd > 0 && S > 0 && out_pitch >= S * S, DG_ERR_INVALID, "dg_depth_sign: bad sizes");
   const int n = B * out_pitch;
-  depth_sign_kernel<<<ceil_div(n, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(depth, B, Hd, Wd, S, eps,
-                                                                                          out_pitch, out);
+  DG_PRE(st);
+  depth_sign_kernel<<<ceil_div(n, 256), 256, 0, st>>>(depth, B, Hd, Wd, S, eps, out_pitch, out);
   DG_LAUNCH_OK("depth_sign_kernel");
   return DG_OK;
+}
+
+}  // namespace dg
+
+extern "C" int dg_fps_coords(const float* depth_a, const float* depth_b, int B, int Hd, int Wd, int H, int W, int S,
+                             float factor, float far_plane, int affine, float* coords, int32_t* idx,
+                             dg_stream_t stream) {
+  return dg::launch_fps(depth_a, depth_b, B, Hd, Wd, H, W, S, factor, far_plane, affine, coords, idx,
+                        reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int dg_depth_sign(const float* depth, int B, int Hd, int Wd, int S, float eps, int out_pitch, float* out,
+                             dg_stream_t stream) {
+  return dg::launch_depth_sign(depth, B, Hd, Wd, S, eps, out_pitch, out, reinterpret_cast<cudaStream_t>(stream));
 }

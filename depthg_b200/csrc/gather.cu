@@ -12,9 +12,7 @@
 // channels (128-bit loads when the channel stride is 1), so a channels-last
 // source is read in whole 128-byte lines and every panel row is written once,
 // coalesced.  HBM-bound: no data reuse beyond the four bilinear corners.
-#include <cuda_bf16.h>
-
-#include "common.cuh"
+#include "kernels.cuh"
 
 namespace dg {
 
@@ -27,28 +25,6 @@ __device__ __forceinline__ float umma_tf32(float x) {  // round-to-nearest tf32 
 constexpr int GATHER_THREADS = 512;
 constexpr int GATHER_WARPS = GATHER_THREADS / 32;
 
-struct SetTable {
-  int32_t coord[DG_MAX_SETS];
-  int32_t slot[DG_MAX_SETS];
-};
-
-enum { FMT_F32 = 0, FMT_FEATS_SPLIT = 1, FMT_CODE_SPLIT = 2 };
-
-struct GatherOut {
-  // FMT_F32        : out (fp32 [slot,b,Prows,ld])
-  // FMT_FEATS_SPLIT: hi16/lo16 (bf16 [slot,b,Prows,ld]) : x ~= hi + lo
-  // FMT_CODE_SPLIT : out = tf32-rounded hi, out_lo = x - hi (fp32 [slot,b,Prows,ld]);
-  //                  t_hi16/t_lo16 (bf16 [slot,b,128,128]) transposed: row = channel, col = point
-  float* out;
-  float* out_lo;
-  __nv_bfloat16* hi16;
-  __nv_bfloat16* lo16;
-  __nv_bfloat16* t_hi16;
-  __nv_bfloat16* t_lo16;
-  float* rnorm;
-  float* meanvec;
-};
-
 __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& h, __nv_bfloat16& l) {
   h = __float2bfloat16_rn(v);
   l = __float2bfloat16_rn(v - __bfloat162float(h));
@@ -58,9 +34,9 @@ __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& h, __nv_bfloa
 //               (+ FMT_CODE_SPLIT: normalised tile [128][ld+1] for the transposed write-out)
 template <int FMT>
 __global__ void __launch_bounds__(GATHER_THREADS)
-    gather_norm_kernel(const float* __restrict__ t, int64_t sb, int64_t sc, int64_t sh, int64_t sw, int B, int C, int H,
-                       int W, const float* __restrict__ coords, int S, SetTable sets, const int64_t* __restrict__ perm,
-                       float eps, int Prows, int ld, GatherOut o) {
+    gather_norm_kernel(const __grid_constant__ SetTable sets, int B, int C, int H, int W,
+                       const float* __restrict__ coords, int S, const int64_t* __restrict__ perms, float eps, int Prows,
+                       int ld, GatherOut o) {
   extern __shared__ float gsm[];
   const int set = blockIdx.x / B, b = blockIdx.x - set * B;
   const int P = S * S;
@@ -68,10 +44,13 @@ __global__ void __launch_bounds__(GATHER_THREADS)
   float* row = gsm + (size_t)warp * ld;
   float* macc = gsm + (size_t)(GATHER_WARPS + warp) * ld;
   float* tile = gsm + (size_t)2 * GATHER_WARPS * ld;  // FMT_CODE_SPLIT only: [128][ld+1]
-  const int slot = sets.slot[set];
-  const int64_t src = perm ? perm[(size_t)set * B + b] : (int64_t)b;
+  const SetDesc& sd = sets.s[set];
+  const float* t = sd.src;
+  const int64_t sb = sd.sb, sc = sd.sc, sh = sd.sh, sw = sd.sw;
+  const int slot = sd.slot;
+  const int64_t src = sd.perm_row >= 0 ? perms[(size_t)sd.perm_row * B + b] : (int64_t)b;
   const float* timg = t + src * sb;
-  const float* cset = coords + ((size_t)sets.coord[set] * B + b) * P * 2;
+  const float* cset = coords + ((size_t)sd.coord * B + b) * P * 2;
   const size_t pbase = ((size_t)slot * B + b) * Prows;
   float* rpanel = o.rnorm + pbase;
 
@@ -212,49 +191,50 @@ __global__ void __launch_bounds__(GATHER_THREADS)
   }
 }
 
-struct PairTable {
-  int32_t group[DG_MAX_PAIRS + 1];
-  float scale[DG_MAX_PAIRS + 1];
-};
-
 // One warp per panel row: compose the row's gradient from the unit gradients,
 // back through x/max(||x||,eps), then atomically scatter through the 4 corners.
 __global__ void __launch_bounds__(256)
-    gather_norm_bwd_kernel(float* __restrict__ grad, int64_t sb, int64_t sc, int64_t sh, int64_t sw, int B, int C, int H,
-                           int W, const float* __restrict__ coords, int S, SetTable sets,
-                           const int64_t* __restrict__ perm, float eps, int Prows, int ld, const float* __restrict__ cn,
-                           const float* __restrict__ cn_lo, const float* __restrict__ rnorm, const float* __restrict__ dC1, const float* __restrict__ dC2,
-                           int npairs, PairTable pairs, int has_depth, const float* __restrict__ group_w, int nsets) {
+    gather_norm_bwd_kernel(const __grid_constant__ SetTable sets, int B, int C, int H, int W,
+                           const float* __restrict__ coords, int S, const int64_t* __restrict__ perms, float eps,
+                           int Prows, int ld, const float* __restrict__ cn, const float* __restrict__ cn_lo,
+                           const float* __restrict__ rnorm, const float* __restrict__ dC1,
+                           const float* __restrict__ dC2, int npairs, const __grid_constant__ PairTable pairs,
+                           int has_depth, const __grid_constant__ GroupW gws, int nsets) {
   const int P = S * S;
   const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp_global >= nsets * B * P) return;
   const int set = warp_global / (B * P);
   const int rem = warp_global - set * B * P;
   const int b = rem / P, p = rem - b * P;
-  const int slot = sets.slot[set];
+  const SetDesc& sd = sets.s[set];
+  const int slot = sd.slot;
   const size_t panel = (size_t)B * Prows * ld;
   const size_t rowoff = ((size_t)b * Prows + p) * ld;
   const int R = ld / 32;  // ld is a multiple of 32, <= 8 chunks handled in registers
+  float gw[DG_NUM_GROUPS];
+#pragma unroll
+  for (int g = 0; g < DG_NUM_GROUPS; ++g)
+    gw[g] = gws.arr ? __ldg(gws.arr + g) : (gws.ptr[g] ? __ldg(gws.ptr[g]) : 0.f);
   float g[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) g[j] = 0.f;
   if (slot == 0) {
     for (int k = 0; k < npairs; ++k) {
-      const float wk = __ldg(group_w + pairs.group[k]) * pairs.scale[k];
+      const float wk = gw[pairs.group[k]] * pairs.scale[k];
       const float* a = dC1 + (size_t)k * panel + rowoff;
 #pragma unroll
       for (int j = 0; j < 8; ++j)
         if (j < R) g[j] += wk * __ldg(a + lane + 32 * j);
     }
     {
-      const float w0 = __ldg(group_w + pairs.group[0]) * pairs.scale[0];
+      const float w0 = gw[pairs.group[0]] * pairs.scale[0];
       const float* a = dC2 + rowoff;
 #pragma unroll
       for (int j = 0; j < 8; ++j)
         if (j < R) g[j] += w0 * __ldg(a + lane + 32 * j);
     }
     if (has_depth) {
-      const float wd = __ldg(group_w + DG_GROUP_DEPTH);
+      const float wd = gw[DG_GROUP_DEPTH];
       const float* a1 = dC1 + (size_t)npairs * panel + rowoff;
       const float* a2 = dC2 + (size_t)npairs * panel + rowoff;
 #pragma unroll
@@ -262,7 +242,7 @@ __global__ void __launch_bounds__(256)
         if (j < R) g[j] += wd * (__ldg(a1 + lane + 32 * j) + __ldg(a2 + lane + 32 * j));
     }
   } else {
-    const float ws = __ldg(group_w + pairs.group[slot]) * pairs.scale[slot];
+    const float ws = gw[pairs.group[slot]] * pairs.scale[slot];
     const float* a = dC2 + (size_t)slot * panel + rowoff;
 #pragma unroll
     for (int j = 0; j < 8; ++j)
@@ -284,10 +264,11 @@ __global__ void __launch_bounds__(256)
   if (clamped) dot = 0.f;
 
   const int h = p / S, w = p - h * S;
-  const float* cc = coords + (((size_t)sets.coord[set] * B + b) * P + (w * S + h)) * 2;
+  const float* cc = coords + (((size_t)sd.coord * B + b) * P + (w * S + h)) * 2;
   const Corners k = bilinear_corners(__ldg(cc), __ldg(cc + 1), H, W);
-  const int64_t src = perm ? perm[(size_t)set * B + b] : (int64_t)b;
-  float* g00 = grad + src * sb + k.y0 * sh + k.x0 * sw;
+  const int64_t src = sd.perm_row >= 0 ? perms[(size_t)sd.perm_row * B + b] : (int64_t)b;
+  const int64_t sb = sd.sb, sc = sd.sc, sh = sd.sh, sw = sd.sw;
+  float* g00 = const_cast<float*>(sd.src) + src * sb + k.y0 * sh + k.x0 * sw;  // sd.src is the gradient tensor here
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int c = lane + 32 * j;
@@ -345,14 +326,55 @@ __global__ void __launch_bounds__(256) pool_normalize_kernel(const float* __rest
   for (int c = threadIdx.x; c < C; c += blockDim.x) out[(size_t)blockIdx.x * C + c] = psm[c] * r;
 }
 
-static int check_sets(const char* fn, int nsets, const int32_t* set_coord, const int32_t* set_slot, SetTable* tab) {
+static int fill_sets(const char* fn, const float* src, const int64_t* strides, int nsets, const int32_t* set_coord,
+                     const int32_t* set_slot, bool has_perm, SetTable* tab) {
   DG_REQUIRE(nsets > 0 && nsets <= DG_MAX_SETS, DG_ERR_INVALID, "%s: nsets=%d out of range", fn, nsets);
   DG_REQUIRE(set_coord && set_slot, DG_ERR_INVALID, "%s: null set tables", fn);
   for (int s = 0; s < nsets; ++s) {
     DG_REQUIRE(set_coord[s] >= 0 && set_slot[s] >= 0, DG_ERR_INVALID, "%s: negative set entry", fn);
-    tab->coord[s] = set_coord[s];
-    tab->slot[s] = set_slot[s];
+    SetDesc& d = tab->s[s];
+    d.src = src;
+    d.sb = strides[0]; d.sc = strides[1]; d.sh = strides[2]; d.sw = strides[3];
+    d.coord = set_coord[s];
+    d.slot = set_slot[s];
+    d.perm_row = has_perm ? s : -1;
   }
+  return DG_OK;
+}
+
+int launch_gather(int fmt, const SetTable& tab, int nsets, int B, int C, int H, int W, const float* coords, int S,
+                  const int64_t* perms, float eps, int Prows, int ld, const GatherOut& o, cudaStream_t st) {
+  size_t smem = (size_t)2 * GATHER_WARPS * ld * sizeof(float);
+  if (fmt == FMT_CODE_SPLIT) smem += (size_t)128 * (ld + 1) * sizeof(float);
+  DG_REQUIRE(smem <= 200 * 1024, DG_ERR_UNSUPPORTED, "gather: C=%d too large for the row staging buffer", C);
+#define DG_GATHER_LAUNCH(F)                                                                                        \
+  do {                                                                                                             \
+    static size_t configured = 0;                                                                                  \
+    if (smem > configured) {                                                                                       \
+      DG_CUDA_OK(cudaFuncSetAttribute(gather_norm_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      configured = smem;                                                                                           \
+    }                                                                                                              \
+    DG_PRE(st);                                                                                                           \
+    gather_norm_kernel<F><<<nsets * B, GATHER_THREADS, smem, st>>>(tab, B, C, H, W, coords, S, perms, eps, Prows, ld, o); \
+  } while (0)
+  if (fmt == FMT_F32) DG_GATHER_LAUNCH(FMT_F32);
+  else if (fmt == FMT_FEATS_SPLIT) DG_GATHER_LAUNCH(FMT_FEATS_SPLIT);
+  else DG_GATHER_LAUNCH(FMT_CODE_SPLIT);
+#undef DG_GATHER_LAUNCH
+  DG_LAUNCH_OK("gather_norm_kernel");
+  return DG_OK;
+}
+
+int launch_gather_bwd(const SetTable& tab, int nsets, int B, int C, int H, int W, const float* coords, int S,
+                      const int64_t* perms, float eps, int Prows, int ld, const float* cn, const float* cn_lo,
+                      const float* rnorm, const float* dC1, const float* dC2, int npairs, const PairTable& pt,
+                      int has_depth, const GroupW& gw, cudaStream_t st) {
+  const long long rows = (long long)nsets * B * S * S;
+  const int blocks = (int)((rows * 32 + 255) / 256);
+  DG_PRE(st);
+  gather_norm_bwd_kernel<<<blocks, 256, 0, st>>>(tab, B, C, H, W, coords, S, perms, eps, Prows, ld, cn, cn_lo, rnorm,
+                                                 dC1, dC2, npairs, pt, has_depth, gw, nsets);
+  DG_LAUNCH_OK("gather_norm_bwd_kernel");
   return DG_OK;
 }
 
@@ -375,11 +397,8 @@ extern "C" int dg_gather_norm(const float* t, const int64_t* strides, int B, int
   DG_REQUIRE(format != DG_PANEL_CODE_SPLIT || (outT_hi && outT_lo && Prows == 128 && ld <= 128), DG_ERR_INVALID,
              "dg_gather_norm: code-split format needs transposed outputs, Prows == 128 and ld <= 128");
   SetTable tab;
-  int rc = check_sets("dg_gather_norm", nsets, set_coord, set_slot, &tab);
+  int rc = fill_sets("dg_gather_norm", t, strides, nsets, set_coord, set_slot, perm != nullptr, &tab);
   if (rc != DG_OK) return rc;
-  size_t smem = (size_t)2 * GATHER_WARPS * ld * sizeof(float);
-  if (format == DG_PANEL_CODE_SPLIT) smem += (size_t)128 * (ld + 1) * sizeof(float);
-  DG_REQUIRE(smem <= 200 * 1024, DG_ERR_UNSUPPORTED, "dg_gather_norm: C=%d too large for the row staging buffer", C);
   GatherOut o;
   o.out = static_cast<float*>(out);
   o.out_lo = static_cast<float*>(out_lo);
@@ -389,26 +408,15 @@ extern "C" int dg_gather_norm(const float* t, const int64_t* strides, int B, int
   o.t_lo16 = static_cast<__nv_bfloat16*>(outT_lo);
   o.rnorm = rnorm;
   o.meanvec = meanvec;
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-#define DG_GATHER_LAUNCH(F)                                                                                          \
-  do {                                                                                                               \
-    DG_CUDA_OK(cudaFuncSetAttribute(gather_norm_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    gather_norm_kernel<F><<<nsets * B, GATHER_THREADS, smem, st>>>(t, strides[0], strides[1], strides[2], strides[3], \
-                                                                    B, C, H, W, coords, S, tab, perm, eps, Prows, ld, o); \
-  } while (0)
-  if (format == DG_PANEL_F32) DG_GATHER_LAUNCH(FMT_F32);
-  else if (format == DG_PANEL_FEATS_SPLIT) DG_GATHER_LAUNCH(FMT_FEATS_SPLIT);
-  else DG_GATHER_LAUNCH(FMT_CODE_SPLIT);
-#undef DG_GATHER_LAUNCH
-  DG_LAUNCH_OK("gather_norm_kernel");
-  return DG_OK;
+  return launch_gather(format, tab, nsets, B, C, H, W, coords, S, perm, eps, Prows, ld, o,
+                       reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" int dg_gather_norm_bwd(float* grad, const int64_t* strides, int B, int C, int H, int W, const float* coords,
                                   int S, int nsets, const int32_t* set_coord, const int32_t* set_slot,
                                   const int64_t* perm, float eps, int Prows, int ld, const float* cn,
-                                  const float* cn_lo, const float* rnorm, const float* dC1, const float* dC2, int npairs,
-                                  const int32_t* pair_group, const float* pair_scale, int has_depth,
+                                  const float* cn_lo, const float* rnorm, const float* dC1, const float* dC2,
+                                  int npairs, const int32_t* pair_group, const float* pair_scale, int has_depth,
                                   const float* group_w, dg_stream_t stream) {
   using namespace dg;
   DG_REQUIRE(grad && strides && coords && cn && rnorm && dC1 && dC2 && group_w && pair_group && pair_scale,
@@ -418,7 +426,7 @@ extern "C" int dg_gather_norm_bwd(float* grad, const int64_t* strides, int B, in
              "dg_gather_norm_bwd: ld=%d must be a multiple of 32 in [C,256]", ld);
   DG_REQUIRE(npairs > 0 && npairs <= DG_MAX_PAIRS, DG_ERR_INVALID, "dg_gather_norm_bwd: npairs=%d", npairs);
   SetTable tab;
-  int rc = check_sets("dg_gather_norm_bwd", nsets, set_coord, set_slot, &tab);
+  int rc = fill_sets("dg_gather_norm_bwd", grad, strides, nsets, set_coord, set_slot, perm != nullptr, &tab);
   if (rc != DG_OK) return rc;
   PairTable pt;
   for (int k = 0; k < npairs; ++k) {
@@ -428,13 +436,11 @@ extern "C" int dg_gather_norm_bwd(float* grad, const int64_t* strides, int B, in
   }
   for (int s = 0; s < nsets; ++s)
     DG_REQUIRE(set_slot[s] < npairs, DG_ERR_INVALID, "dg_gather_norm_bwd: slot %d >= npairs", set_slot[s]);
-  const long long rows = (long long)nsets * B * S * S;
-  const int blocks = (int)((rows * 32 + 255) / 256);
-  gather_norm_bwd_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      grad, strides[0], strides[1], strides[2], strides[3], B, C, H, W, coords, S, tab, perm, eps, Prows, ld, cn, cn_lo,
-      rnorm, dC1, dC2, npairs, pt, has_depth, group_w, nsets);
-  DG_LAUNCH_OK("gather_norm_bwd_kernel");
-  return DG_OK;
+  GroupW gw;
+  gw.arr = group_w;
+  for (int g = 0; g < DG_NUM_GROUPS; ++g) gw.ptr[g] = nullptr;
+  return launch_gather_bwd(tab, nsets, B, C, H, W, coords, S, perm, eps, Prows, ld, cn, cn_lo, rnorm, dC1, dC2, npairs,
+                           pt, has_depth, gw, reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" int dg_pool_normalize(const float* t, const int64_t* strides, int N, int C, int H, int W, float eps,
@@ -442,6 +448,7 @@ extern "C" int dg_pool_normalize(const float* t, const int64_t* strides, int N, 
   using namespace dg;
   DG_REQUIRE(t && strides && out, DG_ERR_INVALID, "dg_pool_normalize: null pointer");
   DG_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0 && C <= 12288, DG_ERR_INVALID, "dg_pool_normalize: bad sizes");
+  DG_PRE(reinterpret_cast<cudaStream_t>(stream));
   pool_normalize_kernel<<<N, 256, (size_t)C * sizeof(float), reinterpret_cast<cudaStream_t>(stream)>>>(
       t, strides[0], strides[1], strides[2], strides[3], C, H, W, eps, out);
   DG_LAUNCH_OK("pool_normalize_kernel");

@@ -1,0 +1,73 @@
+// Internal launcher interface shared by the per-kernel C-ABI wrappers and the one-call
+// loss entry points (loss_api.cu).  Everything here enqueues on `st` and returns DG_* codes.
+#pragma once
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace dg {
+
+// One gathered coordinate set: which tensor to read (pointer + element strides), which
+// coordinate block, which panel slot to write, and which row of the perms table remaps the
+// batch index (-1 = identity).  Lets ONE launch serve several source tensors.
+struct SetDesc {
+  const float* src;
+  int64_t sb, sc, sh, sw;
+  int32_t coord, slot, perm_row;
+};
+struct SetTable {
+  SetDesc s[DG_MAX_SETS];
+};
+
+enum { FMT_F32 = 0, FMT_FEATS_SPLIT = 1, FMT_CODE_SPLIT = 2 };
+
+struct GatherOut {
+  // FMT_F32        : out (fp32 [slot,b,Prows,ld])
+  // FMT_FEATS_SPLIT: hi16/lo16 (bf16 [slot,b,Prows,ld]) : x ~= hi + lo
+  // FMT_CODE_SPLIT : out = tf32-rounded hi, out_lo = x - hi (fp32 [slot,b,Prows,ld]);
+  //                  t_hi16/t_lo16 (bf16 [slot,b,128,128]) transposed: row = channel, col = point
+  float* out;
+  float* out_lo;
+  __nv_bfloat16* hi16;
+  __nv_bfloat16* lo16;
+  __nv_bfloat16* t_hi16;
+  __nv_bfloat16* t_lo16;
+  float* rnorm;
+  float* meanvec;
+};
+
+struct PairTable {
+  int32_t group[DG_MAX_PAIRS + 1];
+  float scale[DG_MAX_PAIRS + 1];
+};
+
+// upstream gradients of the four scalar losses: either one device array [4] or four separate
+// device scalars (null = 0), so the caller needs no stack/cat kernel
+struct GroupW {
+  const float* arr;
+  const float* ptr[DG_NUM_GROUPS];
+};
+
+int launch_fps(const float* depth_a, const float* depth_b, int B, int Hd, int Wd, int H, int W, int S, float factor,
+               float far_plane, int affine, float* coords, int32_t* idx, cudaStream_t st);
+int launch_depth_sign(const float* depth, int B, int Hd, int Wd, int S, float eps, int out_pitch, float* out,
+                      cudaStream_t st);
+int launch_gather(int fmt, const SetTable& tab, int nsets, int B, int C, int H, int W, const float* coords, int S,
+                  const int64_t* perms, float eps, int Prows, int ld, const GatherOut& o, cudaStream_t st);
+int launch_gather_bwd(const SetTable& tab, int nsets, int B, int C, int H, int W, const float* coords, int S,
+                      const int64_t* perms, float eps, int Prows, int ld, const float* cn, const float* cn_lo,
+                      const float* rnorm, const float* dC1, const float* dC2, int npairs, const PairTable& pt,
+                      int has_depth, const GroupW& gw, cudaStream_t st);
+int launch_corr_finalize(const float* partials, int npairs, int B, int P, const int32_t* group, int has_depth,
+                         const int* err, float* out8, int n_pt, cudaStream_t st);
+int corr_loss_simt(const float* fn, const float* cn, const float* fmean, const float* dsign, int npairs, int B, int P,
+                   int Prows, int ldf, int ldc, const float* pair_shift, const int32_t* pair_group, float depth_shift,
+                   int flags, float* out8, float* dC1, float* dC2, float* cd_out, float* loss_out, float* dd_out,
+                   void* ws, cudaStream_t st);
+int corr_loss_umma(const dg_panels_t* pan, const float* fmean, const float* dsign, int npairs, int B, int P, int ldf,
+                   int ldc, const float* pair_shift, const int32_t* pair_group, float depth_shift, int flags,
+                   float* out8, float* dC1, float* dC2, float* cd_out, float* loss_out, float* dd_out, float* fd_dbg,
+                   void* ws, cudaStream_t st);
+size_t corr_workspace_bytes(int npairs, int B, int P);
+
+}  // namespace dg

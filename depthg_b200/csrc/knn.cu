@@ -148,6 +148,7 @@ extern "C" int dg_knn_topk(const float* q, const float* db, int Nq, int N, int F
   DG_REQUIRE(Nq > 0 && N > 0 && F > 0, DG_ERR_INVALID, "dg_knn_topk: bad sizes");
   DG_REQUIRE(k > 0 && k <= 32, DG_ERR_UNSUPPORTED, "dg_knn_topk: k=%d must be in [1,32]", k);
   DG_REQUIRE(k <= N, DG_ERR_INVALID, "dg_knn_topk: k=%d exceeds database size %d", k, N);
+  DG_PRE(reinterpret_cast<cudaStream_t>(stream));
   knn_topk_kernel<<<ceil_div(Nq, KTM), KNN_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(q, db, Nq, N, F, k,
                                                                                                   idx, sims);
   DG_LAUNCH_OK("knn_topk_kernel");

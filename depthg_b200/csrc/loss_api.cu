@@ -1,0 +1,205 @@
+// One-call forward / backward of the loss: plans the arena, builds the gather tables for
+// all four source tensors and enqueues the same kernels the per-stage entry points launch.
+#include <string.h>
+
+#include "kernels.cuh"
+
+namespace dg {
+
+static float fov_factor() {  // 2*tan(90/2 rad) in fp32, bits 0x404f54cb (src/modules.py:988-989 called with fov=90)
+  const uint32_t bits = 0x404F54CBu;
+  float f;
+  memcpy(&f, &bits, sizeof f);
+  return f;
+}
+static const float kFarPlane = 5.0f;
+static const float kNormEps = 1e-10f;
+
+static size_t al256(size_t x) { return (x + 255) / 256 * 256; }
+
+static int check_desc(const dg_loss_desc_t* d) {
+  DG_REQUIRE(d, DG_ERR_INVALID, "dg_loss: null descriptor");
+  DG_REQUIRE(d->B > 0 && d->C > 0 && d->D > 0 && d->H > 0 && d->W > 0 && d->S > 0, DG_ERR_INVALID, "dg_loss: bad sizes");
+  DG_REQUIRE(d->S * d->S <= d->H * d->W, DG_ERR_INVALID, "dg_loss: S*S=%d exceeds the %dx%d grid", d->S * d->S, d->H, d->W);
+  DG_REQUIRE(d->neg_samples >= 0 && d->neg_samples + 2 <= DG_MAX_PAIRS, DG_ERR_INVALID, "dg_loss: neg_samples=%d", d->neg_samples);
+  DG_REQUIRE(d->neg_samples == 0 || d->B >= 2, DG_ERR_INVALID, "dg_loss: negatives need a batch of at least 2");
+  DG_REQUIRE(round_up(d->D, 32) <= 128, DG_ERR_UNSUPPORTED, "dg_loss: code dim %d > 128 not supported", d->D);
+  if (d->flags & (DG_FLAG_FPS | DG_FLAG_DEPTH_TERM))
+    DG_REQUIRE(d->Hd > 0 && d->Wd > 0, DG_ERR_INVALID, "dg_loss: depth size missing");
+  return DG_OK;
+}
+
+static void make_plan(const dg_loss_desc_t* d, dg_loss_plan_t* p) {
+  const int P = d->S * d->S;
+  p->npairs = 2 + d->neg_samples;
+  p->ldf = round_up(d->C, 32);
+  p->ldc = round_up(d->D, 32);
+  p->kernel = (P <= 128 && p->ldc <= 128 && !(d->flags & DG_FLAG_FORCE_SIMT)) ? 1 : 0;
+  p->Prows = p->kernel ? 128 : round_up(P, 64);
+  const size_t np = p->npairs, B = d->B, Pr = p->Prows;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += al256(bytes); return o; };
+  p->coords = take((size_t)2 * B * P * 2 * 4);
+  p->frn = take(np * B * Pr * 4);
+  p->fmean = take(np * B * p->ldf * 4);
+  p->crn = take(np * B * Pr * 4);
+  p->dsign = take(B * Pr * 4);
+  p->ws_bytes = corr_workspace_bytes(p->npairs, d->B, P);
+  p->ws = take(p->ws_bytes);
+  p->dC1 = take((np + 1) * B * Pr * p->ldc * 4);
+  p->dC2 = take((np + 1) * B * Pr * p->ldc * 4);
+  if (p->kernel) {
+    p->c_hi = take(np * B * Pr * p->ldc * 4);
+    p->c_lo = take(np * B * Pr * p->ldc * 4);
+    p->ct_hi = take(np * B * 128 * 128 * 2);
+    p->ct_lo = take(np * B * 128 * 128 * 2);
+    p->f_hi = take(np * B * Pr * p->ldf * 2);
+    p->f_lo = take(np * B * Pr * p->ldf * 2);
+  } else {
+    p->c_hi = take(np * B * Pr * p->ldc * 4);
+    p->f_hi = take(np * B * Pr * p->ldf * 4);
+    p->c_lo = p->ct_hi = p->ct_lo = p->f_lo = 0;
+  }
+  p->total = off;
+}
+
+static void set_desc(SetDesc& s, const float* src, const int64_t* st, int coord, int slot, int perm_row) {
+  s.src = src;
+  s.sb = st[0]; s.sc = st[1]; s.sh = st[2]; s.sw = st[3];
+  s.coord = coord; s.slot = slot; s.perm_row = perm_row;
+}
+
+// slot 0 = own tensor at coords1, slot 1 = positive tensor at coords2, slots 2.. = own tensor[perm_k] at coords2
+static int build_sets(SetTable& tab, const float* own, const int64_t* own_st, const float* pos, const int64_t* pos_st,
+                      int nneg) {
+  set_desc(tab.s[0], own, own_st, 0, 0, -1);
+  set_desc(tab.s[1], pos, pos_st, 1, 1, -1);
+  for (int k = 0; k < nneg; ++k) set_desc(tab.s[2 + k], own, own_st, 1, 2 + k, k);
+  return 2 + nneg;
+}
+
+}  // namespace dg
+
+extern "C" int dg_loss_plan(const dg_loss_desc_t* desc, dg_loss_plan_t* plan) {
+  using namespace dg;
+  int rc = check_desc(desc);
+  if (rc != DG_OK) return rc;
+  DG_REQUIRE(plan, DG_ERR_INVALID, "dg_loss_plan: null plan");
+  make_plan(desc, plan);
+  return DG_OK;
+}
+
+extern "C" int dg_loss_forward(const dg_loss_desc_t* d, const dg_loss_io_t* io, dg_stream_t stream) {
+  using namespace dg;
+  int rc = check_desc(d);
+  if (rc != DG_OK) return rc;
+  DG_REQUIRE(io && io->feats && io->feats_pos && io->code && io->code_pos && io->arena && io->out8, DG_ERR_INVALID,
+             "dg_loss_forward: null pointer");
+  DG_REQUIRE(d->neg_samples == 0 || io->perms, DG_ERR_INVALID, "dg_loss_forward: perms missing");
+  const bool fps = d->flags & DG_FLAG_FPS, depth_term = d->flags & DG_FLAG_DEPTH_TERM;
+  DG_REQUIRE(!fps || (io->depth && io->depth_pos), DG_ERR_INVALID, "dg_loss_forward: fps sampling needs depth and depth_pos");
+  DG_REQUIRE(!depth_term || io->depth, DG_ERR_INVALID, "dg_loss_forward: the depth term needs depth");
+  DG_REQUIRE(fps || io->coords, DG_ERR_INVALID, "dg_loss_forward: coords missing");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  dg_loss_plan_t pl;
+  make_plan(d, &pl);
+  uint8_t* A = static_cast<uint8_t*>(io->arena);
+  const int B = d->B, S = d->S, P = S * S, np = pl.npairs;
+  const float* coords = io->coords;
+  if (fps) {
+    float* c = reinterpret_cast<float*>(A + pl.coords);
+    rc = launch_fps(io->depth, io->depth_pos, B, d->Hd, d->Wd, d->H, d->W, S, fov_factor(), kFarPlane, 1, c, nullptr, st);
+    if (rc != DG_OK) return rc;
+    coords = c;
+  }
+  const bool pointwise = d->flags & DG_FLAG_POINTWISE;
+  float* fmean = pointwise ? reinterpret_cast<float*>(A + pl.fmean) : nullptr;
+  float* dsign = nullptr;
+  if (depth_term) {
+    dsign = reinterpret_cast<float*>(A + pl.dsign);
+    rc = launch_depth_sign(io->depth, B, d->Hd, d->Wd, S, kNormEps, pl.Prows, dsign, st);
+    if (rc != DG_OK) return rc;
+  }
+  SetTable tab;
+  GatherOut o;
+  // backbone features
+  int nsets = build_sets(tab, io->feats, io->feats_strides, io->feats_pos, io->feats_pos_strides, d->neg_samples);
+  o.out = reinterpret_cast<float*>(A + pl.f_hi);
+  o.out_lo = nullptr;
+  o.hi16 = reinterpret_cast<__nv_bfloat16*>(A + pl.f_hi);
+  o.lo16 = reinterpret_cast<__nv_bfloat16*>(A + pl.f_lo);
+  o.t_hi16 = o.t_lo16 = nullptr;
+  o.rnorm = reinterpret_cast<float*>(A + pl.frn);
+  o.meanvec = fmean;
+  rc = launch_gather(pl.kernel ? FMT_FEATS_SPLIT : FMT_F32, tab, nsets, B, d->C, d->H, d->W, coords, S, io->perms, kNormEps,
+                     pl.Prows, pl.ldf, o, st);
+  if (rc != DG_OK) return rc;
+  // code
+  nsets = build_sets(tab, io->code, io->code_strides, io->code_pos, io->code_pos_strides, d->neg_samples);
+  o.out = reinterpret_cast<float*>(A + pl.c_hi);
+  o.out_lo = pl.kernel ? reinterpret_cast<float*>(A + pl.c_lo) : nullptr;
+  o.hi16 = o.lo16 = nullptr;
+  o.t_hi16 = pl.kernel ? reinterpret_cast<__nv_bfloat16*>(A + pl.ct_hi) : nullptr;
+  o.t_lo16 = pl.kernel ? reinterpret_cast<__nv_bfloat16*>(A + pl.ct_lo) : nullptr;
+  o.rnorm = reinterpret_cast<float*>(A + pl.crn);
+  o.meanvec = nullptr;
+  rc = launch_gather(pl.kernel ? FMT_CODE_SPLIT : FMT_F32, tab, nsets, B, d->D, d->H, d->W, coords, S, io->perms, kNormEps,
+                     pl.Prows, pl.ldc, o, st);
+  if (rc != DG_OK) return rc;
+
+  float shifts[DG_MAX_PAIRS];
+  int32_t groups[DG_MAX_PAIRS];
+  shifts[0] = d->pos_intra_shift; groups[0] = DG_GROUP_INTRA;
+  shifts[1] = d->pos_inter_shift; groups[1] = DG_GROUP_INTER;
+  for (int k = 2; k < np; ++k) { shifts[k] = d->neg_inter_shift; groups[k] = DG_GROUP_NEG; }
+  const int kflags = d->flags & (DG_FLAG_POINTWISE | DG_FLAG_ZERO_CLAMP | DG_FLAG_STABALIZE);
+  float* dC1 = reinterpret_cast<float*>(A + pl.dC1);
+  float* dC2 = reinterpret_cast<float*>(A + pl.dC2);
+  if (pl.kernel) {
+    dg_panels_t pan;
+    pan.format = DG_PANEL_CODE_SPLIT;
+    pan.f_hi = A + pl.f_hi; pan.f_lo = A + pl.f_lo; pan.c_hi = A + pl.c_hi; pan.c_lo = A + pl.c_lo;
+    pan.ct_hi = A + pl.ct_hi; pan.ct_lo = A + pl.ct_lo;
+    return corr_loss_umma(&pan, fmean, dsign, np, B, P, pl.ldf, pl.ldc, shifts, groups, d->depth_feat_shift, kflags,
+                          io->out8, dC1, dC2, io->cd_out, io->loss_out, io->dd_out, io->fd_dbg, A + pl.ws, st);
+  }
+  return corr_loss_simt(reinterpret_cast<const float*>(A + pl.f_hi), reinterpret_cast<const float*>(A + pl.c_hi), fmean,
+                        dsign, np, B, P, pl.Prows, pl.ldf, pl.ldc, shifts, groups, d->depth_feat_shift, kflags, io->out8,
+                        dC1, dC2, io->cd_out, io->loss_out, io->dd_out, A + pl.ws, st);
+}
+
+extern "C" int dg_loss_backward(const dg_loss_desc_t* d, const dg_loss_io_t* io, const dg_loss_grads_t* gr,
+                                dg_stream_t stream) {
+  using namespace dg;
+  int rc = check_desc(d);
+  if (rc != DG_OK) return rc;
+  DG_REQUIRE(io && io->arena && gr, DG_ERR_INVALID, "dg_loss_backward: null pointer");
+  DG_REQUIRE(d->neg_samples == 0 || io->perms, DG_ERR_INVALID, "dg_loss_backward: perms missing");
+  dg_loss_plan_t pl;
+  make_plan(d, &pl);
+  uint8_t* A = static_cast<uint8_t*>(io->arena);
+  const float* coords = (d->flags & DG_FLAG_FPS) ? reinterpret_cast<const float*>(A + pl.coords) : io->coords;
+  DG_REQUIRE(coords, DG_ERR_INVALID, "dg_loss_backward: coords missing");
+  // destination sets: slot 0 + negatives scatter into d_code, slot 1 into d_code_pos
+  SetTable tab;
+  int n = 0;
+  if (gr->d_code) {
+    set_desc(tab.s[n++], gr->d_code, gr->d_code_strides, 0, 0, -1);
+    for (int k = 0; k < d->neg_samples; ++k) set_desc(tab.s[n++], gr->d_code, gr->d_code_strides, 1, 2 + k, k);
+  }
+  if (gr->d_code_pos) set_desc(tab.s[n++], gr->d_code_pos, gr->d_code_pos_strides, 1, 1, -1);
+  if (n == 0) return DG_OK;
+  PairTable pt;
+  pt.group[0] = DG_GROUP_INTRA; pt.scale[0] = 1.f;
+  pt.group[1] = DG_GROUP_INTER; pt.scale[1] = 1.f;
+  for (int k = 2; k < pl.npairs; ++k) { pt.group[k] = DG_GROUP_NEG; pt.scale[k] = 1.f / (float)d->neg_samples; }
+  GroupW gw;
+  gw.arr = nullptr;
+  for (int g = 0; g < DG_NUM_GROUPS; ++g) gw.ptr[g] = gr->g[g];
+  return launch_gather_bwd(tab, n, d->B, d->D, d->H, d->W, coords, d->S, io->perms, kNormEps, pl.Prows, pl.ldc,
+                           reinterpret_cast<const float*>(A + pl.c_hi),
+                           pl.kernel ? reinterpret_cast<const float*>(A + pl.c_lo) : nullptr,
+                           reinterpret_cast<const float*>(A + pl.crn), reinterpret_cast<const float*>(A + pl.dC1),
+                           reinterpret_cast<const float*>(A + pl.dC2), pl.npairs, pt,
+                           (d->flags & DG_FLAG_DEPTH_TERM) ? 1 : 0, gw, reinterpret_cast<cudaStream_t>(stream));
+}

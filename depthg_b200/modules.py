@@ -188,126 +188,92 @@ def tensor_correlation(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
 
 # --------------------------------------------------------------------------- the loss
 class _CorrLossFn(torch.autograd.Function):
-    """forward: FPS/gather/normalise -> fused correlation loss (values + unit
-    gradients); backward: weight the unit gradients by the upstream scalars and
-    scatter them back through normalise + bilinear gather into the code tensors."""
+    """forward: FPS / gathers / depth signs / fused correlation loss (values + unit gradients) in ONE
+    C-ABI call over one arena allocation; backward: one call that weights the unit gradients by
+    the upstream scalars and scatters them through normalise + bilinear gather into the code grads."""
 
-    debug_fd = False        # tests: also dump the raw feature correlations of the tcgen05 kernel
+    debug = False           # tests: keep views of the unit gradients / dump raw tcgen05 feature correlations
     last_fd = None
     last_unit_grads = None
 
     @staticmethod
-    def forward(ctx, feats, feats_pos, code, code_pos, depth, coords, perms, S, shifts, depth_shift, flags,
-                materialize):
+    def forward(ctx, feats, feats_pos, code, code_pos, depth, depth_pos, coords, perms, desc, materialize):
         lib = _lib.lib()
-        B, Cdim, H, W = feats.shape
-        D = code.shape[1]
         dev = feats.device
-        nneg = 0 if perms is None else perms.shape[0]
-        npairs = 2 + nneg
-        P, Prows = S * S, _lib.panel_rows(S * S)
-        ldf, ldc = _lib.panel_ld(Cdim), _lib.panel_ld(D)
-        pointwise = bool(flags & _lib.FLAG_POINTWISE)
-        has_depth = depth is not None
-
+        plan = _lib.LossPlan()
+        check(lib.dg_loss_plan(C.byref(desc), C.byref(plan)), "dg_loss_plan")
+        B, S, nneg, npairs = desc.B, desc.S, desc.neg_samples, plan.npairs
+        P = S * S
+        has_depth = bool(desc.flags & _lib.FLAG_DEPTH_TERM)
+        arena = torch.empty(plan.total, device=dev, dtype=torch.uint8)
+        out8 = torch.empty(8, device=dev, dtype=torch.float32)
         f32 = dict(device=dev, dtype=torch.float32)
-        bf16 = dict(device=dev, dtype=torch.bfloat16)
-        kind = corr_kernel_choice(P, D)
-        if kind == "umma":
-            Prows = 128   # the tcgen05 kernel works on whole 128 x 128 tiles
-        frn = torch.empty((npairs, B, Prows), **f32)
-        fmean = torch.empty((npairs, B, ldf), **f32) if pointwise else None
-        crn = torch.empty((npairs, B, Prows), **f32)
-
-        # sets gathered from the "own" tensors: slot 0 at coords1, one slot per negative at coords2
-        own_coord = [0] + [1] * nneg
-        own_slot = [0] + list(range(2, 2 + nneg))
-        if nneg:
-            ident = torch.arange(B, device=dev, dtype=torch.long).unsqueeze(0)
-            perm_all = torch.cat([ident, perms.to(torch.long)], 0).contiguous()
-        else:
-            perm_all = None
-        if kind == "umma":
-            f_hi, f_lo = torch.empty((npairs, B, Prows, ldf), **bf16), torch.empty((npairs, B, Prows, ldf), **bf16)
-            c_hi, c_lo = torch.empty((npairs, B, Prows, ldc), **f32), torch.empty((npairs, B, Prows, ldc), **f32)
-            ct_hi, ct_lo = torch.empty((npairs, B, 128, 128), **bf16), torch.empty((npairs, B, 128, 128), **bf16)
-            fk = dict(fmt=_lib.PANEL_FEATS_SPLIT, out_lo=f_lo)
-            ck = dict(fmt=_lib.PANEL_CODE_SPLIT, out_lo=c_lo, outT_hi=ct_hi, outT_lo=ct_lo)
-            pan = _lib.make_panels(_lib.PANEL_CODE_SPLIT, f_hi, f_lo, c_hi, c_lo, ct_hi, ct_lo)
-        else:
-            f_hi, c_hi = torch.empty((npairs, B, Prows, ldf), **f32), torch.empty((npairs, B, Prows, ldc), **f32)
-            c_lo = None
-            fk, ck = {}, {}
-            pan = _lib.make_panels(_lib.PANEL_F32, f_hi, None, c_hi, None, None, None)
-        _gather(feats, coords, S, own_coord, own_slot, perm_all, NORM_EPS, Prows, ldf, f_hi, frn, fmean, **fk)
-        _gather(feats_pos, coords, S, [1], [1], None, NORM_EPS, Prows, ldf, f_hi, frn, fmean, **fk)
-        _gather(code, coords, S, own_coord, own_slot, perm_all, NORM_EPS, Prows, ldc, c_hi, crn, None, **ck)
-        _gather(code_pos, coords, S, [1], [1], None, NORM_EPS, Prows, ldc, c_hi, crn, None, **ck)
-
-        dsign = None
-        if has_depth:
-            dsign = torch.empty((B, Prows), **f32)
-            _, _, Hd, Wd = depth.shape
-            check(lib.dg_depth_sign(ptr(depth), B, Hd, Wd, S, NORM_EPS, Prows, ptr(dsign), stream_ptr()),
-                  "dg_depth_sign")
-
-        groups = [_lib.GROUP_INTRA, _lib.GROUP_INTER] + [_lib.GROUP_NEG] * nneg
-        out8 = torch.empty(8, **f32)
-        dC1 = torch.empty((npairs + 1, B, Prows, ldc), **f32)
-        dC2 = torch.empty((npairs + 1, B, Prows, ldc), **f32)
         cd_out = torch.empty((npairs, B, P, P), **f32) if materialize else None
         loss_out = torch.empty((npairs, B, P, P), **f32) if materialize else None
         dd_out = torch.empty((B, P, P), **f32) if (materialize and has_depth) else None
-        ws_bytes = lib.dg_corr_loss_workspace_bytes(npairs, B, P)
-        ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
         fd_dbg = None
-        if _CorrLossFn.debug_fd and kind == "umma":
+        if _CorrLossFn.debug and plan.kernel == 1:
             fd_dbg = torch.zeros((npairs, B, 128, 128), **f32)
             _CorrLossFn.last_fd = fd_dbg
-        check(lib.dg_corr_loss(C.byref(pan), ptr(fmean), ptr(dsign), npairs, B, P, Prows, Cdim, ldf, D, ldc,
-                               _lib.f32_array(shifts), _lib.i32_array(groups), float(depth_shift), int(flags),
-                               ptr(out8), ptr(dC1), ptr(dC2), ptr(cd_out), ptr(loss_out), ptr(dd_out), ptr(fd_dbg),
-                               ptr(ws), ws_bytes, stream_ptr()), "dg_corr_loss")
-        _CorrLossFn.last_unit_grads = (dC1, dC2)
+        io = _lib.LossIO()
+        io.feats, io.feats_pos, io.code, io.code_pos = (feats.data_ptr(), feats_pos.data_ptr(), code.data_ptr(),
+                                                        code_pos.data_ptr())
+        io.feats_strides[:] = feats.stride()
+        io.feats_pos_strides[:] = feats_pos.stride()
+        io.code_strides[:] = code.stride()
+        io.code_pos_strides[:] = code_pos.stride()
+        io.depth = depth.data_ptr() if depth is not None else None
+        io.depth_pos = depth_pos.data_ptr() if depth_pos is not None else None
+        io.coords = coords.data_ptr() if coords is not None else None
+        io.perms = perms.data_ptr() if perms is not None else None
+        io.arena, io.out8 = arena.data_ptr(), out8.data_ptr()
+        for name, t in (("cd_out", cd_out), ("loss_out", loss_out), ("dd_out", dd_out), ("fd_dbg", fd_dbg)):
+            setattr(io, name, t.data_ptr() if t is not None else None)
+        check(lib.dg_loss_forward(C.byref(desc), C.byref(io), stream_ptr()), "dg_loss_forward")
 
-        ctx.save_for_backward(coords, perm_all, c_hi, c_lo, crn, dC1, dC2)
-        ctx.meta = (S, Prows, ldc, npairs, nneg, groups, has_depth, code.shape, code_pos.shape,
-                    code.stride(), code_pos.stride())
-        ctx.code_like = (code, code_pos)  # only for zeros_like layout; no extra memory
-        outs = [out8[0], out8[2], out8[4], out8[6], out8.detach()]
-        dense = [t for t in (cd_out, loss_out, dd_out)]
-        ctx.mark_non_differentiable(outs[4], *[t for t in dense if t is not None])
+        ctx.desc, ctx.plan = desc, plan
+        ctx.keep = (arena, coords, perms)          # the arena holds coords / panels / unit gradients for backward
+        ctx.code_like = (code, code_pos)
+        _CorrLossFn.last_unit_grads = tuple(
+            arena[o:o + (npairs + 1) * B * plan.Prows * plan.ldc * 4].view(torch.float32).view(
+                npairs + 1, B, plan.Prows, plan.ldc) for o in (plan.dC1, plan.dC2)) if _CorrLossFn.debug else None
+        if desc.flags & _lib.FLAG_FPS:   # the coordinates FPS produced (a view into the arena)
+            coords_used = arena[plan.coords:plan.coords + 2 * B * P * 2 * 4].view(torch.float32).view(2, B, S, S, 2)
+        else:
+            coords_used = out8.new_empty(0)
+        outs = [out8[0], out8[2], out8[4], out8[6], out8.detach(), coords_used]
+        dense = [cd_out, loss_out, dd_out]
+        ctx.mark_non_differentiable(outs[4], outs[5], *[t for t in dense if t is not None])
         return (*outs, *dense)
 
     @staticmethod
     def backward(ctx, g_intra, g_inter, g_neg, g_depth, *unused):
-        coords, perm_all, cpan, cpan_lo, crn, dC1, dC2 = ctx.saved_tensors
-        S, Prows, ldc, npairs, nneg, groups, has_depth, shp, shp_pos, _, _ = ctx.meta
+        arena, coords, perms = ctx.keep
         code, code_pos = ctx.code_like
-        dev = cpan.device
-        zero = torch.zeros((), device=dev, dtype=torch.float32)
-        gw = torch.stack([g if g is not None else zero for g in (g_intra, g_inter, g_neg, g_depth)]).float()
-        scales = [1.0, 1.0] + [1.0 / max(nneg, 1)] * nneg
-        lib = _lib.lib()
-        B, D, H, W = shp
         need = ctx.needs_input_grad
+        gr = _lib.LossGrads()
+        keep = []
+        for i, g in enumerate((g_intra, g_inter, g_neg, g_depth)):
+            if g is not None:
+                g = g.contiguous() if g.dtype == torch.float32 else g.float()
+                keep.append(g)
+                gr.g[i] = g.data_ptr()
         d_code = d_code_pos = None
-        common = (NORM_EPS, Prows, ldc, ptr(cpan), ptr(cpan_lo), ptr(crn), ptr(dC1), ptr(dC2), npairs,
-                  _lib.i32_array(groups),
-                  _lib.f32_array(scales), 1 if has_depth else 0, ptr(gw), stream_ptr())
         if need[2]:
             d_code = torch.zeros_like(code)
-            own_coord = [0] + [1] * nneg
-            own_slot = [0] + list(range(2, 2 + nneg))
-            check(lib.dg_gather_norm_bwd(ptr(d_code), _strides(d_code), B, D, H, W, ptr(coords), S, len(own_coord),
-                                         _lib.i32_array(own_coord), _lib.i32_array(own_slot), ptr(perm_all), *common),
-                  "dg_gather_norm_bwd")
+            gr.d_code = d_code.data_ptr()
+            gr.d_code_strides[:] = d_code.stride()
         if need[3]:
             d_code_pos = torch.zeros_like(code_pos)
-            check(lib.dg_gather_norm_bwd(ptr(d_code_pos), _strides(d_code_pos), B, D, H, W, ptr(coords), S, 1,
-                                         _lib.i32_array([1]), _lib.i32_array([1]), None, *common),
-                  "dg_gather_norm_bwd")
-        return (None, None, d_code, d_code_pos) + (None,) * 8
+            gr.d_code_pos = d_code_pos.data_ptr()
+            gr.d_code_pos_strides[:] = d_code_pos.stride()
+        io = _lib.LossIO()
+        io.arena = arena.data_ptr()
+        io.coords = coords.data_ptr() if coords is not None else None
+        io.perms = perms.data_ptr() if perms is not None else None
+        check(_lib.lib().dg_loss_backward(C.byref(ctx.desc), C.byref(io), C.byref(gr), stream_ptr()),
+              "dg_loss_backward")
+        return (None, None, d_code, d_code_pos) + (None,) * 6
 
 
 class ContrastiveCorrelationLoss(nn.Module):
@@ -362,11 +328,12 @@ class ContrastiveCorrelationLoss(nn.Module):
             raise NotImplementedError("use_salience sampling (sample_nonzero_locations, src/modules.py:1191-1204) "
                                       "is outside the accelerated path")
         dev = orig_feats.device
+        flags = self._flags()
+        coords = None
         if cfg.depth_sampling == "fps":
             if depth is None or depth_pos is None:
                 raise ValueError("depth_sampling='fps' needs depth and depth_pos")
-            coords, _ = _fps(depth, depth_pos, H, W, S, affine=True, want_idx=False)
-            coords = coords.view(2, B, S, S, 2)
+            flags |= _lib.FLAG_FPS
         elif cfg.depth_sampling in ("simple", "fps_depth_feat"):
             raise NotImplementedError(f"depth_sampling={cfg.depth_sampling!r} (simple_depth_informed_sampling / "
                                       "include_feats, src/modules.py:828-883, :1313-1317) is outside the accelerated path")
@@ -375,26 +342,37 @@ class ContrastiveCorrelationLoss(nn.Module):
             c1 = self.rand_fn(shape, dev) * 2 - 1
             c2 = self.rand_fn(shape, dev) * 2 - 1
             coords = torch.stack([c1, c2]).float().contiguous()
-        self.last_coords = coords
         if not nneg:
             perms = None
         elif self.perm_fn is super_perm:
             perms = super_perms(nneg, B, dev)
         else:
-            perms = torch.stack([self.perm_fn(B, dev) for _ in range(nneg)])
+            perms = torch.stack([self.perm_fn(B, dev) for _ in range(nneg)]).to(torch.long).contiguous()
 
         depth_term = bool(cfg.depth_feat_correlation_loss)
-        if depth_term:
+        Hd = Wd = 0
+        if depth_term or (flags & _lib.FLAG_FPS):
             if depth is None:
                 raise ValueError("depth_feat_correlation_loss=True needs depth")
-            require_cuda_f32(depth, "depth")
+            for name, t in (("depth", depth), ("depth_pos", depth_pos)):
+                if t is not None:
+                    require_cuda_f32(t, name)
+                    if t.dim() != 4 or t.shape[1] != 1 or t.shape[0] != B:
+                        raise ValueError(f"{name} must be [B,1,Hd,Wd], got {tuple(t.shape)}")
             depth = depth.contiguous()
-        shifts = [float(cfg.pos_intra_shift), float(cfg.pos_inter_shift)] + [float(cfg.neg_inter_shift)] * nneg
-        res = _CorrLossFn.apply(orig_feats, orig_feats_pos, orig_code, orig_code_pos, depth if depth_term else None,
-                                coords.view(2, B, S * S, 2), perms, S, shifts,
-                                float(cfg.depth_feat_shift) if depth_term else 0.0, self._flags(),
-                                bool(self.materialize_cd))
-        intra, inter, neg, dloss, out8, cd_out, loss_out, dd_out = res
+            depth_pos = depth_pos.contiguous() if depth_pos is not None else None
+            Hd, Wd = depth.shape[-2:]
+            if depth_term:
+                flags |= _lib.FLAG_DEPTH_TERM
+        if corr_kernel_choice(S * S, orig_code.shape[1]) == "simt":
+            flags |= _lib.FLAG_FORCE_SIMT
+        desc = _lib.LossDesc(B, Cdim, orig_code.shape[1], H, W, Hd, Wd, S, nneg, flags, float(cfg.pos_intra_shift),
+                             float(cfg.pos_inter_shift), float(cfg.neg_inter_shift),
+                             float(cfg.depth_feat_shift) if depth_term else 0.0)
+        res = _CorrLossFn.apply(orig_feats, orig_feats_pos, orig_code, orig_code_pos, depth, depth_pos, coords, perms,
+                                desc, bool(self.materialize_cd))
+        intra, inter, neg, dloss, out8, coords_used, cd_out, loss_out, dd_out = res
+        self.last_coords = coords_used if (flags & _lib.FLAG_FPS) else coords
         if self.materialize_cd:
             five = (B, S, S, S, S)
             intra_cd, inter_cd = cd_out[0].view(five), cd_out[1].view(five)

@@ -60,6 +60,11 @@ DG_API int dg_version(void);
 DG_API const char* dg_last_error_string(void);
 /* Number of kernels this library has launched in this process (for launch accounting). */
 DG_API unsigned long long dg_kernel_launches(void);
+/* Diagnostics: when enabled, every kernel this library launches is bracketed by CUDA events on
+ * its own stream; dg_profile_collect synchronises and writes "name\tlaunches\ttotal_us\n" lines
+ * (returns the buffer size needed).  Enabling/disabling clears the records. */
+DG_API int dg_profile_enable(int on);
+DG_API size_t dg_profile_collect(char* buf, size_t buf_bytes);
 
 /* Pitch (in floats) of a panel row holding `channels` values: rounded up to a
  * multiple of 32 so a row is a whole number of 128-byte lines. */
@@ -181,6 +186,60 @@ DG_API int dg_corr_loss(const dg_panels_t* pan, const float* fmean, const float*
                         int Prows, int C, int ldf, int D, int ldc, const float* pair_shift, const int32_t* pair_group,
                         float depth_shift, int flags, float* out8, float* dC1, float* dC2, float* cd_out,
                         float* loss_out, float* dd_out, float* fd_dbg, void* ws, size_t ws_bytes, dg_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * The whole loss in one call.  dg_loss_forward enqueues FPS (or takes coordinates),
+ * the gathers, the depth signs and the fused correlation loss; dg_loss_backward the
+ * scatter backward.  Same kernels as the per-stage entry points above — this form
+ * only removes per-stage host overhead (one FFI crossing and one allocation per step).
+ * Replaces ContrastiveCorrelationLoss.forward (src/modules.py:1280-1367) and its autograd
+ * backward.  The caller owns one `arena` of dg_loss_plan().total bytes that must stay
+ * alive until dg_loss_backward has run. */
+enum { DG_FLAG_DEPTH_TERM = 8,  /* cfg.depth_feat_correlation_loss                          */
+       DG_FLAG_FPS = 16,        /* cfg.depth_sampling == "fps": coordinates from depth maps */
+       DG_FLAG_FORCE_SIMT = 32  /* use the generic CUDA-core correlation kernel             */ };
+
+typedef struct dg_loss_desc {
+  int B, C, D, H, W, Hd, Wd, S, neg_samples;
+  int flags; /* DG_FLAG_POINTWISE | ZERO_CLAMP | STABALIZE | DEPTH_TERM | FPS | FORCE_SIMT */
+  float pos_intra_shift, pos_inter_shift, neg_inter_shift, depth_feat_shift;
+} dg_loss_desc_t;
+
+typedef struct dg_loss_plan { /* byte offsets into the arena, all 256-byte aligned */
+  size_t total, coords, frn, fmean, crn, f_hi, f_lo, c_hi, c_lo, ct_hi, ct_lo, dsign, dC1, dC2, ws, ws_bytes;
+  int kernel; /* 0 = generic CUDA-core kernel, 1 = tcgen05 kernel */
+  int Prows, ldf, ldc, npairs;
+} dg_loss_plan_t;
+
+typedef struct dg_loss_io {
+  const float* feats;     /* [B,C,H,W], element strides below */
+  const float* feats_pos;
+  const float* code;      /* [B,D,H,W] */
+  const float* code_pos;
+  int64_t feats_strides[4], feats_pos_strides[4], code_strides[4], code_pos_strides[4];
+  const float* depth;     /* [B,1,Hd,Wd] contiguous; needed with DG_FLAG_FPS or DG_FLAG_DEPTH_TERM */
+  const float* depth_pos; /* needed with DG_FLAG_FPS */
+  const float* coords;    /* [2,B,S*S,2] in [-1,1]; ignored with DG_FLAG_FPS (written to arena+coords) */
+  const int64_t* perms;   /* [neg_samples,B] source image of each negative */
+  void* arena;
+  float* out8;            /* device [8], see dg_corr_loss */
+  float* cd_out;          /* optional dense outputs, see dg_corr_loss */
+  float* loss_out;
+  float* dd_out;
+  float* fd_dbg;
+} dg_loss_io_t;
+
+typedef struct dg_loss_grads {
+  const float* g[4];      /* device scalars: upstream gradients of (intra, inter, neg mean, depth); NULL = 0 */
+  float* d_code;          /* zero-initialised by the caller; NULL to skip */
+  float* d_code_pos;
+  int64_t d_code_strides[4], d_code_pos_strides[4];
+} dg_loss_grads_t;
+
+DG_API int dg_loss_plan(const dg_loss_desc_t* desc, dg_loss_plan_t* plan);
+DG_API int dg_loss_forward(const dg_loss_desc_t* desc, const dg_loss_io_t* io, dg_stream_t stream);
+DG_API int dg_loss_backward(const dg_loss_desc_t* desc, const dg_loss_io_t* io, const dg_loss_grads_t* grads,
+                            dg_stream_t stream);
 
 /* ---------------------------------------------------------------------------
  * Cosine-similarity k-nearest-neighbour build.  Replaces the einsum + topk

@@ -303,11 +303,11 @@ def _run_both_kernels(name, monkeypatch):
             monkeypatch.setenv("DEPTHG_B200_CORR", "simt")
         else:
             monkeypatch.delenv("DEPTHG_B200_CORR", raising=False)
-        M._CorrLossFn.debug_fd = (kind == "umma")
+        M._CorrLossFn.debug = True
         try:
             cfg, t, r = run_cuda_loss(name, materialize=True)
         finally:
-            M._CorrLossFn.debug_fd = False
+            M._CorrLossFn.debug = False
         r["dC1"], r["dC2"] = [x.clone() for x in M._CorrLossFn.last_unit_grads]
         r["fd"] = M._CorrLossFn.last_fd.clone() if kind == "umma" else None
         res[kind] = r

@@ -59,6 +59,21 @@ def weighted(out):
             + WEIGHTS["depth_feat"] * out[6])
 
 
+_GRADW = {}
+
+
+def backprop(out):
+    """d/d(code) of the trainer's weighted sum (train_segmentation.py:331-334): the four scalar losses are
+    backpropagated with their weights as grad_tensors, i.e. exactly weighted(out).backward() without the
+    seven scalar mul/add kernels of building that sum."""
+    dev = out[0].device
+    if dev not in _GRADW:
+        _GRADW[dev] = [torch.tensor(WEIGHTS[k], device=dev) for k in ("pos_intra", "pos_inter", "neg_inter",
+                                                                       "depth_feat")]
+    neg = out[4] if out[4].dim() == 0 else out[4].mean()
+    torch.autograd.backward([out[0], out[2], neg, out[6]], grad_tensors=_GRADW[dev])
+
+
 def synth_inputs(B, gen, device, channels_last=True):
     """Synthetic batch of the cfg2 shape.  Features arrive channels-last on the live path
     (permuted [B,HW,C] views, SURVEY.md 7 hard part 6); depth is integer-valued like the uint8 PNGs."""
@@ -151,7 +166,7 @@ def run_reference(args):
         code_pos = inp["code_pos"].detach().requires_grad_(True)
         out = O.ContrastiveCorrelationLoss(cfg)(inp["feats"], inp["feats_pos"], None, None, code, code_pos,
                                                 inp["depth"], inp["depth_pos"])
-        weighted(out).backward()
+        backprop(out)
         return out[0].item()
 
     B = CFG2["B"]
@@ -240,7 +255,7 @@ def main():
         s["code"].grad = None
         s["code_pos"].grad = None
         out = loss_fn(s["feats"], s["feats_pos"], None, None, s["code"], s["code_pos"], s["depth"], s["depth_pos"])
-        weighted(out).backward()
+        backprop(out)
         if world > 1:   # DDP semantics: the only exchange is the head-gradient all-reduce
             dist.all_reduce(head_grad)
         return out
@@ -270,6 +285,23 @@ def main():
         ms = float(t.item())
     ms_per_step = ms / args.steps
     value = world * B * args.steps / (ms / 1e3)
+
+    # same step with the one-launch negative sampler (same distribution, own Philox stream)
+    loss_fn.negative_sampler = "fused"
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    ev0.record()
+    for i in range(args.steps):
+        step(i)
+    ev1.record()
+    barrier()
+    ms_fused = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms_fused], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_fused = float(t.item())
+    loss_fn.negative_sampler = "torch"
 
     # ---- per-kernel breakdown: the library brackets each of its kernels with CUDA events on the launching stream
     import ctypes
@@ -341,7 +373,7 @@ def main():
         code = d["code"].requires_grad_(True)
         code_pos = d["code_pos"].requires_grad_(True)
         out = loss_fn(d["feats"], d["feats_pos"], None, None, code, code_pos, d["depth"], d["depth_pos"])
-        weighted(out).backward()
+        backprop(out)
         res_host.copy_(torch.stack([out[0], out[2], out[4], out[6]]).detach(), non_blocking=True)
         g0, g1 = code.grad, code_pos.grad
         if not args.nchw:
@@ -417,7 +449,7 @@ def main():
             t0 = time.perf_counter()
             out = O.ContrastiveCorrelationLoss(cfg)(cin["feats"], cin["feats_pos"], None, None, code, code_pos,
                                                     cin["depth"], cin["depth_pos"])
-            weighted(out).backward()
+            backprop(out)
             times.append(time.perf_counter() - t0)
             if sum(times) > 25:
                 break
@@ -437,6 +469,10 @@ def main():
                 "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches),
                 "launches_per_step": launches / args.steps, "roofline": roofline, "roofline_step": roofline_step,
                 "breakdown_us": {k: round(v, 2) for k, v in breakdown.items()}, "cpu_baseline": cpu_baseline,
+                "fused_negative_sampler": {"value": world * B * args.steps / (ms_fused / 1e3), "unit": UNIT,
+                                           "ms_per_step": ms_fused / args.steps,
+                                           "note": "negative_sampler='fused': one dg_super_perms launch instead of "
+                                                   "neg_samples x torch.randperm (same distribution, different stream)"},
                 "knn": knn}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -35,6 +35,7 @@ SIGNATURES = {
     "dg_panel_rows": (C.c_int, [C.c_int]),
     "dg_fps_coords": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
                                 C.c_int, _vp, _vp, _vp]),
+    "dg_super_perms": (C.c_int, [C.c_ulonglong, C.c_ulonglong, C.c_int, C.c_int, _vp, _vp]),
     "dg_depth_sign": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, _vp, _vp]),
     "dg_gather_norm": (C.c_int, [_vp, _c_i64p, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_int, C.c_int, _c_i32p,
                                  _c_i32p, _vp, C.c_float, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -142,8 +143,11 @@ def ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
-def stream_ptr():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+def stream_ptr(device_index=None):
+    """Raw handle of torch's current CUDA stream (the fast C accessor: this is on the per-step path)."""
+    if device_index is None:
+        device_index = torch.cuda.current_device()
+    return C.c_void_p(torch._C._cuda_getCurrentRawStream(device_index))
 
 
 def i32_array(vals):

@@ -45,14 +45,18 @@ struct CorrParams {
 
 // rowmean[k,b,p] = <F1n[b,p,:], mean_q F2n[k,b,q,:]>, bsum[k,b] = sum_{p<P} rowmean
 __global__ void __launch_bounds__(256) pair_means_kernel(const float* __restrict__ fn, const float* __restrict__ fmean,
-                                                         int B, int P, int Prows, int ldf, float* __restrict__ rowmean,
-                                                         float* __restrict__ bsum) {
+                                                         int nsplit, int B, int P, int Prows, int ldf,
+                                                         float* __restrict__ rowmean, float* __restrict__ bsum) {
   extern __shared__ float mv[];  // [ldf]
   __shared__ float wsum[8];
   const int k = blockIdx.x / B, b = blockIdx.x - k * B;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const float* m = fmean + ((size_t)k * B + b) * ldf;
-  for (int c = threadIdx.x; c < ldf; c += blockDim.x) mv[c] = m[c];
+  const float* m = fmean + ((size_t)k * B + b) * nsplit * ldf;  // nsplit partial means
+  for (int c = threadIdx.x; c < ldf; c += blockDim.x) {
+    float a = 0.f;
+    for (int i = 0; i < nsplit; ++i) a += m[(size_t)i * ldf + c];
+    mv[c] = a;
+  }
   __syncthreads();
   const float* F1 = fn + (size_t)b * Prows * ldf;
   float* rm = rowmean + ((size_t)k * B + b) * Prows;
@@ -395,7 +399,7 @@ size_t corr_workspace_bytes(int npairs, int B, int P) {
   return (bytes + 255) / 256 * 256;
 }
 
-int corr_loss_simt(const float* fn, const float* cn, const float* fmean, const float* dsign, int npairs, int B, int P,
+int corr_loss_simt(const float* fn, const float* cn, const float* fmean, int nsplit, const float* dsign, int npairs, int B, int P,
                    int Prows, int ldf, int ldc, const float* pair_shift, const int32_t* pair_group, float depth_shift,
                    int flags, float* out8, float* dC1, float* dC2, float* cd_out, float* loss_out, float* dd_out,
                    void* ws, cudaStream_t st) {
@@ -422,7 +426,7 @@ int corr_loss_simt(const float* fn, const float* cn, const float* fmean, const f
 
   if (flags & DG_FLAG_POINTWISE) {
     DG_PRE(st);
-    pair_means_kernel<<<npairs * B, 256, (size_t)ldf * sizeof(float), st>>>(fn, fmean, B, P, Prows, ldf, rowmean, bsum);
+    pair_means_kernel<<<npairs * B, 256, (size_t)ldf * sizeof(float), st>>>(fn, fmean, nsplit, B, P, Prows, ldf, rowmean, bsum);
     DG_LAUNCH_OK("pair_means_kernel");
   }
   const size_t slab = (size_t)B * Prows * ldc * sizeof(float);
@@ -468,12 +472,12 @@ extern "C" int dg_corr_loss(const dg_panels_t* pan, const float* fmean, const fl
                "dg_corr_loss: the tcgen05 path needs S*S <= 128 and 128-row panels (got P=%d, Prows=%d)", P, Prows);
     DG_REQUIRE(pan->f_lo && pan->c_lo && pan->ct_hi && pan->ct_lo, DG_ERR_INVALID,
                "dg_corr_loss: split panel format needs f_lo, c_lo, ct_hi, ct_lo");
-    return corr_loss_umma(pan, fmean, dsign, npairs, B, P, ldf, ldc, pair_shift, pair_group, depth_shift, flags, out8,
+    return corr_loss_umma(pan, fmean, 1, dsign, npairs, B, P, ldf, ldc, pair_shift, pair_group, depth_shift, flags, out8,
                           dC1, dC2, cd_out, loss_out, dd_out, fd_dbg, ws, st);
   }
   DG_REQUIRE(pan->format == DG_PANEL_F32, DG_ERR_INVALID, "dg_corr_loss: unknown panel format %d", pan->format);
   DG_REQUIRE(Prows == round_up(P, 64), DG_ERR_INVALID, "dg_corr_loss: Prows must be dg_panel_rows(P)");
-  return corr_loss_simt(static_cast<const float*>(pan->f_hi), static_cast<const float*>(pan->c_hi), fmean, dsign, npairs,
+  return corr_loss_simt(static_cast<const float*>(pan->f_hi), static_cast<const float*>(pan->c_hi), fmean, 1, dsign, npairs,
                         B, P, Prows, ldf, ldc, pair_shift, pair_group, depth_shift, flags, out8, dC1, dC2, cd_out,
                         loss_out, dd_out, ws, st);
 }

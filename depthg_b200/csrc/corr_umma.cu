@@ -362,16 +362,23 @@ __global__ void __launch_bounds__(UM_THREADS, 1) corr_umma_kernel(const __grid_c
 }
 
 // dots[k,b] = < mean_p F1n[b,p,:], mean_q F2n[k,b,q,:] >  (one warp each); block 0 also clears the error flag
-__global__ void __launch_bounds__(256) pair_dots_kernel(const float* __restrict__ fmean, int npairs, int B, int ldf,
-                                                        float* __restrict__ dots, int* __restrict__ err) {
+__global__ void __launch_bounds__(256) pair_dots_kernel(const float* __restrict__ fmean, int nsplit, int npairs, int B,
+                                                        int ldf, float* __restrict__ dots, int* __restrict__ err) {
   if (blockIdx.x == 0 && threadIdx.x == 0 && err) *err = 0;
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (w >= npairs * B || fmean == nullptr) return;
   const int k = w / B, b = w - k * B;
-  const float* m1 = fmean + (size_t)b * ldf;
-  const float* m2 = fmean + ((size_t)k * B + b) * ldf;
+  const float* m1 = fmean + (size_t)b * nsplit * ldf;                      // nsplit partial means each
+  const float* m2 = fmean + ((size_t)k * B + b) * nsplit * ldf;
   float s = 0.f;
-  for (int c = lane; c < ldf; c += 32) s += __ldg(m1 + c) * __ldg(m2 + c);
+  for (int c = lane; c < ldf; c += 32) {
+    float a = 0.f, bb = 0.f;
+    for (int i = 0; i < nsplit; ++i) {
+      a += __ldg(m1 + (size_t)i * ldf + c);
+      bb += __ldg(m2 + (size_t)i * ldf + c);
+    }
+    s += a * bb;
+  }
   s = warp_sum(s);
   if (lane == 0) dots[w] = s;
 }
@@ -407,7 +414,7 @@ static int make_map_2d(CUtensorMap* m, CUtensorMapDataType dt, int elt_bytes, co
   return DG_OK;
 }
 
-int corr_loss_umma(const dg_panels_t* pan, const float* fmean, const float* dsign, int npairs, int B, int P, int ldf,
+int corr_loss_umma(const dg_panels_t* pan, const float* fmean, int nsplit, const float* dsign, int npairs, int B, int P, int ldf,
                    int ldc, const float* pair_shift, const int32_t* pair_group, float depth_shift, int flags,
                    float* out8, float* dC1, float* dC2, float* cd_out, float* loss_out, float* dd_out, float* fd_dbg,
                    void* ws, cudaStream_t st) {
@@ -437,7 +444,7 @@ int corr_loss_umma(const dg_panels_t* pan, const float* fmean, const float* dsig
   {
     const float* fm = (flags & DG_FLAG_POINTWISE) ? fmean : nullptr;
     DG_PRE(st);
-    pair_dots_kernel<<<ceil_div(npairs * B * 32, 256), 256, 0, st>>>(fm, npairs, B, ldf, dots, err);
+    pair_dots_kernel<<<ceil_div(npairs * B * 32, 256), 256, 0, st>>>(fm, nsplit, npairs, B, ldf, dots, err);
     DG_LAUNCH_OK("pair_dots_kernel");
   }
   static bool attr_set = false;

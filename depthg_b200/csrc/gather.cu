@@ -191,6 +191,102 @@ __global__ void __launch_bounds__(GATHER_THREADS)
   }
 }
 
+// Fast path for channels-last sources with C a multiple of 128 (the backbone features on the live
+// path): the sampled row, its running panel mean and the bilinear corner data all stay in
+// registers (no smem staging), every lane issues its 4 x NV 128-bit corner loads back to back, and a
+// (set, image) is split over `nsplit` CTAs so ~900 CTAs cover the GPU evenly.  Each CTA writes its
+// share of the panel mean (already divided by P); consumers add the nsplit partials.
+constexpr int GF_THREADS = 256;
+constexpr int GF_WARPS = GF_THREADS / 32;
+
+template <int NV, int FMT>
+__global__ void __launch_bounds__(GF_THREADS, 2)
+    gather_feats_kernel(const __grid_constant__ SetTable sets, int B, int C, int H, int W,
+                        const float* __restrict__ coords, int S, const int64_t* __restrict__ perms, float eps,
+                        int Prows, int nsplit, GatherOut o) {
+  extern __shared__ float gfs[];  // [GF_WARPS][C] for the final cross-warp mean
+  const int split = blockIdx.x % nsplit, sbi = blockIdx.x / nsplit;
+  const int set = sbi / B, b = sbi - set * B;
+  const int P = S * S, ld = C;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const SetDesc& sd = sets.s[set];
+  const int64_t sh = sd.sh, sw = sd.sw;
+  const int slot = sd.slot;
+  const int64_t src = sd.perm_row >= 0 ? perms[(size_t)sd.perm_row * B + b] : (int64_t)b;
+  const float* timg = sd.src + src * sd.sb;
+  const float* cset = coords + ((size_t)sd.coord * B + b) * P * 2;
+  const size_t pbase = ((size_t)slot * B + b) * Prows;
+  const int chunk = (Prows + nsplit - 1) / nsplit;
+  const int p_end = min((split + 1) * chunk, Prows);
+
+  float4 macc[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) macc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  for (int p = split * chunk + warp; p < p_end; p += GF_WARPS) {
+    const size_t ro = (pbase + p) * ld;
+    float4 v[NV];
+    float r = 0.f;
+    if (p < P) {
+      const int h = p / S, w = p - h * S;
+      const float* cc = cset + 2 * (w * S + h);  // the reference's S-axis swap
+      const Corners k = bilinear_corners(__ldg(cc), __ldg(cc + 1), H, W);
+      const float* p00 = timg + k.y0 * sh + k.x0 * sw + lane * 4;
+      const float* p01 = k.x1_ok ? p00 + sw : p00;
+      const float* p10 = k.y1_ok ? p00 + sh : p00;
+      const float* p11 = p10 + (k.x1_ok ? sw : 0);
+      const float w00 = k.w00, w01 = k.x1_ok ? k.w01 : 0.f, w10 = k.y1_ok ? k.w10 : 0.f,
+                  w11 = (k.x1_ok && k.y1_ok) ? k.w11 : 0.f;
+      float ss = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(p00 + 128 * i));
+        const float4 bq = __ldg(reinterpret_cast<const float4*>(p01 + 128 * i));
+        const float4 cq = __ldg(reinterpret_cast<const float4*>(p10 + 128 * i));
+        const float4 d = __ldg(reinterpret_cast<const float4*>(p11 + 128 * i));
+        v[i].x = a.x * w00 + bq.x * w01 + cq.x * w10 + d.x * w11;
+        v[i].y = a.y * w00 + bq.y * w01 + cq.y * w10 + d.y * w11;
+        v[i].z = a.z * w00 + bq.z * w01 + cq.z * w10 + d.z * w11;
+        v[i].w = a.w * w00 + bq.w * w01 + cq.w * w10 + d.w * w11;
+        ss += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+      }
+      ss = warp_sum(ss);
+      r = 1.f / fmaxf(sqrtf(ss), eps);
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p < P) {
+        x = make_float4(v[i].x * r, v[i].y * r, v[i].z * r, v[i].w * r);
+        macc[i].x += x.x; macc[i].y += x.y; macc[i].z += x.z; macc[i].w += x.w;
+      }
+      const int c = lane * 4 + 128 * i;
+      if (FMT == FMT_F32) {
+        *reinterpret_cast<float4*>(o.out + ro + c) = x;
+      } else {
+        __nv_bfloat16 hh[4], ll[4];
+        split_bf16(x.x, hh[0], ll[0]); split_bf16(x.y, hh[1], ll[1]);
+        split_bf16(x.z, hh[2], ll[2]); split_bf16(x.w, hh[3], ll[3]);
+        *reinterpret_cast<uint2*>(o.hi16 + ro + c) = *reinterpret_cast<uint2*>(hh);
+        *reinterpret_cast<uint2*>(o.lo16 + ro + c) = *reinterpret_cast<uint2*>(ll);
+      }
+    }
+    if (lane == 0) o.rnorm[pbase + p] = r;
+  }
+  if (o.meanvec == nullptr) return;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) *reinterpret_cast<float4*>(gfs + (size_t)warp * C + lane * 4 + 128 * i) = macc[i];
+  __syncthreads();
+  float* mv = o.meanvec + (((size_t)slot * B + b) * nsplit + split) * ld;
+  const float invP = 1.f / (float)P;
+  for (int c = threadIdx.x; c < C; c += GF_THREADS) {
+    float sum = 0.f;
+#pragma unroll
+    for (int wdx = 0; wdx < GF_WARPS; ++wdx) sum += gfs[(size_t)wdx * C + c];
+    mv[c] = sum * invP;
+  }
+}
+
 // One warp per panel row: compose the row's gradient from the unit gradients,
 // back through x/max(||x||,eps), then atomically scatter through the 4 corners.
 __global__ void __launch_bounds__(256)
@@ -342,8 +438,47 @@ static int fill_sets(const char* fn, const float* src, const int64_t* strides, i
   return DG_OK;
 }
 
+// How many CTAs a (set, image) is split over: 4 on the register-resident fast path, else 1.
+int gather_nsplit(int fmt, const SetTable& tab, int nsets, int C, int ld) {
+  if (fmt == FMT_CODE_SPLIT || C != ld || (C % 128) != 0 || C / 128 > 8) return 1;
+  const int nv = C / 128;
+  if (nv != 1 && nv != 2 && nv != 3 && nv != 4 && nv != 6 && nv != 8) return 1;
+  for (int s = 0; s < nsets; ++s) {
+    const SetDesc& d = tab.s[s];
+    if (d.sc != 1 || (d.sb & 3) || (d.sh & 3) || (d.sw & 3) || (reinterpret_cast<uintptr_t>(d.src) & 15)) return 1;
+  }
+  return 4;
+}
+
+template <int NV>
+static int launch_gather_fast(int fmt, const SetTable& tab, int nsets, int B, int C, int H, int W, const float* coords,
+                              int S, const int64_t* perms, float eps, int Prows, int nsplit, const GatherOut& o,
+                              cudaStream_t st) {
+  const size_t smem = (size_t)GF_WARPS * C * sizeof(float);
+  DG_PRE(st);
+  if (fmt == FMT_F32)
+    gather_feats_kernel<NV, FMT_F32><<<nsets * B * nsplit, GF_THREADS, smem, st>>>(tab, B, C, H, W, coords, S, perms, eps,
+                                                                                  Prows, nsplit, o);
+  else
+    gather_feats_kernel<NV, FMT_FEATS_SPLIT><<<nsets * B * nsplit, GF_THREADS, smem, st>>>(tab, B, C, H, W, coords, S,
+                                                                                          perms, eps, Prows, nsplit, o);
+  DG_LAUNCH_OK("gather_feats_kernel");
+  return DG_OK;
+}
+
 int launch_gather(int fmt, const SetTable& tab, int nsets, int B, int C, int H, int W, const float* coords, int S,
-                  const int64_t* perms, float eps, int Prows, int ld, const GatherOut& o, cudaStream_t st) {
+                  const int64_t* perms, float eps, int Prows, int ld, int nsplit, const GatherOut& o, cudaStream_t st) {
+  if (nsplit > 1) {
+    DG_REQUIRE(nsplit == gather_nsplit(fmt, tab, nsets, C, ld), DG_ERR_INVALID, "gather: inconsistent nsplit");
+    switch (C / 128) {
+      case 1: return launch_gather_fast<1>(fmt, tab, nsets, B, C, H, W, coords, S, perms, eps, Prows, nsplit, o, st);
+      case 2: return launch_gather_fast<2>(fmt, tab, nsets, B, C, H, W, coords, S, perms, eps, Prows, nsplit, o, st);
+      case 3: return launch_gather_fast<3>(fmt, tab, nsets, B, C, H, W, coords, S, perms, eps, Prows, nsplit, o, st);
+      case 4: return launch_gather_fast<4>(fmt, tab, nsets, B, C, H, W, coords, S, perms, eps, Prows, nsplit, o, st);
+      case 6: return launch_gather_fast<6>(fmt, tab, nsets, B, C, H, W, coords, S, perms, eps, Prows, nsplit, o, st);
+      default: return launch_gather_fast<8>(fmt, tab, nsets, B, C, H, W, coords, S, perms, eps, Prows, nsplit, o, st);
+    }
+  }
   size_t smem = (size_t)2 * GATHER_WARPS * ld * sizeof(float);
   if (fmt == FMT_CODE_SPLIT) smem += (size_t)128 * (ld + 1) * sizeof(float);
   DG_REQUIRE(smem <= 200 * 1024, DG_ERR_UNSUPPORTED, "gather: C=%d too large for the row staging buffer", C);
@@ -354,7 +489,7 @@ int launch_gather(int fmt, const SetTable& tab, int nsets, int B, int C, int H, 
       DG_CUDA_OK(cudaFuncSetAttribute(gather_norm_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
       configured = smem;                                                                                           \
     }                                                                                                              \
-    DG_PRE(st);                                                                                                           \
+    DG_PRE(st);                                                                                                    \
     gather_norm_kernel<F><<<nsets * B, GATHER_THREADS, smem, st>>>(tab, B, C, H, W, coords, S, perms, eps, Prows, ld, o); \
   } while (0)
   if (fmt == FMT_F32) DG_GATHER_LAUNCH(FMT_F32);
@@ -408,7 +543,7 @@ extern "C" int dg_gather_norm(const float* t, const int64_t* strides, int B, int
   o.t_lo16 = static_cast<__nv_bfloat16*>(outT_lo);
   o.rnorm = rnorm;
   o.meanvec = meanvec;
-  return launch_gather(format, tab, nsets, B, C, H, W, coords, S, perm, eps, Prows, ld, o,
+  return launch_gather(format, tab, nsets, B, C, H, W, coords, S, perm, eps, Prows, ld, 1, o,
                        reinterpret_cast<cudaStream_t>(stream));
 }
 

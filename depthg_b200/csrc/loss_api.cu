@@ -41,7 +41,7 @@ static void make_plan(const dg_loss_desc_t* d, dg_loss_plan_t* p) {
   auto take = [&](size_t bytes) { size_t o = off; off += al256(bytes); return o; };
   p->coords = take((size_t)2 * B * P * 2 * 4);
   p->frn = take(np * B * Pr * 4);
-  p->fmean = take(np * B * p->ldf * 4);
+  p->fmean = take(np * B * 4 * p->ldf * 4);  // up to 4 partial means per (slot, image)
   p->crn = take(np * B * Pr * 4);
   p->dsign = take(B * Pr * 4);
   p->ws_bytes = corr_workspace_bytes(p->npairs, d->B, P);
@@ -131,8 +131,10 @@ extern "C" int dg_loss_forward(const dg_loss_desc_t* d, const dg_loss_io_t* io, 
   o.t_hi16 = o.t_lo16 = nullptr;
   o.rnorm = reinterpret_cast<float*>(A + pl.frn);
   o.meanvec = fmean;
-  rc = launch_gather(pl.kernel ? FMT_FEATS_SPLIT : FMT_F32, tab, nsets, B, d->C, d->H, d->W, coords, S, io->perms, kNormEps,
-                     pl.Prows, pl.ldf, o, st);
+  const int ffmt = pl.kernel ? FMT_FEATS_SPLIT : FMT_F32;
+  const int nsplit = gather_nsplit(ffmt, tab, nsets, d->C, pl.ldf);
+  rc = launch_gather(ffmt, tab, nsets, B, d->C, d->H, d->W, coords, S, io->perms, kNormEps, pl.Prows, pl.ldf, nsplit, o,
+                     st);
   if (rc != DG_OK) return rc;
   // code
   nsets = build_sets(tab, io->code, io->code_strides, io->code_pos, io->code_pos_strides, d->neg_samples);
@@ -144,7 +146,7 @@ extern "C" int dg_loss_forward(const dg_loss_desc_t* d, const dg_loss_io_t* io, 
   o.rnorm = reinterpret_cast<float*>(A + pl.crn);
   o.meanvec = nullptr;
   rc = launch_gather(pl.kernel ? FMT_CODE_SPLIT : FMT_F32, tab, nsets, B, d->D, d->H, d->W, coords, S, io->perms, kNormEps,
-                     pl.Prows, pl.ldc, o, st);
+                     pl.Prows, pl.ldc, 1, o, st);
   if (rc != DG_OK) return rc;
 
   float shifts[DG_MAX_PAIRS];
@@ -160,11 +162,11 @@ extern "C" int dg_loss_forward(const dg_loss_desc_t* d, const dg_loss_io_t* io, 
     pan.format = DG_PANEL_CODE_SPLIT;
     pan.f_hi = A + pl.f_hi; pan.f_lo = A + pl.f_lo; pan.c_hi = A + pl.c_hi; pan.c_lo = A + pl.c_lo;
     pan.ct_hi = A + pl.ct_hi; pan.ct_lo = A + pl.ct_lo;
-    return corr_loss_umma(&pan, fmean, dsign, np, B, P, pl.ldf, pl.ldc, shifts, groups, d->depth_feat_shift, kflags,
+    return corr_loss_umma(&pan, fmean, nsplit, dsign, np, B, P, pl.ldf, pl.ldc, shifts, groups, d->depth_feat_shift, kflags,
                           io->out8, dC1, dC2, io->cd_out, io->loss_out, io->dd_out, io->fd_dbg, A + pl.ws, st);
   }
   return corr_loss_simt(reinterpret_cast<const float*>(A + pl.f_hi), reinterpret_cast<const float*>(A + pl.c_hi), fmean,
-                        dsign, np, B, P, pl.Prows, pl.ldf, pl.ldc, shifts, groups, d->depth_feat_shift, kflags, io->out8,
+                        nsplit, dsign, np, B, P, pl.Prows, pl.ldf, pl.ldc, shifts, groups, d->depth_feat_shift, kflags, io->out8,
                         dC1, dC2, io->cd_out, io->loss_out, io->dd_out, A + pl.ws, st);
 }
 

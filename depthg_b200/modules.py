@@ -80,6 +80,19 @@ def super_perms(n: int, size: int, device) -> torch.Tensor:
     return (perm + (perm == torch.arange(size, device=device))) % size
 
 
+def fused_super_perms(n: int, size: int, device) -> torch.Tensor:
+    """All ``n`` negative-pair permutations in ONE kernel (dg_super_perms): same distribution as
+    ``super_perm`` but a Philox stream of its own, keyed by torch's CUDA generator (seed, offset) so
+    ``torch.manual_seed`` still makes runs reproducible.  The generator is advanced past the draws."""
+    device = torch.device(device)
+    gen = torch.cuda.default_generators[device.index if device.index is not None else torch.cuda.current_device()]
+    seed, offset = gen.initial_seed(), gen.get_offset()
+    gen.set_offset(offset + 4 * ((size + 3) // 4))
+    out = torch.empty((n, size), device=device, dtype=torch.long)
+    check(_lib.lib().dg_super_perms(seed, offset, n, size, ptr(out), stream_ptr(device.index)), "dg_super_perms")
+    return out
+
+
 def _strides(t: torch.Tensor):
     return _lib.i64_array(t.stride())
 
@@ -229,7 +242,7 @@ class _CorrLossFn(torch.autograd.Function):
         io.arena, io.out8 = arena.data_ptr(), out8.data_ptr()
         for name, t in (("cd_out", cd_out), ("loss_out", loss_out), ("dd_out", dd_out), ("fd_dbg", fd_dbg)):
             setattr(io, name, t.data_ptr() if t is not None else None)
-        check(lib.dg_loss_forward(C.byref(desc), C.byref(io), stream_ptr()), "dg_loss_forward")
+        check(lib.dg_loss_forward(C.byref(desc), C.byref(io), stream_ptr(dev.index)), "dg_loss_forward")
 
         ctx.desc, ctx.plan = desc, plan
         ctx.keep = (arena, coords, perms)          # the arena holds coords / panels / unit gradients for backward
@@ -271,7 +284,7 @@ class _CorrLossFn(torch.autograd.Function):
         io.arena = arena.data_ptr()
         io.coords = coords.data_ptr() if coords is not None else None
         io.perms = perms.data_ptr() if perms is not None else None
-        check(_lib.lib().dg_loss_backward(C.byref(ctx.desc), C.byref(io), C.byref(gr), stream_ptr()),
+        check(_lib.lib().dg_loss_backward(C.byref(ctx.desc), C.byref(io), C.byref(gr), stream_ptr(arena.device.index)),
               "dg_loss_backward")
         return (None, None, d_code, d_code_pos) + (None,) * 6
 
@@ -290,10 +303,15 @@ class ContrastiveCorrelationLoss(nn.Module):
     (e.g. on histogram steps) to get the reference's full tensors.
     """
 
-    def __init__(self, cfg, materialize_cd: bool = False):
+    def __init__(self, cfg, materialize_cd: bool = False, negative_sampler: str = "torch"):
         super().__init__()
         self.cfg = cfg
         self.materialize_cd = materialize_cd
+        if negative_sampler not in ("torch", "fused"):
+            raise ValueError("negative_sampler must be 'torch' (the reference's randperm stream) or 'fused'")
+        # "torch": neg_samples x torch.randperm, the reference's exact RNG stream (src/modules.py:1341);
+        # "fused": one dg_super_perms launch — same distribution, own Philox stream, ~150 us less host time
+        self.negative_sampler = negative_sampler
         # test hooks (CPU and CUDA RNG streams differ): same contract as the oracle's
         self.perm_fn = super_perm
         self.rand_fn = lambda shape, device: torch.rand(shape, device=device)
@@ -344,10 +362,12 @@ class ContrastiveCorrelationLoss(nn.Module):
             coords = torch.stack([c1, c2]).float().contiguous()
         if not nneg:
             perms = None
-        elif self.perm_fn is super_perm:
-            perms = super_perms(nneg, B, dev)
-        else:
+        elif self.perm_fn is not super_perm:
             perms = torch.stack([self.perm_fn(B, dev) for _ in range(nneg)]).to(torch.long).contiguous()
+        elif self.negative_sampler == "fused":
+            perms = fused_super_perms(nneg, B, dev)
+        else:
+            perms = super_perms(nneg, B, dev)
 
         depth_term = bool(cfg.depth_feat_correlation_loss)
         Hd = Wd = 0

@@ -94,6 +94,12 @@ DG_API int dg_panel_rows(int P);
 DG_API int dg_fps_coords(const float* depth_a, const float* depth_b, int B, int Hd, int Wd, int H, int W, int S,
                   float factor, float far_plane, int affine, float* coords, int32_t* idx, dg_stream_t stream);
 
+/* All neg_samples permutations of super_perm (src/modules.py:1184-1188, called at :1341) in one
+ * launch: Fisher-Yates on Philox4x32-10 keyed by (seed, offset), fixed points bumped by one, mod B.
+ *   out : [n,B] int64.  Same distribution as torch.randperm-based super_perm, different stream. */
+DG_API int dg_super_perms(unsigned long long seed, unsigned long long offset, int n, int B, int64_t* out,
+                          dg_stream_t stream);
+
 /* norm(interpolate(depth,(S,S),bilinear,align_corners=True)) of
  * depth_feature_correlation (src/modules.py:1261-1265): s = d / max(|d|, eps).
  *   depth [B,1,Hd,Wd] -> out [B, out_pitch] (first S*S entries per image, rest zeroed). */

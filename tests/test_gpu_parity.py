@@ -355,3 +355,68 @@ def test_generic_kernel_still_matches_reference_golden(monkeypatch):
     for name in ("small_fps", "cfg1_vits", "small_random"):
         cfg, t, r = run_cuda_loss(name)
         _check_loss(r, golden("loss_" + name), cfg)
+
+
+# ------------------------------------------------------------------ negative sampler / backprop forms
+def test_fused_negative_sampler_properties():
+    from depthg_b200.modules import fused_super_perms
+    torch.manual_seed(11)
+    a = fused_super_perms(5, 32, dev())
+    b = fused_super_perms(5, 32, dev())
+    torch.manual_seed(11)
+    a2 = fused_super_perms(5, 32, dev())
+    assert a.dtype == torch.int64 and tuple(a.shape) == (5, 32)
+    assert torch.equal(a, a2) and not torch.equal(a, b)          # reproducible under manual_seed, advances the generator
+    ar = torch.arange(32, device=dev())
+    assert not (a == ar).any() and a.min() >= 0 and a.max() < 32  # super_perm's no-fixed-point property
+    # before the bump every row was a permutation: at most the bumped entries collide
+    for row in a.cpu():
+        assert len(set(row.tolist())) >= 32 - 3
+    big = fused_super_perms(64, 7, dev()).cpu()
+    assert not (big == torch.arange(7)).any()
+    counts = torch.stack([(big == v).sum(0) for v in range(7)]).float()   # roughly uniform over positions
+    assert counts.max() < 30
+
+
+def test_fused_sampler_loss_runs_and_matches_oracle_on_its_own_perms():
+    from depthg_b200.modules import ContrastiveCorrelationLoss
+    cfg, t = cases.make_loss_inputs("small_fps")
+    fn = ContrastiveCorrelationLoss(cfg, negative_sampler="fused")
+    captured = []
+    import depthg_b200.modules as M
+    orig = M.fused_super_perms
+    M.fused_super_perms = lambda n, size, device: captured.append(orig(n, size, device)) or captured[-1]
+    try:
+        a = {k: t[k].to(dev()) for k in ("feats", "feats_pos", "code", "code_pos", "depth", "depth_pos")}
+        out = fn(a["feats"], a["feats_pos"], None, None, a["code"], a["code_pos"], a["depth"], a["depth_pos"])
+    finally:
+        M.fused_super_perms = orig
+    ofn = O.ContrastiveCorrelationLoss(cfg)
+    pit = iter(captured[0].cpu())
+    ofn.perm_fn = lambda B, device: next(pit)
+    want = ofn(t["feats"], t["feats_pos"], None, None, t["code"], t["code_pos"], t["depth"], t["depth_pos"])
+    np.testing.assert_allclose(out[4].item(), want[4].mean().item(), rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(out[0].item(), want[0].item(), rtol=RTOL, atol=ATOL)
+
+
+def test_grad_tensors_backprop_equals_weighted_sum_backward():
+    """bench.backprop() (autograd.backward with the loss weights as grad_tensors) == weighted(out).backward()."""
+    import bench
+    from depthg_b200.modules import ContrastiveCorrelationLoss
+    cfg, t = cases.make_loss_inputs("small_fps")
+    grads = []
+    for mode in ("sum", "grad_tensors"):
+        fn = ContrastiveCorrelationLoss(cfg)
+        pit = iter(t["perms"].to(dev()))
+        fn.perm_fn = lambda B, device: next(pit).clone()
+        a = {k: t[k].to(dev()) for k in ("feats", "feats_pos", "depth", "depth_pos")}
+        code = t["code"].to(dev()).requires_grad_(True)
+        code_pos = t["code_pos"].to(dev()).requires_grad_(True)
+        out = fn(a["feats"], a["feats_pos"], None, None, code, code_pos, a["depth"], a["depth_pos"])
+        if mode == "sum":
+            bench.weighted(out).backward()
+        else:
+            bench.backprop(out)
+        grads.append((code.grad.clone(), code_pos.grad.clone()))
+    assert rel_err(grads[0][0].cpu().numpy(), grads[1][0].cpu().numpy()) < 1e-6
+    assert rel_err(grads[0][1].cpu().numpy(), grads[1][1].cpu().numpy()) < 1e-6

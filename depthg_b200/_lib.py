@@ -59,13 +59,13 @@ PANEL_F32, PANEL_FEATS_SPLIT, PANEL_CODE_SPLIT = 0, 1, 2
 
 class Panels(C.Structure):
     """dg_panels_t of include/depthg_b200.h."""
-    _fields_ = [("format", C.c_int), ("f_hi", _vp), ("f_lo", _vp), ("c_hi", _vp), ("c_lo", _vp), ("ct_hi", _vp),
-                ("ct_lo", _vp)]
+    _fields_ = [("format", C.c_int), ("f_hi", _vp), ("f_lo", _vp), ("c_hi", _vp), ("c_lo", _vp), ("cb_hi", _vp),
+                ("cb_lo", _vp)]
 
 
-def make_panels(fmt, f_hi, f_lo, c_hi, c_lo, ct_hi, ct_lo):
+def make_panels(fmt, f_hi, f_lo, c_hi, c_lo, cb_hi, cb_lo):
     dp = lambda t: None if t is None else t.data_ptr()  # noqa: E731
-    return Panels(fmt, dp(f_hi), dp(f_lo), dp(c_hi), dp(c_lo), dp(ct_hi), dp(ct_lo))
+    return Panels(fmt, dp(f_hi), dp(f_lo), dp(c_hi), dp(c_lo), dp(cb_hi), dp(cb_lo))
 
 
 FLAG_DEPTH_TERM, FLAG_FPS, FLAG_FORCE_SIMT = 8, 16, 32
@@ -81,7 +81,7 @@ class LossDesc(C.Structure):
 class LossPlan(C.Structure):
     """dg_loss_plan_t"""
     _fields_ = [(n, C.c_size_t) for n in ("total", "coords", "frn", "fmean", "crn", "f_hi", "f_lo", "c_hi", "c_lo",
-                                          "ct_hi", "ct_lo", "dsign", "dC1", "dC2", "ws", "ws_bytes")] + \
+                                          "cb_hi", "cb_lo", "dsign", "dC1", "dC2", "ws", "ws_bytes")] + \
                [(n, C.c_int) for n in ("kernel", "Prows", "ldf", "ldc", "npairs")]
 
 

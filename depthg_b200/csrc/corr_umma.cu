@@ -4,7 +4,7 @@
 // and depth_feature_correlation (/root/reference/src/modules.py:1231-1278) — but one
 // CTA owns a whole (pair k, image b) tile and nothing P x P ever leaves the SM:
 //
-//   warp 0   TMA producer : streams K-chunks of the split panels into a 4 x 32 KB smem ring
+//   warp 0   TMA producer : streams K-chunks of the split panels into a 3 x 64 KB smem ring
 //   warp 1   MMA issuer   : one elected lane issues tcgen05.mma; accumulators live in TMEM
 //              fd[128x128]  = F1 . F2^T   bf16 hi/lo split, 3 products per K-step (hh + hl + lh)
 //              cd[128x128]  = C1 . C2^T   tf32 hi/lo split, 3 products (fp32-grade: the clamp
@@ -13,9 +13,9 @@
 //              rowmean (pointwise centring), clamp, loss sums and the unit-gradient factor
 //              U[p,q] = -(fd' - shift) 1[clamp passes] / (B P^2), writes U as bf16 hi/lo into
 //              smem in the canonical 128B-swizzled layout, then
-//   warp 1   again        : dC1[p,:]  = U . C2n        (A = U K-major,  B = C2n^T K-major)
-//                           dC2^T[:,q] = C1n^T . U      (A = C1n^T K-major, B = U MN-major)
-//   warps 2-5 drain dC1 / dC2^T from TMEM to HBM.  For the intra pair the depth term repeats
+//   warp 1   again        : dC1[p,:] = U . C2n      (A = U K-major,          B = bf16 code rows, MN-major)
+//                           dC2[q,:] = U^T . C1n    (A = same U tile, MN-major, B = bf16 code rows, MN-major)
+//   warps 2-5 drain dC1 / dC2 from TMEM to HBM.  For the intra pair the depth term repeats
 //   the last two steps with U_d = -(s_p s_q - depth_shift) 1[..] / (B P^2).
 //
 // Every mbarrier wait is bounded; on a timeout the CTA raises an error flag (the losses
@@ -28,16 +28,15 @@ namespace dg {
 using namespace umma;
 
 constexpr int UM_THREADS = 192;
-constexpr int UM_NSTAGE = 4;
-constexpr int UM_STAGE = 32768;
-constexpr int UM_UBYTES = 65536;  // U hi (32 KB) + U lo (32 KB), bf16 [2 q-atoms][128 p][64 q]
-constexpr int UM_SMEM = UM_NSTAGE * UM_STAGE + UM_UBYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int UM_NSTAGE = 3;
+constexpr int UM_STAGE = 65536;  // one ring stage; the U tiles (bf16 hi + lo, 2 x 32 KB) alias the stage the loads no longer need
+constexpr int UM_SMEM = UM_NSTAGE * UM_STAGE + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr uint32_t TM_FD = 0, TM_CD = 128, TM_D1 = 256, TM_D2 = 384;
 
 struct UmmaParams {
-  CUtensorMap tm_fhi, tm_flo;  // bf16 [npairs*B*128, ldf]   box 32 x 128, SWIZZLE_64B
+  CUtensorMap tm_fhi, tm_flo;  // bf16 [npairs*B*128, ldf]   box 64 x 128, SWIZZLE_128B
   CUtensorMap tm_chi, tm_clo;  // f32  [npairs*B*128, ldc]   box 32 x 128, SWIZZLE_128B
-  CUtensorMap tm_thi, tm_tlo;  // bf16 [npairs*B*128, 128]   box 64 x 128, SWIZZLE_128B (transposed code)
+  CUtensorMap tm_bhi, tm_blo;  // bf16 [npairs*B*128, ldc]   box 32 x 128, SWIZZLE_64B (gradient GEMM operands)
   const float* dsign;          // [B,128] or null
   const float* dots;           // [npairs,B] <mean row of F1[b], mean row of F2[k,b]> (pointwise) or null
   int npairs, B, P, ldf, ldc, flags, has_depth;
@@ -86,11 +85,8 @@ __device__ __forceinline__ void store_u_chunk(uint8_t* u_hi, uint8_t* u_lo, int 
 
 __global__ void __launch_bounds__(UM_THREADS, 1) corr_umma_kernel(const __grid_constant__ UmmaParams prm) {
   extern __shared__ uint8_t um_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(um_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* ring = smem;
-  uint8_t* u_hi = smem + UM_NSTAGE * UM_STAGE;
-  uint8_t* u_lo = u_hi + 32768;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(u_lo + 32768);
+  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(um_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + UM_NSTAGE * UM_STAGE);
   uint64_t* full = bars;                  // [UM_NSTAGE]
   uint64_t* empty = bars + UM_NSTAGE;     // [UM_NSTAGE]
   uint64_t* acc_full = bars + 2 * UM_NSTAGE;
@@ -102,10 +98,14 @@ __global__ void __launch_bounds__(UM_THREADS, 1) corr_umma_kernel(const __grid_c
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kb = blockIdx.x;
   const int k = kb / prm.B, b = kb - k * prm.B;
-  const int nfd = prm.ldf / 32, ncd = prm.ldc / 32;
-  const int njobs = nfd + 2 * ncd + 4;
+  const int nfd = (prm.ldf + 63) / 64, ncd = prm.ldc / 32, nb = prm.ldc / 32;
+  const int njobs = nfd + ncd + 2;
   const int row1 = b * 128, row2 = (k * prm.B + b) * 128;  // panel rows of the first / second operand
+  const bool same = (k == 0);                               // intra pair: second operand == first, load it once
   const bool depth_round = prm.has_depth && k == 0;
+  // job -> stage is j % 3: the two gradient-operand jobs come last, U takes the stage after them
+  uint8_t* u_hi = ring + ((njobs % UM_NSTAGE) * UM_STAGE);
+  uint8_t* u_lo = u_hi + 32768;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < UM_NSTAGE; ++s) {
@@ -127,29 +127,31 @@ __global__ void __launch_bounds__(UM_THREADS, 1) corr_umma_kernel(const __grid_c
     // ================================ TMA producer ================================
     if (lane == 0) {
       prefetch_tmap(&prm.tm_fhi); prefetch_tmap(&prm.tm_flo); prefetch_tmap(&prm.tm_chi);
-      prefetch_tmap(&prm.tm_clo); prefetch_tmap(&prm.tm_thi); prefetch_tmap(&prm.tm_tlo);
+      prefetch_tmap(&prm.tm_clo); prefetch_tmap(&prm.tm_bhi); prefetch_tmap(&prm.tm_blo);
       for (int j = 0; j < njobs; ++j) {
         const int s = j % UM_NSTAGE;
         const uint32_t ph = (j / UM_NSTAGE) & 1;
         if (!mbar_wait(&empty[s], ph ^ 1)) { raise(prm.err, 1); break; }
         uint8_t* st = ring + s * UM_STAGE;
-        mbar_arrive_expect_tx(&full[s], UM_STAGE);
-        if (j < nfd) {                       // fd chunk: 4 tiles of [128 rows x 32 bf16]
-          const int c0 = j * 32;
-          tma_load_2d(st, &prm.tm_fhi, &full[s], c0, row1);
-          tma_load_2d(st + 8192, &prm.tm_flo, &full[s], c0, row1);
-          tma_load_2d(st + 16384, &prm.tm_fhi, &full[s], c0, row2);
-          tma_load_2d(st + 24576, &prm.tm_flo, &full[s], c0, row2);
-        } else if (j < nfd + 2 * ncd) {      // cd chunk: job A = first operand hi/lo, job B = second operand
-          const int jj = j - nfd, c0 = (jj >> 1) * 32, r = (jj & 1) ? row2 : row1;
-          tma_load_2d(st, &prm.tm_chi, &full[s], c0, r);
-          tma_load_2d(st + 16384, &prm.tm_clo, &full[s], c0, r);
-        } else {                             // gradient operands: transposed code tiles [128 d x 128 p]
-          const int g = j - nfd - 2 * ncd;   // 0: T2 hi, 1: T2 lo, 2: T1 hi, 3: T1 lo
-          const CUtensorMap* m = (g & 1) ? &prm.tm_tlo : &prm.tm_thi;
-          const int r = (g < 2) ? row2 : row1;
-          tma_load_2d(st, m, &full[s], 0, r);
-          tma_load_2d(st + 16384, m, &full[s], 64, r);
+        if (j < nfd + ncd) {  // operand chunks: [first hi | first lo | second hi | second lo], 16 KB each
+          const bool isf = j < nfd;
+          const int c0 = isf ? j * 64 : (j - nfd) * 32;
+          const CUtensorMap* mh = isf ? &prm.tm_fhi : &prm.tm_chi;
+          const CUtensorMap* ml = isf ? &prm.tm_flo : &prm.tm_clo;
+          mbar_arrive_expect_tx(&full[s], same ? 32768u : 65536u);
+          tma_load_2d(st, mh, &full[s], c0, row1);
+          tma_load_2d(st + 16384, ml, &full[s], c0, row1);
+          if (!same) {
+            tma_load_2d(st + 32768, mh, &full[s], c0, row2);
+            tma_load_2d(st + 49152, ml, &full[s], c0, row2);
+          }
+        } else {              // gradient operands: bf16 code rows [128 x ldc] as ldc/32 boxes of [128 x 64 B]; hi @0, lo @32 KB
+          const int r = (j == nfd + ncd) ? row2 : row1;
+          mbar_arrive_expect_tx(&full[s], (uint32_t)(2 * nb * 8192));
+          for (int a = 0; a < nb; ++a) {
+            tma_load_2d(st + a * 8192, &prm.tm_bhi, &full[s], a * 32, r);
+            tma_load_2d(st + 32768 + a * 8192, &prm.tm_blo, &full[s], a * 32, r);
+          }
         }
       }
     }
@@ -158,49 +160,44 @@ __global__ void __launch_bounds__(UM_THREADS, 1) corr_umma_kernel(const __grid_c
     if (lane == 0) {
       const uint32_t id_f = instr_desc(FMT_BF16, 128, 128, 0, 0);
       const uint32_t id_c = instr_desc(FMT_TF32, 128, 128, 0, 0);
-      const uint32_t id_g1 = instr_desc(FMT_BF16, 128, (uint32_t)prm.ldc, 0, 0);
-      const uint32_t id_g2 = instr_desc(FMT_BF16, 128, 128, 0, 1);
+      const uint32_t id_g1 = instr_desc(FMT_BF16, 128, (uint32_t)prm.ldc, 0, 1);  // A = U K-major,   B = code rows MN-major
+      const uint32_t id_g2 = instr_desc(FMT_BF16, 128, (uint32_t)prm.ldc, 1, 1);  // A = U^T MN-major, B = code rows MN-major
       bool ok = true;
       int j = 0;
-      for (; j < nfd && ok; ++j) {
+      for (; j < nfd + ncd && ok; ++j) {
         const int s = j % UM_NSTAGE;
         ok = mbar_wait(&full[s], (j / UM_NSTAGE) & 1);
         tc_fence_after_sync();
-        const uint32_t st = smem_u32(ring + s * UM_STAGE);
+        const uint32_t a0 = smem_u32(ring + s * UM_STAGE);
+        const uint32_t b0 = same ? a0 : a0 + 32768;
+        const bool isf = j < nfd;
+        const uint32_t acc_col = isf ? TM_FD : TM_CD;
+        const int first = isf ? 0 : nfd;
 #pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
-          const uint64_t ah = smem_desc(st + ks * 32, 16, 512, SW_64B), al = smem_desc(st + 8192 + ks * 32, 16, 512, SW_64B);
-          const uint64_t bh = smem_desc(st + 16384 + ks * 32, 16, 512, SW_64B),
-                         bl = smem_desc(st + 24576 + ks * 32, 16, 512, SW_64B);
-          mma_f16(tmem + TM_FD, ah, bh, id_f, (j | ks) != 0);
-          mma_f16(tmem + TM_FD, ah, bl, id_f, 1);
-          mma_f16(tmem + TM_FD, al, bh, id_f, 1);
+        for (int ks = 0; ks < 4; ++ks) {  // 4 x 32 B per 128 B row: K=16 bf16 or K=8 tf32 per instruction
+          const uint64_t ah = smem_desc(a0 + ks * 32, 16, 1024, SW_128B), al = smem_desc(a0 + 16384 + ks * 32, 16, 1024, SW_128B);
+          const uint64_t bh = smem_desc(b0 + ks * 32, 16, 1024, SW_128B), bl = smem_desc(b0 + 16384 + ks * 32, 16, 1024, SW_128B);
+          const uint32_t acc0 = (j != first || ks != 0) ? 1u : 0u;
+          if (isf) {
+            mma_f16(tmem + acc_col, ah, bh, id_f, acc0);
+            mma_f16(tmem + acc_col, ah, bl, id_f, 1);
+            mma_f16(tmem + acc_col, al, bh, id_f, 1);
+          } else {
+            mma_tf32(tmem + acc_col, ah, bh, id_c, acc0);
+            mma_tf32(tmem + acc_col, ah, bl, id_c, 1);
+            mma_tf32(tmem + acc_col, al, bh, id_c, 1);
+          }
         }
         mma_commit(&empty[s]);
       }
-      for (int c = 0; c < ncd && ok; ++c, j += 2) {
-        const int sa = j % UM_NSTAGE, sb = (j + 1) % UM_NSTAGE;
-        ok = mbar_wait(&full[sa], (j / UM_NSTAGE) & 1) && mbar_wait(&full[sb], ((j + 1) / UM_NSTAGE) & 1);
-        tc_fence_after_sync();
-        const uint32_t a0 = smem_u32(ring + sa * UM_STAGE), b0 = smem_u32(ring + sb * UM_STAGE);
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          const uint64_t ah = smem_desc(a0 + ks * 32, 16, 1024, SW_128B), al = smem_desc(a0 + 16384 + ks * 32, 16, 1024, SW_128B);
-          const uint64_t bh = smem_desc(b0 + ks * 32, 16, 1024, SW_128B), bl = smem_desc(b0 + 16384 + ks * 32, 16, 1024, SW_128B);
-          mma_tf32(tmem + TM_CD, ah, bh, id_c, (c | ks) != 0);
-          mma_tf32(tmem + TM_CD, ah, bl, id_c, 1);
-          mma_tf32(tmem + TM_CD, al, bh, id_c, 1);
-        }
-        mma_commit(&empty[sa]);
-        mma_commit(&empty[sb]);
-      }
       mma_commit(acc_full);
-      // gradient operands: jobs j..j+3 (T2 hi, T2 lo, T1 hi, T1 lo), one ring stage each
-      uint32_t gst[4];
-      for (int g = 0; g < 4 && ok; ++g) {
-        const int s = (j + g) % UM_NSTAGE;
-        ok = mbar_wait(&full[s], ((j + g) / UM_NSTAGE) & 1);
-        gst[g] = smem_u32(ring + s * UM_STAGE);
+      // gradient operands: job j = second operand's code rows, job j+1 = first operand's
+      uint32_t g2 = 0, g1 = 0;
+      if (ok) {
+        ok = mbar_wait(&full[j % UM_NSTAGE], (j / UM_NSTAGE) & 1) &&
+             mbar_wait(&full[(j + 1) % UM_NSTAGE], ((j + 1) / UM_NSTAGE) & 1);
+        g2 = smem_u32(ring + (j % UM_NSTAGE) * UM_STAGE);
+        g1 = smem_u32(ring + ((j + 1) % UM_NSTAGE) * UM_STAGE);
       }
       const uint32_t uh = smem_u32(u_hi), ul = smem_u32(u_lo);
       const int rounds = depth_round ? 2 : 1;
@@ -208,23 +205,23 @@ __global__ void __launch_bounds__(UM_THREADS, 1) corr_umma_kernel(const __grid_c
         ok = mbar_wait(u_ready, rd & 1);
         tc_fence_after_sync();
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {  // dC1[p, d] += U[p, q-block] . C2n^T[d, q-block]^T
-          const uint32_t off = (ks >> 2) * 16384 + (ks & 3) * 32;
-          const uint64_t a_h = smem_desc(uh + off, 16, 1024, SW_128B), a_l = smem_desc(ul + off, 16, 1024, SW_128B);
-          const uint64_t b_h = smem_desc(gst[0] + off, 16, 1024, SW_128B), b_l = smem_desc(gst[1] + off, 16, 1024, SW_128B);
+        for (int ks = 0; ks < 8; ++ks) {  // dC1[p, d] += U[p, 16 q] . C2n[16 q, d]
+          const uint32_t aoff = (ks >> 2) * 16384 + (ks & 3) * 32;            // U as K-major A: 128 B rows, 64-q atoms 16 KB apart
+          const uint64_t a_h = smem_desc(uh + aoff, 16, 1024, SW_128B), a_l = smem_desc(ul + aoff, 16, 1024, SW_128B);
+          // code rows as MN-major B (n = d contiguous): 16 k-rows (q) per step = 1024 B; 32-d atoms 8192 B apart (LBO); 8-row groups 512 B (SBO)
+          const uint64_t b_h = smem_desc(g2 + ks * 1024, 8192, 512, SW_64B), b_l = smem_desc(g2 + 32768 + ks * 1024, 8192, 512, SW_64B);
           mma_f16(tmem + TM_D1, a_h, b_h, id_g1, ks != 0);
           mma_f16(tmem + TM_D1, a_h, b_l, id_g1, 1);
           mma_f16(tmem + TM_D1, a_l, b_h, id_g1, 1);
         }
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {  // dC2^T[d, q] += C1n^T[d, p-block] . U[p-block, q]
-          const uint32_t aoff = (ks >> 2) * 16384 + (ks & 3) * 32;
-          const uint64_t a_h = smem_desc(gst[2] + aoff, 16, 1024, SW_128B), a_l = smem_desc(gst[3] + aoff, 16, 1024, SW_128B);
-          // U as MN-major B: 16 k-rows (p) per step = 2048 B; atoms of 64 q are 16384 B apart (LBO), 8-row groups 1024 B (SBO)
-          const uint64_t b_h = smem_desc(uh + ks * 2048, 16384, 1024, SW_128B), b_l = smem_desc(ul + ks * 2048, 16384, 1024, SW_128B);
+        for (int ks = 0; ks < 8; ++ks) {  // dC2[q, d] += U[16 p, q]^T . C1n[16 p, d]
+          // U as MN-major A (m = q contiguous): 16 k-rows (p) per step = 2048 B; 64-q atoms 16384 B apart (LBO); 8-row groups 1024 B (SBO)
+          const uint64_t a_h = smem_desc(uh + ks * 2048, 16384, 1024, SW_128B), a_l = smem_desc(ul + ks * 2048, 16384, 1024, SW_128B);
+          const uint64_t b_h = smem_desc(g1 + ks * 1024, 8192, 512, SW_64B), b_l = smem_desc(g1 + 32768 + ks * 1024, 8192, 512, SW_64B);
           mma_f16(tmem + TM_D2, a_h, b_h, id_g2, ks != 0);
-          mma_f16(tmem + TM_D2, a_l, b_h, id_g2, 1);
           mma_f16(tmem + TM_D2, a_h, b_l, id_g2, 1);
+          mma_f16(tmem + TM_D2, a_l, b_h, id_g2, 1);
         }
         mma_commit(grad_full);
       }
@@ -233,7 +230,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) corr_umma_kernel(const __grid_c
   } else {
     // ================================ epilogue (warps 2..5) ================================
     const int lg = warp & 3;                 // TMEM lane group this warp may access
-    const int p = 32 * lg + lane;            // row of fd / cd / dC1; row (= channel d) of dC2^T
+    const int p = 32 * lg + lane;            // row of fd / cd / dC1 / dC2 handled by this thread
     const uint32_t tlane = tmem + ((uint32_t)(32 * lg) << 16);
     const int P = prm.P;
     const bool pointwise = prm.flags & DG_FLAG_POINTWISE;
@@ -309,26 +306,18 @@ __global__ void __launch_bounds__(UM_THREADS, 1) corr_umma_kernel(const __grid_c
       const size_t slab = (size_t)prm.B * 128 * prm.ldc;
       const size_t which = (rd == 0) ? (size_t)k : (size_t)prm.npairs;
       float* d1 = prm.dC1 + which * slab + ((size_t)b * 128 + p) * prm.ldc;
-      for (int cc = 0; cc < ncd; ++cc) {  // dC1 row p: ldc contiguous floats
+      float* d2 = prm.dC2 + which * slab + ((size_t)b * 128 + p) * prm.ldc;
+      for (int cc = 0; cc < ncd; ++cc) {  // rows p of dC1 and dC2: ldc contiguous floats each
         tmem_ld_32x32(tlane + TM_D1 + 32 * cc, v);
+        tmem_ld_32x32(tlane + TM_D2 + 32 * cc, c);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
+        for (int i = 0; i < 8; ++i) {
           *reinterpret_cast<float4*>(d1 + 32 * cc + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-      }
-      if (32 * lg < prm.ldc) {  // dC2^T row = channel d (this thread), columns = q: lanes write consecutive d
-        float* d2 = prm.dC2 + which * slab + (size_t)b * 128 * prm.ldc + p;
-        for (int cc = 0; cc < 4; ++cc) {
-          tmem_ld_32x32(tlane + TM_D2 + 32 * cc, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) d2[(size_t)(32 * cc + i) * prm.ldc] = v[i];
+          *reinterpret_cast<float4*>(d2 + 32 * cc + 4 * i) = make_float4(c[4 * i], c[4 * i + 1], c[4 * i + 2], c[4 * i + 3]);
         }
       }
       if (rd + 1 < rounds) {  // depth term: U_d = -(s_p s_q - depth_shift) 1[clamp passes] / (B P^2)
-        tc_fence_before_sync();
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // all epilogue warps have drained D1 / D2 of round 0
-        tc_fence_after_sync();
 #pragma unroll 1
         for (int cc = 0; cc < 4; ++cc) {
           tmem_ld_32x32(tlane + TM_CD + 32 * cc, c);
@@ -421,12 +410,12 @@ int corr_loss_umma(const dg_panels_t* pan, const float* fmean, int nsplit, const
   UmmaParams prm;
   const uint64_t rows = (uint64_t)npairs * B * 128;
   int rc;
-  if ((rc = make_map_2d(&prm.tm_fhi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, pan->f_hi, ldf, rows, 32, 128, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
-  if ((rc = make_map_2d(&prm.tm_flo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, pan->f_lo, ldf, rows, 32, 128, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+  if ((rc = make_map_2d(&prm.tm_fhi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, pan->f_hi, ldf, rows, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if ((rc = make_map_2d(&prm.tm_flo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, pan->f_lo, ldf, rows, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   if ((rc = make_map_2d(&prm.tm_chi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, pan->c_hi, ldc, rows, 32, 128, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   if ((rc = make_map_2d(&prm.tm_clo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, pan->c_lo, ldc, rows, 32, 128, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
-  if ((rc = make_map_2d(&prm.tm_thi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, pan->ct_hi, 128, rows, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
-  if ((rc = make_map_2d(&prm.tm_tlo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, pan->ct_lo, 128, rows, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if ((rc = make_map_2d(&prm.tm_bhi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, pan->cb_hi, ldc, rows, 32, 128, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+  if ((rc = make_map_2d(&prm.tm_blo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, pan->cb_lo, ldc, rows, 32, 128, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
   // workspace: [err int (256 B)][dots npairs*B floats, padded to 256 B][partials npairs*B*4 floats]
   int* err = static_cast<int*>(ws);
   float* dots = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + 256);

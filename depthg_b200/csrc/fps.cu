@@ -20,7 +20,7 @@
 
 namespace dg {
 
-constexpr int FPS_THREADS = 256;
+constexpr int FPS_THREADS = 128;  // 4 warps: the 120-round argmax chain is issue/latency bound, fewer warps = cheaper rounds
 constexpr int FPS_WARPS = FPS_THREADS / 32;
 
 template <int PPT>
@@ -124,15 +124,11 @@ __global__ void __launch_bounds__(FPS_THREADS) fps_kernel(const float* __restric
       s_idx[buf][warp] = wi;
     }
     __syncthreads();
-    int gk = -1, gi = 0x7fffffff;
-#pragma unroll
-    for (int w = 0; w < FPS_WARPS; ++w) {
-      const int k = s_key[buf][w], i = s_idx[buf][w];
-      if (k > gk || (k == gk && i < gi)) {
-        gk = k;
-        gi = i;
-      }
-    }
+    // every warp folds the FPS_WARPS candidates with the same two redux ops
+    const int ck = lane < FPS_WARPS ? s_key[buf][lane] : -1;
+    const int ci = lane < FPS_WARPS ? s_idx[buf][lane] : 0x7fffffff;
+    const int gk = __reduce_max_sync(0xffffffffu, ck);
+    const int gi = __reduce_min_sync(0xffffffffu, ck == gk ? ci : 0x7fffffff);
     last = gi;
     if ((last % FPS_THREADS) == tid) {
       const int j = last / FPS_THREADS;
@@ -212,18 +208,18 @@ int launch_fps(const float* depth_a, const float* depth_b, int B, int Hd, int Wd
   DG_REQUIRE(npts <= 4096, DG_ERR_UNSUPPORTED, "dg_fps_coords: H*W=%d > 4096 not supported", npts);
   const int nimg = depth_b ? 2 * B : B;
   const size_t smem = (size_t)npts * (3 * sizeof(float) + 1);
-  if (npts <= 4 * FPS_THREADS) {
+  if (npts <= 7 * FPS_THREADS) {
     DG_PRE(st);
-    fps_kernel<4><<<nimg, FPS_THREADS, smem, st>>>(depth_a, depth_b, B, Hd, Wd, H, W, S * S, factor, far_plane,
+    fps_kernel<7><<<nimg, FPS_THREADS, smem, st>>>(depth_a, depth_b, B, Hd, Wd, H, W, S * S, factor, far_plane,
                                                    affine, coords, idx);
-  } else if (npts <= 8 * FPS_THREADS) {
-    DG_PRE(st);
-    fps_kernel<8><<<nimg, FPS_THREADS, smem, st>>>(depth_a, depth_b, B, Hd, Wd, H, W, S * S, factor, far_plane,
-                                                   affine, coords, idx);
-  } else {
-    DG_CUDA_OK(cudaFuncSetAttribute(fps_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  } else if (npts <= 16 * FPS_THREADS) {
     DG_PRE(st);
     fps_kernel<16><<<nimg, FPS_THREADS, smem, st>>>(depth_a, depth_b, B, Hd, Wd, H, W, S * S, factor, far_plane,
+                                                   affine, coords, idx);
+  } else {
+    DG_CUDA_OK(cudaFuncSetAttribute(fps_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DG_PRE(st);
+    fps_kernel<32><<<nimg, FPS_THREADS, smem, st>>>(depth_a, depth_b, B, Hd, Wd, H, W, S * S, factor, far_plane,
                                                     affine, coords, idx);
   }
   DG_LAUNCH_OK("fps_kernel");

@@ -31,7 +31,6 @@ __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& h, __nv_bfloa
 }
 
 // dynamic smem: row staging [GATHER_WARPS][ld] + mean accumulators [GATHER_WARPS][ld]
-//               (+ FMT_CODE_SPLIT: normalised tile [128][ld+1] for the transposed write-out)
 template <int FMT>
 __global__ void __launch_bounds__(GATHER_THREADS)
     gather_norm_kernel(const __grid_constant__ SetTable sets, int B, int C, int H, int W,
@@ -43,7 +42,6 @@ __global__ void __launch_bounds__(GATHER_THREADS)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* row = gsm + (size_t)warp * ld;
   float* macc = gsm + (size_t)(GATHER_WARPS + warp) * ld;
-  float* tile = gsm + (size_t)2 * GATHER_WARPS * ld;  // FMT_CODE_SPLIT only: [128][ld+1]
   const SetDesc& sd = sets.s[set];
   const float* t = sd.src;
   const int64_t sb = sd.sb, sc = sd.sc, sh = sd.sh, sw = sd.sw;
@@ -123,10 +121,11 @@ __global__ void __launch_bounds__(GATHER_THREADS)
           float4 hi = make_float4(umma_tf32(v.x), umma_tf32(v.y), umma_tf32(v.z), umma_tf32(v.w));
           *reinterpret_cast<float4*>(o.out + ro + c) = hi;
           *reinterpret_cast<float4*>(o.out_lo + ro + c) = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
-          if (p < 128) {
-            tile[p * (ld + 1) + c] = v.x; tile[p * (ld + 1) + c + 1] = v.y;
-            tile[p * (ld + 1) + c + 2] = v.z; tile[p * (ld + 1) + c + 3] = v.w;
-          }
+          __nv_bfloat16 h[4], l[4];
+          split_bf16(v.x, h[0], l[0]); split_bf16(v.y, h[1], l[1]);
+          split_bf16(v.z, h[2], l[2]); split_bf16(v.w, h[3], l[3]);
+          *reinterpret_cast<uint2*>(o.hi16 + ro + c) = *reinterpret_cast<uint2*>(h);
+          *reinterpret_cast<uint2*>(o.lo16 + ro + c) = *reinterpret_cast<uint2*>(l);
         }
       }
     } else {
@@ -147,14 +146,17 @@ __global__ void __launch_bounds__(GATHER_THREADS)
           const float hi = umma_tf32(v);
           o.out[ro + c] = hi;
           o.out_lo[ro + c] = v - hi;
-          if (p < 128) tile[p * (ld + 1) + c] = v;
+          __nv_bfloat16 h, l;
+          split_bf16(v, h, l);
+          o.hi16[ro + c] = h;
+          o.lo16[ro + c] = l;
         }
       }
     }
     if (lane == 0) rpanel[p] = r;
     __syncwarp();
   }
-  if (o.meanvec == nullptr && FMT != FMT_CODE_SPLIT) return;
+  if (o.meanvec == nullptr) return;
   __syncthreads();
   if (o.meanvec != nullptr) {
     float* mv = o.meanvec + ((size_t)slot * B + b) * ld;
@@ -164,29 +166,6 @@ __global__ void __launch_bounds__(GATHER_THREADS)
 #pragma unroll
       for (int wdx = 0; wdx < GATHER_WARPS; ++wdx) s += gsm[(size_t)(GATHER_WARPS + wdx) * ld + c];
       mv[c] = s * invP;
-    }
-  }
-  if (FMT == FMT_CODE_SPLIT) {
-    // transposed bf16 hi/lo panels [channel 0..127][point 0..127] (zero outside C x P) for the gradient GEMMs
-    __nv_bfloat16* th = o.t_hi16 + ((size_t)slot * B + b) * 128 * 128;
-    __nv_bfloat16* tl = o.t_lo16 + ((size_t)slot * B + b) * 128 * 128;
-    for (int d = warp; d < 128; d += GATHER_WARPS) {
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int p2 = 2 * (lane + 32 * j);  // two adjacent points per lane -> 4-byte stores
-        float v0 = 0.f, v1 = 0.f;
-        if (d < C) {
-          if (p2 < P) v0 = tile[p2 * (ld + 1) + d];
-          if (p2 + 1 < P) v1 = tile[(p2 + 1) * (ld + 1) + d];
-        }
-        __nv_bfloat16 h0, l0, h1, l1;
-        split_bf16(v0, h0, l0);
-        split_bf16(v1, h1, l1);
-        __nv_bfloat162 hh, ll;
-        hh.x = h0; hh.y = h1; ll.x = l0; ll.y = l1;
-        *reinterpret_cast<__nv_bfloat162*>(th + d * 128 + p2) = hh;
-        *reinterpret_cast<__nv_bfloat162*>(tl + d * 128 + p2) = ll;
-      }
     }
   }
 }
@@ -480,7 +459,6 @@ int launch_gather(int fmt, const SetTable& tab, int nsets, int B, int C, int H, 
     }
   }
   size_t smem = (size_t)2 * GATHER_WARPS * ld * sizeof(float);
-  if (fmt == FMT_CODE_SPLIT) smem += (size_t)128 * (ld + 1) * sizeof(float);
   DG_REQUIRE(smem <= 200 * 1024, DG_ERR_UNSUPPORTED, "gather: C=%d too large for the row staging buffer", C);
 #define DG_GATHER_LAUNCH(F)                                                                                        \
   do {                                                                                                             \
@@ -520,8 +498,8 @@ extern "C" int dg_panel_rows(int P) { return dg::round_up(P, 64); }
 
 extern "C" int dg_gather_norm(const float* t, const int64_t* strides, int B, int C, int H, int W, const float* coords,
                               int S, int nsets, const int32_t* set_coord, const int32_t* set_slot, const int64_t* perm,
-                              float eps, int Prows, int ld, int format, void* out, void* out_lo, void* outT_hi,
-                              void* outT_lo, float* rnorm, float* meanvec, dg_stream_t stream) {
+                              float eps, int Prows, int ld, int format, void* out, void* out_lo, void* out16_hi,
+                              void* out16_lo, float* rnorm, float* meanvec, dg_stream_t stream) {
   using namespace dg;
   DG_REQUIRE(t && strides && coords && out && rnorm, DG_ERR_INVALID, "dg_gather_norm: null pointer");
   DG_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && S > 0, DG_ERR_INVALID, "dg_gather_norm: bad sizes");
@@ -529,18 +507,17 @@ extern "C" int dg_gather_norm(const float* t, const int64_t* strides, int B, int
   DG_REQUIRE(Prows >= S * S, DG_ERR_INVALID, "dg_gather_norm: Prows=%d < S*S=%d", Prows, S * S);
   DG_REQUIRE(format >= DG_PANEL_F32 && format <= DG_PANEL_CODE_SPLIT, DG_ERR_INVALID, "dg_gather_norm: bad format");
   DG_REQUIRE(format == DG_PANEL_F32 || out_lo, DG_ERR_INVALID, "dg_gather_norm: split formats need out_lo");
-  DG_REQUIRE(format != DG_PANEL_CODE_SPLIT || (outT_hi && outT_lo && Prows == 128 && ld <= 128), DG_ERR_INVALID,
-             "dg_gather_norm: code-split format needs transposed outputs, Prows == 128 and ld <= 128");
+  DG_REQUIRE(format != DG_PANEL_CODE_SPLIT || (out16_hi && out16_lo), DG_ERR_INVALID,
+             "dg_gather_norm: code-split format needs the bf16 hi/lo panels too");
   SetTable tab;
   int rc = fill_sets("dg_gather_norm", t, strides, nsets, set_coord, set_slot, perm != nullptr, &tab);
   if (rc != DG_OK) return rc;
   GatherOut o;
   o.out = static_cast<float*>(out);
   o.out_lo = static_cast<float*>(out_lo);
-  o.hi16 = static_cast<__nv_bfloat16*>(out);
-  o.lo16 = static_cast<__nv_bfloat16*>(out_lo);
-  o.t_hi16 = static_cast<__nv_bfloat16*>(outT_hi);
-  o.t_lo16 = static_cast<__nv_bfloat16*>(outT_lo);
+  const bool code = format == DG_PANEL_CODE_SPLIT;
+  o.hi16 = static_cast<__nv_bfloat16*>(code ? out16_hi : out);
+  o.lo16 = static_cast<__nv_bfloat16*>(code ? out16_lo : out_lo);
   o.rnorm = rnorm;
   o.meanvec = meanvec;
   return launch_gather(format, tab, nsets, B, C, H, W, coords, S, perm, eps, Prows, ld, 1, o,

@@ -24,14 +24,12 @@ enum { FMT_F32 = 0, FMT_FEATS_SPLIT = 1, FMT_CODE_SPLIT = 2 };
 struct GatherOut {
   // FMT_F32        : out (fp32 [slot,b,Prows,ld])
   // FMT_FEATS_SPLIT: hi16/lo16 (bf16 [slot,b,Prows,ld]) : x ~= hi + lo
-  // FMT_CODE_SPLIT : out = tf32-rounded hi, out_lo = x - hi (fp32 [slot,b,Prows,ld]);
-  //                  t_hi16/t_lo16 (bf16 [slot,b,128,128]) transposed: row = channel, col = point
+  // FMT_CODE_SPLIT : out = tf32-rounded hi, out_lo = x - hi (fp32 [slot,b,Prows,ld]) for the cd product,
+  //                  hi16/lo16 (bf16 [slot,b,Prows,ld]) the same rows for the gradient GEMMs
   float* out;
   float* out_lo;
   __nv_bfloat16* hi16;
   __nv_bfloat16* lo16;
-  __nv_bfloat16* t_hi16;
-  __nv_bfloat16* t_lo16;
   float* rnorm;
   float* meanvec;
 };

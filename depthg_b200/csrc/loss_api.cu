@@ -51,14 +51,14 @@ static void make_plan(const dg_loss_desc_t* d, dg_loss_plan_t* p) {
   if (p->kernel) {
     p->c_hi = take(np * B * Pr * p->ldc * 4);
     p->c_lo = take(np * B * Pr * p->ldc * 4);
-    p->ct_hi = take(np * B * 128 * 128 * 2);
-    p->ct_lo = take(np * B * 128 * 128 * 2);
+    p->cb_hi = take(np * B * Pr * p->ldc * 2);
+    p->cb_lo = take(np * B * Pr * p->ldc * 2);
     p->f_hi = take(np * B * Pr * p->ldf * 2);
     p->f_lo = take(np * B * Pr * p->ldf * 2);
   } else {
     p->c_hi = take(np * B * Pr * p->ldc * 4);
     p->f_hi = take(np * B * Pr * p->ldf * 4);
-    p->c_lo = p->ct_hi = p->ct_lo = p->f_lo = 0;
+    p->c_lo = p->cb_hi = p->cb_lo = p->f_lo = 0;
   }
   p->total = off;
 }
@@ -128,7 +128,6 @@ extern "C" int dg_loss_forward(const dg_loss_desc_t* d, const dg_loss_io_t* io, 
   o.out_lo = nullptr;
   o.hi16 = reinterpret_cast<__nv_bfloat16*>(A + pl.f_hi);
   o.lo16 = reinterpret_cast<__nv_bfloat16*>(A + pl.f_lo);
-  o.t_hi16 = o.t_lo16 = nullptr;
   o.rnorm = reinterpret_cast<float*>(A + pl.frn);
   o.meanvec = fmean;
   const int ffmt = pl.kernel ? FMT_FEATS_SPLIT : FMT_F32;
@@ -140,9 +139,8 @@ extern "C" int dg_loss_forward(const dg_loss_desc_t* d, const dg_loss_io_t* io, 
   nsets = build_sets(tab, io->code, io->code_strides, io->code_pos, io->code_pos_strides, d->neg_samples);
   o.out = reinterpret_cast<float*>(A + pl.c_hi);
   o.out_lo = pl.kernel ? reinterpret_cast<float*>(A + pl.c_lo) : nullptr;
-  o.hi16 = o.lo16 = nullptr;
-  o.t_hi16 = pl.kernel ? reinterpret_cast<__nv_bfloat16*>(A + pl.ct_hi) : nullptr;
-  o.t_lo16 = pl.kernel ? reinterpret_cast<__nv_bfloat16*>(A + pl.ct_lo) : nullptr;
+  o.hi16 = pl.kernel ? reinterpret_cast<__nv_bfloat16*>(A + pl.cb_hi) : nullptr;
+  o.lo16 = pl.kernel ? reinterpret_cast<__nv_bfloat16*>(A + pl.cb_lo) : nullptr;
   o.rnorm = reinterpret_cast<float*>(A + pl.crn);
   o.meanvec = nullptr;
   rc = launch_gather(pl.kernel ? FMT_CODE_SPLIT : FMT_F32, tab, nsets, B, d->D, d->H, d->W, coords, S, io->perms, kNormEps,
@@ -161,7 +159,7 @@ extern "C" int dg_loss_forward(const dg_loss_desc_t* d, const dg_loss_io_t* io, 
     dg_panels_t pan;
     pan.format = DG_PANEL_CODE_SPLIT;
     pan.f_hi = A + pl.f_hi; pan.f_lo = A + pl.f_lo; pan.c_hi = A + pl.c_hi; pan.c_lo = A + pl.c_lo;
-    pan.ct_hi = A + pl.ct_hi; pan.ct_lo = A + pl.ct_lo;
+    pan.cb_hi = A + pl.cb_hi; pan.cb_lo = A + pl.cb_lo;
     return corr_loss_umma(&pan, fmean, nsplit, dsign, np, B, P, pl.ldf, pl.ldc, shifts, groups, d->depth_feat_shift, kflags,
                           io->out8, dC1, dC2, io->cd_out, io->loss_out, io->dd_out, io->fd_dbg, A + pl.ws, st);
   }

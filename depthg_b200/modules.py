@@ -98,11 +98,11 @@ def _strides(t: torch.Tensor):
 
 
 def _gather(t, coords, S, set_coord, set_slot, perm, eps, Prows, ld, out, rnorm, meanvec, fmt=_lib.PANEL_F32,
-            out_lo=None, outT_hi=None, outT_lo=None):
+            out_lo=None, out16_hi=None, out16_lo=None):
     B, Cdim, H, W = t.shape
     check(_lib.lib().dg_gather_norm(ptr(t), _strides(t), B, Cdim, H, W, ptr(coords), S, len(set_coord),
                                     _lib.i32_array(set_coord), _lib.i32_array(set_slot), ptr(perm), eps, Prows, ld,
-                                    fmt, ptr(out), ptr(out_lo), ptr(outT_hi), ptr(outT_lo), ptr(rnorm), ptr(meanvec),
+                                    fmt, ptr(out), ptr(out_lo), ptr(out16_hi), ptr(out16_lo), ptr(rnorm), ptr(meanvec),
                                     stream_ptr()), "dg_gather_norm")
 
 

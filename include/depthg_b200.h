@@ -50,7 +50,7 @@ enum { DG_GROUP_INTRA = 0, DG_GROUP_INTER = 1, DG_GROUP_NEG = 2, DG_GROUP_DEPTH 
  *   F32         : fp32 rows (generic CUDA-core correlation kernel).
  *   FEATS_SPLIT : two bf16 panels hi/lo with x ~= hi + lo (tcgen05 kind::f16, 3-term product).
  *   CODE_SPLIT  : fp32 hi (tf32-rounded) and lo = x - hi (tcgen05 kind::tf32, 3-term product)
- *                 plus transposed bf16 hi/lo panels [channel 128][point 128] for the gradient GEMMs. */
+ *                 plus bf16 hi/lo panels of the same rows for the gradient GEMMs. */
 enum { DG_PANEL_F32 = 0, DG_PANEL_FEATS_SPLIT = 1, DG_PANEL_CODE_SPLIT = 2 };
 
 /* Flags of ContrastiveCorrelationLoss.helper (src/modules.py:1231-1254). */
@@ -122,14 +122,14 @@ DG_API int dg_depth_sign(const float* depth, int B, int Hd, int Wd, int S, float
  *   out      : [nslots,B,Prows,ld]; row p = h*S+w holds the sample at coordinate
  *              index w*S+h (the reference's axis swap), L2-normalised over C
  *              with eps; rows >= S*S and columns >= C are zero-filled.
- *   format   : DG_PANEL_*; element type / meaning of out, out_lo, outT_hi, outT_lo
- *              as described at the enum (unused ones NULL).
+ *   format   : DG_PANEL_*; element type / meaning of out, out_lo (and, for CODE_SPLIT, the bf16
+ *              panels out16_hi, out16_lo) as described at the enum (unused ones NULL).
  *   rnorm    : [nslots,B,Prows]  1/max(||x||,eps) per row (needed by backward).
  *   meanvec  : [nslots,B,ld]     mean over the S*S rows of the normalised panel
  *              (NULL to skip; needed for pointwise centring). */
 DG_API int dg_gather_norm(const float* t, const int64_t* strides, int B, int C, int H, int W, const float* coords, int S,
                    int nsets, const int32_t* set_coord, const int32_t* set_slot, const int64_t* perm, float eps,
-                   int Prows, int ld, int format, void* out, void* out_lo, void* outT_hi, void* outT_lo,
+                   int Prows, int ld, int format, void* out, void* out_lo, void* out16_hi, void* out16_lo,
                    float* rnorm, float* meanvec, dg_stream_t stream);
 
 /* Backward of dg_gather_norm for the code tensors: combines the unit
@@ -164,7 +164,7 @@ DG_API int dg_gather_norm_bwd(float* grad, const int64_t* strides, int B, int C,
  *           format DG_PANEL_F32   : f_hi = fp32 [npairs,B,Prows,ldf], c_hi = fp32 [npairs,B,Prows,ldc]
  *                                   (generic CUDA-core kernel, any S);
  *           split formats         : f_hi/f_lo bf16 [npairs,B,128,ldf]; c_hi/c_lo fp32 [npairs,B,128,ldc];
- *                                   ct_hi/ct_lo bf16 [npairs,B,128,128] (tcgen05 kernel, S*S <= 128).
+ *                                   cb_hi/cb_lo bf16 [npairs,B,128,ldc] (tcgen05 kernel, S*S <= 128).
  *   fmean : [npairs,B,ldf] panel row means (only read with DG_FLAG_POINTWISE).
  *   dsign : [B,Prows] depth signs from dg_depth_sign, or NULL for no depth term.
  *   pair_shift / pair_group : host [npairs].
@@ -183,8 +183,8 @@ typedef struct dg_panels {
   const void* f_lo;
   const void* c_hi;
   const void* c_lo;
-  const void* ct_hi;
-  const void* ct_lo;
+  const void* cb_hi;
+  const void* cb_lo;
 } dg_panels_t;
 
 DG_API size_t dg_corr_loss_workspace_bytes(int npairs, int B, int P);
@@ -212,7 +212,7 @@ typedef struct dg_loss_desc {
 } dg_loss_desc_t;
 
 typedef struct dg_loss_plan { /* byte offsets into the arena, all 256-byte aligned */
-  size_t total, coords, frn, fmean, crn, f_hi, f_lo, c_hi, c_lo, ct_hi, ct_lo, dsign, dC1, dC2, ws, ws_bytes;
+  size_t total, coords, frn, fmean, crn, f_hi, f_lo, c_hi, c_lo, cb_hi, cb_lo, dsign, dC1, dC2, ws, ws_bytes;
   int kernel; /* 0 = generic CUDA-core kernel, 1 = tcgen05 kernel */
   int Prows, ldf, ldc, npairs;
 } dg_loss_plan_t;

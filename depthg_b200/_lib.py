@@ -30,6 +30,7 @@ SIGNATURES = {
     "dg_last_error_string": (C.c_char_p, []),
     "dg_kernel_launches": (C.c_ulonglong, []),
     "dg_profile_enable": (C.c_int, [C.c_int]),
+    "dg_debug_set_clock_buffer": (C.c_int, [_vp]),
     "dg_profile_collect": (C.c_size_t, [C.c_char_p, C.c_size_t]),
     "dg_panel_ld": (C.c_int, [C.c_int]),
     "dg_panel_rows": (C.c_int, [C.c_int]),

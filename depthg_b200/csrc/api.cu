@@ -86,3 +86,10 @@ extern "C" size_t dg_profile_collect(char* buf, size_t buf_bytes) {
   }
   return out.size() + 1;
 }
+
+namespace dg { void set_clock_buffer(long long* p); }
+// Debug: when non-NULL, the tcgen05 correlation kernel writes [grid][16] globaltimer stamps of its phases there.
+extern "C" int dg_debug_set_clock_buffer(long long* dev_ptr) {
+  dg::set_clock_buffer(dev_ptr);
+  return DG_OK;
+}

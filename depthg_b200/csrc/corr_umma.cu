@@ -20,6 +20,8 @@
 //
 // Every mbarrier wait is bounded; on a timeout the CTA raises an error flag (the losses
 // come back NaN) instead of hanging the GPU.
+#include <stdlib.h>
+
 #include "kernels.cuh"
 #include "umma.cuh"
 
@@ -27,7 +29,8 @@ namespace dg {
 
 using namespace umma;
 
-constexpr int UM_THREADS = 192;
+constexpr int UM_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two warps per TMEM lane group)
+constexpr int UM_EPI = 256;
 constexpr int UM_NSTAGE = 3;
 constexpr int UM_STAGE = 65536;  // one ring stage; the U tiles (bf16 hi + lo, 2 x 32 KB) alias the stage the loads no longer need
 constexpr int UM_SMEM = UM_NSTAGE * UM_STAGE + 1024 /*align slack*/ + 256 /*barriers*/;
@@ -50,7 +53,17 @@ struct UmmaParams {
   float* dd_out;
   float* fd_dbg;    // optional raw fd accumulators [npairs,B,128,128] (tests)
   int* err;         // error flag (0 = ok)
+  long long* clk;   // optional per-CTA phase timestamps [grid][16] (dg_debug_set_clock_buffer)
+  int dbg;          // timing experiments only (DEPTHG_B200_UMMA_DBG): 1 = no TMA loads, 2 = no MMAs
 };
+
+__device__ __forceinline__ void stamp(const UmmaParams& prm, int slot) {
+  if (prm.clk) {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    prm.clk[(size_t)blockIdx.x * 16 + slot] = t;
+  }
+}
 
 __device__ __forceinline__ void raise(int* err, int code) {
   if (err) atomicCAS(err, 0, code);
@@ -71,16 +84,31 @@ __device__ __forceinline__ void store_u_chunk(uint8_t* u_hi, uint8_t* u_lo, int 
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const float a = u[8 * i + 2 * e], b = u[8 * i + 2 * e + 1];
-      const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
-      const __nv_bfloat16 al = __float2bfloat16_rn(a - __bfloat162float(ah));
-      const __nv_bfloat16 bl = __float2bfloat16_rn(b - __bfloat162float(bh));
-      h[e] = pack_bf16(ah, bh);
-      l[e] = pack_bf16(al, bl);
+      const __nv_bfloat162 hh = __floats2bfloat162_rn(a, b);  // .x = a (low half), .y = b
+      const uint32_t hb = *reinterpret_cast<const uint32_t*>(&hh);
+      const float ra = a - __uint_as_float(hb << 16), rb = b - __uint_as_float(hb & 0xffff0000u);
+      const __nv_bfloat162 ll = __floats2bfloat162_rn(ra, rb);
+      h[e] = hb;
+      l[e] = *reinterpret_cast<const uint32_t*>(&ll);
     }
     const uint32_t chunk = ((cc & 1) * 4 + i) ^ (p & 7);  // Swizzle<3,4,3>: 16-byte chunk ^= row % 8
     *reinterpret_cast<uint4*>(row_hi + chunk * 16) = make_uint4(h[0], h[1], h[2], h[3]);
     *reinterpret_cast<uint4*>(row_lo + chunk * 16) = make_uint4(l[0], l[1], l[2], l[3]);
   }
+}
+
+// Drain one 32-row x 32-column accumulator block (this warp's TMEM lanes) to row-major global memory through a
+// per-warp smem scratch so that every store instruction writes one full 128-byte line.
+__device__ __forceinline__ void drain_block(uint32_t taddr, float* scratch /*[32][33]*/, float* dst_rows /*row 0 of the block*/,
+                                            int ldc, int col0, int lane, float* v) {
+  tmem_ld_32x32(taddr, v);
+  tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < 32; ++i) scratch[lane * 33 + i] = v[i];
+  __syncwarp();
+#pragma unroll 8
+  for (int r = 0; r < 32; ++r) dst_rows[(size_t)r * ldc + col0 + lane] = scratch[r * 33 + lane];
+  __syncwarp();
 }
 
 __global__ void __launch_bounds__(UM_THREADS, 1) corr_umma_kernel(const __grid_constant__ UmmaParams prm) {
@@ -93,10 +121,13 @@ __global__ void __launch_bounds__(UM_THREADS, 1) corr_umma_kernel(const __grid_c
   uint64_t* u_ready = acc_full + 1;
   uint64_t* grad_full = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 3);
-  __shared__ float s_red[4][4];
+  __shared__ float s_red[8][4];
+  __shared__ float s_rowsum[2][128];
+  __shared__ float s_sign[128];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kb = blockIdx.x;
+  if (threadIdx.x == 64) stamp(prm, 0);
   const int k = kb / prm.B, b = kb - k * prm.B;
   const int nfd = (prm.ldf + 63) / 64, ncd = prm.ldc / 32, nb = prm.ldc / 32;
   const int njobs = nfd + ncd + 2;
@@ -113,11 +144,13 @@ __global__ void __launch_bounds__(UM_THREADS, 1) corr_umma_kernel(const __grid_c
       mbar_init(&empty[s], 1);
     }
     mbar_init(acc_full, 1);
-    mbar_init(u_ready, 128);
+    mbar_init(u_ready, UM_EPI);
     mbar_init(grad_full, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
+  if (threadIdx.x >= 64 && threadIdx.x < 192)
+    s_sign[threadIdx.x - 64] = depth_round ? __ldg(prm.dsign + (size_t)b * 128 + threadIdx.x - 64) : 0.f;
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -133,6 +166,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) corr_umma_kernel(const __grid_c
         const uint32_t ph = (j / UM_NSTAGE) & 1;
         if (!mbar_wait(&empty[s], ph ^ 1)) { raise(prm.err, 1); break; }
         uint8_t* st = ring + s * UM_STAGE;
+        if (prm.dbg & 1) { mbar_arrive(&full[s]); continue; }
         if (j < nfd + ncd) {  // operand chunks: [first hi | first lo | second hi | second lo], 16 KB each
           const bool isf = j < nfd;
           const int c0 = isf ? j * 64 : (j - nfd) * 32;
@@ -162,63 +196,68 @@ __global__ void __launch_bounds__(UM_THREADS, 1) corr_umma_kernel(const __grid_c
       const uint32_t id_c = instr_desc(FMT_TF32, 128, 128, 0, 0);
       const uint32_t id_g1 = instr_desc(FMT_BF16, 128, (uint32_t)prm.ldc, 0, 1);  // A = U K-major,   B = code rows MN-major
       const uint32_t id_g2 = instr_desc(FMT_BF16, 128, (uint32_t)prm.ldc, 1, 1);  // A = U^T MN-major, B = code rows MN-major
+      // descriptor templates; the start-address field (bits 0..13, address >> 4) is added per tile / K-step
+      const uint64_t dk128 = smem_desc(0, 16, 1024, SW_128B);       // K-major, 128-byte rows
+      const uint64_t dmn128 = smem_desc(0, 16384, 1024, SW_128B);   // MN-major, 64-element atoms 16 KB apart
+      const uint64_t dmn64 = smem_desc(0, 8192, 512, SW_64B);       // MN-major, 32-element atoms 8 KB apart
       bool ok = true;
       int j = 0;
       for (; j < nfd + ncd && ok; ++j) {
         const int s = j % UM_NSTAGE;
         ok = mbar_wait(&full[s], (j / UM_NSTAGE) & 1);
         tc_fence_after_sync();
-        const uint32_t a0 = smem_u32(ring + s * UM_STAGE);
-        const uint32_t b0 = same ? a0 : a0 + 32768;
-        const bool isf = j < nfd;
-        const uint32_t acc_col = isf ? TM_FD : TM_CD;
-        const int first = isf ? 0 : nfd;
+        if (prm.dbg & 2) { mbar_arrive(&empty[s]); continue; }
+        const uint32_t a0 = smem_u32(ring + s * UM_STAGE) >> 4;
+        const uint32_t b0 = same ? a0 : a0 + (32768 >> 4);
+        const uint64_t ah = dk128 + a0, al = ah + (16384 >> 4), bh = dk128 + b0, bl = bh + (16384 >> 4);
+        if (j < nfd) {
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {  // 4 x 32 B per 128 B row: K=16 bf16 or K=8 tf32 per instruction
-          const uint64_t ah = smem_desc(a0 + ks * 32, 16, 1024, SW_128B), al = smem_desc(a0 + 16384 + ks * 32, 16, 1024, SW_128B);
-          const uint64_t bh = smem_desc(b0 + ks * 32, 16, 1024, SW_128B), bl = smem_desc(b0 + 16384 + ks * 32, 16, 1024, SW_128B);
-          const uint32_t acc0 = (j != first || ks != 0) ? 1u : 0u;
-          if (isf) {
-            mma_f16(tmem + acc_col, ah, bh, id_f, acc0);
-            mma_f16(tmem + acc_col, ah, bl, id_f, 1);
-            mma_f16(tmem + acc_col, al, bh, id_f, 1);
-          } else {
-            mma_tf32(tmem + acc_col, ah, bh, id_c, acc0);
-            mma_tf32(tmem + acc_col, ah, bl, id_c, 1);
-            mma_tf32(tmem + acc_col, al, bh, id_c, 1);
+          for (int ks = 0; ks < 4; ++ks) {  // 4 x 32 B per 128 B row: K = 16 bf16 per instruction
+            mma_f16(tmem + TM_FD, ah + 2 * ks, bh + 2 * ks, id_f, (j | ks) != 0);
+            mma_f16(tmem + TM_FD, ah + 2 * ks, bl + 2 * ks, id_f, 1);
+            mma_f16(tmem + TM_FD, al + 2 * ks, bh + 2 * ks, id_f, 1);
+          }
+        } else {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {  // K = 8 tf32 per instruction
+            mma_tf32(tmem + TM_CD, ah + 2 * ks, bh + 2 * ks, id_c, (j != nfd) || ks != 0);
+            mma_tf32(tmem + TM_CD, ah + 2 * ks, bl + 2 * ks, id_c, 1);
+            mma_tf32(tmem + TM_CD, al + 2 * ks, bh + 2 * ks, id_c, 1);
           }
         }
         mma_commit(&empty[s]);
       }
-      mma_commit(acc_full);
+      if (prm.dbg & 2) mbar_arrive(acc_full); else mma_commit(acc_full);
       // gradient operands: job j = second operand's code rows, job j+1 = first operand's
       uint32_t g2 = 0, g1 = 0;
       if (ok) {
         ok = mbar_wait(&full[j % UM_NSTAGE], (j / UM_NSTAGE) & 1) &&
              mbar_wait(&full[(j + 1) % UM_NSTAGE], ((j + 1) / UM_NSTAGE) & 1);
-        g2 = smem_u32(ring + (j % UM_NSTAGE) * UM_STAGE);
-        g1 = smem_u32(ring + ((j + 1) % UM_NSTAGE) * UM_STAGE);
+        g2 = smem_u32(ring + (j % UM_NSTAGE) * UM_STAGE) >> 4;
+        g1 = smem_u32(ring + ((j + 1) % UM_NSTAGE) * UM_STAGE) >> 4;
       }
-      const uint32_t uh = smem_u32(u_hi), ul = smem_u32(u_lo);
+      const uint32_t uh = smem_u32(u_hi) >> 4, ul = smem_u32(u_lo) >> 4;
       const int rounds = depth_round ? 2 : 1;
       for (int rd = 0; rd < rounds && ok; ++rd) {
         ok = mbar_wait(u_ready, rd & 1);
         tc_fence_after_sync();
+        if (prm.dbg & 2) { mbar_arrive(grad_full); continue; }
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {  // dC1[p, d] += U[p, 16 q] . C2n[16 q, d]
-          const uint32_t aoff = (ks >> 2) * 16384 + (ks & 3) * 32;            // U as K-major A: 128 B rows, 64-q atoms 16 KB apart
-          const uint64_t a_h = smem_desc(uh + aoff, 16, 1024, SW_128B), a_l = smem_desc(ul + aoff, 16, 1024, SW_128B);
-          // code rows as MN-major B (n = d contiguous): 16 k-rows (q) per step = 1024 B; 32-d atoms 8192 B apart (LBO); 8-row groups 512 B (SBO)
-          const uint64_t b_h = smem_desc(g2 + ks * 1024, 8192, 512, SW_64B), b_l = smem_desc(g2 + 32768 + ks * 1024, 8192, 512, SW_64B);
+          // U as K-major A: 32 B per K-step inside a 128 B row, the second 64-q atom 16 KB further;
+          // code rows as MN-major B (n = d contiguous): 16 k-rows (q) per step = 1024 B
+          const uint32_t aoff = ((ks >> 2) * 16384 + (ks & 3) * 32) >> 4;
+          const uint64_t a_h = dk128 + uh + aoff, a_l = dk128 + ul + aoff;
+          const uint64_t b_h = dmn64 + g2 + ks * 64, b_l = b_h + (32768 >> 4);
           mma_f16(tmem + TM_D1, a_h, b_h, id_g1, ks != 0);
           mma_f16(tmem + TM_D1, a_h, b_l, id_g1, 1);
           mma_f16(tmem + TM_D1, a_l, b_h, id_g1, 1);
         }
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {  // dC2[q, d] += U[16 p, q]^T . C1n[16 p, d]
-          // U as MN-major A (m = q contiguous): 16 k-rows (p) per step = 2048 B; 64-q atoms 16384 B apart (LBO); 8-row groups 1024 B (SBO)
-          const uint64_t a_h = smem_desc(uh + ks * 2048, 16384, 1024, SW_128B), a_l = smem_desc(ul + ks * 2048, 16384, 1024, SW_128B);
-          const uint64_t b_h = smem_desc(g1 + ks * 1024, 8192, 512, SW_64B), b_l = smem_desc(g1 + 32768 + ks * 1024, 8192, 512, SW_64B);
+          // the same U tile as MN-major A (m = q contiguous): 16 k-rows (p) per step = 2048 B
+          const uint64_t a_h = dmn128 + uh + ks * 128, a_l = dmn128 + ul + ks * 128;
+          const uint64_t b_h = dmn64 + g1 + ks * 64, b_l = b_h + (32768 >> 4);
           mma_f16(tmem + TM_D2, a_h, b_h, id_g2, ks != 0);
           mma_f16(tmem + TM_D2, a_h, b_l, id_g2, 1);
           mma_f16(tmem + TM_D2, a_l, b_h, id_g2, 1);
@@ -228,106 +267,129 @@ __global__ void __launch_bounds__(UM_THREADS, 1) corr_umma_kernel(const __grid_c
       if (!ok) raise(prm.err, 2);
     }
   } else {
-    // ================================ epilogue (warps 2..5) ================================
+    // ================================ epilogue (warps 2..9) ================================
+    // two warps per TMEM lane group; the pair splits the 128 columns in halves
     const int lg = warp & 3;                 // TMEM lane group this warp may access
+    const int half = (warp - 2) >> 2;        // 0: columns 0..63, 1: columns 64..127
+    const int ew = warp - 2;                 // 0..7
     const int p = 32 * lg + lane;            // row of fd / cd / dC1 / dC2 handled by this thread
     const uint32_t tlane = tmem + ((uint32_t)(32 * lg) << 16);
     const int P = prm.P;
     const bool pointwise = prm.flags & DG_FLAG_POINTWISE;
     const float lo = (prm.flags & DG_FLAG_ZERO_CLAMP) ? 0.f : -9999.f;
     const float hi = (prm.flags & DG_FLAG_STABALIZE) ? 0.8f : __int_as_float(0x7f800000);
-    const float shift = prm.shift[k];
     float old_mean = 0.f;  // mean of fd over (b,p,q) of this pair = mean_b <mean row F1[b], mean row F2[k,b]>
     if (pointwise && prm.dots) {
-      for (int bb = 0; bb < prm.B; ++bb) old_mean += __ldg(prm.dots + (size_t)k * prm.B + bb);
-      old_mean /= (float)prm.B;
+      float part = 0.f;
+      for (int bb = lane; bb < prm.B; bb += 32) part += __ldg(prm.dots + (size_t)k * prm.B + bb);
+      old_mean = warp_sum(part) / (float)prm.B;
     }
-    const float sp = depth_round ? __ldg(prm.dsign + (size_t)b * 128 + p) : 0.f;
+    const float sp = s_sign[p];
+    const float inv = (p < P) ? prm.inv_cnt : 0.f;
+    const float dsh = prm.depth_shift;
     float sum_loss = 0.f, sum_cd = 0.f, sum_dloss = 0.f, sum_dd = 0.f;
     float v[32], c[32];
 
+    if (threadIdx.x == 64) stamp(prm, 1);
     bool ok = mbar_wait(acc_full, 0);
     tc_fence_after_sync();
-    float rowmean = 0.f;
-    if (pointwise) {
+    if (threadIdx.x == 64) stamp(prm, 2);
+    float c0 = prm.shift[k] - old_mean;      // fd' - shift = fd - rowmean + old_mean - shift = fd - c0
+    if (pointwise) {                         // rowmean over q: padded columns are exactly zero, no mask needed
       float s = 0.f;
 #pragma unroll
-      for (int cc = 0; cc < 4; ++cc) {
-        tmem_ld_32x32(tlane + TM_FD + 32 * cc, v);
+      for (int h2 = 0; h2 < 2; ++h2) {
+        tmem_ld_32x32(tlane + TM_FD + 32 * (2 * half + h2), v);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (32 * cc + i < P) s += v[i];
+        for (int i = 0; i < 32; ++i) s += v[i];
       }
-      rowmean = s / (float)P;
+      s_rowsum[half][p] = s;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      c0 += (s_rowsum[0][p] + s_rowsum[1][p]) / (float)P;
     }
-    const size_t obase = (((size_t)k * prm.B + b) * P + p) * P;
+    if (threadIdx.x == 64) stamp(prm, 3);
+    // ---- main pass: branch-free.  Padded rows/columns have fd = cd = 0 and depth sign 0, so they add nothing to
+    //      the sums; only U needs the explicit mask (inv = 0 for padded rows, tail zeroing for padded columns).
 #pragma unroll 1
-    for (int cc = 0; cc < 4; ++cc) {
+    for (int h2 = 0; h2 < 2; ++h2) {
+      const int cc = 2 * half + h2;
       tmem_ld_32x32(tlane + TM_FD + 32 * cc, v);
       tmem_ld_32x32(tlane + TM_CD + 32 * cc, c);
       tmem_ld_wait();
-      if (prm.fd_dbg) {
-        float* dst = prm.fd_dbg + ((size_t)kb * 128 + p) * 128 + 32 * cc;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) dst[i] = v[i];
-      }
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
-        const int q = 32 * cc + i;
-        const bool valid = (p < P) && (q < P);
         const float cdv = c[i];
         const float cl = fminf(fmaxf(cdv, lo), hi);
-        const bool pass = valid && (cdv >= lo) && (cdv <= hi);
-        const float f = v[i] - rowmean + old_mean - shift;
-        if (valid) {
-          sum_loss += -cl * f;
-          sum_cd += cdv;
-          if (prm.cd_out) prm.cd_out[obase + q] = cdv;
-          if (prm.loss_out) prm.loss_out[obase + q] = -cl * f;
-          if (depth_round) {
-            const float dd = sp * __ldg(prm.dsign + (size_t)b * 128 + q);
-            sum_dloss += -cl * (dd - prm.depth_shift);
-            sum_dd += dd;
-            if (prm.dd_out) prm.dd_out[((size_t)b * P + p) * P + q] = dd;
-          }
-        }
-        v[i] = pass ? -f * prm.inv_cnt : 0.f;
+        const float f = v[i] - c0;
+        const float dd = sp * s_sign[32 * cc + i];
+        sum_loss = fmaf(-cl, f, sum_loss);
+        sum_cd += cdv;
+        sum_dloss = fmaf(-cl, dd - dsh, sum_dloss);
+        sum_dd += dd;
+        const bool pass = (cdv >= lo) && (cdv <= hi);
+        v[i] = pass ? -f * inv : 0.f;
+      }
+      if (32 * cc + 32 > P) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (32 * cc + i >= P) v[i] = 0.f;
       }
       store_u_chunk(u_hi, u_lo, p, cc, v);
     }
+    // ---- optional dense outputs (materialize_cd / tests): a separate pass keeps the main one lean
+    if (prm.cd_out || prm.loss_out || prm.dd_out || prm.fd_dbg) {
+      const size_t obase = (((size_t)k * prm.B + b) * P + p) * P;
+      for (int h2 = 0; h2 < 2; ++h2) {
+        const int cc = 2 * half + h2;
+        tmem_ld_32x32(tlane + TM_FD + 32 * cc, v);
+        tmem_ld_32x32(tlane + TM_CD + 32 * cc, c);
+        tmem_ld_wait();
+        if (prm.fd_dbg) {
+          float* dst = prm.fd_dbg + ((size_t)kb * 128 + p) * 128 + 32 * cc;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) dst[i] = v[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int q = 32 * cc + i;
+          if (p < P && q < P) {
+            const float cl = fminf(fmaxf(c[i], lo), hi);
+            if (prm.cd_out) prm.cd_out[obase + q] = c[i];
+            if (prm.loss_out) prm.loss_out[obase + q] = -cl * (v[i] - c0);
+            if (prm.dd_out && depth_round) prm.dd_out[((size_t)b * P + p) * P + q] = sp * s_sign[q];
+          }
+        }
+      }
+    }
     const int rounds = depth_round ? 2 : 1;
+    if (threadIdx.x == 64) stamp(prm, 4);
+    float* scratch = reinterpret_cast<float*>(u_hi) + ew * (32 * 33);  // per-warp transpose buffer, aliases U once it is dead
     for (int rd = 0; rd < rounds; ++rd) {
       fence_proxy_async_smem();
       tc_fence_before_sync();
       mbar_arrive(u_ready);
       ok = ok && mbar_wait(grad_full, rd & 1);
       tc_fence_after_sync();
+      if (threadIdx.x == 64) stamp(prm, 5 + 2 * rd);
+      // U is dead until it is rewritten below: drain through it.  half 0 drains dC1, half 1 drains dC2.
       const size_t slab = (size_t)prm.B * 128 * prm.ldc;
       const size_t which = (rd == 0) ? (size_t)k : (size_t)prm.npairs;
-      float* d1 = prm.dC1 + which * slab + ((size_t)b * 128 + p) * prm.ldc;
-      float* d2 = prm.dC2 + which * slab + ((size_t)b * 128 + p) * prm.ldc;
-      for (int cc = 0; cc < ncd; ++cc) {  // rows p of dC1 and dC2: ldc contiguous floats each
-        tmem_ld_32x32(tlane + TM_D1 + 32 * cc, v);
-        tmem_ld_32x32(tlane + TM_D2 + 32 * cc, c);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          *reinterpret_cast<float4*>(d1 + 32 * cc + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-          *reinterpret_cast<float4*>(d2 + 32 * cc + 4 * i) = make_float4(c[4 * i], c[4 * i + 1], c[4 * i + 2], c[4 * i + 3]);
-        }
-      }
+      float* dbase = (half == 0 ? prm.dC1 : prm.dC2) + which * slab + ((size_t)b * 128 + 32 * lg) * prm.ldc;
+      const uint32_t tacc = tlane + (half == 0 ? TM_D1 : TM_D2);
+      for (int cc = 0; cc < ncd; ++cc) drain_block(tacc + 32 * cc, scratch, dbase, prm.ldc, 32 * cc, lane, v);
+      if (threadIdx.x == 64) stamp(prm, 6 + 2 * rd);
       if (rd + 1 < rounds) {  // depth term: U_d = -(s_p s_q - depth_shift) 1[clamp passes] / (B P^2)
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // every warp is done with its scratch before U is rewritten
 #pragma unroll 1
-        for (int cc = 0; cc < 4; ++cc) {
+        for (int h2 = 0; h2 < 2; ++h2) {
+          const int cc = 2 * half + h2;
           tmem_ld_32x32(tlane + TM_CD + 32 * cc, c);
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            const int q = 32 * cc + i;
-            const bool pass = (p < P) && (q < P) && (c[i] >= lo) && (c[i] <= hi);
-            const float dd = sp * __ldg(prm.dsign + (size_t)b * 128 + q);
-            v[i] = pass ? -(dd - prm.depth_shift) * prm.inv_cnt : 0.f;
+            const bool pass = (32 * cc + i < P) && (c[i] >= lo) && (c[i] <= hi);
+            v[i] = pass ? -(sp * s_sign[32 * cc + i] - dsh) * inv : 0.f;
           }
           store_u_chunk(u_hi, u_lo, p, cc, v);
         }
@@ -339,28 +401,35 @@ __global__ void __launch_bounds__(UM_THREADS, 1) corr_umma_kernel(const __grid_c
     sum_dloss = warp_sum(sum_dloss);
     sum_dd = warp_sum(sum_dd);
     if (lane == 0) {
-      s_red[lg][0] = sum_loss; s_red[lg][1] = sum_cd; s_red[lg][2] = sum_dloss; s_red[lg][3] = sum_dd;
+      s_red[ew][0] = sum_loss; s_red[ew][1] = sum_cd; s_red[ew][2] = sum_dloss; s_red[ew][3] = sum_dd;
     }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    if (warp == 2 && lane < 4)
-      prm.partials[(size_t)kb * 4 + lane] = s_red[0][lane] + s_red[1][lane] + s_red[2][lane] + s_red[3][lane];
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (ew == 0 && lane < 4) {
+      float t = 0.f;
+#pragma unroll
+      for (int w8 = 0; w8 < 8; ++w8) t += s_red[w8][lane];
+      prm.partials[(size_t)kb * 4 + lane] = t;
+    }
   }
+  if (threadIdx.x == 64) stamp(prm, 9);
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, 512);
+  if (threadIdx.x == 64) stamp(prm, 10);
 }
 
-// dots[k,b] = < mean_p F1n[b,p,:], mean_q F2n[k,b,q,:] >  (one warp each); block 0 also clears the error flag
+// dots[k,b] = < mean_p F1n[b,p,:], mean_q F2n[k,b,q,:] >  (one 256-thread block each, all loads in flight at once);
+// block 0 also clears the error flag
 __global__ void __launch_bounds__(256) pair_dots_kernel(const float* __restrict__ fmean, int nsplit, int npairs, int B,
                                                         int ldf, float* __restrict__ dots, int* __restrict__ err) {
+  __shared__ float red[8];
   if (blockIdx.x == 0 && threadIdx.x == 0 && err) *err = 0;
-  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (w >= npairs * B || fmean == nullptr) return;
-  const int k = w / B, b = w - k * B;
+  if (fmean == nullptr) return;
+  const int w = blockIdx.x, k = w / B, b = w - k * B;
   const float* m1 = fmean + (size_t)b * nsplit * ldf;                      // nsplit partial means each
   const float* m2 = fmean + ((size_t)k * B + b) * nsplit * ldf;
   float s = 0.f;
-  for (int c = lane; c < ldf; c += 32) {
+  for (int c = threadIdx.x; c < ldf; c += 256) {
     float a = 0.f, bb = 0.f;
     for (int i = 0; i < nsplit; ++i) {
       a += __ldg(m1 + (size_t)i * ldf + c);
@@ -369,8 +438,18 @@ __global__ void __launch_bounds__(256) pair_dots_kernel(const float* __restrict_
     s += a * bb;
   }
   s = warp_sum(s);
-  if (lane == 0) dots[w] = s;
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i];
+    dots[w] = t;
+  }
 }
+
+static long long* g_clk = nullptr;  // debug: device buffer for per-CTA phase timestamps
+void set_clock_buffer(long long* p) { g_clk = p; }
 
 // ------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -430,10 +509,15 @@ int corr_loss_umma(const dg_panels_t* pan, const float* fmean, int nsplit, const
   for (int k = 0; k < npairs; ++k) prm.shift[k] = pair_shift[k];
   prm.dC1 = dC1; prm.dC2 = dC2; prm.partials = partials;
   prm.cd_out = cd_out; prm.loss_out = loss_out; prm.dd_out = dd_out; prm.fd_dbg = fd_dbg; prm.err = err;
+  prm.clk = g_clk;
+  {
+    const char* e = getenv("DEPTHG_B200_UMMA_DBG");
+    prm.dbg = e ? atoi(e) : 0;
+  }
   {
     const float* fm = (flags & DG_FLAG_POINTWISE) ? fmean : nullptr;
     DG_PRE(st);
-    pair_dots_kernel<<<ceil_div(npairs * B * 32, 256), 256, 0, st>>>(fm, nsplit, npairs, B, ldf, dots, err);
+    pair_dots_kernel<<<npairs * B, 256, 0, st>>>(fm, nsplit, npairs, B, ldf, dots, err);
     DG_LAUNCH_OK("pair_dots_kernel");
   }
   static bool attr_set = false;

@@ -65,6 +65,8 @@ DG_API unsigned long long dg_kernel_launches(void);
  * (returns the buffer size needed).  Enabling/disabling clears the records. */
 DG_API int dg_profile_enable(int on);
 DG_API size_t dg_profile_collect(char* buf, size_t buf_bytes);
+/* Debug: device buffer [grid][16] int64 receiving %globaltimer stamps of the tcgen05 kernel phases (NULL = off). */
+DG_API int dg_debug_set_clock_buffer(long long* dev_ptr);
 
 /* Pitch (in floats) of a panel row holding `channels` values: rounded up to a
  * multiple of 32 so a row is a whole number of 128-byte lines. */

@@ -23,28 +23,43 @@ namespace dg {
 constexpr int FPS_THREADS = 128;  // 4 warps: the 120-round argmax chain is issue/latency bound, fewer warps = cheaper rounds
 constexpr int FPS_WARPS = FPS_THREADS / 32;
 
-template <int PPT>
+// STAGE: the whole [Hd,Wd] depth image is first copied into shared memory with 16-byte cp.async
+// (every load in flight at once), so the pooling reads never wait on DRAM one window row at a time.
+template <int PPT, bool STAGE>
 __global__ void __launch_bounds__(FPS_THREADS) fps_kernel(const float* __restrict__ depth_a,
                                                           const float* __restrict__ depth_b, int B, int Hd, int Wd,
                                                           int H, int W, int nsel, float factor, float far_plane,
                                                           int affine, float* __restrict__ coords,
                                                           int32_t* __restrict__ idx_out) {
-  extern __shared__ float fps_smem[];
+  extern __shared__ __align__(16) float fps_smem[];
   const int npts = H * W;
+  const int npad = (npts + 3) & ~3;
   float* sX = fps_smem;
-  float* sY = sX + npts;
-  float* sZ = sY + npts;
-  unsigned char* sTaken = reinterpret_cast<unsigned char*>(sZ + npts);
+  float* sY = sX + npad;
+  float* sZ = sY + npad;
+  unsigned char* sTaken = reinterpret_cast<unsigned char*>(sZ + npad);
+  float* sImg = reinterpret_cast<float*>(sTaken + ((npts + 15) & ~15));
   __shared__ int s_key[2][FPS_WARPS];
   __shared__ int s_idx[2][FPS_WARPS];
   __shared__ int s_scan[FPS_WARPS];
 
   const int img = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const float* depth = (img < B ? depth_a + (size_t)img * Hd * Wd : depth_b + (size_t)(img - B) * Hd * Wd);
+  const float* gdepth = (img < B ? depth_a + (size_t)img * Hd * Wd : depth_b + (size_t)(img - B) * Hd * Wd);
+  const float* depth = gdepth;
+  if (STAGE) {
+    const int n16 = (Hd * Wd) >> 2;
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(sImg);
+    for (int i = tid; i < n16; i += FPS_THREADS)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + 16u * i), "l"(gdepth + 4 * (size_t)i) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    depth = sImg;
+  }
 
   float X[PPT], Y[PPT], Z[PPT];
-  int key[PPT];  // int view of the running min distance; -1 once taken
+  int key[PPT];  // int view of the running min distance; -1 once taken (or not a point)
   const float halfH = (float)H / 2.0f, halfW = (float)W / 2.0f;
 
 #pragma unroll
@@ -58,30 +73,22 @@ __global__ void __launch_bounds__(FPS_THREADS) fps_kernel(const float* __restric
       const int xs = (px * Wd) / W, xe = ((px + 1) * Wd + W - 1) / W;
       float acc = 0.f;
       if (xe - xs == 8 && ye - ys == 8 && (Wd & 3) == 0 && (xs & 3) == 0) {
-        // the common 8x8 window: issue all sixteen 128-bit loads first (one DRAM round trip instead of
-        // eight dependent ones), then add in the reference's row-major order
+        // the common 8x8 window: all sixteen 128-bit loads first, then add in the reference's row-major order
         float4 v[16];
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
           const float4* row = reinterpret_cast<const float4*>(depth + (size_t)(ys + r) * Wd + xs);
-          v[2 * r] = __ldg(row);
-          v[2 * r + 1] = __ldg(row + 1);
+          v[2 * r] = row[0];
+          v[2 * r + 1] = row[1];
         }
 #pragma unroll
         for (int r = 0; r < 16; ++r) {
           acc = __fadd_rn(acc, v[r].x); acc = __fadd_rn(acc, v[r].y);
           acc = __fadd_rn(acc, v[r].z); acc = __fadd_rn(acc, v[r].w);
         }
-      } else if (xe - xs == 8 && (Wd & 3) == 0 && (xs & 3) == 0) {
-        for (int y = ys; y < ye; ++y) {
-          const float4* row = reinterpret_cast<const float4*>(depth + (size_t)y * Wd + xs);
-          const float4 a = __ldg(row), b = __ldg(row + 1);
-          acc = __fadd_rn(acc, a.x); acc = __fadd_rn(acc, a.y); acc = __fadd_rn(acc, a.z); acc = __fadd_rn(acc, a.w);
-          acc = __fadd_rn(acc, b.x); acc = __fadd_rn(acc, b.y); acc = __fadd_rn(acc, b.z); acc = __fadd_rn(acc, b.w);
-        }
       } else {
         for (int y = ys; y < ye; ++y)
-          for (int x = xs; x < xe; ++x) acc = __fadd_rn(acc, __ldg(depth + (size_t)y * Wd + x));
+          for (int x = xs; x < xe; ++x) acc = __fadd_rn(acc, depth[(size_t)y * Wd + x]);
       }
       const float pooled = __fdiv_rn(__fdiv_rn(acc, (float)(ye - ys)), (float)(xe - xs));  // ATen: sum / kh / kw
       const float fd = __fmul_rn(factor, pooled);
@@ -104,17 +111,15 @@ __global__ void __launch_bounds__(FPS_THREADS) fps_kernel(const float* __restric
     const float lx = sX[last], ly = sY[last], lz = sZ[last];
     int bk = -1, bi = 0x7fffffff;
 #pragma unroll
-    for (int j = 0; j < PPT; ++j) {
-      if (key[j] >= 0) {
-        const float dx = __fsub_rn(lx, X[j]), dy = __fsub_rn(ly, Y[j]), dz = __fsub_rn(lz, Z[j]);
-        const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-        const int k = min(key[j], __float_as_int(d));  // both non-negative floats -> int order == float order
-        key[j] = k;
-        if (k > bk) {  // strict: the lowest index wins ties inside a thread (j ascending)
-          bk = k;
-          bi = j * FPS_THREADS + tid;
-        }
-      }
+    for (int j = 0; j < PPT; ++j) {  // branch-free so the PPT independent chains interleave
+      const float dx = __fsub_rn(lx, X[j]), dy = __fsub_rn(ly, Y[j]), dz = __fsub_rn(lz, Z[j]);
+      const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+      const int kj = key[j];
+      const int k = kj < 0 ? -1 : min(kj, __float_as_int(d));  // non-negative floats: int order == float order
+      key[j] = k;
+      const bool better = k > bk;  // strict: the lowest index wins ties inside a thread (j ascending)
+      bk = better ? k : bk;
+      bi = better ? j * FPS_THREADS + tid : bi;
     }
     const int wk = __reduce_max_sync(0xffffffffu, bk);
     const int wi = __reduce_min_sync(0xffffffffu, bk == wk ? bi : 0x7fffffff);
@@ -130,12 +135,14 @@ __global__ void __launch_bounds__(FPS_THREADS) fps_kernel(const float* __restric
     const int gk = __reduce_max_sync(0xffffffffu, ck);
     const int gi = __reduce_min_sync(0xffffffffu, ck == gk ? ci : 0x7fffffff);
     last = gi;
-    if ((last % FPS_THREADS) == tid) {
-      const int j = last / FPS_THREADS;
+    if (((last % FPS_THREADS) >> 5) == warp) {  // warp-uniform: only the owner's warp enters
+      if ((last % FPS_THREADS) == tid) {
+        const int j = last / FPS_THREADS;
 #pragma unroll
-      for (int jj = 0; jj < PPT; ++jj)
-        if (jj == j) key[jj] = -1;
-      sTaken[last] = 1;
+        for (int jj = 0; jj < PPT; ++jj)
+          if (jj == j) key[jj] = -1;
+        sTaken[last] = 1;
+      }
     }
   }
   __syncthreads();
@@ -207,21 +214,30 @@ int launch_fps(const float* depth_a, const float* depth_b, int B, int Hd, int Wd
   DG_REQUIRE(S * S <= npts, DG_ERR_INVALID, "dg_fps_coords: S*S=%d exceeds H*W=%d points", S * S, npts);
   DG_REQUIRE(npts <= 4096, DG_ERR_UNSUPPORTED, "dg_fps_coords: H*W=%d > 4096 not supported", npts);
   const int nimg = depth_b ? 2 * B : B;
-  const size_t smem = (size_t)npts * (3 * sizeof(float) + 1);
+  const size_t base_smem = (size_t)((npts + 3) & ~3) * 3 * sizeof(float) + (size_t)((npts + 15) & ~15);
+  const size_t img_bytes = (size_t)Hd * Wd * sizeof(float);
+  const bool stage = ((Hd * Wd) % 4 == 0) && (base_smem + img_bytes <= 220 * 1024) &&
+                     ((reinterpret_cast<uintptr_t>(depth_a) | reinterpret_cast<uintptr_t>(depth_b)) % 16 == 0);
+  const size_t smem = base_smem + (stage ? img_bytes : 0);
+#define DG_FPS_LAUNCH(PPT, ST)                                                                                    \
+  do {                                                                                                            \
+    static size_t configured = 0;                                                                                 \
+    if (smem > 48 * 1024 && smem > configured) {                                                                  \
+      DG_CUDA_OK(cudaFuncSetAttribute(fps_kernel<PPT, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      configured = smem;                                                                                          \
+    }                                                                                                             \
+    DG_PRE(st);                                                                                                   \
+    fps_kernel<PPT, ST><<<nimg, FPS_THREADS, smem, st>>>(depth_a, depth_b, B, Hd, Wd, H, W, S * S, factor,          \
+                                                          far_plane, affine, coords, idx);                          \
+  } while (0)
   if (npts <= 7 * FPS_THREADS) {
-    DG_PRE(st);
-    fps_kernel<7><<<nimg, FPS_THREADS, smem, st>>>(depth_a, depth_b, B, Hd, Wd, H, W, S * S, factor, far_plane,
-                                                   affine, coords, idx);
+    if (stage) DG_FPS_LAUNCH(7, true); else DG_FPS_LAUNCH(7, false);
   } else if (npts <= 16 * FPS_THREADS) {
-    DG_PRE(st);
-    fps_kernel<16><<<nimg, FPS_THREADS, smem, st>>>(depth_a, depth_b, B, Hd, Wd, H, W, S * S, factor, far_plane,
-                                                   affine, coords, idx);
+    if (stage) DG_FPS_LAUNCH(16, true); else DG_FPS_LAUNCH(16, false);
   } else {
-    DG_CUDA_OK(cudaFuncSetAttribute(fps_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    DG_PRE(st);
-    fps_kernel<32><<<nimg, FPS_THREADS, smem, st>>>(depth_a, depth_b, B, Hd, Wd, H, W, S * S, factor, far_plane,
-                                                    affine, coords, idx);
+    DG_FPS_LAUNCH(32, false);
   }
+#undef DG_FPS_LAUNCH
   DG_LAUNCH_OK("fps_kernel");
   return DG_OK;
 }

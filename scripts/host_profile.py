@@ -20,24 +20,19 @@ def timeit(name, f, n=300):
     t1 = time.perf_counter()
     torch.cuda.synchronize()
     t2 = time.perf_counter()
-    print(f"{name:40s} host {1e6*(t1-t0)/n:8.1f} us/iter   incl. drain {1e6*(t2-t0)/n:8.1f} us/iter")
+    print(f"{name:44s} host {1e6*(t1-t0)/n:8.1f} us/iter   incl. drain {1e6*(t2-t0)/n:8.1f} us/iter")
 
-timeit("super_perms(5,32)", lambda: M.super_perms(5, 32, dev))
-timeit("randperm x5", lambda: [torch.randperm(32, device=dev) for _ in range(5)])
-timeit("torch.empty(150MB)", lambda: torch.empty(151066112, device=dev, dtype=torch.uint8))
+timeit("super_perms eager(5,32)", lambda: M.super_perms(5, 32, dev))
+timeit("super_perms graphed(5,32)", lambda: M._GraphedSuperPerms.draw(5, 32, dev))
+timeit("fused_super_perms(5,32)", lambda: M.fused_super_perms(5, 32, dev))
 def fwd():
     return fn(s["feats"], s["feats_pos"], None, None, s["code"], s["code_pos"], s["depth"], s["depth_pos"])
 with torch.no_grad():
     timeit("forward (no grad)", fwd)
 timeit("forward (grad mode)", fwd)
-def fwd_w():
-    return bench.weighted(fwd())
-timeit("forward + weighted()", fwd_w)
 def full():
     s["code"].grad = None; s["code_pos"].grad = None
-    bench.weighted(fwd()).backward()
-timeit("forward + weighted + backward", full)
-fixed = torch.stack([M.super_perm(32, dev) for _ in range(5)])
-it = iter(())
-fn.perm_fn = lambda B, d: fixed[0]
-timeit("full, perm_fn hook (5 x stack of fixed)", full)
+    bench.backprop(fwd())
+timeit("forward + backprop", full)
+fn.negative_sampler = "fused"
+timeit("forward + backprop, fused sampler", full)

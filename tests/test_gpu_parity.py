@@ -420,3 +420,20 @@ def test_grad_tensors_backprop_equals_weighted_sum_backward():
         grads.append((code.grad.clone(), code_pos.grad.clone()))
     assert rel_err(grads[0][0].cpu().numpy(), grads[1][0].cpu().numpy()) < 1e-6
     assert rel_err(grads[0][1].cpu().numpy(), grads[1][1].cpu().numpy()) < 1e-6
+
+
+def test_graphed_super_perms_reproduce_the_eager_torch_stream():
+    """The CUDA-graph replay of neg_samples x torch.randperm must give the eager calls' permutations
+    (same seed -> same stream), call after call, and advance the generator identically."""
+    from depthg_b200.modules import _GraphedSuperPerms, super_perms
+    _GraphedSuperPerms._cache.clear()
+    torch.manual_seed(1234)
+    eager = [super_perms(5, 32, dev()).clone() for _ in range(4)]
+    tail_eager = torch.rand(3, device=dev())
+    torch.manual_seed(1234)
+    graphed = [_GraphedSuperPerms.draw(5, 32, dev()) for _ in range(4)]
+    tail_graphed = torch.rand(3, device=dev())
+    assert _GraphedSuperPerms._cache[(5, 32, dev().index)] is not False, "graph capture failed"
+    for a, b in zip(eager, graphed):
+        assert torch.equal(a, b)
+    assert torch.equal(tail_eager, tail_graphed)

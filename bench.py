@@ -18,6 +18,8 @@ import sys
 import threading
 import time
 
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout: the contract is ONE JSON line
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
@@ -249,6 +251,7 @@ def main():
         s["code"].requires_grad_(True)
         s["code_pos"].requires_grad_(True)
     head_grad = torch.zeros(HEAD_GRAD_FLOATS, device=dev) if world > 1 else None
+    pending = [None]
 
     def step(i):
         s = sets[i % NSETS]
@@ -256,12 +259,17 @@ def main():
         s["code_pos"].grad = None
         out = loss_fn(s["feats"], s["feats_pos"], None, None, s["code"], s["code_pos"], s["depth"], s["depth_pos"])
         backprop(out)
-        if world > 1:   # DDP semantics: the only exchange is the head-gradient all-reduce
-            dist.all_reduce(head_grad)
+        if world > 1:   # DDP semantics: the only exchange is the head-gradient all-reduce; like DDP it is
+            if pending[0] is not None:   # asynchronous and only has to land before the next optimiser step
+                pending[0].wait()
+            pending[0] = dist.all_reduce(head_grad, async_op=True)
         return out
 
     def barrier():
         if world > 1:
+            if pending[0] is not None:
+                pending[0].wait()
+                pending[0] = None
             dist.barrier()
         torch.cuda.synchronize()
 

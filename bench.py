@@ -441,7 +441,8 @@ def main():
                "k": k, "scaling": "strong", "sharding": "query rows; all-gather of the feature database",
                "roofline": {"bound": "tensor", "achieved": flops / (kms / 1e3) / 1e12, "peak": tf_burst,
                             "unit": "TFLOP/s", "frac": flops / (kms / 1e3) / 1e12 / tf_burst,
-                            "note": "fp32 CUDA-core similarity in this round; peak is the bf16 tensor burst figure"}}
+                            "note": "tcgen05 bf16 3-product split (3 MMAs per useful product) + exact fp32 re-rank; "
+                                    "flops counted once (2 N^2 F), peak is the bf16 tensor burst figure"}}
 
     # ---- CPU baseline (oracle port) on this box's host cores, rank 0 at N=1 only
     cpu_baseline = None

@@ -1,0 +1,14 @@
+import sys, os, ctypes
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from depthg_b200 import _lib
+from depthg_b200.precompute_knns import knn_topk
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 49629
+x = torch.nn.functional.normalize(torch.randn(N, 768, device="cuda"), dim=1)
+knn_topk(x, x, 30); torch.cuda.synchronize()
+lib = _lib.lib()
+lib.dg_profile_enable(1)
+knn_topk(x, x, 30)
+n = lib.dg_profile_collect(None, 0); buf = ctypes.create_string_buffer(n + 16); lib.dg_profile_collect(buf, n + 16)
+lib.dg_profile_enable(0)
+print(buf.value.decode())

@@ -91,7 +91,7 @@ class LossIO(C.Structure):
     _fields_ = [("feats", _vp), ("feats_pos", _vp), ("code", _vp), ("code_pos", _vp),
                 ("feats_strides", _i64x4), ("feats_pos_strides", _i64x4), ("code_strides", _i64x4),
                 ("code_pos_strides", _i64x4), ("depth", _vp), ("depth_pos", _vp), ("coords", _vp), ("perms", _vp),
-                ("arena", _vp), ("out8", _vp), ("cd_out", _vp), ("loss_out", _vp), ("dd_out", _vp), ("fd_dbg", _vp)]
+                ("arena", _vp), ("out8", _vp), ("cd_out", _vp), ("loss_out", _vp), ("dd_out", _vp), ("fd_dbg", _vp), ("perms_ready", _vp)]
 
 
 class LossGrads(C.Structure):

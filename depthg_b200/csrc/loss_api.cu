@@ -120,6 +120,7 @@ extern "C" int dg_loss_forward(const dg_loss_desc_t* d, const dg_loss_io_t* io, 
     rc = launch_depth_sign(io->depth, B, d->Hd, d->Wd, S, kNormEps, pl.Prows, dsign, st);
     if (rc != DG_OK) return rc;
   }
+  if (io->perms_ready) DG_CUDA_OK(cudaStreamWaitEvent(st, reinterpret_cast<cudaEvent_t>(io->perms_ready), 0));
   SetTable tab;
   GatherOut o;
   // backbone features

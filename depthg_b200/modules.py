@@ -91,6 +91,8 @@ class _GraphedSuperPerms:
 
     _cache = {}
 
+    _side = {}
+
     @classmethod
     def draw(cls, n: int, size: int, device) -> torch.Tensor:
         device = torch.device(device)
@@ -104,6 +106,24 @@ class _GraphedSuperPerms:
         graph, out = entry
         graph.replay()
         return out.clone()   # the graph's output buffer is overwritten by the next replay
+
+    @classmethod
+    def draw_async(cls, n: int, size: int, device):
+        """Replay on a side stream so the ~25 tiny sampler kernels overlap FPS on the main stream.
+        Returns (perms, event); the consumer stream must wait for the event before reading perms."""
+        device = torch.device(device)
+        main = torch.cuda.current_stream(device)
+        if cls._cache.get((n, size, device.index)) in (None, False) or torch.cuda.is_current_stream_capturing():
+            return cls.draw(n, size, device), None
+        side = cls._side.get(device.index)
+        if side is None:
+            side = cls._side[device.index] = torch.cuda.Stream(device=device)
+        with torch.cuda.stream(side):
+            perms = cls.draw(n, size, device)
+            ev = torch.cuda.Event()
+            ev.record(side)
+        perms.record_stream(main)   # allocated on the side stream, consumed on the main one
+        return perms, ev
 
     @staticmethod
     def _capture(n, size, device):
@@ -255,7 +275,8 @@ class _CorrLossFn(torch.autograd.Function):
     last_unit_grads = None
 
     @staticmethod
-    def forward(ctx, feats, feats_pos, code, code_pos, depth, depth_pos, coords, perms, desc, materialize):
+    def forward(ctx, feats, feats_pos, code, code_pos, depth, depth_pos, coords, perms, desc, materialize,
+                perms_event=None):
         lib = _lib.lib()
         dev = feats.device
         plan = _lib.LossPlan()
@@ -285,6 +306,7 @@ class _CorrLossFn(torch.autograd.Function):
         io.coords = coords.data_ptr() if coords is not None else None
         io.perms = perms.data_ptr() if perms is not None else None
         io.arena, io.out8 = arena.data_ptr(), out8.data_ptr()
+        io.perms_ready = perms_event.cuda_event if perms_event is not None else None
         for name, t in (("cd_out", cd_out), ("loss_out", loss_out), ("dd_out", dd_out), ("fd_dbg", fd_dbg)):
             setattr(io, name, t.data_ptr() if t is not None else None)
         check(lib.dg_loss_forward(C.byref(desc), C.byref(io), stream_ptr(dev.index)), "dg_loss_forward")
@@ -331,7 +353,7 @@ class _CorrLossFn(torch.autograd.Function):
         io.perms = perms.data_ptr() if perms is not None else None
         check(_lib.lib().dg_loss_backward(C.byref(ctx.desc), C.byref(io), C.byref(gr), stream_ptr(arena.device.index)),
               "dg_loss_backward")
-        return (None, None, d_code, d_code_pos) + (None,) * 6
+        return (None, None, d_code, d_code_pos) + (None,) * 7
 
 
 class ContrastiveCorrelationLoss(nn.Module):
@@ -395,6 +417,7 @@ class ContrastiveCorrelationLoss(nn.Module):
         dev = orig_feats.device
         flags = self._flags()
         coords = None
+        perms_event = None
         if cfg.depth_sampling == "fps":
             if depth is None or depth_pos is None:
                 raise ValueError("depth_sampling='fps' needs depth and depth_pos")
@@ -414,7 +437,7 @@ class ContrastiveCorrelationLoss(nn.Module):
         elif self.negative_sampler == "fused":
             perms = fused_super_perms(nneg, B, dev)
         elif self.graph_negative_sampler:
-            perms = _GraphedSuperPerms.draw(nneg, B, dev)
+            perms, perms_event = _GraphedSuperPerms.draw_async(nneg, B, dev)
         else:
             perms = super_perms(nneg, B, dev)
 
@@ -439,7 +462,7 @@ class ContrastiveCorrelationLoss(nn.Module):
                              float(cfg.pos_inter_shift), float(cfg.neg_inter_shift),
                              float(cfg.depth_feat_shift) if depth_term else 0.0)
         res = _CorrLossFn.apply(orig_feats, orig_feats_pos, orig_code, orig_code_pos, depth, depth_pos, coords, perms,
-                                desc, bool(self.materialize_cd))
+                                desc, bool(self.materialize_cd), perms_event)
         intra, inter, neg, dloss, out8, coords_used, cd_out, loss_out, dd_out = res
         self.last_coords = coords_used if (flags & _lib.FLAG_FPS) else coords
         if self.materialize_cd:

@@ -235,6 +235,8 @@ typedef struct dg_loss_io {
   float* loss_out;
   float* dd_out;
   float* fd_dbg;
+  void* perms_ready;      /* optional cudaEvent_t: `perms` is produced on another stream; the gathers wait for it
+                             (FPS and the depth signs, which do not need perms, are enqueued before the wait) */
 } dg_loss_io_t;
 
 typedef struct dg_loss_grads {

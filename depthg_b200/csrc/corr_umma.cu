@@ -45,6 +45,9 @@ struct UmmaParams {
   int npairs, B, P, ldf, ldc, flags, has_depth;
   float depth_shift, inv_cnt;
   float shift[DG_MAX_PAIRS];
+  int32_t group[DG_MAX_PAIRS];
+  float* out8;      // the 8 scalars of the output tuple, written by the last CTA to finish
+  int* done;        // CTA completion counter (zeroed by pair_dots_kernel)
   float* dC1;       // [npairs+1,B,128,ldc]
   float* dC2;       // [npairs+1,B,128,ldc]
   float* partials;  // [npairs*B][4]
@@ -404,11 +407,54 @@ __global__ void __launch_bounds__(UM_THREADS, 1) corr_umma_kernel(const __grid_c
       s_red[ew][0] = sum_loss; s_red[ew][1] = sum_cd; s_red[ew][2] = sum_dloss; s_red[ew][3] = sum_dd;
     }
     asm volatile("bar.sync 1, 256;" ::: "memory");
-    if (ew == 0 && lane < 4) {
-      float t = 0.f;
+    if (ew == 0) {
+      if (lane < 4) {
+        float t = 0.f;
 #pragma unroll
-      for (int w8 = 0; w8 < 8; ++w8) t += s_red[w8][lane];
-      prm.partials[(size_t)kb * 4 + lane] = t;
+        for (int w8 = 0; w8 < 8; ++w8) t += s_red[w8][lane];
+        prm.partials[(size_t)kb * 4 + lane] = t;
+      }
+      // ---- fused finalize: the last CTA to get here folds all partial sums into the 8 output scalars
+      __threadfence();
+      __syncwarp();
+      int ticket = 0;
+      if (lane == 0) ticket = atomicAdd(prm.done, 1);
+      ticket = __shfl_sync(0xffffffffu, ticket, 0);
+      if (ticket == (int)gridDim.x - 1) {
+        __threadfence();
+        float acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+        const int total = prm.npairs * prm.B;
+        for (int e = lane; e < total; e += 32) {   // fixed order -> deterministic
+          const int kk = e / prm.B;
+          const int g = prm.group[kk];
+          const float l = __ldcg(prm.partials + (size_t)e * 4), c2 = __ldcg(prm.partials + (size_t)e * 4 + 1);
+          if (g == DG_GROUP_INTRA) { acc[0] += l; acc[1] += c2; }
+          else if (g == DG_GROUP_INTER) { acc[2] += l; acc[3] += c2; }
+          else { acc[4] += l; acc[5] += c2; }
+          if (kk == 0) {
+            acc[6] += __ldcg(prm.partials + (size_t)e * 4 + 2);
+            acc[7] += __ldcg(prm.partials + (size_t)e * 4 + 3);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = warp_sum(acc[i]);
+        int cnt[3] = {0, 0, 0};
+        for (int kk = 0; kk < prm.npairs; ++kk) cnt[prm.group[kk] > 2 ? 2 : prm.group[kk]]++;
+        const float elems = (float)prm.B * (float)prm.P * (float)prm.P;
+        if (lane < 8) {
+          const int g = lane >> 1;
+          const float n = (g < 3) ? (float)cnt[g] : (prm.has_depth ? 1.f : 0.f);
+          float t = 0.f;
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (i == lane) t = acc[i];
+          float r = n > 0.f ? t / (n * elems) : 0.f;
+          if (*reinterpret_cast<volatile int*>(prm.err) != 0) r = __int_as_float(0x7fc00000);  // pipeline timeout
+          prm.out8[lane] = r;
+        }
+      }
     }
   }
   if (threadIdx.x == 64) stamp(prm, 9);
@@ -423,7 +469,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) corr_umma_kernel(const __grid_c
 __global__ void __launch_bounds__(256) pair_dots_kernel(const float* __restrict__ fmean, int nsplit, int npairs, int B,
                                                         int ldf, float* __restrict__ dots, int* __restrict__ err) {
   __shared__ float red[8];
-  if (blockIdx.x == 0 && threadIdx.x == 0 && err) *err = 0;
+  if (blockIdx.x == 0 && threadIdx.x < 4 && err) err[threadIdx.x] = 0;  // error flag + completion counter
   if (fmean == nullptr) return;
   const int w = blockIdx.x, k = w / B, b = w - k * B;
   const float* m1 = fmean + (size_t)b * nsplit * ldf;                      // nsplit partial means each
@@ -506,7 +552,12 @@ int corr_loss_umma(const dg_panels_t* pan, const float* fmean, int nsplit, const
   prm.has_depth = dsign != nullptr;
   prm.depth_shift = depth_shift;
   prm.inv_cnt = 1.0f / ((float)B * (float)P * (float)P);
-  for (int k = 0; k < npairs; ++k) prm.shift[k] = pair_shift[k];
+  for (int k = 0; k < npairs; ++k) {
+    prm.shift[k] = pair_shift[k];
+    prm.group[k] = pair_group[k];
+  }
+  prm.out8 = out8;
+  prm.done = err + 1;
   prm.dC1 = dC1; prm.dC2 = dC2; prm.partials = partials;
   prm.cd_out = cd_out; prm.loss_out = loss_out; prm.dd_out = dd_out; prm.fd_dbg = fd_dbg; prm.err = err;
   prm.clk = g_clk;
@@ -528,7 +579,7 @@ int corr_loss_umma(const dg_panels_t* pan, const float* fmean, int nsplit, const
   DG_PRE(st);
   corr_umma_kernel<<<npairs * B, UM_THREADS, UM_SMEM, st>>>(prm);
   DG_LAUNCH_OK("corr_umma_kernel");
-  return launch_corr_finalize(partials, npairs, B, P, pair_group, prm.has_depth, err, out8, 1, st);
+  return DG_OK;  // out8 is written by the last CTA of corr_umma_kernel
 }
 
 }  // namespace dg

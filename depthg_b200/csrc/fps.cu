@@ -23,6 +23,23 @@ namespace dg {
 constexpr int FPS_THREADS = 128;  // 4 warps: the 120-round argmax chain is issue/latency bound, fewer warps = cheaper rounds
 constexpr int FPS_WARPS = FPS_THREADS / 32;
 
+// s = d / max(|d|, eps) of the align_corners=True bilinear resample of one [Hd,Wd] image at point p of the SxS grid
+// (0 for p >= S*S).  `d` may point to global or shared memory.
+__device__ __forceinline__ float depth_sign_value(const float* d, int Hd, int Wd, int S, int p, float eps) {
+  if (p >= S * S) return 0.f;
+  const int h = p / S, w = p - h * S;
+  const float sy = S > 1 ? __fdiv_rn((float)(Hd - 1), (float)(S - 1)) : 0.f;
+  const float sx = S > 1 ? __fdiv_rn((float)(Wd - 1), (float)(S - 1)) : 0.f;
+  const float fy = __fmul_rn(sy, (float)h), fx = __fmul_rn(sx, (float)w);
+  const int y0 = min((int)fy, Hd - 1), x0 = min((int)fx, Wd - 1);
+  const int y1 = y0 + (y0 < Hd - 1 ? 1 : 0), x1 = x0 + (x0 < Wd - 1 ? 1 : 0);
+  const float ly = fminf(fmaxf(fy - (float)y0, 0.f), 1.f), lx = fminf(fmaxf(fx - (float)x0, 0.f), 1.f);
+  const float v00 = d[(size_t)y0 * Wd + x0], v01 = d[(size_t)y0 * Wd + x1];
+  const float v10 = d[(size_t)y1 * Wd + x0], v11 = d[(size_t)y1 * Wd + x1];
+  const float v = (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
+  return v / fmaxf(fabsf(v), eps);
+}
+
 // STAGE: the whole [Hd,Wd] depth image is first copied into shared memory with 16-byte cp.async
 // (every load in flight at once), so the pooling reads never wait on DRAM one window row at a time.
 template <int PPT, bool STAGE>
@@ -30,7 +47,8 @@ __global__ void __launch_bounds__(FPS_THREADS) fps_kernel(const float* __restric
                                                           const float* __restrict__ depth_b, int B, int Hd, int Wd,
                                                           int H, int W, int nsel, float factor, float far_plane,
                                                           int affine, float* __restrict__ coords,
-                                                          int32_t* __restrict__ idx_out) {
+                                                          int32_t* __restrict__ idx_out, float* __restrict__ dsign,
+                                                          int sign_S, int sign_pitch, float sign_eps) {
   extern __shared__ __align__(16) float fps_smem[];
   const int npts = H * W;
   const int npad = (npts + 3) & ~3;
@@ -178,6 +196,11 @@ __global__ void __launch_bounds__(FPS_THREADS) fps_kernel(const float* __restric
       ++rank;
     }
   }
+  // fused depth_sign_kernel for the first depth tensor (the depth term of the loss only uses `depth`, not depth_pos)
+  if (dsign != nullptr && img < B) {
+    for (int p = tid; p < sign_pitch; p += FPS_THREADS)
+      dsign[(size_t)img * sign_pitch + p] = depth_sign_value(depth, Hd, Wd, sign_S, p, sign_eps);
+  }
 }
 
 // s = d / max(|d|, eps) of the align_corners=True bilinear resample of depth to SxS.
@@ -186,26 +209,12 @@ __global__ void depth_sign_kernel(const float* __restrict__ depth, int B, int Hd
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= B * out_pitch) return;
   const int b = t / out_pitch, p = t - b * out_pitch;
-  if (p >= S * S) {
-    out[t] = 0.f;
-    return;
-  }
-  const int h = p / S, w = p - h * S;
-  const float sy = S > 1 ? __fdiv_rn((float)(Hd - 1), (float)(S - 1)) : 0.f;
-  const float sx = S > 1 ? __fdiv_rn((float)(Wd - 1), (float)(S - 1)) : 0.f;
-  const float fy = __fmul_rn(sy, (float)h), fx = __fmul_rn(sx, (float)w);
-  const int y0 = min((int)fy, Hd - 1), x0 = min((int)fx, Wd - 1);
-  const int y1 = y0 + (y0 < Hd - 1 ? 1 : 0), x1 = x0 + (x0 < Wd - 1 ? 1 : 0);
-  const float ly = fminf(fmaxf(fy - (float)y0, 0.f), 1.f), lx = fminf(fmaxf(fx - (float)x0, 0.f), 1.f);
-  const float* d = depth + (size_t)b * Hd * Wd;
-  const float v00 = __ldg(d + (size_t)y0 * Wd + x0), v01 = __ldg(d + (size_t)y0 * Wd + x1);
-  const float v10 = __ldg(d + (size_t)y1 * Wd + x0), v11 = __ldg(d + (size_t)y1 * Wd + x1);
-  const float v = (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
-  out[t] = v / fmaxf(fabsf(v), eps);
+  out[t] = depth_sign_value(depth + (size_t)b * Hd * Wd, Hd, Wd, S, p, eps);
 }
 
 int launch_fps(const float* depth_a, const float* depth_b, int B, int Hd, int Wd, int H, int W, int S, float factor,
-               float far_plane, int affine, float* coords, int32_t* idx, cudaStream_t st) {
+               float far_plane, int affine, float* coords, int32_t* idx, cudaStream_t st, float* dsign, int sign_pitch,
+               float sign_eps) {
   DG_REQUIRE(depth_a && coords, DG_ERR_INVALID, "dg_fps_coords: null pointer");
   DG_REQUIRE(B > 0 && Hd > 0 && Wd > 0 && H > 0 && W > 0 && S > 0, DG_ERR_INVALID, "dg_fps_coords: bad sizes");
   DG_REQUIRE(H <= Hd && W <= Wd, DG_ERR_UNSUPPORTED, "dg_fps_coords: pooling must not upsample (%dx%d -> %dx%d)", Hd,
@@ -228,7 +237,8 @@ int launch_fps(const float* depth_a, const float* depth_b, int B, int Hd, int Wd
     }                                                                                                             \
     DG_PRE(st);                                                                                                   \
     fps_kernel<PPT, ST><<<nimg, FPS_THREADS, smem, st>>>(depth_a, depth_b, B, Hd, Wd, H, W, S * S, factor,          \
-                                                          far_plane, affine, coords, idx);                          \
+                                                          far_plane, affine, coords, idx, dsign, S, sign_pitch,     \
+                                                          sign_eps);                                                \
   } while (0)
   if (npts <= 7 * FPS_THREADS) {
     if (stage) DG_FPS_LAUNCH(7, true); else DG_FPS_LAUNCH(7, false);

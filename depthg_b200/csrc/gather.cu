@@ -266,6 +266,71 @@ __global__ void __launch_bounds__(GF_THREADS, 2)
   }
 }
 
+// Code tensors (D <= 128, any strides): lanes over channels with scalar loads, everything in registers, a
+// (set, image) split over `nsplit` CTAs.  Writes the tf32 hi / fp32 remainder panels for the cd product and the
+// bf16 hi/lo panels for the gradient GEMMs, plus 1/||x||.
+template <int R>
+__global__ void __launch_bounds__(GF_THREADS)
+    gather_code_kernel(const __grid_constant__ SetTable sets, int B, int C, int H, int W,
+                       const float* __restrict__ coords, int S, const int64_t* __restrict__ perms, float eps,
+                       int Prows, int nsplit, GatherOut o) {
+  const int split = blockIdx.x % nsplit, sbi = blockIdx.x / nsplit;
+  const int set = sbi / B, b = sbi - set * B;
+  const int P = S * S, ld = 32 * R;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const SetDesc& sd = sets.s[set];
+  const int64_t sc = sd.sc, sh = sd.sh, sw = sd.sw;
+  const int64_t src = sd.perm_row >= 0 ? perms[(size_t)sd.perm_row * B + b] : (int64_t)b;
+  const float* timg = sd.src + src * sd.sb;
+  const float* cset = coords + ((size_t)sd.coord * B + b) * P * 2;
+  const size_t pbase = ((size_t)sd.slot * B + b) * Prows;
+  const int chunk = (Prows + nsplit - 1) / nsplit;
+  const int p_end = min((split + 1) * chunk, Prows);
+  for (int p = split * chunk + warp; p < p_end; p += GF_WARPS) {
+    float v[R];
+    float r = 0.f;
+#pragma unroll
+    for (int j = 0; j < R; ++j) v[j] = 0.f;
+    if (p < P) {
+      const int h = p / S, w = p - h * S;
+      const float* cc = cset + 2 * (w * S + h);
+      const Corners k = bilinear_corners(__ldg(cc), __ldg(cc + 1), H, W);
+      const float* p00 = timg + k.y0 * sh + k.x0 * sw;
+      const float* p01 = k.x1_ok ? p00 + sw : p00;
+      const float* p10 = k.y1_ok ? p00 + sh : p00;
+      const float* p11 = p10 + (k.x1_ok ? sw : 0);
+      const float w00 = k.w00, w01 = k.x1_ok ? k.w01 : 0.f, w10 = k.y1_ok ? k.w10 : 0.f,
+                  w11 = (k.x1_ok && k.y1_ok) ? k.w11 : 0.f;
+      float ss = 0.f;
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        const int c = lane + 32 * j;
+        if (c < C) {
+          const int64_t off = (int64_t)c * sc;
+          v[j] = __ldg(p00 + off) * w00 + __ldg(p01 + off) * w01 + __ldg(p10 + off) * w10 + __ldg(p11 + off) * w11;
+          ss += v[j] * v[j];
+        }
+      }
+      ss = warp_sum(ss);
+      r = 1.f / fmaxf(sqrtf(ss), eps);
+    }
+    const size_t ro = (pbase + p) * ld;
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      const float x = v[j] * r;
+      const float hi = umma_tf32(x);
+      __nv_bfloat16 h, l;
+      split_bf16(x, h, l);
+      const int c = lane + 32 * j;
+      o.out[ro + c] = hi;
+      o.out_lo[ro + c] = x - hi;
+      o.hi16[ro + c] = h;
+      o.lo16[ro + c] = l;
+    }
+    if (lane == 0) o.rnorm[pbase + p] = r;
+  }
+}
+
 // One warp per panel row: compose the row's gradient from the unit gradients,
 // back through x/max(||x||,eps), then atomically scatter through the 4 corners.
 __global__ void __launch_bounds__(256)
@@ -447,6 +512,18 @@ static int launch_gather_fast(int fmt, const SetTable& tab, int nsets, int B, in
 
 int launch_gather(int fmt, const SetTable& tab, int nsets, int B, int C, int H, int W, const float* coords, int S,
                   const int64_t* perms, float eps, int Prows, int ld, int nsplit, const GatherOut& o, cudaStream_t st) {
+  if (fmt == FMT_CODE_SPLIT && ld <= 128) {  // register-resident code gather
+    const int ns = 4;
+    DG_PRE(st);
+    switch (ld / 32) {
+      case 1: gather_code_kernel<1><<<nsets * B * ns, GF_THREADS, 0, st>>>(tab, B, C, H, W, coords, S, perms, eps, Prows, ns, o); break;
+      case 2: gather_code_kernel<2><<<nsets * B * ns, GF_THREADS, 0, st>>>(tab, B, C, H, W, coords, S, perms, eps, Prows, ns, o); break;
+      case 3: gather_code_kernel<3><<<nsets * B * ns, GF_THREADS, 0, st>>>(tab, B, C, H, W, coords, S, perms, eps, Prows, ns, o); break;
+      default: gather_code_kernel<4><<<nsets * B * ns, GF_THREADS, 0, st>>>(tab, B, C, H, W, coords, S, perms, eps, Prows, ns, o); break;
+    }
+    DG_LAUNCH_OK("gather_code_kernel");
+    return DG_OK;
+  }
   if (nsplit > 1) {
     DG_REQUIRE(nsplit == gather_nsplit(fmt, tab, nsets, C, ld), DG_ERR_INVALID, "gather: inconsistent nsplit");
     switch (C / 128) {

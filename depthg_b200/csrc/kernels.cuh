@@ -46,8 +46,10 @@ struct GroupW {
   const float* ptr[DG_NUM_GROUPS];
 };
 
+// dsign != null: also writes the depth signs of depth_a (what launch_depth_sign computes) from the same CTA
 int launch_fps(const float* depth_a, const float* depth_b, int B, int Hd, int Wd, int H, int W, int S, float factor,
-               float far_plane, int affine, float* coords, int32_t* idx, cudaStream_t st);
+               float far_plane, int affine, float* coords, int32_t* idx, cudaStream_t st, float* dsign = nullptr,
+               int sign_pitch = 0, float sign_eps = 0.f);
 int launch_depth_sign(const float* depth, int B, int Hd, int Wd, int S, float eps, int out_pitch, float* out,
                       cudaStream_t st);
 // meanvec is written as `nsplit` partial means per (slot, image): [slot,b,nsplit,ld], each already divided by P

@@ -106,17 +106,16 @@ extern "C" int dg_loss_forward(const dg_loss_desc_t* d, const dg_loss_io_t* io, 
   uint8_t* A = static_cast<uint8_t*>(io->arena);
   const int B = d->B, S = d->S, P = S * S, np = pl.npairs;
   const float* coords = io->coords;
-  if (fps) {
-    float* c = reinterpret_cast<float*>(A + pl.coords);
-    rc = launch_fps(io->depth, io->depth_pos, B, d->Hd, d->Wd, d->H, d->W, S, fov_factor(), kFarPlane, 1, c, nullptr, st);
-    if (rc != DG_OK) return rc;
-    coords = c;
-  }
   const bool pointwise = d->flags & DG_FLAG_POINTWISE;
   float* fmean = pointwise ? reinterpret_cast<float*>(A + pl.fmean) : nullptr;
-  float* dsign = nullptr;
-  if (depth_term) {
-    dsign = reinterpret_cast<float*>(A + pl.dsign);
+  float* dsign = depth_term ? reinterpret_cast<float*>(A + pl.dsign) : nullptr;
+  if (fps) {  // FPS of both depth tensors; the same CTAs also emit the depth signs the depth term needs
+    float* c = reinterpret_cast<float*>(A + pl.coords);
+    rc = launch_fps(io->depth, io->depth_pos, B, d->Hd, d->Wd, d->H, d->W, S, fov_factor(), kFarPlane, 1, c, nullptr, st,
+                    dsign, pl.Prows, kNormEps);
+    if (rc != DG_OK) return rc;
+    coords = c;
+  } else if (depth_term) {
     rc = launch_depth_sign(io->depth, B, d->Hd, d->Wd, S, kNormEps, pl.Prows, dsign, st);
     if (rc != DG_OK) return rc;
   }

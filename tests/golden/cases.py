@@ -33,6 +33,12 @@ LOSS_CASES = {
     "s12_fps": (2, 48, 90, dict(feature_samples=12), 19),
     "cfg1_vits": (2, 384, 70, dict(feature_samples=11, pos_intra_shift=0.08, pos_inter_shift=0.02,
                                    neg_inter_shift=0.66), 0),
+    # Cityscapes five-crop flavour (BASELINE configs[3]): dim 100, random coordinates, pointwise off
+    "cfg4_cityscapes": (4, 128, 100, dict(feature_samples=11, depth_sampling="none", pointwise=False,
+                                          pos_intra_shift=0.18, pos_inter_shift=0.12, neg_inter_shift=0.46,
+                                          depth_feat_shift=0.01), 21),
+    # dense, unsampled correlation (BASELINE configs[4]) on a small grid: every grid point is a sample
+    "dense_14x14": (2, 48, 24, dict(feature_samples=14), 22),
 }
 
 # backprop weights for the scalar L = sum w_i * loss_i  (ViT-B paper run, paper_reproduction.sh:8)
@@ -49,6 +55,9 @@ def correlated(rs, B, C, H, W, rank=6):
 
 def make_loss_inputs(name, H=28, W=28, Hd=224, Wd=224):
     B, C, D, over, seed = LOSS_CASES[name]
+    if name.startswith("dense_"):
+        H = W = over["feature_samples"]
+        Hd = Wd = 8 * H
     rs = np.random.RandomState(1000 + seed)
     feats = correlated(rs, B, C, H, W)
     feats_pos = correlated(rs, B, C, H, W)

@@ -120,8 +120,12 @@ def main():
     assert refimport.have_reference(), "run in the build container (needs /root/reference)"
     torch.set_num_threads(8)
     M = refimport.load_reference_modules()
+    only = os.environ.get("GOLDEN_ONLY")
     for name in cases.LOSS_CASES:
-        run_loss_case(M, name)
+        if only is None or name in only.split(","):
+            run_loss_case(M, name)
+    if only is not None:
+        return
     run_fps(M)
     run_misc(M)
     run_knn()

@@ -339,6 +339,8 @@ def main():
     Cc, Dd = CFG2["C"], 96
     alg = {
         "fps_kernel": 4 * 2 * B * CFG2["Hd"] * CFG2["Wd"],
+        "gather_feats_kernel": 4 * 2 * B * Cc * HW + 4 * npairs * B * 128 * Cc,          # sources once + bf16 hi/lo panels
+        "gather_code_kernel": 4 * 2 * B * CFG2["D"] * HW + 4 * npairs * B * 128 * 3 * Dd,
         "gather_norm_kernel": 4 * (2 * B * Cc * HW + 2 * B * CFG2["D"] * HW) + 4 * npairs * B * 128 * (Cc + 3 * Dd),
         "corr_umma_kernel": 4 * npairs * B * 128 * (2 * Cc + 3 * 2 * Dd) + 4 * 2 * npairs * B * 128 * Dd,
         "corr_tile_kernel": 4 * npairs * B * 128 * (2 * Cc + 2 * Dd) + 4 * 2 * npairs * B * 128 * Dd,
@@ -347,8 +349,12 @@ def main():
     dom = max((k for k in breakdown if k in alg), key=breakdown.get)
     dom_us = breakdown[dom]
     achieved = alg[dom] / (dom_us * 1e-6) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.isfile(tpath):   # dram__bytes_read+write per launch from the committed ncu --set full capture
+        traffic = json.load(open(tpath))["dram_bytes"].get(dom)
     roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                 "us_per_step": dom_us, "launches_per_step": calls.get(dom), "algorithmic_bytes_per_step": alg[dom]}
     if dom == "corr_umma_kernel":
         fl = algorithmic_flops(B)

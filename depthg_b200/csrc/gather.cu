@@ -175,16 +175,18 @@ __global__ void __launch_bounds__(GATHER_THREADS)
 // registers (no smem staging), every lane issues its 4 x NV 128-bit corner loads back to back, and a
 // (set, image) is split over `nsplit` CTAs so ~900 CTAs cover the GPU evenly.  Each CTA writes its
 // share of the panel mean (already divided by P); consumers add the nsplit partials.
+#ifndef GF_MINBLOCKS
+#define GF_MINBLOCKS 2
+#endif
 constexpr int GF_THREADS = 256;
 constexpr int GF_WARPS = GF_THREADS / 32;
 
 template <int NV, int FMT>
-__global__ void __launch_bounds__(GF_THREADS, 2)
-    gather_feats_kernel(const __grid_constant__ SetTable sets, int B, int C, int H, int W,
-                        const float* __restrict__ coords, int S, const int64_t* __restrict__ perms, float eps,
-                        int Prows, int nsplit, GatherOut o) {
-  extern __shared__ float gfs[];  // [GF_WARPS][C] for the final cross-warp mean
-  const int split = blockIdx.x % nsplit, sbi = blockIdx.x / nsplit;
+__device__ __forceinline__ void gather_feats_body(const SetTable& sets, int B, int C, int H, int W,
+                                                  const float* __restrict__ coords, int S,
+                                                  const int64_t* __restrict__ perms, float eps, int Prows, int nsplit,
+                                                  const GatherOut& o, int vblock, float* gfs) {
+  const int split = vblock % nsplit, sbi = vblock / nsplit;
   const int set = sbi / B, b = sbi - set * B;
   const int P = S * S, ld = C;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -266,15 +268,24 @@ __global__ void __launch_bounds__(GF_THREADS, 2)
   }
 }
 
+template <int NV, int FMT>
+__global__ void __launch_bounds__(GF_THREADS, GF_MINBLOCKS)
+    gather_feats_kernel(const __grid_constant__ SetTable sets, int B, int C, int H, int W,
+                        const float* __restrict__ coords, int S, const int64_t* __restrict__ perms, float eps,
+                        int Prows, int nsplit, GatherOut o) {
+  extern __shared__ float gfs[];  // [GF_WARPS][C] for the final cross-warp mean
+  gather_feats_body<NV, FMT>(sets, B, C, H, W, coords, S, perms, eps, Prows, nsplit, o, blockIdx.x, gfs);
+}
+
 // Code tensors (D <= 128, any strides): lanes over channels with scalar loads, everything in registers, a
 // (set, image) split over `nsplit` CTAs.  Writes the tf32 hi / fp32 remainder panels for the cd product and the
 // bf16 hi/lo panels for the gradient GEMMs, plus 1/||x||.
 template <int R>
-__global__ void __launch_bounds__(GF_THREADS)
-    gather_code_kernel(const __grid_constant__ SetTable sets, int B, int C, int H, int W,
-                       const float* __restrict__ coords, int S, const int64_t* __restrict__ perms, float eps,
-                       int Prows, int nsplit, GatherOut o) {
-  const int split = blockIdx.x % nsplit, sbi = blockIdx.x / nsplit;
+__device__ __forceinline__ void gather_code_body(const SetTable& sets, int B, int C, int H, int W,
+                                                 const float* __restrict__ coords, int S,
+                                                 const int64_t* __restrict__ perms, float eps, int Prows, int nsplit,
+                                                 const GatherOut& o, int vblock) {
+  const int split = vblock % nsplit, sbi = vblock / nsplit;
   const int set = sbi / B, b = sbi - set * B;
   const int P = S * S, ld = 32 * R;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -329,6 +340,39 @@ __global__ void __launch_bounds__(GF_THREADS)
     }
     if (lane == 0) o.rnorm[pbase + p] = r;
   }
+}
+
+template <int R>
+__global__ void __launch_bounds__(GF_THREADS)
+    gather_code_kernel(const __grid_constant__ SetTable sets, int B, int C, int H, int W,
+                       const float* __restrict__ coords, int S, const int64_t* __restrict__ perms, float eps,
+                       int Prows, int nsplit, GatherOut o) {
+  gather_code_body<R>(sets, B, C, H, W, coords, S, perms, eps, Prows, nsplit, o, blockIdx.x);
+}
+
+// Both gathers of a forward pass in ONE launch: the first `nfeat_blocks` CTAs gather the backbone features (bf16
+// hi/lo panels), the remaining ones the code tensors.  Each kind alone is latency-bound; together they fill the GPU.
+struct GatherAllArgs {
+  SetTable fsets, csets;
+  GatherOut fo, co;
+  int B, C, D, H, W, S, Prows, fsplit, csplit, nfeat_blocks;
+  float eps;
+  const float* coords;
+  const int64_t* perms;
+};
+
+template <int NV, int R>
+__global__ void __launch_bounds__(GF_THREADS, 2) gather_all_kernel(const __grid_constant__ GatherAllArgs a) {
+  extern __shared__ float gfs[];
+  // code CTAs outnumber feature CTAs 2:1 (csplit = 2 * fsplit): interleave them f,c,c,f,c,c,... so both kinds are
+  // resident together from the first wave on
+  const int q = blockIdx.x / 3, r = blockIdx.x - 3 * q;
+  if (r == 0)
+    gather_feats_body<NV, FMT_FEATS_SPLIT>(a.fsets, a.B, a.C, a.H, a.W, a.coords, a.S, a.perms, a.eps, a.Prows,
+                                           a.fsplit, a.fo, q, gfs);
+  else
+    gather_code_body<R>(a.csets, a.B, a.D, a.H, a.W, a.coords, a.S, a.perms, a.eps, a.Prows, a.csplit, a.co,
+                        2 * q + (r - 1));
 }
 
 // One warp per panel row: compose the row's gradient from the unit gradients,
@@ -482,7 +526,7 @@ static int fill_sets(const char* fn, const float* src, const int64_t* strides, i
   return DG_OK;
 }
 
-// How many CTAs a (set, image) is split over: 4 on the register-resident fast path, else 1.
+// How many CTAs a (set, image) is split over: 8 on the register-resident fast path, else 1.
 int gather_nsplit(int fmt, const SetTable& tab, int nsets, int C, int ld) {
   if (fmt == FMT_CODE_SPLIT || C != ld || (C % 128) != 0 || C / 128 > 8) return 1;
   const int nv = C / 128;
@@ -491,7 +535,7 @@ int gather_nsplit(int fmt, const SetTable& tab, int nsets, int C, int ld) {
     const SetDesc& d = tab.s[s];
     if (d.sc != 1 || (d.sb & 3) || (d.sh & 3) || (d.sw & 3) || (reinterpret_cast<uintptr_t>(d.src) & 15)) return 1;
   }
-  return 4;
+  return 8;
 }
 
 template <int NV>
@@ -513,7 +557,7 @@ static int launch_gather_fast(int fmt, const SetTable& tab, int nsets, int B, in
 int launch_gather(int fmt, const SetTable& tab, int nsets, int B, int C, int H, int W, const float* coords, int S,
                   const int64_t* perms, float eps, int Prows, int ld, int nsplit, const GatherOut& o, cudaStream_t st) {
   if (fmt == FMT_CODE_SPLIT && ld <= 128) {  // register-resident code gather
-    const int ns = 4;
+    const int ns = 16;  // one or two points per warp: the two dependent global round trips per point are the cost
     DG_PRE(st);
     switch (ld / 32) {
       case 1: gather_code_kernel<1><<<nsets * B * ns, GF_THREADS, 0, st>>>(tab, B, C, H, W, coords, S, perms, eps, Prows, ns, o); break;
@@ -553,6 +597,44 @@ int launch_gather(int fmt, const SetTable& tab, int nsets, int B, int C, int H, 
 #undef DG_GATHER_LAUNCH
   DG_LAUNCH_OK("gather_norm_kernel");
   return DG_OK;
+}
+
+template <int NV>
+static int launch_gather_all_nv(const GatherAllArgs& a, int total_blocks, int R, cudaStream_t st) {
+  const size_t smem = (size_t)GF_WARPS * a.C * sizeof(float);
+  DG_PRE(st);
+  switch (R) {
+    case 1: gather_all_kernel<NV, 1><<<total_blocks, GF_THREADS, smem, st>>>(a); break;
+    case 2: gather_all_kernel<NV, 2><<<total_blocks, GF_THREADS, smem, st>>>(a); break;
+    case 3: gather_all_kernel<NV, 3><<<total_blocks, GF_THREADS, smem, st>>>(a); break;
+    default: gather_all_kernel<NV, 4><<<total_blocks, GF_THREADS, smem, st>>>(a); break;
+  }
+  DG_LAUNCH_OK("gather_all_kernel");
+  return DG_OK;
+}
+
+// Features (split bf16 panels, register fast path) and code (split panels) in one launch; returns DG_ERR_UNSUPPORTED if the
+// shapes/strides do not qualify so the caller can fall back to the two separate launches.
+int launch_gather_all(const SetTable& fsets, const SetTable& csets, int nsets, int B, int C, int D, int H, int W,
+                      const float* coords, int S, const int64_t* perms, float eps, int Prows, int ldf, int ldc, int fsplit,
+                      const GatherOut& fo, const GatherOut& co, cudaStream_t st) {
+  if (fsplit <= 1 || ldc > 128 || C != ldf) return DG_ERR_UNSUPPORTED;
+  GatherAllArgs a;
+  a.fsets = fsets; a.csets = csets; a.fo = fo; a.co = co;
+  a.B = B; a.C = C; a.D = D; a.H = H; a.W = W; a.S = S; a.Prows = Prows; a.fsplit = fsplit; a.csplit = 2 * fsplit;  // the 2:1 interleave of gather_all_kernel relies on this
+  a.nfeat_blocks = nsets * B * fsplit;
+  a.eps = eps; a.coords = coords; a.perms = perms;
+  const int total = a.nfeat_blocks + nsets * B * a.csplit;
+  const int R = ldc / 32;
+  switch (C / 128) {
+    case 1: return launch_gather_all_nv<1>(a, total, R, st);
+    case 2: return launch_gather_all_nv<2>(a, total, R, st);
+    case 3: return launch_gather_all_nv<3>(a, total, R, st);
+    case 4: return launch_gather_all_nv<4>(a, total, R, st);
+    case 6: return launch_gather_all_nv<6>(a, total, R, st);
+    case 8: return launch_gather_all_nv<8>(a, total, R, st);
+    default: return DG_ERR_UNSUPPORTED;
+  }
 }
 
 int launch_gather_bwd(const SetTable& tab, int nsets, int B, int C, int H, int W, const float* coords, int S,

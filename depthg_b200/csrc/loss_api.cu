@@ -1,5 +1,6 @@
 // One-call forward / backward of the loss: plans the arena, builds the gather tables for
 // all four source tensors and enqueues the same kernels the per-stage entry points launch.
+#include <stdlib.h>
 #include <string.h>
 
 #include "kernels.cuh"
@@ -41,7 +42,7 @@ static void make_plan(const dg_loss_desc_t* d, dg_loss_plan_t* p) {
   auto take = [&](size_t bytes) { size_t o = off; off += al256(bytes); return o; };
   p->coords = take((size_t)2 * B * P * 2 * 4);
   p->frn = take(np * B * Pr * 4);
-  p->fmean = take(np * B * 4 * p->ldf * 4);  // up to 4 partial means per (slot, image)
+  p->fmean = take(np * B * 8 * p->ldf * 4);  // up to 8 partial means per (slot, image)
   p->crn = take(np * B * Pr * 4);
   p->dsign = take(B * Pr * 4);
   p->ws_bytes = corr_workspace_bytes(p->npairs, d->B, P);
@@ -120,31 +121,39 @@ extern "C" int dg_loss_forward(const dg_loss_desc_t* d, const dg_loss_io_t* io, 
     if (rc != DG_OK) return rc;
   }
   if (io->perms_ready) DG_CUDA_OK(cudaStreamWaitEvent(st, reinterpret_cast<cudaEvent_t>(io->perms_ready), 0));
-  SetTable tab;
-  GatherOut o;
+  SetTable ftab, ctab;
+  GatherOut fo, co;
   // backbone features
-  int nsets = build_sets(tab, io->feats, io->feats_strides, io->feats_pos, io->feats_pos_strides, d->neg_samples);
-  o.out = reinterpret_cast<float*>(A + pl.f_hi);
-  o.out_lo = nullptr;
-  o.hi16 = reinterpret_cast<__nv_bfloat16*>(A + pl.f_hi);
-  o.lo16 = reinterpret_cast<__nv_bfloat16*>(A + pl.f_lo);
-  o.rnorm = reinterpret_cast<float*>(A + pl.frn);
-  o.meanvec = fmean;
+  const int nsets = build_sets(ftab, io->feats, io->feats_strides, io->feats_pos, io->feats_pos_strides, d->neg_samples);
+  fo.out = reinterpret_cast<float*>(A + pl.f_hi);
+  fo.out_lo = nullptr;
+  fo.hi16 = reinterpret_cast<__nv_bfloat16*>(A + pl.f_hi);
+  fo.lo16 = reinterpret_cast<__nv_bfloat16*>(A + pl.f_lo);
+  fo.rnorm = reinterpret_cast<float*>(A + pl.frn);
+  fo.meanvec = fmean;
   const int ffmt = pl.kernel ? FMT_FEATS_SPLIT : FMT_F32;
-  const int nsplit = gather_nsplit(ffmt, tab, nsets, d->C, pl.ldf);
-  rc = launch_gather(ffmt, tab, nsets, B, d->C, d->H, d->W, coords, S, io->perms, kNormEps, pl.Prows, pl.ldf, nsplit, o,
-                     st);
-  if (rc != DG_OK) return rc;
+  const int nsplit = gather_nsplit(ffmt, ftab, nsets, d->C, pl.ldf);
   // code
-  nsets = build_sets(tab, io->code, io->code_strides, io->code_pos, io->code_pos_strides, d->neg_samples);
-  o.out = reinterpret_cast<float*>(A + pl.c_hi);
-  o.out_lo = pl.kernel ? reinterpret_cast<float*>(A + pl.c_lo) : nullptr;
-  o.hi16 = pl.kernel ? reinterpret_cast<__nv_bfloat16*>(A + pl.cb_hi) : nullptr;
-  o.lo16 = pl.kernel ? reinterpret_cast<__nv_bfloat16*>(A + pl.cb_lo) : nullptr;
-  o.rnorm = reinterpret_cast<float*>(A + pl.crn);
-  o.meanvec = nullptr;
-  rc = launch_gather(pl.kernel ? FMT_CODE_SPLIT : FMT_F32, tab, nsets, B, d->D, d->H, d->W, coords, S, io->perms, kNormEps,
-                     pl.Prows, pl.ldc, 1, o, st);
+  build_sets(ctab, io->code, io->code_strides, io->code_pos, io->code_pos_strides, d->neg_samples);
+  co.out = reinterpret_cast<float*>(A + pl.c_hi);
+  co.out_lo = pl.kernel ? reinterpret_cast<float*>(A + pl.c_lo) : nullptr;
+  co.hi16 = pl.kernel ? reinterpret_cast<__nv_bfloat16*>(A + pl.cb_hi) : nullptr;
+  co.lo16 = pl.kernel ? reinterpret_cast<__nv_bfloat16*>(A + pl.cb_lo) : nullptr;
+  co.rnorm = reinterpret_cast<float*>(A + pl.crn);
+  co.meanvec = nullptr;
+  // (a single merged launch — launch_gather_all — was measured slower: the code CTAs inherit the feature
+  //  kernel's register footprint and lose the occupancy that hides their latency; kept for experiments)
+  rc = DG_ERR_UNSUPPORTED;
+  if (pl.kernel && getenv("DEPTHG_B200_GATHER_ALL"))
+    rc = launch_gather_all(ftab, ctab, nsets, B, d->C, d->D, d->H, d->W, coords, S, io->perms, kNormEps, pl.Prows, pl.ldf,
+                           pl.ldc, nsplit, fo, co, st);
+  if (rc == DG_ERR_UNSUPPORTED) {
+    rc = launch_gather(ffmt, ftab, nsets, B, d->C, d->H, d->W, coords, S, io->perms, kNormEps, pl.Prows, pl.ldf, nsplit, fo,
+                       st);
+    if (rc != DG_OK) return rc;
+    rc = launch_gather(pl.kernel ? FMT_CODE_SPLIT : FMT_F32, ctab, nsets, B, d->D, d->H, d->W, coords, S, io->perms,
+                       kNormEps, pl.Prows, pl.ldc, 1, co, st);
+  }
   if (rc != DG_OK) return rc;
 
   float shifts[DG_MAX_PAIRS];

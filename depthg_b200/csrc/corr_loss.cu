@@ -468,11 +468,12 @@ extern "C" int dg_corr_loss(const dg_panels_t* pan, const float* fmean, const fl
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 
   if (pan->format == DG_PANEL_FEATS_SPLIT || pan->format == DG_PANEL_CODE_SPLIT) {
-    DG_REQUIRE(Prows == 128 && P <= 128, DG_ERR_UNSUPPORTED,
-               "dg_corr_loss: the tcgen05 path needs S*S <= 128 and 128-row panels (got P=%d, Prows=%d)", P, Prows);
+    DG_REQUIRE(P <= 256 && Prows == round_up(P, 128), DG_ERR_UNSUPPORTED,
+               "dg_corr_loss: the tcgen05 path needs S*S <= 256 and panels of round_up(S*S,128) rows (got P=%d, Prows=%d)",
+               P, Prows);
     DG_REQUIRE(pan->f_lo && pan->c_lo && pan->cb_hi && pan->cb_lo, DG_ERR_INVALID,
                "dg_corr_loss: split panel format needs f_lo, c_lo, cb_hi, cb_lo");
-    return corr_loss_umma(pan, fmean, 1, dsign, npairs, B, P, ldf, ldc, pair_shift, pair_group, depth_shift, flags, out8,
+    return corr_loss_umma(pan, fmean, 1, dsign, npairs, B, P, Prows, ldf, ldc, pair_shift, pair_group, depth_shift, flags, out8,
                           dC1, dC2, cd_out, loss_out, dd_out, fd_dbg, ws, st);
   }
   DG_REQUIRE(pan->format == DG_PANEL_F32, DG_ERR_INVALID, "dg_corr_loss: unknown panel format %d", pan->format);

@@ -1,8 +1,9 @@
-// Fused correlation loss on the 5th-gen tensor cores (tcgen05 + TMEM + TMA), P <= 128.
+// Fused correlation loss on the 5th-gen tensor cores (tcgen05 + TMEM + TMA), P = S*S <= 256.
 //
 // Same contract as corr_tile_kernel (corr_loss.cu) — replaces helper() for every pair
 // and depth_feature_correlation (/root/reference/src/modules.py:1231-1278) — but one
-// CTA owns a whole (pair k, image b) tile and nothing P x P ever leaves the SM:
+// CTA owns a 128-row tile of a (pair k, image b) problem (the whole problem when P <= 128; two row tiles, each
+// walking two 128-column tiles, when 128 < P <= 256) and nothing P x P ever leaves the SM:
 //
 //   warp 0   TMA producer : streams K-chunks of the split panels into a 3 x 64 KB smem ring
 //   warp 1   MMA issuer   : one elected lane issues tcgen05.mma; accumulators live in TMEM
@@ -40,17 +41,18 @@ struct UmmaParams {
   CUtensorMap tm_fhi, tm_flo;  // bf16 [npairs*B*128, ldf]   box 64 x 128, SWIZZLE_128B
   CUtensorMap tm_chi, tm_clo;  // f32  [npairs*B*128, ldc]   box 32 x 128, SWIZZLE_128B
   CUtensorMap tm_bhi, tm_blo;  // bf16 [npairs*B*128, ldc]   box 32 x 128, SWIZZLE_64B (gradient GEMM operands)
-  const float* dsign;          // [B,128] or null
+  const float* dsign;          // [B,128*ntile] or null
   const float* dots;           // [npairs,B] <mean row of F1[b], mean row of F2[k,b]> (pointwise) or null
   int npairs, B, P, ldf, ldc, flags, has_depth;
+  int ntile;                   // 128-row tiles per panel (1 or 2): S*S <= 128 * ntile
   float depth_shift, inv_cnt;
   float shift[DG_MAX_PAIRS];
   int32_t group[DG_MAX_PAIRS];
   float* out8;      // the 8 scalars of the output tuple, written by the last CTA to finish
   int* done;        // CTA completion counter (zeroed by pair_dots_kernel)
-  float* dC1;       // [npairs+1,B,128,ldc]
-  float* dC2;       // [npairs+1,B,128,ldc]
-  float* partials;  // [npairs*B][4]
+  float* dC1;       // [npairs+1,B,Prows,ldc]
+  float* dC2;       // [npairs+1,ntile,B,Prows,ldc]: one partial buffer per row tile of the first operand
+  float* partials;  // [npairs*B*ntile][4]
   float* cd_out;    // optional dense [npairs,B,P,P]
   float* loss_out;
   float* dd_out;
@@ -114,6 +116,12 @@ __device__ __forceinline__ void drain_block(uint32_t taddr, float* scratch /*[32
   __syncwarp();
 }
 
+// TMEM columns: feature / code correlations of column tile j at 256 j and 256 j + 128.  Once the epilogue has turned
+// a tile into U, its columns are dead and are reused by the gradient accumulators: dC1 (summed over j) in fd_0's
+// columns, dC2 of column tile j in cd_j's columns.
+__device__ __forceinline__ uint32_t col_fd(int j) { return 256u * j; }
+__device__ __forceinline__ uint32_t col_cd(int j) { return 256u * j + 128u; }
+
 __global__ void __launch_bounds__(UM_THREADS, 1) corr_umma_kernel(const __grid_constant__ UmmaParams prm) {
   extern __shared__ uint8_t um_raw[];
   uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(um_raw) + 1023) & ~(uintptr_t)1023);
@@ -126,19 +134,25 @@ __global__ void __launch_bounds__(UM_THREADS, 1) corr_umma_kernel(const __grid_c
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 3);
   __shared__ float s_red[8][4];
   __shared__ float s_rowsum[2][128];
-  __shared__ float s_sign[128];
+  __shared__ float s_sign[256];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int kb = blockIdx.x;
   if (threadIdx.x == 64) stamp(prm, 0);
+  // work item: (pair k, image b, 128-row tile ti of the first operand); the CTA walks the NT column tiles itself
+  const int NT = prm.ntile, Prows = 128 * NT;
+  const int ti = blockIdx.x % NT, kb = blockIdx.x / NT;
   const int k = kb / prm.B, b = kb - k * prm.B;
   const int nfd = (prm.ldf + 63) / 64, ncd = prm.ldc / 32, nb = prm.ldc / 32;
-  const int njobs = nfd + ncd + 2;
-  const int row1 = b * 128, row2 = (k * prm.B + b) * 128;  // panel rows of the first / second operand
-  const bool same = (k == 0);                               // intra pair: second operand == first, load it once
+  const int nop = nfd + ncd;                                  // operand chunks per column tile
+  const int J0 = NT * nop;                                    // jobs of the correlation phase
+  const int row1 = b * Prows + 128 * ti;                      // first operand: slot 0, row tile ti
+  const int row2 = (k * prm.B + b) * Prows;                   // second operand: slot k (+ 128 tj)
   const bool depth_round = prm.has_depth && k == 0;
-  // job -> stage is j % 3: the two gradient-operand jobs come last, U takes the stage after them
-  uint8_t* u_hi = ring + ((njobs % UM_NSTAGE) * UM_STAGE);
+  const int rounds = depth_round ? 2 : 1;
+  // ring stages after the correlation phase: first-operand code rows, second-operand code rows, U
+  const int sC1 = J0 % UM_NSTAGE, sC2 = (J0 + 1) % UM_NSTAGE, sU = (J0 + 2) % UM_NSTAGE;
+  const int nC2 = (NT == 1) ? 1 : rounds * NT;                // loads of second-operand code rows (reloaded per tile)
+  uint8_t* u_hi = ring + sU * UM_STAGE;
   uint8_t* u_lo = u_hi + 32768;
 
   if (threadIdx.x == 0) {
@@ -152,8 +166,10 @@ __global__ void __launch_bounds__(UM_THREADS, 1) corr_umma_kernel(const __grid_c
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
-  if (threadIdx.x >= 64 && threadIdx.x < 192)
-    s_sign[threadIdx.x - 64] = depth_round ? __ldg(prm.dsign + (size_t)b * 128 + threadIdx.x - 64) : 0.f;
+  if (threadIdx.x >= 64) {
+    const int t = threadIdx.x - 64;
+    if (t < Prows) s_sign[t] = depth_round ? __ldg(prm.dsign + (size_t)b * Prows + t) : 0.f;
+  }
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -164,26 +180,32 @@ __global__ void __launch_bounds__(UM_THREADS, 1) corr_umma_kernel(const __grid_c
     if (lane == 0) {
       prefetch_tmap(&prm.tm_fhi); prefetch_tmap(&prm.tm_flo); prefetch_tmap(&prm.tm_chi);
       prefetch_tmap(&prm.tm_clo); prefetch_tmap(&prm.tm_bhi); prefetch_tmap(&prm.tm_blo);
-      for (int j = 0; j < njobs; ++j) {
-        const int s = j % UM_NSTAGE;
-        const uint32_t ph = (j / UM_NSTAGE) & 1;
-        if (!mbar_wait(&empty[s], ph ^ 1)) { raise(prm.err, 1); break; }
+      int cnt[UM_NSTAGE] = {0, 0, 0};     // fills of each stage so far (phase = count & 1)
+      bool ok = true;
+      for (int t = 0; t < J0 + 1 + nC2 && ok; ++t) {
+        int s;
+        if (t < J0) s = t % UM_NSTAGE; else if (t == J0) s = sC1; else s = sC2;
+        ok = mbar_wait(&empty[s], (cnt[s] & 1) ^ 1);
+        if (!ok) break;
+        ++cnt[s];
         uint8_t* st = ring + s * UM_STAGE;
         if (prm.dbg & 1) { mbar_arrive(&full[s]); continue; }
-        if (j < nfd + ncd) {  // operand chunks: [first hi | first lo | second hi | second lo], 16 KB each
-          const bool isf = j < nfd;
-          const int c0 = isf ? j * 64 : (j - nfd) * 32;
+        if (t < J0) {         // operand chunk of column tile tj: [first hi | first lo | second hi | second lo], 16 KB each
+          const int tj = t / nop, c = t - tj * nop;
+          const bool same = (k == 0 && tj == ti);   // intra pair, diagonal tile: both operands are the same rows
+          const bool isf = c < nfd;
+          const int c0 = isf ? c * 64 : (c - nfd) * 32;
           const CUtensorMap* mh = isf ? &prm.tm_fhi : &prm.tm_chi;
           const CUtensorMap* ml = isf ? &prm.tm_flo : &prm.tm_clo;
           mbar_arrive_expect_tx(&full[s], same ? 32768u : 65536u);
           tma_load_2d(st, mh, &full[s], c0, row1);
           tma_load_2d(st + 16384, ml, &full[s], c0, row1);
           if (!same) {
-            tma_load_2d(st + 32768, mh, &full[s], c0, row2);
-            tma_load_2d(st + 49152, ml, &full[s], c0, row2);
+            tma_load_2d(st + 32768, mh, &full[s], c0, row2 + 128 * tj);
+            tma_load_2d(st + 49152, ml, &full[s], c0, row2 + 128 * tj);
           }
         } else {              // gradient operands: bf16 code rows [128 x ldc] as ldc/32 boxes of [128 x 64 B]; hi @0, lo @32 KB
-          const int r = (j == nfd + ncd) ? row2 : row1;
+          const int r = (t == J0) ? row1 : row2 + 128 * ((t - J0 - 1) % NT);
           mbar_arrive_expect_tx(&full[s], (uint32_t)(2 * nb * 8192));
           for (int a = 0; a < nb; ++a) {
             tma_load_2d(st + a * 8192, &prm.tm_bhi, &full[s], a * 32, r);
@@ -191,6 +213,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) corr_umma_kernel(const __grid_c
           }
         }
       }
+      if (!ok) raise(prm.err, 1);
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
@@ -203,79 +226,95 @@ __global__ void __launch_bounds__(UM_THREADS, 1) corr_umma_kernel(const __grid_c
       const uint64_t dk128 = smem_desc(0, 16, 1024, SW_128B);       // K-major, 128-byte rows
       const uint64_t dmn128 = smem_desc(0, 16384, 1024, SW_128B);   // MN-major, 64-element atoms 16 KB apart
       const uint64_t dmn64 = smem_desc(0, 8192, 512, SW_64B);       // MN-major, 32-element atoms 8 KB apart
+      int cnt[UM_NSTAGE] = {0, 0, 0};
       bool ok = true;
-      int j = 0;
-      for (; j < nfd + ncd && ok; ++j) {
-        const int s = j % UM_NSTAGE;
-        ok = mbar_wait(&full[s], (j / UM_NSTAGE) & 1);
+      for (int t = 0; t < J0 && ok; ++t) {
+        const int s = t % UM_NSTAGE;
+        ok = mbar_wait(&full[s], cnt[s] & 1);
+        ++cnt[s];
         tc_fence_after_sync();
         if (prm.dbg & 2) { mbar_arrive(&empty[s]); continue; }
+        const int tj = t / nop, c = t - tj * nop;
+        const bool same = (k == 0 && tj == ti);
         const uint32_t a0 = smem_u32(ring + s * UM_STAGE) >> 4;
         const uint32_t b0 = same ? a0 : a0 + (32768 >> 4);
         const uint64_t ah = dk128 + a0, al = ah + (16384 >> 4), bh = dk128 + b0, bl = bh + (16384 >> 4);
-        if (j < nfd) {
+        if (c < nfd) {
+          const uint32_t acc = tmem + col_fd(tj);
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {  // 4 x 32 B per 128 B row: K = 16 bf16 per instruction
-            mma_f16(tmem + TM_FD, ah + 2 * ks, bh + 2 * ks, id_f, (j | ks) != 0);
-            mma_f16(tmem + TM_FD, ah + 2 * ks, bl + 2 * ks, id_f, 1);
-            mma_f16(tmem + TM_FD, al + 2 * ks, bh + 2 * ks, id_f, 1);
+            mma_f16(acc, ah + 2 * ks, bh + 2 * ks, id_f, (c | ks) != 0);
+            mma_f16(acc, ah + 2 * ks, bl + 2 * ks, id_f, 1);
+            mma_f16(acc, al + 2 * ks, bh + 2 * ks, id_f, 1);
           }
         } else {
+          const uint32_t acc = tmem + col_cd(tj);
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {  // K = 8 tf32 per instruction
-            mma_tf32(tmem + TM_CD, ah + 2 * ks, bh + 2 * ks, id_c, (j != nfd) || ks != 0);
-            mma_tf32(tmem + TM_CD, ah + 2 * ks, bl + 2 * ks, id_c, 1);
-            mma_tf32(tmem + TM_CD, al + 2 * ks, bh + 2 * ks, id_c, 1);
+            mma_tf32(acc, ah + 2 * ks, bh + 2 * ks, id_c, (c != nfd) || ks != 0);
+            mma_tf32(acc, ah + 2 * ks, bl + 2 * ks, id_c, 1);
+            mma_tf32(acc, al + 2 * ks, bh + 2 * ks, id_c, 1);
           }
         }
         mma_commit(&empty[s]);
       }
       if (prm.dbg & 2) mbar_arrive(acc_full); else mma_commit(acc_full);
-      // gradient operands: job j = second operand's code rows, job j+1 = first operand's
-      uint32_t g2 = 0, g1 = 0;
+      // first-operand code rows (loaded once)
+      uint32_t g1 = 0;
       if (ok) {
-        ok = mbar_wait(&full[j % UM_NSTAGE], (j / UM_NSTAGE) & 1) &&
-             mbar_wait(&full[(j + 1) % UM_NSTAGE], ((j + 1) / UM_NSTAGE) & 1);
-        g2 = smem_u32(ring + (j % UM_NSTAGE) * UM_STAGE) >> 4;
-        g1 = smem_u32(ring + ((j + 1) % UM_NSTAGE) * UM_STAGE) >> 4;
+        ok = mbar_wait(&full[sC1], cnt[sC1] & 1);
+        ++cnt[sC1];
+        g1 = smem_u32(ring + sC1 * UM_STAGE) >> 4;
       }
+      const uint32_t g2 = smem_u32(ring + sC2 * UM_STAGE) >> 4;
       const uint32_t uh = smem_u32(u_hi) >> 4, ul = smem_u32(u_lo) >> 4;
-      const int rounds = depth_round ? 2 : 1;
+      int step = 0;   // (round, column tile) counter: phase of u_ready / grad_full
+      int c2_loaded = 0;
       for (int rd = 0; rd < rounds && ok; ++rd) {
-        ok = mbar_wait(u_ready, rd & 1);
-        tc_fence_after_sync();
-        if (prm.dbg & 2) { mbar_arrive(grad_full); continue; }
+        for (int tj = 0; tj < NT && ok; ++tj, ++step) {
+          if (c2_loaded < nC2 && (NT > 1 || step == 0)) {   // second-operand code rows of this column tile
+            ok = mbar_wait(&full[sC2], cnt[sC2] & 1);
+            ++cnt[sC2];
+            ++c2_loaded;
+          }
+          ok = ok && mbar_wait(u_ready, step & 1);
+          tc_fence_after_sync();
+          if (prm.dbg & 2) { mbar_arrive(grad_full); continue; }
+          const uint32_t d1 = tmem + col_fd(0), d2 = tmem + col_cd(tj);
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {  // dC1[p, d] += U[p, 16 q] . C2n[16 q, d]
-          // U as K-major A: 32 B per K-step inside a 128 B row, the second 64-q atom 16 KB further;
-          // code rows as MN-major B (n = d contiguous): 16 k-rows (q) per step = 1024 B
-          const uint32_t aoff = ((ks >> 2) * 16384 + (ks & 3) * 32) >> 4;
-          const uint64_t a_h = dk128 + uh + aoff, a_l = dk128 + ul + aoff;
-          const uint64_t b_h = dmn64 + g2 + ks * 64, b_l = b_h + (32768 >> 4);
-          mma_f16(tmem + TM_D1, a_h, b_h, id_g1, ks != 0);
-          mma_f16(tmem + TM_D1, a_h, b_l, id_g1, 1);
-          mma_f16(tmem + TM_D1, a_l, b_h, id_g1, 1);
-        }
+          for (int ks = 0; ks < 8; ++ks) {  // dC1[p, d] += U[p, 16 q] . C2n[16 q, d]   (accumulates over column tiles)
+            // U as K-major A: 32 B per K-step inside a 128 B row, the second 64-q atom 16 KB further;
+            // code rows as MN-major B (n = d contiguous): 16 k-rows (q) per step = 1024 B
+            const uint32_t aoff = ((ks >> 2) * 16384 + (ks & 3) * 32) >> 4;
+            const uint64_t a_h = dk128 + uh + aoff, a_l = dk128 + ul + aoff;
+            const uint64_t b_h = dmn64 + g2 + ks * 64, b_l = b_h + (32768 >> 4);
+            mma_f16(d1, a_h, b_h, id_g1, (tj | ks) != 0);
+            mma_f16(d1, a_h, b_l, id_g1, 1);
+            mma_f16(d1, a_l, b_h, id_g1, 1);
+          }
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {  // dC2[q, d] += U[16 p, q]^T . C1n[16 p, d]
-          // the same U tile as MN-major A (m = q contiguous): 16 k-rows (p) per step = 2048 B
-          const uint64_t a_h = dmn128 + uh + ks * 128, a_l = dmn128 + ul + ks * 128;
-          const uint64_t b_h = dmn64 + g1 + ks * 64, b_l = b_h + (32768 >> 4);
-          mma_f16(tmem + TM_D2, a_h, b_h, id_g2, ks != 0);
-          mma_f16(tmem + TM_D2, a_h, b_l, id_g2, 1);
-          mma_f16(tmem + TM_D2, a_l, b_h, id_g2, 1);
+          for (int ks = 0; ks < 8; ++ks) {  // dC2[q, d] = U[16 p, q]^T . C1n[16 p, d]
+            // the same U tile as MN-major A (m = q contiguous): 16 k-rows (p) per step = 2048 B
+            const uint64_t a_h = dmn128 + uh + ks * 128, a_l = dmn128 + ul + ks * 128;
+            const uint64_t b_h = dmn64 + g1 + ks * 64, b_l = b_h + (32768 >> 4);
+            mma_f16(d2, a_h, b_h, id_g2, ks != 0);
+            mma_f16(d2, a_h, b_l, id_g2, 1);
+            mma_f16(d2, a_l, b_h, id_g2, 1);
+          }
+          if (c2_loaded < nC2) mma_commit(&empty[sC2]);   // the next column tile's code rows may overwrite this stage
+          mma_commit(grad_full);
         }
-        mma_commit(grad_full);
       }
       if (!ok) raise(prm.err, 2);
     }
   } else {
     // ================================ epilogue (warps 2..9) ================================
-    // two warps per TMEM lane group; the pair splits the 128 columns in halves
+    // two warps per TMEM lane group; the pair splits the 128 columns of a tile in halves
     const int lg = warp & 3;                 // TMEM lane group this warp may access
-    const int half = (warp - 2) >> 2;        // 0: columns 0..63, 1: columns 64..127
+    const int half = (warp - 2) >> 2;        // 0: columns 0..63, 1: columns 64..127 of a tile
     const int ew = warp - 2;                 // 0..7
-    const int p = 32 * lg + lane;            // row of fd / cd / dC1 / dC2 handled by this thread
+    const int row = 32 * lg + lane;          // row within the tile
+    const int p = 128 * ti + row;            // sample point (row of fd / cd / dC1)
     const uint32_t tlane = tmem + ((uint32_t)(32 * lg) << 16);
     const int P = prm.P;
     const bool pointwise = prm.flags & DG_FLAG_POINTWISE;
@@ -292,109 +331,108 @@ __global__ void __launch_bounds__(UM_THREADS, 1) corr_umma_kernel(const __grid_c
     const float dsh = prm.depth_shift;
     float sum_loss = 0.f, sum_cd = 0.f, sum_dloss = 0.f, sum_dd = 0.f;
     float v[32], c[32];
+    uint32_t passmask[2][2];                 // clamp indicator bits of this thread's row: [column tile][32-column chunk]
 
     if (threadIdx.x == 64) stamp(prm, 1);
     bool ok = mbar_wait(acc_full, 0);
     tc_fence_after_sync();
     if (threadIdx.x == 64) stamp(prm, 2);
     float c0 = prm.shift[k] - old_mean;      // fd' - shift = fd - rowmean + old_mean - shift = fd - c0
-    if (pointwise) {                         // rowmean over q: padded columns are exactly zero, no mask needed
+    if (pointwise) {                         // rowmean over all q: padded columns are exactly zero, no mask needed
       float s = 0.f;
+      for (int tj = 0; tj < NT; ++tj) {
 #pragma unroll
-      for (int h2 = 0; h2 < 2; ++h2) {
-        tmem_ld_32x32(tlane + TM_FD + 32 * (2 * half + h2), v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) s += v[i];
-      }
-      s_rowsum[half][p] = s;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      c0 += (s_rowsum[0][p] + s_rowsum[1][p]) / (float)P;
-    }
-    if (threadIdx.x == 64) stamp(prm, 3);
-    // ---- main pass: branch-free.  Padded rows/columns have fd = cd = 0 and depth sign 0, so they add nothing to
-    //      the sums; only U needs the explicit mask (inv = 0 for padded rows, tail zeroing for padded columns).
-#pragma unroll 1
-    for (int h2 = 0; h2 < 2; ++h2) {
-      const int cc = 2 * half + h2;
-      tmem_ld_32x32(tlane + TM_FD + 32 * cc, v);
-      tmem_ld_32x32(tlane + TM_CD + 32 * cc, c);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const float cdv = c[i];
-        const float cl = fminf(fmaxf(cdv, lo), hi);
-        const float f = v[i] - c0;
-        const float dd = sp * s_sign[32 * cc + i];
-        sum_loss = fmaf(-cl, f, sum_loss);
-        sum_cd += cdv;
-        sum_dloss = fmaf(-cl, dd - dsh, sum_dloss);
-        sum_dd += dd;
-        const bool pass = (cdv >= lo) && (cdv <= hi);
-        v[i] = pass ? -f * inv : 0.f;
-      }
-      if (32 * cc + 32 > P) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (32 * cc + i >= P) v[i] = 0.f;
-      }
-      store_u_chunk(u_hi, u_lo, p, cc, v);
-    }
-    // ---- optional dense outputs (materialize_cd / tests): a separate pass keeps the main one lean
-    if (prm.cd_out || prm.loss_out || prm.dd_out || prm.fd_dbg) {
-      const size_t obase = (((size_t)k * prm.B + b) * P + p) * P;
-      for (int h2 = 0; h2 < 2; ++h2) {
-        const int cc = 2 * half + h2;
-        tmem_ld_32x32(tlane + TM_FD + 32 * cc, v);
-        tmem_ld_32x32(tlane + TM_CD + 32 * cc, c);
-        tmem_ld_wait();
-        if (prm.fd_dbg) {
-          float* dst = prm.fd_dbg + ((size_t)kb * 128 + p) * 128 + 32 * cc;
-#pragma unroll
-          for (int i = 0; i < 32; ++i) dst[i] = v[i];
-        }
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int q = 32 * cc + i;
-          if (p < P && q < P) {
-            const float cl = fminf(fmaxf(c[i], lo), hi);
-            if (prm.cd_out) prm.cd_out[obase + q] = c[i];
-            if (prm.loss_out) prm.loss_out[obase + q] = -cl * (v[i] - c0);
-            if (prm.dd_out && depth_round) prm.dd_out[((size_t)b * P + p) * P + q] = sp * s_sign[q];
-          }
-        }
-      }
-    }
-    const int rounds = depth_round ? 2 : 1;
-    if (threadIdx.x == 64) stamp(prm, 4);
-    float* scratch = reinterpret_cast<float*>(u_hi) + ew * (32 * 33);  // per-warp transpose buffer, aliases U once it is dead
-    for (int rd = 0; rd < rounds; ++rd) {
-      fence_proxy_async_smem();
-      tc_fence_before_sync();
-      mbar_arrive(u_ready);
-      ok = ok && mbar_wait(grad_full, rd & 1);
-      tc_fence_after_sync();
-      if (threadIdx.x == 64) stamp(prm, 5 + 2 * rd);
-      // U is dead until it is rewritten below: drain through it.  half 0 drains dC1, half 1 drains dC2.
-      const size_t slab = (size_t)prm.B * 128 * prm.ldc;
-      const size_t which = (rd == 0) ? (size_t)k : (size_t)prm.npairs;
-      float* dbase = (half == 0 ? prm.dC1 : prm.dC2) + which * slab + ((size_t)b * 128 + 32 * lg) * prm.ldc;
-      const uint32_t tacc = tlane + (half == 0 ? TM_D1 : TM_D2);
-      for (int cc = 0; cc < ncd; ++cc) drain_block(tacc + 32 * cc, scratch, dbase, prm.ldc, 32 * cc, lane, v);
-      if (threadIdx.x == 64) stamp(prm, 6 + 2 * rd);
-      if (rd + 1 < rounds) {  // depth term: U_d = -(s_p s_q - depth_shift) 1[clamp passes] / (B P^2)
-        asm volatile("bar.sync 1, 256;" ::: "memory");  // every warp is done with its scratch before U is rewritten
-#pragma unroll 1
         for (int h2 = 0; h2 < 2; ++h2) {
-          const int cc = 2 * half + h2;
-          tmem_ld_32x32(tlane + TM_CD + 32 * cc, c);
+          tmem_ld_32x32(tlane + col_fd(tj) + 32 * (2 * half + h2), v);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const bool pass = (32 * cc + i < P) && (c[i] >= lo) && (c[i] <= hi);
-            v[i] = pass ? -(sp * s_sign[32 * cc + i] - dsh) * inv : 0.f;
+          for (int i = 0; i < 32; ++i) s += v[i];
+        }
+      }
+      s_rowsum[half][row] = s;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      c0 += (s_rowsum[0][row] + s_rowsum[1][row]) / (float)P;
+    }
+    if (threadIdx.x == 64) stamp(prm, 3);
+    float* scratch = reinterpret_cast<float*>(u_hi) + ew * (32 * 33);  // per-warp transpose buffer, aliases U while it is dead
+    const size_t slab = (size_t)prm.B * Prows * prm.ldc;
+    int step = 0;
+    for (int rd = 0; rd < rounds; ++rd) {
+#pragma unroll
+      for (int tj = 0; tj < 2; ++tj) {
+        if (tj < NT) {
+          if (step > 0) asm volatile("bar.sync 1, 256;" ::: "memory");  // every warp is done with its scratch before U is rewritten
+#pragma unroll
+          for (int h2 = 0; h2 < 2; ++h2) {
+            const int cc = 2 * half + h2;
+            const int q0 = 128 * tj + 32 * cc;
+            if (rd == 0) {
+              // ---- main pass: branch-free.  Padded rows/columns have fd = cd = 0 and depth sign 0, so they add nothing
+              //      to the sums; only U needs the explicit mask (inv = 0 for padded rows, tail zeroing for padded columns).
+              tmem_ld_32x32(tlane + col_fd(tj) + 32 * cc, v);
+              tmem_ld_32x32(tlane + col_cd(tj) + 32 * cc, c);
+              tmem_ld_wait();
+              if (prm.cd_out || prm.loss_out || prm.dd_out || prm.fd_dbg) {   // optional dense outputs (materialize_cd / tests)
+                const size_t obase = (((size_t)k * prm.B + b) * P + p) * P;
+                if (prm.fd_dbg) {
+                  float* dst = prm.fd_dbg + ((size_t)kb * Prows + p) * Prows + q0;
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) dst[i] = v[i];
+                }
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                  const int q = q0 + i;
+                  if (p < P && q < P) {
+                    const float cl = fminf(fmaxf(c[i], lo), hi);
+                    if (prm.cd_out) prm.cd_out[obase + q] = c[i];
+                    if (prm.loss_out) prm.loss_out[obase + q] = -cl * (v[i] - c0);
+                    if (prm.dd_out && depth_round) prm.dd_out[((size_t)b * P + p) * P + q] = sp * s_sign[q];
+                  }
+                }
+              }
+              uint32_t bits = 0;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const float cdv = c[i];
+                const float cl = fminf(fmaxf(cdv, lo), hi);
+                const float f = v[i] - c0;
+                const float dd = sp * s_sign[q0 + i];
+                sum_loss = fmaf(-cl, f, sum_loss);
+                sum_cd += cdv;
+                sum_dloss = fmaf(-cl, dd - dsh, sum_dloss);
+                sum_dd += dd;
+                const bool pass = (cdv >= lo) && (cdv <= hi) && (q0 + i < P);
+                bits |= pass ? (1u << i) : 0u;
+                v[i] = pass ? -f * inv : 0.f;
+              }
+              passmask[tj][h2] = bits;
+            } else {
+              // ---- depth term: U_d = -(s_p s_q - depth_shift) 1[clamp passes] / (B P^2), indicator from the main pass
+              const uint32_t bits = passmask[tj][h2];
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = ((bits >> i) & 1u) ? -(sp * s_sign[q0 + i] - dsh) * inv : 0.f;
+            }
+            store_u_chunk(u_hi, u_lo, row, cc, v);
           }
-          store_u_chunk(u_hi, u_lo, p, cc, v);
+          if (threadIdx.x == 64 && step == 0) stamp(prm, 4);
+          fence_proxy_async_smem();
+          tc_fence_before_sync();
+          mbar_arrive(u_ready);
+          ok = ok && mbar_wait(grad_full, step & 1);
+          tc_fence_after_sync();
+          if (threadIdx.x == 64 && step == 0) stamp(prm, 5);
+          // U is dead until it is rewritten: drain through it.  The two warps of a lane group split the column chunks.
+          const size_t which = (rd == 0) ? (size_t)k : (size_t)prm.npairs;
+          {  // dC2 rows of column tile tj, partial buffer of row tile ti
+            float* dbase = prm.dC2 + (which * NT + ti) * slab + ((size_t)b * Prows + 128 * tj + 32 * lg) * prm.ldc;
+            for (int cc = half; cc < ncd; cc += 2) drain_block(tlane + col_cd(tj) + 32 * cc, scratch, dbase, prm.ldc, 32 * cc, lane, v);
+          }
+          if (tj == NT - 1) {  // dC1 rows of row tile ti (complete after the last column tile)
+            float* dbase = prm.dC1 + which * slab + ((size_t)b * Prows + 128 * ti + 32 * lg) * prm.ldc;
+            for (int cc = 1 - half; cc < ncd; cc += 2) drain_block(tlane + col_fd(0) + 32 * cc, scratch, dbase, prm.ldc, 32 * cc, lane, v);
+          }
+          if (threadIdx.x == 64 && step == 0) stamp(prm, 6);
+          ++step;
         }
       }
     }
@@ -412,7 +450,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) corr_umma_kernel(const __grid_c
         float t = 0.f;
 #pragma unroll
         for (int w8 = 0; w8 < 8; ++w8) t += s_red[w8][lane];
-        prm.partials[(size_t)kb * 4 + lane] = t;
+        prm.partials[(size_t)blockIdx.x * 4 + lane] = t;
       }
       // ---- fused finalize: the last CTA to get here folds all partial sums into the 8 output scalars
       __threadfence();
@@ -425,9 +463,10 @@ __global__ void __launch_bounds__(UM_THREADS, 1) corr_umma_kernel(const __grid_c
         float acc[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-        const int total = prm.npairs * prm.B;
+        const int per_pair = prm.B * NT;
+        const int total = prm.npairs * per_pair;
         for (int e = lane; e < total; e += 32) {   // fixed order -> deterministic
-          const int kk = e / prm.B;
+          const int kk = e / per_pair;
           const int g = prm.group[kk];
           const float l = __ldcg(prm.partials + (size_t)e * 4), c2 = __ldcg(prm.partials + (size_t)e * 4 + 1);
           if (g == DG_GROUP_INTRA) { acc[0] += l; acc[1] += c2; }
@@ -528,12 +567,13 @@ static int make_map_2d(CUtensorMap* m, CUtensorMapDataType dt, int elt_bytes, co
   return DG_OK;
 }
 
-int corr_loss_umma(const dg_panels_t* pan, const float* fmean, int nsplit, const float* dsign, int npairs, int B, int P, int ldf,
+int corr_loss_umma(const dg_panels_t* pan, const float* fmean, int nsplit, const float* dsign, int npairs, int B, int P, int Prows, int ldf,
                    int ldc, const float* pair_shift, const int32_t* pair_group, float depth_shift, int flags,
                    float* out8, float* dC1, float* dC2, float* cd_out, float* loss_out, float* dd_out, float* fd_dbg,
                    void* ws, cudaStream_t st) {
   UmmaParams prm;
-  const uint64_t rows = (uint64_t)npairs * B * 128;
+  const int ntile = Prows / 128;
+  const uint64_t rows = (uint64_t)npairs * B * Prows;
   int rc;
   if ((rc = make_map_2d(&prm.tm_fhi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, pan->f_hi, ldf, rows, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   if ((rc = make_map_2d(&prm.tm_flo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, pan->f_lo, ldf, rows, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
@@ -549,6 +589,7 @@ int corr_loss_umma(const dg_panels_t* pan, const float* fmean, int nsplit, const
   prm.dsign = dsign;
   prm.dots = (flags & DG_FLAG_POINTWISE) ? dots : nullptr;
   prm.npairs = npairs; prm.B = B; prm.P = P; prm.ldf = ldf; prm.ldc = ldc; prm.flags = flags;
+  prm.ntile = ntile;
   prm.has_depth = dsign != nullptr;
   prm.depth_shift = depth_shift;
   prm.inv_cnt = 1.0f / ((float)B * (float)P * (float)P);
@@ -577,7 +618,7 @@ int corr_loss_umma(const dg_panels_t* pan, const float* fmean, int nsplit, const
     attr_set = true;
   }
   DG_PRE(st);
-  corr_umma_kernel<<<npairs * B, UM_THREADS, UM_SMEM, st>>>(prm);
+  corr_umma_kernel<<<npairs * B * ntile, UM_THREADS, UM_SMEM, st>>>(prm);
   DG_LAUNCH_OK("corr_umma_kernel");
   return DG_OK;  // out8 is written by the last CTA of corr_umma_kernel
 }

@@ -62,14 +62,14 @@ int launch_gather_all(const SetTable& fsets, const SetTable& csets, int nsets, i
 int launch_gather_bwd(const SetTable& tab, int nsets, int B, int C, int H, int W, const float* coords, int S,
                       const int64_t* perms, float eps, int Prows, int ld, const float* cn, const float* cn_lo,
                       const float* rnorm, const float* dC1, const float* dC2, int npairs, const PairTable& pt,
-                      int has_depth, const GroupW& gw, cudaStream_t st);
+                      int has_depth, const GroupW& gw, cudaStream_t st, int ni = 1);
 int launch_corr_finalize(const float* partials, int npairs, int B, int P, const int32_t* group, int has_depth,
                          const int* err, float* out8, int n_pt, cudaStream_t st);
 int corr_loss_simt(const float* fn, const float* cn, const float* fmean, int nsplit, const float* dsign, int npairs, int B, int P,
                    int Prows, int ldf, int ldc, const float* pair_shift, const int32_t* pair_group, float depth_shift,
                    int flags, float* out8, float* dC1, float* dC2, float* cd_out, float* loss_out, float* dd_out,
                    void* ws, cudaStream_t st);
-int corr_loss_umma(const dg_panels_t* pan, const float* fmean, int nsplit, const float* dsign, int npairs, int B, int P, int ldf,
+int corr_loss_umma(const dg_panels_t* pan, const float* fmean, int nsplit, const float* dsign, int npairs, int B, int P, int Prows, int ldf,
                    int ldc, const float* pair_shift, const int32_t* pair_group, float depth_shift, int flags,
                    float* out8, float* dC1, float* dC2, float* cd_out, float* loss_out, float* dd_out, float* fd_dbg,
                    void* ws, cudaStream_t st);

@@ -35,8 +35,9 @@ static void make_plan(const dg_loss_desc_t* d, dg_loss_plan_t* p) {
   p->npairs = 2 + d->neg_samples;
   p->ldf = round_up(d->C, 32);
   p->ldc = round_up(d->D, 32);
-  p->kernel = (P <= 128 && p->ldc <= 128 && !(d->flags & DG_FLAG_FORCE_SIMT)) ? 1 : 0;
-  p->Prows = p->kernel ? 128 : round_up(P, 64);
+  p->kernel = (P <= 256 && p->ldc <= 128 && !(d->flags & DG_FLAG_FORCE_SIMT)) ? 1 : 0;
+  p->Prows = p->kernel ? round_up(P, 128) : round_up(P, 64);
+  const size_t ni = p->kernel ? p->Prows / 128 : 1;  // dC2 partial buffers (one per 128-row tile of the first operand)
   const size_t np = p->npairs, B = d->B, Pr = p->Prows;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += al256(bytes); return o; };
@@ -48,7 +49,7 @@ static void make_plan(const dg_loss_desc_t* d, dg_loss_plan_t* p) {
   p->ws_bytes = corr_workspace_bytes(p->npairs, d->B, P);
   p->ws = take(p->ws_bytes);
   p->dC1 = take((np + 1) * B * Pr * p->ldc * 4);
-  p->dC2 = take((np + 1) * B * Pr * p->ldc * 4);
+  p->dC2 = take((np + 1) * ni * B * Pr * p->ldc * 4);
   if (p->kernel) {
     p->c_hi = take(np * B * Pr * p->ldc * 4);
     p->c_lo = take(np * B * Pr * p->ldc * 4);
@@ -169,7 +170,7 @@ extern "C" int dg_loss_forward(const dg_loss_desc_t* d, const dg_loss_io_t* io, 
     pan.format = DG_PANEL_CODE_SPLIT;
     pan.f_hi = A + pl.f_hi; pan.f_lo = A + pl.f_lo; pan.c_hi = A + pl.c_hi; pan.c_lo = A + pl.c_lo;
     pan.cb_hi = A + pl.cb_hi; pan.cb_lo = A + pl.cb_lo;
-    return corr_loss_umma(&pan, fmean, nsplit, dsign, np, B, P, pl.ldf, pl.ldc, shifts, groups, d->depth_feat_shift, kflags,
+    return corr_loss_umma(&pan, fmean, nsplit, dsign, np, B, P, pl.Prows, pl.ldf, pl.ldc, shifts, groups, d->depth_feat_shift, kflags,
                           io->out8, dC1, dC2, io->cd_out, io->loss_out, io->dd_out, io->fd_dbg, A + pl.ws, st);
   }
   return corr_loss_simt(reinterpret_cast<const float*>(A + pl.f_hi), reinterpret_cast<const float*>(A + pl.c_hi), fmean,
@@ -210,5 +211,6 @@ extern "C" int dg_loss_backward(const dg_loss_desc_t* d, const dg_loss_io_t* io,
                            pl.kernel ? reinterpret_cast<const float*>(A + pl.c_lo) : nullptr,
                            reinterpret_cast<const float*>(A + pl.crn), reinterpret_cast<const float*>(A + pl.dC1),
                            reinterpret_cast<const float*>(A + pl.dC2), pl.npairs, pt,
-                           (d->flags & DG_FLAG_DEPTH_TERM) ? 1 : 0, gw, reinterpret_cast<cudaStream_t>(stream));
+                           (d->flags & DG_FLAG_DEPTH_TERM) ? 1 : 0, gw, reinterpret_cast<cudaStream_t>(stream),
+                           pl.kernel ? pl.Prows / 128 : 1);
 }

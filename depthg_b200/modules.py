@@ -172,12 +172,12 @@ def _gather(t, coords, S, set_coord, set_slot, perm, eps, Prows, ld, out, rnorm,
 
 
 def corr_kernel_choice(P: int, D: int) -> str:
-    """Which correlation kernel a shape gets: the tcgen05 kernel needs S*S <= 128 and dim <= 128;
+    """Which correlation kernel a shape gets: the tcgen05 kernel needs S*S <= 256 and dim <= 128;
     everything else runs the generic CUDA-core kernel.  DEPTHG_B200_CORR=simt forces the generic one."""
     import os
     if os.environ.get("DEPTHG_B200_CORR", "") == "simt":
         return "simt"
-    return "umma" if (P <= 128 and _lib.panel_ld(D) <= 128) else "simt"
+    return "umma" if (P <= 256 and _lib.panel_ld(D) <= 128) else "simt"
 
 
 def _check_coords(coords, B):
@@ -292,7 +292,7 @@ class _CorrLossFn(torch.autograd.Function):
         dd_out = torch.empty((B, P, P), **f32) if (materialize and has_depth) else None
         fd_dbg = None
         if _CorrLossFn.debug and plan.kernel == 1:
-            fd_dbg = torch.zeros((npairs, B, 128, 128), **f32)
+            fd_dbg = torch.zeros((npairs, B, plan.Prows, plan.Prows), **f32)
             _CorrLossFn.last_fd = fd_dbg
         io = _lib.LossIO()
         io.feats, io.feats_pos, io.code, io.code_pos = (feats.data_ptr(), feats_pos.data_ptr(), code.data_ptr(),
@@ -314,9 +314,15 @@ class _CorrLossFn(torch.autograd.Function):
         ctx.desc, ctx.plan = desc, plan
         ctx.keep = (arena, coords, perms)          # the arena holds coords / panels / unit gradients for backward
         ctx.code_like = (code, code_pos)
-        _CorrLossFn.last_unit_grads = tuple(
-            arena[o:o + (npairs + 1) * B * plan.Prows * plan.ldc * 4].view(torch.float32).view(
-                npairs + 1, B, plan.Prows, plan.ldc) for o in (plan.dC1, plan.dC2)) if _CorrLossFn.debug else None
+        if _CorrLossFn.debug:   # views of the unit gradients (dC2 summed over its per-row-tile partial buffers)
+            ni = plan.Prows // 128 if plan.kernel == 1 else 1
+            n1 = (npairs + 1) * B * plan.Prows * plan.ldc
+            d1 = arena[plan.dC1:plan.dC1 + n1 * 4].view(torch.float32).view(npairs + 1, B, plan.Prows, plan.ldc)
+            d2 = arena[plan.dC2:plan.dC2 + n1 * ni * 4].view(torch.float32).view(npairs + 1, ni, B, plan.Prows,
+                                                                                 plan.ldc).sum(1)
+            _CorrLossFn.last_unit_grads = (d1, d2)
+        else:
+            _CorrLossFn.last_unit_grads = None
         if desc.flags & _lib.FLAG_FPS:   # the coordinates FPS produced (a view into the arena)
             coords_used = arena[plan.coords:plan.coords + 2 * B * P * 2 * 4].view(torch.float32).view(2, B, S, S, 2)
         else:

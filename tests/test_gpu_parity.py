@@ -353,7 +353,8 @@ def _run_both_kernels(name, monkeypatch):
     return cfg, t, res
 
 
-@pytest.mark.parametrize("name", ["small_fps", "small_random_pointwise", "cfg1_vits", "small_fps_noclamp"])
+@pytest.mark.parametrize("name", ["small_fps", "small_random_pointwise", "cfg1_vits", "small_fps_noclamp", "s12_fps",
+                                  "dense_14x14", "cfg4_cityscapes"])
 def test_tcgen05_kernel_matches_generic_kernel_stage_by_stage(name, monkeypatch):
     from depthg_b200.modules import corr_kernel_choice
     cfg, t, res = _run_both_kernels(name, monkeypatch)
@@ -370,7 +371,8 @@ def test_tcgen05_kernel_matches_generic_kernel_stage_by_stage(name, monkeypatch)
     got = u["fd"].cpu().numpy()
     np.testing.assert_allclose(got[0][:, :P, :P], fd_intra, atol=2e-5)
     np.testing.assert_allclose(got[1][:, :P, :P], fd_inter, atol=2e-5)
-    assert np.abs(got[:, :, P:, :]).max() == 0 and np.abs(got[:, :, :, P:]).max() == 0   # zero padding rows
+    if P % 128:
+        assert np.abs(got[:, :, P:, :]).max() == 0 and np.abs(got[:, :, :, P:]).max() == 0   # zero padding rows
     # (2) code correlations (tf32 x3 split must be fp32-grade) and the dense loss tensors
     for i, atol in ((1, 1e-6), (3, 1e-6), (5, 1e-6), (4, 1e-5)):   # cd tensors fp32-grade; loss carries the bf16x3 fd error
         np.testing.assert_allclose(u["out"][i].detach().cpu().numpy(), s["out"][i].detach().cpu().numpy(),
@@ -378,7 +380,8 @@ def test_tcgen05_kernel_matches_generic_kernel_stage_by_stage(name, monkeypatch)
     # (3) unit gradients of every pair (and the depth term) from the tensor-core GEMMs
     for key in ("dC1", "dC2"):
         a, b_ = u[key].cpu().numpy()[:, :, :P], s[key].cpu().numpy()[:, :, :P]
-        assert np.abs(u[key].cpu().numpy()[:-1, :, P:]).max() == 0
+        if P % 128:
+            assert np.abs(u[key].cpu().numpy()[:-1, :, P:]).max() == 0
         for k in range(a.shape[0]):
             if np.linalg.norm(b_[k]) > 0:
                 assert rel_err(a[k], b_[k]) < 5e-5, (key, k, rel_err(a[k], b_[k]))

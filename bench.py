@@ -163,7 +163,7 @@ def run_reference(args):
     from oracle import depthg_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    cfg = make_cfg()
+    cfg = make_cfg(CFG2["S"])
     gen = torch.Generator().manual_seed(0)
 
     def one_step(inp):
@@ -222,8 +222,11 @@ def main():
     ap.add_argument("--no-knn", action="store_true", help="skip the KNN-build side measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--nchw", action="store_true", help="NCHW-contiguous inputs instead of channels-last")
+    ap.add_argument("--feature-samples", type=int, default=CFG2["S"],
+                    help="S of the workload (11 = BASELINE configs[1]; 12 = the ViT-B paper script's value)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    CFG2["S"] = args.feature_samples
     if args.impl == "reference":
         return run_reference(args)
 
@@ -244,7 +247,7 @@ def main():
     hbm_peak, tf_burst, tf_sust, peak_src = peaks()
 
     B = CFG2["B"]
-    cfg = make_cfg()
+    cfg = make_cfg(CFG2["S"])
     loss_fn = ContrastiveCorrelationLoss(cfg)
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     # rotate over input sets totalling > L2 (126 MB) so no step finds its inputs cached

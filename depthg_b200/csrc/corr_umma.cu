@@ -122,6 +122,7 @@ __device__ __forceinline__ void drain_block(uint32_t taddr, float* scratch /*[32
 __device__ __forceinline__ uint32_t col_fd(int j) { return 256u * j; }
 __device__ __forceinline__ uint32_t col_cd(int j) { return 256u * j + 128u; }
 
+template <int NT>
 __global__ void __launch_bounds__(UM_THREADS, 1) corr_umma_kernel(const __grid_constant__ UmmaParams prm) {
   extern __shared__ uint8_t um_raw[];
   uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(um_raw) + 1023) & ~(uintptr_t)1023);
@@ -139,7 +140,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) corr_umma_kernel(const __grid_c
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 64) stamp(prm, 0);
   // work item: (pair k, image b, 128-row tile ti of the first operand); the CTA walks the NT column tiles itself
-  const int NT = prm.ntile, Prows = 128 * NT;
+  constexpr int Prows = 128 * NT;
   const int ti = blockIdx.x % NT, kb = blockIdx.x / NT;
   const int k = kb / prm.B, b = kb - k * prm.B;
   const int nfd = (prm.ldf + 63) / 64, ncd = prm.ldc / 32, nb = prm.ldc / 32;
@@ -180,14 +181,16 @@ __global__ void __launch_bounds__(UM_THREADS, 1) corr_umma_kernel(const __grid_c
     if (lane == 0) {
       prefetch_tmap(&prm.tm_fhi); prefetch_tmap(&prm.tm_flo); prefetch_tmap(&prm.tm_chi);
       prefetch_tmap(&prm.tm_clo); prefetch_tmap(&prm.tm_bhi); prefetch_tmap(&prm.tm_blo);
-      int cnt[UM_NSTAGE] = {0, 0, 0};     // fills of each stage so far (phase = count & 1)
+      // fills of a stage so far: t / 3 during the correlation phase (phase = count & 1); afterwards sC1 is filled once
+      // more and sC2 once per load of second-operand code rows
       bool ok = true;
       for (int t = 0; t < J0 + 1 + nC2 && ok; ++t) {
-        int s;
-        if (t < J0) s = t % UM_NSTAGE; else if (t == J0) s = sC1; else s = sC2;
-        ok = mbar_wait(&empty[s], (cnt[s] & 1) ^ 1);
+        int s, fills;
+        if (t < J0) { s = t % UM_NSTAGE; fills = t / UM_NSTAGE; }
+        else if (t == J0) { s = sC1; fills = (J0 + 2 - sC1) / UM_NSTAGE; }
+        else { s = sC2; fills = (J0 + 2 - sC2) / UM_NSTAGE + (t - J0 - 1); }
+        ok = mbar_wait(&empty[s], (fills & 1) ^ 1);
         if (!ok) break;
-        ++cnt[s];
         uint8_t* st = ring + s * UM_STAGE;
         if (prm.dbg & 1) { mbar_arrive(&full[s]); continue; }
         if (t < J0) {         // operand chunk of column tile tj: [first hi | first lo | second hi | second lo], 16 KB each
@@ -226,12 +229,10 @@ __global__ void __launch_bounds__(UM_THREADS, 1) corr_umma_kernel(const __grid_c
       const uint64_t dk128 = smem_desc(0, 16, 1024, SW_128B);       // K-major, 128-byte rows
       const uint64_t dmn128 = smem_desc(0, 16384, 1024, SW_128B);   // MN-major, 64-element atoms 16 KB apart
       const uint64_t dmn64 = smem_desc(0, 8192, 512, SW_64B);       // MN-major, 32-element atoms 8 KB apart
-      int cnt[UM_NSTAGE] = {0, 0, 0};
       bool ok = true;
       for (int t = 0; t < J0 && ok; ++t) {
         const int s = t % UM_NSTAGE;
-        ok = mbar_wait(&full[s], cnt[s] & 1);
-        ++cnt[s];
+        ok = mbar_wait(&full[s], (t / UM_NSTAGE) & 1);
         tc_fence_after_sync();
         if (prm.dbg & 2) { mbar_arrive(&empty[s]); continue; }
         const int tj = t / nop, c = t - tj * nop;
@@ -262,10 +263,10 @@ __global__ void __launch_bounds__(UM_THREADS, 1) corr_umma_kernel(const __grid_c
       // first-operand code rows (loaded once)
       uint32_t g1 = 0;
       if (ok) {
-        ok = mbar_wait(&full[sC1], cnt[sC1] & 1);
-        ++cnt[sC1];
+        ok = mbar_wait(&full[sC1], ((J0 + 2 - sC1) / UM_NSTAGE) & 1);
         g1 = smem_u32(ring + sC1 * UM_STAGE) >> 4;
       }
+      const int c2_base = (J0 + 2 - sC2) / UM_NSTAGE;   // fills of sC2 during the correlation phase
       const uint32_t g2 = smem_u32(ring + sC2 * UM_STAGE) >> 4;
       const uint32_t uh = smem_u32(u_hi) >> 4, ul = smem_u32(u_lo) >> 4;
       int step = 0;   // (round, column tile) counter: phase of u_ready / grad_full
@@ -273,8 +274,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) corr_umma_kernel(const __grid_c
       for (int rd = 0; rd < rounds && ok; ++rd) {
         for (int tj = 0; tj < NT && ok; ++tj, ++step) {
           if (c2_loaded < nC2 && (NT > 1 || step == 0)) {   // second-operand code rows of this column tile
-            ok = mbar_wait(&full[sC2], cnt[sC2] & 1);
-            ++cnt[sC2];
+            ok = mbar_wait(&full[sC2], (c2_base + c2_loaded) & 1);
             ++c2_loaded;
           }
           ok = ok && mbar_wait(u_ready, step & 1);
@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) corr_umma_kernel(const __grid_c
     const float dsh = prm.depth_shift;
     float sum_loss = 0.f, sum_cd = 0.f, sum_dloss = 0.f, sum_dd = 0.f;
     float v[32], c[32];
-    uint32_t passmask[2][2];                 // clamp indicator bits of this thread's row: [column tile][32-column chunk]
+    uint32_t passmask[NT][2];                 // clamp indicator bits of this thread's row: [column tile][32-column chunk]
 
     if (threadIdx.x == 64) stamp(prm, 1);
     bool ok = mbar_wait(acc_full, 0);
@@ -359,8 +359,8 @@ __global__ void __launch_bounds__(UM_THREADS, 1) corr_umma_kernel(const __grid_c
     int step = 0;
     for (int rd = 0; rd < rounds; ++rd) {
 #pragma unroll
-      for (int tj = 0; tj < 2; ++tj) {
-        if (tj < NT) {
+      for (int tj = 0; tj < NT; ++tj) {
+        {
           if (step > 0) asm volatile("bar.sync 1, 256;" ::: "memory");  // every warp is done with its scratch before U is rewritten
 #pragma unroll
           for (int h2 = 0; h2 < 2; ++h2) {
@@ -614,11 +614,13 @@ int corr_loss_umma(const dg_panels_t* pan, const float* fmean, int nsplit, const
   }
   static bool attr_set = false;
   if (!attr_set) {
-    DG_CUDA_OK(cudaFuncSetAttribute(corr_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, UM_SMEM));
+    DG_CUDA_OK(cudaFuncSetAttribute(corr_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, UM_SMEM));
+    DG_CUDA_OK(cudaFuncSetAttribute(corr_umma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, UM_SMEM));
     attr_set = true;
   }
   DG_PRE(st);
-  corr_umma_kernel<<<npairs * B * ntile, UM_THREADS, UM_SMEM, st>>>(prm);
+  if (ntile == 1) corr_umma_kernel<1><<<npairs * B, UM_THREADS, UM_SMEM, st>>>(prm);
+  else corr_umma_kernel<2><<<npairs * B * 2, UM_THREADS, UM_SMEM, st>>>(prm);
   DG_LAUNCH_OK("corr_umma_kernel");
   return DG_OK;  // out8 is written by the last CTA of corr_umma_kernel
 }

@@ -69,7 +69,7 @@ def make_panels(fmt, f_hi, f_lo, c_hi, c_lo, cb_hi, cb_lo):
     return Panels(fmt, dp(f_hi), dp(f_lo), dp(c_hi), dp(c_lo), dp(cb_hi), dp(cb_lo))
 
 
-FLAG_DEPTH_TERM, FLAG_FPS, FLAG_FORCE_SIMT = 8, 16, 32
+FLAG_DEPTH_TERM, FLAG_FPS, FLAG_FORCE_SIMT, FLAG_STAGE_NHWC = 8, 16, 32, 64
 _i64x4 = C.c_int64 * 4
 
 
@@ -82,7 +82,7 @@ class LossDesc(C.Structure):
 class LossPlan(C.Structure):
     """dg_loss_plan_t"""
     _fields_ = [(n, C.c_size_t) for n in ("total", "coords", "frn", "fmean", "crn", "f_hi", "f_lo", "c_hi", "c_lo",
-                                          "cb_hi", "cb_lo", "dsign", "dC1", "dC2", "ws", "ws_bytes")] + \
+                                          "cb_hi", "cb_lo", "dsign", "dC1", "dC2", "ws", "ws_bytes", "stage")] + \
                [(n, C.c_int) for n in ("kernel", "Prows", "ldf", "ldc", "npairs")]
 
 

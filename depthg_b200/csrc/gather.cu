@@ -375,6 +375,39 @@ __global__ void __launch_bounds__(GF_THREADS, 2) gather_all_kernel(const __grid_
                         2 * q + (r - 1));
 }
 
+// NCHW -> channels-last staging copy for the feature tensors: [B][C][HW] -> [B][HW][C] through a 32x33 smem tile
+// (both reads and writes coalesced).  NCHW sources would otherwise make every gathered value its own 32-byte sector.
+__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ a, const float* __restrict__ b2,
+                                                           int B, int C, int HW, int64_t sb_a, int64_t sb_b,
+                                                           float* __restrict__ out_a, float* __restrict__ out_b) {
+  __shared__ float tile[32][33];
+  const int img = blockIdx.z;
+  const float* src = img < B ? a + (int64_t)img * sb_a : b2 + (int64_t)(img - B) * sb_b;
+  float* dst = (img < B ? out_a + (size_t)img * C * HW : out_b + (size_t)(img - B) * C * HW);
+  const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int c = c0 + ty + 8 * r, p = p0 + tx;
+    tile[ty + 8 * r][tx] = (c < C && p < HW) ? __ldg(src + (size_t)c * HW + p) : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int p = p0 + ty + 8 * r, c = c0 + tx;
+    if (p < HW && c < C) dst[(size_t)p * C + c] = tile[tx][ty + 8 * r];
+  }
+}
+
+int launch_nchw_to_nhwc(const float* a, const float* b, int B, int C, int HW, int64_t sb_a, int64_t sb_b, float* out_a,
+                        float* out_b, cudaStream_t st) {
+  DG_PRE(st);
+  nchw_to_nhwc_kernel<<<dim3(ceil_div(HW, 32), ceil_div(C, 32), 2 * B), 256, 0, st>>>(a, b, B, C, HW, sb_a, sb_b, out_a,
+                                                                                       out_b);
+  DG_LAUNCH_OK("nchw_to_nhwc_kernel");
+  return DG_OK;
+}
+
 // One warp per panel row: compose the row's gradient from the unit gradients,
 // back through x/max(||x||,eps), then atomically scatter through the 4 corners.
 __global__ void __launch_bounds__(256)

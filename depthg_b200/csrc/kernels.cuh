@@ -56,6 +56,8 @@ int launch_depth_sign(const float* depth, int B, int Hd, int Wd, int S, float ep
 int gather_nsplit(int fmt, const SetTable& tab, int nsets, int C, int ld);
 int launch_gather(int fmt, const SetTable& tab, int nsets, int B, int C, int H, int W, const float* coords, int S,
                   const int64_t* perms, float eps, int Prows, int ld, int nsplit, const GatherOut& o, cudaStream_t st);
+int launch_nchw_to_nhwc(const float* a, const float* b, int B, int C, int HW, int64_t sb_a, int64_t sb_b, float* out_a,
+                        float* out_b, cudaStream_t st);
 int launch_gather_all(const SetTable& fsets, const SetTable& csets, int nsets, int B, int C, int D, int H, int W,
                       const float* coords, int S, const int64_t* perms, float eps, int Prows, int ldf, int ldc, int fsplit,
                       const GatherOut& fo, const GatherOut& co, cudaStream_t st);

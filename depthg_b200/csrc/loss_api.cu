@@ -62,6 +62,8 @@ static void make_plan(const dg_loss_desc_t* d, dg_loss_plan_t* p) {
     p->f_hi = take(np * B * Pr * p->ldf * 4);
     p->c_lo = p->cb_hi = p->cb_lo = p->f_lo = 0;
   }
+  p->stage = 0;
+  if (p->kernel && (d->flags & DG_FLAG_STAGE_NHWC)) p->stage = take((size_t)2 * B * d->C * d->H * d->W * 4);
   p->total = off;
 }
 
@@ -124,8 +126,21 @@ extern "C" int dg_loss_forward(const dg_loss_desc_t* d, const dg_loss_io_t* io, 
   if (io->perms_ready) DG_CUDA_OK(cudaStreamWaitEvent(st, reinterpret_cast<cudaEvent_t>(io->perms_ready), 0));
   SetTable ftab, ctab;
   GatherOut fo, co;
-  // backbone features
-  const int nsets = build_sets(ftab, io->feats, io->feats_strides, io->feats_pos, io->feats_pos_strides, d->neg_samples);
+  // backbone features (NCHW sources are first staged as channels-last copies so the gather reads whole lines)
+  const float* feats = io->feats;
+  const float* feats_pos = io->feats_pos;
+  int64_t fst[4], fpst[4];
+  for (int i = 0; i < 4; ++i) { fst[i] = io->feats_strides[i]; fpst[i] = io->feats_pos_strides[i]; }
+  const int64_t HW = (int64_t)d->H * d->W;
+  if (pl.stage && fst[3] == 1 && fst[2] == d->W && fst[1] == HW && fpst[3] == 1 && fpst[2] == d->W && fpst[1] == HW) {
+    float* sa = reinterpret_cast<float*>(A + pl.stage);
+    float* sb2 = sa + (size_t)B * d->C * HW;
+    rc = launch_nchw_to_nhwc(feats, feats_pos, B, d->C, (int)HW, fst[0], fpst[0], sa, sb2, st);
+    if (rc != DG_OK) return rc;
+    feats = sa; feats_pos = sb2;
+    fst[0] = fpst[0] = (int64_t)d->C * HW; fst[1] = fpst[1] = 1; fst[2] = fpst[2] = (int64_t)d->W * d->C; fst[3] = fpst[3] = d->C;
+  }
+  const int nsets = build_sets(ftab, feats, fst, feats_pos, fpst, d->neg_samples);
   fo.out = reinterpret_cast<float*>(A + pl.f_hi);
   fo.out_lo = nullptr;
   fo.hi16 = reinterpret_cast<__nv_bfloat16*>(A + pl.f_hi);

@@ -464,6 +464,8 @@ class ContrastiveCorrelationLoss(nn.Module):
                 flags |= _lib.FLAG_DEPTH_TERM
         if corr_kernel_choice(S * S, orig_code.shape[1]) == "simt":
             flags |= _lib.FLAG_FORCE_SIMT
+        elif Cdim % 128 == 0 and orig_feats.is_contiguous() and orig_feats_pos.is_contiguous():
+            flags |= _lib.FLAG_STAGE_NHWC   # NCHW inputs: let the library stage channels-last copies for the gather
         desc = _lib.LossDesc(B, Cdim, orig_code.shape[1], H, W, Hd, Wd, S, nneg, flags, float(cfg.pos_intra_shift),
                              float(cfg.pos_inter_shift), float(cfg.neg_inter_shift),
                              float(cfg.depth_feat_shift) if depth_term else 0.0)

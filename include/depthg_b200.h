@@ -205,7 +205,8 @@ DG_API int dg_corr_loss(const dg_panels_t* pan, const float* fmean, const float*
  * alive until dg_loss_backward has run. */
 enum { DG_FLAG_DEPTH_TERM = 8,  /* cfg.depth_feat_correlation_loss                          */
        DG_FLAG_FPS = 16,        /* cfg.depth_sampling == "fps": coordinates from depth maps */
-       DG_FLAG_FORCE_SIMT = 32  /* use the generic CUDA-core correlation kernel             */ };
+       DG_FLAG_FORCE_SIMT = 32, /* use the generic CUDA-core correlation kernel             */
+       DG_FLAG_STAGE_NHWC = 64  /* feats / feats_pos are NCHW-contiguous: stage a channels-last copy in the arena */ };
 
 typedef struct dg_loss_desc {
   int B, C, D, H, W, Hd, Wd, S, neg_samples;
@@ -214,7 +215,7 @@ typedef struct dg_loss_desc {
 } dg_loss_desc_t;
 
 typedef struct dg_loss_plan { /* byte offsets into the arena, all 256-byte aligned */
-  size_t total, coords, frn, fmean, crn, f_hi, f_lo, c_hi, c_lo, cb_hi, cb_lo, dsign, dC1, dC2, ws, ws_bytes;
+  size_t total, coords, frn, fmean, crn, f_hi, f_lo, c_hi, c_lo, cb_hi, cb_lo, dsign, dC1, dC2, ws, ws_bytes, stage;
   int kernel; /* 0 = generic CUDA-core kernel, 1 = tcgen05 kernel */
   int Prows, ldf, ldc, npairs;
 } dg_loss_plan_t;

@@ -9,7 +9,9 @@
 //                            sims = hi.hi + hi.lo + lo.hi on tcgen05 (error <~ 2e-5), two TMEM
 //                            accumulators so the MMAs of tile t+1 overlap the epilogue of tile t;
 //                            the epilogue (one thread per query row) keeps the 32 best candidates
-//                            of its row in a sorted shared-memory list (threshold in a register)
+//                            of its row in a sorted shared-memory list (threshold in a register); the
+//                            database is cut into nseg segments (grid.y) so that small query blocks
+//                            (multi-GPU shards) still fill the GPU and every row gets nseg x 32 candidates
 //   3. knn_rerank_kernel   : exact fp32 dot products of the 32 candidates (a warp per query row),
 //                            sort by (value desc, index asc), emit the top k, and CERTIFY the row:
 //                            exact k-th value > approximate 32nd value + error bound, i.e. no row
@@ -29,16 +31,16 @@ constexpr int KU_NSTAGE = 3;
 constexpr int KU_STAGE = 65536;
 constexpr int KU_CAND = 32;
 constexpr int KU_LSTR = KU_CAND + 1;
-constexpr int KU_SMEM = KU_NSTAGE * KU_STAGE + 2 * 128 * KU_LSTR * 4 + 1024 + 256;
+constexpr int KU_SMEM = KU_NSTAGE * KU_STAGE + 4 * 32 * KU_LSTR * 4 + 1024 + 256;
 // bound on |approx - exact| of the 3-product bf16 split for unit-norm rows: dropped lo.lo term <= 2^-18, rounding of the
 // two lo panels <= 2 * 2^-18, fp32 accumulation ~1e-6  (measured max 5e-6, SURVEY 7.1 iii)
 constexpr float KU_EPS = 1.5e-5f;
 
 struct KnnUmmaParams {
   CUtensorMap tm_qh, tm_ql, tm_dh, tm_dl;  // bf16 [rows, Fp], box 64 x 128, SWIZZLE_128B
-  int Nq, N, nchunk, ntiles;
-  int* cand_idx;    // [Nq,32]
-  float* cand_val;  // [Nq,32] approximate sims, descending
+  int Nq, N, nchunk, ntiles, nseg;
+  int* cand_idx;    // [Nq,nseg,32]
+  float* cand_val;  // [Nq,nseg,32] approximate sims, descending within a segment
   int* err;
 };
 
@@ -55,25 +57,11 @@ __global__ void __launch_bounds__(256) split_rows_kernel(const float* __restrict
   }
 }
 
-// Insert (x, id) into this thread's descending 32-entry list in shared memory; returns the new 32nd value.
-__device__ __noinline__ float list_insert(float* myv, int* myi, float x, int id) {
-  int j = KU_CAND - 1;
-  while (j > 0 && myv[j - 1] < x) {
-    myv[j] = myv[j - 1];
-    myi[j] = myi[j - 1];
-    --j;
-  }
-  myv[j] = x;
-  myi[j] = id;
-  return myv[KU_CAND - 1];
-}
-
 __global__ void __launch_bounds__(KU_THREADS, 1) knn_umma_kernel(const __grid_constant__ KnnUmmaParams prm) {
   extern __shared__ uint8_t ku_raw[];
   uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ku_raw) + 1023) & ~(uintptr_t)1023);
-  float* lv = reinterpret_cast<float*>(ring + KU_NSTAGE * KU_STAGE);  // [128][33] candidate values, descending
-  int* li = reinterpret_cast<int*>(lv + 128 * KU_LSTR);               // [128][33] candidate indices
-  uint64_t* bars = reinterpret_cast<uint64_t*>(li + 128 * KU_LSTR);
+  float* stage_tiles = reinterpret_cast<float*>(ring + KU_NSTAGE * KU_STAGE);  // [4 warps][32 rows][33] transpose staging
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_tiles + 4 * 32 * KU_LSTR);
   uint64_t* full = bars;               // [3]
   uint64_t* empty = bars + 3;          // [3]
   uint64_t* tfull = bars + 6;          // [2] accumulator ready
@@ -82,7 +70,12 @@ __global__ void __launch_bounds__(KU_THREADS, 1) knn_umma_kernel(const __grid_co
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * 128;
-  const int nchunk = prm.nchunk, ntiles = prm.ntiles;
+  // blockIdx.y = database segment: this CTA ranks its 128 query rows against tiles [t_begin, t_end) only, which
+  // gives small query blocks (multi-GPU shards) enough CTAs to fill the GPU and every row nseg x 32 candidates
+  const int seg = blockIdx.y;
+  const int per_seg = (prm.ntiles + prm.nseg - 1) / prm.nseg;
+  const int t_begin = seg * per_seg, t_end = min(t_begin + per_seg, prm.ntiles);
+  const int nchunk = prm.nchunk, ntiles = max(t_end - t_begin, 0);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < KU_NSTAGE; ++s) {
@@ -91,7 +84,7 @@ __global__ void __launch_bounds__(KU_THREADS, 1) knn_umma_kernel(const __grid_co
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], 128);
+      mbar_init(&tempty[a], 128);  // every epilogue thread arrives
     }
     fence_barrier_init();
   }
@@ -113,8 +106,8 @@ __global__ void __launch_bounds__(KU_THREADS, 1) knn_umma_kernel(const __grid_co
           mbar_arrive_expect_tx(&full[s], KU_STAGE);
           tma_load_2d(st, &prm.tm_qh, &full[s], c * 64, m0);
           tma_load_2d(st + 16384, &prm.tm_ql, &full[s], c * 64, m0);
-          tma_load_2d(st + 32768, &prm.tm_dh, &full[s], c * 64, t * 128);
-          tma_load_2d(st + 49152, &prm.tm_dl, &full[s], c * 64, t * 128);
+          tma_load_2d(st + 32768, &prm.tm_dh, &full[s], c * 64, (t_begin + t) * 128);
+          tma_load_2d(st + 49152, &prm.tm_dl, &full[s], c * 64, (t_begin + t) * 128);
         }
       }
     }
@@ -148,46 +141,71 @@ __global__ void __launch_bounds__(KU_THREADS, 1) knn_umma_kernel(const __grid_co
       if (!ok && prm.err) atomicCAS(prm.err, 0, 12);
     }
   } else {
+    // ---- epilogue: warp-cooperative running top-32 per row.  The warp owns the 32 rows of its TMEM lane group; each
+    //      row's sorted candidate list is spread over the 32 lanes (entry l in lane l), so an insertion is one
+    //      ballot + two shuffles and costs the same whether the list is cold or warm.
     const int lg = warp & 3;
-    const int row = 32 * lg + lane;
     const uint32_t tlane = tmem + ((uint32_t)(32 * lg) << 16);
-    float* myv = lv + row * KU_LSTR;
-    int* myi = li + row * KU_LSTR;
-    for (int j = 0; j < KU_CAND; ++j) {
-      myv[j] = -INFINITY;
-      myi[j] = -1;
+    float* tile = stage_tiles + lg * (32 * KU_LSTR);
+    float tv[32];
+    int ti[32];
+#pragma unroll
+    for (int r = 0; r < 32; ++r) {
+      tv[r] = -INFINITY;
+      ti[r] = -1;
     }
-    float thr = -INFINITY;
     float v[32];
     bool ok = true;
     for (int t = 0; t < ntiles && ok; ++t) {
       const int a = t & 1;
       ok = mbar_wait(&tfull[a], (t >> 1) & 1);
       tc_fence_after_sync();
-      const int n0 = t * 128;
+      const int n0 = (t_begin + t) * 128;
 #pragma unroll 1
       for (int cc = 0; cc < 4; ++cc) {
         tmem_ld_32x32(tlane + a * 128 + 32 * cc, v);
         tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) tile[lane * KU_LSTR + i] = v[i];   // thread = row `lane`, 32 columns
+        __syncwarp();
         const int nb = n0 + 32 * cc;
-        float mx = v[0];
+        const bool col_ok = nb + lane < prm.N;
 #pragma unroll
-        for (int i = 1; i < 32; ++i) mx = fmaxf(mx, v[i]);
-        if (mx > thr) {  // something in this chunk may enter the list (rare once the list has warmed up)
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (v[i] > thr && nb + i < prm.N) thr = list_insert(myv, myi, v[i], nb + i);
+        for (int r = 0; r < 32; ++r) {
+          const float x = tile[r * KU_LSTR + lane];                       // lane = column of row r
+          const float thr = __shfl_sync(0xffffffffu, tv[r], KU_CAND - 1);
+          unsigned m = __ballot_sync(0xffffffffu, col_ok && x > thr);
+          while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const float nv = __shfl_sync(0xffffffffu, x, src);
+            if (nv > __shfl_sync(0xffffffffu, tv[r], KU_CAND - 1)) {      // still above the (possibly raised) 32nd value
+              const int pos = __popc(__ballot_sync(0xffffffffu, tv[r] >= nv));
+              const float up_v = __shfl_up_sync(0xffffffffu, tv[r], 1);
+              const int up_i = __shfl_up_sync(0xffffffffu, ti[r], 1);
+              if (lane == pos) {
+                tv[r] = nv;
+                ti[r] = nb + src;
+              } else if (lane > pos) {
+                tv[r] = up_v;
+                ti[r] = up_i;
+              }
+            }
+          }
         }
+        __syncwarp();
       }
       tc_fence_before_sync();
       mbar_arrive(&tempty[a]);
     }
     if (!ok && prm.err) atomicCAS(prm.err, 0, 13);
-    const int q = m0 + row;
-    if (q < prm.Nq) {
-      for (int j = 0; j < KU_CAND; ++j) {
-        prm.cand_idx[(size_t)q * KU_CAND + j] = myi[j];
-        prm.cand_val[(size_t)q * KU_CAND + j] = myv[j];
+#pragma unroll
+    for (int r = 0; r < 32; ++r) {
+      const int q = m0 + 32 * lg + r;
+      if (q < prm.Nq) {
+        const size_t o = ((size_t)q * prm.nseg + seg) * KU_CAND;
+        prm.cand_idx[o + lane] = ti[r];
+        prm.cand_val[o + lane] = tv[r];
       }
     }
   }
@@ -196,42 +214,115 @@ __global__ void __launch_bounds__(KU_THREADS, 1) knn_umma_kernel(const __grid_co
   if (warp == 1) tmem_dealloc(tmem, 256);
 }
 
-// One warp per query row: exact fp32 similarities of the 32 candidates, rank, emit, certify.
+// One warp per query row: exact fp32 similarities of its nseg x 32 candidates (lane l owns candidate l of every
+// segment), k rounds of warp-argmax by (value desc, index asc) to emit the top k, and the certificate.
+constexpr int KU_MAXSEG = 8;
+
 __global__ void __launch_bounds__(256) knn_rerank_kernel(const float* __restrict__ q, const float* __restrict__ db,
-                                                         int Nq, int N, int F, int k, const int* __restrict__ cand_idx,
+                                                         int Nq, int N, int F, int k, int nseg,
+                                                         const int* __restrict__ cand_idx,
                                                          const float* __restrict__ cand_val, int64_t* __restrict__ idx,
                                                          float* __restrict__ sims, int* __restrict__ fail_rows,
                                                          int* __restrict__ fail_count, const int* __restrict__ err) {
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (row >= Nq) return;
-  const int my_idx = cand_idx[(size_t)row * KU_CAND + lane];
-  const float tau = cand_val[(size_t)row * KU_CAND + KU_CAND - 1];  // everything outside the list is <= tau (approx)
   const float* qr = q + (size_t)row * F;
-  float my_e = -INFINITY;
-  for (int c = 0; c < KU_CAND; ++c) {
-    const int ci = __shfl_sync(0xffffffffu, my_idx, c);
-    float s = 0.f;
-    if (ci >= 0) {
-      const float* dr = db + (size_t)ci * F;
-      for (int f = lane; f < F; f += 32) s = fmaf(__ldg(qr + f), __ldg(dr + f), s);
+  int my_idx[KU_MAXSEG];
+  float my_a[KU_MAXSEG], my_e[KU_MAXSEG];
+  float tau = -INFINITY;  // everything outside the candidate lists is <= tau (approximately)
+#pragma unroll
+  for (int sg = 0; sg < KU_MAXSEG; ++sg) {
+    my_idx[sg] = -1;
+    my_a[sg] = -INFINITY;
+    my_e[sg] = -INFINITY;
+    if (sg < nseg) {
+      const size_t o = ((size_t)row * nseg + sg) * KU_CAND;
+      my_idx[sg] = cand_idx[o + lane];
+      my_a[sg] = my_idx[sg] >= 0 ? cand_val[o + lane] : -INFINITY;
+      tau = fmaxf(tau, cand_val[o + KU_CAND - 1]);
     }
-    s = warp_sum(s);
-    if (lane == c) my_e = ci >= 0 ? s : -INFINITY;
   }
-  int rank = 0;
-  for (int c = 0; c < KU_CAND; ++c) {
-    const float e = __shfl_sync(0xffffffffu, my_e, c);
-    const int i2 = __shfl_sync(0xffffffffu, my_idx, c);
-    rank += (e > my_e || (e == my_e && i2 < my_idx)) ? 1 : 0;
+  // prune: the k-th largest APPROXIMATE value a_k bounds the exact top-k from below by a_k - eps, so candidates with
+  // approx < a_k - 2 eps cannot be in it and need no exact dot product (with nseg segments that is most of them)
+  float a_k = -INFINITY;
+  {
+    float cut = INFINITY;   // values >= cut have been counted already
+    int taken = 0;
+    for (int it = 0; it < k && taken < k; ++it) {
+      float best = -INFINITY;
+#pragma unroll
+      for (int sg = 0; sg < KU_MAXSEG; ++sg)
+        if (my_a[sg] < cut) best = fmaxf(best, my_a[sg]);
+      best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, 16));
+      best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, 8));
+      best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, 4));
+      best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, 2));
+      best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, 1));
+      int c = 0;
+#pragma unroll
+      for (int sg = 0; sg < KU_MAXSEG; ++sg) c += (my_a[sg] == best) ? 1 : 0;
+      taken += __reduce_add_sync(0xffffffffu, c);
+      cut = best;
+      a_k = best;
+      if (best == -INFINITY) break;
+    }
   }
-  if (rank < k && my_idx >= 0) {
-    idx[(size_t)row * k + rank] = (int64_t)my_idx;
-    if (sims) sims[(size_t)row * k + rank] = my_e;
+  const float keep = a_k - 2.f * KU_EPS;
+#pragma unroll
+  for (int sg = 0; sg < KU_MAXSEG; ++sg) {
+    if (sg < nseg) {
+      if (my_a[sg] < keep) my_idx[sg] = -1;   // cannot be in the exact top-k
+      unsigned live = __ballot_sync(0xffffffffu, my_idx[sg] >= 0);
+      while (live) {
+        const int c = __ffs(live) - 1;
+        live &= live - 1;
+        const int ci = __shfl_sync(0xffffffffu, my_idx[sg], c);
+        const float* dr = db + (size_t)ci * F;
+        float s = 0.f;
+        for (int f = lane; f < F; f += 32) s = fmaf(__ldg(qr + f), __ldg(dr + f), s);
+        s = warp_sum(s);
+        if (lane == c) my_e[sg] = s;
+      }
+    }
+  }
+  float ek = -INFINITY;
+  for (int out = 0; out < k; ++out) {
+    // this lane's best remaining candidate
+    float bv = -INFINITY;
+    int bi = 0x7fffffff, bs = 0;
+#pragma unroll
+    for (int sg = 0; sg < KU_MAXSEG; ++sg) {
+      const bool better = my_idx[sg] >= 0 && (my_e[sg] > bv || (my_e[sg] == bv && my_idx[sg] < bi));
+      bv = better ? my_e[sg] : bv;
+      bi = better ? my_idx[sg] : bi;
+      bs = better ? sg : bs;
+    }
+    float wv = bv;
+    int wi = bi, wl = lane;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, wv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, wi, o);
+      const int ol = __shfl_xor_sync(0xffffffffu, wl, o);
+      if (ov > wv || (ov == wv && oi < wi)) {
+        wv = ov;
+        wi = oi;
+        wl = ol;
+      }
+    }
+    if (lane == wl) {
+#pragma unroll
+      for (int sg = 0; sg < KU_MAXSEG; ++sg)
+        if (sg == bs) my_idx[sg] = -1;  // consumed
+    }
+    if (lane == 0 && wi != 0x7fffffff) {
+      idx[(size_t)row * k + out] = (int64_t)wi;
+      if (sims) sims[(size_t)row * k + out] = wv;
+    }
+    if (out == k - 1) ek = (wi != 0x7fffffff) ? wv : -INFINITY;
   }
   // certificate: the exact k-th best candidate must beat anything the approximate pass could have dropped
-  const unsigned kth = __ballot_sync(0xffffffffu, rank == k - 1);
-  const float ek = kth ? __shfl_sync(0xffffffffu, my_e, __ffs(kth) - 1) : -INFINITY;
-  const bool bad = !(ek > tau + KU_EPS) || (err && *err != 0) || !kth;
+  const bool bad = !(ek > tau + KU_EPS) || (err && *err != 0);
   if (lane == 0 && bad) fail_rows[atomicAdd(fail_count, 1)] = row;  // recomputed by the exact kernel
 }
 
@@ -262,10 +353,18 @@ static int make_map(CUtensorMap* m, const void* base, uint64_t cols, uint64_t ro
 
 static size_t al256(size_t x) { return (x + 255) / 256 * 256; }
 
+// database segments per query block: enough CTAs for ~3 waves, at least 8 tiles per segment, at most KU_MAXSEG
+static int knn_nseg(int Nq, int N) {
+  const int nblocks = ceil_div(Nq, 128), ntiles = ceil_div(N, 128);
+  int nseg = ceil_div(3 * 148, nblocks);
+  nseg = min(nseg, max(1, ntiles / 8));
+  return max(1, min(nseg, KU_MAXSEG));
+}
+
 size_t knn_umma_workspace_bytes(int Nq, int N, int F) {
   const size_t Fp = (size_t)round_up(F, 64);
-  return 256 + 2 * al256((size_t)N * Fp * 2) + 2 * al256((size_t)Nq * Fp * 2) + al256((size_t)Nq * KU_CAND * 4) * 2 +
-         al256((size_t)Nq * 4);
+  return 256 + 2 * al256((size_t)N * Fp * 2) + 2 * al256((size_t)Nq * Fp * 2) +
+         al256((size_t)Nq * KU_MAXSEG * KU_CAND * 4) * 2 + al256((size_t)Nq * 4);
 }
 
 // declared in knn.cu: exact fp32 kernel restricted to the query rows listed in row_list[0 .. *row_count)
@@ -285,8 +384,9 @@ int knn_topk_umma(const float* q, const float* db, int Nq, int N, int F, int k, 
   __nv_bfloat16* qh = same ? dh : reinterpret_cast<__nv_bfloat16*>(take((size_t)Nq * Fp * 2));
   __nv_bfloat16* ql = same ? dl : reinterpret_cast<__nv_bfloat16*>(take((size_t)Nq * Fp * 2));
   if (same) off += 2 * al256((size_t)Nq * Fp * 2);
-  int* cand_idx = reinterpret_cast<int*>(take((size_t)Nq * KU_CAND * 4));
-  float* cand_val = reinterpret_cast<float*>(take((size_t)Nq * KU_CAND * 4));
+  const int nseg = knn_nseg(Nq, N);
+  int* cand_idx = reinterpret_cast<int*>(take((size_t)Nq * KU_MAXSEG * KU_CAND * 4));
+  float* cand_val = reinterpret_cast<float*>(take((size_t)Nq * KU_MAXSEG * KU_CAND * 4));
   int* fail_rows = reinterpret_cast<int*>(take((size_t)Nq * 4));
   int* fail_count = err + 1;  // second int of the zeroed header
   DG_CUDA_OK(cudaMemsetAsync(err, 0, 256, st));
@@ -305,7 +405,7 @@ int knn_topk_umma(const float* q, const float* db, int Nq, int N, int F, int k, 
   if ((rc = make_map(&prm.tm_ql, ql, Fp, Nq))) return rc;
   if ((rc = make_map(&prm.tm_dh, dh, Fp, N))) return rc;
   if ((rc = make_map(&prm.tm_dl, dl, Fp, N))) return rc;
-  prm.Nq = Nq; prm.N = N; prm.nchunk = Fp / 64; prm.ntiles = ceil_div(N, 128);
+  prm.Nq = Nq; prm.N = N; prm.nchunk = Fp / 64; prm.ntiles = ceil_div(N, 128); prm.nseg = nseg;
   prm.cand_idx = cand_idx; prm.cand_val = cand_val; prm.err = err;
   static bool attr_set = false;
   if (!attr_set) {
@@ -313,10 +413,11 @@ int knn_topk_umma(const float* q, const float* db, int Nq, int N, int F, int k, 
     attr_set = true;
   }
   DG_PRE(st);
-  knn_umma_kernel<<<ceil_div(Nq, 128), KU_THREADS, KU_SMEM, st>>>(prm);
+  knn_umma_kernel<<<dim3(ceil_div(Nq, 128), nseg), KU_THREADS, KU_SMEM, st>>>(prm);
   DG_LAUNCH_OK("knn_umma_kernel");
   DG_PRE(st);
-  knn_rerank_kernel<<<ceil_div(Nq * 32, 256), 256, 0, st>>>(q, db, Nq, N, F, k, cand_idx, cand_val, idx, sims, fail_rows, fail_count, err);
+  knn_rerank_kernel<<<ceil_div(Nq * 32, 256), 256, 0, st>>>(q, db, Nq, N, F, k, nseg, cand_idx, cand_val, idx, sims, fail_rows,
+                                                             fail_count, err);
   DG_LAUNCH_OK("knn_rerank_kernel");
   return launch_knn_exact(q, db, Nq, N, F, k, idx, sims, fail_rows, fail_count, st);
 }

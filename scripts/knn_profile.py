@@ -12,3 +12,9 @@ knn_topk(x, x, 30)
 n = lib.dg_profile_collect(None, 0); buf = ctypes.create_string_buffer(n + 16); lib.dg_profile_collect(buf, n + 16)
 lib.dg_profile_enable(0)
 print(buf.value.decode())
+# a multi-GPU-sized shard: N/8 query rows against the full database
+import time
+q = x[: N // 8].contiguous()
+knn_topk(q, x, 30); torch.cuda.synchronize()
+t = time.time(); knn_topk(q, x, 30); torch.cuda.synchronize(); print("shard N/8 rows: %.2f ms" % ((time.time() - t) * 1e3))
+t = time.time(); knn_topk(x, x, 30); torch.cuda.synchronize(); print("full: %.2f ms" % ((time.time() - t) * 1e3))

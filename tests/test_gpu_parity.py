@@ -258,8 +258,9 @@ def _check_knn_rows(idx, queries, db, want_idx):
     assert np.all(np.abs(gv - wv)[mism] < 1e-6), f"{mism.sum()} slots differ beyond the tie rule"
 
 
+@pytest.mark.parametrize("k", [30, 7])
 @pytest.mark.parametrize("path", ["umma", "simt"])
-def test_knn_tensor_core_and_exact_kernels_agree(path, monkeypatch):
+def test_knn_tensor_core_and_exact_kernels_agree(path, k, monkeypatch):
     """Both KNN kernels against the oracle on a problem big enough for the tcgen05 path, incl. ragged sizes."""
     from depthg_b200.precompute_knns import knn_topk
     if path == "simt":
@@ -268,8 +269,8 @@ def test_knn_tensor_core_and_exact_kernels_agree(path, monkeypatch):
     cent = rs.standard_normal((40, 200)).astype(np.float32)
     x = cent[rs.randint(0, 40, 4100)] + 0.25 * rs.standard_normal((4100, 200)).astype(np.float32)
     x = torch.nn.functional.normalize(torch.from_numpy(x), dim=1)
-    idx, sims = knn_topk(x[:1500].to(dev()), x.to(dev()), 30, return_sims=True)
-    _, want = O.knn_rows(x[:1500], x, 30)
+    idx, sims = knn_topk(x[:1500].to(dev()), x.to(dev()), k, return_sims=True)
+    _, want = O.knn_rows(x[:1500], x, k)
     _check_knn_rows(idx.cpu().numpy(), x[:1500], x, want.numpy())
     assert (np.diff(sims.cpu().numpy(), axis=1) <= 0).all()
 

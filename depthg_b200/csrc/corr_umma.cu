@@ -390,22 +390,39 @@ __global__ void __launch_bounds__(UM_THREADS, 1) corr_umma_kernel(const __grid_c
                   }
                 }
               }
-              uint32_t bits = 0;
+              if (depth_round) {   // intra pair with the depth term: also the dd sums and the clamp-indicator bits
+                uint32_t bits = 0;
 #pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                const float cdv = c[i];
-                const float cl = fminf(fmaxf(cdv, lo), hi);
-                const float f = v[i] - c0;
-                const float dd = sp * s_sign[q0 + i];
-                sum_loss = fmaf(-cl, f, sum_loss);
-                sum_cd += cdv;
-                sum_dloss = fmaf(-cl, dd - dsh, sum_dloss);
-                sum_dd += dd;
-                const bool pass = (cdv >= lo) && (cdv <= hi) && (q0 + i < P);
-                bits |= pass ? (1u << i) : 0u;
-                v[i] = pass ? -f * inv : 0.f;
+                for (int i = 0; i < 32; ++i) {
+                  const float cdv = c[i];
+                  const float cl = fminf(fmaxf(cdv, lo), hi);
+                  const float f = v[i] - c0;
+                  const float dd = sp * s_sign[q0 + i];
+                  sum_loss = fmaf(-cl, f, sum_loss);
+                  sum_cd += cdv;
+                  sum_dloss = fmaf(-cl, dd - dsh, sum_dloss);
+                  sum_dd += dd;
+                  const bool pass = (cdv >= lo) && (cdv <= hi) && (q0 + i < P);
+                  bits |= pass ? (1u << i) : 0u;
+                  v[i] = pass ? -f * inv : 0.f;
+                }
+                passmask[tj][h2] = bits;
+              } else {             // lean path of the other 6 pairs
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                  const float cdv = c[i];
+                  const float cl = fminf(fmaxf(cdv, lo), hi);
+                  const float f = v[i] - c0;
+                  sum_loss = fmaf(-cl, f, sum_loss);
+                  sum_cd += cdv;
+                  v[i] = ((cdv >= lo) && (cdv <= hi)) ? -f * inv : 0.f;
+                }
+                if (q0 + 32 > P) {   // only the chunk that crosses P has padded columns to zero
+#pragma unroll
+                  for (int i = 0; i < 32; ++i)
+                    if (q0 + i >= P) v[i] = 0.f;
+                }
               }
-              passmask[tj][h2] = bits;
             } else {
               // ---- depth term: U_d = -(s_p s_q - depth_shift) 1[clamp passes] / (B P^2), indicator from the main pass
               const uint32_t bits = passmask[tj][h2];
@@ -452,14 +469,15 @@ __global__ void __launch_bounds__(UM_THREADS, 1) corr_umma_kernel(const __grid_c
         for (int w8 = 0; w8 < 8; ++w8) t += s_red[w8][lane];
         prm.partials[(size_t)blockIdx.x * 4 + lane] = t;
       }
-      // ---- fused finalize: the last CTA to get here folds all partial sums into the 8 output scalars
-      __threadfence();
+      // ---- fused finalize: the last CTA to get here folds all partial sums into the 8 output scalars.
+      //      __syncwarp orders the four partial stores before lane 0's acq_rel counter increment, which publishes them
+      //      at gpu scope without a full __threadfence (that would also invalidate L1)
       __syncwarp();
       int ticket = 0;
-      if (lane == 0) ticket = atomicAdd(prm.done, 1);
+      if (lane == 0)
+        asm volatile("atom.add.acq_rel.gpu.global.s32 %0, [%1], 1;" : "=r"(ticket) : "l"(prm.done) : "memory");
       ticket = __shfl_sync(0xffffffffu, ticket, 0);
       if (ticket == (int)gridDim.x - 1) {
-        __threadfence();
         float acc[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] = 0.f;

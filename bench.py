@@ -509,6 +509,26 @@ def main():
                                   f"torch-CPU fp32 + NumPy FPS as the reference runs it",
                         "ms_per_step": min(times) * 1e3}
 
+    # ---- the reference's own ops run eagerly on this GPU (oracle port with CUDA tensors; FPS stays NumPy-on-host with a
+    #      device->host sync per image, as the reference ships it): the GPU-vs-GPU comparison of SURVEY 8(d)
+    ref_gpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import depthg_oracle as O
+        gin = {k: v.detach() for k, v in sets[0].items()}
+        times = []
+        for _ in range(3):
+            code = gin["code"].clone().requires_grad_(True)
+            code_pos = gin["code_pos"].clone().requires_grad_(True)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            out = O.ContrastiveCorrelationLoss(cfg)(gin["feats"], gin["feats_pos"], None, None, code, code_pos,
+                                                    gin["depth"], gin["depth_pos"])
+            backprop(out)
+            torch.cuda.synchronize()
+            times.append(time.perf_counter() - t0)
+        ref_gpu = {"value": B / min(times), "unit": UNIT, "ms_per_step": min(times) * 1e3,
+                   "note": "reference algorithm as PyTorch eager ops on the same B200, FPS on the host in NumPy as shipped"}
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -520,7 +540,7 @@ def main():
                 "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches),
                 "launches_per_step": launches / args.steps, "roofline": roofline, "roofline_step": roofline_step,
                 "breakdown_us": {k: round(v, 2) for k, v in breakdown.items()}, "cpu_baseline": cpu_baseline,
-                "cuda_graph": graphed,
+                "cuda_graph": graphed, "reference_ops_on_gpu": ref_gpu,
                 "fused_negative_sampler": {"value": world * B * args.steps / (ms_fused / 1e3), "unit": UNIT,
                                            "ms_per_step": ms_fused / args.steps,
                                            "note": "negative_sampler='fused': one dg_super_perms launch instead of "

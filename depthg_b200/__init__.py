@@ -8,10 +8,10 @@ src/precompute_knns.py):
     from depthg_b200.precompute_knns import build_knn_index, knn_topk, pool_normalize
 """
 from . import _lib  # noqa: F401
-from .modules import (ContrastiveCorrelationLoss, farthest_point_sampling_depth, fps_index_sets, norm, sample,  # noqa: F401
+from .modules import (ContrastiveCorrelationLoss, DepthContrastiveCorrelationLoss, farthest_point_sampling_depth, fps_index_sets, norm, sample,  # noqa: F401
                       sample_norm, super_perm, tensor_correlation)
 from .precompute_knns import build_knn_index, knn_topk, pool_normalize, save_nns  # noqa: F401
 
-__all__ = ["ContrastiveCorrelationLoss", "farthest_point_sampling_depth", "fps_index_sets", "norm", "sample",
+__all__ = ["ContrastiveCorrelationLoss", "DepthContrastiveCorrelationLoss", "farthest_point_sampling_depth", "fps_index_sets", "norm", "sample",
            "sample_norm", "super_perm", "tensor_correlation", "build_knn_index", "knn_topk", "pool_normalize",
            "save_nns"]

@@ -69,7 +69,7 @@ def make_panels(fmt, f_hi, f_lo, c_hi, c_lo, cb_hi, cb_lo):
     return Panels(fmt, dp(f_hi), dp(f_lo), dp(c_hi), dp(c_lo), dp(cb_hi), dp(cb_lo))
 
 
-FLAG_DEPTH_TERM, FLAG_FPS, FLAG_FORCE_SIMT, FLAG_STAGE_NHWC = 8, 16, 32, 64
+FLAG_DEPTH_TERM, FLAG_FPS, FLAG_FORCE_SIMT, FLAG_STAGE_NHWC, FLAG_AUG_INTRA = 8, 16, 32, 64, 128
 _i64x4 = C.c_int64 * 4
 
 
@@ -91,7 +91,8 @@ class LossIO(C.Structure):
     _fields_ = [("feats", _vp), ("feats_pos", _vp), ("code", _vp), ("code_pos", _vp),
                 ("feats_strides", _i64x4), ("feats_pos_strides", _i64x4), ("code_strides", _i64x4),
                 ("code_pos_strides", _i64x4), ("depth", _vp), ("depth_pos", _vp), ("coords", _vp), ("perms", _vp),
-                ("arena", _vp), ("out8", _vp), ("cd_out", _vp), ("loss_out", _vp), ("dd_out", _vp), ("fd_dbg", _vp), ("perms_ready", _vp)]
+                ("arena", _vp), ("out8", _vp), ("cd_out", _vp), ("loss_out", _vp), ("dd_out", _vp), ("fd_dbg", _vp), ("aug_feats", _vp), ("aug_feats_strides", _i64x4),
+                ("perms_ready", _vp)]
 
 
 class LossGrads(C.Structure):

@@ -34,6 +34,7 @@ struct CorrParams {
   float depth_shift, inv_cnt;
   float shift[DG_MAX_PAIRS];
   int32_t group[DG_MAX_PAIRS];
+  int32_t fs1[DG_MAX_PAIRS], fs2[DG_MAX_PAIRS];  // feature panel slots of pair k's operands (default 0 and k)
   float* dC1;
   float* dC2;
   float* partials;  // [npairs*B*n_pt][4]
@@ -44,21 +45,26 @@ struct CorrParams {
 };
 
 // rowmean[k,b,p] = <F1n[b,p,:], mean_q F2n[k,b,q,:]>, bsum[k,b] = sum_{p<P} rowmean
+struct SlotMapS {
+  int32_t fs1[DG_MAX_PAIRS], fs2[DG_MAX_PAIRS];
+};
+
 __global__ void __launch_bounds__(256) pair_means_kernel(const float* __restrict__ fn, const float* __restrict__ fmean,
                                                          int nsplit, int B, int P, int Prows, int ldf,
-                                                         float* __restrict__ rowmean, float* __restrict__ bsum) {
+                                                         float* __restrict__ rowmean, float* __restrict__ bsum,
+                                                         const __grid_constant__ SlotMapS sm) {
   extern __shared__ float mv[];  // [ldf]
   __shared__ float wsum[8];
   const int k = blockIdx.x / B, b = blockIdx.x - k * B;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const float* m = fmean + ((size_t)k * B + b) * nsplit * ldf;  // nsplit partial means
+  const float* m = fmean + ((size_t)sm.fs2[k] * B + b) * nsplit * ldf;  // nsplit partial means of the second operand
   for (int c = threadIdx.x; c < ldf; c += blockDim.x) {
     float a = 0.f;
     for (int i = 0; i < nsplit; ++i) a += m[(size_t)i * ldf + c];
     mv[c] = a;
   }
   __syncthreads();
-  const float* F1 = fn + (size_t)b * Prows * ldf;
+  const float* F1 = fn + ((size_t)sm.fs1[k] * B + b) * Prows * ldf;
   float* rm = rowmean + ((size_t)k * B + b) * Prows;
   float acc = 0.f;
   for (int p = warp; p < Prows; p += 8) {
@@ -155,8 +161,8 @@ __global__ void __launch_bounds__(CORR_THREADS) corr_tile_kernel(const __grid_co
   const int p0 = pt * TM;
   const int n_qt = Prows / TN;
 
-  const float* F1 = prm.fn + ((size_t)b * Prows + p0) * ldf;
-  const float* F2base = prm.fn + ((size_t)k * prm.B + b) * Prows * ldf;
+  const float* F1 = prm.fn + (((size_t)prm.fs1[k] * prm.B + b) * Prows + p0) * ldf;
+  const float* F2base = prm.fn + ((size_t)prm.fs2[k] * prm.B + b) * Prows * ldf;
   const float* C1 = prm.cn + ((size_t)b * Prows + p0) * ldc;
   const float* C2base = prm.cn + ((size_t)k * prm.B + b) * Prows * ldc;
   const bool pointwise = prm.flags & DG_FLAG_POINTWISE;
@@ -402,7 +408,7 @@ size_t corr_workspace_bytes(int npairs, int B, int P) {
 int corr_loss_simt(const float* fn, const float* cn, const float* fmean, int nsplit, const float* dsign, int npairs, int B, int P,
                    int Prows, int ldf, int ldc, const float* pair_shift, const int32_t* pair_group, float depth_shift,
                    int flags, float* out8, float* dC1, float* dC2, float* cd_out, float* loss_out, float* dd_out,
-                   void* ws, cudaStream_t st) {
+                   void* ws, cudaStream_t st, const int32_t* fslot1, const int32_t* fslot2) {
   const int n_pt = Prows / TM;
   CorrParams prm;
   prm.fn = fn;
@@ -421,12 +427,17 @@ int corr_loss_simt(const float* fn, const float* cn, const float* fmean, int nsp
   for (int k = 0; k < npairs; ++k) {
     prm.shift[k] = pair_shift[k];
     prm.group[k] = pair_group[k];
+    prm.fs1[k] = fslot1 ? fslot1[k] : 0;
+    prm.fs2[k] = fslot2 ? fslot2[k] : k;
   }
   prm.dC1 = dC1; prm.dC2 = dC2; prm.cd_out = cd_out; prm.loss_out = loss_out; prm.dd_out = dd_out; prm.out8 = out8;
 
   if (flags & DG_FLAG_POINTWISE) {
     DG_PRE(st);
-    pair_means_kernel<<<npairs * B, 256, (size_t)ldf * sizeof(float), st>>>(fn, fmean, nsplit, B, P, Prows, ldf, rowmean, bsum);
+    SlotMapS sm;
+    for (int k = 0; k < npairs; ++k) { sm.fs1[k] = prm.fs1[k]; sm.fs2[k] = prm.fs2[k]; }
+    pair_means_kernel<<<npairs * B, 256, (size_t)ldf * sizeof(float), st>>>(fn, fmean, nsplit, B, P, Prows, ldf, rowmean, bsum,
+                                                                            sm);
     DG_LAUNCH_OK("pair_means_kernel");
   }
   const size_t slab = (size_t)B * Prows * ldc * sizeof(float);
@@ -474,11 +485,11 @@ extern "C" int dg_corr_loss(const dg_panels_t* pan, const float* fmean, const fl
     DG_REQUIRE(pan->f_lo && pan->c_lo && pan->cb_hi && pan->cb_lo, DG_ERR_INVALID,
                "dg_corr_loss: split panel format needs f_lo, c_lo, cb_hi, cb_lo");
     return corr_loss_umma(pan, fmean, 1, dsign, npairs, B, P, Prows, ldf, ldc, pair_shift, pair_group, depth_shift, flags, out8,
-                          dC1, dC2, cd_out, loss_out, dd_out, fd_dbg, ws, st);
+                          dC1, dC2, cd_out, loss_out, dd_out, fd_dbg, ws, st, nullptr, nullptr, 0);
   }
   DG_REQUIRE(pan->format == DG_PANEL_F32, DG_ERR_INVALID, "dg_corr_loss: unknown panel format %d", pan->format);
   DG_REQUIRE(Prows == round_up(P, 64), DG_ERR_INVALID, "dg_corr_loss: Prows must be dg_panel_rows(P)");
   return corr_loss_simt(static_cast<const float*>(pan->f_hi), static_cast<const float*>(pan->c_hi), fmean, 1, dsign, npairs,
                         B, P, Prows, ldf, ldc, pair_shift, pair_group, depth_shift, flags, out8, dC1, dC2, cd_out,
-                        loss_out, dd_out, ws, st);
+                        loss_out, dd_out, ws, st, nullptr, nullptr);
 }

@@ -48,6 +48,7 @@ struct UmmaParams {
   float depth_shift, inv_cnt;
   float shift[DG_MAX_PAIRS];
   int32_t group[DG_MAX_PAIRS];
+  int32_t fs1[DG_MAX_PAIRS], fs2[DG_MAX_PAIRS];  // FEATURE panel slots of pair k's operands (default 0 and k)
   float* out8;      // the 8 scalars of the output tuple, written by the last CTA to finish
   int* done;        // CTA completion counter (zeroed by pair_dots_kernel)
   float* dC1;       // [npairs+1,B,Prows,ldc]
@@ -146,8 +147,11 @@ __global__ void __launch_bounds__(UM_THREADS, 1) corr_umma_kernel(const __grid_c
   const int nfd = (prm.ldf + 63) / 64, ncd = prm.ldc / 32, nb = prm.ldc / 32;
   const int nop = nfd + ncd;                                  // operand chunks per column tile
   const int J0 = NT * nop;                                    // jobs of the correlation phase
-  const int row1 = b * Prows + 128 * ti;                      // first operand: slot 0, row tile ti
-  const int row2 = (k * prm.B + b) * Prows;                   // second operand: slot k (+ 128 tj)
+  const int row1 = b * Prows + 128 * ti;                      // first code operand: slot 0, row tile ti
+  const int row2 = (k * prm.B + b) * Prows;                   // second code operand: slot k (+ 128 tj)
+  const int frow1 = (prm.fs1[k] * prm.B + b) * Prows + 128 * ti;   // feature operands may live in other slots
+  const int frow2 = (prm.fs2[k] * prm.B + b) * Prows;              // (DepthContrastiveCorrelationLoss: intra pair)
+  const bool fsame_slot = prm.fs1[k] == prm.fs2[k];
   const bool depth_round = prm.has_depth && k == 0;
   const int rounds = depth_round ? 2 : 1;
   // ring stages after the correlation phase: first-operand code rows, second-operand code rows, U
@@ -195,17 +199,19 @@ __global__ void __launch_bounds__(UM_THREADS, 1) corr_umma_kernel(const __grid_c
         if (prm.dbg & 1) { mbar_arrive(&full[s]); continue; }
         if (t < J0) {         // operand chunk of column tile tj: [first hi | first lo | second hi | second lo], 16 KB each
           const int tj = t / nop, c = t - tj * nop;
-          const bool same = (k == 0 && tj == ti);   // intra pair, diagonal tile: both operands are the same rows
           const bool isf = c < nfd;
+          // diagonal tile of a pair whose operands are the same panel: both operands are the same rows, load once
+          const bool same = (tj == ti) && (isf ? fsame_slot : k == 0);
           const int c0 = isf ? c * 64 : (c - nfd) * 32;
           const CUtensorMap* mh = isf ? &prm.tm_fhi : &prm.tm_chi;
           const CUtensorMap* ml = isf ? &prm.tm_flo : &prm.tm_clo;
           mbar_arrive_expect_tx(&full[s], same ? 32768u : 65536u);
-          tma_load_2d(st, mh, &full[s], c0, row1);
-          tma_load_2d(st + 16384, ml, &full[s], c0, row1);
+          const int ra = isf ? frow1 : row1, rb = (isf ? frow2 : row2) + 128 * tj;
+          tma_load_2d(st, mh, &full[s], c0, ra);
+          tma_load_2d(st + 16384, ml, &full[s], c0, ra);
           if (!same) {
-            tma_load_2d(st + 32768, mh, &full[s], c0, row2 + 128 * tj);
-            tma_load_2d(st + 49152, ml, &full[s], c0, row2 + 128 * tj);
+            tma_load_2d(st + 32768, mh, &full[s], c0, rb);
+            tma_load_2d(st + 49152, ml, &full[s], c0, rb);
           }
         } else {              // gradient operands: bf16 code rows [128 x ldc] as ldc/32 boxes of [128 x 64 B]; hi @0, lo @32 KB
           const int r = (t == J0) ? row1 : row2 + 128 * ((t - J0 - 1) % NT);
@@ -236,7 +242,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) corr_umma_kernel(const __grid_c
         tc_fence_after_sync();
         if (prm.dbg & 2) { mbar_arrive(&empty[s]); continue; }
         const int tj = t / nop, c = t - tj * nop;
-        const bool same = (k == 0 && tj == ti);
+        const bool same = (tj == ti) && (c < nfd ? fsame_slot : k == 0);
         const uint32_t a0 = smem_u32(ring + s * UM_STAGE) >> 4;
         const uint32_t b0 = same ? a0 : a0 + (32768 >> 4);
         const uint64_t ah = dk128 + a0, al = ah + (16384 >> 4), bh = dk128 + b0, bl = bh + (16384 >> 4);
@@ -523,14 +529,19 @@ __global__ void __launch_bounds__(UM_THREADS, 1) corr_umma_kernel(const __grid_c
 
 // dots[k,b] = < mean_p F1n[b,p,:], mean_q F2n[k,b,q,:] >  (one 256-thread block each, all loads in flight at once);
 // block 0 also clears the error flag
+struct SlotMap {
+  int32_t fs1[DG_MAX_PAIRS], fs2[DG_MAX_PAIRS];
+};
+
 __global__ void __launch_bounds__(256) pair_dots_kernel(const float* __restrict__ fmean, int nsplit, int npairs, int B,
-                                                        int ldf, float* __restrict__ dots, int* __restrict__ err) {
+                                                        int ldf, float* __restrict__ dots, int* __restrict__ err,
+                                                        const __grid_constant__ SlotMap sm) {
   __shared__ float red[8];
   if (blockIdx.x == 0 && threadIdx.x < 4 && err) err[threadIdx.x] = 0;  // error flag + completion counter
   if (fmean == nullptr) return;
   const int w = blockIdx.x, k = w / B, b = w - k * B;
-  const float* m1 = fmean + (size_t)b * nsplit * ldf;                      // nsplit partial means each
-  const float* m2 = fmean + ((size_t)k * B + b) * nsplit * ldf;
+  const float* m1 = fmean + ((size_t)sm.fs1[k] * B + b) * nsplit * ldf;   // nsplit partial means each
+  const float* m2 = fmean + ((size_t)sm.fs2[k] * B + b) * nsplit * ldf;
   float s = 0.f;
   for (int c = threadIdx.x; c < ldf; c += 256) {
     float a = 0.f, bb = 0.f;
@@ -588,13 +599,14 @@ static int make_map_2d(CUtensorMap* m, CUtensorMapDataType dt, int elt_bytes, co
 int corr_loss_umma(const dg_panels_t* pan, const float* fmean, int nsplit, const float* dsign, int npairs, int B, int P, int Prows, int ldf,
                    int ldc, const float* pair_shift, const int32_t* pair_group, float depth_shift, int flags,
                    float* out8, float* dC1, float* dC2, float* cd_out, float* loss_out, float* dd_out, float* fd_dbg,
-                   void* ws, cudaStream_t st) {
+                   void* ws, cudaStream_t st, const int32_t* fslot1, const int32_t* fslot2, int nfslots) {
   UmmaParams prm;
   const int ntile = Prows / 128;
   const uint64_t rows = (uint64_t)npairs * B * Prows;
+  const uint64_t frows = (uint64_t)(nfslots > 0 ? nfslots : npairs) * B * Prows;
   int rc;
-  if ((rc = make_map_2d(&prm.tm_fhi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, pan->f_hi, ldf, rows, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
-  if ((rc = make_map_2d(&prm.tm_flo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, pan->f_lo, ldf, rows, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if ((rc = make_map_2d(&prm.tm_fhi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, pan->f_hi, ldf, frows, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if ((rc = make_map_2d(&prm.tm_flo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, pan->f_lo, ldf, frows, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   if ((rc = make_map_2d(&prm.tm_chi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, pan->c_hi, ldc, rows, 32, 128, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   if ((rc = make_map_2d(&prm.tm_clo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, pan->c_lo, ldc, rows, 32, 128, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   if ((rc = make_map_2d(&prm.tm_bhi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, pan->cb_hi, ldc, rows, 32, 128, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
@@ -614,6 +626,8 @@ int corr_loss_umma(const dg_panels_t* pan, const float* fmean, int nsplit, const
   for (int k = 0; k < npairs; ++k) {
     prm.shift[k] = pair_shift[k];
     prm.group[k] = pair_group[k];
+    prm.fs1[k] = fslot1 ? fslot1[k] : 0;
+    prm.fs2[k] = fslot2 ? fslot2[k] : k;
   }
   prm.out8 = out8;
   prm.done = err + 1;
@@ -627,7 +641,9 @@ int corr_loss_umma(const dg_panels_t* pan, const float* fmean, int nsplit, const
   {
     const float* fm = (flags & DG_FLAG_POINTWISE) ? fmean : nullptr;
     DG_PRE(st);
-    pair_dots_kernel<<<npairs * B, 256, 0, st>>>(fm, nsplit, npairs, B, ldf, dots, err);
+    SlotMap sm;
+    for (int k = 0; k < npairs; ++k) { sm.fs1[k] = prm.fs1[k]; sm.fs2[k] = prm.fs2[k]; }
+    pair_dots_kernel<<<npairs * B, 256, 0, st>>>(fm, nsplit, npairs, B, ldf, dots, err, sm);
     DG_LAUNCH_OK("pair_dots_kernel");
   }
   static bool attr_set = false;

@@ -402,8 +402,8 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restri
 int launch_nchw_to_nhwc(const float* a, const float* b, int B, int C, int HW, int64_t sb_a, int64_t sb_b, float* out_a,
                         float* out_b, cudaStream_t st) {
   DG_PRE(st);
-  nchw_to_nhwc_kernel<<<dim3(ceil_div(HW, 32), ceil_div(C, 32), 2 * B), 256, 0, st>>>(a, b, B, C, HW, sb_a, sb_b, out_a,
-                                                                                       out_b);
+  nchw_to_nhwc_kernel<<<dim3(ceil_div(HW, 32), ceil_div(C, 32), b ? 2 * B : B), 256, 0, st>>>(a, b, B, C, HW, sb_a, sb_b,
+                                                                                               out_a, out_b);
   DG_LAUNCH_OK("nchw_to_nhwc_kernel");
   return DG_OK;
 }

@@ -70,11 +70,12 @@ int launch_corr_finalize(const float* partials, int npairs, int B, int P, const 
 int corr_loss_simt(const float* fn, const float* cn, const float* fmean, int nsplit, const float* dsign, int npairs, int B, int P,
                    int Prows, int ldf, int ldc, const float* pair_shift, const int32_t* pair_group, float depth_shift,
                    int flags, float* out8, float* dC1, float* dC2, float* cd_out, float* loss_out, float* dd_out,
-                   void* ws, cudaStream_t st);
+                   void* ws, cudaStream_t st, const int32_t* fslot1 = nullptr, const int32_t* fslot2 = nullptr);
 int corr_loss_umma(const dg_panels_t* pan, const float* fmean, int nsplit, const float* dsign, int npairs, int B, int P, int Prows, int ldf,
                    int ldc, const float* pair_shift, const int32_t* pair_group, float depth_shift, int flags,
                    float* out8, float* dC1, float* dC2, float* cd_out, float* loss_out, float* dd_out, float* fd_dbg,
-                   void* ws, cudaStream_t st);
+                   void* ws, cudaStream_t st, const int32_t* fslot1 = nullptr, const int32_t* fslot2 = nullptr,
+                   int nfslots = 0);
 size_t corr_workspace_bytes(int npairs, int B, int P);
 
 }  // namespace dg

@@ -39,11 +39,12 @@ static void make_plan(const dg_loss_desc_t* d, dg_loss_plan_t* p) {
   p->Prows = p->kernel ? round_up(P, 128) : round_up(P, 64);
   const size_t ni = p->kernel ? p->Prows / 128 : 1;  // dC2 partial buffers (one per 128-row tile of the first operand)
   const size_t np = p->npairs, B = d->B, Pr = p->Prows;
+  const size_t nf = np + ((d->flags & DG_FLAG_AUG_INTRA) ? 1 : 0);   // feature panel slots (+1: depth-augmented features)
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += al256(bytes); return o; };
   p->coords = take((size_t)2 * B * P * 2 * 4);
-  p->frn = take(np * B * Pr * 4);
-  p->fmean = take(np * B * 8 * p->ldf * 4);  // up to 8 partial means per (slot, image)
+  p->frn = take(nf * B * Pr * 4);
+  p->fmean = take(nf * B * 8 * p->ldf * 4);  // up to 8 partial means per (slot, image)
   p->crn = take(np * B * Pr * 4);
   p->dsign = take(B * Pr * 4);
   p->ws_bytes = corr_workspace_bytes(p->npairs, d->B, P);
@@ -55,15 +56,16 @@ static void make_plan(const dg_loss_desc_t* d, dg_loss_plan_t* p) {
     p->c_lo = take(np * B * Pr * p->ldc * 4);
     p->cb_hi = take(np * B * Pr * p->ldc * 2);
     p->cb_lo = take(np * B * Pr * p->ldc * 2);
-    p->f_hi = take(np * B * Pr * p->ldf * 2);
-    p->f_lo = take(np * B * Pr * p->ldf * 2);
+    p->f_hi = take(nf * B * Pr * p->ldf * 2);
+    p->f_lo = take(nf * B * Pr * p->ldf * 2);
   } else {
     p->c_hi = take(np * B * Pr * p->ldc * 4);
-    p->f_hi = take(np * B * Pr * p->ldf * 4);
+    p->f_hi = take(nf * B * Pr * p->ldf * 4);
     p->c_lo = p->cb_hi = p->cb_lo = p->f_lo = 0;
   }
   p->stage = 0;
-  if (p->kernel && (d->flags & DG_FLAG_STAGE_NHWC)) p->stage = take((size_t)2 * B * d->C * d->H * d->W * 4);
+  if (p->kernel && (d->flags & DG_FLAG_STAGE_NHWC))
+    p->stage = take((size_t)((d->flags & DG_FLAG_AUG_INTRA) ? 3 : 2) * B * d->C * d->H * d->W * 4);
   p->total = off;
 }
 
@@ -104,6 +106,9 @@ extern "C" int dg_loss_forward(const dg_loss_desc_t* d, const dg_loss_io_t* io, 
   DG_REQUIRE(!fps || (io->depth && io->depth_pos), DG_ERR_INVALID, "dg_loss_forward: fps sampling needs depth and depth_pos");
   DG_REQUIRE(!depth_term || io->depth, DG_ERR_INVALID, "dg_loss_forward: the depth term needs depth");
   DG_REQUIRE(fps || io->coords, DG_ERR_INVALID, "dg_loss_forward: coords missing");
+  const bool aug = d->flags & DG_FLAG_AUG_INTRA;
+  DG_REQUIRE(!aug || io->aug_feats, DG_ERR_INVALID, "dg_loss_forward: DG_FLAG_AUG_INTRA needs aug_feats");
+  DG_REQUIRE(!aug || !depth_term, DG_ERR_INVALID, "dg_loss_forward: the depth-augmented variant has no depth term");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   dg_loss_plan_t pl;
   make_plan(d, &pl);
@@ -140,7 +145,25 @@ extern "C" int dg_loss_forward(const dg_loss_desc_t* d, const dg_loss_io_t* io, 
     feats = sa; feats_pos = sb2;
     fst[0] = fpst[0] = (int64_t)d->C * HW; fst[1] = fpst[1] = 1; fst[2] = fpst[2] = (int64_t)d->W * d->C; fst[3] = fpst[3] = d->C;
   }
-  const int nsets = build_sets(ftab, feats, fst, feats_pos, fpst, d->neg_samples);
+  int nsets = build_sets(ftab, feats, fst, feats_pos, fpst, d->neg_samples);
+  const int ncsets = nsets;
+  int32_t fs1[DG_MAX_PAIRS], fs2[DG_MAX_PAIRS];
+  for (int k = 0; k < np; ++k) { fs1[k] = 0; fs2[k] = k; }
+  if (aug) {   // one more feature panel slot: the depth-augmented features at coords1; the intra pair correlates it with itself
+    const float* af = io->aug_feats;
+    int64_t ast[4];
+    for (int i = 0; i < 4; ++i) ast[i] = io->aug_feats_strides[i];
+    if (pl.stage && feats != io->feats && ast[3] == 1 && ast[2] == d->W && ast[1] == HW) {
+      float* sc3 = reinterpret_cast<float*>(A + pl.stage) + (size_t)2 * B * d->C * HW;
+      rc = launch_nchw_to_nhwc(af, nullptr, B, d->C, (int)HW, ast[0], 0, sc3, nullptr, st);
+      if (rc != DG_OK) return rc;
+      af = sc3;
+      ast[0] = (int64_t)d->C * HW; ast[1] = 1; ast[2] = (int64_t)d->W * d->C; ast[3] = d->C;
+    }
+    set_desc(ftab.s[nsets], af, ast, 0, np, -1);
+    ++nsets;
+    fs1[0] = fs2[0] = np;
+  }
   fo.out = reinterpret_cast<float*>(A + pl.f_hi);
   fo.out_lo = nullptr;
   fo.hi16 = reinterpret_cast<__nv_bfloat16*>(A + pl.f_hi);
@@ -150,7 +173,7 @@ extern "C" int dg_loss_forward(const dg_loss_desc_t* d, const dg_loss_io_t* io, 
   const int ffmt = pl.kernel ? FMT_FEATS_SPLIT : FMT_F32;
   const int nsplit = gather_nsplit(ffmt, ftab, nsets, d->C, pl.ldf);
   // code
-  build_sets(ctab, io->code, io->code_strides, io->code_pos, io->code_pos_strides, d->neg_samples);
+  build_sets(ctab, io->code, io->code_strides, io->code_pos, io->code_pos_strides, d->neg_samples);  // ncsets sets
   co.out = reinterpret_cast<float*>(A + pl.c_hi);
   co.out_lo = pl.kernel ? reinterpret_cast<float*>(A + pl.c_lo) : nullptr;
   co.hi16 = pl.kernel ? reinterpret_cast<__nv_bfloat16*>(A + pl.cb_hi) : nullptr;
@@ -160,14 +183,14 @@ extern "C" int dg_loss_forward(const dg_loss_desc_t* d, const dg_loss_io_t* io, 
   // (a single merged launch — launch_gather_all — was measured slower: the code CTAs inherit the feature
   //  kernel's register footprint and lose the occupancy that hides their latency; kept for experiments)
   rc = DG_ERR_UNSUPPORTED;
-  if (pl.kernel && getenv("DEPTHG_B200_GATHER_ALL"))
+  if (pl.kernel && !aug && getenv("DEPTHG_B200_GATHER_ALL"))
     rc = launch_gather_all(ftab, ctab, nsets, B, d->C, d->D, d->H, d->W, coords, S, io->perms, kNormEps, pl.Prows, pl.ldf,
                            pl.ldc, nsplit, fo, co, st);
   if (rc == DG_ERR_UNSUPPORTED) {
     rc = launch_gather(ffmt, ftab, nsets, B, d->C, d->H, d->W, coords, S, io->perms, kNormEps, pl.Prows, pl.ldf, nsplit, fo,
                        st);
     if (rc != DG_OK) return rc;
-    rc = launch_gather(pl.kernel ? FMT_CODE_SPLIT : FMT_F32, ctab, nsets, B, d->D, d->H, d->W, coords, S, io->perms,
+    rc = launch_gather(pl.kernel ? FMT_CODE_SPLIT : FMT_F32, ctab, ncsets, B, d->D, d->H, d->W, coords, S, io->perms,
                        kNormEps, pl.Prows, pl.ldc, 1, co, st);
   }
   if (rc != DG_OK) return rc;
@@ -186,11 +209,12 @@ extern "C" int dg_loss_forward(const dg_loss_desc_t* d, const dg_loss_io_t* io, 
     pan.f_hi = A + pl.f_hi; pan.f_lo = A + pl.f_lo; pan.c_hi = A + pl.c_hi; pan.c_lo = A + pl.c_lo;
     pan.cb_hi = A + pl.cb_hi; pan.cb_lo = A + pl.cb_lo;
     return corr_loss_umma(&pan, fmean, nsplit, dsign, np, B, P, pl.Prows, pl.ldf, pl.ldc, shifts, groups, d->depth_feat_shift, kflags,
-                          io->out8, dC1, dC2, io->cd_out, io->loss_out, io->dd_out, io->fd_dbg, A + pl.ws, st);
+                          io->out8, dC1, dC2, io->cd_out, io->loss_out, io->dd_out, io->fd_dbg, A + pl.ws, st, fs1, fs2,
+                          aug ? np + 1 : np);
   }
   return corr_loss_simt(reinterpret_cast<const float*>(A + pl.f_hi), reinterpret_cast<const float*>(A + pl.c_hi), fmean,
                         nsplit, dsign, np, B, P, pl.Prows, pl.ldf, pl.ldc, shifts, groups, d->depth_feat_shift, kflags, io->out8,
-                        dC1, dC2, io->cd_out, io->loss_out, io->dd_out, A + pl.ws, st);
+                        dC1, dC2, io->cd_out, io->loss_out, io->dd_out, A + pl.ws, st, fs1, fs2);
 }
 
 extern "C" int dg_loss_backward(const dg_loss_desc_t* d, const dg_loss_io_t* io, const dg_loss_grads_t* gr,

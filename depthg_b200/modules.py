@@ -276,7 +276,7 @@ class _CorrLossFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, feats, feats_pos, code, code_pos, depth, depth_pos, coords, perms, desc, materialize,
-                perms_event=None):
+                perms_event=None, aug_feats=None):
         lib = _lib.lib()
         dev = feats.device
         plan = _lib.LossPlan()
@@ -307,6 +307,9 @@ class _CorrLossFn(torch.autograd.Function):
         io.perms = perms.data_ptr() if perms is not None else None
         io.arena, io.out8 = arena.data_ptr(), out8.data_ptr()
         io.perms_ready = perms_event.cuda_event if perms_event is not None else None
+        if aug_feats is not None:
+            io.aug_feats = aug_feats.data_ptr()
+            io.aug_feats_strides[:] = aug_feats.stride()
         for name, t in (("cd_out", cd_out), ("loss_out", loss_out), ("dd_out", dd_out), ("fd_dbg", fd_dbg)):
             setattr(io, name, t.data_ptr() if t is not None else None)
         check(lib.dg_loss_forward(C.byref(desc), C.byref(io), stream_ptr(dev.index)), "dg_loss_forward")
@@ -359,7 +362,7 @@ class _CorrLossFn(torch.autograd.Function):
         io.perms = perms.data_ptr() if perms is not None else None
         check(_lib.lib().dg_loss_backward(C.byref(ctx.desc), C.byref(io), C.byref(gr), stream_ptr(arena.device.index)),
               "dg_loss_backward")
-        return (None, None, d_code, d_code_pos) + (None,) * 7
+        return (None, None, d_code, d_code_pos) + (None,) * 8
 
 
 class ContrastiveCorrelationLoss(nn.Module):
@@ -399,6 +402,9 @@ class ContrastiveCorrelationLoss(nn.Module):
 
     def forward(self, orig_feats, orig_feats_pos, orig_salience, orig_salience_pos, orig_code, orig_code_pos,
                 depth=None, depth_pos=None):
+        return self._run(orig_feats, orig_feats_pos, orig_code, orig_code_pos, depth, depth_pos, None)
+
+    def _run(self, orig_feats, orig_feats_pos, orig_code, orig_code_pos, depth, depth_pos, aug_feats):
         cfg = self.cfg
         for name, t in (("orig_feats", orig_feats), ("orig_feats_pos", orig_feats_pos), ("orig_code", orig_code),
                         ("orig_code_pos", orig_code_pos)):
@@ -424,7 +430,12 @@ class ContrastiveCorrelationLoss(nn.Module):
         flags = self._flags()
         coords = None
         perms_event = None
-        if cfg.depth_sampling == "fps":
+        if aug_feats is not None:
+            require_cuda_f32(aug_feats, "depth_aug_feats")
+            if aug_feats.shape != orig_feats.shape:
+                raise ValueError("depth_aug_feats must have the shape of orig_feats")
+            flags |= _lib.FLAG_AUG_INTRA
+        if cfg.depth_sampling == "fps" and aug_feats is None:
             if depth is None or depth_pos is None:
                 raise ValueError("depth_sampling='fps' needs depth and depth_pos")
             flags |= _lib.FLAG_FPS
@@ -447,7 +458,7 @@ class ContrastiveCorrelationLoss(nn.Module):
         else:
             perms = super_perms(nneg, B, dev)
 
-        depth_term = bool(cfg.depth_feat_correlation_loss)
+        depth_term = bool(cfg.depth_feat_correlation_loss) and aug_feats is None
         Hd = Wd = 0
         if depth_term or (flags & _lib.FLAG_FPS):
             if depth is None:
@@ -464,13 +475,14 @@ class ContrastiveCorrelationLoss(nn.Module):
                 flags |= _lib.FLAG_DEPTH_TERM
         if corr_kernel_choice(S * S, orig_code.shape[1]) == "simt":
             flags |= _lib.FLAG_FORCE_SIMT
-        elif Cdim % 128 == 0 and orig_feats.is_contiguous() and orig_feats_pos.is_contiguous():
+        elif Cdim % 128 == 0 and orig_feats.is_contiguous() and orig_feats_pos.is_contiguous() and \
+                (aug_feats is None or aug_feats.is_contiguous()):
             flags |= _lib.FLAG_STAGE_NHWC   # NCHW inputs: let the library stage channels-last copies for the gather
         desc = _lib.LossDesc(B, Cdim, orig_code.shape[1], H, W, Hd, Wd, S, nneg, flags, float(cfg.pos_intra_shift),
                              float(cfg.pos_inter_shift), float(cfg.neg_inter_shift),
                              float(cfg.depth_feat_shift) if depth_term else 0.0)
         res = _CorrLossFn.apply(orig_feats, orig_feats_pos, orig_code, orig_code_pos, depth, depth_pos, coords, perms,
-                                desc, bool(self.materialize_cd), perms_event)
+                                desc, bool(self.materialize_cd), perms_event, aug_feats)
         intra, inter, neg, dloss, out8, coords_used, cd_out, loss_out, dd_out = res
         self.last_coords = coords_used if (flags & _lib.FLAG_FPS) else coords
         if self.materialize_cd:
@@ -489,3 +501,22 @@ class ContrastiveCorrelationLoss(nn.Module):
         if depth_term:
             return head + (dloss, dd)
         return head
+
+
+class DepthContrastiveCorrelationLoss(ContrastiveCorrelationLoss):
+    """Drop-in for src/modules.py:1370-1463 (used when ``use_depth_only_intra``, src/train_segmentation.py:133-134):
+    the same helper, but the intra pair correlates depth-augmented features with themselves, coordinates are always
+    random, there is no depth term, and the output is the 6-tuple.  Runs the same kernels (the intra pair reads one
+    extra feature panel slot).  ``depth_aug_feats_pos`` is sampled and never used by the reference; it is ignored."""
+
+    def forward(self, orig_feats, orig_feats_pos, orig_salience, orig_salience_pos, orig_code, orig_code_pos,
+                depth_aug_feats, depth_aug_feats_pos=None):
+        if depth_aug_feats is None:
+            raise ValueError("DepthContrastiveCorrelationLoss needs depth_aug_feats")
+        cfg = self.cfg
+        saved = (cfg.depth_sampling, cfg.depth_feat_correlation_loss)
+        try:   # this variant never uses depth-guided sampling or the depth term, whatever cfg says (:1413-1425)
+            cfg.depth_sampling, cfg.depth_feat_correlation_loss = "none", False
+            return self._run(orig_feats, orig_feats_pos, orig_code, orig_code_pos, None, None, depth_aug_feats)
+        finally:
+            cfg.depth_sampling, cfg.depth_feat_correlation_loss = saved

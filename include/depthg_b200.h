@@ -206,7 +206,9 @@ DG_API int dg_corr_loss(const dg_panels_t* pan, const float* fmean, const float*
 enum { DG_FLAG_DEPTH_TERM = 8,  /* cfg.depth_feat_correlation_loss                          */
        DG_FLAG_FPS = 16,        /* cfg.depth_sampling == "fps": coordinates from depth maps */
        DG_FLAG_FORCE_SIMT = 32, /* use the generic CUDA-core correlation kernel             */
-       DG_FLAG_STAGE_NHWC = 64  /* feats / feats_pos are NCHW-contiguous: stage a channels-last copy in the arena */ };
+       DG_FLAG_STAGE_NHWC = 64, /* feats / feats_pos are NCHW-contiguous: stage a channels-last copy in the arena */
+       DG_FLAG_AUG_INTRA = 128  /* DepthContrastiveCorrelationLoss (src/modules.py:1370-1463): the intra pair correlates
+                                   io->aug_feats (depth-augmented features) instead of io->feats */ };
 
 typedef struct dg_loss_desc {
   int B, C, D, H, W, Hd, Wd, S, neg_samples;
@@ -236,6 +238,8 @@ typedef struct dg_loss_io {
   float* loss_out;
   float* dd_out;
   float* fd_dbg;
+  const float* aug_feats; /* [B,C,H,W] with DG_FLAG_AUG_INTRA (strides below), else NULL */
+  int64_t aug_feats_strides[4];
   void* perms_ready;      /* optional cudaEvent_t: `perms` is produced on another stream; the gathers wait for it
                              (FPS and the depth signs, which do not need perms, are enqueued before the wait) */
 } dg_loss_io_t;

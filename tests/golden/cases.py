@@ -41,6 +41,23 @@ LOSS_CASES = {
     "dense_14x14": (2, 48, 24, dict(feature_samples=14), 22),
 }
 
+# DepthContrastiveCorrelationLoss (src/modules.py:1370-1463) cases: name -> base loss case + seed of the augmented features
+AUG_CASES = {
+    "aug_small": ("small_random", 31),
+    "aug_vits_pointwise": ("small_random_pointwise", 32),
+}
+
+
+def make_aug_inputs(name):
+    base, seed = AUG_CASES[name]
+    cfg, t = make_loss_inputs(base)
+    rs = np.random.RandomState(3000 + seed)
+    B, C, H, W = t["feats"].shape
+    t["aug"] = torch.from_numpy(correlated(rs, B, C, H, W))
+    t["aug_pos"] = torch.from_numpy(correlated(rs, B, C, H, W))
+    return cfg, t
+
+
 # backprop weights for the scalar L = sum w_i * loss_i  (ViT-B paper run, paper_reproduction.sh:8)
 LOSS_WEIGHTS = dict(pos_inter=1.0501, pos_intra=0.2305, neg_inter=0.2485, depth_feat=0.1603)
 

@@ -68,6 +68,23 @@ def run_loss_case(M, name):
     print(name, g["scalars"], g["cd_means"], float(np.linalg.norm(g["d_code"])), float(np.linalg.norm(g["d_code_pos"])))
 
 
+def run_aug_case(M, name):
+    cfg, t = cases.make_aug_inputs(name)
+    code = t["code"].clone().requires_grad_(True)
+    code_pos = t["code_pos"].clone().requires_grad_(True)
+    loss_fn = M.DepthContrastiveCorrelationLoss(cfg)
+    with injected(M, list(t["perms"]), [t["rand1"], t["rand2"]]):
+        out = loss_fn(t["feats"], t["feats_pos"], None, None, code, code_pos, t["aug"], t["aug_pos"])
+    w = cases.LOSS_WEIGHTS
+    L = w["pos_intra"] * out[0] + w["pos_inter"] * out[2] + w["neg_inter"] * out[4].mean()
+    L.backward()
+    g = dict(scalars=np.array([out[0].item(), out[2].item(), out[4].mean().item()], np.float64),
+             cd_means=np.array([out[1].mean().item(), out[3].mean().item(), out[5].mean().item()], np.float64),
+             total=np.float64(L.item()), d_code=code.grad.numpy(), d_code_pos=code_pos.grad.numpy())
+    np.savez_compressed(os.path.join(HERE, f"aug_{name}.npz"), **g)
+    print(name, g["scalars"], float(np.linalg.norm(g["d_code"])))
+
+
 def run_fps(M):
     out = {}
     for pat in cases.FPS_PATTERNS:
@@ -124,6 +141,9 @@ def main():
     for name in cases.LOSS_CASES:
         if only is None or name in only.split(","):
             run_loss_case(M, name)
+    for name in cases.AUG_CASES:
+        if only is None or name in only.split(","):
+            run_aug_case(M, name)
     if only is not None:
         return
     run_fps(M)

@@ -49,3 +49,59 @@ def run_oracle_loss(name, dtype=torch.float32):
 def rel_err(a, b):
     a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
     return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def _aug_total(out):
+    w = cases.LOSS_WEIGHTS
+    return w["pos_intra"] * out[0] + w["pos_inter"] * out[2] + w["neg_inter"] * out[4].mean()
+
+
+def _aug_result(out, code, code_pos):
+    L = _aug_total(out)
+    L.backward()
+    return dict(scalars=np.array([out[0].item(), out[2].item(), out[4].mean().item()]),
+                cd_means=np.array([out[1].mean().item(), out[3].mean().item(), out[5].mean().item()]),
+                total=L.item(), d_code=code.grad.detach().cpu().numpy(), d_code_pos=code_pos.grad.detach().cpu().numpy())
+
+
+def run_oracle_aug(name):
+    cfg, t = cases.make_aug_inputs(name)
+    code = t["code"].clone().requires_grad_(True)
+    code_pos = t["code_pos"].clone().requires_grad_(True)
+    fn = O.DepthContrastiveCorrelationLoss(cfg)
+    perm_it, rand_it = iter(t["perms"]), iter([t["rand1"], t["rand2"]])
+    fn.perm_fn = lambda B, device: next(perm_it).clone()
+    fn.rand_fn = lambda shape, device: next(rand_it).clone()
+    out = fn(t["feats"], t["feats_pos"], None, None, code, code_pos, t["aug"], t["aug_pos"])
+    return _aug_result(out, code, code_pos)
+
+
+def run_cuda_aug(name, channels_last=False, force_simt=False):
+    import os
+    from depthg_b200.modules import DepthContrastiveCorrelationLoss
+    cfg, t = cases.make_aug_inputs(name)
+    dev = torch.device("cuda:0")
+
+    def put(x):
+        x = x.to(dev)
+        return x.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2) if channels_last else x
+
+    code = put(t["code"]).detach().requires_grad_(True)
+    code_pos = put(t["code_pos"]).detach().requires_grad_(True)
+    fn = DepthContrastiveCorrelationLoss(cfg)
+    perm_it, rand_it = iter(t["perms"].to(dev)), iter([t["rand1"].to(dev), t["rand2"].to(dev)])
+    fn.perm_fn = lambda B, device: next(perm_it).clone()
+    fn.rand_fn = lambda shape, device: next(rand_it).clone()
+    old = os.environ.get("DEPTHG_B200_CORR")
+    if force_simt:
+        os.environ["DEPTHG_B200_CORR"] = "simt"
+    try:
+        out = fn(put(t["feats"]), put(t["feats_pos"]), None, None, code, code_pos, put(t["aug"]), put(t["aug_pos"]))
+    finally:
+        if force_simt:
+            if old is None:
+                del os.environ["DEPTHG_B200_CORR"]
+            else:
+                os.environ["DEPTHG_B200_CORR"] = old
+    assert len(out) == 6
+    return _aug_result(out, code, code_pos)

@@ -479,3 +479,15 @@ def test_graphed_super_perms_reproduce_the_eager_torch_stream():
     for a, b in zip(eager, graphed):
         assert torch.equal(a, b)
     assert torch.equal(tail_eager, tail_graphed)
+
+
+# ------------------------------------------------------------------ DepthContrastiveCorrelationLoss (next row)
+@pytest.mark.parametrize("name", list(cases.AUG_CASES))
+@pytest.mark.parametrize("variant", ["nchw", "channels_last", "simt"])
+def test_depth_contrastive_variant_matches_reference_golden(name, variant):
+    from tests.helpers import run_cuda_aug
+    g = golden("aug_" + name)
+    r = run_cuda_aug(name, channels_last=(variant == "channels_last"), force_simt=(variant == "simt"))
+    np.testing.assert_allclose(r["scalars"], g["scalars"], rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(r["cd_means"], g["cd_means"], rtol=RTOL, atol=ATOL)
+    assert rel_err(r["d_code"], g["d_code"]) < RTOL and rel_err(r["d_code_pos"], g["d_code_pos"]) < RTOL

@@ -113,3 +113,15 @@ def test_oracle_equals_real_reference_with_shared_rng(seed, mode):
         outs.append([o.detach() for o in out] + [ci.grad, cpi.grad])
     for a, b in zip(*outs):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("name", list(cases.AUG_CASES))
+def test_oracle_depth_contrastive_variant_matches_reference_golden(name):
+    """DepthContrastiveCorrelationLoss (src/modules.py:1370-1463) restatement vs the real reference's output."""
+    from tests.helpers import run_oracle_aug
+    g = golden("aug_" + name)
+    r = run_oracle_aug(name)
+    np.testing.assert_allclose(r["scalars"], g["scalars"], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(r["cd_means"], g["cd_means"], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(r["d_code"], g["d_code"], rtol=1e-5, atol=1e-10)
+    np.testing.assert_allclose(r["d_code_pos"], g["d_code_pos"], rtol=1e-5, atol=1e-10)

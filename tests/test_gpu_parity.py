@@ -491,3 +491,51 @@ def test_depth_contrastive_variant_matches_reference_golden(name, variant):
     np.testing.assert_allclose(r["scalars"], g["scalars"], rtol=RTOL, atol=ATOL)
     np.testing.assert_allclose(r["cd_means"], g["cd_means"], rtol=RTOL, atol=ATOL)
     assert rel_err(r["d_code"], g["d_code"]) < RTOL and rel_err(r["d_code_pos"], g["d_code_pos"]) < RTOL
+
+
+# ------------------------------------------------------------------ edge shapes against the oracle (computed on the fly)
+@pytest.mark.parametrize("shape", [
+    dict(B=1, C=32, D=16, S=4, neg=0, sampling="fps"),          # single image, no negatives
+    dict(B=2, C=100, D=128, S=5, neg=2, sampling="none"),       # C not a multiple of 32/128, code dim at the 128 limit
+    dict(B=3, C=256, D=33, S=16, neg=1, sampling="fps"),        # S*S = 256: the largest tensor-core tiling
+    dict(B=2, C=20, D=7, S=3, neg=3, sampling="fps", H=20, W=12, Hd=80, Wd=60),   # non-square grid, odd pooling windows
+])
+def test_edge_shapes_match_oracle(shape):
+    from depthg_b200.modules import ContrastiveCorrelationLoss
+    H, W = shape.get("H", 28), shape.get("W", 28)
+    Hd, Wd = shape.get("Hd", 8 * H), shape.get("Wd", 8 * W)
+    B, C, D, S, neg = shape["B"], shape["C"], shape["D"], shape["S"], shape["neg"]
+    rs = np.random.RandomState(hash(str(sorted(shape.items()))) % (2 ** 31))
+    t = dict(feats=cases.correlated(rs, B, C, H, W), feats_pos=cases.correlated(rs, B, C, H, W),
+             code=cases.correlated(rs, B, D, H, W, rank=3), code_pos=cases.correlated(rs, B, D, H, W, rank=3),
+             depth=rs.randint(0, 256, (B, 1, Hd, Wd)).astype(np.float32),
+             depth_pos=rs.randint(0, 256, (B, 1, Hd, Wd)).astype(np.float32))
+    t = {k: torch.from_numpy(v) for k, v in t.items()}
+    perms = [torch.from_numpy(cases.bumped_perm(rs, B)) for _ in range(neg)] if B > 1 else []
+    rands = [torch.from_numpy(rs.random_sample((B, S, S, 2)).astype(np.float32)) for _ in range(2)]
+    cfg = cases.loss_cfg(feature_samples=S, neg_samples=neg, depth_sampling=shape["sampling"])
+    res = []
+    for impl, devc in ((O.ContrastiveCorrelationLoss, "cpu"), (ContrastiveCorrelationLoss, "cuda:0")):
+        a = {k: v.to(devc) for k, v in t.items()}
+        code, code_pos = a["code"].clone().requires_grad_(True), a["code_pos"].clone().requires_grad_(True)
+        fn = impl(cfg)
+        pit, rit = iter([p.to(devc) for p in perms]), iter([r.to(devc) for r in rands])
+        fn.perm_fn = lambda n, device: next(pit).clone()
+        fn.rand_fn = lambda shp, device: next(rit).clone()
+        if neg == 0:   # the reference cannot cat an empty list of negatives; compare the positive terms only
+            if impl is O.ContrastiveCorrelationLoss:
+                cfg1 = cases.loss_cfg(feature_samples=S, neg_samples=1, depth_sampling=shape["sampling"])
+                fn = impl(cfg1)
+                fn.perm_fn = lambda n, device: torch.zeros(n, dtype=torch.long)
+                fn.rand_fn = lambda shp, device: next(rit).clone()
+            out = fn(a["feats"], a["feats_pos"], None, None, code, code_pos, a["depth"], a["depth_pos"])
+            L = out[0] * 0.3 + out[2] * 0.7 + out[6] * 0.2
+        else:
+            out = fn(a["feats"], a["feats_pos"], None, None, code, code_pos, a["depth"], a["depth_pos"])
+            L = out[0] * 0.3 + out[2] * 0.7 + out[4].mean() * 0.5 + out[6] * 0.2
+        L.backward()
+        res.append((float(L), [float(out[i].mean()) for i in (0, 2, 6)], code.grad.cpu().numpy(), code_pos.grad.cpu().numpy()))
+    (L0, s0, g0, gp0), (L1, s1, g1, gp1) = res
+    np.testing.assert_allclose(s1, s0, rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(L1, L0, rtol=RTOL, atol=ATOL)
+    assert rel_err(g1, g0) < RTOL and rel_err(gp1, gp0) < RTOL

@@ -516,18 +516,21 @@ def main():
         from oracle import depthg_oracle as O
         gin = {k: v.detach() for k, v in sets[0].items()}
         times = []
-        for _ in range(3):
-            code = gin["code"].clone().requires_grad_(True)
-            code_pos = gin["code_pos"].clone().requires_grad_(True)
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            out = O.ContrastiveCorrelationLoss(cfg)(gin["feats"], gin["feats_pos"], None, None, code, code_pos,
-                                                    gin["depth"], gin["depth_pos"])
-            backprop(out)
-            torch.cuda.synchronize()
-            times.append(time.perf_counter() - t0)
-        ref_gpu = {"value": B / min(times), "unit": UNIT, "ms_per_step": min(times) * 1e3,
-                   "note": "reference algorithm as PyTorch eager ops on the same B200, FPS on the host in NumPy as shipped"}
+        try:   # an auxiliary comparison: it must never cost the bench line
+            for _ in range(3):
+                code = gin["code"].clone().requires_grad_(True)
+                code_pos = gin["code_pos"].clone().requires_grad_(True)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                out = O.ContrastiveCorrelationLoss(cfg)(gin["feats"], gin["feats_pos"], None, None, code, code_pos,
+                                                        gin["depth"], gin["depth_pos"])
+                backprop(out)
+                torch.cuda.synchronize()
+                times.append(time.perf_counter() - t0)
+            ref_gpu = {"value": B / min(times), "unit": UNIT, "ms_per_step": min(times) * 1e3,
+                       "note": "reference algorithm as PyTorch eager ops on the same B200, FPS on the host in NumPy as shipped"}
+        except Exception as e:  # noqa: BLE001
+            ref_gpu = {"error": f"{type(e).__name__}: {e}"[:200]}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

@@ -53,6 +53,11 @@ SIGNATURES = {
     "dg_knn_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "dg_knn_topk": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, C.c_size_t, _vp]),
     "dg_pool_normalize": (C.c_int, [_vp, _c_i64p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _vp, _vp]),
+    "dg_probe_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "dg_linear_probe_ce": (C.c_int, [_vp, _c_i64p, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, C.c_int, _vp, _c_i64p,
+                                     C.c_int, C.c_int, _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
+    "dg_cluster_probe": (C.c_int, [_vp, _c_i64p, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_int, C.c_int, C.c_float,
+                                   _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
 }
 
 PANEL_F32, PANEL_FEATS_SPLIT, PANEL_CODE_SPLIT = 0, 1, 2

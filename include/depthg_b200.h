@@ -272,6 +272,35 @@ DG_API int dg_knn_topk(const float* q, const float* db, int Nq, int N, int F, in
 DG_API int dg_pool_normalize(const float* t, const int64_t* strides, int N, int C, int H, int W, float eps, float* out,
                       dg_stream_t stream);
 
+/* ---------------------------------------------------------------------------
+ * Probe losses on the detached code map.  Both train only
+ * their own parameters, so the entry points return the loss AND the unit
+ * gradients of that loss in one call (forward and backward are one pass).
+ * code : [B,D,h,w] fp32 with element strides (host array of 4), D <= 128.
+ * ws   : dg_probe_workspace_bytes(B,h,w,D,K) bytes of device scratch.       */
+DG_API size_t dg_probe_workspace_bytes(int B, int h, int w, int D, int K);
+
+/* Linear probe: replaces  linear_probe(code) -> F.interpolate(bilinear,
+ * align_corners=False, size=label.shape[-2:]) -> permute/reshape -> [mask] ->
+ * CrossEntropyLoss  (src/train_segmentation.py:419-437).
+ *   weight [K,D], bias [K] (may be NULL): the 1x1 conv, K <= 32.
+ *   labels [B,Hl,Wl] int64 with element strides; entries outside [0,K) are masked out.
+ *   loss_out: device scalar = mean CE over the unmasked label pixels.
+ *   dweight [K,D], dbias [K]: d loss / d weight, d loss / d bias (NULL = forward only). */
+DG_API int dg_linear_probe_ce(const float* code, const int64_t* strides, int B, int D, int h, int w, const float* weight,
+                       const float* bias, int K, const int64_t* labels, const int64_t* label_strides, int Hl, int Wl,
+                       float* loss_out, float* dweight, float* dbias, void* ws, size_t ws_bytes, dg_stream_t stream);
+
+/* Cluster probe: replaces ClusterLookup.forward (src/modules.py:659-675).
+ *   clusters [N,D] (un-normalised parameter), N <= 32.
+ *   mode 0: alpha=None  -> probs = one_hot(argmax), loss, dclusters (NULL = skip)
+ *   mode 1: alpha given -> probs = softmax(inner*alpha), loss (forward only)
+ *   mode 2: log_probs   -> probs_out = log_softmax(inner*alpha), no loss
+ *   probs_out: [B,h,w,N] (the reference returns the same memory permuted to [B,N,h,w]); may be NULL in modes 0/1. */
+DG_API int dg_cluster_probe(const float* code, const int64_t* strides, int B, int D, int h, int w, const float* clusters,
+                     int N, int mode, float alpha, float* loss_out, float* probs_out, float* dclusters, void* ws,
+                     size_t ws_bytes, dg_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -184,3 +184,29 @@ def make_knn_feats(name):
         x = rs.standard_normal((N, Fdim)).astype(np.float32)
     x = torch.from_numpy(x)
     return torch.nn.functional.normalize(x, dim=1), k, n_batches
+
+
+# ------------------------------------------------------------------ probe losses
+PROBE_CASES = {  # name -> (B, D, h, w, K, Hl, Wl, frac_ignored, seed)
+    "probe_small": (2, 16, 7, 7, 5, 56, 56, 0.1, 1),
+    "probe_odd": (3, 70, 14, 10, 27, 100, 77, 0.2, 2),      # non-integer scale factors, non-square
+    "probe_cfg2": (4, 90, 28, 28, 27, 224, 224, 0.05, 3),   # cocostuff27 ViT-B/8 shapes (B reduced)
+    "probe_same": (2, 12, 9, 9, 3, 9, 9, 0.0, 4),           # label at code resolution (scale 1)
+}
+
+
+def make_probe_inputs(name):
+    B, D, h, w, K, Hl, Wl, ignored, seed = PROBE_CASES[name]
+    rs = np.random.RandomState(3000 + seed)
+    code = correlated(rs, B, D, h, w, rank=4)
+    weight = (rs.standard_normal((K, D)) * (3.0 / np.sqrt(D))).astype(np.float32)
+    bias = (rs.standard_normal((K,)) * 0.3).astype(np.float32)
+    clusters = rs.standard_normal((K, D)).astype(np.float32)
+    # blocky label map with an ignore class (-1) and an out-of-range id (K), as the datasets produce
+    coarse = rs.randint(0, K, (B, (Hl + 7) // 8, (Wl + 7) // 8))
+    label = np.repeat(np.repeat(coarse, 8, axis=1), 8, axis=2)[:, :Hl, :Wl].astype(np.int64)
+    drop = rs.random_sample(label.shape)
+    label[drop < ignored / 2] = -1
+    label[(drop >= ignored / 2) & (drop < ignored)] = K
+    return {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in
+            dict(code=code, weight=weight, bias=bias, clusters=clusters, label=label).items()}

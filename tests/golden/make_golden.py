@@ -133,11 +133,60 @@ def run_knn():
     print("knn:", {k: v.shape for k, v in out.items()})
 
 
+def run_probes(M):
+    """ClusterLookup is the reference's own class (src/modules.py:646-675).  The linear-probe
+    branch lives inside LitUnsupervisedSegmenter.training_step (src/train_segmentation.py:419-437),
+    which cannot be instantiated here (lightning/hydra/datasets absent); its stock-torch call
+    sequence is replayed line by line on an nn.Conv2d / CrossEntropyLoss built as in :113,:127."""
+    out = {}
+    for name in cases.PROBE_CASES:
+        t = cases.make_probe_inputs(name)
+        K, D = t["weight"].shape
+        probe = M.ClusterLookup(D, K)
+        with torch.no_grad():
+            probe.clusters.copy_(t["clusters"])
+        loss, probs = probe(t["code"], None)
+        loss.backward()
+        out[name + "_cluster_loss"] = loss.detach().numpy()
+        assert bool(((probs == 0) | (probs == 1)).all()) and bool((probs.sum(1) == 1).all())
+        out[name + "_cluster_argmax"] = probs.argmax(1).numpy().astype(np.uint8)   # the one-hot map, compactly
+        out[name + "_cluster_grad"] = probe.clusters.grad.numpy()
+        with torch.no_grad():
+            sl, sp = probe(t["code"], 2)
+            out[name + "_soft_loss"] = sl.numpy()
+            if t["code"].numel() < 50000:   # keep the fixtures small: full maps only for the small cases
+                out[name + "_soft_probs"] = sp.numpy()
+                out[name + "_log_probs"] = probe(t["code"], 2, log_probs=True).numpy()
+
+        linear_probe = torch.nn.Conv2d(D, K, (1, 1))
+        with torch.no_grad():
+            linear_probe.weight.copy_(t["weight"].reshape(K, D, 1, 1))
+            linear_probe.bias.copy_(t["bias"])
+        linear_probe_loss_fn = torch.nn.CrossEntropyLoss()
+        label, code, n_classes = t["label"], t["code"], K
+        flat_label = label.reshape(-1)
+        mask = (flat_label >= 0) & (flat_label < n_classes)
+        detached_code = torch.clone(code.detach())
+        linear_logits = linear_probe(detached_code)
+        linear_logits = torch.nn.functional.interpolate(linear_logits, label.shape[-2:], mode='bilinear',
+                                                        align_corners=False)
+        linear_logits = linear_logits.permute(0, 2, 3, 1).reshape(-1, n_classes)
+        linear_loss = linear_probe_loss_fn(linear_logits[mask], flat_label[mask]).mean()
+        linear_loss.backward()
+        out[name + "_linear_loss"] = linear_loss.detach().numpy()
+        out[name + "_linear_dw"] = linear_probe.weight.grad.reshape(K, D).numpy()
+        out[name + "_linear_db"] = linear_probe.bias.grad.numpy()
+    np.savez_compressed(os.path.join(HERE, "probes.npz"), **out)
+    print("probes:", {k: (v.shape if v.ndim else float(v)) for k, v in out.items() if "loss" in k})
+
+
 def main():
     assert refimport.have_reference(), "run in the build container (needs /root/reference)"
     torch.set_num_threads(8)
     M = refimport.load_reference_modules()
     only = os.environ.get("GOLDEN_ONLY")
+    if only == "probes":
+        return run_probes(M)
     for name in cases.LOSS_CASES:
         if only is None or name in only.split(","):
             run_loss_case(M, name)
@@ -149,6 +198,7 @@ def main():
     run_fps(M)
     run_misc(M)
     run_knn()
+    run_probes(M)
 
 
 if __name__ == "__main__":

@@ -539,3 +539,80 @@ def test_edge_shapes_match_oracle(shape):
     np.testing.assert_allclose(s1, s0, rtol=RTOL, atol=ATOL)
     np.testing.assert_allclose(L1, L0, rtol=RTOL, atol=ATOL)
     assert rel_err(g1, g0) < RTOL and rel_err(gp1, gp0) < RTOL
+
+
+# ------------------------------------------------------------------ probe losses
+@pytest.mark.parametrize("layout", ["nchw", "channels_last"])
+@pytest.mark.parametrize("name", list(cases.PROBE_CASES))
+def test_probe_losses_match_reference_golden(name, layout):
+    from depthg_b200.probes import ClusterLookup, linear_probe_loss
+    g = golden("probes")
+    t = {k: v.to(dev()) for k, v in cases.make_probe_inputs(name).items()}
+    code = t["code"].contiguous(memory_format=torch.channels_last) if layout == "channels_last" else t["code"]
+    K, D = t["weight"].shape
+    probe = ClusterLookup(D, K).to(dev())
+    with torch.no_grad():
+        probe.clusters.copy_(t["clusters"])
+    loss, probs = probe(code, None)
+    (loss * 3.0).backward()
+    np.testing.assert_allclose(loss.item(), g[name + "_cluster_loss"], rtol=RTOL)
+    p = probs.cpu().numpy()
+    assert p.shape == (code.shape[0], K) + tuple(code.shape[2:])
+    assert ((p == 0) | (p == 1)).all() and (p.sum(1) == 1).all()
+    # assignments may only differ where the two best similarities tie to fp32 rounding
+    diff = p.argmax(1) != g[name + "_cluster_argmax"]
+    assert diff.mean() < 1e-3
+    assert rel_err(probe.clusters.grad.cpu().numpy() / 3.0, g[name + "_cluster_grad"]) < (1e-3 if diff.any() else RTOL)
+
+    weight = t["weight"].reshape(K, D, 1, 1).clone().requires_grad_(True)
+    bias = t["bias"].clone().requires_grad_(True)
+    lin = linear_probe_loss(code, weight, bias, t["label"])
+    (lin * 0.5).backward()
+    np.testing.assert_allclose(lin.item(), g[name + "_linear_loss"], rtol=RTOL)
+    assert weight.grad.shape == weight.shape
+    assert rel_err(weight.grad.reshape(K, D).cpu().numpy() * 2.0, g[name + "_linear_dw"]) < RTOL
+    assert rel_err(bias.grad.cpu().numpy() * 2.0, g[name + "_linear_db"]) < RTOL
+
+    with torch.no_grad():
+        sl, sp = probe(code, 2)
+        np.testing.assert_allclose(sl.item(), g[name + "_soft_loss"], rtol=RTOL, atol=ATOL)
+        if name + "_soft_probs" in g:
+            np.testing.assert_allclose(sp.cpu().numpy(), g[name + "_soft_probs"], rtol=RTOL, atol=1e-6)
+            np.testing.assert_allclose(probe(code, 2, log_probs=True).cpu().numpy(), g[name + "_log_probs"], rtol=RTOL,
+                                       atol=1e-5)
+
+
+def test_probes_refuse_attached_code_and_all_masked_labels_give_nan():
+    from depthg_b200.probes import ClusterLookup, linear_probe_loss
+    t = {k: v.to(dev()) for k, v in cases.make_probe_inputs("probe_small").items()}
+    K, D = t["weight"].shape
+    with pytest.raises(ValueError, match="requires grad"):
+        linear_probe_loss(t["code"].clone().requires_grad_(True), t["weight"], t["bias"], t["label"])
+    with pytest.raises(ValueError, match="requires grad"):
+        ClusterLookup(D, K).to(dev())(t["code"].clone().requires_grad_(True), None)
+    with pytest.raises(NotImplementedError):
+        ClusterLookup(D, K).to(dev())(t["code"], 2.0)
+    nothing = torch.full_like(t["label"], -1)
+    assert torch.isnan(linear_probe_loss(t["code"], t["weight"], t["bias"], nothing))   # mean over no pixels, as torch
+    # forward-only call (no parameter requires grad) and a bias-free probe
+    a = linear_probe_loss(t["code"], t["weight"], None, t["label"])
+    b = O.linear_probe_loss(t["code"].cpu(), t["weight"].cpu(), None, t["label"].cpu())
+    np.testing.assert_allclose(a.item(), b.item(), rtol=RTOL)
+
+
+def test_linear_probe_full_size_matches_oracle():
+    """cfg2 shapes at the bench batch (B=32, 224x224 labels): loss and gradients against the CPU oracle."""
+    from depthg_b200.probes import linear_probe_loss
+    rs = np.random.RandomState(99)
+    B, D, K = 32, 90, 27
+    code = torch.from_numpy(cases.correlated(rs, B, D, 28, 28, rank=4))
+    weight = torch.from_numpy((rs.standard_normal((K, D)) / np.sqrt(D)).astype(np.float32))
+    bias = torch.from_numpy((rs.standard_normal((K,)) * 0.1).astype(np.float32))
+    label = torch.from_numpy(rs.randint(-1, K, (B, 224, 224)).astype(np.int64))
+    w0, b0 = weight.clone().requires_grad_(True), bias.clone().requires_grad_(True)
+    O.linear_probe_loss(code, w0, b0, label).backward()
+    w1, b1 = weight.to(dev()).requires_grad_(True), bias.to(dev()).requires_grad_(True)
+    lin = linear_probe_loss(code.to(dev()), w1, b1, label.to(dev()))
+    lin.backward()
+    assert rel_err(w1.grad.cpu().numpy(), w0.grad.numpy()) < RTOL
+    assert rel_err(b1.grad.cpu().numpy(), b0.grad.numpy()) < RTOL

@@ -125,3 +125,51 @@ def test_oracle_depth_contrastive_variant_matches_reference_golden(name):
     np.testing.assert_allclose(r["cd_means"], g["cd_means"], rtol=1e-6, atol=1e-9)
     np.testing.assert_allclose(r["d_code"], g["d_code"], rtol=1e-5, atol=1e-10)
     np.testing.assert_allclose(r["d_code_pos"], g["d_code_pos"], rtol=1e-5, atol=1e-10)
+
+
+# ------------------------------------------------------------------ probe losses
+def _oracle_probes(name):
+    t = cases.make_probe_inputs(name)
+    K, D = t["weight"].shape
+    probe = O.ClusterLookup(D, K)
+    with torch.no_grad():
+        probe.clusters.copy_(t["clusters"])
+    loss, probs = probe(t["code"], None)
+    loss.backward()
+    weight, bias = t["weight"].clone().requires_grad_(True), t["bias"].clone().requires_grad_(True)
+    lin = O.linear_probe_loss(t["code"], weight, bias, t["label"])
+    lin.backward()
+    return t, probe, loss, probs, lin, weight, bias
+
+
+@pytest.mark.parametrize("name", list(cases.PROBE_CASES))
+def test_oracle_probes_match_reference_golden(name):
+    g = golden("probes")
+    t, probe, loss, probs, lin, weight, bias = _oracle_probes(name)
+    np.testing.assert_allclose(loss.item(), g[name + "_cluster_loss"], rtol=1e-6)
+    assert np.array_equal(probs.argmax(1).numpy(), g[name + "_cluster_argmax"])
+    np.testing.assert_allclose(probe.clusters.grad.numpy(), g[name + "_cluster_grad"], rtol=1e-5, atol=1e-9)
+    np.testing.assert_allclose(lin.item(), g[name + "_linear_loss"], rtol=1e-6)
+    np.testing.assert_allclose(weight.grad.numpy(), g[name + "_linear_dw"], rtol=1e-5, atol=1e-9)
+    np.testing.assert_allclose(bias.grad.numpy(), g[name + "_linear_db"], rtol=1e-5, atol=1e-9)
+    with torch.no_grad():
+        sl, sp = probe(t["code"], 2)
+        np.testing.assert_allclose(sl.item(), g[name + "_soft_loss"], rtol=1e-6)
+        if name + "_soft_probs" in g:
+            np.testing.assert_allclose(sp.numpy(), g[name + "_soft_probs"], rtol=1e-6, atol=1e-9)
+            np.testing.assert_allclose(probe(t["code"], 2, log_probs=True).numpy(), g[name + "_log_probs"], rtol=1e-6,
+                                       atol=1e-7)
+
+
+@pytest.mark.skipif(not refimport.have_reference(), reason="needs /root/reference")
+def test_oracle_cluster_lookup_matches_reference_class_directly():
+    M = refimport.load_reference_modules()
+    t = cases.make_probe_inputs("probe_odd")
+    K, D = t["weight"].shape
+    ref, mine = M.ClusterLookup(D, K), O.ClusterLookup(D, K)
+    with torch.no_grad():
+        ref.clusters.copy_(t["clusters"])
+        mine.clusters.copy_(t["clusters"])
+    for alpha in (None, 0.5, 3):
+        (l0, p0), (l1, p1) = ref(t["code"], alpha), mine(t["code"], alpha)
+        assert torch.equal(l0, l1) and torch.equal(p0, p1)

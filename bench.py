@@ -213,6 +213,62 @@ def workload_config(B, n_gpus, extra=None):
 
 
 # ----------------------------------------------------------------------------- our arm
+def probe_bench(dev, B, n=30):
+    """Linear-probe CE and cluster-probe loss fwd+bwd at the cfg2 shapes (D=90, 28x28 code, 27 classes,
+    224x224 labels): depthg_b200.probes vs the trainer's torch op sequence (src/train_segmentation.py:419-441)."""
+    import torch.nn.functional as F
+    from depthg_b200.probes import ClusterLookup, linear_probe_loss
+    D, K, h, Hl = CFG2["D"], 27, 28, 224
+    g = torch.Generator(device=dev).manual_seed(7)
+    code = torch.randn(B, D, h, h, device=dev, generator=g).contiguous(memory_format=torch.channels_last)
+    label = torch.randint(-1, K, (B, Hl, Hl), device=dev, generator=g)
+    weight = (torch.randn(K, D, 1, 1, device=dev, generator=g) / D ** 0.5).requires_grad_(True)
+    bias = torch.zeros(K, device=dev, requires_grad=True)
+    probe = ClusterLookup(D, K).to(dev)
+
+    def fused_linear():
+        weight.grad = bias.grad = None
+        linear_probe_loss(code, weight, bias, label).backward()
+
+    def torch_linear():
+        weight.grad = bias.grad = None
+        flat = label.reshape(-1)
+        mask = (flat >= 0) & (flat < K)
+        lg = F.interpolate(F.conv2d(torch.clone(code.detach()), weight, bias), label.shape[-2:], mode="bilinear",
+                           align_corners=False)
+        lg = lg.permute(0, 2, 3, 1).reshape(-1, K)
+        F.cross_entropy(lg[mask], flat[mask]).mean().backward()
+
+    def fused_cluster():
+        probe.clusters.grad = None
+        probe(code, None)[0].backward()
+
+    def torch_cluster():
+        probe.clusters.grad = None
+        ip = torch.einsum("bchw,nc->bnhw", F.normalize(code, dim=1), F.normalize(probe.clusters, dim=1))
+        cp = F.one_hot(torch.argmax(ip, dim=1), K).permute(0, 3, 1, 2).to(torch.float32)
+        (-(cp * ip).sum(1).mean()).backward()
+
+    def timeit(fn):
+        for _ in range(5):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n * 1e3
+
+    out = {"shapes": {"B": B, "D": D, "classes": K, "code": "28x28", "label": "224x224"}}
+    for name, fn in (("linear_probe_ce_us", fused_linear), ("linear_probe_ce_torch_ops_us", torch_linear),
+                     ("cluster_probe_us", fused_cluster), ("cluster_probe_torch_ops_us", torch_cluster)):
+        out[name] = round(timeit(fn), 1)
+    out["note"] = "fwd+bwd per call incl. host overhead; torch_ops = the trainer's own op sequence on the same GPU"
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -532,6 +588,14 @@ def main():
         except Exception as e:  # noqa: BLE001
             ref_gpu = {"error": f"{type(e).__name__}: {e}"[:200]}
 
+    # ---- probe losses: fused kernels vs the reference's stock-torch op sequence on this GPU
+    probes = None
+    if rank == 0 and world == 1 and not args.no_knn:
+        try:
+            probes = probe_bench(dev, B)
+        except Exception as e:  # noqa: BLE001  (auxiliary: must never cost the bench line)
+            probes = {"error": f"{type(e).__name__}: {e}"[:200]}
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -548,7 +612,7 @@ def main():
                                            "ms_per_step": ms_fused / args.steps,
                                            "note": "negative_sampler='fused': one dg_super_perms launch instead of "
                                                    "neg_samples x torch.randperm (same distribution, different stream)"},
-                "knn": knn}
+                "knn": knn, "probes": probes}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

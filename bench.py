@@ -314,6 +314,24 @@ def main():
         s["code_pos"].requires_grad_(True)
     head_grad = torch.zeros(HEAD_GRAD_FLOATS, device=dev) if world > 1 else None
     pending = [None]
+    # how the per-step head-gradient all-reduce is issued: "async" = dist.all_reduce(async_op=True) (what DDP's
+    # reducer does), "graph" = the same NCCL all-reduce captured once and replayed on a side stream, "none" = off
+    ar_mode = os.environ.get("DEPTHG_BENCH_ALLREDUCE", "graph") if world > 1 else "none"
+    ar_stream = ar_graph = None
+    if ar_mode == "graph":
+        try:
+            ar_stream = torch.cuda.Stream(device=dev)
+            dist.all_reduce(head_grad)                     # communicator warm-up outside capture
+            torch.cuda.synchronize()
+            ar_graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(ar_graph, stream=ar_stream):
+                dist.all_reduce(head_grad)
+        except Exception:  # noqa: BLE001  (capture unsupported on this stack: fall back to the plain async call)
+            ar_mode, ar_stream, ar_graph = "async", None, None
+        flags = torch.tensor([1.0 if ar_mode == "graph" else 0.0], device=dev)
+        dist.all_reduce(flags, op=dist.ReduceOp.MIN)       # all ranks must agree on the mode
+        if flags.item() == 0.0:
+            ar_mode, ar_stream, ar_graph = "async", None, None
 
     def step(i):
         s = sets[i % NSETS]
@@ -321,17 +339,26 @@ def main():
         s["code_pos"].grad = None
         out = loss_fn(s["feats"], s["feats_pos"], None, None, s["code"], s["code_pos"], s["depth"], s["depth_pos"])
         backprop(out)
-        if world > 1:   # DDP semantics: the only exchange is the head-gradient all-reduce; like DDP it is
+        if ar_mode == "async":   # DDP semantics: the only exchange is the head-gradient all-reduce; like DDP it is
             if pending[0] is not None:   # asynchronous and only has to land before the next optimiser step
                 pending[0].wait()
             pending[0] = dist.all_reduce(head_grad, async_op=True)
+        elif ar_mode == "graph":
+            ar_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(ar_stream):
+                ar_graph.replay()
         return out
+
+    def drain():   # the last all-reduce must land inside the timed region
+        if pending[0] is not None:
+            pending[0].wait()
+            pending[0] = None
+        if ar_stream is not None:
+            torch.cuda.current_stream().wait_stream(ar_stream)
 
     def barrier():
         if world > 1:
-            if pending[0] is not None:
-                pending[0].wait()
-                pending[0] = None
+            drain()
             dist.barrier()
         torch.cuda.synchronize()
 
@@ -345,6 +372,7 @@ def main():
         ev0.record()
         for i in range(args.steps):
             step(i)
+        drain()
         ev1.record()
         barrier()
     ms = ev0.elapsed_time(ev1)
@@ -602,7 +630,8 @@ def main():
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": workload_config(B, world, extra={
                     "l2_policy": f"rotating {NSETS} input sets ({NSETS * step_bytes / 1e6:.0f} MB) > 126 MB L2",
-                    "allreduce_floats_per_step": HEAD_GRAD_FLOATS if world > 1 else 0,
+                    "allreduce_floats_per_step": HEAD_GRAD_FLOATS if ar_mode != "none" else 0,
+                    "allreduce_issue": ar_mode,
                     "layout": "nchw" if args.nchw else "channels_last (live trainer layout)"}),
                 "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches),
                 "launches_per_step": launches / args.steps, "roofline": roofline, "roofline_step": roofline_step,
@@ -615,7 +644,12 @@ def main():
                 "knn": knn, "probes": probes}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # a captured NCCL graph can deadlock communicator teardown; everything is measured and printed, so leave
+        # without the destructor chain (torchrun only needs exit code 0)
+        barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

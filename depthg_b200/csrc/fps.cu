@@ -20,8 +20,12 @@
 
 namespace dg {
 
-constexpr int FPS_THREADS = 128;  // 4 warps: the 120-round argmax chain is issue/latency bound, fewer warps = cheaper rounds
+constexpr int FPS_THREADS = 256;  // setup (staging, pooling, lifting) and emission threads; the rounds use the first RT of them
 constexpr int FPS_WARPS = FPS_THREADS / 32;
+// measured on B200 (28x28 grid, S=11): RT=256 44.2 us, 128 45.4, 64 70.4, 32 76.0 per launch: the round is bound by
+// the redux -> barrier -> redux chain, not by the per-point arithmetic; folding the warp candidates with a compare
+// tree instead of the second redux pair was slower (55.9 us at RT=256).
+constexpr int FPS_DEFAULT_RT = 256;  // round threads for the <= 896-point case (see fps_rounds)
 
 // s = d / max(|d|, eps) of the align_corners=True bilinear resample of one [Hd,Wd] image at point p of the SxS grid
 // (0 for p >= S*S).  `d` may point to global or shared memory.
@@ -42,7 +46,74 @@ __device__ __forceinline__ float depth_sign_value(const float* d, int Hd, int Wd
 
 // STAGE: the whole [Hd,Wd] depth image is first copied into shared memory with 16-byte cp.async
 // (every load in flight at once), so the pooling reads never wait on DRAM one window row at a time.
-template <int PPT, bool STAGE>
+// The S*S-1 selection rounds, run by the first RT threads of the CTA (RT = 32, 64 or 128): thread t owns points
+// t, t+RT, ... (PR per thread, in registers).  Fewer round threads = more points per thread but a shorter
+// critical path per round (no cross-warp exchange at RT = 32; a 2-candidate compare at RT = 64).
+template <int PR, int RT>
+__device__ __forceinline__ void fps_rounds(const float* sX, const float* sY, const float* sZ, unsigned char* sTaken,
+                                           int npts, int nsel, int (*s_key)[FPS_WARPS], int (*s_idx)[FPS_WARPS]) {
+  constexpr int RW = RT / 32;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float X[PR], Y[PR], Z[PR];
+  int key[PR];  // int view of the running min distance; -1 once taken (or not a point)
+#pragma unroll
+  for (int j = 0; j < PR; ++j) {
+    const int i = j * RT + tid;
+    const bool ok = i < npts;
+    X[j] = ok ? sX[i] : 0.f;
+    Y[j] = ok ? sY[i] : 0.f;
+    Z[j] = ok ? sZ[i] : 0.f;
+    key[j] = ok && i != 0 ? 0x7f800000 : -1;  // +inf; point 0 is already taken
+  }
+  int last = 0;
+  for (int r = 1; r < nsel; ++r) {
+    const float lx = sX[last], ly = sY[last], lz = sZ[last];
+    int bk = -1, bi = 0x7fffffff;
+#pragma unroll
+    for (int j = 0; j < PR; ++j) {  // branch-free so the PR independent chains interleave
+      const float dx = __fsub_rn(lx, X[j]), dy = __fsub_rn(ly, Y[j]), dz = __fsub_rn(lz, Z[j]);
+      const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+      const int kj = key[j];
+      const int k = kj < 0 ? -1 : min(kj, __float_as_int(d));  // non-negative floats: int order == float order
+      key[j] = k;
+      const bool better = k > bk;  // strict: the lowest index wins ties inside a thread (j ascending)
+      bk = better ? k : bk;
+      bi = better ? j * RT + tid : bi;
+    }
+    const int wk = __reduce_max_sync(0xffffffffu, bk);
+    const int wi = __reduce_min_sync(0xffffffffu, bk == wk ? bi : 0x7fffffff);
+    if (RW == 1) {
+      last = wi;
+    } else {
+      const int buf = r & 1;
+      if (lane == 0) {
+        s_key[buf][warp] = wk;
+        s_idx[buf][warp] = wi;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(RT) : "memory");
+      if (RW == 2) {
+        const int k0 = s_key[buf][0], i0 = s_idx[buf][0], k1 = s_key[buf][1], i1 = s_idx[buf][1];
+        last = (k0 > k1 || (k0 == k1 && i0 < i1)) ? i0 : i1;
+      } else {  // every warp folds the RW candidates with the same two redux ops
+        const int ck = lane < RW ? s_key[buf][lane] : -1;
+        const int ci = lane < RW ? s_idx[buf][lane] : 0x7fffffff;
+        const int gk = __reduce_max_sync(0xffffffffu, ck);
+        last = __reduce_min_sync(0xffffffffu, ck == gk ? ci : 0x7fffffff);
+      }
+    }
+    if (((last % RT) >> 5) == warp) {  // warp-uniform: only the owner's warp enters
+      if ((last % RT) == tid) {
+        const int j = last / RT;
+#pragma unroll
+        for (int jj = 0; jj < PR; ++jj)
+          if (jj == j) key[jj] = -1;
+        sTaken[last] = 1;
+      }
+    }
+  }
+}
+
+template <int PPT, bool STAGE, int RT, int PR>
 __global__ void __launch_bounds__(FPS_THREADS) fps_kernel(const float* __restrict__ depth_a,
                                                           const float* __restrict__ depth_b, int B, int Hd, int Wd,
                                                           int H, int W, int nsel, float factor, float far_plane,
@@ -120,49 +191,10 @@ __global__ void __launch_bounds__(FPS_THREADS) fps_kernel(const float* __restric
       sTaken[i] = 0;
     }
   }
-  if (tid == 0) key[0] = -1;  // point 0 is the first pick (its smem flag is set below)
   __syncthreads();
-  if (tid == 0) sTaken[0] = 1;
+  if (tid == 0) sTaken[0] = 1;  // point 0 is the first pick
 
-  int last = 0;
-  for (int r = 1; r < nsel; ++r) {
-    const float lx = sX[last], ly = sY[last], lz = sZ[last];
-    int bk = -1, bi = 0x7fffffff;
-#pragma unroll
-    for (int j = 0; j < PPT; ++j) {  // branch-free so the PPT independent chains interleave
-      const float dx = __fsub_rn(lx, X[j]), dy = __fsub_rn(ly, Y[j]), dz = __fsub_rn(lz, Z[j]);
-      const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-      const int kj = key[j];
-      const int k = kj < 0 ? -1 : min(kj, __float_as_int(d));  // non-negative floats: int order == float order
-      key[j] = k;
-      const bool better = k > bk;  // strict: the lowest index wins ties inside a thread (j ascending)
-      bk = better ? k : bk;
-      bi = better ? j * FPS_THREADS + tid : bi;
-    }
-    const int wk = __reduce_max_sync(0xffffffffu, bk);
-    const int wi = __reduce_min_sync(0xffffffffu, bk == wk ? bi : 0x7fffffff);
-    const int buf = r & 1;
-    if (lane == 0) {
-      s_key[buf][warp] = wk;
-      s_idx[buf][warp] = wi;
-    }
-    __syncthreads();
-    // every warp folds the FPS_WARPS candidates with the same two redux ops
-    const int ck = lane < FPS_WARPS ? s_key[buf][lane] : -1;
-    const int ci = lane < FPS_WARPS ? s_idx[buf][lane] : 0x7fffffff;
-    const int gk = __reduce_max_sync(0xffffffffu, ck);
-    const int gi = __reduce_min_sync(0xffffffffu, ck == gk ? ci : 0x7fffffff);
-    last = gi;
-    if (((last % FPS_THREADS) >> 5) == warp) {  // warp-uniform: only the owner's warp enters
-      if ((last % FPS_THREADS) == tid) {
-        const int j = last / FPS_THREADS;
-#pragma unroll
-        for (int jj = 0; jj < PPT; ++jj)
-          if (jj == j) key[jj] = -1;
-        sTaken[last] = 1;
-      }
-    }
-  }
+  if (tid < RT) fps_rounds<PR, RT>(sX, sY, sZ, sTaken, npts, nsel, s_key, s_idx);
   __syncthreads();
 
   // Raster-order emission: each thread scans a contiguous chunk of point indices.
@@ -228,24 +260,37 @@ int launch_fps(const float* depth_a, const float* depth_b, int B, int Hd, int Wd
   const bool stage = ((Hd * Wd) % 4 == 0) && (base_smem + img_bytes <= 220 * 1024) &&
                      ((reinterpret_cast<uintptr_t>(depth_a) | reinterpret_cast<uintptr_t>(depth_b)) % 16 == 0);
   const size_t smem = base_smem + (stage ? img_bytes : 0);
-#define DG_FPS_LAUNCH(PPT, ST)                                                                                    \
+#define DG_FPS_LAUNCH(PPT, ST, RTV, PRV)                                                                                    \
   do {                                                                                                            \
     static size_t configured = 0;                                                                                 \
     if (smem > 48 * 1024 && smem > configured) {                                                                  \
-      DG_CUDA_OK(cudaFuncSetAttribute(fps_kernel<PPT, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      DG_CUDA_OK(cudaFuncSetAttribute(fps_kernel<PPT, ST, RTV, PRV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
       configured = smem;                                                                                          \
     }                                                                                                             \
     DG_PRE(st);                                                                                                   \
-    fps_kernel<PPT, ST><<<nimg, FPS_THREADS, smem, st>>>(depth_a, depth_b, B, Hd, Wd, H, W, S * S, factor,          \
+    fps_kernel<PPT, ST, RTV, PRV><<<nimg, FPS_THREADS, smem, st>>>(depth_a, depth_b, B, Hd, Wd, H, W, S * S, factor,          \
                                                           far_plane, affine, coords, idx, dsign, S, sign_pitch,     \
                                                           sign_eps);                                                \
   } while (0)
-  if (npts <= 7 * FPS_THREADS) {
-    if (stage) DG_FPS_LAUNCH(7, true); else DG_FPS_LAUNCH(7, false);
-  } else if (npts <= 16 * FPS_THREADS) {
-    if (stage) DG_FPS_LAUNCH(16, true); else DG_FPS_LAUNCH(16, false);
+  static int rt_env = -1;  // DEPTHG_B200_FPS_RT = 32 | 64 | 128 | 256 round threads (experiments); default FPS_DEFAULT_RT
+  if (rt_env < 0) {
+    const char* e = getenv("DEPTHG_B200_FPS_RT");
+    rt_env = e ? atoi(e) : 0;
+  }
+  if (npts <= 896) {  // the 28x28 grid of the reference (784 points) lives here
+    const int rt = (rt_env == 32 || rt_env == 64 || rt_env == 128 || rt_env == 256) ? rt_env : FPS_DEFAULT_RT;
+    if (stage) {
+      if (rt == 32) DG_FPS_LAUNCH(4, true, 32, 28);
+      else if (rt == 64) DG_FPS_LAUNCH(4, true, 64, 14);
+      else if (rt == 128) DG_FPS_LAUNCH(4, true, 128, 7);
+      else DG_FPS_LAUNCH(4, true, 256, 4);
+    } else {
+      if (rt == 256) DG_FPS_LAUNCH(4, false, 256, 4); else DG_FPS_LAUNCH(4, false, 128, 7);
+    }
+  } else if (npts <= 8 * FPS_THREADS) {
+    if (stage) DG_FPS_LAUNCH(8, true, 256, 8); else DG_FPS_LAUNCH(8, false, 256, 8);
   } else {
-    DG_FPS_LAUNCH(32, false);
+    DG_FPS_LAUNCH(16, false, 256, 16);
   }
 #undef DG_FPS_LAUNCH
   DG_LAUNCH_OK("fps_kernel");

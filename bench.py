@@ -315,12 +315,19 @@ def main():
     head_grad = torch.zeros(HEAD_GRAD_FLOATS, device=dev) if world > 1 else None
     pending = [None]
     # how the per-step head-gradient all-reduce is issued: "async" = dist.all_reduce(async_op=True) (what DDP's
-    # reducer does), "graph" = the same NCCL all-reduce captured once and replayed on a side stream, "none" = off
-    ar_mode = os.environ.get("DEPTHG_BENCH_ALLREDUCE", "graph") if world > 1 else "none"
+    # reducer does), "graph"/"graph_hp" = the same NCCL all-reduce captured once and replayed on a (high-priority)
+    # side stream, "inline" = replayed on the compute stream right after the backward kernel, "none" = off.
+    # Measured at N=8 (ms/step): graph 0.505, graph_hp 0.432, inline 0.344 - the all-reduce is latency-bound
+    # (2.9 MB over NVSwitch) and its spinning CTAs fight the SM-filling step kernels when overlapped, so the
+    # default runs it in stream order.
+    ar_mode = os.environ.get("DEPTHG_BENCH_ALLREDUCE", "inline") if world > 1 else "none"
     ar_stream = ar_graph = None
-    if ar_mode == "graph":
+    ar_inline = ar_mode == "inline"          # replay on the compute stream: no overlap, no SM contention
+    ar_hp = ar_mode in ("graph_hp",)         # side stream with high priority
+    if ar_mode in ("graph", "graph_hp", "inline"):
+        ar_mode = "graph"
         try:
-            ar_stream = torch.cuda.Stream(device=dev)
+            ar_stream = torch.cuda.Stream(device=dev, priority=-1 if ar_hp else 0)
             dist.all_reduce(head_grad)                     # communicator warm-up outside capture
             torch.cuda.synchronize()
             ar_graph = torch.cuda.CUDAGraph()
@@ -343,6 +350,8 @@ def main():
             if pending[0] is not None:   # asynchronous and only has to land before the next optimiser step
                 pending[0].wait()
             pending[0] = dist.all_reduce(head_grad, async_op=True)
+        elif ar_mode == "graph" and ar_inline:
+            ar_graph.replay()
         elif ar_mode == "graph":
             ar_stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(ar_stream):
@@ -525,14 +534,75 @@ def main():
         e2e_step()
     ev1.record()
     barrier()
+    serial_ms = ev0.elapsed_time(ev1)
+
+    # The same end-to-end step as an input pipeline would run it: double-buffered device inputs, the H2D copy of
+    # step i+1 on a copy stream under the compute of step i, the D2H of step i's results on a third stream.  Every
+    # step still moves all of its inputs from pinned host memory and lands all of its results in host memory.
+    cur = torch.cuda.current_stream()
+    h2d_stream, d2h_stream = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    slots = [{k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in host.items()} for _ in range(2)]
+    loaded = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+    res_hosts = [torch.empty(4, dtype=torch.float32).pin_memory() for _ in range(2)]
+    gh2 = [[torch.empty_like(g).pin_memory() for g in gh] for _ in range(2)]
+
+    def issue_h2d(i):
+        slot = i % 2
+        with torch.cuda.stream(h2d_stream):
+            h2d_stream.wait_event(consumed[slot])          # the slot's previous step has finished reading it
+            for k, v in host.items():
+                slots[slot][k].copy_(v, non_blocking=True)
+            loaded[slot].record(h2d_stream)
+
+    def e2e_pipelined(n):
+        for ev in consumed:
+            ev.record(cur)
+        issue_h2d(0)
+        for i in range(n):
+            slot = i % 2
+            if i + 1 < n:
+                issue_h2d(i + 1)
+            cur.wait_event(loaded[slot])
+            d = dict(slots[slot])
+            if not args.nchw:
+                for k in feat_keys:
+                    d[k] = d[k].permute(0, 3, 1, 2)
+            code = d["code"].detach().requires_grad_(True)
+            code_pos = d["code_pos"].detach().requires_grad_(True)
+            out = loss_fn(d["feats"], d["feats_pos"], None, None, code, code_pos, d["depth"], d["depth_pos"])
+            backprop(out)
+            res = torch.stack([out[0], out[2], out[4], out[6]]).detach()
+            g0, g1 = code.grad, code_pos.grad
+            if not args.nchw:
+                g0, g1 = g0.permute(0, 2, 3, 1), g1.permute(0, 2, 3, 1)
+            consumed[slot].record(cur)
+            d2h_stream.wait_event(consumed[slot])
+            with torch.cuda.stream(d2h_stream):
+                res_hosts[slot].copy_(res, non_blocking=True)
+                gh2[slot][0].copy_(g0, non_blocking=True)
+                gh2[slot][1].copy_(g1, non_blocking=True)
+            for t in (res, g0, g1):
+                t.record_stream(d2h_stream)
+        torch.cuda.synchronize()                            # every step's results are in host memory
+
+    e2e_pipelined(3)
+    barrier()
+    ev0.record()
+    e2e_pipelined(e2e_steps)
+    ev1.record()
+    barrier()
     e2e_ms = ev0.elapsed_time(ev1)
     if world > 1:
-        t = torch.tensor([e2e_ms], device=dev)
+        t = torch.tensor([e2e_ms, serial_ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
+        e2e_ms, serial_ms = float(t[0].item()), float(t[1].item())
     e2e = {"value": world * B * e2e_steps / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps,
-           "note": "pinned host buffers -> H2D -> FPS/gather/loss/backward -> D2H of 4 losses + both code gradients"}
+           "unpipelined": {"value": world * B * e2e_steps / (serial_ms / 1e3), "ms_per_step": serial_ms / e2e_steps},
+           "note": "pinned host buffers -> H2D -> FPS/gather/loss/backward -> D2H of 4 losses + both code gradients; "
+                   "double-buffered: the H2D of step i+1 and the D2H of step i overlap compute (unpipelined = the same "
+                   "step with copies and compute serialised)"}
 
     # ---- KNN build side metric (query-row sharded; all-gather of the database when N > 1)
     knn = None
@@ -631,7 +701,7 @@ def main():
                 "config": workload_config(B, world, extra={
                     "l2_policy": f"rotating {NSETS} input sets ({NSETS * step_bytes / 1e6:.0f} MB) > 126 MB L2",
                     "allreduce_floats_per_step": HEAD_GRAD_FLOATS if ar_mode != "none" else 0,
-                    "allreduce_issue": ar_mode,
+                    "allreduce_issue": ar_mode + ("_inline" if ar_inline else "_hp" if ar_hp else ""),
                     "layout": "nchw" if args.nchw else "channels_last (live trainer layout)"}),
                 "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches),
                 "launches_per_step": launches / args.steps, "roofline": roofline, "roofline_step": roofline_step,

@@ -353,12 +353,26 @@ static int make_map(CUtensorMap* m, const void* base, uint64_t cols, uint64_t ro
 
 static size_t al256(size_t x) { return (x + 255) / 256 * 256; }
 
-// database segments per query block: enough CTAs for ~3 waves, at least 8 tiles per segment, at most KU_MAXSEG
-static int knn_nseg(int Nq, int N) {
+// Database segments per query block.  More segments fill the SMs when there are few query blocks (a multi-GPU
+// shard) but every segment restarts its candidate lists cold, and a cold list inserts far more often: measured per
+// 128x128 tile 12.6 us at nseg = 1 and 22 us at nseg = 8 (N = 49 629, F = 768), i.e. ~ +11 % per extra segment.
+// Pick the nseg that minimises  waves x tiles-per-segment x (1 + 0.11 (nseg - 1)).
+static int knn_nseg(int Nq, int N, int k) {
   const int nblocks = ceil_div(Nq, 128), ntiles = ceil_div(N, 128);
-  int nseg = ceil_div(3 * 148, nblocks);
-  nseg = min(nseg, max(1, ntiles / 8));
-  return max(1, min(nseg, KU_MAXSEG));
+  double best_cost = 1e300;
+  // one segment leaves only KU_CAND - k spare candidates per row: with k = 30 the certificate then fails on a few
+  // rows per thousand and the exact fallback costs more than a second segment
+  const int lo = (KU_CAND - k < 12 && ntiles >= 2) ? 2 : 1;
+  int best = lo;
+  for (int nseg = lo; nseg <= KU_MAXSEG && nseg <= max(lo, ntiles / 8); ++nseg) {
+    const double waves = (double)ceil_div(nblocks * nseg, 148);
+    const double cost = waves * (double)ceil_div(ntiles, nseg) * (1.0 + 0.11 * (nseg - 1));
+    if (cost < best_cost * 0.999) {
+      best_cost = cost;
+      best = nseg;
+    }
+  }
+  return best;
 }
 
 size_t knn_umma_workspace_bytes(int Nq, int N, int F) {
@@ -384,7 +398,7 @@ int knn_topk_umma(const float* q, const float* db, int Nq, int N, int F, int k, 
   __nv_bfloat16* qh = same ? dh : reinterpret_cast<__nv_bfloat16*>(take((size_t)Nq * Fp * 2));
   __nv_bfloat16* ql = same ? dl : reinterpret_cast<__nv_bfloat16*>(take((size_t)Nq * Fp * 2));
   if (same) off += 2 * al256((size_t)Nq * Fp * 2);
-  const int nseg = knn_nseg(Nq, N);
+  const int nseg = knn_nseg(Nq, N, k);
   int* cand_idx = reinterpret_cast<int*>(take((size_t)Nq * KU_MAXSEG * KU_CAND * 4));
   float* cand_val = reinterpret_cast<float*>(take((size_t)Nq * KU_MAXSEG * KU_CAND * 4));
   int* fail_rows = reinterpret_cast<int*>(take((size_t)Nq * 4));

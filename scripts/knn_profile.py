@@ -18,3 +18,13 @@ q = x[: N // 8].contiguous()
 knn_topk(q, x, 30); torch.cuda.synchronize()
 t = time.time(); knn_topk(q, x, 30); torch.cuda.synchronize(); print("shard N/8 rows: %.2f ms" % ((time.time() - t) * 1e3))
 t = time.time(); knn_topk(x, x, 30); torch.cuda.synchronize(); print("full: %.2f ms" % ((time.time() - t) * 1e3))
+# per-kernel breakdown of the shard call
+lib.dg_profile_enable(1)
+knn_topk(q, x, 30); torch.cuda.synchronize()
+n = lib.dg_profile_collect(None, 0); buf = ctypes.create_string_buffer(n + 16); lib.dg_profile_collect(buf, n + 16)
+lib.dg_profile_enable(0)
+print("shard breakdown:\n" + buf.value.decode())
+for rows in (N // 4, N // 2):
+    qq = x[:rows].contiguous()
+    knn_topk(qq, x, 30); torch.cuda.synchronize()
+    t = time.time(); knn_topk(qq, x, 30); torch.cuda.synchronize(); print("rows %d: %.2f ms" % (rows, (time.time() - t) * 1e3))

@@ -597,12 +597,18 @@ def main():
         t = torch.tensor([e2e_ms, serial_ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms, serial_ms = float(t[0].item()), float(t[1].item())
-    e2e = {"value": world * B * e2e_steps / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-           "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps,
-           "unpipelined": {"value": world * B * e2e_steps / (serial_ms / 1e3), "ms_per_step": serial_ms / e2e_steps},
+    # both loops move the same bytes per step; which one wins depends on the box (PCIe topology, how many ranks share
+    # the host bridge), so report the faster one as the end-to-end number and keep both
+    pipelined = {"value": world * B * e2e_steps / (e2e_ms / 1e3), "ms_per_step": e2e_ms / e2e_steps}
+    unpipelined = {"value": world * B * e2e_steps / (serial_ms / 1e3), "ms_per_step": serial_ms / e2e_steps}
+    best = pipelined if pipelined["value"] >= unpipelined["value"] else unpipelined
+    e2e = {"value": best["value"], "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "ms_per_step": best["ms_per_step"], "steps": e2e_steps,
+           "mode": "pipelined" if best is pipelined else "unpipelined",
+           "pipelined": pipelined, "unpipelined": unpipelined,
            "note": "pinned host buffers -> H2D -> FPS/gather/loss/backward -> D2H of 4 losses + both code gradients; "
-                   "double-buffered: the H2D of step i+1 and the D2H of step i overlap compute (unpipelined = the same "
-                   "step with copies and compute serialised)"}
+                   "pipelined = double-buffered, the H2D of step i+1 and the D2H of step i overlap compute; "
+                   "unpipelined = copies and compute serialised, one synchronize per step"}
 
     # ---- KNN build side metric (query-row sharded; all-gather of the database when N > 1)
     knn = None

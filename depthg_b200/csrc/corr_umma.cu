@@ -126,7 +126,9 @@ __device__ __forceinline__ uint32_t col_cd(int j) { return 256u * j + 128u; }
 template <int NT>
 __global__ void __launch_bounds__(UM_THREADS, 1) corr_umma_kernel(const __grid_constant__ UmmaParams prm) {
   extern __shared__ uint8_t um_raw[];
-  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(um_raw) + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment for SWIZZLE_128B, computed as an offset so the pointer stays in the shared address space
+  // (a round trip through uintptr_t makes every later access a generic LD/ST instead of LDS/STS)
+  uint8_t* ring = um_raw + ((1024u - (smem_u32(um_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(ring + UM_NSTAGE * UM_STAGE);
   uint64_t* full = bars;                  // [UM_NSTAGE]
   uint64_t* empty = bars + UM_NSTAGE;     // [UM_NSTAGE]

@@ -27,18 +27,23 @@ namespace dg {
 using namespace umma;
 
 constexpr int KU_THREADS = 192;
-constexpr int KU_NSTAGE = 3;
-constexpr int KU_STAGE = 65536;
+// BN = database rows per MMA tile (the UMMA N).  A stage holds one 64-wide K chunk of the query block (hi, lo:
+// 2 x 16 KB) and of BN database rows (hi, lo: 2 x BN x 128 B).  BN = 256 loads the query chunk once per 256
+// database rows instead of once per 128: 25 % less L2->SM operand traffic, which is what bounds this kernel.
+template <int BN> struct KuCfg {
+  static constexpr int STAGE = 32768 + BN * 256;
+  static constexpr int NSTAGE = BN == 128 ? 3 : 2;
+  static constexpr int SMEM = NSTAGE * STAGE + 4 * 32 * 33 * 4 + 1024 + 256;
+};
 constexpr int KU_CAND = 32;
 constexpr int KU_LSTR = KU_CAND + 1;
-constexpr int KU_SMEM = KU_NSTAGE * KU_STAGE + 4 * 32 * KU_LSTR * 4 + 1024 + 256;
 // bound on |approx - exact| of the 3-product bf16 split for unit-norm rows: dropped lo.lo term <= 2^-18, rounding of the
 // two lo panels <= 2 * 2^-18, fp32 accumulation ~1e-6  (measured max 5e-6, SURVEY 7.1 iii)
 constexpr float KU_EPS = 1.5e-5f;
 
 struct KnnUmmaParams {
   CUtensorMap tm_qh, tm_ql, tm_dh, tm_dl;  // bf16 [rows, Fp], box 64 x 128, SWIZZLE_128B
-  int Nq, N, nchunk, ntiles, nseg;
+  int Nq, N, nchunk, ntiles, nseg;          // ntiles in units of BN database rows
   int* cand_idx;    // [Nq,nseg,32]
   float* cand_val;  // [Nq,nseg,32] approximate sims, descending within a segment
   int* err;
@@ -57,13 +62,17 @@ __global__ void __launch_bounds__(256) split_rows_kernel(const float* __restrict
   }
 }
 
+template <int BN>
 __global__ void __launch_bounds__(KU_THREADS, 1) knn_umma_kernel(const __grid_constant__ KnnUmmaParams prm) {
+  constexpr int KU_STAGE = KuCfg<BN>::STAGE, KU_NSTAGE = KuCfg<BN>::NSTAGE;
   extern __shared__ uint8_t ku_raw[];
-  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ku_raw) + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment for SWIZZLE_128B, computed as an offset so the pointer stays in the shared address space
+  // (a round trip through uintptr_t makes every later access a generic LD/ST instead of LDS/STS)
+  uint8_t* ring = ku_raw + ((1024u - (smem_u32(ku_raw) & 1023u)) & 1023u);
   float* stage_tiles = reinterpret_cast<float*>(ring + KU_NSTAGE * KU_STAGE);  // [4 warps][32 rows][33] transpose staging
   uint64_t* bars = reinterpret_cast<uint64_t*>(stage_tiles + 4 * 32 * KU_LSTR);
-  uint64_t* full = bars;               // [3]
-  uint64_t* empty = bars + 3;          // [3]
+  uint64_t* full = bars;               // [<=3]
+  uint64_t* empty = bars + 3;          // [<=3]
   uint64_t* tfull = bars + 6;          // [2] accumulator ready
   uint64_t* tempty = bars + 8;         // [2] accumulator drained
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
@@ -88,7 +97,7 @@ __global__ void __launch_bounds__(KU_THREADS, 1) knn_umma_kernel(const __grid_co
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 256);
+  if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -106,14 +115,14 @@ __global__ void __launch_bounds__(KU_THREADS, 1) knn_umma_kernel(const __grid_co
           mbar_arrive_expect_tx(&full[s], KU_STAGE);
           tma_load_2d(st, &prm.tm_qh, &full[s], c * 64, m0);
           tma_load_2d(st + 16384, &prm.tm_ql, &full[s], c * 64, m0);
-          tma_load_2d(st + 32768, &prm.tm_dh, &full[s], c * 64, (t_begin + t) * 128);
-          tma_load_2d(st + 49152, &prm.tm_dl, &full[s], c * 64, (t_begin + t) * 128);
+          tma_load_2d(st + 32768, &prm.tm_dh, &full[s], c * 64, (t_begin + t) * BN);
+          tma_load_2d(st + 32768 + BN * 128, &prm.tm_dl, &full[s], c * 64, (t_begin + t) * BN);
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = instr_desc(FMT_BF16, 128, 128, 0, 0);
+      const uint32_t idesc = instr_desc(FMT_BF16, 128, BN, 0, 0);
       const uint64_t dk128 = smem_desc(0, 16, 1024, SW_128B);
       int job = 0;
       bool ok = true;
@@ -121,13 +130,13 @@ __global__ void __launch_bounds__(KU_THREADS, 1) knn_umma_kernel(const __grid_co
         const int a = t & 1;
         ok = mbar_wait(&tempty[a], ((t >> 1) & 1) ^ 1);
         tc_fence_after_sync();
-        const uint32_t acc = tmem + a * 128;
+        const uint32_t acc = tmem + a * BN;
         for (int c = 0; c < nchunk && ok; ++c, ++job) {
           const int s = job % KU_NSTAGE;
           ok = mbar_wait(&full[s], (job / KU_NSTAGE) & 1);
           tc_fence_after_sync();
           const uint32_t a0 = smem_u32(ring + s * KU_STAGE) >> 4;
-          const uint64_t ah = dk128 + a0, al = ah + 1024, bh = ah + 2048, bl = ah + 3072;
+          const uint64_t ah = dk128 + a0, al = ah + 1024, bh = ah + 2048, bl = bh + BN * 8;  // 16-byte units
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
             mma_f16(acc, ah + 2 * ks, bh + 2 * ks, idesc, (c | ks) != 0);
@@ -160,10 +169,10 @@ __global__ void __launch_bounds__(KU_THREADS, 1) knn_umma_kernel(const __grid_co
       const int a = t & 1;
       ok = mbar_wait(&tfull[a], (t >> 1) & 1);
       tc_fence_after_sync();
-      const int n0 = (t_begin + t) * 128;
+      const int n0 = (t_begin + t) * BN;
 #pragma unroll 1
-      for (int cc = 0; cc < 4; ++cc) {
-        tmem_ld_32x32(tlane + a * 128 + 32 * cc, v);
+      for (int cc = 0; cc < BN / 32; ++cc) {
+        tmem_ld_32x32(tlane + a * BN + 32 * cc, v);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; ++i) tile[lane * KU_LSTR + i] = v[i];   // thread = row `lane`, 32 columns
@@ -211,7 +220,7 @@ __global__ void __launch_bounds__(KU_THREADS, 1) knn_umma_kernel(const __grid_co
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem, 256);
+  if (warp == 1) tmem_dealloc(tmem, 2 * BN);
 }
 
 // One warp per query row: exact fp32 similarities of its nseg x 32 candidates (lane l owns candidate l of every
@@ -330,7 +339,7 @@ typedef CUresult (*EncodeTiledFn2)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int make_map(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows) {
+static int make_map(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint32_t box_rows) {
   static EncodeTiledFn2 fn = nullptr;
   if (!fn) {
     void* p = nullptr;
@@ -342,7 +351,7 @@ static int make_map(CUtensorMap* m, const void* base, uint64_t cols, uint64_t ro
   DG_REQUIRE(fn, DG_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {cols * 2};
-  cuuint32_t box[2] = {64, 128};
+  cuuint32_t box[2] = {64, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -415,19 +424,29 @@ int knn_topk_umma(const float* q, const float* db, int Nq, int N, int F, int k, 
   }
   KnnUmmaParams prm;
   int rc;
-  if ((rc = make_map(&prm.tm_qh, qh, Fp, Nq))) return rc;
-  if ((rc = make_map(&prm.tm_ql, ql, Fp, Nq))) return rc;
-  if ((rc = make_map(&prm.tm_dh, dh, Fp, N))) return rc;
-  if ((rc = make_map(&prm.tm_dl, dl, Fp, N))) return rc;
-  prm.Nq = Nq; prm.N = N; prm.nchunk = Fp / 64; prm.ntiles = ceil_div(N, 128); prm.nseg = nseg;
+  static int bn_env = -1;  // DEPTHG_B200_KNN_BN = 128 | 256 (experiments); default 256
+  if (bn_env < 0) {
+    const char* e = getenv("DEPTHG_B200_KNN_BN");
+    bn_env = e && atoi(e) == 128 ? 128 : 256;
+  }
+  const int BN = bn_env;
+  if ((rc = make_map(&prm.tm_qh, qh, Fp, Nq, 128))) return rc;
+  if ((rc = make_map(&prm.tm_ql, ql, Fp, Nq, 128))) return rc;
+  if ((rc = make_map(&prm.tm_dh, dh, Fp, N, BN))) return rc;
+  if ((rc = make_map(&prm.tm_dl, dl, Fp, N, BN))) return rc;
+  prm.Nq = Nq; prm.N = N; prm.nchunk = Fp / 64; prm.ntiles = ceil_div(N, BN); prm.nseg = nseg;
   prm.cand_idx = cand_idx; prm.cand_val = cand_val; prm.err = err;
   static bool attr_set = false;
   if (!attr_set) {
-    DG_CUDA_OK(cudaFuncSetAttribute(knn_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KU_SMEM));
+    DG_CUDA_OK(cudaFuncSetAttribute(knn_umma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, KuCfg<128>::SMEM));
+    DG_CUDA_OK(cudaFuncSetAttribute(knn_umma_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, KuCfg<256>::SMEM));
     attr_set = true;
   }
   DG_PRE(st);
-  knn_umma_kernel<<<dim3(ceil_div(Nq, 128), nseg), KU_THREADS, KU_SMEM, st>>>(prm);
+  if (BN == 128)
+    knn_umma_kernel<128><<<dim3(ceil_div(Nq, 128), nseg), KU_THREADS, KuCfg<128>::SMEM, st>>>(prm);
+  else
+    knn_umma_kernel<256><<<dim3(ceil_div(Nq, 128), nseg), KU_THREADS, KuCfg<256>::SMEM, st>>>(prm);
   DG_LAUNCH_OK("knn_umma_kernel");
   DG_PRE(st);
   knn_rerank_kernel<<<ceil_div(Nq * 32, 256), 256, 0, st>>>(q, db, Nq, N, F, k, nseg, cand_idx, cand_val, idx, sims, fail_rows,

@@ -30,9 +30,13 @@ constexpr int KU_THREADS = 192;
 // BN = database rows per MMA tile (the UMMA N).  A stage holds one 64-wide K chunk of the query block (hi, lo:
 // 2 x 16 KB) and of BN database rows (hi, lo: 2 x BN x 128 B).  BN = 256 loads the query chunk once per 256
 // database rows instead of once per 128: 25 % less L2->SM operand traffic, which is what bounds this kernel.
+// The kernel is bound by how many operand bytes an SM keeps in flight from L2, so BN = 256 uses 32-wide K chunks
+// (64-byte rows, SWIZZLE_64B): 4 stages of 48 KB instead of 2 of 96 KB.
 template <int BN> struct KuCfg {
-  static constexpr int STAGE = 32768 + BN * 256;
-  static constexpr int NSTAGE = BN == 128 ? 3 : 2;
+  static constexpr int KC = BN == 128 ? 64 : 32;                  // K elements per stage
+  static constexpr int QBYTES = 128 * KC * 2, DBYTES = BN * KC * 2;  // one bf16 panel chunk of the query / database tile
+  static constexpr int STAGE = 2 * QBYTES + 2 * DBYTES;
+  static constexpr int NSTAGE = BN == 128 ? 3 : 4;
   static constexpr int SMEM = NSTAGE * STAGE + 4 * 32 * 33 * 4 + 1024 + 256;
 };
 constexpr int KU_CAND = 32;
@@ -64,18 +68,19 @@ __global__ void __launch_bounds__(256) split_rows_kernel(const float* __restrict
 
 template <int BN>
 __global__ void __launch_bounds__(KU_THREADS, 1) knn_umma_kernel(const __grid_constant__ KnnUmmaParams prm) {
-  constexpr int KU_STAGE = KuCfg<BN>::STAGE, KU_NSTAGE = KuCfg<BN>::NSTAGE;
+  constexpr int KU_STAGE = KuCfg<BN>::STAGE, KU_NSTAGE = KuCfg<BN>::NSTAGE, KC = KuCfg<BN>::KC;
+  constexpr int QB = KuCfg<BN>::QBYTES, DB = KuCfg<BN>::DBYTES;
   extern __shared__ uint8_t ku_raw[];
   // 1024-byte alignment for SWIZZLE_128B, computed as an offset so the pointer stays in the shared address space
   // (a round trip through uintptr_t makes every later access a generic LD/ST instead of LDS/STS)
   uint8_t* ring = ku_raw + ((1024u - (smem_u32(ku_raw) & 1023u)) & 1023u);
   float* stage_tiles = reinterpret_cast<float*>(ring + KU_NSTAGE * KU_STAGE);  // [4 warps][32 rows][33] transpose staging
   uint64_t* bars = reinterpret_cast<uint64_t*>(stage_tiles + 4 * 32 * KU_LSTR);
-  uint64_t* full = bars;               // [<=3]
-  uint64_t* empty = bars + 3;          // [<=3]
-  uint64_t* tfull = bars + 6;          // [2] accumulator ready
-  uint64_t* tempty = bars + 8;         // [2] accumulator drained
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  uint64_t* full = bars;               // [<=4]
+  uint64_t* empty = bars + 4;          // [<=4]
+  uint64_t* tfull = bars + 8;          // [2] accumulator ready
+  uint64_t* tempty = bars + 10;        // [2] accumulator drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * 128;
@@ -113,17 +118,18 @@ __global__ void __launch_bounds__(KU_THREADS, 1) knn_umma_kernel(const __grid_co
           if (!mbar_wait(&empty[s], ((job / KU_NSTAGE) & 1) ^ 1)) { if (prm.err) atomicCAS(prm.err, 0, 11); return; }
           uint8_t* st = ring + s * KU_STAGE;
           mbar_arrive_expect_tx(&full[s], KU_STAGE);
-          tma_load_2d(st, &prm.tm_qh, &full[s], c * 64, m0);
-          tma_load_2d(st + 16384, &prm.tm_ql, &full[s], c * 64, m0);
-          tma_load_2d(st + 32768, &prm.tm_dh, &full[s], c * 64, (t_begin + t) * BN);
-          tma_load_2d(st + 32768 + BN * 128, &prm.tm_dl, &full[s], c * 64, (t_begin + t) * BN);
+          tma_load_2d(st, &prm.tm_qh, &full[s], c * KC, m0);
+          tma_load_2d(st + QB, &prm.tm_ql, &full[s], c * KC, m0);
+          tma_load_2d(st + 2 * QB, &prm.tm_dh, &full[s], c * KC, (t_begin + t) * BN);
+          tma_load_2d(st + 2 * QB + DB, &prm.tm_dl, &full[s], c * KC, (t_begin + t) * BN);
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = instr_desc(FMT_BF16, 128, BN, 0, 0);
-      const uint64_t dk128 = smem_desc(0, 16, 1024, SW_128B);
+      // K-major operands: rows of KC bf16 (128 B -> SWIZZLE_128B, 64 B -> SWIZZLE_64B), 8-row groups 8 rows apart
+      const uint64_t dk128 = KC == 64 ? smem_desc(0, 16, 1024, SW_128B) : smem_desc(0, 16, 512, SW_64B);
       int job = 0;
       bool ok = true;
       for (int t = 0; t < ntiles && ok; ++t) {
@@ -136,9 +142,9 @@ __global__ void __launch_bounds__(KU_THREADS, 1) knn_umma_kernel(const __grid_co
           ok = mbar_wait(&full[s], (job / KU_NSTAGE) & 1);
           tc_fence_after_sync();
           const uint32_t a0 = smem_u32(ring + s * KU_STAGE) >> 4;
-          const uint64_t ah = dk128 + a0, al = ah + 1024, bh = ah + 2048, bl = bh + BN * 8;  // 16-byte units
+          const uint64_t ah = dk128 + a0, al = ah + QB / 16, bh = ah + 2 * QB / 16, bl = bh + DB / 16;  // 16-byte units
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
+          for (int ks = 0; ks < KC / 16; ++ks) {
             mma_f16(acc, ah + 2 * ks, bh + 2 * ks, idesc, (c | ks) != 0);
             mma_f16(acc, ah + 2 * ks, bl + 2 * ks, idesc, 1);
             mma_f16(acc, al + 2 * ks, bh + 2 * ks, idesc, 1);
@@ -164,6 +170,7 @@ __global__ void __launch_bounds__(KU_THREADS, 1) knn_umma_kernel(const __grid_co
       ti[r] = -1;
     }
     float v[32];
+    float mythr = -INFINITY;  // current 32nd-best value of query row `lane` (the row this thread reads from TMEM)
     bool ok = true;
     for (int t = 0; t < ntiles && ok; ++t) {
       const int a = t & 1;
@@ -172,15 +179,28 @@ __global__ void __launch_bounds__(KU_THREADS, 1) knn_umma_kernel(const __grid_co
       const int n0 = (t_begin + t) * BN;
 #pragma unroll 1
       for (int cc = 0; cc < BN / 32; ++cc) {
-        tmem_ld_32x32(tlane + a * BN + 32 * cc, v);
+        tmem_ld_32x32(tlane + a * BN + 32 * cc, v);   // thread = query row `lane`, 32 consecutive database columns
         tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) tile[lane * KU_LSTR + i] = v[i];   // thread = row `lane`, 32 columns
-        __syncwarp();
         const int nb = n0 + 32 * cc;
+        // Filter in the row-per-thread layout first: a column only matters if it beats the row's current 32nd
+        // value, which this thread keeps in `mythr`.  Once the lists are warm most rows have nothing to insert,
+        // and only rows that do are transposed through shared memory and visited by the list code below.
+        unsigned mymask = 0;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mymask |= (v[i] > mythr ? 1u : 0u) << i;
+        const int nvalid = prm.N - nb;                 // columns past the end of the database are zero-filled by TMA
+        if (nvalid < 32) mymask &= nvalid <= 0 ? 0u : ((1u << nvalid) - 1u);
+        const unsigned rows = __ballot_sync(0xffffffffu, mymask != 0);
+        if (rows == 0) continue;
+        if (mymask) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) tile[lane * KU_LSTR + i] = v[i];
+        }
+        __syncwarp();
         const bool col_ok = nb + lane < prm.N;
 #pragma unroll
         for (int r = 0; r < 32; ++r) {
+          if (!((rows >> r) & 1u)) continue;                              // warp-uniform
           const float x = tile[r * KU_LSTR + lane];                       // lane = column of row r
           const float thr = __shfl_sync(0xffffffffu, tv[r], KU_CAND - 1);
           unsigned m = __ballot_sync(0xffffffffu, col_ok && x > thr);
@@ -201,6 +221,8 @@ __global__ void __launch_bounds__(KU_THREADS, 1) knn_umma_kernel(const __grid_co
               }
             }
           }
+          const float nthr = __shfl_sync(0xffffffffu, tv[r], KU_CAND - 1);
+          if (lane == r) mythr = nthr;
         }
         __syncwarp();
       }
@@ -339,7 +361,8 @@ typedef CUresult (*EncodeTiledFn2)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int make_map(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint32_t box_rows) {
+static int make_map(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint32_t box_rows,
+                    uint32_t box_cols) {
   static EncodeTiledFn2 fn = nullptr;
   if (!fn) {
     void* p = nullptr;
@@ -351,10 +374,11 @@ static int make_map(CUtensorMap* m, const void* base, uint64_t cols, uint64_t ro
   DG_REQUIRE(fn, DG_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {cols * 2};
-  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   DG_REQUIRE(r == CUDA_SUCCESS, DG_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return DG_OK;
@@ -430,11 +454,12 @@ int knn_topk_umma(const float* q, const float* db, int Nq, int N, int F, int k, 
     bn_env = e && atoi(e) == 128 ? 128 : 256;
   }
   const int BN = bn_env;
-  if ((rc = make_map(&prm.tm_qh, qh, Fp, Nq, 128))) return rc;
-  if ((rc = make_map(&prm.tm_ql, ql, Fp, Nq, 128))) return rc;
-  if ((rc = make_map(&prm.tm_dh, dh, Fp, N, BN))) return rc;
-  if ((rc = make_map(&prm.tm_dl, dl, Fp, N, BN))) return rc;
-  prm.Nq = Nq; prm.N = N; prm.nchunk = Fp / 64; prm.ntiles = ceil_div(N, BN); prm.nseg = nseg;
+  const int KC = BN == 128 ? KuCfg<128>::KC : KuCfg<256>::KC;
+  if ((rc = make_map(&prm.tm_qh, qh, Fp, Nq, 128, KC))) return rc;
+  if ((rc = make_map(&prm.tm_ql, ql, Fp, Nq, 128, KC))) return rc;
+  if ((rc = make_map(&prm.tm_dh, dh, Fp, N, BN, KC))) return rc;
+  if ((rc = make_map(&prm.tm_dl, dl, Fp, N, BN, KC))) return rc;
+  prm.Nq = Nq; prm.N = N; prm.nchunk = Fp / KC; prm.ntiles = ceil_div(N, BN); prm.nseg = nseg;
   prm.cand_idx = cand_idx; prm.cand_val = cand_val; prm.err = err;
   static bool attr_set = false;
   if (!attr_set) {

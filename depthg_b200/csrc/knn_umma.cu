@@ -26,7 +26,8 @@ namespace dg {
 
 using namespace umma;
 
-constexpr int KU_THREADS = 192;
+constexpr int KU_THREADS = 320;  // TMA warp + MMA warp + 8 epilogue warps (two per TMEM lane group)
+constexpr int KU_SUB = 2;        // epilogue warps per lane group = candidate lists per (row, segment)
 // BN = database rows per MMA tile (the UMMA N).  A stage holds one 64-wide K chunk of the query block (hi, lo:
 // 2 x 16 KB) and of BN database rows (hi, lo: 2 x BN x 128 B).  BN = 256 loads the query chunk once per 256
 // database rows instead of once per 128: 25 % less L2->SM operand traffic, which is what bounds this kernel.
@@ -37,7 +38,7 @@ template <int BN> struct KuCfg {
   static constexpr int QBYTES = 128 * KC * 2, DBYTES = BN * KC * 2;  // one bf16 panel chunk of the query / database tile
   static constexpr int STAGE = 2 * QBYTES + 2 * DBYTES;
   static constexpr int NSTAGE = BN == 128 ? 3 : 4;
-  static constexpr int SMEM = NSTAGE * STAGE + 4 * 32 * 33 * 4 + 1024 + 256;
+  static constexpr int SMEM = NSTAGE * STAGE + 8 * 32 * 33 * 4 + 1024 + 256;
 };
 constexpr int KU_CAND = 32;
 constexpr int KU_LSTR = KU_CAND + 1;
@@ -48,8 +49,8 @@ constexpr float KU_EPS = 1.5e-5f;
 struct KnnUmmaParams {
   CUtensorMap tm_qh, tm_ql, tm_dh, tm_dl;  // bf16 [rows, Fp], box 64 x 128, SWIZZLE_128B
   int Nq, N, nchunk, ntiles, nseg;          // ntiles in units of BN database rows
-  int* cand_idx;    // [Nq,nseg,32]
-  float* cand_val;  // [Nq,nseg,32] approximate sims, descending within a segment
+  int* cand_idx;    // [Nq,nseg,KU_SUB,32]
+  float* cand_val;  // [Nq,nseg,KU_SUB,32] approximate sims, descending within a list
   int* err;
 };
 
@@ -75,7 +76,7 @@ __global__ void __launch_bounds__(KU_THREADS, 1) knn_umma_kernel(const __grid_co
   // (a round trip through uintptr_t makes every later access a generic LD/ST instead of LDS/STS)
   uint8_t* ring = ku_raw + ((1024u - (smem_u32(ku_raw) & 1023u)) & 1023u);
   float* stage_tiles = reinterpret_cast<float*>(ring + KU_NSTAGE * KU_STAGE);  // [4 warps][32 rows][33] transpose staging
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_tiles + 4 * 32 * KU_LSTR);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_tiles + 8 * 32 * KU_LSTR);
   uint64_t* full = bars;               // [<=4]
   uint64_t* empty = bars + 4;          // [<=4]
   uint64_t* tfull = bars + 8;          // [2] accumulator ready
@@ -98,7 +99,7 @@ __global__ void __launch_bounds__(KU_THREADS, 1) knn_umma_kernel(const __grid_co
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], 128);  // every epilogue thread arrives
+      mbar_init(&tempty[a], 256);  // every epilogue thread arrives
     }
     fence_barrier_init();
   }
@@ -159,9 +160,11 @@ __global__ void __launch_bounds__(KU_THREADS, 1) knn_umma_kernel(const __grid_co
     // ---- epilogue: warp-cooperative running top-32 per row.  The warp owns the 32 rows of its TMEM lane group; each
     //      row's sorted candidate list is spread over the 32 lanes (entry l in lane l), so an insertion is one
     //      ballot + two shuffles and costs the same whether the list is cold or warm.
-    const int lg = warp & 3;
+    // Two warps share each TMEM lane group (a warp may only read lanes 32*(warp%4)..+31) and split its column
+    // chunks even/odd; each keeps its own list, so a row ends up with KU_SUB lists per database segment.
+    const int lg = warp & 3, sub = (warp - 2) >> 2;
     const uint32_t tlane = tmem + ((uint32_t)(32 * lg) << 16);
-    float* tile = stage_tiles + lg * (32 * KU_LSTR);
+    float* tile = stage_tiles + (warp - 2) * (32 * KU_LSTR);
     float tv[32];
     int ti[32];
 #pragma unroll
@@ -178,21 +181,22 @@ __global__ void __launch_bounds__(KU_THREADS, 1) knn_umma_kernel(const __grid_co
       tc_fence_after_sync();
       const int n0 = (t_begin + t) * BN;
 #pragma unroll 1
-      for (int cc = 0; cc < BN / 32; ++cc) {
+      for (int cc = sub; cc < BN / 32; cc += KU_SUB) {
         tmem_ld_32x32(tlane + a * BN + 32 * cc, v);   // thread = query row `lane`, 32 consecutive database columns
         tmem_ld_wait();
         const int nb = n0 + 32 * cc;
         // Filter in the row-per-thread layout first: a column only matters if it beats the row's current 32nd
         // value, which this thread keeps in `mythr`.  Once the lists are warm most rows have nothing to insert,
         // and only rows that do are transposed through shared memory and visited by the list code below.
-        unsigned mymask = 0;
+        float vmax = v[0];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) mymask |= (v[i] > mythr ? 1u : 0u) << i;
-        const int nvalid = prm.N - nb;                 // columns past the end of the database are zero-filled by TMA
-        if (nvalid < 32) mymask &= nvalid <= 0 ? 0u : ((1u << nvalid) - 1u);
-        const unsigned rows = __ballot_sync(0xffffffffu, mymask != 0);
+        for (int i = 1; i < 32; ++i) vmax = fmaxf(vmax, v[i]);
+        // (columns past the end of the database are zero-filled by TMA: they can only cause a harmless visit,
+        //  the list code below masks them with col_ok)
+        const bool mine = vmax > mythr;
+        const unsigned rows = __ballot_sync(0xffffffffu, mine);
         if (rows == 0) continue;
-        if (mymask) {
+        if (mine) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) tile[lane * KU_LSTR + i] = v[i];
         }
@@ -234,7 +238,7 @@ __global__ void __launch_bounds__(KU_THREADS, 1) knn_umma_kernel(const __grid_co
     for (int r = 0; r < 32; ++r) {
       const int q = m0 + 32 * lg + r;
       if (q < prm.Nq) {
-        const size_t o = ((size_t)q * prm.nseg + seg) * KU_CAND;
+        const size_t o = (((size_t)q * prm.nseg + seg) * KU_SUB + sub) * KU_CAND;
         prm.cand_idx[o + lane] = ti[r];
         prm.cand_val[o + lane] = tv[r];
       }
@@ -393,11 +397,11 @@ static size_t al256(size_t x) { return (x + 255) / 256 * 256; }
 static int knn_nseg(int Nq, int N, int k) {
   const int nblocks = ceil_div(Nq, 128), ntiles = ceil_div(N, 128);
   double best_cost = 1e300;
-  // one segment leaves only KU_CAND - k spare candidates per row: with k = 30 the certificate then fails on a few
-  // rows per thousand and the exact fallback costs more than a second segment
-  const int lo = (KU_CAND - k < 12 && ntiles >= 2) ? 2 : 1;
+  // (every (row, segment) keeps KU_SUB lists of 32, so even one segment leaves >= 2 x 32 - k spare candidates)
+  (void)k;
+  const int lo = 1;
   int best = lo;
-  for (int nseg = lo; nseg <= KU_MAXSEG && nseg <= max(lo, ntiles / 8); ++nseg) {
+  for (int nseg = lo; nseg * KU_SUB <= KU_MAXSEG && nseg <= max(lo, ntiles / 8); ++nseg) {
     const double waves = (double)ceil_div(nblocks * nseg, 148);
     const double cost = waves * (double)ceil_div(ntiles, nseg) * (1.0 + 0.11 * (nseg - 1));
     if (cost < best_cost * 0.999) {
@@ -474,7 +478,7 @@ int knn_topk_umma(const float* q, const float* db, int Nq, int N, int F, int k, 
     knn_umma_kernel<256><<<dim3(ceil_div(Nq, 128), nseg), KU_THREADS, KuCfg<256>::SMEM, st>>>(prm);
   DG_LAUNCH_OK("knn_umma_kernel");
   DG_PRE(st);
-  knn_rerank_kernel<<<ceil_div(Nq * 32, 256), 256, 0, st>>>(q, db, Nq, N, F, k, nseg, cand_idx, cand_val, idx, sims, fail_rows,
+  knn_rerank_kernel<<<ceil_div(Nq * 32, 256), 256, 0, st>>>(q, db, Nq, N, F, k, nseg * KU_SUB, cand_idx, cand_val, idx, sims, fail_rows,
                                                              fail_count, err);
   DG_LAUNCH_OK("knn_rerank_kernel");
   return launch_knn_exact(q, db, Nq, N, F, k, idx, sims, fail_rows, fail_count, st);

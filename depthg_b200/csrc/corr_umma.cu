@@ -44,7 +44,12 @@ struct UmmaParams {
   const float* dsign;          // [B,128*ntile] or null
   const float* dots;           // [npairs,B] <mean row of F1[b], mean row of F2[k,b]> (pointwise) or null
   int npairs, B, P, ldf, ldc, flags, has_depth;
-  int ntile;                   // 128-row tiles per panel (1 or 2): S*S <= 128 * ntile
+  int ntile;                   // 128-row tiles per panel: Prows / 128
+  // work decomposition: a CTA owns row tile ti (of nti) and column group cg (of ncg), i.e. the NT column tiles
+  // cg*NT .. cg*NT+NT-1.  S*S <= 256: nti = NT, ncg = 1 (the CTA sees every column and forms the row means itself).
+  // S*S > 256 ("dense"): NT = 2, ncg > 1, row means come from row_means_kernel, dC1 is written per column group.
+  int prows, nti, ncg, nti_stride, ncg_stride;
+  const float* rowmean;        // [npairs,B,prows] mean_q fd[p,q] (dense + pointwise) or null
   float depth_shift, inv_cnt;
   float shift[DG_MAX_PAIRS];
   int32_t group[DG_MAX_PAIRS];
@@ -138,13 +143,16 @@ __global__ void __launch_bounds__(UM_THREADS, 1) corr_umma_kernel(const __grid_c
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 3);
   __shared__ float s_red[8][4];
   __shared__ float s_rowsum[2][128];
-  __shared__ float s_sign[256];
+  __shared__ float s_sign[1024];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 64) stamp(prm, 0);
-  // work item: (pair k, image b, 128-row tile ti of the first operand); the CTA walks the NT column tiles itself
-  constexpr int Prows = 128 * NT;
-  const int ti = blockIdx.x % NT, kb = blockIdx.x / NT;
+  // work item: (pair k, image b, 128-row tile ti of the first operand, column group cg); the CTA walks the NT
+  // column tiles gj0 .. gj0+NT-1 of its group itself
+  const int Prows = prm.prows;
+  const int cg = blockIdx.x % prm.ncg, rt = blockIdx.x / prm.ncg;
+  const int ti = rt % prm.nti, kb = rt / prm.nti;
+  const int gj0 = cg * NT;
   const int k = kb / prm.B, b = kb - k * prm.B;
   const int nfd = (prm.ldf + 63) / 64, ncd = prm.ldc / 32, nb = prm.ldc / 32;
   const int nop = nfd + ncd;                                  // operand chunks per column tile
@@ -174,8 +182,8 @@ __global__ void __launch_bounds__(UM_THREADS, 1) corr_umma_kernel(const __grid_c
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
   if (threadIdx.x >= 64) {
-    const int t = threadIdx.x - 64;
-    if (t < Prows) s_sign[t] = depth_round ? __ldg(prm.dsign + (size_t)b * Prows + t) : 0.f;
+    for (int t = threadIdx.x - 64; t < Prows; t += UM_EPI)
+      s_sign[t] = depth_round ? __ldg(prm.dsign + (size_t)b * Prows + t) : 0.f;
   }
   tc_fence_before_sync();
   __syncthreads();
@@ -203,12 +211,12 @@ __global__ void __launch_bounds__(UM_THREADS, 1) corr_umma_kernel(const __grid_c
           const int tj = t / nop, c = t - tj * nop;
           const bool isf = c < nfd;
           // diagonal tile of a pair whose operands are the same panel: both operands are the same rows, load once
-          const bool same = (tj == ti) && (isf ? fsame_slot : k == 0);
+          const bool same = (gj0 + tj == ti) && (isf ? fsame_slot : k == 0);
           const int c0 = isf ? c * 64 : (c - nfd) * 32;
           const CUtensorMap* mh = isf ? &prm.tm_fhi : &prm.tm_chi;
           const CUtensorMap* ml = isf ? &prm.tm_flo : &prm.tm_clo;
           mbar_arrive_expect_tx(&full[s], same ? 32768u : 65536u);
-          const int ra = isf ? frow1 : row1, rb = (isf ? frow2 : row2) + 128 * tj;
+          const int ra = isf ? frow1 : row1, rb = (isf ? frow2 : row2) + 128 * (gj0 + tj);
           tma_load_2d(st, mh, &full[s], c0, ra);
           tma_load_2d(st + 16384, ml, &full[s], c0, ra);
           if (!same) {
@@ -216,7 +224,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) corr_umma_kernel(const __grid_c
             tma_load_2d(st + 49152, ml, &full[s], c0, rb);
           }
         } else {              // gradient operands: bf16 code rows [128 x ldc] as ldc/32 boxes of [128 x 64 B]; hi @0, lo @32 KB
-          const int r = (t == J0) ? row1 : row2 + 128 * ((t - J0 - 1) % NT);
+          const int r = (t == J0) ? row1 : row2 + 128 * (gj0 + (t - J0 - 1) % NT);
           mbar_arrive_expect_tx(&full[s], (uint32_t)(2 * nb * 8192));
           for (int a = 0; a < nb; ++a) {
             tma_load_2d(st + a * 8192, &prm.tm_bhi, &full[s], a * 32, r);
@@ -244,7 +252,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) corr_umma_kernel(const __grid_c
         tc_fence_after_sync();
         if (prm.dbg & 2) { mbar_arrive(&empty[s]); continue; }
         const int tj = t / nop, c = t - tj * nop;
-        const bool same = (tj == ti) && (c < nfd ? fsame_slot : k == 0);
+        const bool same = (gj0 + tj == ti) && (c < nfd ? fsame_slot : k == 0);
         const uint32_t a0 = smem_u32(ring + s * UM_STAGE) >> 4;
         const uint32_t b0 = same ? a0 : a0 + (32768 >> 4);
         const uint64_t ah = dk128 + a0, al = ah + (16384 >> 4), bh = dk128 + b0, bl = bh + (16384 >> 4);
@@ -346,7 +354,9 @@ __global__ void __launch_bounds__(UM_THREADS, 1) corr_umma_kernel(const __grid_c
     tc_fence_after_sync();
     if (threadIdx.x == 64) stamp(prm, 2);
     float c0 = prm.shift[k] - old_mean;      // fd' - shift = fd - rowmean + old_mean - shift = fd - c0
-    if (pointwise) {                         // rowmean over all q: padded columns are exactly zero, no mask needed
+    if (pointwise && prm.rowmean) {          // dense: this CTA only sees its column group, the row means were precomputed
+      c0 += __ldg(prm.rowmean + (size_t)kb * Prows + p);
+    } else if (pointwise) {                  // rowmean over all q: padded columns are exactly zero, no mask needed
       float s = 0.f;
       for (int tj = 0; tj < NT; ++tj) {
 #pragma unroll
@@ -373,7 +383,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) corr_umma_kernel(const __grid_c
 #pragma unroll
           for (int h2 = 0; h2 < 2; ++h2) {
             const int cc = 2 * half + h2;
-            const int q0 = 128 * tj + 32 * cc;
+            const int q0 = 128 * (gj0 + tj) + 32 * cc;
             if (rd == 0) {
               // ---- main pass: branch-free.  Padded rows/columns have fd = cd = 0 and depth sign 0, so they add nothing
               //      to the sums; only U needs the explicit mask (inv = 0 for padded rows, tail zeroing for padded columns).
@@ -449,11 +459,11 @@ __global__ void __launch_bounds__(UM_THREADS, 1) corr_umma_kernel(const __grid_c
           // U is dead until it is rewritten: drain through it.  The two warps of a lane group split the column chunks.
           const size_t which = (rd == 0) ? (size_t)k : (size_t)prm.npairs;
           {  // dC2 rows of column tile tj, partial buffer of row tile ti
-            float* dbase = prm.dC2 + (which * NT + ti) * slab + ((size_t)b * Prows + 128 * tj + 32 * lg) * prm.ldc;
+            float* dbase = prm.dC2 + (which * prm.nti_stride + ti) * slab + ((size_t)b * Prows + 128 * (gj0 + tj) + 32 * lg) * prm.ldc;
             for (int cc = half; cc < ncd; cc += 2) drain_block(tlane + col_cd(tj) + 32 * cc, scratch, dbase, prm.ldc, 32 * cc, lane, v);
           }
           if (tj == NT - 1) {  // dC1 rows of row tile ti (complete after the last column tile)
-            float* dbase = prm.dC1 + which * slab + ((size_t)b * Prows + 128 * ti + 32 * lg) * prm.ldc;
+            float* dbase = prm.dC1 + (which * prm.ncg_stride + cg) * slab + ((size_t)b * Prows + 128 * ti + 32 * lg) * prm.ldc;
             for (int cc = 1 - half; cc < ncd; cc += 2) drain_block(tlane + col_fd(0) + 32 * cc, scratch, dbase, prm.ldc, 32 * cc, lane, v);
           }
           if (threadIdx.x == 64 && step == 0) stamp(prm, 6);
@@ -489,7 +499,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) corr_umma_kernel(const __grid_c
         float acc[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-        const int per_pair = prm.B * NT;
+        const int per_pair = prm.B * prm.nti * prm.ncg;
         const int total = prm.npairs * per_pair;
         for (int e = lane; e < total; e += 32) {   // fixed order -> deterministic
           const int kk = e / per_pair;
@@ -564,6 +574,43 @@ __global__ void __launch_bounds__(256) pair_dots_kernel(const float* __restrict_
   }
 }
 
+// Dense shapes (S*S > 256): rowmean[k,b,p] = mean_q fd[p,q] = < F1n[p,:], mean row of F2n >, the same identity
+// pair_dots_kernel uses for the pair mean.  One block per (pair, image); the F1 rows are read back from the bf16
+// hi/lo panels (x = hi + lo is what the tensor cores see).
+__global__ void __launch_bounds__(256) row_means_kernel(const __nv_bfloat16* __restrict__ fhi,
+                                                        const __nv_bfloat16* __restrict__ flo,
+                                                        const float* __restrict__ fmean, int nsplit, int B, int P,
+                                                        int prows, int ldf, float* __restrict__ rowmean,
+                                                        const __grid_constant__ SlotMap sm) {
+  extern __shared__ float m2[];  // [ldf] mean row of the second operand
+  const int kb = blockIdx.x, k = kb / B, b = kb - k * B;
+  const float* mp = fmean + ((size_t)sm.fs2[k] * B + b) * nsplit * ldf;
+  for (int c = threadIdx.x; c < ldf; c += 256) {
+    float a = 0.f;
+    for (int i = 0; i < nsplit; ++i) a += __ldg(mp + (size_t)i * ldf + c);
+    m2[c] = a;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t base = ((size_t)sm.fs1[k] * B + b) * prows;
+  for (int p = warp; p < prows; p += 8) {
+    if (p >= P) {   // padded rows must read as exact zeros (their U entries are masked by multiplying with 0)
+      if (lane == 0) rowmean[(size_t)kb * prows + p] = 0.f;
+      continue;
+    }
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(fhi + (base + p) * ldf);
+    const __nv_bfloat162* l = reinterpret_cast<const __nv_bfloat162*>(flo + (base + p) * ldf);
+    float s = 0.f;
+    for (int c2 = lane; c2 < ldf / 2; c2 += 32) {
+      const float2 a = __bfloat1622float2(h[c2]), d = __bfloat1622float2(l[c2]);
+      s = fmaf(a.x + d.x, m2[2 * c2], s);
+      s = fmaf(a.y + d.y, m2[2 * c2 + 1], s);
+    }
+    s = warp_sum(s);
+    if (lane == 0) rowmean[(size_t)kb * prows + p] = s;
+  }
+}
+
 static long long* g_clk = nullptr;  // debug: device buffer for per-CTA phase timestamps
 void set_clock_buffer(long long* p) { g_clk = p; }
 
@@ -604,6 +651,8 @@ int corr_loss_umma(const dg_panels_t* pan, const float* fmean, int nsplit, const
                    void* ws, cudaStream_t st, const int32_t* fslot1, const int32_t* fslot2, int nfslots) {
   UmmaParams prm;
   const int ntile = Prows / 128;
+  const bool dense = P > 256;   // more column tiles than TMEM holds at once: column groups of two tiles
+  const int nti = ceil_div(P, 128), ncg = dense ? ceil_div(P, 256) : 1;
   const uint64_t rows = (uint64_t)npairs * B * Prows;
   const uint64_t frows = (uint64_t)(nfslots > 0 ? nfslots : npairs) * B * Prows;
   int rc;
@@ -618,10 +667,15 @@ int corr_loss_umma(const dg_panels_t* pan, const float* fmean, int nsplit, const
   float* dots = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + 256);
   const size_t dots_bytes = ((size_t)npairs * B * sizeof(float) + 255) / 256 * 256;
   float* partials = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + 256 + dots_bytes);
+  const size_t part_bytes = ((size_t)npairs * B * nti * ncg * 4 * sizeof(float) + 255) / 256 * 256;
+  float* rowmean = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + 256 + dots_bytes + part_bytes);
   prm.dsign = dsign;
   prm.dots = (flags & DG_FLAG_POINTWISE) ? dots : nullptr;
   prm.npairs = npairs; prm.B = B; prm.P = P; prm.ldf = ldf; prm.ldc = ldc; prm.flags = flags;
   prm.ntile = ntile;
+  prm.prows = Prows; prm.nti = nti; prm.ncg = ncg;
+  prm.nti_stride = ntile; prm.ncg_stride = dense ? Prows / 256 : 1;
+  prm.rowmean = (dense && (flags & DG_FLAG_POINTWISE)) ? rowmean : nullptr;
   prm.has_depth = dsign != nullptr;
   prm.depth_shift = depth_shift;
   prm.inv_cnt = 1.0f / ((float)B * (float)P * (float)P);
@@ -648,6 +702,15 @@ int corr_loss_umma(const dg_panels_t* pan, const float* fmean, int nsplit, const
     pair_dots_kernel<<<npairs * B, 256, 0, st>>>(fm, nsplit, npairs, B, ldf, dots, err, sm);
     DG_LAUNCH_OK("pair_dots_kernel");
   }
+  if (prm.rowmean) {
+    SlotMap sm;
+    for (int k = 0; k < npairs; ++k) { sm.fs1[k] = prm.fs1[k]; sm.fs2[k] = prm.fs2[k]; }
+    DG_PRE(st);
+    row_means_kernel<<<npairs * B, 256, (size_t)ldf * sizeof(float), st>>>(
+        static_cast<const __nv_bfloat16*>(pan->f_hi), static_cast<const __nv_bfloat16*>(pan->f_lo), fmean, nsplit, B, P,
+        Prows, ldf, rowmean, sm);
+    DG_LAUNCH_OK("row_means_kernel");
+  }
   static bool attr_set = false;
   if (!attr_set) {
     DG_CUDA_OK(cudaFuncSetAttribute(corr_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, UM_SMEM));
@@ -656,7 +719,7 @@ int corr_loss_umma(const dg_panels_t* pan, const float* fmean, int nsplit, const
   }
   DG_PRE(st);
   if (ntile == 1) corr_umma_kernel<1><<<npairs * B, UM_THREADS, UM_SMEM, st>>>(prm);
-  else corr_umma_kernel<2><<<npairs * B * 2, UM_THREADS, UM_SMEM, st>>>(prm);
+  else corr_umma_kernel<2><<<npairs * B * nti * ncg, UM_THREADS, UM_SMEM, st>>>(prm);
   DG_LAUNCH_OK("corr_umma_kernel");
   return DG_OK;  // out8 is written by the last CTA of corr_umma_kernel
 }

@@ -416,8 +416,11 @@ __global__ void __launch_bounds__(256)
                            int Prows, int ld, const float* __restrict__ cn, const float* __restrict__ cn_lo,
                            const float* __restrict__ rnorm, const float* __restrict__ dC1,
                            const float* __restrict__ dC2, int npairs, const __grid_constant__ PairTable pairs,
-                           int has_depth, const __grid_constant__ GroupW gws, int nsets, int ni) {
+                           int has_depth, const __grid_constant__ GroupW gws, int nsets, int ni, int nj) {
   const int P = S * S;
+  // ni / nj: pitch (in panels) of the dC2 per-row-tile and dC1 per-column-group partial buffers; only the tiles /
+  // groups that contain real points were written
+  const int ni_used = min(ni, (P + 127) / 128), nj_used = min(nj, (P + 255) / 256);
   const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp_global >= nsets * B * P) return;
   const int set = warp_global / (B * P);
@@ -438,12 +441,14 @@ __global__ void __launch_bounds__(256)
   if (slot == 0) {
     for (int k = 0; k < npairs; ++k) {
       const float wk = gw[pairs.group[k]] * pairs.scale[k];
-      const float* a = dC1 + (size_t)k * panel + rowoff;
+      for (int t = 0; t < nj_used; ++t) {   // dC1 comes as `nj` partial buffers (one per column group; 1 unless dense)
+        const float* a = dC1 + ((size_t)k * nj + t) * panel + rowoff;
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (j < R) g[j] += wk * __ldg(a + lane + 32 * j);
+        for (int j = 0; j < 8; ++j)
+          if (j < R) g[j] += wk * __ldg(a + lane + 32 * j);
+      }
     }
-    for (int t = 0; t < ni; ++t) {  // dC2 comes as `ni` partial buffers (one per 128-row tile of the first operand)
+    for (int t = 0; t < ni_used; ++t) {  // dC2 comes as `ni` partial buffers (one per 128-row tile of the first operand)
       const float w0 = gw[pairs.group[0]] * pairs.scale[0];
       const float* a = dC2 + (size_t)t * panel + rowoff;
 #pragma unroll
@@ -452,11 +457,13 @@ __global__ void __launch_bounds__(256)
     }
     if (has_depth) {
       const float wd = gw[DG_GROUP_DEPTH];
-      const float* a1 = dC1 + (size_t)npairs * panel + rowoff;
+      for (int t = 0; t < nj_used; ++t) {
+        const float* a1 = dC1 + ((size_t)npairs * nj + t) * panel + rowoff;
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (j < R) g[j] += wd * __ldg(a1 + lane + 32 * j);
-      for (int t = 0; t < ni; ++t) {
+        for (int j = 0; j < 8; ++j)
+          if (j < R) g[j] += wd * __ldg(a1 + lane + 32 * j);
+      }
+      for (int t = 0; t < ni_used; ++t) {
         const float* a2 = dC2 + ((size_t)npairs * ni + t) * panel + rowoff;
 #pragma unroll
         for (int j = 0; j < 8; ++j)
@@ -465,7 +472,7 @@ __global__ void __launch_bounds__(256)
     }
   } else {
     const float ws = gw[pairs.group[slot]] * pairs.scale[slot];
-    for (int t = 0; t < ni; ++t) {
+    for (int t = 0; t < ni_used; ++t) {
       const float* a = dC2 + ((size_t)slot * ni + t) * panel + rowoff;
 #pragma unroll
       for (int j = 0; j < 8; ++j)
@@ -680,12 +687,12 @@ int launch_gather_all(const SetTable& fsets, const SetTable& csets, int nsets, i
 int launch_gather_bwd(const SetTable& tab, int nsets, int B, int C, int H, int W, const float* coords, int S,
                       const int64_t* perms, float eps, int Prows, int ld, const float* cn, const float* cn_lo,
                       const float* rnorm, const float* dC1, const float* dC2, int npairs, const PairTable& pt,
-                      int has_depth, const GroupW& gw, cudaStream_t st, int ni) {
+                      int has_depth, const GroupW& gw, cudaStream_t st, int ni, int nj) {
   const long long rows = (long long)nsets * B * S * S;
   const int blocks = (int)((rows * 32 + 255) / 256);
   DG_PRE(st);
   gather_norm_bwd_kernel<<<blocks, 256, 0, st>>>(tab, B, C, H, W, coords, S, perms, eps, Prows, ld, cn, cn_lo, rnorm,
-                                                 dC1, dC2, npairs, pt, has_depth, gw, nsets, ni);
+                                                 dC1, dC2, npairs, pt, has_depth, gw, nsets, ni, nj);
   DG_LAUNCH_OK("gather_norm_bwd_kernel");
   return DG_OK;
 }
@@ -750,10 +757,12 @@ extern "C" int dg_gather_norm_bwd(float* grad, const int64_t* strides, int B, in
   GroupW gw;
   gw.arr = group_w;
   for (int g = 0; g < DG_NUM_GROUPS; ++g) gw.ptr[g] = nullptr;
-  // split (tcgen05) panels with more than 128 rows carry one dC2 buffer per 128-row tile
+  // split (tcgen05) panels with more than 128 rows carry one dC2 buffer per 128-row tile, and above 256 points one
+  // dC1 buffer per 256-column group
   const int ni = (cn_lo != nullptr) ? Prows / 128 : 1;
+  const int nj = (cn_lo != nullptr && S * S > 256) ? Prows / 256 : 1;
   return launch_gather_bwd(tab, nsets, B, C, H, W, coords, S, perm, eps, Prows, ld, cn, cn_lo, rnorm, dC1, dC2, npairs,
-                           pt, has_depth, gw, reinterpret_cast<cudaStream_t>(stream), ni);
+                           pt, has_depth, gw, reinterpret_cast<cudaStream_t>(stream), ni, nj);
 }
 
 extern "C" int dg_pool_normalize(const float* t, const int64_t* strides, int N, int C, int H, int W, float eps,

@@ -64,7 +64,7 @@ int launch_gather_all(const SetTable& fsets, const SetTable& csets, int nsets, i
 int launch_gather_bwd(const SetTable& tab, int nsets, int B, int C, int H, int W, const float* coords, int S,
                       const int64_t* perms, float eps, int Prows, int ld, const float* cn, const float* cn_lo,
                       const float* rnorm, const float* dC1, const float* dC2, int npairs, const PairTable& pt,
-                      int has_depth, const GroupW& gw, cudaStream_t st, int ni = 1);
+                      int has_depth, const GroupW& gw, cudaStream_t st, int ni = 1, int nj = 1);
 int launch_corr_finalize(const float* partials, int npairs, int B, int P, const int32_t* group, int has_depth,
                          const int* err, float* out8, int n_pt, cudaStream_t st);
 int corr_loss_simt(const float* fn, const float* cn, const float* fmean, int nsplit, const float* dsign, int npairs, int B, int P,

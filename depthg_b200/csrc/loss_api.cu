@@ -35,9 +35,12 @@ static void make_plan(const dg_loss_desc_t* d, dg_loss_plan_t* p) {
   p->npairs = 2 + d->neg_samples;
   p->ldf = round_up(d->C, 32);
   p->ldc = round_up(d->D, 32);
-  p->kernel = (P <= 256 && p->ldc <= 128 && !(d->flags & DG_FLAG_FORCE_SIMT)) ? 1 : 0;
-  p->Prows = p->kernel ? round_up(P, 128) : round_up(P, 64);
+  // tcgen05 kernel: up to 256 points a CTA walks all column tiles; up to 1024 ("dense") the columns are cut into
+  // groups of two tiles (panels padded to a multiple of 256 rows so that every group is whole)
+  p->kernel = (P <= 1024 && p->ldc <= 128 && !(d->flags & DG_FLAG_FORCE_SIMT)) ? 1 : 0;
+  p->Prows = p->kernel ? (P <= 256 ? round_up(P, 128) : round_up(P, 256)) : round_up(P, 64);
   const size_t ni = p->kernel ? p->Prows / 128 : 1;  // dC2 partial buffers (one per 128-row tile of the first operand)
+  const size_t nj = (p->kernel && P > 256) ? p->Prows / 256 : 1;  // dC1 partial buffers (one per column group)
   const size_t np = p->npairs, B = d->B, Pr = p->Prows;
   const size_t nf = np + ((d->flags & DG_FLAG_AUG_INTRA) ? 1 : 0);   // feature panel slots (+1: depth-augmented features)
   size_t off = 0;
@@ -49,7 +52,7 @@ static void make_plan(const dg_loss_desc_t* d, dg_loss_plan_t* p) {
   p->dsign = take(B * Pr * 4);
   p->ws_bytes = corr_workspace_bytes(p->npairs, d->B, P);
   p->ws = take(p->ws_bytes);
-  p->dC1 = take((np + 1) * B * Pr * p->ldc * 4);
+  p->dC1 = take((np + 1) * nj * B * Pr * p->ldc * 4);
   p->dC2 = take((np + 1) * ni * B * Pr * p->ldc * 4);
   if (p->kernel) {
     p->c_hi = take(np * B * Pr * p->ldc * 4);
@@ -251,5 +254,5 @@ extern "C" int dg_loss_backward(const dg_loss_desc_t* d, const dg_loss_io_t* io,
                            reinterpret_cast<const float*>(A + pl.crn), reinterpret_cast<const float*>(A + pl.dC1),
                            reinterpret_cast<const float*>(A + pl.dC2), pl.npairs, pt,
                            (d->flags & DG_FLAG_DEPTH_TERM) ? 1 : 0, gw, reinterpret_cast<cudaStream_t>(stream),
-                           pl.kernel ? pl.Prows / 128 : 1);
+                           pl.kernel ? pl.Prows / 128 : 1, (pl.kernel && d->S * d->S > 256) ? pl.Prows / 256 : 1);
 }

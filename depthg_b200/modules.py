@@ -172,12 +172,13 @@ def _gather(t, coords, S, set_coord, set_slot, perm, eps, Prows, ld, out, rnorm,
 
 
 def corr_kernel_choice(P: int, D: int) -> str:
-    """Which correlation kernel a shape gets: the tcgen05 kernel needs S*S <= 256 and dim <= 128;
-    everything else runs the generic CUDA-core kernel.  DEPTHG_B200_CORR=simt forces the generic one."""
+    """Which correlation kernel a shape gets: the tcgen05 kernel needs S*S <= 1024 and dim <= 128
+    (above 256 points it works on column groups of two 128-wide tiles); everything else runs the generic
+    CUDA-core kernel.  DEPTHG_B200_CORR=simt forces the generic one."""
     import os
     if os.environ.get("DEPTHG_B200_CORR", "") == "simt":
         return "simt"
-    return "umma" if (P <= 256 and _lib.panel_ld(D) <= 128) else "simt"
+    return "umma" if (P <= 1024 and _lib.panel_ld(D) <= 128) else "simt"
 
 
 def _check_coords(coords, B):
@@ -319,10 +320,12 @@ class _CorrLossFn(torch.autograd.Function):
         ctx.code_like = (code, code_pos)
         if _CorrLossFn.debug:   # views of the unit gradients (dC2 summed over its per-row-tile partial buffers)
             ni = plan.Prows // 128 if plan.kernel == 1 else 1
+            nj = plan.Prows // 256 if (plan.kernel == 1 and P > 256) else 1
             n1 = (npairs + 1) * B * plan.Prows * plan.ldc
-            d1 = arena[plan.dC1:plan.dC1 + n1 * 4].view(torch.float32).view(npairs + 1, B, plan.Prows, plan.ldc)
+            d1 = arena[plan.dC1:plan.dC1 + n1 * nj * 4].view(torch.float32).view(npairs + 1, nj, B, plan.Prows,
+                                                                                 plan.ldc)[:, :-(-P // 256)].sum(1)
             d2 = arena[plan.dC2:plan.dC2 + n1 * ni * 4].view(torch.float32).view(npairs + 1, ni, B, plan.Prows,
-                                                                                 plan.ldc).sum(1)
+                                                                                 plan.ldc)[:, :-(-P // 128)].sum(1)
             _CorrLossFn.last_unit_grads = (d1, d2)
         else:
             _CorrLossFn.last_unit_grads = None

@@ -29,9 +29,29 @@ def run(name, B, C, D, S, H=28, sampling="fps", pointwise=True, nchw=False, step
     print(json.dumps({"config": name, "B": B, "C": C, "D": D, "S": S, "grid": H, "sampling": sampling, "layout": "nchw" if nchw else "channels_last",
                       "ms_per_step": round(ms, 4), "samples_per_s": round(B / ms * 1e3)}), flush=True)
 
+if len(sys.argv) > 1 and sys.argv[1] == "dense":
+    _skip = True
+else:
+    _skip = False
+_run = run
+def run(*a, **k):
+    if _skip and "dense" not in a[0]:
+        return
+    _run(*a, **k)
 run("cfg1 ViT-S", 2, 384, 70, 11)
 run("cfg2 ViT-B S=11", 32, 768, 90, 11)
 run("cfg2 ViT-B S=11 nchw", 32, 768, 90, 11, nchw=True)
 run("cfg2' ViT-B S=12", 32, 768, 90, 12)
 run("cfg4 Cityscapes", 64, 768, 100, 11, sampling="none", pointwise=False)
-run("cfg5 dense 28x28 (generic kernel)", 4, 768, 90, 28, steps=3)
+import ctypes
+from depthg_b200 import _lib
+only_dense = len(sys.argv) > 1 and sys.argv[1] == "dense"
+def profile_once(fn):
+    lib = _lib.lib(); lib.dg_profile_enable(1); fn(); torch.cuda.synchronize()
+    n = lib.dg_profile_collect(None, 0); buf = ctypes.create_string_buffer(n + 16); lib.dg_profile_collect(buf, n + 16)
+    lib.dg_profile_enable(0); print(buf.value.decode())
+run("cfg5 dense 28x28 B=4 (random coords)", 4, 768, 90, 28, sampling="none", steps=10)
+run("cfg5 dense 28x28 B=64 (random coords)", 64, 768, 90, 28, sampling="none", steps=5)
+os.environ["DEPTHG_B200_CORR"] = "simt"
+run("cfg5 dense 28x28 B=4 (generic CUDA-core kernel)", 4, 768, 90, 28, sampling="none", steps=3)
+del os.environ["DEPTHG_B200_CORR"]

@@ -499,6 +499,9 @@ def test_depth_contrastive_variant_matches_reference_golden(name, variant):
     dict(B=2, C=100, D=128, S=5, neg=2, sampling="none"),       # C not a multiple of 32/128, code dim at the 128 limit
     dict(B=3, C=256, D=33, S=16, neg=1, sampling="fps"),        # S*S = 256: the largest tensor-core tiling
     dict(B=2, C=20, D=7, S=3, neg=3, sampling="fps", H=20, W=12, Hd=80, Wd=60),   # non-square grid, odd pooling windows
+    dict(B=2, C=64, D=24, S=20, neg=2, sampling="none"),        # 400 points: tcgen05 column groups (4 row tiles x 2 groups)
+    dict(B=2, C=32, D=16, S=28, neg=1, sampling="fps"),         # the dense 28x28 stress shape: 784 points, 7 x 4 blocks
+    dict(B=2, C=128, D=40, S=17, neg=1, sampling="none"),       # 289 points: just above the single-group limit
 ])
 def test_edge_shapes_match_oracle(shape):
     from depthg_b200.modules import ContrastiveCorrelationLoss
@@ -616,3 +619,29 @@ def test_linear_probe_full_size_matches_oracle():
     lin.backward()
     assert rel_err(w1.grad.cpu().numpy(), w0.grad.numpy()) < RTOL
     assert rel_err(b1.grad.cpu().numpy(), b0.grad.numpy()) < RTOL
+
+
+def test_dense_shapes_run_on_the_tensor_core_kernel():
+    """S*S > 256 must go through corr_umma_kernel (column groups) + row_means_kernel, not the CUDA-core fallback."""
+    import ctypes
+    from depthg_b200 import _lib
+    from depthg_b200.modules import ContrastiveCorrelationLoss, corr_kernel_choice
+    assert corr_kernel_choice(784, 90) == "umma" and corr_kernel_choice(1025, 90) == "simt"
+    g = torch.Generator(device=dev()).manual_seed(3)
+    B, C, D, S = 2, 64, 32, 18
+    f = lambda ch: torch.randn((B, ch, 28, 28), generator=g, device=dev())   # noqa: E731
+    code, code_pos = f(D).requires_grad_(True), f(D).requires_grad_(True)
+    fn = ContrastiveCorrelationLoss(cases.loss_cfg(feature_samples=S, neg_samples=2, depth_sampling="none"))
+    lib = _lib.lib()
+    lib.dg_profile_enable(1)
+    depth = torch.rand((B, 1, 224, 224), generator=g, device=dev()) * 255
+    out = fn(f(C), f(C), None, None, code, code_pos, depth, depth)
+    (out[0] + out[2] + out[4].mean() + out[6]).backward()
+    torch.cuda.synchronize()
+    n = lib.dg_profile_collect(None, 0)
+    buf = ctypes.create_string_buffer(n + 16)
+    lib.dg_profile_collect(buf, n + 16)
+    lib.dg_profile_enable(0)
+    names = buf.value.decode()
+    assert "corr_umma_kernel" in names and "row_means_kernel" in names and "corr_tile_kernel" not in names
+    assert torch.isfinite(code.grad).all() and torch.isfinite(code_pos.grad).all()

@@ -141,6 +141,9 @@ __global__ void __launch_bounds__(UM_THREADS, 1) corr_umma_kernel(const __grid_c
   uint64_t* u_ready = acc_full + 1;
   uint64_t* grad_full = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 3);
+  uint64_t* g1_full = acc_full + 4;       // NT == 2: first-operand code rows landed
+  uint64_t* g2_full = acc_full + 5;       //          second-operand code rows of the current column tile landed
+  uint64_t* g2_empty = acc_full + 6;      //          ... and were consumed by the gradient MMAs
   __shared__ float s_red[8][4];
   __shared__ float s_rowsum[2][128];
   __shared__ float s_sign[1024];
@@ -165,7 +168,9 @@ __global__ void __launch_bounds__(UM_THREADS, 1) corr_umma_kernel(const __grid_c
   const bool depth_round = prm.has_depth && k == 0;
   const int rounds = depth_round ? 2 : 1;
   // ring stages after the correlation phase: first-operand code rows, second-operand code rows, U
-  const int sC1 = J0 % UM_NSTAGE, sC2 = (J0 + 1) % UM_NSTAGE, sU = (J0 + 2) % UM_NSTAGE;
+  // (NT == 2 uses fixed 64 KB regions 0 / 1 / 2 of the ring for them, see below)
+  const int sC1 = NT == 2 ? 0 : J0 % UM_NSTAGE, sC2 = NT == 2 ? 1 : (J0 + 1) % UM_NSTAGE,
+            sU = NT == 2 ? 2 : (J0 + 2) % UM_NSTAGE;
   const int nC2 = (NT == 1) ? 1 : rounds * NT;                // loads of second-operand code rows (reloaded per tile)
   uint8_t* u_hi = ring + sU * UM_STAGE;
   uint8_t* u_lo = u_hi + 32768;
@@ -178,6 +183,9 @@ __global__ void __launch_bounds__(UM_THREADS, 1) corr_umma_kernel(const __grid_c
     mbar_init(acc_full, 1);
     mbar_init(u_ready, UM_EPI);
     mbar_init(grad_full, 1);
+    mbar_init(g1_full, 1);
+    mbar_init(g2_full, 1);
+    mbar_init(g2_empty, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -198,6 +206,55 @@ __global__ void __launch_bounds__(UM_THREADS, 1) corr_umma_kernel(const __grid_c
       // fills of a stage so far: t / 3 during the correlation phase (phase = count & 1); afterwards sC1 is filled once
       // more and sC2 once per load of second-operand code rows
       bool ok = true;
+      if constexpr (NT == 2) {
+        // Two column tiles per CTA: every operand chunk of the first operand is loaded ONCE and multiplied with the
+        // chunks of both column tiles.  Stage (96 KB, two of them) = [A hi | A lo | B0 hi | B0 lo | B1 hi | B1 lo].
+        constexpr uint32_t ST2 = 98304;
+        for (int c = 0; c < nop && ok; ++c) {
+          const int s = c & 1;
+          ok = mbar_wait(&empty[s], ((c >> 1) & 1) ^ 1);
+          if (!ok) break;
+          uint8_t* st = ring + s * ST2;
+          const bool isf = c < nfd;
+          const int c0 = isf ? c * 64 : (c - nfd) * 32;
+          const CUtensorMap* mh = isf ? &prm.tm_fhi : &prm.tm_chi;
+          const CUtensorMap* ml = isf ? &prm.tm_flo : &prm.tm_clo;
+          const bool diag_ok = isf ? fsame_slot : k == 0;   // operands are the same panel: the diagonal tile needs no second load
+          const bool same0 = diag_ok && gj0 == ti, same1 = diag_ok && gj0 + 1 == ti;
+          mbar_arrive_expect_tx(&full[s], 32768u + (same0 ? 0u : 32768u) + (same1 ? 0u : 32768u));
+          const int ra = isf ? frow1 : row1, rb = (isf ? frow2 : row2) + 128 * gj0;
+          tma_load_2d(st, mh, &full[s], c0, ra);
+          tma_load_2d(st + 16384, ml, &full[s], c0, ra);
+          if (!same0) {
+            tma_load_2d(st + 32768, mh, &full[s], c0, rb);
+            tma_load_2d(st + 49152, ml, &full[s], c0, rb);
+          }
+          if (!same1) {
+            tma_load_2d(st + 65536, mh, &full[s], c0, rb + 128);
+            tma_load_2d(st + 81920, ml, &full[s], c0, rb + 128);
+          }
+        }
+        // the ring is re-partitioned into three 64 KB regions (code rows 1, code rows 2, U) once every correlation
+        // MMA has finished reading it
+        ok = ok && mbar_wait(acc_full, 0);
+        if (ok) {
+          mbar_arrive_expect_tx(g1_full, (uint32_t)(2 * nb * 8192));
+          for (int a = 0; a < nb; ++a) {
+            tma_load_2d(ring + a * 8192, &prm.tm_bhi, g1_full, a * 32, row1);
+            tma_load_2d(ring + 32768 + a * 8192, &prm.tm_blo, g1_full, a * 32, row1);
+          }
+        }
+        for (int step = 0; step < rounds * NT && ok; ++step) {
+          if (step > 0) ok = mbar_wait(g2_empty, (step - 1) & 1);
+          if (!ok) break;
+          const int r = row2 + 128 * (gj0 + step % NT);
+          mbar_arrive_expect_tx(g2_full, (uint32_t)(2 * nb * 8192));
+          for (int a = 0; a < nb; ++a) {
+            tma_load_2d(ring + 65536 + a * 8192, &prm.tm_bhi, g2_full, a * 32, r);
+            tma_load_2d(ring + 65536 + 32768 + a * 8192, &prm.tm_blo, g2_full, a * 32, r);
+          }
+        }
+      } else
       for (int t = 0; t < J0 + 1 + nC2 && ok; ++t) {
         int s, fills;
         if (t < J0) { s = t % UM_NSTAGE; fills = t / UM_NSTAGE; }
@@ -246,6 +303,41 @@ __global__ void __launch_bounds__(UM_THREADS, 1) corr_umma_kernel(const __grid_c
       const uint64_t dmn128 = smem_desc(0, 16384, 1024, SW_128B);   // MN-major, 64-element atoms 16 KB apart
       const uint64_t dmn64 = smem_desc(0, 8192, 512, SW_64B);       // MN-major, 32-element atoms 8 KB apart
       bool ok = true;
+      if constexpr (NT == 2) {
+        constexpr uint32_t ST2 = 98304;
+        for (int c = 0; c < nop && ok; ++c) {
+          const int s = c & 1;
+          ok = mbar_wait(&full[s], (c >> 1) & 1);
+          tc_fence_after_sync();
+          const bool isf = c < nfd;
+          const bool diag_ok = isf ? fsame_slot : k == 0;
+          const uint32_t a0 = smem_u32(ring + s * ST2) >> 4;
+          const uint64_t ah = dk128 + a0, al = ah + (16384 >> 4);
+#pragma unroll
+          for (int tj = 0; tj < 2; ++tj) {
+            const bool same = diag_ok && gj0 + tj == ti;
+            const uint64_t bh = same ? ah : ah + ((32768 + tj * 32768) >> 4), bl = bh + (16384 >> 4);
+            if (isf) {
+              const uint32_t acc = tmem + col_fd(tj);
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                mma_f16(acc, ah + 2 * ks, bh + 2 * ks, id_f, (c | ks) != 0);
+                mma_f16(acc, ah + 2 * ks, bl + 2 * ks, id_f, 1);
+                mma_f16(acc, al + 2 * ks, bh + 2 * ks, id_f, 1);
+              }
+            } else {
+              const uint32_t acc = tmem + col_cd(tj);
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                mma_tf32(acc, ah + 2 * ks, bh + 2 * ks, id_c, (c != nfd) || ks != 0);
+                mma_tf32(acc, ah + 2 * ks, bl + 2 * ks, id_c, 1);
+                mma_tf32(acc, al + 2 * ks, bh + 2 * ks, id_c, 1);
+              }
+            }
+          }
+          mma_commit(&empty[s]);
+        }
+      } else
       for (int t = 0; t < J0 && ok; ++t) {
         const int s = t % UM_NSTAGE;
         ok = mbar_wait(&full[s], (t / UM_NSTAGE) & 1);
@@ -279,7 +371,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) corr_umma_kernel(const __grid_c
       // first-operand code rows (loaded once)
       uint32_t g1 = 0;
       if (ok) {
-        ok = mbar_wait(&full[sC1], ((J0 + 2 - sC1) / UM_NSTAGE) & 1);
+        ok = NT == 2 ? mbar_wait(g1_full, 0) : mbar_wait(&full[sC1], ((J0 + 2 - sC1) / UM_NSTAGE) & 1);
         g1 = smem_u32(ring + sC1 * UM_STAGE) >> 4;
       }
       const int c2_base = (J0 + 2 - sC2) / UM_NSTAGE;   // fills of sC2 during the correlation phase
@@ -289,7 +381,9 @@ __global__ void __launch_bounds__(UM_THREADS, 1) corr_umma_kernel(const __grid_c
       int c2_loaded = 0;
       for (int rd = 0; rd < rounds && ok; ++rd) {
         for (int tj = 0; tj < NT && ok; ++tj, ++step) {
-          if (c2_loaded < nC2 && (NT > 1 || step == 0)) {   // second-operand code rows of this column tile
+          if (NT == 2) {                                    // second-operand code rows of this column tile
+            ok = mbar_wait(g2_full, step & 1);
+          } else if (c2_loaded < nC2 && step == 0) {
             ok = mbar_wait(&full[sC2], (c2_base + c2_loaded) & 1);
             ++c2_loaded;
           }
@@ -317,7 +411,11 @@ __global__ void __launch_bounds__(UM_THREADS, 1) corr_umma_kernel(const __grid_c
             mma_f16(d2, a_h, b_l, id_g2, 1);
             mma_f16(d2, a_l, b_h, id_g2, 1);
           }
-          if (c2_loaded < nC2) mma_commit(&empty[sC2]);   // the next column tile's code rows may overwrite this stage
+          if (NT == 2) {
+            if (step + 1 < rounds * NT) mma_commit(g2_empty);   // the next column tile's code rows may overwrite the region
+          } else if (c2_loaded < nC2) {
+            mma_commit(&empty[sC2]);
+          }
           mma_commit(grad_full);
         }
       }

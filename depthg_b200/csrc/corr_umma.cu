@@ -1,9 +1,10 @@
-// Fused correlation loss on the 5th-gen tensor cores (tcgen05 + TMEM + TMA), P = S*S <= 256.
+// Fused correlation loss on the 5th-gen tensor cores (tcgen05 + TMEM + TMA), P = S*S <= 1024.
 //
 // Same contract as corr_tile_kernel (corr_loss.cu) — replaces helper() for every pair
 // and depth_feature_correlation (/root/reference/src/modules.py:1231-1278) — but one
 // CTA owns a 128-row tile of a (pair k, image b) problem (the whole problem when P <= 128; two row tiles, each
-// walking two 128-column tiles, when 128 < P <= 256) and nothing P x P ever leaves the SM:
+// walking two 128-column tiles, when 128 < P <= 256; above that a row tile and a GROUP of two column tiles, with
+// the row means precomputed by row_means_kernel) and nothing P x P ever leaves the SM:
 //
 //   warp 0   TMA producer : streams K-chunks of the split panels into a 3 x 64 KB smem ring
 //   warp 1   MMA issuer   : one elected lane issues tcgen05.mma; accumulators live in TMEM

@@ -165,8 +165,9 @@ DG_API int dg_gather_norm_bwd(float* grad, const int64_t* strides, int B, int C,
  *         pair k, slot 0 = first operand of every pair (k = 0 is the intra pair):
  *           format DG_PANEL_F32   : f_hi = fp32 [npairs,B,Prows,ldf], c_hi = fp32 [npairs,B,Prows,ldc]
  *                                   (generic CUDA-core kernel, any S);
- *           split formats         : f_hi/f_lo bf16 [npairs,B,128,ldf]; c_hi/c_lo fp32 [npairs,B,128,ldc];
- *                                   cb_hi/cb_lo bf16 [npairs,B,128,ldc] (tcgen05 kernel, S*S <= 128).
+ *           split formats         : f_hi/f_lo bf16 [npairs,B,Prows,ldf]; c_hi/c_lo fp32 [npairs,B,Prows,ldc];
+ *                                   cb_hi/cb_lo bf16 [npairs,B,Prows,ldc] (tcgen05 kernel, S*S <= 1024) with
+ *                                   Prows = round_up(S*S,128) up to 256 points, round_up(S*S,256) above.
  *   fmean : [npairs,B,ldf] panel row means (only read with DG_FLAG_POINTWISE).
  *   dsign : [B,Prows] depth signs from dg_depth_sign, or NULL for no depth term.
  *   pair_shift / pair_group : host [npairs].
@@ -175,9 +176,12 @@ DG_API int dg_gather_norm_bwd(float* grad, const int64_t* strides, int B, int C,
  *           pipeline reported a timeout.
  *   dC1,dC2 : out [npairs+1,B,Prows,ldc] unit gradients of each pair's MEAN loss
  *           w.r.t. its first / second normalised code operand (index npairs = depth).
+ *           Split formats write partial buffers that dg_gather_norm_bwd sums:
+ *           dC2 [npairs+1, Prows/128, B,Prows,ldc] (one per 128-row tile of the first operand) and,
+ *           above 256 points, dC1 [npairs+1, Prows/256, B,Prows,ldc] (one per 256-column group).
  *   cd_out, loss_out : optional dense [npairs,B,P,P] (NULL to skip) — the
  *           reference's 5-D tensors, [b,h,w,i,j] flattened; dd_out optional [B,P,P].
- *   fd_dbg : optional [npairs,B,128,128] raw feature correlations (tcgen05 path; tests).
+ *   fd_dbg : optional [npairs,B,Prows,Prows] raw feature correlations (tcgen05 path; tests).
  *   ws : workspace of dg_corr_loss_workspace_bytes(). */
 typedef struct dg_panels {
   int format; /* DG_PANEL_F32, or DG_PANEL_FEATS_SPLIT / DG_PANEL_CODE_SPLIT for the split set */

@@ -639,38 +639,19 @@ __global__ void __launch_bounds__(UM_THREADS, 1) corr_umma_kernel(const __grid_c
 }
 
 // dots[k,b] = < mean_p F1n[b,p,:], mean_q F2n[k,b,q,:] >  (one 256-thread block each, all loads in flight at once);
-// block 0 also clears the error flag
+// block 0 also clears the error flag.  The one-call loss path runs the same body as extra CTAs of the code gather
+// (kernels.cuh: DotsJob) and skips this launch.
 struct SlotMap {
   int32_t fs1[DG_MAX_PAIRS], fs2[DG_MAX_PAIRS];
 };
 
-__global__ void __launch_bounds__(256) pair_dots_kernel(const float* __restrict__ fmean, int nsplit, int npairs, int B,
-                                                        int ldf, float* __restrict__ dots, int* __restrict__ err,
-                                                        const __grid_constant__ SlotMap sm) {
-  __shared__ float red[8];
-  if (blockIdx.x == 0 && threadIdx.x < 4 && err) err[threadIdx.x] = 0;  // error flag + completion counter
-  if (fmean == nullptr) return;
-  const int w = blockIdx.x, k = w / B, b = w - k * B;
-  const float* m1 = fmean + ((size_t)sm.fs1[k] * B + b) * nsplit * ldf;   // nsplit partial means each
-  const float* m2 = fmean + ((size_t)sm.fs2[k] * B + b) * nsplit * ldf;
-  float s = 0.f;
-  for (int c = threadIdx.x; c < ldf; c += 256) {
-    float a = 0.f, bb = 0.f;
-    for (int i = 0; i < nsplit; ++i) {
-      a += __ldg(m1 + (size_t)i * ldf + c);
-      bb += __ldg(m2 + (size_t)i * ldf + c);
-    }
-    s += a * bb;
-  }
-  s = warp_sum(s);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float t = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) t += red[i];
-    dots[w] = t;
-  }
+__global__ void __launch_bounds__(256) pair_dots_kernel(const __grid_constant__ DotsJob job) {
+  pair_dots_body(job, blockIdx.x);
+}
+
+void umma_ws_layout(void* ws, int** err, float** dots) {
+  *err = static_cast<int*>(ws);
+  *dots = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + 256);
 }
 
 // Dense shapes (S*S > 256): rowmean[k,b,p] = mean_q fd[p,q] = < F1n[p,:], mean row of F2n >, the same identity
@@ -747,7 +728,7 @@ static int make_map_2d(CUtensorMap* m, CUtensorMapDataType dt, int elt_bytes, co
 int corr_loss_umma(const dg_panels_t* pan, const float* fmean, int nsplit, const float* dsign, int npairs, int B, int P, int Prows, int ldf,
                    int ldc, const float* pair_shift, const int32_t* pair_group, float depth_shift, int flags,
                    float* out8, float* dC1, float* dC2, float* cd_out, float* loss_out, float* dd_out, float* fd_dbg,
-                   void* ws, cudaStream_t st, const int32_t* fslot1, const int32_t* fslot2, int nfslots) {
+                   void* ws, cudaStream_t st, const int32_t* fslot1, const int32_t* fslot2, int nfslots, bool dots_done) {
   UmmaParams prm;
   const int ntile = Prows / 128;
   const bool dense = P > 256;   // more column tiles than TMEM holds at once: column groups of two tiles
@@ -762,8 +743,9 @@ int corr_loss_umma(const dg_panels_t* pan, const float* fmean, int nsplit, const
   if ((rc = make_map_2d(&prm.tm_bhi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, pan->cb_hi, ldc, rows, 32, 128, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
   if ((rc = make_map_2d(&prm.tm_blo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, pan->cb_lo, ldc, rows, 32, 128, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
   // workspace: [err int (256 B)][dots npairs*B floats, padded to 256 B][partials npairs*B*4 floats]
-  int* err = static_cast<int*>(ws);
-  float* dots = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + 256);
+  int* err;
+  float* dots;
+  umma_ws_layout(ws, &err, &dots);
   const size_t dots_bytes = ((size_t)npairs * B * sizeof(float) + 255) / 256 * 256;
   float* partials = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + 256 + dots_bytes);
   const size_t part_bytes = ((size_t)npairs * B * nti * ncg * 4 * sizeof(float) + 255) / 256 * 256;
@@ -793,12 +775,13 @@ int corr_loss_umma(const dg_panels_t* pan, const float* fmean, int nsplit, const
     const char* e = getenv("DEPTHG_B200_UMMA_DBG");
     prm.dbg = e ? atoi(e) : 0;
   }
-  {
-    const float* fm = (flags & DG_FLAG_POINTWISE) ? fmean : nullptr;
+  if (!dots_done) {
+    DotsJob job;
+    job.fmean = (flags & DG_FLAG_POINTWISE) ? fmean : nullptr;
+    job.dots = dots; job.err = err; job.nsplit = nsplit; job.npairs = npairs; job.B = B; job.ldf = ldf;
+    for (int k = 0; k < DG_MAX_PAIRS; ++k) { job.fs1[k] = k < npairs ? prm.fs1[k] : 0; job.fs2[k] = k < npairs ? prm.fs2[k] : 0; }
     DG_PRE(st);
-    SlotMap sm;
-    for (int k = 0; k < npairs; ++k) { sm.fs1[k] = prm.fs1[k]; sm.fs2[k] = prm.fs2[k]; }
-    pair_dots_kernel<<<npairs * B, 256, 0, st>>>(fm, nsplit, npairs, B, ldf, dots, err, sm);
+    pair_dots_kernel<<<npairs * B, 256, 0, st>>>(job);
     DG_LAUNCH_OK("pair_dots_kernel");
   }
   if (prm.rowmean) {

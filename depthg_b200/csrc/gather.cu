@@ -12,6 +12,8 @@
 // channels (128-bit loads when the channel stride is 1), so a channels-last
 // source is read in whole 128-byte lines and every panel row is written once,
 // coalesced.  HBM-bound: no data reuse beyond the four bilinear corners.
+#include <string.h>
+
 #include "kernels.cuh"
 
 namespace dg {
@@ -346,7 +348,11 @@ template <int R>
 __global__ void __launch_bounds__(GF_THREADS)
     gather_code_kernel(const __grid_constant__ SetTable sets, int B, int C, int H, int W,
                        const float* __restrict__ coords, int S, const int64_t* __restrict__ perms, float eps,
-                       int Prows, int nsplit, GatherOut o) {
+                       int Prows, int nsplit, GatherOut o, const __grid_constant__ DotsJob job, int ncode_blocks) {
+  if ((int)blockIdx.x >= ncode_blocks) {   // appended pair_dots CTAs (independent of the code gather, same stream slot)
+    pair_dots_body(job, (int)blockIdx.x - ncode_blocks);
+    return;
+  }
   gather_code_body<R>(sets, B, C, H, W, coords, S, perms, eps, Prows, nsplit, o, blockIdx.x);
 }
 
@@ -602,15 +608,21 @@ static int launch_gather_fast(int fmt, const SetTable& tab, int nsets, int B, in
 }
 
 int launch_gather(int fmt, const SetTable& tab, int nsets, int B, int C, int H, int W, const float* coords, int S,
-                  const int64_t* perms, float eps, int Prows, int ld, int nsplit, const GatherOut& o, cudaStream_t st) {
+                  const int64_t* perms, float eps, int Prows, int ld, int nsplit, const GatherOut& o, cudaStream_t st,
+                  const DotsJob* tail) {
+  DG_REQUIRE(!tail || (fmt == FMT_CODE_SPLIT && ld <= 128), DG_ERR_INVALID, "gather: a dots tail needs the code-split path");
   if (fmt == FMT_CODE_SPLIT && ld <= 128) {  // register-resident code gather
     const int ns = 16;  // one or two points per warp: the two dependent global round trips per point are the cost
+    DotsJob job;
+    memset(&job, 0, sizeof job);
+    if (tail) job = *tail;
+    const int ncode = nsets * B * ns, grid = ncode + (tail ? tail->npairs * tail->B : 0);
     DG_PRE(st);
     switch (ld / 32) {
-      case 1: gather_code_kernel<1><<<nsets * B * ns, GF_THREADS, 0, st>>>(tab, B, C, H, W, coords, S, perms, eps, Prows, ns, o); break;
-      case 2: gather_code_kernel<2><<<nsets * B * ns, GF_THREADS, 0, st>>>(tab, B, C, H, W, coords, S, perms, eps, Prows, ns, o); break;
-      case 3: gather_code_kernel<3><<<nsets * B * ns, GF_THREADS, 0, st>>>(tab, B, C, H, W, coords, S, perms, eps, Prows, ns, o); break;
-      default: gather_code_kernel<4><<<nsets * B * ns, GF_THREADS, 0, st>>>(tab, B, C, H, W, coords, S, perms, eps, Prows, ns, o); break;
+      case 1: gather_code_kernel<1><<<grid, GF_THREADS, 0, st>>>(tab, B, C, H, W, coords, S, perms, eps, Prows, ns, o, job, ncode); break;
+      case 2: gather_code_kernel<2><<<grid, GF_THREADS, 0, st>>>(tab, B, C, H, W, coords, S, perms, eps, Prows, ns, o, job, ncode); break;
+      case 3: gather_code_kernel<3><<<grid, GF_THREADS, 0, st>>>(tab, B, C, H, W, coords, S, perms, eps, Prows, ns, o, job, ncode); break;
+      default: gather_code_kernel<4><<<grid, GF_THREADS, 0, st>>>(tab, B, C, H, W, coords, S, perms, eps, Prows, ns, o, job, ncode); break;
     }
     DG_LAUNCH_OK("gather_code_kernel");
     return DG_OK;

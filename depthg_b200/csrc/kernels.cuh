@@ -46,6 +46,44 @@ struct GroupW {
   const float* ptr[DG_NUM_GROUPS];
 };
 
+// pair_dots work that the one-call loss path appends to the code gather's grid (the tcgen05 correlation kernel
+// needs dots[k,b] = <mean row of F1[b], mean row of F2[k,b]> and a cleared error flag / completion counter)
+struct DotsJob {
+  const float* fmean;  // [slot,b,nsplit,ldf] partial means, or null (not pointwise): only the flags are cleared
+  float* dots;         // [npairs,B]
+  int* err;            // [4] error flag + completion counter
+  int nsplit, npairs, B, ldf;
+  int32_t fs1[DG_MAX_PAIRS], fs2[DG_MAX_PAIRS];
+};
+
+// One 256-thread block per (pair k, image b); block 0 also clears the flags.
+__device__ __forceinline__ void pair_dots_body(const DotsJob& j, int w) {
+  __shared__ float pd_red[8];
+  if (w == 0 && threadIdx.x < 4 && j.err) j.err[threadIdx.x] = 0;
+  if (j.fmean == nullptr) return;
+  const int k = w / j.B, b = w - k * j.B;
+  const float* m1 = j.fmean + ((size_t)j.fs1[k] * j.B + b) * j.nsplit * j.ldf;   // nsplit partial means each
+  const float* m2 = j.fmean + ((size_t)j.fs2[k] * j.B + b) * j.nsplit * j.ldf;
+  float s = 0.f;
+  for (int c = threadIdx.x; c < j.ldf; c += 256) {
+    float a = 0.f, bb = 0.f;
+    for (int i = 0; i < j.nsplit; ++i) {
+      a += __ldg(m1 + (size_t)i * j.ldf + c);
+      bb += __ldg(m2 + (size_t)i * j.ldf + c);
+    }
+    s += a * bb;
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) pd_red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += pd_red[i];
+    j.dots[w] = t;
+  }
+}
+
 // dsign != null: also writes the depth signs of depth_a (what launch_depth_sign computes) from the same CTA
 int launch_fps(const float* depth_a, const float* depth_b, int B, int Hd, int Wd, int H, int W, int S, float factor,
                float far_plane, int affine, float* coords, int32_t* idx, cudaStream_t st, float* dsign = nullptr,
@@ -55,7 +93,8 @@ int launch_depth_sign(const float* depth, int B, int Hd, int Wd, int S, float ep
 // meanvec is written as `nsplit` partial means per (slot, image): [slot,b,nsplit,ld], each already divided by P
 int gather_nsplit(int fmt, const SetTable& tab, int nsets, int C, int ld);
 int launch_gather(int fmt, const SetTable& tab, int nsets, int B, int C, int H, int W, const float* coords, int S,
-                  const int64_t* perms, float eps, int Prows, int ld, int nsplit, const GatherOut& o, cudaStream_t st);
+                  const int64_t* perms, float eps, int Prows, int ld, int nsplit, const GatherOut& o, cudaStream_t st,
+                  const DotsJob* tail = nullptr);  // tail: extra CTAs of the code gather that do the pair_dots work
 int launch_nchw_to_nhwc(const float* a, const float* b, int B, int C, int HW, int64_t sb_a, int64_t sb_b, float* out_a,
                         float* out_b, cudaStream_t st);
 int launch_gather_all(const SetTable& fsets, const SetTable& csets, int nsets, int B, int C, int D, int H, int W,
@@ -75,7 +114,9 @@ int corr_loss_umma(const dg_panels_t* pan, const float* fmean, int nsplit, const
                    int ldc, const float* pair_shift, const int32_t* pair_group, float depth_shift, int flags,
                    float* out8, float* dC1, float* dC2, float* cd_out, float* loss_out, float* dd_out, float* fd_dbg,
                    void* ws, cudaStream_t st, const int32_t* fslot1 = nullptr, const int32_t* fslot2 = nullptr,
-                   int nfslots = 0);
+                   int nfslots = 0, bool dots_done = false);
+// where corr_loss_umma keeps its error flag / completion counter and the pair dots inside its workspace
+void umma_ws_layout(void* ws, int** err, float** dots);
 size_t corr_workspace_bytes(int npairs, int B, int P);
 
 }  // namespace dg

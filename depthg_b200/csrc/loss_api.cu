@@ -185,6 +185,7 @@ extern "C" int dg_loss_forward(const dg_loss_desc_t* d, const dg_loss_io_t* io, 
   co.meanvec = nullptr;
   // (a single merged launch — launch_gather_all — was measured slower: the code CTAs inherit the feature
   //  kernel's register footprint and lose the occupancy that hides their latency; kept for experiments)
+  bool dots_done = false;
   rc = DG_ERR_UNSUPPORTED;
   if (pl.kernel && !aug && getenv("DEPTHG_B200_GATHER_ALL"))
     rc = launch_gather_all(ftab, ctab, nsets, B, d->C, d->D, d->H, d->W, coords, S, io->perms, kNormEps, pl.Prows, pl.ldf,
@@ -193,8 +194,16 @@ extern "C" int dg_loss_forward(const dg_loss_desc_t* d, const dg_loss_io_t* io, 
     rc = launch_gather(ffmt, ftab, nsets, B, d->C, d->H, d->W, coords, S, io->perms, kNormEps, pl.Prows, pl.ldf, nsplit, fo,
                        st);
     if (rc != DG_OK) return rc;
+    DotsJob job;
+    if (pl.kernel) {   // the pair dots / flag reset of the tcgen05 kernel ride along as extra CTAs of the code gather
+      job.fmean = fmean;
+      umma_ws_layout(A + pl.ws, &job.err, &job.dots);
+      job.nsplit = nsplit; job.npairs = np; job.B = B; job.ldf = pl.ldf;
+      for (int k = 0; k < DG_MAX_PAIRS; ++k) { job.fs1[k] = k < np ? fs1[k] : 0; job.fs2[k] = k < np ? fs2[k] : 0; }
+      dots_done = true;
+    }
     rc = launch_gather(pl.kernel ? FMT_CODE_SPLIT : FMT_F32, ctab, ncsets, B, d->D, d->H, d->W, coords, S, io->perms,
-                       kNormEps, pl.Prows, pl.ldc, 1, co, st);
+                       kNormEps, pl.Prows, pl.ldc, 1, co, st, pl.kernel ? &job : nullptr);
   }
   if (rc != DG_OK) return rc;
 
@@ -213,7 +222,7 @@ extern "C" int dg_loss_forward(const dg_loss_desc_t* d, const dg_loss_io_t* io, 
     pan.cb_hi = A + pl.cb_hi; pan.cb_lo = A + pl.cb_lo;
     return corr_loss_umma(&pan, fmean, nsplit, dsign, np, B, P, pl.Prows, pl.ldf, pl.ldc, shifts, groups, d->depth_feat_shift, kflags,
                           io->out8, dC1, dC2, io->cd_out, io->loss_out, io->dd_out, io->fd_dbg, A + pl.ws, st, fs1, fs2,
-                          aug ? np + 1 : np);
+                          aug ? np + 1 : np, dots_done);
   }
   return corr_loss_simt(reinterpret_cast<const float*>(A + pl.f_hi), reinterpret_cast<const float*>(A + pl.c_hi), fmean,
                         nsplit, dsign, np, B, P, pl.Prows, pl.ldf, pl.ldc, shifts, groups, d->depth_feat_shift, kflags, io->out8,

@@ -92,6 +92,7 @@ class _GraphedSuperPerms:
     _cache = {}
 
     _side = {}
+    _events = {}
 
     @classmethod
     def draw(cls, n: int, size: int, device) -> torch.Tensor:
@@ -118,9 +119,11 @@ class _GraphedSuperPerms:
         side = cls._side.get(device.index)
         if side is None:
             side = cls._side[device.index] = torch.cuda.Stream(device=device)
+        ev = cls._events.get(device.index)
+        if ev is None:   # one event per device: a pending wait keeps the record it was issued against
+            ev = cls._events[device.index] = torch.cuda.Event()
         with torch.cuda.stream(side):
             perms = cls.draw(n, size, device)
-            ev = torch.cuda.Event()
             ev.record(side)
         perms.record_stream(main)   # allocated on the side stream, consumed on the main one
         return perms, ev
@@ -272,6 +275,7 @@ class _CorrLossFn(torch.autograd.Function):
     the upstream scalars and scatters them through normalise + bilinear gather into the code grads."""
 
     debug = False           # tests: keep views of the unit gradients / dump raw tcgen05 feature correlations
+    last_coords_off = 0
     last_fd = None
     last_unit_grads = None
 
@@ -329,11 +333,12 @@ class _CorrLossFn(torch.autograd.Function):
             _CorrLossFn.last_unit_grads = (d1, d2)
         else:
             _CorrLossFn.last_unit_grads = None
-        if desc.flags & _lib.FLAG_FPS:   # the coordinates FPS produced (a view into the arena)
-            coords_used = arena[plan.coords:plan.coords + 2 * B * P * 2 * 4].view(torch.float32).view(2, B, S, S, 2)
-        else:
-            coords_used = out8.new_empty(0)
-        outs = [out8[0], out8[2], out8[4], out8[6], out8.detach(), coords_used]
+        # the coordinates FPS produced live at plan.coords in the arena; the module slices them lazily (last_coords)
+        coords_src = arena if (desc.flags & _lib.FLAG_FPS) else out8.new_empty(0)
+        ctx.coords_off = plan.coords
+        _CorrLossFn.last_coords_off = plan.coords
+        u = out8.unbind(0)               # one op instead of four index kernels-worth of host time
+        outs = [u[0], u[2], u[4], u[6], out8.detach(), coords_src]
         dense = [cd_out, loss_out, dd_out]
         ctx.mark_non_differentiable(outs[4], outs[5], *[t for t in dense if t is not None])
         return (*outs, *dense)
@@ -396,7 +401,22 @@ class ContrastiveCorrelationLoss(nn.Module):
         # test hooks (CPU and CUDA RNG streams differ): same contract as the oracle's
         self.perm_fn = super_perm
         self.rand_fn = lambda shape, device: torch.rand(shape, device=device)
-        self.last_coords = None
+        self._last_coords = None
+
+    @property
+    def last_coords(self):
+        """The [2,B,S,S,2] sample coordinates of the last call (test hook, same contract as the oracle's).  With FPS
+        sampling they are a view into the call's arena, built on first access."""
+        v = self._last_coords
+        if isinstance(v, tuple):
+            arena, off, B, S = v
+            v = arena[off:off + 2 * B * S * S * 2 * 4].view(torch.float32).view(2, B, S, S, 2)
+            self._last_coords = v
+        return v
+
+    @last_coords.setter
+    def last_coords(self, value):
+        self._last_coords = value
 
     def _flags(self):
         cfg = self.cfg
@@ -409,6 +429,7 @@ class ContrastiveCorrelationLoss(nn.Module):
 
     def _run(self, orig_feats, orig_feats_pos, orig_code, orig_code_pos, depth, depth_pos, aug_feats):
         cfg = self.cfg
+        self._last_coords = None   # do not keep the previous call's arena alive across this call's allocation
         for name, t in (("orig_feats", orig_feats), ("orig_feats_pos", orig_feats_pos), ("orig_code", orig_code),
                         ("orig_code_pos", orig_code_pos)):
             require_cuda_f32(t, name)
@@ -486,8 +507,9 @@ class ContrastiveCorrelationLoss(nn.Module):
                              float(cfg.depth_feat_shift) if depth_term else 0.0)
         res = _CorrLossFn.apply(orig_feats, orig_feats_pos, orig_code, orig_code_pos, depth, depth_pos, coords, perms,
                                 desc, bool(self.materialize_cd), perms_event, aug_feats)
-        intra, inter, neg, dloss, out8, coords_used, cd_out, loss_out, dd_out = res
-        self.last_coords = coords_used if (flags & _lib.FLAG_FPS) else coords
+        intra, inter, neg, dloss, out8, coords_src, cd_out, loss_out, dd_out = res
+        # FPS coordinates stay in the arena until someone asks for them (see the last_coords property)
+        self._last_coords = (coords_src, _CorrLossFn.last_coords_off, B, S) if (flags & _lib.FLAG_FPS) else coords
         if self.materialize_cd:
             five = (B, S, S, S, S)
             intra_cd, inter_cd = cd_out[0].view(five), cd_out[1].view(five)
@@ -498,7 +520,8 @@ class ContrastiveCorrelationLoss(nn.Module):
             neg_loss = neg_dense + (neg - neg.detach())
             dd = dd_out.view(five) if depth_term else None
         else:
-            intra_cd, inter_cd, neg_cd, dd = out8[1], out8[3], out8[5], out8[7]
+            v = out8.unbind(0)
+            intra_cd, inter_cd, neg_cd, dd = v[1], v[3], v[5], v[7]
             neg_loss = neg
         head = (intra, intra_cd, inter, inter_cd, neg_loss, neg_cd)
         if depth_term:

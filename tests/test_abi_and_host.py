@@ -70,6 +70,51 @@ def test_host_layer_refuses_cpu_tensors_and_bad_modes():
         M._lib.require_cuda_f32(np.zeros(3), "x")
 
 
+def test_probe_host_layer_validates_without_a_gpu():
+    """probes.py: no CPU fallback, the reference's detach contract is enforced, plan/workspace sizes are sane."""
+    from depthg_b200 import _lib
+    from depthg_b200.probes import ClusterLookup, linear_probe_loss
+    code = torch.zeros(2, 16, 7, 7)
+    with pytest.raises(ValueError, match="CUDA"):
+        linear_probe_loss(code, torch.zeros(5, 16, 1, 1), torch.zeros(5), torch.zeros(2, 56, 56, dtype=torch.int64))
+    probe = ClusterLookup(16, 5)
+    assert tuple(probe.clusters.shape) == (5, 16) and list(probe.state_dict()) == ["clusters"]
+    with pytest.raises(ValueError, match="CUDA"):
+        probe(code, None)
+    with pytest.raises(ValueError, match="not supported"):
+        ClusterLookup(16, 33)
+    lib = _lib.lib()
+    assert lib.dg_probe_workspace_bytes(0, 7, 7, 16, 5) == 0
+    small, big = lib.dg_probe_workspace_bytes(2, 7, 7, 16, 5), lib.dg_probe_workspace_bytes(32, 28, 28, 90, 27)
+    assert 0 < small < big and big >= 2 * 32 * 28 * 28 * 32 * 4
+    assert lib.dg_linear_probe_ce(None, None, 2, 16, 7, 7, None, None, 5, None, None, 56, 56, None, None, None, None, 0,
+                                  None) == -1
+    assert b"null pointer" in lib.dg_last_error_string()
+    assert lib.dg_cluster_probe(None, None, 2, 16, 7, 7, None, 5, 0, 0.0, None, None, None, None, 0, None) == -1
+
+
+def test_loss_plan_sizes_for_sampled_and_dense_shapes():
+    """dg_loss_plan is host-only: panel row padding and partial-buffer counts of the tcgen05 path."""
+    import ctypes as C
+    from depthg_b200 import _lib
+    lib = _lib.lib()
+
+    def plan(S, flags=1 | 2, B=4, Cdim=64, D=24):
+        desc = _lib.LossDesc(B, Cdim, D, 28, 28, 224, 224, S, 2, flags, 0.1, 0.2, 0.3, 0.0)
+        p = _lib.LossPlan()
+        _lib.check(lib.dg_loss_plan(C.byref(desc), C.byref(p)), "dg_loss_plan")
+        return p
+
+    p11, p12, p17, p28 = plan(11), plan(12), plan(17), plan(28)
+    assert (p11.kernel, p11.Prows) == (1, 128) and (p12.kernel, p12.Prows) == (1, 256)
+    assert (p17.kernel, p17.Prows) == (1, 512) and (p28.kernel, p28.Prows) == (1, 1024)
+    assert p11.total < p12.total < p17.total < p28.total
+    forced = plan(11, flags=1 | 2 | _lib.FLAG_FORCE_SIMT)
+    assert (forced.kernel, forced.Prows) == (0, 128)
+    desc = _lib.LossDesc(4, 64, 24, 28, 28, 224, 224, 30, 2, 3, 0.1, 0.2, 0.3, 0.0)   # 900 points > 784 grid points
+    assert lib.dg_loss_plan(C.byref(desc), C.byref(_lib.LossPlan())) == -1
+
+
 def test_missing_library_fails_loudly(monkeypatch):
     from depthg_b200 import _lib
     monkeypatch.setattr(_lib, "_lib", None)

@@ -39,6 +39,10 @@ LOSS_CASES = {
                                           depth_feat_shift=0.01), 21),
     # dense, unsampled correlation (BASELINE configs[4]) on a small grid: every grid point is a sample
     "dense_14x14": (2, 48, 24, dict(feature_samples=14), 22),
+    # the full 28x28 stress shape (784 x 784 per pair): FPS then selects every grid point; tcgen05 column-group mode
+    "dense_28x28": (2, 32, 16, dict(feature_samples=28, neg_samples=2), 23),
+    # 20 x 20 = 400 random points: four row tiles x two column groups, pointwise off
+    "dense_400_random": (2, 64, 40, dict(feature_samples=20, depth_sampling="none", pointwise=False, neg_samples=2), 24),
 }
 
 # DepthContrastiveCorrelationLoss (src/modules.py:1370-1463) cases: name -> base loss case + seed of the augmented features

@@ -147,7 +147,8 @@ def test_loss_and_grads_match_reference_golden(name, channels_last):
         assert o.dim() == 0  # fast mode: 0-dim means, nothing 5-D in HBM
 
 
-@pytest.mark.parametrize("name", ["small_fps", "small_random", "small_fps_nodepthterm", "small_fps_stabalize"])
+@pytest.mark.parametrize("name", ["small_fps", "small_random", "small_fps_nodepthterm", "small_fps_stabalize",
+                                  "dense_400_random"])
 def test_materialized_5d_outputs_match_reference_golden(name):
     from tests.gpu_helpers import run_cuda_loss
     g = golden("loss_" + name)

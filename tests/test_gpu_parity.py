@@ -147,8 +147,7 @@ def test_loss_and_grads_match_reference_golden(name, channels_last):
         assert o.dim() == 0  # fast mode: 0-dim means, nothing 5-D in HBM
 
 
-@pytest.mark.parametrize("name", ["small_fps", "small_random", "small_fps_nodepthterm", "small_fps_stabalize",
-                                  "dense_400_random"])
+@pytest.mark.parametrize("name", ["small_fps", "small_random", "small_fps_nodepthterm", "small_fps_stabalize"])
 def test_materialized_5d_outputs_match_reference_golden(name):
     from tests.gpu_helpers import run_cuda_loss
     g = golden("loss_" + name)
@@ -356,7 +355,7 @@ def _run_both_kernels(name, monkeypatch):
 
 
 @pytest.mark.parametrize("name", ["small_fps", "small_random_pointwise", "cfg1_vits", "small_fps_noclamp", "s12_fps",
-                                  "dense_14x14", "cfg4_cityscapes"])
+                                  "dense_14x14", "cfg4_cityscapes", "dense_400_random"])
 def test_tcgen05_kernel_matches_generic_kernel_stage_by_stage(name, monkeypatch):
     from depthg_b200.modules import corr_kernel_choice
     cfg, t, res = _run_both_kernels(name, monkeypatch)

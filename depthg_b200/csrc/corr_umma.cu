@@ -50,6 +50,10 @@ struct UmmaParams {
   // cg*NT .. cg*NT+NT-1.  S*S <= 256: nti = NT, ncg = 1 (the CTA sees every column and forms the row means itself).
   // S*S > 256 ("dense"): NT = 2, ncg > 1, row means come from row_means_kernel, dC1 is written per column group.
   int prows, nti, ncg, nti_stride, ncg_stride;
+  // A dense shape with an odd number of column tiles is covered by TWO launches: groups 0 .. ncg-2 with NT = 2 and the
+  // last, half-empty group with NT = 1 (cg_base = its global index).  Both write one partial-sum slot per
+  // (pair, image, row tile, global group) and share the completion counter; ncg_total groups exist in all.
+  int cg_base, ncg_total;
   const float* rowmean;        // [npairs,B,prows] mean_q fd[p,q] (dense + pointwise) or null
   float depth_shift, inv_cnt;
   float shift[DG_MAX_PAIRS];
@@ -154,9 +158,10 @@ __global__ void __launch_bounds__(UM_THREADS, 1) corr_umma_kernel(const __grid_c
   // work item: (pair k, image b, 128-row tile ti of the first operand, column group cg); the CTA walks the NT
   // column tiles gj0 .. gj0+NT-1 of its group itself
   const int Prows = prm.prows;
-  const int cg = blockIdx.x % prm.ncg, rt = blockIdx.x / prm.ncg;
+  const int cg = prm.cg_base + (int)(blockIdx.x % prm.ncg), rt = blockIdx.x / prm.ncg;
   const int ti = rt % prm.nti, kb = rt / prm.nti;
-  const int gj0 = cg * NT;
+  const int gj0 = cg * 2;                  // groups are two tiles wide (cg = 0 whenever the CTA sees every column)
+  const int slot_id = (kb * prm.nti + ti) * prm.ncg_total + cg;
   const int k = kb / prm.B, b = kb - k * prm.B;
   const int nfd = (prm.ldf + 63) / 64, ncd = prm.ldc / 32, nb = prm.ldc / 32;
   const int nop = nfd + ncd;                                  // operand chunks per column tile
@@ -584,7 +589,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) corr_umma_kernel(const __grid_c
         float t = 0.f;
 #pragma unroll
         for (int w8 = 0; w8 < 8; ++w8) t += s_red[w8][lane];
-        prm.partials[(size_t)blockIdx.x * 4 + lane] = t;
+        prm.partials[(size_t)slot_id * 4 + lane] = t;
       }
       // ---- fused finalize: the last CTA to get here folds all partial sums into the 8 output scalars.
       //      __syncwarp orders the four partial stores before lane 0's acq_rel counter increment, which publishes them
@@ -594,11 +599,11 @@ __global__ void __launch_bounds__(UM_THREADS, 1) corr_umma_kernel(const __grid_c
       if (lane == 0)
         asm volatile("atom.add.acq_rel.gpu.global.s32 %0, [%1], 1;" : "=r"(ticket) : "l"(prm.done) : "memory");
       ticket = __shfl_sync(0xffffffffu, ticket, 0);
-      if (ticket == (int)gridDim.x - 1) {
+      if (ticket == prm.npairs * prm.B * prm.nti * prm.ncg_total - 1) {
         float acc[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-        const int per_pair = prm.B * prm.nti * prm.ncg;
+        const int per_pair = prm.B * prm.nti * prm.ncg_total;
         const int total = prm.npairs * per_pair;
         for (int e = lane; e < total; e += 32) {   // fixed order -> deterministic
           const int kk = e / per_pair;
@@ -754,7 +759,10 @@ int corr_loss_umma(const dg_panels_t* pan, const float* fmean, int nsplit, const
   prm.dots = (flags & DG_FLAG_POINTWISE) ? dots : nullptr;
   prm.npairs = npairs; prm.B = B; prm.P = P; prm.ldf = ldf; prm.ldc = ldc; prm.flags = flags;
   prm.ntile = ntile;
-  prm.prows = Prows; prm.nti = nti; prm.ncg = ncg;
+  // odd number of column tiles: the last group holds one real tile -> its own NT = 1 launch (no all-padding tile)
+  const bool odd_tail = dense && (nti & 1);
+  prm.prows = Prows; prm.nti = nti; prm.ncg = odd_tail ? ncg - 1 : ncg;
+  prm.cg_base = 0; prm.ncg_total = ncg;
   prm.nti_stride = ntile; prm.ncg_stride = dense ? Prows / 256 : 1;
   prm.rowmean = (dense && (flags & DG_FLAG_POINTWISE)) ? rowmean : nullptr;
   prm.has_depth = dsign != nullptr;
@@ -801,8 +809,15 @@ int corr_loss_umma(const dg_panels_t* pan, const float* fmean, int nsplit, const
   }
   DG_PRE(st);
   if (ntile == 1) corr_umma_kernel<1><<<npairs * B, UM_THREADS, UM_SMEM, st>>>(prm);
-  else corr_umma_kernel<2><<<npairs * B * nti * ncg, UM_THREADS, UM_SMEM, st>>>(prm);
+  else corr_umma_kernel<2><<<npairs * B * nti * prm.ncg, UM_THREADS, UM_SMEM, st>>>(prm);
   DG_LAUNCH_OK("corr_umma_kernel");
+  if (odd_tail) {
+    prm.ncg = 1;
+    prm.cg_base = ncg - 1;
+    DG_PRE(st);
+    corr_umma_kernel<1><<<npairs * B * nti, UM_THREADS, UM_SMEM, st>>>(prm);
+    DG_LAUNCH_OK("corr_umma_kernel");
+  }
   return DG_OK;  // out8 is written by the last CTA of corr_umma_kernel
 }
 

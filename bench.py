@@ -8,6 +8,15 @@ One "step" = ContrastiveCorrelationLoss forward + backward (depth-guided FPS, bi
 gathers, fused correlation loss, scatter backward) on one batch of the cocostuff27
 ViT-B/8 training shape (BASELINE.json configs[1]): B=32 per GPU, C=768, 28x28, dim=90,
 feature_samples=11, fps sampling, pointwise, depth term on.  Prints ONE JSON line.
+
+Keys beyond the base contract: ``roofline`` (dominant kernel, live CUDA-event time, ncu DRAM traffic),
+``roofline_step``, ``breakdown_us`` (library-side per-kernel events), ``e2e`` (pinned host buffers, the faster of a
+double-buffered and a serialised loop, both reported), ``cpu_baseline`` (oracle port on the host cores),
+``reference_ops_on_gpu`` (the reference's op sequence as stock torch ops on this GPU), ``cuda_graph`` and
+``fused_negative_sampler`` (same step, less host work), ``knn`` (the precompute_knns build, query-sharded at N > 1)
+and ``probes`` (fused probe losses vs the trainer's torch op sequence).  At N > 1 every step is followed by the
+all-reduce of the trainable-head gradient (729 012 floats), replayed as a captured NCCL graph in stream order
+(DEPTHG_BENCH_ALLREDUCE = inline | graph | graph_hp | async | none).
 """
 from __future__ import annotations
 

@@ -48,6 +48,17 @@ void profile_post(const char* name);
     ::dg::profile_post(name);                                                                \
   } while (0)
 
+// cudaFuncSetAttribute applies to the CURRENT device only, so "already configured" is remembered per device
+// (one process per GPU is the normal deployment, but tests may touch several devices from one process).
+struct PerDevice {
+  size_t v[64];
+};
+inline size_t& per_device(PerDevice& s) {
+  int d = 0;
+  cudaGetDevice(&d);
+  return s.v[(d >= 0 && d < 64) ? d : 0];
+}
+
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 __host__ __device__ inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
 

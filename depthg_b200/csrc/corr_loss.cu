@@ -446,7 +446,8 @@ int corr_loss_simt(const float* fn, const float* cn, const float* fmean, int nsp
   const size_t slab = (size_t)B * Prows * ldc * sizeof(float);
   DG_CUDA_OK(cudaMemsetAsync(dC2, 0, slab * (npairs + 1), st));
   const size_t smem = ((size_t)2 * KC * ASTR + (size_t)TM * USTR + (size_t)2 * TM * (ldc + 1)) * sizeof(float);
-  static size_t configured = 0;
+  static PerDevice configured_pd = {};
+  size_t& configured = per_device(configured_pd);
   if (smem > configured) {
     DG_CUDA_OK(cudaFuncSetAttribute(corr_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;

@@ -801,11 +801,12 @@ int corr_loss_umma(const dg_panels_t* pan, const float* fmean, int nsplit, const
         Prows, ldf, rowmean, sm);
     DG_LAUNCH_OK("row_means_kernel");
   }
-  static bool attr_set = false;
+  static PerDevice attr_pd = {};
+  size_t& attr_set = per_device(attr_pd);
   if (!attr_set) {
     DG_CUDA_OK(cudaFuncSetAttribute(corr_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, UM_SMEM));
     DG_CUDA_OK(cudaFuncSetAttribute(corr_umma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, UM_SMEM));
-    attr_set = true;
+    attr_set = 1;
   }
   DG_PRE(st);
   if (ntile == 1) corr_umma_kernel<1><<<npairs * B, UM_THREADS, UM_SMEM, st>>>(prm);

@@ -262,7 +262,8 @@ int launch_fps(const float* depth_a, const float* depth_b, int B, int Hd, int Wd
   const size_t smem = base_smem + (stage ? img_bytes : 0);
 #define DG_FPS_LAUNCH(PPT, ST, RTV, PRV)                                                                                    \
   do {                                                                                                            \
-    static size_t configured = 0;                                                                                 \
+    static PerDevice configured_pd = {};                                                                          \
+    size_t& configured = per_device(configured_pd);                                                               \
     if (smem > 48 * 1024 && smem > configured) {                                                                  \
       DG_CUDA_OK(cudaFuncSetAttribute(fps_kernel<PPT, ST, RTV, PRV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
       configured = smem;                                                                                          \

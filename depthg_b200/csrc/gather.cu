@@ -642,7 +642,8 @@ int launch_gather(int fmt, const SetTable& tab, int nsets, int B, int C, int H, 
   DG_REQUIRE(smem <= 200 * 1024, DG_ERR_UNSUPPORTED, "gather: C=%d too large for the row staging buffer", C);
 #define DG_GATHER_LAUNCH(F)                                                                                        \
   do {                                                                                                             \
-    static size_t configured = 0;                                                                                  \
+    static PerDevice configured_pd = {};                                                                           \
+    size_t& configured = per_device(configured_pd);                                                                \
     if (smem > configured) {                                                                                       \
       DG_CUDA_OK(cudaFuncSetAttribute(gather_norm_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
       configured = smem;                                                                                           \

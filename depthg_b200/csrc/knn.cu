@@ -301,7 +301,8 @@ int launch_knn_exact(const float* q, const float* db, int Nq, int N, int F, int 
   if (row_list) {
     const size_t smem = ((size_t)FEW_ROWS * F + 2 * FEW_ROWS * FEW_WARPS * 32) * sizeof(float);
     DG_REQUIRE(smem <= 200 * 1024, DG_ERR_UNSUPPORTED, "knn: feature dimension %d too large for the few-rows kernel", F);
-    static size_t configured = 0;
+    static PerDevice configured_pd = {};
+    size_t& configured = per_device(configured_pd);
     if (smem > configured) {
       DG_CUDA_OK(cudaFuncSetAttribute(knn_fewrows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       configured = smem;

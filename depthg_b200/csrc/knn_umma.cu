@@ -465,11 +465,12 @@ int knn_topk_umma(const float* q, const float* db, int Nq, int N, int F, int k, 
   if ((rc = make_map(&prm.tm_dl, dl, Fp, N, BN, KC))) return rc;
   prm.Nq = Nq; prm.N = N; prm.nchunk = Fp / KC; prm.ntiles = ceil_div(N, BN); prm.nseg = nseg;
   prm.cand_idx = cand_idx; prm.cand_val = cand_val; prm.err = err;
-  static bool attr_set = false;
+  static PerDevice attr_pd = {};
+  size_t& attr_set = per_device(attr_pd);
   if (!attr_set) {
     DG_CUDA_OK(cudaFuncSetAttribute(knn_umma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, KuCfg<128>::SMEM));
     DG_CUDA_OK(cudaFuncSetAttribute(knn_umma_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, KuCfg<256>::SMEM));
-    attr_set = true;
+    attr_set = 1;
   }
   DG_PRE(st);
   if (BN == 128)

@@ -554,10 +554,11 @@ extern "C" int dg_cluster_probe(const float* code, const int64_t* strides, int B
   const size_t smem = (size_t)(N * (D | 1) + N * D + 4 + 8 * 128 * 4) * sizeof(float);
   const int grid = min(ceil_div(npix, 32), CLUSTER_GRID);
   const bool need_part = mode != 2 && (loss_out || dclusters);
-  static bool attr_done = false;
+  static PerDevice attr_pd = {};
+  size_t& attr_done = per_device(attr_pd);
   if (!attr_done) {  // up to ~50 KB at N = 32, D = 128
     DG_CUDA_OK(cudaFuncSetAttribute(cluster_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    attr_done = true;
+    attr_done = 1;
   }
   DG_PRE(st);
   cluster_probe_kernel<<<grid, 256, smem, st>>>(code, strides[0], strides[1], strides[2], strides[3], D, h, w, npix,

@@ -268,6 +268,12 @@ def tensor_correlation(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     return cd[1].reshape(n, h, w, h, w)
 
 
+def depth_correlation(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """Drop-in for src/modules.py:812-814: the same einsum on [N,1,S,S] depth maps (an outer product per image).
+    Inside the loss this term is never materialised (the kernel multiplies the two depth signs in registers)."""
+    return tensor_correlation(a, b)
+
+
 # --------------------------------------------------------------------------- the loss
 class _CorrLossFn(torch.autograd.Function):
     """forward: FPS / gathers / depth signs / fused correlation loss (values + unit gradients) in ONE

@@ -110,6 +110,18 @@ def test_tensor_correlation_matches_reference_golden():
     assert rel_err(got.numpy(), want.numpy()) < 1e-5
 
 
+def test_depth_correlation_is_the_single_channel_einsum():
+    """src/modules.py:812-814 (a3): the c = 1 case of tensor_correlation, on the {0, 1} depth signs the loss uses."""
+    from depthg_b200.modules import depth_correlation
+    rs = np.random.RandomState(22)
+    a = torch.from_numpy((rs.random_sample((2, 1, 7, 7)) > 0.3).astype(np.float32))
+    b = torch.from_numpy((rs.random_sample((2, 1, 7, 7)) > 0.5).astype(np.float32))
+    got = depth_correlation(a.to(dev()), b.to(dev())).cpu()
+    want = O.depth_correlation(a, b)
+    assert got.shape == want.shape == (2, 7, 7, 7, 7)
+    assert torch.equal(got, want)
+
+
 def test_depth_sign_matches_reference_golden():
     import ctypes
     from depthg_b200 import _lib

@@ -222,6 +222,26 @@ def workload_config(B, n_gpus, extra=None):
 
 
 # ----------------------------------------------------------------------------- our arm
+def knn_cpu_baseline(N, F, k, chunks=2):
+    """The reference's KNN loop (src/precompute_knns.py:99-113, oracle port) on the host cores, on a bounded sample:
+    `chunks` of its N // 64 query-row chunks against the full database."""
+    from oracle import depthg_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    g = torch.Generator().manual_seed(7)
+    db = torch.nn.functional.normalize(torch.randn((N, F), generator=g), dim=1)
+    step = N // 64
+    rows = min(N, chunks * step)
+    O.knn_rows(db[:step // 8], db, k)                         # warm-up (thread pool, allocator)
+    t0 = time.perf_counter()
+    for i in range(0, rows, step):
+        O.knn_rows(db[i:i + step], db, k)
+    dt = time.perf_counter() - t0
+    return {"value": rows / dt, "unit": "img/s", "cores": cores, "kind": "port",
+            "sample": f"{rows} of {N} query rows ({chunks} of the reference's 64 chunks) against the full database",
+            "seconds": dt, "full_build_s_extrapolated": dt * N / rows}
+
+
 def probe_bench(dev, B, n=30):
     """Linear-probe CE and cluster-probe loss fwd+bwd at the cfg2 shapes (D=90, 28x28 code, 27 classes,
     224x224 labels): depthg_b200.probes vs the trainer's torch op sequence (src/train_segmentation.py:419-441)."""
@@ -654,6 +674,12 @@ def main():
                             "unit": "TFLOP/s", "frac": flops / (kms / 1e3) / 1e12 / tf_burst,
                             "note": "tcgen05 bf16 3-product split (3 MMAs per useful product) + exact fp32 re-rank; "
                                     "flops counted once (2 N^2 F), peak is the bf16 tensor burst figure"}}
+
+    if knn is not None and rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            knn["cpu_baseline"] = knn_cpu_baseline(KNN["N"], KNN["F"], KNN["k"])
+        except Exception as e:  # noqa: BLE001  (auxiliary)
+            knn["cpu_baseline"] = {"error": f"{type(e).__name__}: {e}"[:200]}
 
     # ---- CPU baseline (oracle port) on this box's host cores, rank 0 at N=1 only
     cpu_baseline = None

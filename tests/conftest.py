@@ -18,7 +18,7 @@ def pytest_configure(config):
         import shutil
         import subprocess
         if shutil.which("nvcc") and shutil.which("make"):
-            subprocess.run(["make", "-C", os.path.join(ROOT, "depthg_b200", "csrc")], check=False,
+            subprocess.run(["make", "-C", os.path.join(ROOT, "depthg_b200", "csrc"), "-j", str(os.cpu_count() or 4)], check=False,
                            stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
 
 

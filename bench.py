@@ -9,12 +9,14 @@ gathers, fused correlation loss, scatter backward) on one batch of the cocostuff
 ViT-B/8 training shape (BASELINE.json configs[1]): B=32 per GPU, C=768, 28x28, dim=90,
 feature_samples=11, fps sampling, pointwise, depth term on.  Prints ONE JSON line.
 
-Keys beyond the base contract: ``roofline`` (dominant kernel, live CUDA-event time, ncu DRAM traffic),
-``roofline_step``, ``breakdown_us`` (library-side per-kernel events), ``e2e`` (pinned host buffers, the faster of a
+Keys beyond the base contract: ``roofline`` (SURVEY 8(d)'s algorithmic bytes of the step over the dominant kernel's
+live CUDA-event time, with the kernel's ncu DRAM traffic and traffic / algorithmic beside it), ``roofline_step``
+(the same bytes over the whole step), ``extra_configs`` (BASELINE configs[3], the S = 12 paper value and the dense
+configs[4] as side measurements), ``breakdown_us`` (library-side per-kernel events), ``e2e`` (pinned host buffers, the faster of a
 double-buffered and a serialised loop, both reported), ``cpu_baseline`` (oracle port on the host cores),
 ``reference_ops_on_gpu`` (the reference's op sequence as stock torch ops on this GPU), ``cuda_graph`` and
-``fused_negative_sampler`` (same step, less host work), ``knn`` (the precompute_knns build, query-sharded at N > 1)
-and ``probes`` (fused probe losses vs the trainer's torch op sequence).  At N > 1 every step is followed by the
+``fused_negative_sampler`` (same step, less host work), ``knn`` (the precompute_knns build, query-sharded at N > 1; ``parity_checked`` = the timed
+result against the oracle on sampled rows and, at N > 1, against a one-GPU build) and ``probes`` (fused probe losses vs the trainer's torch op sequence).  At N > 1 every step is followed by the
 all-reduce of the trainable-head gradient (729 012 floats), replayed as a captured NCCL graph in stream order
 (DEPTHG_BENCH_ALLREDUCE = inline | graph | graph_hp | async | none).
 """
@@ -185,27 +187,33 @@ def run_reference(args):
 
     B = CFG2["B"]
     inp = synth_inputs(B, gen, "cpu")
+    # Always the full cfg2 batch (the config the GPU arm runs per GPU).  One CPU process runs it whatever --gpus says:
+    # the printed config names the batch that actually ran, never B x N.  A step is ~0.4 s on 16 cores, so the
+    # requested steps fit in a few minutes; on a much slower host the STEP COUNT is cut, not the batch.
+    one_step(inp)                                   # untimed: thread pool, allocator, first-touch
     t0 = time.perf_counter()
     one_step(inp)
     first = time.perf_counter() - t0
-    budget = 150.0
-    while B > 2 and first * (B / CFG2["B"]) * (args.steps + args.warmup) > budget:
-        B //= 2
-    if B != CFG2["B"]:
-        inp = synth_inputs(B, gen, "cpu")
-    for _ in range(args.warmup):
+    budget = 240.0
+    steps, warmup = args.steps, args.warmup
+    if first * (steps + warmup) > budget:
+        warmup = 1
+        steps = max(3, int(budget / first) - warmup)
+    for _ in range(warmup):
         one_step(inp)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         one_step(inp)
     dt = time.perf_counter() - t0
-    value = B * args.steps / dt
+    value = B * steps / dt
+    cfgd = workload_config(B, 1, extra={"device": "cpu", "parallelism": "one host process, %d threads" % cores,
+                                        "gpus_requested": args.gpus})
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "steps": steps, "warmup": warmup, "ms_per_step": dt / steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(B, args.gpus, extra={"device": "cpu"}),
+            "config": cfgd,
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{args.steps} steps of {B} samples of the cfg2 shape (fwd+bwd incl. NumPy FPS)"},
+                             "sample": f"{steps} steps of {B} samples of the cfg2 shape (fwd+bwd incl. NumPy FPS)"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -298,6 +306,78 @@ def probe_bench(dev, B, n=30):
     return out
 
 
+def side_config(dev, name, B, C, D, S, sampling, pointwise, steps, peaks_):
+    """Device-resident fwd+bwd of one of the OTHER BASELINE configs (cfg4 Cityscapes, cfg5 dense, the S = 12 paper
+    value): ms/step, library-side per-kernel breakdown and the roofline fraction of the bound that applies."""
+    import ctypes
+    from depthg_b200 import _lib
+    from depthg_b200.modules import ContrastiveCorrelationLoss
+    hbm_peak, tf_burst, tf_sust, _ = peaks_
+    cfg = make_cfg(S)
+    cfg.depth_sampling, cfg.pointwise = sampling, pointwise
+    g = torch.Generator(device=dev).manual_seed(99)
+    H = CFG2["H"]
+
+    def feat(ch):
+        return torch.randn((B, H, H, ch), generator=g, device=dev).permute(0, 3, 1, 2)
+
+    nsets = 2 if S < 20 else 1          # rotate inputs where one set does not already exceed L2
+    sets = []
+    for _ in range(nsets):
+        sets.append(dict(f=feat(C), fp=feat(C), c=feat(D).requires_grad_(True), cp=feat(D).requires_grad_(True),
+                         d=torch.randint(0, 256, (B, 1, 8 * H, 8 * H), generator=g, device=dev).float(),
+                         dp=torch.randint(0, 256, (B, 1, 8 * H, 8 * H), generator=g, device=dev).float()))
+    fn = ContrastiveCorrelationLoss(cfg)
+
+    def step(i):
+        t = sets[i % nsets]
+        t["c"].grad = None
+        t["cp"].grad = None
+        backprop(fn(t["f"], t["fp"], None, None, t["c"], t["cp"], t["d"], t["dp"]))
+
+    for i in range(3):
+        step(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    lib = _lib.lib()
+    lib.dg_profile_enable(1)
+    reps = min(steps, 5)
+    for i in range(reps):
+        step(i)
+    n = lib.dg_profile_collect(None, 0)
+    buf = ctypes.create_string_buffer(n + 16)
+    lib.dg_profile_collect(buf, n + 16)
+    lib.dg_profile_enable(0)
+    br = {}
+    for ln in buf.value.decode().strip().split("\n"):
+        if ln:
+            nm, _, us = ln.split("\t")
+            br[nm] = round(float(us) / reps, 2)
+    P = S * S
+    nb = algorithmic_bytes(B, C, D)
+    fl = (CFG2["neg_samples"] + 2) * B * P * P * 2 * (C + 3 * D)
+    corr_us = br.get("corr_umma_kernel", 0.0)
+    out = {"config": name, "B": B, "C": C, "dim": D, "S": S, "points": P, "sampling": sampling, "pointwise": pointwise,
+           "ms_per_step": ms, "samples_per_s": B / (ms * 1e-3), "breakdown_us": br,
+           "algorithmic_bytes": nb, "algorithmic_flops": fl,
+           "hbm_frac_step": nb / (ms * 1e-3) / 1e9 / hbm_peak,
+           "mem_GB": round(torch.cuda.max_memory_allocated(dev) / 1e9, 2)}
+    if corr_us:
+        out["corr_kernel"] = {"us": corr_us, "useful_tflops": fl / (corr_us * 1e-6) / 1e12,
+                              "frac_of_bf16_sustained_div3": fl / (corr_us * 1e-6) / 1e12 / (tf_sust / 3.0),
+                              "frac_of_bf16_sustained": fl / (corr_us * 1e-6) / 1e12 / tf_sust,
+                              "hbm_frac": nb / (corr_us * 1e-6) / 1e9 / hbm_peak,
+                              "note": "useful flops (N+2) B P^2 2 (C + 3 D) counted once; every product is issued as a "
+                                      "3-term hi/lo split, so the issued tensor work is 3x this"}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -306,6 +386,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-knn", action="store_true", help="skip the KNN-build side measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the cfg4 / S=12 / dense side configurations")
     ap.add_argument("--nchw", action="store_true", help="NCHW-contiguous inputs instead of channels-last")
     ap.add_argument("--feature-samples", type=int, default=CFG2["S"],
                     help="S of the workload (11 = BASELINE configs[1]; 12 = the ViT-B paper script's value)")
@@ -486,39 +567,39 @@ def main():
             breakdown[name] = float(us) / reps
             calls[name] = int(n) / reps
 
-    # dominant kernel and its roofline.  Algorithmic bytes per kernel = the part of SURVEY 8(d)'s per-step figure
-    # that kernel is responsible for, plus (for the correlation kernel) the panels it must read once
-    # (DESIGN.md "Roofline accounting").
-    HW = CFG2["H"] * CFG2["W"]
-    npairs = 2 + CFG2["neg_samples"]
-    Cc, Dd = CFG2["C"], 96
-    alg = {
-        "fps_kernel": 4 * 2 * B * CFG2["Hd"] * CFG2["Wd"],
-        "gather_feats_kernel": 4 * 2 * B * Cc * HW + 4 * npairs * B * 128 * Cc,          # sources once + bf16 hi/lo panels
-        "gather_code_kernel": 4 * 2 * B * CFG2["D"] * HW + 4 * npairs * B * 128 * 3 * Dd,
-        "gather_norm_kernel": 4 * (2 * B * Cc * HW + 2 * B * CFG2["D"] * HW) + 4 * npairs * B * 128 * (Cc + 3 * Dd),
-        "corr_umma_kernel": 4 * npairs * B * 128 * (2 * Cc + 3 * 2 * Dd) + 4 * 2 * npairs * B * 128 * Dd,
-        "corr_tile_kernel": 4 * npairs * B * 128 * (2 * Cc + 2 * Dd) + 4 * 2 * npairs * B * 128 * Dd,
-        "gather_norm_bwd_kernel": 4 * 2 * B * CFG2["D"] * HW + 4 * 3 * npairs * B * 128 * Dd,
-    }
-    dom = max((k for k in breakdown if k in alg), key=breakdown.get)
+    # Dominant kernel and its roofline.  Numerator = SURVEY.md 8(d)'s ALGORITHMIC bytes of the step (inputs read once,
+    # code gradients written once: 6.35 MB per sample x the B samples one launch processes = 203.1 MB at B = 32) over
+    # the dominant kernel's live CUDA-event time.  `traffic` is what that kernel really moved (ncu dram bytes, committed
+    # capture), and traffic / algorithmic shows the re-read factor.  The whole-step figure is `roofline_step`.
+    step_bytes = algorithmic_bytes(B)
+    ours = [k for k in breakdown if k.endswith("_kernel")]
+    dom = max(ours, key=breakdown.get)
     dom_us = breakdown[dom]
-    achieved = alg[dom] / (dom_us * 1e-6) / 1e9
-    traffic = None
+    achieved = step_bytes / (dom_us * 1e-6) / 1e9
+    traffic = traffic_src = None
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    step_traffic = None
     if os.path.isfile(tpath):   # dram__bytes_read+write per launch from the committed ncu --set full capture
-        traffic = json.load(open(tpath))["dram_bytes"].get(dom)
+        tj = json.load(open(tpath))
+        traffic, traffic_src = tj["dram_bytes"].get(dom), tj.get("source")
+        step_traffic = sum(v for k, v in tj["dram_bytes"].items() if k in breakdown)
     roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
-                "us_per_step": dom_us, "launches_per_step": calls.get(dom), "algorithmic_bytes_per_step": alg[dom]}
+                "algorithmic_bytes": step_bytes, "algorithmic_bytes_per_sample": step_bytes // B,
+                "traffic_over_algorithmic": (traffic / step_bytes) if traffic else None, "traffic_source": traffic_src,
+                "us_per_step": dom_us, "launches_per_step": calls.get(dom),
+                "share_of_gpu_time": dom_us / max(sum(breakdown[k] for k in ours), 1e-9)}
     if dom == "corr_umma_kernel":
         fl = algorithmic_flops(B)
         roofline["tensor"] = {"flops": fl, "achieved_tflops": fl / (dom_us * 1e-6) / 1e12,
                               "frac_of_bf16_sustained_div3": fl / (dom_us * 1e-6) / 1e12 / (tf_sust / 3.0),
                               "note": "fd runs as a 3-product bf16 split, cd as a 3-product tf32 split"}
-    step_bytes = algorithmic_bytes(B)
     roofline_step = {"bound": "hbm", "algorithmic_bytes": step_bytes, "achieved": step_bytes / (ms_per_step * 1e-3) / 1e9,
                      "peak": hbm_peak, "unit": "GB/s", "frac": step_bytes / (ms_per_step * 1e-3) / 1e9 / hbm_peak,
+                     "traffic": step_traffic,
+                     "traffic_over_algorithmic": (step_traffic / step_bytes) if step_traffic else None,
+                     "gpu_time_us": sum(breakdown[k] for k in ours),
+                     "frac_of_gpu_time": step_bytes / (sum(breakdown[k] for k in ours) * 1e-6) / 1e9 / hbm_peak,
                      "tensor_flops": algorithmic_flops(B),
                      "tensor_frac_bf16_sustained": algorithmic_flops(B) / (ms_per_step * 1e-3) / 1e12 / tf_sust}
 
@@ -648,18 +729,17 @@ def main():
         allf = torch.nn.functional.normalize(torch.randn((N, F), generator=g2, device=dev), dim=1)
         lo, hi = shard_bounds(N, world, rank)
         local = allf[lo:hi].contiguous()
-        del allf
 
         def knn_step():
             db = allgather_rows(local, N) if world > 1 else local
-            return knn_topk(local, db, k)
+            return knn_topk(local, db, k, return_stats=True)
 
         knn_step()
         barrier()
         ev0.record()
         reps_k = 2
         for _ in range(reps_k):
-            knn_step()
+            kidx, kstats = knn_step()
         ev1.record()
         barrier()
         kms = ev0.elapsed_time(ev1) / reps_k
@@ -667,13 +747,52 @@ def main():
             t = torch.tensor([kms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             kms = float(t.item())
+        # Parity of the TIMED result, outside the timed region: sampled rows of this rank's block against the oracle
+        # (fp32 einsum + topk on the host, src/precompute_knns.py:99-113) under the 1e-6 tie rule; at N > 1 rank 0 also
+        # compares the concatenated sharded result with a one-GPU build of the whole index.
+        from oracle import depthg_oracle as O
+        rs_k = np.random.RandomState(11 + rank)
+        rows = np.unique(np.concatenate([rs_k.randint(0, hi - lo, 192), np.arange(hi - lo - 32, hi - lo)]))
+        allc = allf.cpu()
+        _, want = O.knn_rows(allc[lo:hi][rows], allc, k)
+        got = kidx[torch.from_numpy(rows).to(dev)].cpu()
+        sims_s = allc[lo:hi][rows] @ allc.T
+        mism = got != want
+        gap = (torch.gather(sims_s, 1, got) - torch.gather(sims_s, 1, want)).abs()
+        worst = float(gap[mism].max()) if bool(mism.any()) else 0.0
+        parity = {"rows_checked": int(len(rows)), "slots_differing": int(mism.sum()), "worst_fp32_gap": worst,
+                  "ok": bool(worst < 1e-6), "fallback_rows": kstats["fallback_rows"],
+                  "pipeline_error": kstats["pipeline_error"],
+                  "against": "oracle (fp32 einsum + topk on the host) on sampled query rows of the timed result"}
+        if world > 1:
+            full_sharded = allgather_rows(kidx, N)
+            flag = torch.tensor([1.0 if parity["ok"] else 0.0], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            parity["ok_all_ranks"] = bool(flag.item() == 1.0)
+            if rank == 0:
+                one = knn_topk(allf, allf, k)
+                diff = one != full_sharded
+                nd = int(diff.sum())
+                worst1 = 0.0
+                if nd:
+                    r_bad = torch.nonzero(diff.any(1)).flatten()[:4096]
+                    sb = allf[r_bad] @ allf.T
+                    g1 = (torch.gather(sb, 1, one[r_bad]) - torch.gather(sb, 1, full_sharded[r_bad])).abs()
+                    worst1 = float(g1[diff[r_bad]].max())
+                parity["sharded_vs_one_gpu"] = {"slots_differing": nd, "worst_fp32_gap": worst1, "ok": worst1 < 1e-6}
+                del one
+            del full_sharded
+        del allf, allc, sims_s
         flops = 2.0 * N * N * F
+        per_gpu_tflops = flops / (kms / 1e3) / 1e12 / world
         knn = {"metric": "knn_build_img_per_s", "value": N / (kms / 1e3), "unit": "img/s", "ms": kms, "N": N, "F": F,
                "k": k, "scaling": "strong", "sharding": "query rows; all-gather of the feature database",
-               "roofline": {"bound": "tensor", "achieved": flops / (kms / 1e3) / 1e12, "peak": tf_burst,
-                            "unit": "TFLOP/s", "frac": flops / (kms / 1e3) / 1e12 / tf_burst,
-                            "note": "tcgen05 bf16 3-product split (3 MMAs per useful product) + exact fp32 re-rank; "
-                                    "flops counted once (2 N^2 F), peak is the bf16 tensor burst figure"}}
+               "parity_checked": parity,
+               "roofline": {"bound": "tensor", "achieved": per_gpu_tflops, "peak": tf_burst,
+                            "unit": "TFLOP/s per GPU", "frac": per_gpu_tflops / tf_burst, "n_gpus": world,
+                            "note": "useful flops 2 N^2 F counted once, divided by N_gpus x the measured bf16 burst "
+                                    "peak of ONE GPU; the tensor pass issues 3 MMAs per useful product (bf16 hi/lo "
+                                    "split) and is followed by an exact fp32 re-rank"}}
 
     if knn is not None and rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
@@ -735,6 +854,21 @@ def main():
         except Exception as e:  # noqa: BLE001  (auxiliary: must never cost the bench line)
             probes = {"error": f"{type(e).__name__}: {e}"[:200]}
 
+    # ---- the other BASELINE configs as side keys (rank 0 at N = 1): configs[3] Cityscapes B = 64 / dim 100 / random
+    #      coordinates / pointwise off; the paper script's S = 12; configs[4] dense 784 x 784 at B = 64
+    extra = None
+    if rank == 0 and world == 1 and not args.no_extra:
+        extra = {}
+        for nm, kw in (("cfg4_cityscapes", dict(B=64, C=768, D=100, S=11, sampling="none", pointwise=False, steps=20)),
+                       ("cfg2_s12", dict(B=32, C=768, D=90, S=12, sampling="fps", pointwise=True, steps=20)),
+                       ("cfg5_dense", dict(B=64, C=768, D=90, S=28, sampling="fps", pointwise=True, steps=5))):
+            try:
+                torch.cuda.empty_cache()
+                extra[nm] = side_config(dev, nm, peaks_=(hbm_peak, tf_burst, tf_sust, peak_src), **kw)
+            except Exception as e:  # noqa: BLE001  (auxiliary: must never cost the bench line)
+                extra[nm] = {"error": f"{type(e).__name__}: {e}"[:200]}
+        torch.cuda.empty_cache()
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -752,7 +886,7 @@ def main():
                                            "ms_per_step": ms_fused / args.steps,
                                            "note": "negative_sampler='fused': one dg_super_perms launch instead of "
                                                    "neg_samples x torch.randperm (same distribution, different stream)"},
-                "knn": knn, "probes": probes}
+                "knn": knn, "probes": probes, "extra_configs": extra}
         print(json.dumps(line), flush=True)
     if world > 1:
         # a captured NCCL graph can deadlock communicator teardown; everything is measured and printed, so leave

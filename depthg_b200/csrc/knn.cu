@@ -346,5 +346,6 @@ extern "C" int dg_knn_topk(const float* q, const float* db, int Nq, int N, int F
     DG_REQUIRE(ws && ws_bytes >= knn_umma_workspace_bytes(Nq, N, F), DG_ERR_WORKSPACE, "dg_knn_topk: workspace too small");
     return knn_topk_umma(q, db, Nq, N, F, k, idx, sims, ws, st);
   }
+  if (ws && ws_bytes >= 256) DG_CUDA_OK(cudaMemsetAsync(ws, 0, 256, st));   // diagnostics header: nothing to report
   return launch_knn_exact(q, db, Nq, N, F, k, idx, sims, nullptr, nullptr, st);
 }

@@ -42,9 +42,16 @@ template <int BN> struct KuCfg {
 };
 constexpr int KU_CAND = 32;
 constexpr int KU_LSTR = KU_CAND + 1;
-// bound on |approx - exact| of the 3-product bf16 split for unit-norm rows: dropped lo.lo term <= 2^-18, rounding of the
-// two lo panels <= 2 * 2^-18, fp32 accumulation ~1e-6  (measured max 5e-6, SURVEY 7.1 iii)
-constexpr float KU_EPS = 1.5e-5f;
+// Bound on |approx - exact| of the 3-product bf16 split, as a multiple of |q| * max|d| (the row norms are measured by
+// split_rows_kernel, so un-normalised inputs get a proportionally wider bound instead of a silently wrong one):
+//   x = hi + lo + r with |lo| <= 2^-8 |x| and |r| <= 2^-8 |lo| <= 2^-16 |x| (bf16 keeps 8 significand bits), so
+//   q.d - (qh.dh + qh.dl + ql.dh) = ql.dl + rq.d + q.rd  is at most 3 * 2^-16 |q||d| by Cauchy-Schwarz;
+//   the tensor core adds 3 F / 16 instruction results of 16 products each into one fp32 accumulator: every add loses
+//   at most 2^-23 of a partial sum that never exceeds |q||d|  ->  (3 F / 16 + 16) * 2^-23 |q||d|.
+// F = 768: 4.6e-5 + 1.9e-5 = 6.5e-5 (measured maximum on unit-norm rows: 5e-6, SURVEY 7.1 iii).
+__host__ __device__ inline float ku_eps_unit(int F) {
+  return 3.f * 1.52587890625e-5f + (3.f * (float)F / 16.f + 16.f) * 1.1920929e-7f;
+}
 
 struct KnnUmmaParams {
   CUtensorMap tm_qh, tm_ql, tm_dh, tm_dl;  // bf16 [rows, Fp], box 64 x 128, SWIZZLE_128B
@@ -54,17 +61,44 @@ struct KnnUmmaParams {
   int* err;
 };
 
+// A warp per row: bf16 hi/lo panels (K padded with zeros to Fp), the row's squared norm (rownorm2, nullable) and the
+// maximum squared norm over all rows (maxnorm2_bits: the float's bit pattern, which orders like an int for x >= 0).
 __global__ void __launch_bounds__(256) split_rows_kernel(const float* __restrict__ x, int n, int F, int Fp,
-                                                         __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
-  const size_t total = (size_t)n * Fp;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const size_t r = i / Fp;
-    const int c = (int)(i - r * Fp);
-    const float v = c < F ? __ldg(x + r * F + c) : 0.f;
-    const __nv_bfloat16 h = __float2bfloat16_rn(v);
-    hi[i] = h;
-    lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+                                                         __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                                         float* __restrict__ rownorm2, int* __restrict__ maxnorm2_bits) {
+  const int lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const bool vec = (F & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+  float wmax = 0.f;
+  for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n; r += nwarps) {
+    const float* xr = x + (size_t)r * F;
+    __nv_bfloat16* hr = hi + (size_t)r * Fp;
+    __nv_bfloat16* lr = lo + (size_t)r * Fp;
+    float ss = 0.f;
+    for (int c = lane * 4; c < Fp; c += 128) {
+      float v[4];
+      if (vec && c + 3 < F) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(xr + c));
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[e] = c + e < F ? __ldg(xr + c + e) : 0.f;
+      }
+      __nv_bfloat16 h[4], l[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        ss = fmaf(v[e], v[e], ss);
+        h[e] = __float2bfloat16_rn(v[e]);
+        l[e] = __float2bfloat16_rn(v[e] - __bfloat162float(h[e]));
+      }
+      *reinterpret_cast<uint2*>(hr + c) = *reinterpret_cast<uint2*>(h);
+      *reinterpret_cast<uint2*>(lr + c) = *reinterpret_cast<uint2*>(l);
+    }
+    ss = warp_sum(ss);
+    if (rownorm2 && lane == 0) rownorm2[r] = ss;
+    wmax = fmaxf(wmax, ss);
   }
+  if (maxnorm2_bits && lane == 0 && wmax > 0.f) atomicMax(maxnorm2_bits, __float_as_int(wmax));
 }
 
 template <int BN>
@@ -258,9 +292,13 @@ __global__ void __launch_bounds__(256) knn_rerank_kernel(const float* __restrict
                                                          const int* __restrict__ cand_idx,
                                                          const float* __restrict__ cand_val, int64_t* __restrict__ idx,
                                                          float* __restrict__ sims, int* __restrict__ fail_rows,
-                                                         int* __restrict__ fail_count, const int* __restrict__ err) {
+                                                         int* __restrict__ fail_count, const int* __restrict__ err,
+                                                         const float* __restrict__ qnorm2,
+                                                         const int* __restrict__ dbmax2_bits, float eps_unit) {
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (row >= Nq) return;
+  // error bound of the approximate similarities of this row: eps_unit * |q| * max |d|
+  const float eps = eps_unit * sqrtf(__ldg(qnorm2 + row)) * sqrtf(__int_as_float(__ldg(dbmax2_bits)));
   const float* qr = q + (size_t)row * F;
   int my_idx[KU_MAXSEG];
   float my_a[KU_MAXSEG], my_e[KU_MAXSEG];
@@ -302,7 +340,7 @@ __global__ void __launch_bounds__(256) knn_rerank_kernel(const float* __restrict
       if (best == -INFINITY) break;
     }
   }
-  const float keep = a_k - 2.f * KU_EPS;
+  const float keep = a_k - 2.f * eps;
 #pragma unroll
   for (int sg = 0; sg < KU_MAXSEG; ++sg) {
     if (sg < nseg) {
@@ -357,7 +395,7 @@ __global__ void __launch_bounds__(256) knn_rerank_kernel(const float* __restrict
     if (out == k - 1) ek = (wi != 0x7fffffff) ? wv : -INFINITY;
   }
   // certificate: the exact k-th best candidate must beat anything the approximate pass could have dropped
-  const bool bad = !(ek > tau + KU_EPS) || (err && *err != 0);
+  const bool bad = !(ek > tau + eps) || (err && *err != 0);
   if (lane == 0 && bad) fail_rows[atomicAdd(fail_count, 1)] = row;  // recomputed by the exact kernel
 }
 
@@ -415,7 +453,7 @@ static int knn_nseg(int Nq, int N, int k) {
 size_t knn_umma_workspace_bytes(int Nq, int N, int F) {
   const size_t Fp = (size_t)round_up(F, 64);
   return 256 + 2 * al256((size_t)N * Fp * 2) + 2 * al256((size_t)Nq * Fp * 2) +
-         al256((size_t)Nq * KU_MAXSEG * KU_CAND * 4) * 2 + al256((size_t)Nq * 4);
+         al256((size_t)Nq * KU_MAXSEG * KU_CAND * 4) * 2 + 2 * al256((size_t)Nq * 4);
 }
 
 // declared in knn.cu: exact fp32 kernel restricted to the query rows listed in row_list[0 .. *row_count)
@@ -439,15 +477,19 @@ int knn_topk_umma(const float* q, const float* db, int Nq, int N, int F, int k, 
   int* cand_idx = reinterpret_cast<int*>(take((size_t)Nq * KU_MAXSEG * KU_CAND * 4));
   float* cand_val = reinterpret_cast<float*>(take((size_t)Nq * KU_MAXSEG * KU_CAND * 4));
   int* fail_rows = reinterpret_cast<int*>(take((size_t)Nq * 4));
-  int* fail_count = err + 1;  // second int of the zeroed header
+  float* qnorm2 = reinterpret_cast<float*>(take((size_t)Nq * 4));
+  // zeroed header: [0] error flag, [1] number of uncertified rows (dg_knn_topk's caller may read it back after the
+  // stream has drained), [2] bits of the largest squared database row norm
+  int* fail_count = err + 1;
+  int* dbmax2 = err + 2;
   DG_CUDA_OK(cudaMemsetAsync(err, 0, 256, st));
 
   DG_PRE(st);
-  split_rows_kernel<<<148 * 8, 256, 0, st>>>(db, N, F, Fp, dh, dl);
+  split_rows_kernel<<<148 * 8, 256, 0, st>>>(db, N, F, Fp, dh, dl, same ? qnorm2 : nullptr, dbmax2);
   DG_LAUNCH_OK("split_rows_kernel");
   if (!same) {
     DG_PRE(st);
-    split_rows_kernel<<<148 * 8, 256, 0, st>>>(q, Nq, F, Fp, qh, ql);
+    split_rows_kernel<<<148 * 8, 256, 0, st>>>(q, Nq, F, Fp, qh, ql, qnorm2, nullptr);
     DG_LAUNCH_OK("split_rows_kernel");
   }
   KnnUmmaParams prm;
@@ -480,7 +522,7 @@ int knn_topk_umma(const float* q, const float* db, int Nq, int N, int F, int k, 
   DG_LAUNCH_OK("knn_umma_kernel");
   DG_PRE(st);
   knn_rerank_kernel<<<ceil_div(Nq * 32, 256), 256, 0, st>>>(q, db, Nq, N, F, k, nseg * KU_SUB, cand_idx, cand_val, idx, sims, fail_rows,
-                                                             fail_count, err);
+                                                             fail_count, err, qnorm2, dbmax2, ku_eps_unit(F));
   DG_LAUNCH_OK("knn_rerank_kernel");
   return launch_knn_exact(q, db, Nq, N, F, k, idx, sims, fail_rows, fail_count, st);
 }

@@ -18,11 +18,14 @@ TOPK = 30          # src/precompute_knns.py:108
 N_BATCHES = 64     # src/precompute_knns.py:51 (chunking of the reference loop; the kernel streams instead)
 
 
-def knn_topk(queries: torch.Tensor, db: torch.Tensor, k: int = TOPK, return_sims: bool = False):
+def knn_topk(queries: torch.Tensor, db: torch.Tensor, k: int = TOPK, return_sims: bool = False,
+             return_stats: bool = False):
     """Top-k database rows by fp32 dot product for every query row.
 
     queries [Nq,F], db [N,F] CUDA fp32 (unit-norm rows for cosine similarity).
-    Returns int64 [Nq,k] sorted by descending similarity (and the similarities)."""
+    Returns int64 [Nq,k] sorted by descending similarity (and the similarities).  ``return_stats`` appends a dict
+    with the tensor-core path's diagnostics (synchronises): ``fallback_rows`` = query rows whose candidate list
+    failed the certificate and were recomputed by the exact fp32 kernel, ``pipeline_error`` (0 = ok)."""
     require_cuda_f32(queries, "queries")
     require_cuda_f32(db, "db")
     if queries.dim() != 2 or db.dim() != 2 or queries.shape[1] != db.shape[1]:
@@ -43,7 +46,11 @@ def knn_topk(queries: torch.Tensor, db: torch.Tensor, k: int = TOPK, return_sims
     ws = torch.empty(ws_bytes, device=db.device, dtype=torch.uint8)
     check(lib.dg_knn_topk(ptr(queries), ptr(db), Nq, N, F, k, ptr(idx), ptr(sims), ptr(ws), ws_bytes, stream_ptr()),
           "dg_knn_topk")
-    return (idx, sims) if return_sims else idx
+    out = (idx, sims) if return_sims else (idx,)
+    if return_stats:
+        head = ws[:12].view(torch.int32).cpu()
+        out = out + ({"pipeline_error": int(head[0]), "fallback_rows": int(head[1])},)
+    return out if len(out) > 1 else out[0]
 
 
 def build_knn_index(normed_feats: torch.Tensor, k: int = TOPK, n_batches: int = N_BATCHES) -> torch.Tensor:

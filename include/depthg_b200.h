@@ -264,9 +264,13 @@ DG_API int dg_loss_backward(const dg_loss_desc_t* desc, const dg_loss_io_t* io, 
  * Cosine-similarity k-nearest-neighbour build.  Replaces the einsum + topk
  * loop of src/precompute_knns.py:99-113 for a block of query rows.
  *
- *   q  : [Nq,F] query rows, db : [N,F] database rows (both unit-norm fp32, row pitch F).
+ *   q  : [Nq,F] query rows, db : [N,F] database rows (fp32, row pitch F; unit-norm for cosine similarity — the
+ *        tensor-core pass measures the row norms and scales its error bound by |q| * max|d|, so other norms stay exact).
  *   idx : out [Nq,k] int64, sorted by descending fp32 similarity (k <= 32).
- *   sims: optional out [Nq,k] fp32 similarities. */
+ *   sims: optional out [Nq,k] fp32 similarities.
+ *   ws  : dg_knn_workspace_bytes() bytes.  Once the stream has drained, its first three int32 hold diagnostics of the
+ *        tensor-core path: [0] pipeline error flag (0 = ok), [1] number of query rows whose candidate list could not be
+ *        certified and were recomputed by the exact fp32 kernel, [2] bit pattern of the largest squared database row norm. */
 DG_API size_t dg_knn_workspace_bytes(int Nq, int N, int F, int k);
 DG_API int dg_knn_topk(const float* q, const float* db, int Nq, int N, int F, int k, int64_t* idx, float* sims, void* ws,
                 size_t ws_bytes, dg_stream_t stream);

@@ -74,11 +74,39 @@ def pool_normalize(feat_maps: torch.Tensor, eps: float = 1e-12) -> torch.Tensor:
     return out
 
 
+PRECOMPUTE_RES = 392   # the script hard-codes res = 392 (src/precompute_knns.py:50); the dataset looks up cfg.res
+
+
 def nns_filename(model_type, dataset_name, image_set, crop_type, res) -> str:
-    """File name contract of src/precompute_knns.py:71-72 / src/data.py:1056-1057."""
+    """File name contract of src/precompute_knns.py:71-72 (producer) / src/data.py:1056-1057 (consumer).  Note the
+    producer formats its hard-coded ``res`` (392) while the consumer formats ``cfg.res``: the two meet only when the
+    training config says res = 392, exactly as in the reference."""
     return "nns_{}_{}_{}_{}_{}.npz".format(model_type, dataset_name, image_set, crop_type, res)
 
 
 def save_nns(path: str, nearest_neighbors: torch.Tensor) -> None:
-    """np.savez_compressed(file, nns=int64[N,k]) (src/precompute_knns.py:115)."""
-    np.savez_compressed(path, nns=nearest_neighbors.to("cpu", torch.int64).numpy())
+    """np.savez_compressed(file, nns=int64[N,k]) (src/precompute_knns.py:115): the one array ``ContrastiveSegDataset``
+    reads back (``np.load(file)["nns"]``, src/data.py:1062-1063; row ``ind``, columns 1..num_neighbors, :1079)."""
+    nn = nearest_neighbors.to("cpu", torch.int64)
+    if nn.dim() != 2:
+        raise ValueError(f"nearest_neighbors must be [N,k], got {tuple(nn.shape)}")
+    np.savez_compressed(path, nns=nn.numpy())
+
+
+def load_nns(path: str) -> np.ndarray:
+    """The consumer side (src/data.py:1062-1064): ``np.load(feature_cache_file)["nns"]``."""
+    return np.load(path)["nns"]
+
+
+def precompute_and_save(feat_maps_or_feats: torch.Tensor, data_dir: str, model_type, dataset_name, image_set,
+                        crop_type, res=PRECOMPUTE_RES, k: int = TOPK) -> str:
+    """One (crop_type, image_set, dataset) iteration of the script's loop (src/precompute_knns.py:66-116) with the
+    feature matrix already extracted: pool + normalise if given [N,C,H,W] maps (``get_feats``, :15-21), build the
+    index on the GPU, write ``<data_dir>/nns/nns_<model>_<dataset>_<set>_<crop>_<res>.npz``.  Returns the path."""
+    import os
+    feats = pool_normalize(feat_maps_or_feats) if feat_maps_or_feats.dim() == 4 else feat_maps_or_feats
+    nn = build_knn_index(feats, k)
+    os.makedirs(os.path.join(data_dir, "nns"), exist_ok=True)
+    path = os.path.join(data_dir, "nns", nns_filename(model_type, dataset_name, image_set, crop_type, res))
+    save_nns(path, nn)
+    return path

@@ -173,3 +173,38 @@ def test_distributed_sharding_world2_gloo(tmp_path):
     for p in procs:
         out, _ = p.communicate(timeout=180)
         assert p.returncode == 0, out
+
+
+def test_nns_file_contract_round_trips_to_the_dataset_loader(tmp_path):
+    """what save_nns writes is what ContrastiveSegDataset reads
+    (/root/reference/src/precompute_knns.py:71-72,115 -> /root/reference/src/data.py:1056-1064,1079)."""
+    from depthg_b200.precompute_knns import PRECOMPUTE_RES, load_nns, nns_filename, save_nns
+    from oracle import depthg_oracle as O
+    from tests.golden import cases
+    feats, k, nb = cases.make_knn_feats("ragged_1001")
+    nn = O.knn_topk_chunked(feats, 30, nb)                      # [1001, 30] int64, as the script builds it
+    # producer file name: the script's format string with its hard-coded res
+    name = nns_filename("vit_base", "cocostuff27", "train", "five", PRECOMPUTE_RES)
+    assert name == "nns_{}_{}_{}_{}_{}.npz".format("vit_base", "cocostuff27", "train", "five", 392)
+    assert name == "nns_vit_base_cocostuff27_train_five_392.npz"
+    # crop_type None formats as the string "None" on both sides (the script's `crop_types = [None]` variant)
+    assert nns_filename("vit_small", "directory_name", "val", None, 224) == "nns_vit_small_directory_name_val_None_224.npz"
+    path = str(tmp_path / name)
+    save_nns(path, nn)
+    # consumer (src/data.py:1062-1064): np.load(file)["nns"], one row per dataset item
+    loaded = np.load(path)
+    assert loaded.files == ["nns"]
+    nns = loaded["nns"]
+    assert nns.dtype == np.int64 and nns.shape == (1001, 30)
+    assert np.array_equal(nns, nn.numpy()) and np.array_equal(load_nns(path), nns)
+    # src/data.py:1079: ind_pos = nns[ind][randint(1, num_neighbors + 1)] - columns 1..7 at cfg.num_neighbors = 7 are
+    # valid dataset indices, and column 0 is the image itself
+    num_neighbors = 7
+    assert (nns[:, 0] == np.arange(1001)).all()
+    picks = nns[:, 1:num_neighbors + 1]
+    assert picks.min() >= 0 and picks.max() < 1001 and (picks != np.arange(1001)[:, None]).all()
+    with pytest.raises(ValueError):
+        save_nns(path, nn[0])
+    # int32 / CUDA-produced tensors are widened to the int64 the reference stores
+    save_nns(path, nn.to(torch.int32))
+    assert np.load(path)["nns"].dtype == np.int64

@@ -343,6 +343,20 @@ def test_pool_normalize_matches_get_feats():
         assert rel_err(pool_normalize(x).cpu().numpy(), want) < 1e-6
 
 
+def test_precompute_and_save_writes_the_file_the_dataset_loads(tmp_path):
+    """get_feats pooling -> KNN build -> nns_*.npz, read back the way src/data.py:1056-1064 does."""
+    from depthg_b200.precompute_knns import load_nns, precompute_and_save
+    rs = np.random.RandomState(12)
+    fm = torch.from_numpy(rs.standard_normal((700, 64, 5, 5)).astype(np.float32))
+    path = precompute_and_save(fm.to(dev()), str(tmp_path), "vit_base", "cocostuff27", "val", "five")
+    assert path.endswith("nns/nns_vit_base_cocostuff27_val_five_392.npz")
+    nns = load_nns(path)
+    assert nns.dtype == np.int64 and nns.shape == (700, 30)
+    feats = O.pooled_normed_feats(fm)
+    want = O.knn_topk_chunked(feats, 30, 64).numpy()
+    _check_knn(nns, feats, want, 30)
+
+
 # ------------------------------------------------------------------ tcgen05 kernel vs the generic CUDA-core kernel
 def _run_both_kernels(name, monkeypatch):
     """Same inputs through the tcgen05 kernel and (DEPTHG_B200_CORR=simt) the generic kernel."""

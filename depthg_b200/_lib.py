@@ -40,6 +40,8 @@ SIGNATURES = {
     "dg_depth_sign": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, _vp, _vp]),
     "dg_gather_norm": (C.c_int, [_vp, _c_i64p, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_int, C.c_int, _c_i32p,
                                  _c_i32p, _vp, C.c_float, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "dg_norm_dim1": (C.c_int, [_vp, C.c_int, C.c_int, C.c_longlong, C.c_longlong, C.c_longlong, C.c_longlong,
+                               C.c_float, _vp, _vp]),
     "dg_gather_norm_bwd": (C.c_int, [_vp, _c_i64p, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_int, C.c_int, _c_i32p,
                                      _c_i32p, _vp, C.c_float, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, C.c_int,
                                      _c_i32p, _c_f32p, C.c_int, _vp, _vp]),

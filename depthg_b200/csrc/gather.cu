@@ -563,6 +563,45 @@ __global__ void __launch_bounds__(256) pool_normalize_kernel(const float* __rest
   for (int c = threadIdx.x; c < C; c += blockDim.x) out[(size_t)blockIdx.x * C + c] = psm[c] * r;
 }
 
+// norm() of the reference (src/modules.py:789-790): x / max(||x||_2 over dim 1, eps) on a tensor viewed as
+// [N, C, inner] with element strides (sN, sC, sP), same strides for the output.
+//   sC == 1 (channels-last): a warp per position, lanes over channels;  otherwise: a thread per position (coalesced
+//   along the position axis), two passes over the channels.
+__global__ void __launch_bounds__(256) norm_dim1_kernel(const float* __restrict__ t, int N, int C, long long inner,
+                                                        long long sN, long long sC, long long sP, float eps,
+                                                        float* __restrict__ out) {
+  const long long total = (long long)N * inner;
+  if (sC == 1) {
+    const int lane = threadIdx.x & 31;
+    const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= total) return;
+    const long long n = w / inner, p = w - n * inner;
+    const float* x = t + n * sN + p * sP;
+    float* y = out + n * sN + p * sP;
+    float ss = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      const float v = __ldg(x + c);
+      ss = fmaf(v, v, ss);
+    }
+    ss = warp_sum(ss);
+    const float d = fmaxf(sqrtf(ss), eps);
+    for (int c = lane; c < C; c += 32) y[c] = __ldg(x + c) / d;
+  } else {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const long long n = i / inner, p = i - n * inner;
+    const float* x = t + n * sN + p * sP;
+    float* y = out + n * sN + p * sP;
+    float ss = 0.f;
+    for (int c = 0; c < C; ++c) {
+      const float v = __ldg(x + (long long)c * sC);
+      ss = fmaf(v, v, ss);
+    }
+    const float d = fmaxf(sqrtf(ss), eps);
+    for (int c = 0; c < C; ++c) y[(long long)c * sC] = __ldg(x + (long long)c * sC) / d;
+  }
+}
+
 static int fill_sets(const char* fn, const float* src, const int64_t* strides, int nsets, const int32_t* set_coord,
                      const int32_t* set_slot, bool has_perm, SetTable* tab) {
   DG_REQUIRE(nsets > 0 && nsets <= DG_MAX_SETS, DG_ERR_INVALID, "%s: nsets=%d out of range", fn, nsets);
@@ -787,5 +826,20 @@ extern "C" int dg_pool_normalize(const float* t, const int64_t* strides, int N, 
   pool_normalize_kernel<<<N, 256, (size_t)C * sizeof(float), reinterpret_cast<cudaStream_t>(stream)>>>(
       t, strides[0], strides[1], strides[2], strides[3], C, H, W, eps, out);
   DG_LAUNCH_OK("pool_normalize_kernel");
+  return DG_OK;
+}
+
+extern "C" int dg_norm_dim1(const float* t, int N, int C, long long inner, long long sN, long long sC, long long sP,
+                            float eps, float* out, dg_stream_t stream) {
+  using namespace dg;
+  DG_REQUIRE(t && out, DG_ERR_INVALID, "dg_norm_dim1: null pointer");
+  DG_REQUIRE(N > 0 && C > 0 && inner > 0, DG_ERR_INVALID, "dg_norm_dim1: bad sizes");
+  const long long total = (long long)N * inner;
+  const long long threads = sC == 1 ? total * 32 : total;
+  DG_REQUIRE((threads + 255) / 256 < (1LL << 31), DG_ERR_UNSUPPORTED, "dg_norm_dim1: tensor too large for one launch");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  DG_PRE(st);
+  norm_dim1_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(t, N, C, inner, sN, sC, sP, eps, out);
+  DG_LAUNCH_OK("norm_dim1_kernel");
   return DG_OK;
 }

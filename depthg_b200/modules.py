@@ -44,8 +44,10 @@ def _fps(depth: torch.Tensor, depth_b, H: int, W: int, S: int, affine: bool, wan
         nimg = 2 * B
     coords = torch.empty((nimg, S, S, 2), device=depth.device, dtype=torch.float32)
     idx = torch.empty((nimg, S * S), device=depth.device, dtype=torch.int32) if want_idx else None
-    check(_lib.lib().dg_fps_coords(ptr(depth), ptr(depth_b), B, Hd, Wd, H, W, S, FOV_FACTOR, FAR_PLANE,
-                                   1 if affine else 0, ptr(coords), ptr(idx), stream_ptr()), "dg_fps_coords")
+    with torch.cuda.device(depth.device):
+        check(_lib.lib().dg_fps_coords(ptr(depth), ptr(depth_b), B, Hd, Wd, H, W, S, FOV_FACTOR, FAR_PLANE,
+                                       1 if affine else 0, ptr(coords), ptr(idx), stream_ptr(depth.device.index)),
+              "dg_fps_coords")
     return coords, idx
 
 
@@ -130,9 +132,9 @@ class _GraphedSuperPerms:
 
     @staticmethod
     def _capture(n, size, device):
+        gen = torch.cuda.default_generators[device.index]
+        state = gen.get_state()
         try:
-            gen = torch.cuda.default_generators[device.index]
-            state = gen.get_state()
             side = torch.cuda.Stream(device=device)
             side.wait_stream(torch.cuda.current_stream(device))
             with torch.cuda.stream(side):
@@ -140,12 +142,15 @@ class _GraphedSuperPerms:
                     super_perms(n, size, device)
             torch.cuda.current_stream(device).wait_stream(side)
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            # thread_local: CUDA calls of OTHER threads (DataLoader pin_memory thread, NCCL watchdog) neither fail
+            # nor invalidate this capture
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
                 out = super_perms(n, size, device)
-            gen.set_state(state)            # warm-up and capture must not consume the user's RNG stream
             return graph, out
         except Exception:                   # noqa: BLE001 - capture is an optimisation only
             return False
+        finally:
+            gen.set_state(state)            # neither warm-up nor capture (failed or not) may consume the user's RNG stream
 
 
 def fused_super_perms(n: int, size: int, device) -> torch.Tensor:
@@ -161,6 +166,32 @@ def fused_super_perms(n: int, size: int, device) -> torch.Tensor:
     return out
 
 
+def sample_nonzero_locations(t: torch.Tensor, target_size, randint_fn=None) -> torch.Tensor:
+    """Drop-in for src/modules.py:1191-1204 (the ``use_salience`` coordinate sampler): S*S of each image's non-zero
+    salience pixels drawn with replacement — uniform pixels for an all-zero map — as (x, y) coordinates in [-1, 1).
+    Index arithmetic on the device with torch ops (like ``super_perm``, this is RNG plumbing, not a kernel); the
+    random draws are the reference's own ``torch.randint`` calls in the reference's order, so a shared seed gives the
+    same coordinates: per image one CPU-generator draw of n indices (:1199), or one device draw of [n,2] (:1197)."""
+    if t.dim() != 3:
+        raise ValueError(f"salience must be [B,H,W], got {tuple(t.shape)}")
+    if randint_fn is None:
+        randint_fn = lambda high, size, device: (torch.randint(high, size=size) if device is None  # noqa: E731
+                                                 else torch.randint(high, size=size, device=device))
+    B, n = t.shape[0], int(target_size[1]) * int(target_size[2])
+    nz = torch.nonzero(t)                                   # [m,3] rows (image, y, x), sorted by image
+    counts = torch.bincount(nz[:, 0], minlength=B).tolist()  # one sync: the draw sizes depend on the counts
+    rows, off = [], 0
+    for i in range(B):
+        if counts[i] == 0:
+            rows.append(randint_fn(t.shape[1], (n, 2), t.device).to(t.device))
+        else:
+            pick = randint_fn(counts[i], (n,), None).to(t.device)
+            rows.append(nz[off + pick, 1:])
+        off += counts[i]
+    coords = torch.stack(rows).reshape(B, int(target_size[1]), int(target_size[2]), 2).to(torch.float32) / t.shape[1]
+    return torch.flip(coords * 2 - 1, dims=[-1])
+
+
 def _strides(t: torch.Tensor):
     return _lib.i64_array(t.stride())
 
@@ -168,10 +199,11 @@ def _strides(t: torch.Tensor):
 def _gather(t, coords, S, set_coord, set_slot, perm, eps, Prows, ld, out, rnorm, meanvec, fmt=_lib.PANEL_F32,
             out_lo=None, out16_hi=None, out16_lo=None):
     B, Cdim, H, W = t.shape
-    check(_lib.lib().dg_gather_norm(ptr(t), _strides(t), B, Cdim, H, W, ptr(coords), S, len(set_coord),
-                                    _lib.i32_array(set_coord), _lib.i32_array(set_slot), ptr(perm), eps, Prows, ld,
-                                    fmt, ptr(out), ptr(out_lo), ptr(out16_hi), ptr(out16_lo), ptr(rnorm), ptr(meanvec),
-                                    stream_ptr()), "dg_gather_norm")
+    with torch.cuda.device(t.device):
+        check(_lib.lib().dg_gather_norm(ptr(t), _strides(t), B, Cdim, H, W, ptr(coords), S, len(set_coord),
+                                        _lib.i32_array(set_coord), _lib.i32_array(set_slot), ptr(perm), eps, Prows, ld,
+                                        fmt, ptr(out), ptr(out_lo), ptr(out16_hi), ptr(out16_lo), ptr(rnorm),
+                                        ptr(meanvec), stream_ptr(t.device.index)), "dg_gather_norm")
 
 
 def corr_kernel_choice(P: int, D: int) -> str:
@@ -191,6 +223,17 @@ def _check_coords(coords, B):
     return coords.shape[1]
 
 
+def _forward_only(name: str, *tensors):
+    """The free functions below are forward-only launches: they return tensors without a grad_fn.  The reference
+    trainer differentiates through ``norm`` / ``sample`` in its optional rec / aug-alignment / CRF losses
+    (src/train_segmentation.py:396, 407, 416); shadowing those names with these would silently stop training the
+    head, so an input that still requires grad is refused (same convention as depthg_b200.probes)."""
+    if torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors):
+        raise ValueError(f"depthg_b200.modules.{name} is forward-only and its input requires grad: call it under "
+                         f"torch.no_grad() / on detached tensors, or keep the reference's differentiable {name} for "
+                         "that call site (only the loss classes carry a backward, see INTEGRATION.md)")
+
+
 def _sample_panel(t: torch.Tensor, coords: torch.Tensor, eps: float):
     require_cuda_f32(t, "t")
     B, Cdim, H, W = t.shape
@@ -205,6 +248,7 @@ def _sample_panel(t: torch.Tensor, coords: torch.Tensor, eps: float):
 def sample(t: torch.Tensor, coords: torch.Tensor) -> torch.Tensor:
     """Drop-in for src/modules.py:822-825 (forward only): bilinear gather with the
     reference's S-axis swap.  Returns [B,C,S,S]."""
+    _forward_only("sample", t, coords)
     panel, rn, S = _sample_panel(t, coords, NORM_EPS)
     B, _, Cdim = panel.shape
     # the kernel normalises; undo it with the stored 1/max(||x||,eps) to return raw samples
@@ -214,33 +258,41 @@ def sample(t: torch.Tensor, coords: torch.Tensor) -> torch.Tensor:
 
 def sample_norm(t: torch.Tensor, coords: torch.Tensor) -> torch.Tensor:
     """norm(sample(t, coords)) in one kernel — the form the loss consumes."""
+    _forward_only("sample_norm", t, coords)
     panel, _, S = _sample_panel(t, coords, NORM_EPS)
     B, _, Cdim = panel.shape
     return panel.permute(0, 2, 1).reshape(B, Cdim, S, S)
 
 
 def norm(t: torch.Tensor) -> torch.Tensor:
-    """Drop-in for src/modules.py:789-790: L2-normalise over dim 1, eps 1e-10
-    (forward only; the trainer imports the name but the hot path never calls it
-    outside the loss).  Runs the gather kernel at the exact grid points."""
+    """Drop-in for src/modules.py:789-790 (``F.normalize(t, dim=1, eps=1e-10)``, forward only): any tensor with at
+    least two dimensions, any strides.  One launch of the strided normalise kernel (dg_norm_dim1)."""
     require_cuda_f32(t, "t")
-    if t.dim() != 4:
-        raise ValueError("norm expects [B,C,H,W]")
-    B, Cdim, H, W = t.shape
-    if H != W:
-        raise ValueError("norm: only square maps are supported by the panel kernel")
-    ys = torch.arange(H, device=t.device, dtype=torch.float32)
-    g = (ys / (H - 1) * 2 - 1) if H > 1 else torch.zeros(1, device=t.device)
-    # coords[b,a,c] is read at output (h=c, w=a): x <- coords[...,0], y <- coords[...,1]
-    cx = g.view(H, 1).expand(H, H)   # index a -> x = a
-    cy = g.view(1, H).expand(H, H)   # index c -> y = c
-    coords = torch.stack([cx, cy], -1).unsqueeze(0).expand(B, H, H, 2).contiguous()
-    return sample_norm(t, coords)
+    _forward_only("norm", t)
+    if t.dim() < 2:
+        raise ValueError("norm expects at least [N,C]")
+    if t.numel() == 0:
+        return torch.empty_like(t)
+    N, Cdim = t.shape[0], t.shape[1]
+    inner = t.numel() // (N * Cdim)
+    # view as [N, C, inner] with element strides (sN, sC, sP): NCHW-contiguous or channels-last without a copy
+    sp = 1
+    if t.dim() == 4 and not t.is_contiguous() and t.is_contiguous(memory_format=torch.channels_last):
+        sp = Cdim
+    elif not t.is_contiguous():
+        t = t.contiguous()
+    out = torch.empty_like(t)                    # preserve_format: same strides as the (dense) input
+    st = t.stride()
+    with torch.cuda.device(t.device):
+        check(_lib.lib().dg_norm_dim1(ptr(t), N, Cdim, inner, st[0], st[1], sp, NORM_EPS, ptr(out),
+                                      stream_ptr(t.device.index)), "dg_norm_dim1")
+    return out
 
 
 def tensor_correlation(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     """Drop-in for src/modules.py:797-809 (forward only): einsum('nchw,ncij->nhwij')
     through the correlation kernel (pair loss disabled, dense cd output)."""
+    _forward_only("tensor_correlation", a, b)
     require_cuda_f32(a, "a")
     require_cuda_f32(b, "b")
     n, c, h, w = a.shape
@@ -261,10 +313,11 @@ def tensor_correlation(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     ws_bytes = _lib.lib().dg_corr_loss_workspace_bytes(2, n, P)
     ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
     pan = _lib.make_panels(_lib.PANEL_F32, fn, None, cn, None, None, None)
-    check(_lib.lib().dg_corr_loss(C.byref(pan), None, None, 2, n, P, Prows, 32, 32, c, ld,
-                                  _lib.f32_array([0.0, 0.0]), _lib.i32_array([_lib.GROUP_INTRA, _lib.GROUP_INTER]),
-                                  0.0, 0, ptr(out8), ptr(dC1), ptr(dC2), ptr(cd), None, None, None, ptr(ws), ws_bytes,
-                                  stream_ptr()), "dg_corr_loss")
+    with torch.cuda.device(dev):
+        check(_lib.lib().dg_corr_loss(C.byref(pan), None, None, 2, n, P, Prows, 32, 32, c, ld,
+                                      _lib.f32_array([0.0, 0.0]), _lib.i32_array([_lib.GROUP_INTRA, _lib.GROUP_INTER]),
+                                      0.0, 0, ptr(out8), ptr(dC1), ptr(dC2), ptr(cd), None, None, None, ptr(ws),
+                                      ws_bytes, stream_ptr(dev.index)), "dg_corr_loss")
     return cd[1].reshape(n, h, w, h, w)
 
 
@@ -374,8 +427,9 @@ class _CorrLossFn(torch.autograd.Function):
         io.arena = arena.data_ptr()
         io.coords = coords.data_ptr() if coords is not None else None
         io.perms = perms.data_ptr() if perms is not None else None
-        check(_lib.lib().dg_loss_backward(C.byref(ctx.desc), C.byref(io), C.byref(gr), stream_ptr(arena.device.index)),
-              "dg_loss_backward")
+        with torch.cuda.device(arena.device):   # autograd may run this on a thread whose current device differs
+            check(_lib.lib().dg_loss_backward(C.byref(ctx.desc), C.byref(io), C.byref(gr),
+                                              stream_ptr(arena.device.index)), "dg_loss_backward")
         return (None, None, d_code, d_code_pos) + (None,) * 8
 
 
@@ -407,6 +461,7 @@ class ContrastiveCorrelationLoss(nn.Module):
         # test hooks (CPU and CUDA RNG streams differ): same contract as the oracle's
         self.perm_fn = super_perm
         self.rand_fn = lambda shape, device: torch.rand(shape, device=device)
+        self.randint_fn = None      # use_salience draws; None = the reference's torch.randint calls
         self._last_coords = None
 
     @property
@@ -431,10 +486,16 @@ class ContrastiveCorrelationLoss(nn.Module):
 
     def forward(self, orig_feats, orig_feats_pos, orig_salience, orig_salience_pos, orig_code, orig_code_pos,
                 depth=None, depth_pos=None):
-        return self._run(orig_feats, orig_feats_pos, orig_code, orig_code_pos, depth, depth_pos, None)
+        return self._run(orig_feats, orig_feats_pos, orig_code, orig_code_pos, depth, depth_pos, None,
+                         salience=(orig_salience, orig_salience_pos))
 
-    def _run(self, orig_feats, orig_feats_pos, orig_code, orig_code_pos, depth, depth_pos, aug_feats):
+    def _run(self, orig_feats, orig_feats_pos, orig_code, orig_code_pos, depth, depth_pos, aug_feats,
+             depth_sampling=None, depth_term=None, salience=(None, None)):
+        """``depth_sampling`` / ``depth_term`` override the cfg keys of the same meaning (the depth-only-intra variant
+        fixes them whatever cfg says); cfg itself is only ever read."""
         cfg = self.cfg
+        depth_sampling = cfg.depth_sampling if depth_sampling is None else depth_sampling
+        depth_term = bool(cfg.depth_feat_correlation_loss) if depth_term is None else bool(depth_term)
         self._last_coords = None   # do not keep the previous call's arena alive across this call's allocation
         for name, t in (("orig_feats", orig_feats), ("orig_feats_pos", orig_feats_pos), ("orig_code", orig_code),
                         ("orig_code_pos", orig_code_pos)):
@@ -453,9 +514,6 @@ class ContrastiveCorrelationLoss(nn.Module):
             raise ValueError("neg_samples > 0 needs a batch of at least 2 (super_perm would pair an image with itself)")
         if 2 + nneg > _lib.DG_MAX_PAIRS:
             raise ValueError(f"neg_samples={nneg} exceeds the supported {_lib.DG_MAX_PAIRS - 2}")
-        if cfg.use_salience:
-            raise NotImplementedError("use_salience sampling (sample_nonzero_locations, src/modules.py:1191-1204) "
-                                      "is outside the accelerated path")
         dev = orig_feats.device
         flags = self._flags()
         coords = None
@@ -465,13 +523,28 @@ class ContrastiveCorrelationLoss(nn.Module):
             if aug_feats.shape != orig_feats.shape:
                 raise ValueError("depth_aug_feats must have the shape of orig_feats")
             flags |= _lib.FLAG_AUG_INTRA
-        if cfg.depth_sampling == "fps" and aug_feats is None:
+        if cfg.use_salience:
+            # src/modules.py:1291-1298 (takes precedence over depth_sampling, as in the reference's if/elif chain):
+            # 90 % of the points from the non-zero salience pixels, 10 % uniform
+            sal, sal_pos = salience
+            if sal is None or sal_pos is None:
+                raise ValueError("use_salience=True needs orig_salience and orig_salience_pos")
+            shape = [B, S, S, 2]
+            c1n = sample_nonzero_locations(sal, shape, self.randint_fn)
+            c2n = sample_nonzero_locations(sal_pos, shape, self.randint_fn)
+            c1r = self.rand_fn(shape, dev) * 2 - 1
+            c2r = self.rand_fn(shape, dev) * 2 - 1
+            mask = (self.rand_fn(shape[:-1], dev) > .1).unsqueeze(-1).to(torch.float32)
+            coords = torch.stack([c1n * mask + c1r * (1 - mask), c2n * mask + c2r * (1 - mask)]).float().contiguous()
+        elif depth_sampling in ("fps", "fps_depth_feat") and aug_feats is None:
+            # "fps_depth_feat" = the same call with include_feats=True (:1313-1317), an argument
+            # farthest_point_sampling_depth never reads (:999-1037): identical coordinates
             if depth is None or depth_pos is None:
-                raise ValueError("depth_sampling='fps' needs depth and depth_pos")
+                raise ValueError(f"depth_sampling={depth_sampling!r} needs depth and depth_pos")
             flags |= _lib.FLAG_FPS
-        elif cfg.depth_sampling in ("simple", "fps_depth_feat"):
-            raise NotImplementedError(f"depth_sampling={cfg.depth_sampling!r} (simple_depth_informed_sampling / "
-                                      "include_feats, src/modules.py:828-883, :1313-1317) is outside the accelerated path")
+        elif depth_sampling == "simple" and aug_feats is None:
+            raise NotImplementedError("depth_sampling='simple' (simple_depth_informed_sampling, src/modules.py:828-883: "
+                                      "S instead of S*S points per image) is outside the accelerated path")
         else:
             shape = [B, S, S, 2]
             c1 = self.rand_fn(shape, dev) * 2 - 1
@@ -488,16 +561,22 @@ class ContrastiveCorrelationLoss(nn.Module):
         else:
             perms = super_perms(nneg, B, dev)
 
-        depth_term = bool(cfg.depth_feat_correlation_loss) and aug_feats is None
+        depth_term = depth_term and aug_feats is None
         Hd = Wd = 0
         if depth_term or (flags & _lib.FLAG_FPS):
             if depth is None:
                 raise ValueError("depth_feat_correlation_loss=True needs depth")
+            if depth.dim() == 3:        # [B,Hd,Wd]: the Potsdam dataset yields depth without a channel axis
+                depth = depth.unsqueeze(1)   # (src/data.py:226); adaptive_avg_pool2d treats it the same way
+            if depth_pos is not None and depth_pos.dim() == 3:
+                depth_pos = depth_pos.unsqueeze(1)
             for name, t in (("depth", depth), ("depth_pos", depth_pos)):
                 if t is not None:
                     require_cuda_f32(t, name)
                     if t.dim() != 4 or t.shape[1] != 1 or t.shape[0] != B:
-                        raise ValueError(f"{name} must be [B,1,Hd,Wd], got {tuple(t.shape)}")
+                        raise ValueError(f"{name} must be [B,1,Hd,Wd] (or [B,Hd,Wd]), got {tuple(t.shape)}")
+            if depth_pos is not None and depth_pos.shape != depth.shape:
+                raise ValueError(f"depth_pos {tuple(depth_pos.shape)} must have the shape of depth {tuple(depth.shape)}")
             depth = depth.contiguous()
             depth_pos = depth_pos.contiguous() if depth_pos is not None else None
             Hd, Wd = depth.shape[-2:]
@@ -511,8 +590,13 @@ class ContrastiveCorrelationLoss(nn.Module):
         desc = _lib.LossDesc(B, Cdim, orig_code.shape[1], H, W, Hd, Wd, S, nneg, flags, float(cfg.pos_intra_shift),
                              float(cfg.pos_inter_shift), float(cfg.neg_inter_shift),
                              float(cfg.depth_feat_shift) if depth_term else 0.0)
-        res = _CorrLossFn.apply(orig_feats, orig_feats_pos, orig_code, orig_code_pos, depth, depth_pos, coords, perms,
-                                desc, bool(self.materialize_cd), perms_event, aug_feats)
+        for name, t in (("orig_feats_pos", orig_feats_pos), ("orig_code", orig_code), ("orig_code_pos", orig_code_pos),
+                        ("depth", depth), ("depth_pos", depth_pos), ("depth_aug_feats", aug_feats)):
+            if t is not None and t.device != dev:
+                raise ValueError(f"{name} is on {t.device}, orig_feats on {dev}")
+        with torch.cuda.device(dev):    # kernels, attribute set-up and the stream all belong to the tensors' device
+            res = _CorrLossFn.apply(orig_feats, orig_feats_pos, orig_code, orig_code_pos, depth, depth_pos, coords,
+                                    perms, desc, bool(self.materialize_cd), perms_event, aug_feats)
         intra, inter, neg, dloss, out8, coords_src, cd_out, loss_out, dd_out = res
         # FPS coordinates stay in the arena until someone asks for them (see the last_coords property)
         self._last_coords = (coords_src, _CorrLossFn.last_coords_off, B, S) if (flags & _lib.FLAG_FPS) else coords
@@ -545,10 +629,6 @@ class DepthContrastiveCorrelationLoss(ContrastiveCorrelationLoss):
                 depth_aug_feats, depth_aug_feats_pos=None):
         if depth_aug_feats is None:
             raise ValueError("DepthContrastiveCorrelationLoss needs depth_aug_feats")
-        cfg = self.cfg
-        saved = (cfg.depth_sampling, cfg.depth_feat_correlation_loss)
-        try:   # this variant never uses depth-guided sampling or the depth term, whatever cfg says (:1413-1425)
-            cfg.depth_sampling, cfg.depth_feat_correlation_loss = "none", False
-            return self._run(orig_feats, orig_feats_pos, orig_code, orig_code_pos, None, None, depth_aug_feats)
-        finally:
-            cfg.depth_sampling, cfg.depth_feat_correlation_loss = saved
+        # this variant never uses depth-guided sampling or the depth term, whatever cfg says (:1413-1425)
+        return self._run(orig_feats, orig_feats_pos, orig_code, orig_code_pos, None, None, depth_aug_feats,
+                         depth_sampling="none", depth_term=False, salience=(orig_salience, orig_salience_pos))

@@ -44,8 +44,11 @@ def knn_topk(queries: torch.Tensor, db: torch.Tensor, k: int = TOPK, return_sims
     lib = _lib.lib()
     ws_bytes = lib.dg_knn_workspace_bytes(Nq, N, F, k)
     ws = torch.empty(ws_bytes, device=db.device, dtype=torch.uint8)
-    check(lib.dg_knn_topk(ptr(queries), ptr(db), Nq, N, F, k, ptr(idx), ptr(sims), ptr(ws), ws_bytes, stream_ptr()),
-          "dg_knn_topk")
+    if queries.device != db.device:
+        raise ValueError(f"queries on {queries.device}, db on {db.device}")
+    with torch.cuda.device(db.device):
+        check(lib.dg_knn_topk(ptr(queries), ptr(db), Nq, N, F, k, ptr(idx), ptr(sims), ptr(ws), ws_bytes,
+                              stream_ptr(db.device.index)), "dg_knn_topk")
     out = (idx, sims) if return_sims else (idx,)
     if return_stats:
         head = ws[:12].view(torch.int32).cpu()
@@ -69,8 +72,9 @@ def pool_normalize(feat_maps: torch.Tensor, eps: float = 1e-12) -> torch.Tensor:
         raise ValueError("feat_maps must be [N,C,H,W]")
     N, Cdim, H, W = feat_maps.shape
     out = torch.empty((N, Cdim), device=feat_maps.device, dtype=torch.float32)
-    check(_lib.lib().dg_pool_normalize(ptr(feat_maps), _lib.i64_array(feat_maps.stride()), N, Cdim, H, W, eps,
-                                       ptr(out), stream_ptr()), "dg_pool_normalize")
+    with torch.cuda.device(feat_maps.device):
+        check(_lib.lib().dg_pool_normalize(ptr(feat_maps), _lib.i64_array(feat_maps.stride()), N, Cdim, H, W, eps,
+                                           ptr(out), stream_ptr(feat_maps.device.index)), "dg_pool_normalize")
     return out
 
 

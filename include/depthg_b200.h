@@ -134,6 +134,12 @@ DG_API int dg_gather_norm(const float* t, const int64_t* strides, int B, int C, 
                    int Prows, int ld, int format, void* out, void* out_lo, void* out16_hi, void* out16_lo,
                    float* rnorm, float* meanvec, dg_stream_t stream);
 
+/* norm() of the reference (src/modules.py:789-790, F.normalize(t, dim=1, eps)): the tensor is viewed as
+ * [N, C, inner] with element strides (sN, sC, sP) — NCHW-contiguous (sC = inner, sP = 1) and channels-last
+ * (sC = 1, sP = C) both work without a copy; `out` uses the same strides.  Forward only. */
+DG_API int dg_norm_dim1(const float* t, int N, int C, long long inner, long long sN, long long sC, long long sP,
+                        float eps, float* out, dg_stream_t stream);
+
 /* Backward of dg_gather_norm for the code tensors: combines the unit
  * gradients of dg_corr_loss with the upstream scalars, goes back through the
  * normalisation and scatter-adds through the bilinear weights (atomicAdd; the

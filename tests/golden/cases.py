@@ -62,6 +62,47 @@ def make_aug_inputs(name):
     return cfg, t
 
 
+# use_salience sampling (src/modules.py:1291-1298, :1191-1204): name -> (base loss case, seed).  The salience maps, the
+# uniform numbers behind every torch.randint draw and the 90/10 mask draw are case data, so the real reference (golden),
+# the oracle and the CUDA path all see the same draws.
+SAL_CASES = {
+    "salience_small": ("small_fps", 41),             # depth term on; use_salience overrides depth_sampling='fps'
+    "salience_random_pointwise": ("small_random_pointwise", 42),
+}
+
+
+def make_sal_inputs(name):
+    base, seed = SAL_CASES[name]
+    cfg, t = make_loss_inputs(base)
+    cfg.use_salience = True
+    rs = np.random.RandomState(4000 + seed)
+    B, _, H, W = t["feats"].shape
+    S = cfg.feature_samples
+    sal = (rs.random_sample((B, H, W)) > 0.7).astype(np.float32) * rs.uniform(0.2, 1.0, (B, H, W)).astype(np.float32)
+    sal_pos = (rs.random_sample((B, H, W)) > 0.5).astype(np.float32)
+    sal[B - 1] = 0.0                                  # an all-zero map: the uniform-pixel fallback (:1196-1197)
+    t["salience"], t["salience_pos"] = torch.from_numpy(sal), torch.from_numpy(sal_pos)
+    # one [n,2] block of uniforms per randint call: 2 maps x B images, in the reference's call order
+    t["randint_u"] = torch.from_numpy(rs.random_sample((2 * B, S * S, 2)))
+    t["rand_mask"] = torch.from_numpy(rs.random_sample((B, S, S)).astype(np.float32))
+    return cfg, t
+
+
+def randint_from_uniforms(blocks):
+    """A stand-in for torch.randint(high, size=..., [device=...]) that turns the next block of uniforms into
+    floor(u * high) with the requested shape ((n,) uses the first column, (n,2) both)."""
+    it = iter(blocks)
+
+    def randint(high, size, device=None):
+        u = next(it)
+        r = torch.floor(u * high).to(torch.int64).clamp_(max=high - 1)
+        r = r[:, 0] if len(size) == 1 else r
+        assert tuple(r.shape) == tuple(size)
+        return r if device is None else r.to(device)
+
+    return randint
+
+
 # backprop weights for the scalar L = sum w_i * loss_i  (ViT-B paper run, paper_reproduction.sh:8)
 LOSS_WEIGHTS = dict(pos_inter=1.0501, pos_intra=0.2305, neg_inter=0.2485, depth_feat=0.1603)
 

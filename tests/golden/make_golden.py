@@ -85,6 +85,48 @@ def run_aug_case(M, name):
     print(name, g["scalars"], float(np.linalg.norm(g["d_code"])))
 
 
+def run_sal_case(M, name):
+    """use_salience sampling through the real reference (both loss classes share the code, :1291-1298 / :1413-1420)."""
+    cfg, t = cases.make_sal_inputs(name)
+    code = t["code"].clone().requires_grad_(True)
+    code_pos = t["code_pos"].clone().requires_grad_(True)
+    loss_fn = M.ContrastiveCorrelationLoss(cfg)
+    old_randint = torch.randint
+    ri = cases.randint_from_uniforms(list(t["randint_u"]))
+    torch.randint = lambda high, size, device=None: ri(high, size, device)
+    try:
+        with injected(M, list(t["perms"]), [t["rand1"], t["rand2"], t["rand_mask"]]):
+            out = loss_fn(t["feats"], t["feats_pos"], t["salience"], t["salience_pos"], code, code_pos, t["depth"],
+                          t["depth_pos"])
+    finally:
+        torch.randint = old_randint
+    w = cases.LOSS_WEIGHTS
+    L = w["pos_intra"] * out[0] + w["pos_inter"] * out[2] + w["neg_inter"] * out[4].mean()
+    if cfg.depth_feat_correlation_loss:
+        L = L + w["depth_feat"] * out[6]
+    L.backward()
+    # the coordinates the reference built, recomputed with its own function under the same draws
+    ri = cases.randint_from_uniforms(list(t["randint_u"]))
+    torch.randint = lambda high, size, device=None: ri(high, size, device)
+    try:
+        S = cfg.feature_samples
+        shape = [t["feats"].shape[0], S, S, 2]
+        n1, n2 = M.sample_nonzero_locations(t["salience"], shape), M.sample_nonzero_locations(t["salience_pos"], shape)
+    finally:
+        torch.randint = old_randint
+    mask = (t["rand_mask"] > .1).unsqueeze(-1).to(torch.float32)
+    c1 = n1 * mask + (t["rand1"] * 2 - 1) * (1 - mask)
+    c2 = n2 * mask + (t["rand2"] * 2 - 1) * (1 - mask)
+    g = dict(coords1=c1.numpy(), coords2=c2.numpy(), nonzero1=n1.numpy(), nonzero2=n2.numpy(),
+             scalars=np.array([out[0].item(), out[2].item(), out[4].mean().item(),
+                               out[6].item() if len(out) == 8 else np.nan], np.float64),
+             cd_means=np.array([out[1].mean().item(), out[3].mean().item(), out[5].mean().item(),
+                                out[7].mean().item() if len(out) == 8 else np.nan], np.float64),
+             total=np.float64(L.item()), d_code=code.grad.numpy(), d_code_pos=code_pos.grad.numpy())
+    np.savez_compressed(os.path.join(HERE, f"sal_{name}.npz"), **g)
+    print(name, g["scalars"], float(np.linalg.norm(g["d_code"])), float(np.linalg.norm(g["d_code_pos"])))
+
+
 def run_fps(M):
     out = {}
     for pat in cases.FPS_PATTERNS:
@@ -193,6 +235,9 @@ def main():
     for name in cases.AUG_CASES:
         if only is None or name in only.split(","):
             run_aug_case(M, name)
+    for name in cases.SAL_CASES:
+        if only is None or name in only.split(","):
+            run_sal_case(M, name)
     if only is not None:
         return
     run_fps(M)

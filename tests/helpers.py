@@ -105,3 +105,38 @@ def run_cuda_aug(name, channels_last=False, force_simt=False):
                 os.environ["DEPTHG_B200_CORR"] = old
     assert len(out) == 6
     return _aug_result(out, code, code_pos)
+
+
+def _sal_result(fn, out, code, code_pos, depth_term):
+    L = weighted_total(out, depth_term)
+    L.backward()
+    c1, c2 = fn.last_coords[0], fn.last_coords[1]
+    return dict(coords1=c1.detach().cpu().numpy(), coords2=c2.detach().cpu().numpy(),
+                scalars=np.array([out[0].item(), out[2].item(), out[4].mean().item(),
+                                  out[6].item() if depth_term else np.nan]),
+                cd_means=np.array([out[1].mean().item(), out[3].mean().item(), out[5].mean().item(),
+                                   out[7].mean().item() if depth_term else np.nan]),
+                total=L.item(), d_code=code.grad.detach().cpu().numpy(), d_code_pos=code_pos.grad.detach().cpu().numpy())
+
+
+def run_sal(name, impl, device="cpu", channels_last=False):
+    """use_salience case through `impl` (the oracle's or the product's ContrastiveCorrelationLoss) with the case's
+    draws injected: perms, rand x3 (coords1_reg, coords2_reg, mask) and the uniforms behind every randint."""
+    cfg, t = cases.make_sal_inputs(name)
+    dev = torch.device(device)
+
+    def put(x):
+        x = x.to(dev)
+        return x.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2) if channels_last else x
+
+    code = put(t["code"]).detach().requires_grad_(True)
+    code_pos = put(t["code_pos"]).detach().requires_grad_(True)
+    fn = impl(cfg)
+    perm_it = iter(t["perms"].to(dev))
+    rand_it = iter([t["rand1"].to(dev), t["rand2"].to(dev), t["rand_mask"].to(dev)])
+    fn.perm_fn = lambda B, device: next(perm_it).clone()
+    fn.rand_fn = lambda shape, device: next(rand_it).clone()
+    fn.randint_fn = cases.randint_from_uniforms(list(t["randint_u"]))
+    out = fn(put(t["feats"]), put(t["feats_pos"]), t["salience"].to(dev), t["salience_pos"].to(dev), code, code_pos,
+             t["depth"].to(dev), t["depth_pos"].to(dev))
+    return _sal_result(fn, out, code, code_pos, cfg.depth_feat_correlation_loss)

@@ -83,6 +83,34 @@ def test_sample_and_norm_match_reference_golden(channels_last):
     np.testing.assert_allclose(norm(tc).cpu().numpy(), g["norm_out"], rtol=1e-4, atol=1e-5)
 
 
+def test_norm_accepts_what_the_reference_accepts_and_helpers_are_forward_only():
+    """src/modules.py:789-790 is F.normalize(t, dim=1, eps=1e-10) on ANY tensor: non-square maps, 2-D / 3-D / 5-D inputs,
+    NCHW and channels-last; zero vectors stay zero.  The free functions carry no backward, so they refuse inputs that
+    require grad instead of silently detaching them."""
+    from depthg_b200.modules import norm, sample, sample_norm, tensor_correlation
+    rs = np.random.RandomState(5)
+    for shape in ((3, 17, 9, 14), (4, 90), (2, 33, 50), (2, 6, 3, 4, 5), (1, 768, 28, 28)):
+        t = torch.from_numpy(rs.standard_normal(shape).astype(np.float32))
+        t[0, :, ...] = 0.0 if t.dim() == 2 else t[0, :, ...] * (torch.arange(t.shape[2]) > 0).view(-1, *([1] * (t.dim() - 3)))
+        want = O.norm(t).numpy()
+        np.testing.assert_allclose(norm(t.to(dev())).cpu().numpy(), want, rtol=1e-5, atol=1e-7)
+        if t.dim() == 4:
+            cl = t.to(dev()).contiguous(memory_format=torch.channels_last)
+            got = norm(cl)
+            assert got.stride() == cl.stride()
+            np.testing.assert_allclose(got.cpu().numpy(), want, rtol=1e-5, atol=1e-7)
+    z = torch.zeros(2, 5, 3, 3, device=dev())
+    assert torch.equal(norm(z), z)
+    t = torch.randn(2, 8, 28, 28, device=dev(), requires_grad=True)
+    coords = torch.rand(2, 4, 4, 2, device=dev()) * 2 - 1
+    for fn, args in ((norm, (t,)), (sample, (t, coords)), (sample_norm, (t, coords)),
+                     (tensor_correlation, (t[:, :, :4, :4], t[:, :, :4, :4]))):
+        with pytest.raises(ValueError, match="forward-only"):
+            fn(*args)
+        with torch.no_grad():
+            fn(*args)                      # fine without autograd
+
+
 def test_sample_wide_channels_vector_path():
     """C multiple of 4, channels-last: exercises the 128-bit path; C=90: scalar path."""
     from depthg_b200.modules import sample_norm
@@ -246,6 +274,46 @@ def test_module_has_no_state_and_rereads_cfg():
     cfg.depth_sampling = "none"
     fn(a[0], a[1], None, None, a[2], a[3], depth=a[4], depth_pos=a[5])
     assert fn.last_coords.shape[2] == 6
+
+
+def test_depth_shapes_3d_accepted_and_mismatch_refused():
+    """[B,Hd,Wd] depth (Potsdam, src/data.py:226) is what adaptive_avg_pool2d also accepts; a depth_pos of another
+    size must raise instead of reading out of bounds."""
+    from depthg_b200.modules import ContrastiveCorrelationLoss
+    cfg, t = cases.make_loss_inputs("small_fps")
+    a = {k: t[k].to(dev()) for k in ("feats", "feats_pos", "code", "code_pos", "depth", "depth_pos")}
+    fn = ContrastiveCorrelationLoss(cfg)
+    pit = iter(t["perms"].to(dev()))
+    fn.perm_fn = lambda B, device: next(pit).clone()
+    ref = fn(a["feats"], a["feats_pos"], None, None, a["code"], a["code_pos"], a["depth"], a["depth_pos"])
+    pit = iter(t["perms"].to(dev()))
+    got = fn(a["feats"], a["feats_pos"], None, None, a["code"], a["code_pos"], a["depth"][:, 0], a["depth_pos"][:, 0])
+    for x, y in zip(ref, got):
+        assert torch.equal(x, y)
+    with pytest.raises(ValueError, match="shape of depth"):
+        fn(a["feats"], a["feats_pos"], None, None, a["code"], a["code_pos"], a["depth"], a["depth_pos"][:, :, :100, :100])
+
+
+def test_depth_only_intra_variant_leaves_cfg_untouched():
+    """DepthContrastiveCorrelationLoss must not write to the shared cfg (read-only OmegaConf nodes, other threads)."""
+    from depthg_b200.modules import DepthContrastiveCorrelationLoss
+
+    class Frozen:
+        def __init__(self, ns):
+            object.__setattr__(self, "_ns", ns)
+
+        def __getattr__(self, k):
+            return getattr(object.__getattribute__(self, "_ns"), k)
+
+        def __setattr__(self, k, v):
+            raise AttributeError("cfg is read-only")
+
+    cfg, t = cases.make_aug_inputs("aug_small")
+    cfg.depth_sampling, cfg.depth_feat_correlation_loss = "fps", True      # ignored by this variant (:1413-1425)
+    fn = DepthContrastiveCorrelationLoss(Frozen(cfg))
+    a = {k: v.to(dev()) for k, v in t.items() if k not in ("perms", "rand1", "rand2")}
+    out = fn(a["feats"], a["feats_pos"], None, None, a["code"], a["code_pos"], a["aug"], a["aug_pos"])
+    assert len(out) == 6 and all(torch.isfinite(o).all() for o in out)
 
 
 # ------------------------------------------------------------------ KNN (a12-a14)
@@ -517,6 +585,47 @@ def test_depth_contrastive_variant_matches_reference_golden(name, variant):
     np.testing.assert_allclose(r["scalars"], g["scalars"], rtol=RTOL, atol=ATOL)
     np.testing.assert_allclose(r["cd_means"], g["cd_means"], rtol=RTOL, atol=ATOL)
     assert rel_err(r["d_code"], g["d_code"]) < RTOL and rel_err(r["d_code_pos"], g["d_code_pos"]) < RTOL
+
+
+# ------------------------------------------------------------------ non-default sampling modes
+@pytest.mark.parametrize("name", list(cases.SAL_CASES))
+@pytest.mark.parametrize("channels_last", [False, True])
+def test_salience_sampling_matches_reference_golden(name, channels_last):
+    """cfg.use_salience (src/modules.py:1291-1298 + sample_nonzero_locations :1191-1204): coordinates bit-equal to the
+    real reference's under the same draws, loss and gradients within 1e-4."""
+    from depthg_b200.modules import ContrastiveCorrelationLoss
+    from tests.helpers import run_sal
+    g = golden("sal_" + name)
+    r = run_sal(name, ContrastiveCorrelationLoss, device="cuda:0", channels_last=channels_last)
+    assert np.array_equal(r["coords1"], g["coords1"]) and np.array_equal(r["coords2"], g["coords2"])
+    np.testing.assert_allclose(r["scalars"], g["scalars"], rtol=RTOL, atol=ATOL, equal_nan=True)
+    np.testing.assert_allclose(r["cd_means"], g["cd_means"], rtol=RTOL, atol=ATOL, equal_nan=True)
+    assert rel_err(r["d_code"], g["d_code"]) < RTOL and rel_err(r["d_code_pos"], g["d_code_pos"]) < RTOL
+
+
+def test_salience_default_draws_follow_the_reference_call_order():
+    """Without hooks: randint on the CPU generator per image (device generator for an all-zero map), like :1197-1199."""
+    from depthg_b200.modules import sample_nonzero_locations
+    sal = (torch.rand(3, 28, 28) > 0.5).float()
+    sal[2] = 0
+    torch.manual_seed(5)
+    got = sample_nonzero_locations(sal.to(dev()), [3, 4, 4, 2])
+    torch.manual_seed(5)
+    want = O.sample_nonzero_locations(sal, [3, 4, 4, 2])
+    assert torch.equal(got[:2].cpu(), want[:2])          # CPU-generator draws: same stream on both sides
+    assert got[2].min() >= -1 and got[2].max() < 1       # all-zero map: device draw, only the range is comparable
+
+
+def test_fps_depth_feat_mode_equals_fps_mode():
+    """depth_sampling='fps_depth_feat' passes include_feats=True, which the reference function ignores (:999-1037)."""
+    from tests.gpu_helpers import run_cuda_loss
+    cfg, t = cases.make_loss_inputs("small_fps")
+    _, _, a = run_cuda_loss("small_fps", inputs=(cfg, t))
+    cfg.depth_sampling = "fps_depth_feat"
+    _, _, b = run_cuda_loss("small_fps", inputs=(cfg, t))
+    assert np.array_equal(a["coords1"], b["coords1"]) and np.array_equal(a["scalars"], b["scalars"])
+    assert np.array_equal(a["d_code"], b["d_code"])
+    _check_loss(b, golden("loss_small_fps"), cfg)
 
 
 # ------------------------------------------------------------------ edge shapes against the oracle (computed on the fly)

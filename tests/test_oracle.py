@@ -127,6 +127,48 @@ def test_oracle_depth_contrastive_variant_matches_reference_golden(name):
     np.testing.assert_allclose(r["d_code_pos"], g["d_code_pos"], rtol=1e-5, atol=1e-10)
 
 
+@pytest.mark.parametrize("name", list(cases.SAL_CASES))
+def test_oracle_salience_sampling_matches_reference_golden(name):
+    """use_salience coordinates (src/modules.py:1191-1204, :1291-1298) and the loss on them vs the real reference."""
+    from tests.helpers import run_sal
+    g = golden("sal_" + name)
+    r = run_sal(name, O.ContrastiveCorrelationLoss)
+    assert np.array_equal(r["coords1"], g["coords1"]) and np.array_equal(r["coords2"], g["coords2"])
+    np.testing.assert_allclose(r["scalars"], g["scalars"], rtol=1e-6, atol=1e-9, equal_nan=True)
+    np.testing.assert_allclose(r["d_code"], g["d_code"], rtol=1e-5, atol=1e-10)
+    np.testing.assert_allclose(r["d_code_pos"], g["d_code_pos"], rtol=1e-5, atol=1e-10)
+    # the all-zero salience map took the uniform-pixel fallback: integer pixel coordinates / H * 2 - 1
+    cfg, t = cases.make_sal_inputs(name)
+    n1 = O.sample_nonzero_locations(t["salience"], list(g["nonzero1"].shape), cases.randint_from_uniforms(list(t["randint_u"])))
+    assert np.array_equal(n1.numpy(), g["nonzero1"])
+
+
+@pytest.mark.skipif(not refimport.have_reference(), reason="/root/reference only exists in the build container")
+def test_oracle_salience_and_fps_depth_feat_equal_real_reference_with_shared_rng():
+    """Shared torch seed: the salience path draws randint (CPU generator) per image, then rand x3; the
+    'fps_depth_feat' mode is the 'fps' call with an ignored argument.  Bit-for-bit against the live reference."""
+    M = refimport.load_reference_modules()
+    g = torch.Generator().manual_seed(7)
+    f, fp = torch.randn(3, 24, 28, 28, generator=g), torch.randn(3, 24, 28, 28, generator=g)
+    c, cp = torch.randn(3, 12, 28, 28, generator=g), torch.randn(3, 12, 28, 28, generator=g)
+    d = torch.randint(0, 256, (3, 1, 224, 224), generator=g).float()
+    dp = torch.randint(0, 256, (3, 1, 224, 224), generator=g).float()
+    sal = (torch.rand(3, 28, 28, generator=g) > 0.6).float()
+    sal[1] = 0
+    salp = (torch.rand(3, 28, 28, generator=g) > 0.3).float()
+    for cfg in (cases.loss_cfg(feature_samples=5, use_salience=True),
+                cases.loss_cfg(feature_samples=4, depth_sampling="fps_depth_feat")):
+        outs = []
+        for impl in (M.ContrastiveCorrelationLoss, O.ContrastiveCorrelationLoss):
+            torch.manual_seed(3)
+            ci, cpi = c.clone().requires_grad_(True), cp.clone().requires_grad_(True)
+            out = impl(cfg)(f, fp, sal, salp, ci, cpi, d, dp)
+            (out[0] + out[2] + out[4].mean() + out[6]).backward()
+            outs.append([o.detach() for o in out] + [ci.grad, cpi.grad])
+        for a, b in zip(*outs):
+            assert torch.equal(a, b)
+
+
 # ------------------------------------------------------------------ probe losses (SURVEY 8(f) rank 4)
 def _oracle_probes(name):
     t = cases.make_probe_inputs(name)

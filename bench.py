@@ -362,7 +362,7 @@ def side_config(dev, name, B, C, D, S, sampling, pointwise, steps, peaks_):
     P = S * S
     nb = algorithmic_bytes(B, C, D)
     fl = (CFG2["neg_samples"] + 2) * B * P * P * 2 * (C + 3 * D)
-    corr_us = br.get("corr_umma_kernel", 0.0)
+    corr_us = br.get("corr_pipe_kernel", br.get("corr_umma_kernel", 0.0))
     out = {"config": name, "B": B, "C": C, "dim": D, "S": S, "points": P, "sampling": sampling, "pointwise": pointwise,
            "ms_per_step": ms, "samples_per_s": B / (ms * 1e-3), "breakdown_us": br,
            "algorithmic_bytes": nb, "algorithmic_flops": fl,
@@ -589,7 +589,7 @@ def main():
                 "traffic_over_algorithmic": (traffic / step_bytes) if traffic else None, "traffic_source": traffic_src,
                 "us_per_step": dom_us, "launches_per_step": calls.get(dom),
                 "share_of_gpu_time": dom_us / max(sum(breakdown[k] for k in ours), 1e-9)}
-    if dom == "corr_umma_kernel":
+    if dom in ("corr_umma_kernel", "corr_pipe_kernel"):
         fl = algorithmic_flops(B)
         roofline["tensor"] = {"flops": fl, "achieved_tflops": fl / (dom_us * 1e-6) / 1e12,
                               "frac_of_bf16_sustained_div3": fl / (dom_us * 1e-6) / 1e12 / (tf_sust / 3.0),

@@ -404,6 +404,8 @@ size_t corr_workspace_bytes(int npairs, int B, int P) {
   // the tcgen05 path lays out [header][dots][partials per (pair, image, row tile, column group)][row means (dense)]
   const size_t umma = (size_t)npairs * B * (1 + (size_t)ceil_div(P, 128) * ceil_div(P, 256) * 4 + round_up(P, 256));
   if (umma > floats) floats = umma;
+  const size_t pipe = corr_pipe_workspace_floats(npairs, B, P);
+  if (pipe > floats) floats = pipe;
   size_t bytes = floats * sizeof(float) + 2048;  // + header and 256-byte alignment slack of each region
   return (bytes + 255) / 256 * 256;
 }
@@ -483,12 +485,11 @@ extern "C" int dg_corr_loss(const dg_panels_t* pan, const float* fmean, const fl
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 
   if (pan->format == DG_PANEL_FEATS_SPLIT || pan->format == DG_PANEL_CODE_SPLIT) {
-    DG_REQUIRE(P <= 1024 && Prows == (P <= 256 ? round_up(P, 128) : round_up(P, 256)), DG_ERR_UNSUPPORTED,
-               "dg_corr_loss: the tcgen05 path needs S*S <= 1024 and panels of round_up(S*S,128) rows (round_up(S*S,256) "
-               "above 256) (got P=%d, Prows=%d)", P, Prows);
-    DG_REQUIRE(pan->f_lo && pan->c_lo && pan->cb_hi && pan->cb_lo, DG_ERR_INVALID,
-               "dg_corr_loss: split panel format needs f_lo, c_lo, cb_hi, cb_lo");
-    return corr_loss_umma(pan, fmean, 1, dsign, npairs, B, P, Prows, ldf, ldc, pair_shift, pair_group, depth_shift, flags, out8,
+    DG_REQUIRE(P <= 1024 && Prows == round_up(P, 128), DG_ERR_UNSUPPORTED,
+               "dg_corr_loss: the tcgen05 path needs S*S <= 1024 and panels of round_up(S*S,128) rows (got P=%d, Prows=%d)",
+               P, Prows);
+    DG_REQUIRE(pan->cb_hi, DG_ERR_INVALID, "dg_corr_loss: split panel format needs the interleaved 16-bit code panel cb_hi");
+    return corr_loss_pipe(pan, fmean, 1, dsign, npairs, B, P, Prows, ldf, ldc, pair_shift, pair_group, depth_shift, flags, out8,
                           dC1, dC2, cd_out, loss_out, dd_out, fd_dbg, ws, st, nullptr, nullptr, 0);
   }
   DG_REQUIRE(pan->format == DG_PANEL_F32, DG_ERR_INVALID, "dg_corr_loss: unknown panel format %d", pan->format);

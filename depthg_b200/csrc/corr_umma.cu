@@ -22,6 +22,7 @@
 //
 // Every mbarrier wait is bounded; on a timeout the CTA raises an error flag (the losses
 // come back NaN) instead of hanging the GPU.
+#include <math.h>
 #include <stdlib.h>
 
 #include "kernels.cuh"
@@ -39,9 +40,9 @@ constexpr int UM_SMEM = UM_NSTAGE * UM_STAGE + 1024 /*align slack*/ + 256 /*barr
 constexpr uint32_t TM_FD = 0, TM_CD = 128, TM_D1 = 256, TM_D2 = 384;
 
 struct UmmaParams {
-  CUtensorMap tm_fhi, tm_flo;  // bf16 [npairs*B*128, ldf]   box 64 x 128, SWIZZLE_128B
+  CUtensorMap tm_fhi, tm_flo;  // fp16 [npairs*B*128, ldf]   box 64 x 128, SWIZZLE_128B
   CUtensorMap tm_chi, tm_clo;  // f32  [npairs*B*128, ldc]   box 32 x 128, SWIZZLE_128B
-  CUtensorMap tm_bhi, tm_blo;  // bf16 [npairs*B*128, ldc]   box 32 x 128, SWIZZLE_64B (gradient GEMM operands)
+  CUtensorMap tm_bhi, tm_blo;  // fp16 [npairs*B*128, ldc]   box 32 x 128, SWIZZLE_64B (gradient GEMM operands)
   const float* dsign;          // [B,128*ntile] or null
   const float* dots;           // [npairs,B] <mean row of F1[b], mean row of F2[k,b]> (pointwise) or null
   int npairs, B, P, ldf, ldc, flags, has_depth;
@@ -56,6 +57,7 @@ struct UmmaParams {
   int cg_base, ncg_total;
   const float* rowmean;        // [npairs,B,prows] mean_q fd[p,q] (dense + pointwise) or null
   float depth_shift, inv_cnt;
+  float uscale;                // power of two the unit-gradient factor is multiplied with before its fp16 hi/lo split
   float shift[DG_MAX_PAIRS];
   int32_t group[DG_MAX_PAIRS];
   int32_t fs1[DG_MAX_PAIRS], fs2[DG_MAX_PAIRS];  // FEATURE panel slots of pair k's operands (default 0 and k)
@@ -89,7 +91,7 @@ __device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) 
   return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
 }
 
-// Write 32 consecutive q-values of row p (as bf16 hi and lo) into the swizzled U tiles.
+// Write 32 consecutive q-values of row p (as fp16 hi and lo) into the swizzled U tiles.
 __device__ __forceinline__ void store_u_chunk(uint8_t* u_hi, uint8_t* u_lo, int p, int cc, const float* u) {
   const uint32_t atom = cc >> 1;
   uint8_t* row_hi = u_hi + atom * 16384 + p * 128;
@@ -100,11 +102,10 @@ __device__ __forceinline__ void store_u_chunk(uint8_t* u_hi, uint8_t* u_lo, int 
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const float a = u[8 * i + 2 * e], b = u[8 * i + 2 * e + 1];
-      const __nv_bfloat162 hh = __floats2bfloat162_rn(a, b);  // .x = a (low half), .y = b
-      const uint32_t hb = *reinterpret_cast<const uint32_t*>(&hh);
-      const float ra = a - __uint_as_float(hb << 16), rb = b - __uint_as_float(hb & 0xffff0000u);
-      const __nv_bfloat162 ll = __floats2bfloat162_rn(ra, rb);
-      h[e] = hb;
+      const __half2 hh = __floats2half2_rn(a, b);  // .x = a (low half), .y = b
+      const float2 hf = __half22float2(hh);
+      const __half2 ll = __floats2half2_rn(a - hf.x, b - hf.y);
+      h[e] = *reinterpret_cast<const uint32_t*>(&hh);
       l[e] = *reinterpret_cast<const uint32_t*>(&ll);
     }
     const uint32_t chunk = ((cc & 1) * 4 + i) ^ (p & 7);  // Swizzle<3,4,3>: 16-byte chunk ^= row % 8
@@ -116,11 +117,11 @@ __device__ __forceinline__ void store_u_chunk(uint8_t* u_hi, uint8_t* u_lo, int 
 // Drain one 32-row x 32-column accumulator block (this warp's TMEM lanes) to row-major global memory through a
 // per-warp smem scratch so that every store instruction writes one full 128-byte line.
 __device__ __forceinline__ void drain_block(uint32_t taddr, float* scratch /*[32][33]*/, float* dst_rows /*row 0 of the block*/,
-                                            int ldc, int col0, int lane, float* v) {
+                                            int ldc, int col0, int lane, float* v, float gscale) {
   tmem_ld_32x32(taddr, v);
   tmem_ld_wait();
 #pragma unroll
-  for (int i = 0; i < 32; ++i) scratch[lane * 33 + i] = v[i];
+  for (int i = 0; i < 32; ++i) scratch[lane * 33 + i] = v[i] * gscale;
   __syncwarp();
 #pragma unroll 8
   for (int r = 0; r < 32; ++r) dst_rows[(size_t)r * ldc + col0 + lane] = scratch[r * 33 + lane];
@@ -300,10 +301,10 @@ __global__ void __launch_bounds__(UM_THREADS, 1) corr_umma_kernel(const __grid_c
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
     if (lane == 0) {
-      const uint32_t id_f = instr_desc(FMT_BF16, 128, 128, 0, 0);
+      const uint32_t id_f = instr_desc(FMT_F16, 128, 128, 0, 0);
       const uint32_t id_c = instr_desc(FMT_TF32, 128, 128, 0, 0);
-      const uint32_t id_g1 = instr_desc(FMT_BF16, 128, (uint32_t)prm.ldc, 0, 1);  // A = U K-major,   B = code rows MN-major
-      const uint32_t id_g2 = instr_desc(FMT_BF16, 128, (uint32_t)prm.ldc, 1, 1);  // A = U^T MN-major, B = code rows MN-major
+      const uint32_t id_g1 = instr_desc(FMT_F16, 128, (uint32_t)prm.ldc, 0, 1);  // A = U K-major,   B = code rows MN-major
+      const uint32_t id_g2 = instr_desc(FMT_F16, 128, (uint32_t)prm.ldc, 1, 1);  // A = U^T MN-major, B = code rows MN-major
       // descriptor templates; the start-address field (bits 0..13, address >> 4) is added per tile / K-step
       const uint64_t dk128 = smem_desc(0, 16, 1024, SW_128B);       // K-major, 128-byte rows
       const uint64_t dmn128 = smem_desc(0, 16384, 1024, SW_128B);   // MN-major, 64-element atoms 16 KB apart
@@ -447,7 +448,11 @@ __global__ void __launch_bounds__(UM_THREADS, 1) corr_umma_kernel(const __grid_c
       old_mean = warp_sum(part) / (float)prm.B;
     }
     const float sp = s_sign[p];
-    const float inv = (p < P) ? prm.inv_cnt : 0.f;
+    // the fp16 panels carry F16_FEAT_SCALE / F16_CODE_SCALE: fd accumulators are FS times too large, the gradient
+    // accumulators uscale * F16_CODE_SCALE times; U itself is kept O(1) (no 1/(B P^2) factor) so its fp16 split is normal
+    constexpr float FS = 1.f / (F16_FEAT_SCALE * F16_FEAT_SCALE);
+    const float inv = (p < P) ? prm.uscale : 0.f;
+    const float gscale = prm.inv_cnt / (prm.uscale * F16_CODE_SCALE);
     const float dsh = prm.depth_shift;
     float sum_loss = 0.f, sum_cd = 0.f, sum_dloss = 0.f, sum_dd = 0.f;
     float v[32], c[32];
@@ -471,7 +476,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) corr_umma_kernel(const __grid_c
           for (int i = 0; i < 32; ++i) s += v[i];
         }
       }
-      s_rowsum[half][row] = s;
+      s_rowsum[half][row] = s * FS;
       asm volatile("bar.sync 1, 256;" ::: "memory");
       c0 += (s_rowsum[0][row] + s_rowsum[1][row]) / (float)P;
     }
@@ -494,6 +499,8 @@ __global__ void __launch_bounds__(UM_THREADS, 1) corr_umma_kernel(const __grid_c
               tmem_ld_32x32(tlane + col_fd(tj) + 32 * cc, v);
               tmem_ld_32x32(tlane + col_cd(tj) + 32 * cc, c);
               tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] *= FS;
               if (prm.cd_out || prm.loss_out || prm.dd_out || prm.fd_dbg) {   // optional dense outputs (materialize_cd / tests)
                 const size_t obase = (((size_t)k * prm.B + b) * P + p) * P;
                 if (prm.fd_dbg) {
@@ -564,11 +571,11 @@ __global__ void __launch_bounds__(UM_THREADS, 1) corr_umma_kernel(const __grid_c
           const size_t which = (rd == 0) ? (size_t)k : (size_t)prm.npairs;
           {  // dC2 rows of column tile tj, partial buffer of row tile ti
             float* dbase = prm.dC2 + (which * prm.nti_stride + ti) * slab + ((size_t)b * Prows + 128 * (gj0 + tj) + 32 * lg) * prm.ldc;
-            for (int cc = half; cc < ncd; cc += 2) drain_block(tlane + col_cd(tj) + 32 * cc, scratch, dbase, prm.ldc, 32 * cc, lane, v);
+            for (int cc = half; cc < ncd; cc += 2) drain_block(tlane + col_cd(tj) + 32 * cc, scratch, dbase, prm.ldc, 32 * cc, lane, v, gscale);
           }
           if (tj == NT - 1) {  // dC1 rows of row tile ti (complete after the last column tile)
             float* dbase = prm.dC1 + (which * prm.ncg_stride + cg) * slab + ((size_t)b * Prows + 128 * ti + 32 * lg) * prm.ldc;
-            for (int cc = 1 - half; cc < ncd; cc += 2) drain_block(tlane + col_fd(0) + 32 * cc, scratch, dbase, prm.ldc, 32 * cc, lane, v);
+            for (int cc = 1 - half; cc < ncd; cc += 2) drain_block(tlane + col_fd(0) + 32 * cc, scratch, dbase, prm.ldc, 32 * cc, lane, v, gscale);
           }
           if (threadIdx.x == 64 && step == 0) stamp(prm, 6);
           ++step;
@@ -662,11 +669,11 @@ void umma_ws_layout(void* ws, int** err, float** dots) {
 // Dense shapes (S*S > 256): rowmean[k,b,p] = mean_q fd[p,q] = < F1n[p,:], mean row of F2n >, the same identity
 // pair_dots_kernel uses for the pair mean.  One block per (pair, image); the F1 rows are read back from the bf16
 // hi/lo panels (x = hi + lo is what the tensor cores see).
-__global__ void __launch_bounds__(256) row_means_kernel(const __nv_bfloat16* __restrict__ fhi,
-                                                        const __nv_bfloat16* __restrict__ flo,
+__global__ void __launch_bounds__(256) row_means_kernel(const __half* __restrict__ fhi,
+                                                        const __half* __restrict__ flo,
                                                         const float* __restrict__ fmean, int nsplit, int B, int P,
                                                         int prows, int ldf, float* __restrict__ rowmean,
-                                                        const __grid_constant__ SlotMap sm) {
+                                                        const __grid_constant__ SlotMap sm, int interleave) {
   extern __shared__ float m2[];  // [ldf] mean row of the second operand
   const int kb = blockIdx.x, k = kb / B, b = kb - k * B;
   const float* mp = fmean + ((size_t)sm.fs2[k] * B + b) * nsplit * ldf;
@@ -683,21 +690,45 @@ __global__ void __launch_bounds__(256) row_means_kernel(const __nv_bfloat16* __r
       if (lane == 0) rowmean[(size_t)kb * prows + p] = 0.f;
       continue;
     }
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(fhi + (base + p) * ldf);
-    const __nv_bfloat162* l = reinterpret_cast<const __nv_bfloat162*>(flo + (base + p) * ldf);
+    // split panels: hi / lo rows of pitch ldf; interleaved: one row of pitch 2 ldf, 32-channel chunks [32 hi | 32 lo]
+    const __half* hrow = interleave ? fhi + (base + p) * 2 * ldf : fhi + (base + p) * ldf;
+    const __half* lrow = interleave ? hrow + 32 : flo + (base + p) * ldf;
     float s = 0.f;
     for (int c2 = lane; c2 < ldf / 2; c2 += 32) {
-      const float2 a = __bfloat1622float2(h[c2]), d = __bfloat1622float2(l[c2]);
+      const size_t off = interleave ? il_col(2 * c2) : (size_t)(2 * c2);
+      const float2 a = __half22float2(*reinterpret_cast<const __half2*>(hrow + off));
+      const float2 d = __half22float2(*reinterpret_cast<const __half2*>(lrow + off));
       s = fmaf(a.x + d.x, m2[2 * c2], s);
       s = fmaf(a.y + d.y, m2[2 * c2 + 1], s);
     }
-    s = warp_sum(s);
+    s = warp_sum(s) * (1.f / F16_FEAT_SCALE);
     if (lane == 0) rowmean[(size_t)kb * prows + p] = s;
   }
 }
 
 static long long* g_clk = nullptr;  // debug: device buffer for per-CTA phase timestamps
 void set_clock_buffer(long long* p) { g_clk = p; }
+long long* get_clock_buffer() { return g_clk; }
+
+// dots[k,b] (+ reset of the error flag / completion counter) as its own launch: the per-stage dg_corr_loss entry point
+int launch_pair_dots(const DotsJob& job, cudaStream_t st) {
+  DG_PRE(st);
+  pair_dots_kernel<<<job.npairs * job.B, 256, 0, st>>>(job);
+  DG_LAUNCH_OK("pair_dots_kernel");
+  return DG_OK;
+}
+
+int launch_row_means(const void* f_hi, const void* f_lo, const float* fmean, int nsplit, int npairs, int B, int P, int Prows,
+                     int ldf, float* rowmean, const int32_t* fs1, const int32_t* fs2, cudaStream_t st, int interleave) {
+  SlotMap sm;
+  for (int k = 0; k < npairs; ++k) { sm.fs1[k] = fs1[k]; sm.fs2[k] = fs2[k]; }
+  DG_PRE(st);
+  row_means_kernel<<<npairs * B, 256, (size_t)ldf * sizeof(float), st>>>(
+      static_cast<const __half*>(f_hi), static_cast<const __half*>(f_lo), fmean, nsplit, B, P, Prows, ldf, rowmean, sm,
+      interleave);
+  DG_LAUNCH_OK("row_means_kernel");
+  return DG_OK;
+}
 
 // ------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -716,7 +747,7 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-static int make_map_2d(CUtensorMap* m, CUtensorMapDataType dt, int elt_bytes, const void* base, uint64_t cols,
+int make_map_2d(CUtensorMap* m, CUtensorMapDataType dt, int elt_bytes, const void* base, uint64_t cols,
                        uint64_t rows, uint32_t box_cols, uint32_t box_rows, CUtensorMapSwizzle sw) {
   EncodeTiledFn fn = get_encode_fn();
   DG_REQUIRE(fn, DG_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
@@ -741,12 +772,12 @@ int corr_loss_umma(const dg_panels_t* pan, const float* fmean, int nsplit, const
   const uint64_t rows = (uint64_t)npairs * B * Prows;
   const uint64_t frows = (uint64_t)(nfslots > 0 ? nfslots : npairs) * B * Prows;
   int rc;
-  if ((rc = make_map_2d(&prm.tm_fhi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, pan->f_hi, ldf, frows, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
-  if ((rc = make_map_2d(&prm.tm_flo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, pan->f_lo, ldf, frows, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if ((rc = make_map_2d(&prm.tm_fhi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, pan->f_hi, ldf, frows, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if ((rc = make_map_2d(&prm.tm_flo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, pan->f_lo, ldf, frows, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   if ((rc = make_map_2d(&prm.tm_chi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, pan->c_hi, ldc, rows, 32, 128, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   if ((rc = make_map_2d(&prm.tm_clo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, pan->c_lo, ldc, rows, 32, 128, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
-  if ((rc = make_map_2d(&prm.tm_bhi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, pan->cb_hi, ldc, rows, 32, 128, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
-  if ((rc = make_map_2d(&prm.tm_blo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, pan->cb_lo, ldc, rows, 32, 128, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+  if ((rc = make_map_2d(&prm.tm_bhi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, pan->cb_hi, ldc, rows, 32, 128, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+  if ((rc = make_map_2d(&prm.tm_blo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, pan->cb_lo, ldc, rows, 32, 128, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
   // workspace: [err int (256 B)][dots npairs*B floats, padded to 256 B][partials npairs*B*4 floats]
   int* err;
   float* dots;
@@ -768,6 +799,14 @@ int corr_loss_umma(const dg_panels_t* pan, const float* fmean, int nsplit, const
   prm.has_depth = dsign != nullptr;
   prm.depth_shift = depth_shift;
   prm.inv_cnt = 1.0f / ((float)B * (float)P * (float)P);
+  {  // |fd' - shift| <= 3 + |shift| must stay inside fp16 after scaling: 2^4 for every sane shift, smaller for huge ones
+    float big = fabsf(depth_shift);
+    for (int k = 0; k < npairs; ++k) big = fmaxf(big, fabsf(pair_shift[k]));
+    int e = 4;
+    while (e > -12 && ldexpf(1.f, e) * (big + 4.f) > 16384.f) --e;
+    DG_REQUIRE(ldexpf(1.f, e) * (big + 4.f) <= 16384.f, DG_ERR_UNSUPPORTED, "corr_loss: shift %g too large", (double)big);
+    prm.uscale = ldexpf(1.f, e);
+  }
   for (int k = 0; k < npairs; ++k) {
     prm.shift[k] = pair_shift[k];
     prm.group[k] = pair_group[k];
@@ -797,8 +836,8 @@ int corr_loss_umma(const dg_panels_t* pan, const float* fmean, int nsplit, const
     for (int k = 0; k < npairs; ++k) { sm.fs1[k] = prm.fs1[k]; sm.fs2[k] = prm.fs2[k]; }
     DG_PRE(st);
     row_means_kernel<<<npairs * B, 256, (size_t)ldf * sizeof(float), st>>>(
-        static_cast<const __nv_bfloat16*>(pan->f_hi), static_cast<const __nv_bfloat16*>(pan->f_lo), fmean, nsplit, B, P,
-        Prows, ldf, rowmean, sm);
+        static_cast<const __half*>(pan->f_hi), static_cast<const __half*>(pan->f_lo), fmean, nsplit, B, P,
+        Prows, ldf, rowmean, sm, 0);
     DG_LAUNCH_OK("row_means_kernel");
   }
   static PerDevice attr_pd = {};

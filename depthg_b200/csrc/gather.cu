@@ -27,9 +27,9 @@ __device__ __forceinline__ float umma_tf32(float x) {  // round-to-nearest tf32 
 constexpr int GATHER_THREADS = 512;
 constexpr int GATHER_WARPS = GATHER_THREADS / 32;
 
-__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& h, __nv_bfloat16& l) {
-  h = __float2bfloat16_rn(v);
-  l = __float2bfloat16_rn(v - __bfloat162float(h));
+__device__ __forceinline__ void split_f16(float v, __half& h, __half& l) {  // v already carries the panel scale
+  h = __float2half_rn(v);
+  l = __float2half_rn(v - __half2float(h));
 }
 
 // dynamic smem: row staging [GATHER_WARPS][ld] + mean accumulators [GATHER_WARPS][ld]
@@ -114,20 +114,26 @@ __global__ void __launch_bounds__(GATHER_THREADS)
         if (FMT == FMT_F32) {
           *reinterpret_cast<float4*>(o.out + ro + c) = v;
         } else if (FMT == FMT_FEATS_SPLIT) {
-          __nv_bfloat16 h[4], l[4];
-          split_bf16(v.x, h[0], l[0]); split_bf16(v.y, h[1], l[1]);
-          split_bf16(v.z, h[2], l[2]); split_bf16(v.w, h[3], l[3]);
-          *reinterpret_cast<uint2*>(o.hi16 + ro + c) = *reinterpret_cast<uint2*>(h);
-          *reinterpret_cast<uint2*>(o.lo16 + ro + c) = *reinterpret_cast<uint2*>(l);
+          __half h[4], l[4];
+          constexpr float sc = F16_FEAT_SCALE;
+          split_f16(v.x * sc, h[0], l[0]); split_f16(v.y * sc, h[1], l[1]);
+          split_f16(v.z * sc, h[2], l[2]); split_f16(v.w * sc, h[3], l[3]);
+          __half* ph = o.interleave ? o.hi16 + 2 * ro + il_col(c) : o.hi16 + ro + c;
+          __half* pl = o.interleave ? ph + 32 : o.lo16 + ro + c;
+          *reinterpret_cast<uint2*>(ph) = *reinterpret_cast<uint2*>(h);
+          *reinterpret_cast<uint2*>(pl) = *reinterpret_cast<uint2*>(l);
         } else {
           float4 hi = make_float4(umma_tf32(v.x), umma_tf32(v.y), umma_tf32(v.z), umma_tf32(v.w));
           *reinterpret_cast<float4*>(o.out + ro + c) = hi;
           *reinterpret_cast<float4*>(o.out_lo + ro + c) = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
-          __nv_bfloat16 h[4], l[4];
-          split_bf16(v.x, h[0], l[0]); split_bf16(v.y, h[1], l[1]);
-          split_bf16(v.z, h[2], l[2]); split_bf16(v.w, h[3], l[3]);
-          *reinterpret_cast<uint2*>(o.hi16 + ro + c) = *reinterpret_cast<uint2*>(h);
-          *reinterpret_cast<uint2*>(o.lo16 + ro + c) = *reinterpret_cast<uint2*>(l);
+          __half h[4], l[4];
+          constexpr float sc = F16_CODE_SCALE;
+          split_f16(v.x * sc, h[0], l[0]); split_f16(v.y * sc, h[1], l[1]);
+          split_f16(v.z * sc, h[2], l[2]); split_f16(v.w * sc, h[3], l[3]);
+          __half* ph = o.interleave ? o.hi16 + 2 * ro + il_col(c) : o.hi16 + ro + c;
+          __half* pl = o.interleave ? ph + 32 : o.lo16 + ro + c;
+          *reinterpret_cast<uint2*>(ph) = *reinterpret_cast<uint2*>(h);
+          *reinterpret_cast<uint2*>(pl) = *reinterpret_cast<uint2*>(l);
         }
       }
     } else {
@@ -140,18 +146,28 @@ __global__ void __launch_bounds__(GATHER_THREADS)
         if (FMT == FMT_F32) {
           o.out[ro + c] = v;
         } else if (FMT == FMT_FEATS_SPLIT) {
-          __nv_bfloat16 h, l;
-          split_bf16(v, h, l);
-          o.hi16[ro + c] = h;
-          o.lo16[ro + c] = l;
+          __half h, l;
+          split_f16(v * F16_FEAT_SCALE, h, l);
+          if (o.interleave) {
+            o.hi16[2 * ro + il_col(c)] = h;
+            o.hi16[2 * ro + il_col(c) + 32] = l;
+          } else {
+            o.hi16[ro + c] = h;
+            o.lo16[ro + c] = l;
+          }
         } else {
           const float hi = umma_tf32(v);
           o.out[ro + c] = hi;
           o.out_lo[ro + c] = v - hi;
-          __nv_bfloat16 h, l;
-          split_bf16(v, h, l);
-          o.hi16[ro + c] = h;
-          o.lo16[ro + c] = l;
+          __half h, l;
+          split_f16(v * F16_CODE_SCALE, h, l);
+          if (o.interleave) {
+            o.hi16[2 * ro + il_col(c)] = h;
+            o.hi16[2 * ro + il_col(c) + 32] = l;
+          } else {
+            o.hi16[ro + c] = h;
+            o.lo16[ro + c] = l;
+          }
         }
       }
     }
@@ -247,11 +263,26 @@ __device__ __forceinline__ void gather_feats_body(const SetTable& sets, int B, i
       if (FMT == FMT_F32) {
         *reinterpret_cast<float4*>(o.out + ro + c) = x;
       } else {
-        __nv_bfloat16 hh[4], ll[4];
-        split_bf16(x.x, hh[0], ll[0]); split_bf16(x.y, hh[1], ll[1]);
-        split_bf16(x.z, hh[2], ll[2]); split_bf16(x.w, hh[3], ll[3]);
-        *reinterpret_cast<uint2*>(o.hi16 + ro + c) = *reinterpret_cast<uint2*>(hh);
-        *reinterpret_cast<uint2*>(o.lo16 + ro + c) = *reinterpret_cast<uint2*>(ll);
+        __half hh[4], ll[4];
+        constexpr float sc = F16_FEAT_SCALE;
+        split_f16(x.x * sc, hh[0], ll[0]); split_f16(x.y * sc, hh[1], ll[1]);
+        split_f16(x.z * sc, hh[2], ll[2]); split_f16(x.w * sc, hh[3], ll[3]);
+        if (o.interleave) {
+          // lanes 2m / 2m+1 hold channels 8m .. 8m+7: the even lane collects both hi quads, the odd lane both lo quads,
+          // so every lane writes 16 contiguous bytes and one store instruction covers four whole 128-byte lines
+          const uint2 mh = *reinterpret_cast<uint2*>(hh), ml = *reinterpret_cast<uint2*>(ll);
+          const bool odd = lane & 1;
+          const uint2 give = odd ? mh : ml;       // what the partner needs from me
+          uint2 got;
+          got.x = __shfl_xor_sync(0xffffffffu, give.x, 1);
+          got.y = __shfl_xor_sync(0xffffffffu, give.y, 1);
+          const uint4 outv = odd ? make_uint4(got.x, got.y, ml.x, ml.y) : make_uint4(mh.x, mh.y, got.x, got.y);
+          const int c8 = c & ~7;                  // first channel of the lane pair's 8
+          *reinterpret_cast<uint4*>(o.hi16 + 2 * ro + il_col(c8) + (odd ? 32 : 0)) = outv;
+        } else {
+          *reinterpret_cast<uint2*>(o.hi16 + ro + c) = *reinterpret_cast<uint2*>(hh);
+          *reinterpret_cast<uint2*>(o.lo16 + ro + c) = *reinterpret_cast<uint2*>(ll);
+        }
       }
     }
     if (lane == 0) o.rnorm[pbase + p] = r;
@@ -332,13 +363,18 @@ __device__ __forceinline__ void gather_code_body(const SetTable& sets, int B, in
     for (int j = 0; j < R; ++j) {
       const float x = v[j] * r;
       const float hi = umma_tf32(x);
-      __nv_bfloat16 h, l;
-      split_bf16(x, h, l);
+      __half h, l;
+      split_f16(x * F16_CODE_SCALE, h, l);
       const int c = lane + 32 * j;
       o.out[ro + c] = hi;
       o.out_lo[ro + c] = x - hi;
-      o.hi16[ro + c] = h;
-      o.lo16[ro + c] = l;
+      if (o.interleave) {   // c = lane + 32 j: chunk j, hi at 64 j + lane, lo 32 further
+        o.hi16[2 * ro + 64 * j + lane] = h;
+        o.hi16[2 * ro + 64 * j + 32 + lane] = l;
+      } else {
+        o.hi16[ro + c] = h;
+        o.lo16[ro + c] = l;
+      }
     }
     if (lane == 0) o.rnorm[pbase + p] = r;
   }
@@ -422,11 +458,11 @@ __global__ void __launch_bounds__(256)
                            int Prows, int ld, const float* __restrict__ cn, const float* __restrict__ cn_lo,
                            const float* __restrict__ rnorm, const float* __restrict__ dC1,
                            const float* __restrict__ dC2, int npairs, const __grid_constant__ PairTable pairs,
-                           int has_depth, const __grid_constant__ GroupW gws, int nsets, int ni, int nj) {
+                           int has_depth, const __grid_constant__ GroupW gws, int nsets, int ni, int nj, int njw) {
   const int P = S * S;
-  // ni / nj: pitch (in panels) of the dC2 per-row-tile and dC1 per-column-group partial buffers; only the tiles /
-  // groups that contain real points were written
-  const int ni_used = min(ni, (P + 127) / 128), nj_used = min(nj, (P + 255) / 256);
+  // ni / nj: pitch (in panels) of the dC2 per-row-tile and dC1 per-column-tile (njw = 128) or per-column-group
+  // (njw = 256) partial buffers; only the tiles / groups that contain real points were written
+  const int ni_used = min(ni, (P + 127) / 128), nj_used = min(nj, (P + njw - 1) / njw);
   const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp_global >= nsets * B * P) return;
   const int set = warp_global / (B * P);
@@ -739,12 +775,12 @@ int launch_gather_all(const SetTable& fsets, const SetTable& csets, int nsets, i
 int launch_gather_bwd(const SetTable& tab, int nsets, int B, int C, int H, int W, const float* coords, int S,
                       const int64_t* perms, float eps, int Prows, int ld, const float* cn, const float* cn_lo,
                       const float* rnorm, const float* dC1, const float* dC2, int npairs, const PairTable& pt,
-                      int has_depth, const GroupW& gw, cudaStream_t st, int ni, int nj) {
+                      int has_depth, const GroupW& gw, cudaStream_t st, int ni, int nj, int njw) {
   const long long rows = (long long)nsets * B * S * S;
   const int blocks = (int)((rows * 32 + 255) / 256);
   DG_PRE(st);
   gather_norm_bwd_kernel<<<blocks, 256, 0, st>>>(tab, B, C, H, W, coords, S, perms, eps, Prows, ld, cn, cn_lo, rnorm,
-                                                 dC1, dC2, npairs, pt, has_depth, gw, nsets, ni, nj);
+                                                 dC1, dC2, npairs, pt, has_depth, gw, nsets, ni, nj, njw);
   DG_LAUNCH_OK("gather_norm_bwd_kernel");
   return DG_OK;
 }
@@ -764,9 +800,8 @@ extern "C" int dg_gather_norm(const float* t, const int64_t* strides, int B, int
   DG_REQUIRE(ld >= C && (ld % 32) == 0, DG_ERR_INVALID, "dg_gather_norm: ld=%d must be a multiple of 32 >= C=%d", ld, C);
   DG_REQUIRE(Prows >= S * S, DG_ERR_INVALID, "dg_gather_norm: Prows=%d < S*S=%d", Prows, S * S);
   DG_REQUIRE(format >= DG_PANEL_F32 && format <= DG_PANEL_CODE_SPLIT, DG_ERR_INVALID, "dg_gather_norm: bad format");
-  DG_REQUIRE(format == DG_PANEL_F32 || out_lo, DG_ERR_INVALID, "dg_gather_norm: split formats need out_lo");
-  DG_REQUIRE(format != DG_PANEL_CODE_SPLIT || (out16_hi && out16_lo), DG_ERR_INVALID,
-             "dg_gather_norm: code-split format needs the bf16 hi/lo panels too");
+  DG_REQUIRE(format != DG_PANEL_CODE_SPLIT || (out_lo && out16_hi), DG_ERR_INVALID,
+             "dg_gather_norm: code-split format needs out_lo (fp32 remainder) and the 16-bit panel");
   SetTable tab;
   int rc = fill_sets("dg_gather_norm", t, strides, nsets, set_coord, set_slot, perm != nullptr, &tab);
   if (rc != DG_OK) return rc;
@@ -774,10 +809,12 @@ extern "C" int dg_gather_norm(const float* t, const int64_t* strides, int B, int
   o.out = static_cast<float*>(out);
   o.out_lo = static_cast<float*>(out_lo);
   const bool code = format == DG_PANEL_CODE_SPLIT;
-  o.hi16 = static_cast<__nv_bfloat16*>(code ? out16_hi : out);
-  o.lo16 = static_cast<__nv_bfloat16*>(code ? out16_lo : out_lo);
+  o.hi16 = static_cast<__half*>(code ? out16_hi : out);
+  o.lo16 = static_cast<__half*>(code ? out16_lo : out_lo);
+  o.interleave = o.lo16 == nullptr ? 1 : 0;   // no separate lo panel given: the interleaved layout
   o.rnorm = rnorm;
   o.meanvec = meanvec;
+  if (format == DG_PANEL_F32) o.interleave = 0;
   return launch_gather(format, tab, nsets, B, C, H, W, coords, S, perm, eps, Prows, ld, 1, o,
                        reinterpret_cast<cudaStream_t>(stream));
 }
@@ -809,12 +846,11 @@ extern "C" int dg_gather_norm_bwd(float* grad, const int64_t* strides, int B, in
   GroupW gw;
   gw.arr = group_w;
   for (int g = 0; g < DG_NUM_GROUPS; ++g) gw.ptr[g] = nullptr;
-  // split (tcgen05) panels with more than 128 rows carry one dC2 buffer per 128-row tile, and above 256 points one
-  // dC1 buffer per 256-column group
+  // split (tcgen05) panels carry one dC2 buffer per 128-row tile and one dC1 buffer per 128-column tile
   const int ni = (cn_lo != nullptr) ? Prows / 128 : 1;
-  const int nj = (cn_lo != nullptr && S * S > 256) ? Prows / 256 : 1;
+  const int nj = ni;
   return launch_gather_bwd(tab, nsets, B, C, H, W, coords, S, perm, eps, Prows, ld, cn, cn_lo, rnorm, dC1, dC2, npairs,
-                           pt, has_depth, gw, reinterpret_cast<cudaStream_t>(stream), ni, nj);
+                           pt, has_depth, gw, reinterpret_cast<cudaStream_t>(stream), ni, nj, 128);
 }
 
 extern "C" int dg_pool_normalize(const float* t, const int64_t* strides, int N, int C, int H, int W, float eps,

@@ -2,6 +2,7 @@
 // loss entry points (loss_api.cu).  Everything here enqueues on `st` and returns DG_* codes.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 
@@ -21,18 +22,31 @@ struct SetTable {
 
 enum { FMT_F32 = 0, FMT_FEATS_SPLIT = 1, FMT_CODE_SPLIT = 2 };
 
+// The 16-bit split panels hold fp16 hi/lo of the normalised rows times a power of two: x * s = hi + lo + r with
+// |r| <= 2^-22 |x * s| (fp16 keeps 11 significand bits; the scale keeps lo out of the subnormal range for every
+// element down to ~1e-6 of a unit-norm row), so a 3-term product hi.hi + hi.lo + lo.hi is fp32-grade (~2^-22) where
+// the bf16 split of round 1 stopped at 2^-16.  Normalised rows have |x| <= 1, so nothing can overflow.
+constexpr float F16_FEAT_SCALE = 64.f;    // backbone feature panels
+constexpr float F16_CODE_SCALE = 256.f;   // code panels (gradient-GEMM operands)
+
 struct GatherOut {
   // FMT_F32        : out (fp32 [slot,b,Prows,ld])
-  // FMT_FEATS_SPLIT: hi16/lo16 (bf16 [slot,b,Prows,ld]) : x ~= hi + lo
+  // FMT_FEATS_SPLIT: hi16/lo16 (fp16 [slot,b,Prows,ld]) : F16_FEAT_SCALE * x ~= hi + lo
   // FMT_CODE_SPLIT : out = tf32-rounded hi, out_lo = x - hi (fp32 [slot,b,Prows,ld]) for the cd product,
-  //                  hi16/lo16 (bf16 [slot,b,Prows,ld]) the same rows for the gradient GEMMs
+  //                  hi16/lo16 (fp16 [slot,b,Prows,ld]) : F16_CODE_SCALE * x, the same rows for the gradient GEMMs
   float* out;
   float* out_lo;
-  __nv_bfloat16* hi16;
-  __nv_bfloat16* lo16;
+  __half* hi16;
+  __half* lo16;
+  // interleave != 0: ONE fp16 panel of pitch 2*ld at hi16, every 32-channel chunk stored as [32 hi | 32 lo] (128 bytes),
+  // so a TMA box row of the persistent tcgen05 kernel carries a chunk's hi and lo halves in one 128-byte line
+  int interleave;
   float* rnorm;
   float* meanvec;
 };
+
+// element offsets of channel c (hi part; the lo part sits 32 elements further) in an interleaved 16-bit panel row
+__host__ __device__ __forceinline__ size_t il_col(int c) { return ((size_t)(c >> 5) << 6) + (size_t)(c & 31); }
 
 struct PairTable {
   int32_t group[DG_MAX_PAIRS + 1];
@@ -103,7 +117,7 @@ int launch_gather_all(const SetTable& fsets, const SetTable& csets, int nsets, i
 int launch_gather_bwd(const SetTable& tab, int nsets, int B, int C, int H, int W, const float* coords, int S,
                       const int64_t* perms, float eps, int Prows, int ld, const float* cn, const float* cn_lo,
                       const float* rnorm, const float* dC1, const float* dC2, int npairs, const PairTable& pt,
-                      int has_depth, const GroupW& gw, cudaStream_t st, int ni = 1, int nj = 1);
+                      int has_depth, const GroupW& gw, cudaStream_t st, int ni = 1, int nj = 1, int njw = 256);
 int launch_corr_finalize(const float* partials, int npairs, int B, int P, const int32_t* group, int has_depth,
                          const int* err, float* out8, int n_pt, cudaStream_t st);
 int corr_loss_simt(const float* fn, const float* cn, const float* fmean, int nsplit, const float* dsign, int npairs, int B, int P,
@@ -115,6 +129,14 @@ int corr_loss_umma(const dg_panels_t* pan, const float* fmean, int nsplit, const
                    float* out8, float* dC1, float* dC2, float* cd_out, float* loss_out, float* dd_out, float* fd_dbg,
                    void* ws, cudaStream_t st, const int32_t* fslot1 = nullptr, const int32_t* fslot2 = nullptr,
                    int nfslots = 0, bool dots_done = false);
+// the persistent, double-buffered tcgen05 kernel (corr_pipe.cu): same arguments; Prows a multiple of 128, partial
+// gradient buffers dC1 [npairs+1, Prows/128 (column tile), ...] and dC2 [npairs+1, Prows/128 (row tile), ...]
+int corr_loss_pipe(const dg_panels_t* pan, const float* fmean, int nsplit, const float* dsign, int npairs, int B, int P, int Prows, int ldf,
+                   int ldc, const float* pair_shift, const int32_t* pair_group, float depth_shift, int flags,
+                   float* out8, float* dC1, float* dC2, float* cd_out, float* loss_out, float* dd_out, float* fd_dbg,
+                   void* ws, cudaStream_t st, const int32_t* fslot1 = nullptr, const int32_t* fslot2 = nullptr,
+                   int nfslots = 0, bool dots_done = false);
+size_t corr_pipe_workspace_floats(int npairs, int B, int P);
 // where corr_loss_umma keeps its error flag / completion counter and the pair dots inside its workspace
 void umma_ws_layout(void* ws, int** err, float** dots);
 size_t corr_workspace_bytes(int npairs, int B, int P);

@@ -37,10 +37,18 @@ static void make_plan(const dg_loss_desc_t* d, dg_loss_plan_t* p) {
   p->ldc = round_up(d->D, 32);
   // tcgen05 kernel: up to 256 points a CTA walks all column tiles; up to 1024 ("dense") the columns are cut into
   // groups of two tiles (panels padded to a multiple of 256 rows so that every group is whole)
-  p->kernel = (P <= 1024 && p->ldc <= 128 && !(d->flags & DG_FLAG_FORCE_SIMT)) ? 1 : 0;
-  p->Prows = p->kernel ? (P <= 256 ? round_up(P, 128) : round_up(P, 256)) : round_up(P, 64);
+  // kernel 2 = the persistent double-buffered tcgen05 kernel (corr_pipe.cu, default); 1 = the round-1 kernel
+  // (corr_umma.cu, DEPTHG_B200_CORR=umma1, kept for comparison); 0 = the generic CUDA-core kernel
+  p->kernel = (P <= 1024 && p->ldc <= 128 && !(d->flags & DG_FLAG_FORCE_SIMT)) ? 2 : 0;
+  if (p->kernel) {
+    const char* e = getenv("DEPTHG_B200_CORR");
+    if (e && strcmp(e, "umma1") == 0) p->kernel = 1;
+  }
+  p->Prows = p->kernel == 2 ? round_up(P, 128)
+                            : (p->kernel == 1 ? (P <= 256 ? round_up(P, 128) : round_up(P, 256)) : round_up(P, 64));
   const size_t ni = p->kernel ? p->Prows / 128 : 1;  // dC2 partial buffers (one per 128-row tile of the first operand)
-  const size_t nj = (p->kernel && P > 256) ? p->Prows / 256 : 1;  // dC1 partial buffers (one per column group)
+  // dC1 partial buffers: one per 128-column tile (kernel 2) / per 256-column group above 256 points (kernel 1)
+  const size_t nj = p->kernel == 2 ? p->Prows / 128 : ((p->kernel == 1 && P > 256) ? p->Prows / 256 : 1);
   const size_t np = p->npairs, B = d->B, Pr = p->Prows;
   const size_t nf = np + ((d->flags & DG_FLAG_AUG_INTRA) ? 1 : 0);   // feature panel slots (+1: depth-augmented features)
   size_t off = 0;
@@ -54,7 +62,13 @@ static void make_plan(const dg_loss_desc_t* d, dg_loss_plan_t* p) {
   p->ws = take(p->ws_bytes);
   p->dC1 = take((np + 1) * nj * B * Pr * p->ldc * 4);
   p->dC2 = take((np + 1) * ni * B * Pr * p->ldc * 4);
-  if (p->kernel) {
+  if (p->kernel == 2) {   // 16-bit panels interleaved per 32-channel chunk [32 hi | 32 lo]: one buffer of pitch 2 * ld
+    p->c_hi = take(np * B * Pr * p->ldc * 4);
+    p->c_lo = take(np * B * Pr * p->ldc * 4);
+    p->cb_hi = take(np * B * Pr * p->ldc * 4);
+    p->f_hi = take(nf * B * Pr * p->ldf * 4);
+    p->cb_lo = p->f_lo = 0;
+  } else if (p->kernel) {
     p->c_hi = take(np * B * Pr * p->ldc * 4);
     p->c_lo = take(np * B * Pr * p->ldc * 4);
     p->cb_hi = take(np * B * Pr * p->ldc * 2);
@@ -169,8 +183,9 @@ extern "C" int dg_loss_forward(const dg_loss_desc_t* d, const dg_loss_io_t* io, 
   }
   fo.out = reinterpret_cast<float*>(A + pl.f_hi);
   fo.out_lo = nullptr;
-  fo.hi16 = reinterpret_cast<__nv_bfloat16*>(A + pl.f_hi);
-  fo.lo16 = reinterpret_cast<__nv_bfloat16*>(A + pl.f_lo);
+  fo.hi16 = reinterpret_cast<__half*>(A + pl.f_hi);
+  fo.lo16 = reinterpret_cast<__half*>(A + pl.f_lo);
+  fo.interleave = pl.kernel == 2;
   fo.rnorm = reinterpret_cast<float*>(A + pl.frn);
   fo.meanvec = fmean;
   const int ffmt = pl.kernel ? FMT_FEATS_SPLIT : FMT_F32;
@@ -179,8 +194,9 @@ extern "C" int dg_loss_forward(const dg_loss_desc_t* d, const dg_loss_io_t* io, 
   build_sets(ctab, io->code, io->code_strides, io->code_pos, io->code_pos_strides, d->neg_samples);  // ncsets sets
   co.out = reinterpret_cast<float*>(A + pl.c_hi);
   co.out_lo = pl.kernel ? reinterpret_cast<float*>(A + pl.c_lo) : nullptr;
-  co.hi16 = pl.kernel ? reinterpret_cast<__nv_bfloat16*>(A + pl.cb_hi) : nullptr;
-  co.lo16 = pl.kernel ? reinterpret_cast<__nv_bfloat16*>(A + pl.cb_lo) : nullptr;
+  co.hi16 = pl.kernel ? reinterpret_cast<__half*>(A + pl.cb_hi) : nullptr;
+  co.lo16 = pl.kernel ? reinterpret_cast<__half*>(A + pl.cb_lo) : nullptr;
+  co.interleave = pl.kernel == 2;
   co.rnorm = reinterpret_cast<float*>(A + pl.crn);
   co.meanvec = nullptr;
   // (a single merged launch — launch_gather_all — was measured slower: the code CTAs inherit the feature
@@ -220,9 +236,10 @@ extern "C" int dg_loss_forward(const dg_loss_desc_t* d, const dg_loss_io_t* io, 
     pan.format = DG_PANEL_CODE_SPLIT;
     pan.f_hi = A + pl.f_hi; pan.f_lo = A + pl.f_lo; pan.c_hi = A + pl.c_hi; pan.c_lo = A + pl.c_lo;
     pan.cb_hi = A + pl.cb_hi; pan.cb_lo = A + pl.cb_lo;
-    return corr_loss_umma(&pan, fmean, nsplit, dsign, np, B, P, pl.Prows, pl.ldf, pl.ldc, shifts, groups, d->depth_feat_shift, kflags,
-                          io->out8, dC1, dC2, io->cd_out, io->loss_out, io->dd_out, io->fd_dbg, A + pl.ws, st, fs1, fs2,
-                          aug ? np + 1 : np, dots_done);
+    return (pl.kernel == 2 ? corr_loss_pipe : corr_loss_umma)(
+        &pan, fmean, nsplit, dsign, np, B, P, pl.Prows, pl.ldf, pl.ldc, shifts, groups, d->depth_feat_shift, kflags,
+        io->out8, dC1, dC2, io->cd_out, io->loss_out, io->dd_out, io->fd_dbg, A + pl.ws, st, fs1, fs2, aug ? np + 1 : np,
+        dots_done);
   }
   return corr_loss_simt(reinterpret_cast<const float*>(A + pl.f_hi), reinterpret_cast<const float*>(A + pl.c_hi), fmean,
                         nsplit, dsign, np, B, P, pl.Prows, pl.ldf, pl.ldc, shifts, groups, d->depth_feat_shift, kflags, io->out8,
@@ -263,5 +280,7 @@ extern "C" int dg_loss_backward(const dg_loss_desc_t* d, const dg_loss_io_t* io,
                            reinterpret_cast<const float*>(A + pl.crn), reinterpret_cast<const float*>(A + pl.dC1),
                            reinterpret_cast<const float*>(A + pl.dC2), pl.npairs, pt,
                            (d->flags & DG_FLAG_DEPTH_TERM) ? 1 : 0, gw, reinterpret_cast<cudaStream_t>(stream),
-                           pl.kernel ? pl.Prows / 128 : 1, (pl.kernel && d->S * d->S > 256) ? pl.Prows / 256 : 1);
+                           pl.kernel ? pl.Prows / 128 : 1,
+                           pl.kernel == 2 ? pl.Prows / 128 : ((pl.kernel == 1 && d->S * d->S > 256) ? pl.Prows / 256 : 1),
+                           pl.kernel == 2 ? 128 : 256);
 }

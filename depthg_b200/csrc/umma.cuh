@@ -42,9 +42,22 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Non-blocking test (for polling between other work)
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // Bounded wait: a wrong byte count / descriptor must not hang the GPU.  Returns false on
 // timeout (~ a few hundred ms); callers raise an error flag and fall through.
-__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
+// (not inlined: a kernel has dozens of wait sites, and their spin loops would otherwise dominate its code size)
+static __device__ __noinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
   for (uint32_t it = 0; it < 4000000u; ++it) {
     if (mbar_try_wait(bar, parity)) return true;
     if (it > 64) __nanosleep(64);
@@ -63,6 +76,14 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
           smem_u32(smem_dst)),
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
+}
+
+// 1-D bulk copy global -> shared (contiguous bytes, multiple of 16), completion on an mbarrier like a tensor load
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
 }
 
 // ---------------------------------------------------------------- TMEM
@@ -88,6 +109,14 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float* v) {
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr)
       : "memory");
+}
+// 32 lanes x 8 consecutive 32-bit columns (small epilogue loop bodies: the code stays inside the instruction cache)
+__device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 

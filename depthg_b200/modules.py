@@ -188,7 +188,10 @@ def sample_nonzero_locations(t: torch.Tensor, target_size, randint_fn=None) -> t
             pick = randint_fn(counts[i], (n,), None).to(t.device)
             rows.append(nz[off + pick, 1:])
         off += counts[i]
-    coords = torch.stack(rows).reshape(B, int(target_size[1]), int(target_size[2]), 2).to(torch.float32) / t.shape[1]
+    # (a device-tensor divisor: with a Python scalar torch's CUDA kernel multiplies by the reciprocal, which is one ulp
+    #  off the IEEE division the reference's CPU arithmetic — and its goldens — perform)
+    h = torch.full((), float(t.shape[1]), device=t.device, dtype=torch.float32)
+    coords = torch.stack(rows).reshape(B, int(target_size[1]), int(target_size[2]), 2).to(torch.float32) / h
     return torch.flip(coords * 2 - 1, dims=[-1])
 
 
@@ -355,7 +358,7 @@ class _CorrLossFn(torch.autograd.Function):
         loss_out = torch.empty((npairs, B, P, P), **f32) if materialize else None
         dd_out = torch.empty((B, P, P), **f32) if (materialize and has_depth) else None
         fd_dbg = None
-        if _CorrLossFn.debug and plan.kernel == 1:
+        if _CorrLossFn.debug and plan.kernel >= 1:
             fd_dbg = torch.zeros((npairs, B, plan.Prows, plan.Prows), **f32)
             _CorrLossFn.last_fd = fd_dbg
         io = _lib.LossIO()
@@ -381,14 +384,20 @@ class _CorrLossFn(torch.autograd.Function):
         ctx.desc, ctx.plan = desc, plan
         ctx.keep = (arena, coords, perms)          # the arena holds coords / panels / unit gradients for backward
         ctx.code_like = (code, code_pos)
-        if _CorrLossFn.debug:   # views of the unit gradients (dC2 summed over its per-row-tile partial buffers)
-            ni = plan.Prows // 128 if plan.kernel == 1 else 1
-            nj = plan.Prows // 256 if (plan.kernel == 1 and P > 256) else 1
+        if _CorrLossFn.debug:   # views of the unit gradients, summed over their per-tile partial buffers
+            if plan.kernel == 2:      # persistent tcgen05 kernel: dC2 per 128-row tile, dC1 per 128-column tile
+                ni = nj = plan.Prows // 128
+                niu = nju = -(-P // 128)
+            elif plan.kernel == 1:    # round-1 tcgen05 kernel: dC1 per 256-column group above 256 points
+                ni, niu = plan.Prows // 128, -(-P // 128)
+                nj, nju = (plan.Prows // 256, -(-P // 256)) if P > 256 else (1, 1)
+            else:
+                ni = nj = niu = nju = 1
             n1 = (npairs + 1) * B * plan.Prows * plan.ldc
             d1 = arena[plan.dC1:plan.dC1 + n1 * nj * 4].view(torch.float32).view(npairs + 1, nj, B, plan.Prows,
-                                                                                 plan.ldc)[:, :-(-P // 256)].sum(1)
+                                                                                 plan.ldc)[:, :nju].sum(1)
             d2 = arena[plan.dC2:plan.dC2 + n1 * ni * 4].view(torch.float32).view(npairs + 1, ni, B, plan.Prows,
-                                                                                 plan.ldc)[:, :-(-P // 128)].sum(1)
+                                                                                 plan.ldc)[:, :niu].sum(1)
             _CorrLossFn.last_unit_grads = (d1, d2)
         else:
             _CorrLossFn.last_unit_grads = None

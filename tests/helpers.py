@@ -140,3 +140,79 @@ def run_sal(name, impl, device="cpu", channels_last=False):
     out = fn(put(t["feats"]), put(t["feats_pos"]), t["salience"].to(dev), t["salience_pos"].to(dev), code, code_pos,
              t["depth"].to(dev), t["depth_pos"].to(dev))
     return _sal_result(fn, out, code, code_pos, cfg.depth_feat_correlation_loss)
+
+
+def clamp_tie_images(out64, perms, B, tau=1e-6):
+    """Images whose gradient may legitimately differ between two correct evaluations of the loss: the zero clamp is a
+    step function of cd, and a code correlation within `tau` of zero can land on either side depending on the fp32
+    summation order (the reference's own fp32 run flips such indicators against its fp64 run).  `out64` is the fp64
+    oracle's output tuple.  Returns (set of images of d_code, set of images of d_code_pos) touched by such a pair:
+    the intra pair of image b touches code[b]; the inter pair code[b] and code_pos[b]; negative n of image b code[b] and
+    code[perm_n[b]]."""
+    code, code_pos = set(), set()
+    near = lambda cd: (cd.detach().abs().flatten(1) < tau).any(1).numpy()   # noqa: E731
+    for b in np.nonzero(near(out64[1]))[0]:
+        code.add(int(b))
+    for b in np.nonzero(near(out64[3]))[0]:
+        code.add(int(b))
+        code_pos.add(int(b))
+    neg = near(out64[5]).reshape(-1, B)
+    for n, b in zip(*np.nonzero(neg)):
+        code.add(int(b))
+        code.add(int(perms[n][b]))
+    return code, code_pos
+
+
+def check_grads_tie_aware(r, want64, perms, rtol=1e-4, tau=1e-6):
+    """Per-image gradient parity against the fp64 evaluation of the reference algorithm: every image WITHOUT a clamp tie
+    must meet `rtol`; images with one are allowed the flip of that indicator (bounded loosely) — and there must be few."""
+    B = r["d_code"].shape[0]
+    ties = clamp_tie_images(want64["out"], perms, B, tau)
+    worst_clean = 0.0
+    for key, tied in (("d_code", ties[0]), ("d_code_pos", ties[1])):
+        for b in range(B):
+            e = rel_err(r[key][b], want64[key][b])
+            if b in tied:
+                assert e < 5e-2, (key, b, e)
+            else:
+                worst_clean = max(worst_clean, e)
+                assert e < rtol, (key, b, e, sorted(tied))
+        assert rel_err(r[key], want64[key]) < 5e-3, key
+        assert len(tied) <= max(2, B // 2), (key, sorted(tied))
+    return worst_clean, ties
+
+
+def clamp_tie_pixel_masks(out64, coords1, coords2, perms, H, W, tau=1e-6):
+    """Pixel-level version of clamp_tie_images for small cases: boolean masks [B,H,W] over code / code_pos of the pixels
+    a flipped clamp indicator can move.  cd[b,h,w,i,j] pairs the sample at coords1[b,w,h] (the reference's S-axis swap)
+    with the one at coords2[b,j,i]; each sample spreads over its <= 4 bilinear corner pixels."""
+    B, S = coords1.shape[0], coords1.shape[1]
+    m_code, m_pos = np.zeros((B, H, W), bool), np.zeros((B, H, W), bool)
+
+    def mark(mask, b, xy):
+        ix = min(max((xy[0] + 1.0) / 2.0 * (W - 1), 0.0), W - 1.0)
+        iy = min(max((xy[1] + 1.0) / 2.0 * (H - 1), 0.0), H - 1.0)
+        for yy in (int(np.floor(iy)), min(int(np.floor(iy)) + 1, H - 1)):
+            for xx in (int(np.floor(ix)), min(int(np.floor(ix)) + 1, W - 1)):
+                mask[b, yy, xx] = True
+
+    def scan(cd, second_coords, second_target):
+        """cd: [n*B,S,S,S,S]; the first sample always belongs to code[b] at coords1[b]."""
+        idx = np.argwhere(np.abs(cd.detach().numpy()) < tau)
+        for nb, h, w, i, j in idx:
+            b = int(nb) % B
+            mark(m_code, b, coords1[b][w][h])
+            sm, sb = second_target(int(nb))
+            mark(sm, sb, second_coords[b][j][i])
+        return len(idx)
+
+    n = scan(out64[1], coords1, lambda nb: (m_code, nb))                             # intra: code[b] twice
+    n += scan(out64[3], coords2, lambda nb: (m_pos, nb))                             # inter: code_pos[b]
+    n += scan(out64[5], coords2, lambda nb: (m_code, int(perms[nb // B][nb % B])))   # negatives: code[perm_n[b]]
+    return m_code, m_pos, n
+
+
+def masked_rel_err(a, b, mask):
+    keep = ~mask[:, None, :, :]
+    a, b = np.asarray(a, np.float64) * keep, np.asarray(b, np.float64) * keep
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))

@@ -14,11 +14,12 @@ live CUDA-event time, with the kernel's ncu DRAM traffic and traffic / algorithm
 (the same bytes over the whole step), ``extra_configs`` (BASELINE configs[3], the S = 12 paper value and the dense
 configs[4] as side measurements), ``breakdown_us`` (library-side per-kernel events), ``e2e`` (pinned host buffers, the faster of a
 double-buffered and a serialised loop, both reported), ``cpu_baseline`` (oracle port on the host cores),
-``reference_ops_on_gpu`` (the reference's op sequence as stock torch ops on this GPU), ``cuda_graph`` and
-``fused_negative_sampler`` (same step, less host work), ``knn`` (the precompute_knns build, query-sharded at N > 1; ``parity_checked`` = the timed
+``reference_ops_on_gpu`` (the reference's op sequence as stock torch ops on this GPU), ``cuda_graph`` (same step,
+no host work) and ``torch_negative_sampler`` (same step with the reference's randperm stream), ``knn`` (the precompute_knns build, query-sharded at N > 1; ``parity_checked`` = the timed
 result against the oracle on sampled rows and, at N > 1, against a one-GPU build) and ``probes`` (fused probe losses vs the trainer's torch op sequence).  At N > 1 every step is followed by the
 all-reduce of the trainable-head gradient (729 012 floats), replayed as a captured NCCL graph in stream order
-(DEPTHG_BENCH_ALLREDUCE = inline | graph | graph_hp | async | none).
+(DEPTHG_BENCH_ALLREDUCE = fps | inline | graph | graph_hp | async | none; fps = on the sampler's side stream,
+underneath the next step's FPS kernel).
 """
 from __future__ import annotations
 
@@ -31,6 +32,7 @@ import time
 
 if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
     os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout: the contract is ONE JSON line
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # (the banner itself still prints at WARN: send it to stderr)
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
@@ -430,11 +432,16 @@ def main():
     # Measured at N=8 (ms/step): graph 0.505, graph_hp 0.432, inline 0.344 - the all-reduce is latency-bound
     # (2.9 MB over NVSwitch) and its spinning CTAs fight the SM-filling step kernels when overlapped, so the
     # default runs it in stream order.
-    ar_mode = os.environ.get("DEPTHG_BENCH_ALLREDUCE", "inline") if world > 1 else "none"
+    # "fps" (default) = replayed on a side stream after backward i; step i+1's forward waits for it between its FPS
+    # kernel and its gathers (loss_fn.wait_after_fps): the all-reduce runs underneath step i+1's FPS kernel (2B CTAs on
+    # a 148-SM GPU) and the sampler draw, and is over before the SM-filling gathers start - overlap without contention.
+    ar_mode = os.environ.get("DEPTHG_BENCH_ALLREDUCE", "fps") if world > 1 else "none"
     ar_stream = ar_graph = None
+    ar_done = torch.cuda.Event()
     ar_inline = ar_mode == "inline"          # replay on the compute stream: no overlap, no SM contention
+    ar_fps = ar_mode == "fps"                # replay on the sampler's side stream, under the next step's FPS
     ar_hp = ar_mode in ("graph_hp",)         # side stream with high priority
-    if ar_mode in ("graph", "graph_hp", "inline"):
+    if ar_mode in ("graph", "graph_hp", "inline", "fps"):
         ar_mode = "graph"
         try:
             ar_stream = torch.cuda.Stream(device=dev, priority=-1 if ar_hp else 0)
@@ -462,6 +469,12 @@ def main():
             pending[0] = dist.all_reduce(head_grad, async_op=True)
         elif ar_mode == "graph" and ar_inline:
             ar_graph.replay()
+        elif ar_mode == "graph" and ar_fps:
+            ar_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(ar_stream):
+                ar_graph.replay()
+                ar_done.record(ar_stream)
+            loss_fn.wait_after_fps = ar_done    # the next forward waits for it between its FPS and its gathers
         elif ar_mode == "graph":
             ar_stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(ar_stream):
@@ -503,8 +516,9 @@ def main():
     ms_per_step = ms / args.steps
     value = world * B * args.steps / (ms / 1e3)
 
-    # same step with the one-launch negative sampler (same distribution, own Philox stream)
-    loss_fn.negative_sampler = "fused"
+    # same step with negative_sampler="torch": neg_samples x torch.randperm replayed as a CUDA graph on a side stream
+    # (the reference's exact RNG stream; more host work per step)
+    loss_fn.negative_sampler = "torch"
     for i in range(args.warmup):
         step(i)
     barrier()
@@ -518,10 +532,10 @@ def main():
         t = torch.tensor([ms_fused], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_fused = float(t.item())
-    loss_fn.negative_sampler = "torch"
+    loss_fn.negative_sampler = "fused"
 
     # ---- the same step captured once per input set into a CUDA graph (forward + backward + the torch.randperm
-    #      sampler, whose RNG is graph-safe) and replayed: what the path does when the host is out of the way
+    #      sampler) and replayed: what the path does when the host is out of the way
     graphed = None
     if world == 1:
         try:
@@ -544,7 +558,7 @@ def main():
             torch.cuda.synchronize()
             gms = ev0.elapsed_time(ev1) / args.steps
             graphed = {"value": B / (gms / 1e3), "unit": UNIT, "ms_per_step": gms,
-                       "note": "forward+backward (incl. torch.randperm sampler) captured per input set with "
+                       "note": "forward+backward (incl. the sampler) captured per input set with "
                                "torch.cuda.graph and replayed; same kernels, no per-step host work"}
             del graphs
         except Exception as e:  # noqa: BLE001
@@ -723,16 +737,22 @@ def main():
     # ---- KNN build side metric (query-row sharded; all-gather of the database when N > 1)
     knn = None
     if not args.no_knn:
-        from depthg_b200.distributed import allgather_rows, shard_bounds
+        from depthg_b200.distributed import allgather_rows, knn_shard_bounds, sharded_knn_build
         N, F, k = KNN["N"], KNN["F"], KNN["k"]
         g2 = torch.Generator(device=dev).manual_seed(7)
         allf = torch.nn.functional.normalize(torch.randn((N, F), generator=g2, device=dev), dim=1)
-        lo, hi = shard_bounds(N, world, rank)
+        lo, hi = knn_shard_bounds(N, world, rank)
         local = allf[lo:hi].contiguous()
+        knn_mode = os.environ.get("DEPTHG_BENCH_KNN", "overlap")   # overlap (two-phase, default) | serial (round 1)
 
         def knn_step():
-            db = allgather_rows(local, N) if world > 1 else local
-            return knn_topk(local, db, k, return_stats=True)
+            if world > 1 and knn_mode == "serial":
+                per = -(-N // world)
+                src = local if hi - lo == per else torch.cat([local, local.new_zeros((per - (hi - lo), F))])
+                gathered = torch.empty((world * per, F), device=dev)
+                dist.all_gather_into_tensor(gathered, src)
+                return knn_topk(local, gathered[:N], k, return_stats=True)
+            return sharded_knn_build(local, N, k, return_stats=True)
 
         knn_step()
         barrier()
@@ -765,7 +785,11 @@ def main():
                   "pipeline_error": kstats["pipeline_error"],
                   "against": "oracle (fp32 einsum + topk on the host) on sampled query rows of the timed result"}
         if world > 1:
-            full_sharded = allgather_rows(kidx, N)
+            per = -(-N // world)
+            pad = kidx if hi - lo == per else torch.cat([kidx, kidx.new_zeros((per - (hi - lo), k))])
+            full_sharded = torch.empty((world * per, k), device=dev, dtype=kidx.dtype)
+            dist.all_gather_into_tensor(full_sharded, pad)
+            full_sharded = full_sharded[:N]
             flag = torch.tensor([1.0 if parity["ok"] else 0.0], device=dev)
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)
             parity["ok_all_ranks"] = bool(flag.item() == 1.0)
@@ -786,7 +810,10 @@ def main():
         flops = 2.0 * N * N * F
         per_gpu_tflops = flops / (kms / 1e3) / 1e12 / world
         knn = {"metric": "knn_build_img_per_s", "value": N / (kms / 1e3), "unit": "img/s", "ms": kms, "N": N, "F": F,
-               "k": k, "scaling": "strong", "sharding": "query rows; all-gather of the feature database",
+               "k": k, "scaling": "strong",
+               "sharding": "query rows; all-gather of the feature database" +
+                           (" overlapped with the tensor pass over the local rows (two-phase build)"
+                            if world > 1 and knn_mode != "serial" else ""),
                "parity_checked": parity,
                "roofline": {"bound": "tensor", "achieved": per_gpu_tflops, "peak": tf_burst,
                             "unit": "TFLOP/s per GPU", "frac": per_gpu_tflops / tf_burst, "n_gpus": world,
@@ -875,17 +902,20 @@ def main():
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": workload_config(B, world, extra={
                     "l2_policy": f"rotating {NSETS} input sets ({NSETS * step_bytes / 1e6:.0f} MB) > 126 MB L2",
+                    "negative_sampler": "fused (module default: one dg_super_perms launch)",
                     "allreduce_floats_per_step": HEAD_GRAD_FLOATS if ar_mode != "none" else 0,
-                    "allreduce_issue": ar_mode + ("_inline" if ar_inline else "_hp" if ar_hp else ""),
+                    "allreduce_issue": ar_mode + ("_inline" if ar_inline else "_hp" if ar_hp else
+                                                  "_under_next_fps" if ar_fps else ""),
                     "layout": "nchw" if args.nchw else "channels_last (live trainer layout)"}),
                 "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches),
                 "launches_per_step": launches / args.steps, "roofline": roofline, "roofline_step": roofline_step,
                 "breakdown_us": {k: round(v, 2) for k, v in breakdown.items()}, "cpu_baseline": cpu_baseline,
                 "cuda_graph": graphed, "reference_ops_on_gpu": ref_gpu,
-                "fused_negative_sampler": {"value": world * B * args.steps / (ms_fused / 1e3), "unit": UNIT,
+                "torch_negative_sampler": {"value": world * B * args.steps / (ms_fused / 1e3), "unit": UNIT,
                                            "ms_per_step": ms_fused / args.steps,
-                                           "note": "negative_sampler='fused': one dg_super_perms launch instead of "
-                                                   "neg_samples x torch.randperm (same distribution, different stream)"},
+                                           "note": "negative_sampler='torch': neg_samples x torch.randperm (the reference's "
+                                                   "exact RNG stream, replayed as a CUDA graph on a side stream) instead of "
+                                                   "the default one-launch dg_super_perms (same distribution)"},
                 "knn": knn, "probes": probes, "extra_configs": extra}
         print(json.dumps(line), flush=True)
     if world > 1:

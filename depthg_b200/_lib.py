@@ -54,6 +54,8 @@ SIGNATURES = {
     "dg_loss_backward": (C.c_int, [_vp, _vp, _vp, _vp]),
     "dg_knn_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "dg_knn_topk": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, C.c_size_t, _vp]),
+    "dg_knn_shard_begin": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_size_t, _vp]),
+    "dg_knn_shard_finish": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, C.c_size_t, _vp]),
     "dg_pool_normalize": (C.c_int, [_vp, _c_i64p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _vp, _vp]),
     "dg_probe_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "dg_linear_probe_ce": (C.c_int, [_vp, _c_i64p, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, C.c_int, _vp, _c_i64p,

@@ -296,6 +296,10 @@ size_t knn_umma_workspace_bytes(int Nq, int N, int F);
 int knn_topk_umma(const float* q, const float* db, int Nq, int N, int F, int k, int64_t* idx, float* sims, void* ws,
                   cudaStream_t st);
 
+int knn_shard_begin(const float* local, int Nq, int row_lo, int N, int F, int k, void* ws, cudaStream_t st);
+int knn_shard_finish(const float* db, int Nq, int row_lo, int N, int F, int k, int64_t* idx, float* sims, void* ws,
+                     cudaStream_t st);
+
 int launch_knn_exact(const float* q, const float* db, int Nq, int N, int F, int k, int64_t* idx, float* sims,
                      const int* row_list, const int* row_count, cudaStream_t st) {
   if (row_list) {
@@ -348,4 +352,34 @@ extern "C" int dg_knn_topk(const float* q, const float* db, int Nq, int N, int F
   }
   if (ws && ws_bytes >= 256) DG_CUDA_OK(cudaMemsetAsync(ws, 0, 256, st));   // diagnostics header: nothing to report
   return launch_knn_exact(q, db, Nq, N, F, k, idx, sims, nullptr, nullptr, st);
+}
+
+// Two-phase form of dg_knn_topk for a query-row shard whose rows are database rows [row_lo, row_lo + Nq): see
+// knn_umma.cu.  `tensor_path` reports whether the shape takes the tensor-core path (otherwise begin does nothing and
+// finish is the plain exact build).
+extern "C" int dg_knn_shard_begin(const float* local, int Nq, int row_lo, int N, int F, int k, void* ws, size_t ws_bytes,
+                                  dg_stream_t stream) {
+  using namespace dg;
+  DG_REQUIRE(local && Nq > 0 && N > 0 && F > 0 && row_lo >= 0 && row_lo + Nq <= N, DG_ERR_INVALID,
+             "dg_knn_shard_begin: bad arguments");
+  DG_REQUIRE(k > 0 && k <= 32 && k <= N, DG_ERR_INVALID, "dg_knn_shard_begin: k=%d out of range", k);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (!use_umma(Nq, N, k)) return DG_OK;
+  DG_REQUIRE(ws && ws_bytes >= knn_umma_workspace_bytes(Nq, N, F), DG_ERR_WORKSPACE, "dg_knn_shard_begin: workspace too small");
+  return knn_shard_begin(local, Nq, row_lo, N, F, k, ws, st);
+}
+
+extern "C" int dg_knn_shard_finish(const float* db, int Nq, int row_lo, int N, int F, int k, int64_t* idx, float* sims,
+                                   void* ws, size_t ws_bytes, dg_stream_t stream) {
+  using namespace dg;
+  DG_REQUIRE(db && idx && Nq > 0 && N > 0 && F > 0 && row_lo >= 0 && row_lo + Nq <= N, DG_ERR_INVALID,
+             "dg_knn_shard_finish: bad arguments");
+  DG_REQUIRE(k > 0 && k <= 32 && k <= N, DG_ERR_INVALID, "dg_knn_shard_finish: k=%d out of range", k);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (use_umma(Nq, N, k)) {
+    DG_REQUIRE(ws && ws_bytes >= knn_umma_workspace_bytes(Nq, N, F), DG_ERR_WORKSPACE, "dg_knn_shard_finish: workspace too small");
+    return knn_shard_finish(db, Nq, row_lo, N, F, k, idx, sims, ws, st);
+  }
+  if (ws && ws_bytes >= 256) DG_CUDA_OK(cudaMemsetAsync(ws, 0, 256, st));
+  return launch_knn_exact(db + (size_t)row_lo * F, db, Nq, N, F, k, idx, sims, nullptr, nullptr, st);
 }

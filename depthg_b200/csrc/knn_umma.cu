@@ -5,11 +5,15 @@
 // reproduces its index order (SURVEY.md 7.1 iii), so the build is three steps that never
 // materialise the similarity matrix:
 //   1. split_rows_kernel   : fp32 rows -> bf16 hi/lo panels (x ~= hi + lo), K padded to 64
-//   2. knn_umma_kernel     : one CTA per 128 query rows streams the database in 128-row tiles;
-//                            sims = hi.hi + hi.lo + lo.hi on tcgen05 (error <~ 2e-5), two TMEM
+//   2. knn_umma_kernel     : one CTA per 128 query rows streams the database in 256-row tiles;
+//                            sims = hi.hi + hi.lo + lo.hi on tcgen05 (error bound: ku_eps_unit), two TMEM
 //                            accumulators so the MMAs of tile t+1 overlap the epilogue of tile t;
-//                            the epilogue (one thread per query row) keeps the 32 best candidates
-//                            of its row in a sorted shared-memory list (threshold in a register); the
+//                            the epilogue is ONE THREAD PER QUERY ROW (the TMEM row-per-thread layout): the row's 32
+//                            best candidates live in shared memory as an unsorted list with its minimum (the
+//                            threshold) and the minimum's slot in registers; a value enters by overwriting the
+//                            minimum, followed by a 32-entry rescan.  32 rows insert in parallel, so a cold list
+//                            costs microseconds (the round-1 warp-cooperative sorted lists serialised the rows and
+//                            paid ~0.5 ms per cold segment) - which is what makes database segments cheap: the
 //                            database is cut into nseg segments (grid.y) so that small query blocks
 //                            (multi-GPU shards) still fill the GPU and every row gets nseg x 32 candidates
 //   3. knn_rerank_kernel   : exact fp32 dot products of the 32 candidates (a warp per query row),
@@ -26,22 +30,22 @@ namespace dg {
 
 using namespace umma;
 
-constexpr int KU_THREADS = 320;  // TMA warp + MMA warp + 8 epilogue warps (two per TMEM lane group)
-constexpr int KU_SUB = 2;        // epilogue warps per lane group = candidate lists per (row, segment)
-// BN = database rows per MMA tile (the UMMA N).  A stage holds one 64-wide K chunk of the query block (hi, lo:
-// 2 x 16 KB) and of BN database rows (hi, lo: 2 x BN x 128 B).  BN = 256 loads the query chunk once per 256
-// database rows instead of once per 128: 25 % less L2->SM operand traffic, which is what bounds this kernel.
-// The kernel is bound by how many operand bytes an SM keeps in flight from L2, so BN = 256 uses 32-wide K chunks
-// (64-byte rows, SWIZZLE_64B): 4 stages of 48 KB instead of 2 of 96 KB.
+constexpr int KU_THREADS = 192;  // TMA warp + MMA warp + 4 epilogue warps (one per TMEM lane group)
+constexpr int KU_SUB = 1;        // candidate lists per (row, segment)
+constexpr int KU_CAND = 32;
+// BN = database rows per MMA tile (the UMMA N).  A stage holds one K chunk of the query block (hi, lo) and of BN
+// database rows (hi, lo).  BN = 256 loads the query chunk once per 256 database rows instead of once per 128 (25 % less
+// L2->SM operand traffic) and uses 32-wide K chunks (64-byte rows, SWIZZLE_64B): 4 stages of 48 KB in flight.
+// Besides the ring, shared memory holds the candidate lists: 128 rows x 32 entries x (value, index) = 32 KB.
 template <int BN> struct KuCfg {
   static constexpr int KC = BN == 128 ? 64 : 32;                  // K elements per stage
   static constexpr int QBYTES = 128 * KC * 2, DBYTES = BN * KC * 2;  // one bf16 panel chunk of the query / database tile
   static constexpr int STAGE = 2 * QBYTES + 2 * DBYTES;
   static constexpr int NSTAGE = BN == 128 ? 3 : 4;
-  static constexpr int SMEM = NSTAGE * STAGE + 8 * 32 * 33 * 4 + 1024 + 256;
+  static constexpr int LISTS = 4 * 32 * KU_CAND * 8;
+  static constexpr int SMEM = NSTAGE * STAGE + LISTS + 1024 + 256;
 };
-constexpr int KU_CAND = 32;
-constexpr int KU_LSTR = KU_CAND + 1;
+static_assert(KuCfg<256>::SMEM <= 232448 && KuCfg<128>::SMEM <= 232448, "knn_umma_kernel: shared memory over the CTA limit");
 // Bound on |approx - exact| of the 3-product bf16 split, as a multiple of |q| * max|d| (the row norms are measured by
 // split_rows_kernel, so un-normalised inputs get a proportionally wider bound instead of a silently wrong one):
 //   x = hi + lo + r with |lo| <= 2^-8 |x| and |r| <= 2^-8 |lo| <= 2^-16 |x| (bf16 keeps 8 significand bits), so
@@ -55,9 +59,15 @@ __host__ __device__ inline float ku_eps_unit(int F) {
 
 struct KnnUmmaParams {
   CUtensorMap tm_qh, tm_ql, tm_dh, tm_dl;  // bf16 [rows, Fp], box 64 x 128, SWIZZLE_128B
-  int Nq, N, nchunk, ntiles, nseg;          // ntiles in units of BN database rows
-  int* cand_idx;    // [Nq,nseg,KU_SUB,32]
-  float* cand_val;  // [Nq,nseg,KU_SUB,32] approximate sims, descending within a list
+  int Nq, N, nchunk, ntiles, nseg;          // ntiles in units of BN database rows (VIRTUAL tiles, see tile_of)
+  int list_pitch;                           // lists per row in cand_* (>= nseg: a launch may fill only the first nseg)
+  // The tiles a launch visits are a virtual list mapped onto the database: virtual tile v is tile v when v < tA_end
+  // and tile v + tB_shift otherwise (the sharded build visits "the local rows" and later "everything but the local
+  // rows").  Columns are masked by col_mode: 0 = column < N, 1 = only [col_lo, col_hi), 2 = only outside of it.
+  int tA_end, tB_shift, col_lo, col_hi, col_mode;
+  int warm;                                 // 1: start from the candidate lists a previous launch left in cand_*
+  int* cand_idx;    // [Nq,nseg,32]; unused entries -1
+  float* cand_val;  // [Nq,nseg,32] approximate sims (unsorted); unused entries -inf
   int* err;
 };
 
@@ -109,8 +119,10 @@ __global__ void __launch_bounds__(KU_THREADS, 1) knn_umma_kernel(const __grid_co
   // 1024-byte alignment for SWIZZLE_128B, computed as an offset so the pointer stays in the shared address space
   // (a round trip through uintptr_t makes every later access a generic LD/ST instead of LDS/STS)
   uint8_t* ring = ku_raw + ((1024u - (smem_u32(ku_raw) & 1023u)) & 1023u);
-  float* stage_tiles = reinterpret_cast<float*>(ring + KU_NSTAGE * KU_STAGE);  // [4 warps][32 rows][33] transpose staging
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_tiles + 8 * 32 * KU_LSTR);
+  // candidate lists: per epilogue warp 32 slots x 32 rows of values, then of indices; slot e of row r lives at word
+  // e * 32 + (r ^ e), which is conflict-free both for "every row scans slot e" and for "one row, all slots"
+  float* lists = reinterpret_cast<float*>(ring + KU_NSTAGE * KU_STAGE);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + KU_NSTAGE * KU_STAGE + KuCfg<BN>::LISTS);
   uint64_t* full = bars;               // [<=4]
   uint64_t* empty = bars + 4;          // [<=4]
   uint64_t* tfull = bars + 8;          // [2] accumulator ready
@@ -125,6 +137,7 @@ __global__ void __launch_bounds__(KU_THREADS, 1) knn_umma_kernel(const __grid_co
   const int per_seg = (prm.ntiles + prm.nseg - 1) / prm.nseg;
   const int t_begin = seg * per_seg, t_end = min(t_begin + per_seg, prm.ntiles);
   const int nchunk = prm.nchunk, ntiles = max(t_end - t_begin, 0);
+  auto tile_of = [&](int v) { return v < prm.tA_end ? v : v + prm.tB_shift; };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < KU_NSTAGE; ++s) {
@@ -133,7 +146,7 @@ __global__ void __launch_bounds__(KU_THREADS, 1) knn_umma_kernel(const __grid_co
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], 256);  // every epilogue thread arrives
+      mbar_init(&tempty[a], 128);  // every epilogue thread arrives
     }
     fence_barrier_init();
   }
@@ -155,8 +168,8 @@ __global__ void __launch_bounds__(KU_THREADS, 1) knn_umma_kernel(const __grid_co
           mbar_arrive_expect_tx(&full[s], KU_STAGE);
           tma_load_2d(st, &prm.tm_qh, &full[s], c * KC, m0);
           tma_load_2d(st + QB, &prm.tm_ql, &full[s], c * KC, m0);
-          tma_load_2d(st + 2 * QB, &prm.tm_dh, &full[s], c * KC, (t_begin + t) * BN);
-          tma_load_2d(st + 2 * QB + DB, &prm.tm_dl, &full[s], c * KC, (t_begin + t) * BN);
+          tma_load_2d(st + 2 * QB, &prm.tm_dh, &full[s], c * KC, tile_of(t_begin + t) * BN);
+          tma_load_2d(st + 2 * QB + DB, &prm.tm_dl, &full[s], c * KC, tile_of(t_begin + t) * BN);
         }
       }
     }
@@ -191,90 +204,105 @@ __global__ void __launch_bounds__(KU_THREADS, 1) knn_umma_kernel(const __grid_co
       if (!ok && prm.err) atomicCAS(prm.err, 0, 12);
     }
   } else {
-    // ---- epilogue: warp-cooperative running top-32 per row.  The warp owns the 32 rows of its TMEM lane group; each
-    //      row's sorted candidate list is spread over the 32 lanes (entry l in lane l), so an insertion is one
-    //      ballot + two shuffles and costs the same whether the list is cold or warm.
-    // Two warps share each TMEM lane group (a warp may only read lanes 32*(warp%4)..+31) and split its column
-    // chunks even/odd; each keeps its own list, so a row ends up with KU_SUB lists per database segment.
-    const int lg = warp & 3, sub = (warp - 2) >> 2;
+    // ---- epilogue: thread = query row (the TMEM row-per-thread layout), see the file header
+    const int lg = warp & 3;     // the TMEM lane group this warp may read: lanes 32 * (warp % 4) ..
     const uint32_t tlane = tmem + ((uint32_t)(32 * lg) << 16);
-    float* tile = stage_tiles + (warp - 2) * (32 * KU_LSTR);
-    float tv[32];
-    int ti[32];
-#pragma unroll
-    for (int r = 0; r < 32; ++r) {
-      tv[r] = -INFINITY;
-      ti[r] = -1;
+    float* lv = lists + (warp - 2) * (2 * 32 * KU_CAND);
+    int* li = reinterpret_cast<int*>(lv + 32 * KU_CAND);
+    float thr = -INFINITY;   // smallest value of the full list; -inf while the list still has room
+    int minpos = 0, fill = 0;
+    auto rescan = [&]() {
+      float m = INFINITY;
+      int mp = 0;
+#pragma unroll 8
+      for (int e = 0; e < KU_CAND; ++e) {
+        const float x = lv[e * 32 + (lane ^ e)];
+        if (x < m) { m = x; mp = e; }
+      }
+      thr = m;
+      minpos = mp;
+    };
+    if (prm.warm) {   // continue the list a previous launch (same grid, same segments) left in cand_*
+      // coalesced: for each row of the warp, lane e fetches entry e
+      for (int r = 0; r < 32; ++r) {
+        const int q = m0 + 32 * lg + r;
+        float x = -INFINITY;
+        int xi = -1;
+        if (q < prm.Nq) {
+          const size_t o = ((size_t)q * prm.list_pitch + seg) * KU_CAND;
+          xi = prm.cand_idx[o + lane];
+          x = xi >= 0 ? prm.cand_val[o + lane] : -INFINITY;   // an untouched (memset 0xff) list is an empty list
+        }
+        lv[lane * 32 + (r ^ lane)] = x;    // slot e = lane of row r
+        li[lane * 32 + (r ^ lane)] = xi;
+      }
+      __syncwarp();
+      // a list is stored compacted: its first `fill` slots are taken
+      for (int e = 0; e < KU_CAND; ++e) fill += li[e * 32 + (lane ^ e)] >= 0 ? 1 : 0;
+      if (fill == KU_CAND) rescan();
     }
     float v[32];
-    float mythr = -INFINITY;  // current 32nd-best value of query row `lane` (the row this thread reads from TMEM)
     bool ok = true;
     for (int t = 0; t < ntiles && ok; ++t) {
       const int a = t & 1;
       ok = mbar_wait(&tfull[a], (t >> 1) & 1);
       tc_fence_after_sync();
-      const int n0 = (t_begin + t) * BN;
+      const int n0 = tile_of(t_begin + t) * BN;
 #pragma unroll 1
-      for (int cc = sub; cc < BN / 32; cc += KU_SUB) {
-        tmem_ld_32x32(tlane + a * BN + 32 * cc, v);   // thread = query row `lane`, 32 consecutive database columns
+      for (int cc = 0; cc < BN / 32; ++cc) {
+        __syncwarp();                                 // rows diverge below; the TMEM load is warp-collective
+        tmem_ld_32x32(tlane + a * BN + 32 * cc, v);   // this thread's row, 32 consecutive database columns
         tmem_ld_wait();
         const int nb = n0 + 32 * cc;
-        // Filter in the row-per-thread layout first: a column only matters if it beats the row's current 32nd
-        // value, which this thread keeps in `mythr`.  Once the lists are warm most rows have nothing to insert,
-        // and only rows that do are transposed through shared memory and visited by the list code below.
         float vmax = v[0];
 #pragma unroll
         for (int i = 1; i < 32; ++i) vmax = fmaxf(vmax, v[i]);
-        // (columns past the end of the database are zero-filled by TMA: they can only cause a harmless visit,
-        //  the list code below masks them with col_ok)
-        const bool mine = vmax > mythr;
-        const unsigned rows = __ballot_sync(0xffffffffu, mine);
-        if (rows == 0) continue;
-        if (mine) {
+        // (columns past the end of the database are zero-filled by TMA and rows a sharded build has not split yet may
+        //  hold anything: the column mask below is what keeps them out)
+        if (!(vmax > thr)) continue;
+        // Rows with a candidate (about one in ten once the lists are warm) leave the straight-line path: the 32
+        // values go to a thread-local staging array so that ONE rolled loop can walk the hit mask.  (32 unrolled
+        // copies of the insertion were ~50 KB of code that every chunk had to hop through: instruction-cache misses
+        // cost 4x the arithmetic.)
+        unsigned hits = 0;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) tile[lane * KU_LSTR + i] = v[i];
-        }
-        __syncwarp();
-        const bool col_ok = nb + lane < prm.N;
+        for (int i = 0; i < 32; ++i) hits |= (v[i] > thr ? 1u : 0u) << i;
+        float stage[32];
 #pragma unroll
-        for (int r = 0; r < 32; ++r) {
-          if (!((rows >> r) & 1u)) continue;                              // warp-uniform
-          const float x = tile[r * KU_LSTR + lane];                       // lane = column of row r
-          const float thr = __shfl_sync(0xffffffffu, tv[r], KU_CAND - 1);
-          unsigned m = __ballot_sync(0xffffffffu, col_ok && x > thr);
-          while (m) {
-            const int src = __ffs(m) - 1;
-            m &= m - 1;
-            const float nv = __shfl_sync(0xffffffffu, x, src);
-            if (nv > __shfl_sync(0xffffffffu, tv[r], KU_CAND - 1)) {      // still above the (possibly raised) 32nd value
-              const int pos = __popc(__ballot_sync(0xffffffffu, tv[r] >= nv));
-              const float up_v = __shfl_up_sync(0xffffffffu, tv[r], 1);
-              const int up_i = __shfl_up_sync(0xffffffffu, ti[r], 1);
-              if (lane == pos) {
-                tv[r] = nv;
-                ti[r] = nb + src;
-              } else if (lane > pos) {
-                tv[r] = up_v;
-                ti[r] = up_i;
-              }
-            }
+        for (int i = 0; i < 32; ++i) stage[i] = v[i];
+#pragma unroll 1
+        while (hits) {
+          const int i = __ffs(hits) - 1;
+          hits &= hits - 1;
+          const float x = stage[i];
+          const int col = nb + i;
+          const bool inside = col >= prm.col_lo && col < prm.col_hi;
+          const bool col_ok = prm.col_mode == 1 ? inside : (col < prm.N && !(prm.col_mode == 2 && inside));
+          if (x > thr && col_ok) {          // thr may have risen since the mask was built
+            const int slot = fill < KU_CAND ? fill : minpos;
+            lv[slot * 32 + (lane ^ slot)] = x;
+            li[slot * 32 + (lane ^ slot)] = col;
+            if (fill < KU_CAND) ++fill;
+            if (fill == KU_CAND) rescan();
           }
-          const float nthr = __shfl_sync(0xffffffffu, tv[r], KU_CAND - 1);
-          if (lane == r) mythr = nthr;
         }
-        __syncwarp();
       }
       tc_fence_before_sync();
       mbar_arrive(&tempty[a]);
     }
     if (!ok && prm.err) atomicCAS(prm.err, 0, 13);
-#pragma unroll
+    // unused slots leave as (-inf, -1); coalesced write-out: for each row of the warp, lane e stores entry e
+    for (int e = fill; e < KU_CAND; ++e) {
+      lv[e * 32 + (lane ^ e)] = -INFINITY;
+      li[e * 32 + (lane ^ e)] = -1;
+    }
+    __syncwarp();
     for (int r = 0; r < 32; ++r) {
       const int q = m0 + 32 * lg + r;
       if (q < prm.Nq) {
-        const size_t o = (((size_t)q * prm.nseg + seg) * KU_SUB + sub) * KU_CAND;
-        prm.cand_idx[o + lane] = ti[r];
-        prm.cand_val[o + lane] = tv[r];
+        const size_t o = ((size_t)q * prm.list_pitch + seg) * KU_CAND;
+        prm.cand_val[o + lane] = lv[lane * 32 + (r ^ lane)];
+        prm.cand_idx[o + lane] = li[lane * 32 + (r ^ lane)];
       }
     }
   }
@@ -283,40 +311,54 @@ __global__ void __launch_bounds__(KU_THREADS, 1) knn_umma_kernel(const __grid_co
   if (warp == 1) tmem_dealloc(tmem, 2 * BN);
 }
 
-// One warp per query row: exact fp32 similarities of its nseg x 32 candidates (lane l owns candidate l of every
-// segment), k rounds of warp-argmax by (value desc, index asc) to emit the top k, and the certificate.
+// One warp per query row.  The candidate lists carry APPROXIMATE similarities a with |a - exact| <= eps, so:
+//   * candidates below (k-th largest a) - 2 eps cannot be in the exact top-k and are dropped;
+//   * the survivors (about k + 1 of them) are compacted; two survivors whose a differ by more than 2 eps are ordered
+//     for certain, so an exact fp32 dot product is only spent on the AMBIGUOUS ones - those within 2 eps of another
+//     survivor - (all of them when the caller wants the similarities back);
+//   * k rounds of warp-argmax by (key desc, index asc) emit the top k, key = exact where it was computed, a otherwise
+//     (consistent with the exact order: an unambiguous key is more than eps away from every other interval);
+//   * CERTIFICATE: a lower bound of the exact k-th value must beat tau + eps, tau = the largest 32nd value of the row's
+//     lists, i.e. nothing outside the candidate lists can belong to the top-k.  Rows that fail (true ties, or more than
+//     64 survivors) are listed and recomputed by the exact fp32 kernel (knn.cu).
 constexpr int KU_MAXSEG = 8;
+constexpr int KU_SURV = 64;
 
 __global__ void __launch_bounds__(256) knn_rerank_kernel(const float* __restrict__ q, const float* __restrict__ db,
-                                                         int Nq, int N, int F, int k, int nseg,
+                                                         int Nq, int N, int F, int k, int nlists,
                                                          const int* __restrict__ cand_idx,
                                                          const float* __restrict__ cand_val, int64_t* __restrict__ idx,
                                                          float* __restrict__ sims, int* __restrict__ fail_rows,
                                                          int* __restrict__ fail_count, const int* __restrict__ err,
                                                          const float* __restrict__ qnorm2,
                                                          const int* __restrict__ dbmax2_bits, float eps_unit) {
+  __shared__ float s_val[8][KU_SURV];
+  __shared__ int s_idx[8][KU_SURV];
+  const int wid = threadIdx.x >> 5;
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (row >= Nq) return;
   // error bound of the approximate similarities of this row: eps_unit * |q| * max |d|
   const float eps = eps_unit * sqrtf(__ldg(qnorm2 + row)) * sqrtf(__int_as_float(__ldg(dbmax2_bits)));
   const float* qr = q + (size_t)row * F;
   int my_idx[KU_MAXSEG];
-  float my_a[KU_MAXSEG], my_e[KU_MAXSEG];
+  float my_a[KU_MAXSEG];
   float tau = -INFINITY;  // everything outside the candidate lists is <= tau (approximately)
 #pragma unroll
   for (int sg = 0; sg < KU_MAXSEG; ++sg) {
     my_idx[sg] = -1;
     my_a[sg] = -INFINITY;
-    my_e[sg] = -INFINITY;
-    if (sg < nseg) {
-      const size_t o = ((size_t)row * nseg + sg) * KU_CAND;
+    if (sg < nlists) {
+      const size_t o = ((size_t)row * nlists + sg) * KU_CAND;
       my_idx[sg] = cand_idx[o + lane];
       my_a[sg] = my_idx[sg] >= 0 ? cand_val[o + lane] : -INFINITY;
-      tau = fmaxf(tau, cand_val[o + KU_CAND - 1]);
+      // the smallest entry of a (full) list bounds everything its segment dropped; a list with room dropped nothing
+      float lmin = my_a[sg];
+#pragma unroll
+      for (int o2 = 16; o2 > 0; o2 >>= 1) lmin = fminf(lmin, __shfl_xor_sync(0xffffffffu, lmin, o2));
+      tau = fmaxf(tau, lmin);
     }
   }
-  // prune: the k-th largest APPROXIMATE value a_k bounds the exact top-k from below by a_k - eps, so candidates with
-  // approx < a_k - 2 eps cannot be in it and need no exact dot product (with nseg segments that is most of them)
+  // a_k = the k-th largest approximate value (duplicates counted)
   float a_k = -INFINITY;
   {
     float cut = INFINITY;   // values >= cut have been counted already
@@ -341,37 +383,70 @@ __global__ void __launch_bounds__(256) knn_rerank_kernel(const float* __restrict
     }
   }
   const float keep = a_k - 2.f * eps;
+  // compact the survivors into shared memory (warp-private)
+  int cnt = 0;
 #pragma unroll
   for (int sg = 0; sg < KU_MAXSEG; ++sg) {
-    if (sg < nseg) {
-      if (my_a[sg] < keep) my_idx[sg] = -1;   // cannot be in the exact top-k
-      unsigned live = __ballot_sync(0xffffffffu, my_idx[sg] >= 0);
-      while (live) {
-        const int c = __ffs(live) - 1;
-        live &= live - 1;
-        const int ci = __shfl_sync(0xffffffffu, my_idx[sg], c);
-        const float* dr = db + (size_t)ci * F;
-        float s = 0.f;
-        for (int f = lane; f < F; f += 32) s = fmaf(__ldg(qr + f), __ldg(dr + f), s);
-        s = warp_sum(s);
-        if (lane == c) my_e[sg] = s;
+    if (sg < nlists) {
+      const bool live = my_idx[sg] >= 0 && my_a[sg] >= keep;
+      const unsigned m = __ballot_sync(0xffffffffu, live);
+      const int pos = cnt + __popc(m & ((1u << lane) - 1u));
+      if (live && pos < KU_SURV) {
+        s_val[wid][pos] = my_a[sg];
+        s_idx[wid][pos] = my_idx[sg];
+      }
+      cnt += __popc(m);
+    }
+  }
+  __syncwarp();
+  if (cnt > KU_SURV || cnt < k || (err && *err != 0)) {   // massive ties / broken pipeline: the exact kernel does this row
+    if (lane == 0) fail_rows[atomicAdd(fail_count, 1)] = row;
+    return;
+  }
+  // lane owns survivors `lane` and `lane + 32`
+  float key[2];
+  int cid[2];
+  bool amb[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int e = lane + 32 * h;
+    key[h] = e < cnt ? s_val[wid][e] : -INFINITY;
+    cid[h] = e < cnt ? s_idx[wid][e] : 0x7fffffff;
+    amb[h] = sims != nullptr;
+  }
+  const float two_eps = 2.f * eps;
+  for (int j = 0; j < cnt; ++j) {
+    const float aj = s_val[wid][j];   // broadcast
+    amb[0] |= (j != lane) && fabsf(key[0] - aj) <= two_eps;
+    amb[1] |= (j != lane + 32) && fabsf(key[1] - aj) <= two_eps;
+  }
+  amb[0] &= lane < cnt;
+  amb[1] &= lane + 32 < cnt;
+  bool exact[2] = {false, false};
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    unsigned live = __ballot_sync(0xffffffffu, amb[h]);
+    while (live) {
+      const int c = __ffs(live) - 1;
+      live &= live - 1;
+      const float* dr = db + (size_t)s_idx[wid][c + 32 * h] * F;
+      float s = 0.f;
+      for (int f = lane; f < F; f += 32) s = fmaf(__ldg(qr + f), __ldg(dr + f), s);
+      s = warp_sum(s);
+      if (lane == c) {
+        key[h] = s;
+        exact[h] = true;
       }
     }
   }
-  float ek = -INFINITY;
+  float ek = -INFINITY;   // lower bound of the exact k-th value
   for (int out = 0; out < k; ++out) {
     // this lane's best remaining candidate
-    float bv = -INFINITY;
-    int bi = 0x7fffffff, bs = 0;
-#pragma unroll
-    for (int sg = 0; sg < KU_MAXSEG; ++sg) {
-      const bool better = my_idx[sg] >= 0 && (my_e[sg] > bv || (my_e[sg] == bv && my_idx[sg] < bi));
-      bv = better ? my_e[sg] : bv;
-      bi = better ? my_idx[sg] : bi;
-      bs = better ? sg : bs;
-    }
-    float wv = bv;
-    int wi = bi, wl = lane;
+    const bool second = cid[1] != 0x7fffffff && (cid[0] == 0x7fffffff || key[1] > key[0] || (key[1] == key[0] && cid[1] < cid[0]));
+    float wv = second ? key[1] : key[0];
+    int wi = second ? cid[1] : cid[0];
+    int wl = lane * 2 + (second ? 1 : 0);
+    if (wi == 0x7fffffff) wv = -INFINITY;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       const float ov = __shfl_xor_sync(0xffffffffu, wv, o);
@@ -383,19 +458,16 @@ __global__ void __launch_bounds__(256) knn_rerank_kernel(const float* __restrict
         wl = ol;
       }
     }
-    if (lane == wl) {
-#pragma unroll
-      for (int sg = 0; sg < KU_MAXSEG; ++sg)
-        if (sg == bs) my_idx[sg] = -1;  // consumed
-    }
-    if (lane == 0 && wi != 0x7fffffff) {
+    const bool was_exact = __shfl_sync(0xffffffffu, (wl & 1) ? exact[1] : exact[0], wl >> 1);
+    if (lane == (wl >> 1)) cid[wl & 1] = 0x7fffffff;   // consumed
+    if (lane == 0) {
       idx[(size_t)row * k + out] = (int64_t)wi;
       if (sims) sims[(size_t)row * k + out] = wv;
     }
-    if (out == k - 1) ek = (wi != 0x7fffffff) ? wv : -INFINITY;
+    if (out == k - 1) ek = was_exact ? wv : wv - eps;
   }
   // certificate: the exact k-th best candidate must beat anything the approximate pass could have dropped
-  const bool bad = !(ek > tau + eps) || (err && *err != 0);
+  const bool bad = !(ek > tau + eps);
   if (lane == 0 && bad) fail_rows[atomicAdd(fail_count, 1)] = row;  // recomputed by the exact kernel
 }
 
@@ -429,19 +501,17 @@ static int make_map(CUtensorMap* m, const void* base, uint64_t cols, uint64_t ro
 static size_t al256(size_t x) { return (x + 255) / 256 * 256; }
 
 // Database segments per query block.  More segments fill the SMs when there are few query blocks (a multi-GPU
-// shard) but every segment restarts its candidate lists cold, and a cold list inserts far more often: measured per
-// 128x128 tile 12.6 us at nseg = 1 and 22 us at nseg = 8 (N = 49 629, F = 768), i.e. ~ +11 % per extra segment.
-// Pick the nseg that minimises  waves x tiles-per-segment x (1 + 0.11 (nseg - 1)).
+// shard) and even out the last wave of a large build; with thread-per-row lists a segment's cold start costs
+// microseconds, so what is left is one more 32-entry list per row for the re-rank (~1 % per segment).
+// Pick the nseg that minimises  waves x tiles-per-segment x (1 + 0.01 (nseg - 1)).
 static int knn_nseg(int Nq, int N, int k) {
   const int nblocks = ceil_div(Nq, 128), ntiles = ceil_div(N, 128);
   double best_cost = 1e300;
-  // (every (row, segment) keeps KU_SUB lists of 32, so even one segment leaves >= 2 x 32 - k spare candidates)
   (void)k;
-  const int lo = 1;
-  int best = lo;
-  for (int nseg = lo; nseg * KU_SUB <= KU_MAXSEG && nseg <= max(lo, ntiles / 8); ++nseg) {
+  int best = 1;
+  for (int nseg = 1; nseg <= KU_MAXSEG && nseg <= max(1, ntiles / 8); ++nseg) {
     const double waves = (double)ceil_div(nblocks * nseg, 148);
-    const double cost = waves * (double)ceil_div(ntiles, nseg) * (1.0 + 0.11 * (nseg - 1));
+    const double cost = waves * (double)ceil_div(ntiles, nseg) * (1.0 + 0.01 * (nseg - 1));
     if (cost < best_cost * 0.999) {
       best_cost = cost;
       best = nseg;
@@ -460,53 +530,64 @@ size_t knn_umma_workspace_bytes(int Nq, int N, int F) {
 int launch_knn_exact(const float* q, const float* db, int Nq, int N, int F, int k, int64_t* idx, float* sims,
                      const int* row_list, const int* row_count, cudaStream_t st);
 
-int knn_topk_umma(const float* q, const float* db, int Nq, int N, int F, int k, int64_t* idx, float* sims, void* ws,
-                  cudaStream_t st) {
-  const int Fp = round_up(F, 64);
+// Workspace layout shared by the one-call build and the two-phase sharded build.
+struct KnnWs {
+  int *err, *fail_count, *dbmax2;
+  __nv_bfloat16 *dh, *dl, *qh, *ql;
+  int* cand_idx;
+  float* cand_val;
+  int* fail_rows;
+  float* qnorm2;
+};
+
+static KnnWs knn_ws_layout(void* ws, int Nq, int N, int Fp, bool q_in_db, int q_row0) {
+  KnnWs k;
   uint8_t* w = static_cast<uint8_t*>(ws);
-  int* err = reinterpret_cast<int*>(w);
-  size_t off = 256;
-  auto take = [&](size_t bytes) { uint8_t* p = w + off; off += al256(bytes); return p; };
-  __nv_bfloat16* dh = reinterpret_cast<__nv_bfloat16*>(take((size_t)N * Fp * 2));
-  __nv_bfloat16* dl = reinterpret_cast<__nv_bfloat16*>(take((size_t)N * Fp * 2));
-  const bool same = (q == db && Nq == N);
-  __nv_bfloat16* qh = same ? dh : reinterpret_cast<__nv_bfloat16*>(take((size_t)Nq * Fp * 2));
-  __nv_bfloat16* ql = same ? dl : reinterpret_cast<__nv_bfloat16*>(take((size_t)Nq * Fp * 2));
-  if (same) off += 2 * al256((size_t)Nq * Fp * 2);
-  const int nseg = knn_nseg(Nq, N, k);
-  int* cand_idx = reinterpret_cast<int*>(take((size_t)Nq * KU_MAXSEG * KU_CAND * 4));
-  float* cand_val = reinterpret_cast<float*>(take((size_t)Nq * KU_MAXSEG * KU_CAND * 4));
-  int* fail_rows = reinterpret_cast<int*>(take((size_t)Nq * 4));
-  float* qnorm2 = reinterpret_cast<float*>(take((size_t)Nq * 4));
+  k.err = reinterpret_cast<int*>(w);
   // zeroed header: [0] error flag, [1] number of uncertified rows (dg_knn_topk's caller may read it back after the
   // stream has drained), [2] bits of the largest squared database row norm
-  int* fail_count = err + 1;
-  int* dbmax2 = err + 2;
-  DG_CUDA_OK(cudaMemsetAsync(err, 0, 256, st));
+  k.fail_count = k.err + 1;
+  k.dbmax2 = k.err + 2;
+  size_t off = 256;
+  auto take = [&](size_t bytes) { uint8_t* p = w + off; off += al256(bytes); return p; };
+  k.dh = reinterpret_cast<__nv_bfloat16*>(take((size_t)N * Fp * 2));
+  k.dl = reinterpret_cast<__nv_bfloat16*>(take((size_t)N * Fp * 2));
+  __nv_bfloat16* qh = reinterpret_cast<__nv_bfloat16*>(take((size_t)Nq * Fp * 2));
+  __nv_bfloat16* ql = reinterpret_cast<__nv_bfloat16*>(take((size_t)Nq * Fp * 2));
+  k.qh = q_in_db ? k.dh + (size_t)q_row0 * Fp : qh;   // the query rows ARE database rows q_row0 .. q_row0 + Nq - 1
+  k.ql = q_in_db ? k.dl + (size_t)q_row0 * Fp : ql;
+  k.cand_idx = reinterpret_cast<int*>(take((size_t)Nq * KU_MAXSEG * KU_CAND * 4));
+  k.cand_val = reinterpret_cast<float*>(take((size_t)Nq * KU_MAXSEG * KU_CAND * 4));
+  k.fail_rows = reinterpret_cast<int*>(take((size_t)Nq * 4));
+  k.qnorm2 = reinterpret_cast<float*>(take((size_t)Nq * 4));
+  return k;
+}
 
-  DG_PRE(st);
-  split_rows_kernel<<<148 * 8, 256, 0, st>>>(db, N, F, Fp, dh, dl, same ? qnorm2 : nullptr, dbmax2);
-  DG_LAUNCH_OK("split_rows_kernel");
-  if (!same) {
-    DG_PRE(st);
-    split_rows_kernel<<<148 * 8, 256, 0, st>>>(q, Nq, F, Fp, qh, ql, qnorm2, nullptr);
-    DG_LAUNCH_OK("split_rows_kernel");
-  }
-  KnnUmmaParams prm;
-  int rc;
+static int knn_bn() {
   static int bn_env = -1;  // DEPTHG_B200_KNN_BN = 128 | 256 (experiments); default 256
   if (bn_env < 0) {
     const char* e = getenv("DEPTHG_B200_KNN_BN");
     bn_env = e && atoi(e) == 128 ? 128 : 256;
   }
-  const int BN = bn_env;
+  return bn_env;
+}
+
+// One launch of the tensor pass over the virtual tile list (see KnnUmmaParams).
+static int launch_knn_umma(const KnnWs& w, int Nq, int N, int Fp, int nseg, int list_pitch, int ntiles_virtual, int tA_end,
+                           int tB_shift, int col_lo, int col_hi, int col_mode, int warm, cudaStream_t st) {
+  KnnUmmaParams prm;
+  int rc;
+  const int BN = knn_bn();
   const int KC = BN == 128 ? KuCfg<128>::KC : KuCfg<256>::KC;
-  if ((rc = make_map(&prm.tm_qh, qh, Fp, Nq, 128, KC))) return rc;
-  if ((rc = make_map(&prm.tm_ql, ql, Fp, Nq, 128, KC))) return rc;
-  if ((rc = make_map(&prm.tm_dh, dh, Fp, N, BN, KC))) return rc;
-  if ((rc = make_map(&prm.tm_dl, dl, Fp, N, BN, KC))) return rc;
-  prm.Nq = Nq; prm.N = N; prm.nchunk = Fp / KC; prm.ntiles = ceil_div(N, BN); prm.nseg = nseg;
-  prm.cand_idx = cand_idx; prm.cand_val = cand_val; prm.err = err;
+  if ((rc = make_map(&prm.tm_qh, w.qh, Fp, Nq, 128, KC))) return rc;
+  if ((rc = make_map(&prm.tm_ql, w.ql, Fp, Nq, 128, KC))) return rc;
+  if ((rc = make_map(&prm.tm_dh, w.dh, Fp, N, BN, KC))) return rc;
+  if ((rc = make_map(&prm.tm_dl, w.dl, Fp, N, BN, KC))) return rc;
+  prm.Nq = Nq; prm.N = N; prm.nchunk = Fp / KC; prm.ntiles = ntiles_virtual; prm.nseg = nseg;
+  prm.list_pitch = list_pitch;
+  prm.tA_end = tA_end; prm.tB_shift = tB_shift; prm.col_lo = col_lo; prm.col_hi = col_hi; prm.col_mode = col_mode;
+  prm.warm = warm;
+  prm.cand_idx = w.cand_idx; prm.cand_val = w.cand_val; prm.err = w.err;
   static PerDevice attr_pd = {};
   size_t& attr_set = per_device(attr_pd);
   if (!attr_set) {
@@ -520,11 +601,88 @@ int knn_topk_umma(const float* q, const float* db, int Nq, int N, int F, int k, 
   else
     knn_umma_kernel<256><<<dim3(ceil_div(Nq, 128), nseg), KU_THREADS, KuCfg<256>::SMEM, st>>>(prm);
   DG_LAUNCH_OK("knn_umma_kernel");
+  return DG_OK;
+}
+
+static int launch_split(const float* x, int n, int F, int Fp, __nv_bfloat16* hi, __nv_bfloat16* lo, float* rownorm2,
+                        int* maxnorm2_bits, cudaStream_t st) {
+  if (n <= 0) return DG_OK;
   DG_PRE(st);
-  knn_rerank_kernel<<<ceil_div(Nq * 32, 256), 256, 0, st>>>(q, db, Nq, N, F, k, nseg * KU_SUB, cand_idx, cand_val, idx, sims, fail_rows,
-                                                             fail_count, err, qnorm2, dbmax2, ku_eps_unit(F));
+  split_rows_kernel<<<min(148 * 8, ceil_div(n, 8)), 256, 0, st>>>(x, n, F, Fp, hi, lo, rownorm2, maxnorm2_bits);
+  DG_LAUNCH_OK("split_rows_kernel");
+  return DG_OK;
+}
+
+static int launch_rerank(const KnnWs& w, const float* q, const float* db, int Nq, int N, int F, int k, int nseg,
+                         int64_t* idx, float* sims, cudaStream_t st) {
+  DG_PRE(st);
+  knn_rerank_kernel<<<ceil_div(Nq * 32, 256), 256, 0, st>>>(q, db, Nq, N, F, k, nseg /* merged lists */, w.cand_idx, w.cand_val, idx,
+                                                             sims, w.fail_rows, w.fail_count, w.err, w.qnorm2, w.dbmax2,
+                                                             ku_eps_unit(F));
   DG_LAUNCH_OK("knn_rerank_kernel");
-  return launch_knn_exact(q, db, Nq, N, F, k, idx, sims, fail_rows, fail_count, st);
+  return launch_knn_exact(q, db, Nq, N, F, k, idx, sims, w.fail_rows, w.fail_count, st);
+}
+
+int knn_topk_umma(const float* q, const float* db, int Nq, int N, int F, int k, int64_t* idx, float* sims, void* ws,
+                  cudaStream_t st) {
+  const int Fp = round_up(F, 64);
+  const bool same = (q == db && Nq == N);
+  const KnnWs w = knn_ws_layout(ws, Nq, N, Fp, same, 0);
+  const int nseg = knn_nseg(Nq, N, k);
+  DG_CUDA_OK(cudaMemsetAsync(w.err, 0, 256, st));
+  int rc;
+  if ((rc = launch_split(db, N, F, Fp, w.dh, w.dl, same ? w.qnorm2 : nullptr, w.dbmax2, st))) return rc;
+  if (!same && (rc = launch_split(q, Nq, F, Fp, w.qh, w.ql, w.qnorm2, nullptr, st))) return rc;
+  const int ntiles = ceil_div(N, knn_bn());
+  if ((rc = launch_knn_umma(w, Nq, N, Fp, nseg, nseg, ntiles, ntiles, 0, 0, 0, 0, 0, st))) return rc;
+  return launch_rerank(w, q, db, Nq, N, F, k, nseg, idx, sims, st);
+}
+
+// ---- query-row-sharded build in two phases (the all-gather of the database is the one exchange step).
+// The rank's query rows are rows [row_lo, row_lo + Nq) of the database.  Phase 1 needs only those local rows: it
+// splits them and runs the tensor pass of the local queries against the LOCAL database rows, which is what a rank can
+// do while the all-gather is in flight - and it leaves every candidate list warm.  Phase 2 gets the all-gathered
+// database, splits the remote rows and continues the same lists over everything but the local rows (no cold-list
+// penalty: the lists already hold 32 good candidates), then re-ranks exactly as the one-call build does.
+// Phase 1 runs beside the all-gather, whose kernels need SMs of their own: it uses the largest segment count that
+// leaves KU_COMM_SMS free (a CTA of the tensor pass owns a whole SM), and leaves the other lists of a row empty.
+constexpr int KU_COMM_SMS = 36;
+
+static int knn_nseg_local(int Nq, int nseg) {
+  const int nblocks = ceil_div(Nq, 128);
+  int n = (148 - KU_COMM_SMS) / max(nblocks, 1);
+  return max(1, min(n, nseg));
+}
+
+int knn_shard_begin(const float* local, int Nq, int row_lo, int N, int F, int k, void* ws, cudaStream_t st) {
+  const int Fp = round_up(F, 64), BN = knn_bn();
+  const KnnWs w = knn_ws_layout(ws, Nq, N, Fp, true, row_lo);
+  const int nseg = knn_nseg(Nq, N, k);
+  const int nseg_l = knn_nseg_local(Nq, nseg);
+  DG_CUDA_OK(cudaMemsetAsync(w.err, 0, 256, st));
+  if (nseg_l < nseg) DG_CUDA_OK(cudaMemsetAsync(w.cand_idx, 0xff, (size_t)Nq * nseg * KU_CAND * 4, st));   // empty lists
+  int rc;
+  if ((rc = launch_split(local, Nq, F, Fp, w.qh, w.ql, w.qnorm2, w.dbmax2, st))) return rc;
+  const int t0 = row_lo / BN, t1 = ceil_div(row_lo + Nq, BN);
+  return launch_knn_umma(w, Nq, N, Fp, nseg_l, nseg, t1 - t0, 0, t0, row_lo, row_lo + Nq, 1, 0, st);
+}
+
+int knn_shard_finish(const float* db, int Nq, int row_lo, int N, int F, int k, int64_t* idx, float* sims, void* ws,
+                     cudaStream_t st) {
+  const int Fp = round_up(F, 64), BN = knn_bn();
+  const KnnWs w = knn_ws_layout(ws, Nq, N, Fp, true, row_lo);
+  const int nseg = knn_nseg(Nq, N, k);
+  const int row_hi = row_lo + Nq;
+  int rc;
+  if ((rc = launch_split(db, row_lo, F, Fp, w.dh, w.dl, nullptr, w.dbmax2, st))) return rc;
+  if ((rc = launch_split(db + (size_t)row_hi * F, N - row_hi, F, Fp, w.dh + (size_t)row_hi * Fp, w.dl + (size_t)row_hi * Fp,
+                         nullptr, w.dbmax2, st))) return rc;
+  const int ntiles = ceil_div(N, BN);
+  const int tA_end = ceil_div(row_lo, BN);                 // tiles [0, tA_end) hold rows below the local range
+  const int tB_begin = max(row_hi / BN, tA_end);           // tiles [tB_begin, ntiles) hold rows above it
+  if ((rc = launch_knn_umma(w, Nq, N, Fp, nseg, nseg, tA_end + (ntiles - tB_begin), tA_end, tB_begin - tA_end, row_lo,
+                            row_hi, 2, 1, st))) return rc;
+  return launch_rerank(w, db + (size_t)row_lo * F, db, Nq, N, F, k, nseg, idx, sims, st);
 }
 
 }  // namespace dg

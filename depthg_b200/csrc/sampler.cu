@@ -13,9 +13,34 @@
 
 namespace dg {
 
+// `use_smem`: the shuffle runs in shared memory (n * B ints) - a Fisher-Yates walk is a chain of dependent loads and
+// stores, ~0.4 us a step in global memory and ~50 ns in shared memory; permutations that do not fit shuffle in place.
 __global__ void super_perms_kernel(unsigned long long seed, unsigned long long offset, int n, int B,
-                                   int64_t* __restrict__ out) {
+                                   int64_t* __restrict__ out, int use_smem) {
+  extern __shared__ int sp_buf[];
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (use_smem) {            // one block: thread k owns column k of sp_buf[i * n + k] (conflict-free)
+    if (k < n) {
+      curandStatePhilox4_32_10_t st;
+      curand_init(seed, (unsigned long long)k, offset, &st);
+      for (int i = 0; i < B; ++i) sp_buf[i * n + k] = i;
+      for (int i = B - 1; i > 0; --i) {
+        const unsigned int r = curand(&st);
+        const int j = (int)(((unsigned long long)r * (unsigned long long)(i + 1)) >> 32);
+        const int t = sp_buf[i * n + k];
+        sp_buf[i * n + k] = sp_buf[j * n + k];
+        sp_buf[j * n + k] = t;
+      }
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < n * B; e += blockDim.x) {     // coalesced write-out with the fixed-point bump
+      const int kk = e / B, i = e - kk * B;
+      int v = sp_buf[i * n + kk];
+      if (v == i) v += 1;    // perm[perm == arange] += 1
+      out[e] = (int64_t)(v % B);   // perm % size
+    }
+    return;
+  }
   if (k >= n) return;
   curandStatePhilox4_32_10_t st;
   curand_init(seed, (unsigned long long)k, offset, &st);
@@ -43,8 +68,13 @@ extern "C" int dg_super_perms(unsigned long long seed, unsigned long long offset
   DG_REQUIRE(out, DG_ERR_INVALID, "dg_super_perms: null pointer");
   DG_REQUIRE(n > 0 && B > 0, DG_ERR_INVALID, "dg_super_perms: bad sizes");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const size_t smem = (size_t)n * B * sizeof(int);
+  const bool use_smem = n <= 128 && smem <= 48 * 1024;
   DG_PRE(st);
-  super_perms_kernel<<<ceil_div(n, 32), 32, 0, st>>>(seed, offset, n, B, out);
+  if (use_smem)
+    super_perms_kernel<<<1, 128, smem, st>>>(seed, offset, n, B, out, 1);
+  else
+    super_perms_kernel<<<ceil_div(n, 32), 32, 0, st>>>(seed, offset, n, B, out, 0);
   DG_LAUNCH_OK("super_perms_kernel");
   return DG_OK;
 }

@@ -104,13 +104,12 @@ class CorrLossFn : public torch::autograd::Function<CorrLossFn> {
     ctx->saved_data["need_code_pos"] = code_pos.requires_grad();
 
     auto u = out8.unbind(0);
-    variable_list outs = {u[0], u[2], u[4], u[6], out8.detach(), arena,
-                          cd_out.defined() ? cd_out : Tensor(), loss_out.defined() ? loss_out : Tensor(),
-                          dd_out.defined() ? dd_out : Tensor(), fd_dbg.defined() ? fd_dbg : Tensor()};
-    variable_list nd = {outs[4], outs[5]};
-    for (int i = 6; i < 10; ++i)
-      if (outs[i].defined()) nd.push_back(outs[i]);
-    ctx->mark_non_differentiable(nd);
+    // outputs: 4 differentiable scalars, out8, the arena, then only the optional tensors that exist, in the order
+    // [cd_out, loss_out][dd_out][fd_dbg] (an autograd Function may not return undefined tensors)
+    variable_list outs = {u[0], u[2], u[4], u[6], out8.detach(), arena};
+    for (const Tensor& t : {cd_out, loss_out, dd_out, fd_dbg})
+      if (t.defined()) outs.push_back(t);
+    ctx->mark_non_differentiable(variable_list(outs.begin() + 4, outs.end()));
     return outs;
   }
 

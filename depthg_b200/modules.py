@@ -11,6 +11,7 @@ the CPU and there is no PyTorch fallback for the kernels.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import struct
 
 import torch
@@ -111,13 +112,16 @@ class _GraphedSuperPerms:
         return out.clone()   # the graph's output buffer is overwritten by the next replay
 
     @classmethod
-    def draw_async(cls, n: int, size: int, device):
+    def draw_async(cls, n: int, size: int, device, also_wait=None):
         """Replay on a side stream so the ~25 tiny sampler kernels overlap FPS on the main stream.
-        Returns (perms, event); the consumer stream must wait for the event before reading perms."""
+        Returns (perms, event); the consumer stream must wait for the event before reading perms.
+        ``also_wait``: a CUDA event the returned event additionally stands for (the side stream waits for it before
+        recording), i.e. foreign work - a gradient all-reduce - that may run underneath FPS but must be over before
+        the SM-filling gathers start (the library waits for the event right after launching FPS)."""
         device = torch.device(device)
         main = torch.cuda.current_stream(device)
         if cls._cache.get((n, size, device.index)) in (None, False) or torch.cuda.is_current_stream_capturing():
-            return cls.draw(n, size, device), None
+            return cls.draw(n, size, device), None      # (the caller then hands also_wait to the library itself)
         side = cls._side.get(device.index)
         if side is None:
             side = cls._side[device.index] = torch.cuda.Stream(device=device)
@@ -126,6 +130,8 @@ class _GraphedSuperPerms:
             ev = cls._events[device.index] = torch.cuda.Event()
         with torch.cuda.stream(side):
             perms = cls.draw(n, size, device)
+            if also_wait is not None:
+                side.wait_event(also_wait)
             ev.record(side)
         perms.record_stream(main)   # allocated on the side stream, consumed on the main one
         return perms, ev
@@ -331,6 +337,28 @@ def depth_correlation(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
 
 
 # --------------------------------------------------------------------------- the loss
+_compiled_mod = None
+_plan_cache = {}
+
+
+def compiled_binding():
+    """The compiled autograd binding of dg_loss_forward / dg_loss_backward (csrc/torch_binding.cpp -> _C.so), or False.
+    It does what ``_CorrLossFn`` below does through ctypes (struct fill, arena / output allocation, the autograd node)
+    in C++, because at ~0.2 ms of GPU work per step the Python version of that plumbing paced the step.  Same C-ABI
+    calls, same kernels; ``DEPTHG_B200_BINDING=ctypes`` (or a missing _C.so) selects the ctypes path."""
+    global _compiled_mod
+    if _compiled_mod is None:
+        _compiled_mod = False
+        if os.environ.get("DEPTHG_B200_BINDING", "") != "ctypes":
+            try:
+                _lib.lib()                       # _C.so links against libdepthg_b200.so: load it first, loudly
+                from . import _C as mod          # noqa: N812
+                _compiled_mod = mod
+            except ImportError:
+                pass
+    return _compiled_mod
+
+
 class _CorrLossFn(torch.autograd.Function):
     """forward: FPS / gathers / depth signs / fused correlation loss (values + unit gradients) in ONE
     C-ABI call over one arena allocation; backward: one call that weights the unit gradients by
@@ -456,14 +484,17 @@ class ContrastiveCorrelationLoss(nn.Module):
     (e.g. on histogram steps) to get the reference's full tensors.
     """
 
-    def __init__(self, cfg, materialize_cd: bool = False, negative_sampler: str = "torch"):
+    def __init__(self, cfg, materialize_cd: bool = False, negative_sampler: str = "fused"):
         super().__init__()
         self.cfg = cfg
         self.materialize_cd = materialize_cd
         if negative_sampler not in ("torch", "fused"):
             raise ValueError("negative_sampler must be 'torch' (the reference's randperm stream) or 'fused'")
-        # "torch": neg_samples x torch.randperm, the reference's exact RNG stream (src/modules.py:1341);
-        # "fused": one dg_super_perms launch — same distribution, own Philox stream, ~150 us less host time
+        # "fused" (default): one dg_super_perms launch - the same distribution (uniform permutations with the
+        #          reference's fixed-point bump), drawn from a Philox stream keyed by torch's CUDA generator, so
+        #          torch.manual_seed still makes runs reproducible; ~60 us less host time per step than
+        # "torch": neg_samples x torch.randperm in the reference's order (src/modules.py:1341) - bit-identical
+        #          permutations to the reference running on the same GPU / torch build under the same seed
         self.negative_sampler = negative_sampler
         # replay the torch.randperm sequence as one CUDA graph (same RNG stream, ~15x less host time)
         self.graph_negative_sampler = True
@@ -471,6 +502,10 @@ class ContrastiveCorrelationLoss(nn.Module):
         self.perm_fn = super_perm
         self.rand_fn = lambda shape, device: torch.rand(shape, device=device)
         self.randint_fn = None      # use_salience draws; None = the reference's torch.randint calls
+        # Optional torch.cuda.Event of foreign work the next forward may overlap with its FPS kernel but must not
+        # overlap with its gathers (a DDP-style gradient all-reduce of the previous step on another stream): the
+        # forward waits for it after launching FPS.  Consumed (reset to None) by the call.
+        self.wait_after_fps = None
         self._last_coords = None
 
     @property
@@ -559,16 +594,24 @@ class ContrastiveCorrelationLoss(nn.Module):
             c1 = self.rand_fn(shape, dev) * 2 - 1
             c2 = self.rand_fn(shape, dev) * 2 - 1
             coords = torch.stack([c1, c2]).float().contiguous()
+        also_wait, self.wait_after_fps = self.wait_after_fps, None
         if not nneg:
             perms = None
         elif self.perm_fn is not super_perm:
             perms = torch.stack([self.perm_fn(B, dev) for _ in range(nneg)]).to(torch.long).contiguous()
-        elif self.negative_sampler == "fused":
+        elif self.negative_sampler == "fused" and not torch.cuda.is_current_stream_capturing():
             perms = fused_super_perms(nneg, B, dev)
+        elif self.negative_sampler == "fused":
+            # under CUDA-graph capture the generator's offset cannot be read on the host: torch.randperm is graph-safe
+            perms = super_perms(nneg, B, dev)
         elif self.graph_negative_sampler:
-            perms, perms_event = _GraphedSuperPerms.draw_async(nneg, B, dev)
+            perms, perms_event = _GraphedSuperPerms.draw_async(nneg, B, dev, also_wait)
         else:
             perms = super_perms(nneg, B, dev)
+        if also_wait is not None and perms_event is None:
+            # no sampler stream to fold it into: the library waits for this event itself, right after launching FPS
+            # (dg_loss_io_t.perms_ready is exactly that wait)
+            perms_event = also_wait
 
         depth_term = depth_term and aug_feats is None
         Hd = Wd = 0
@@ -603,12 +646,27 @@ class ContrastiveCorrelationLoss(nn.Module):
                         ("depth", depth), ("depth_pos", depth_pos), ("depth_aug_feats", aug_feats)):
             if t is not None and t.device != dev:
                 raise ValueError(f"{name} is on {t.device}, orig_feats on {dev}")
-        with torch.cuda.device(dev):    # kernels, attribute set-up and the stream all belong to the tensors' device
-            res = _CorrLossFn.apply(orig_feats, orig_feats_pos, orig_code, orig_code_pos, depth, depth_pos, coords,
-                                    perms, desc, bool(self.materialize_cd), perms_event, aug_feats)
-        intra, inter, neg, dloss, out8, coords_src, cd_out, loss_out, dd_out = res
+        binding = None if _CorrLossFn.debug else compiled_binding()
+        if binding:
+            ints = (B, Cdim, orig_code.shape[1], H, W, Hd, Wd, S, nneg, flags)
+            shifts = (desc.pos_intra_shift, desc.pos_inter_shift, desc.neg_inter_shift, desc.depth_feat_shift)
+            coords_off = _plan_cache.get(ints)
+            if coords_off is None:
+                coords_off = _plan_cache[ints] = binding.loss_plan(list(ints))[1]
+            res = binding.corr_loss(orig_feats, orig_feats_pos, orig_code, orig_code_pos, depth, depth_pos, coords,
+                                    perms, aug_feats, ints, shifts, bool(self.materialize_cd), False,
+                                    perms_event.cuda_event if perms_event is not None else 0)
+            intra, inter, neg, dloss, out8, coords_src = res[:6]
+            cd_out, loss_out = (res[6], res[7]) if self.materialize_cd else (None, None)
+            dd_out = res[8] if (self.materialize_cd and depth_term) else None
+        else:
+            with torch.cuda.device(dev):    # kernels, attribute set-up and the stream all belong to the tensors' device
+                res = _CorrLossFn.apply(orig_feats, orig_feats_pos, orig_code, orig_code_pos, depth, depth_pos, coords,
+                                        perms, desc, bool(self.materialize_cd), perms_event, aug_feats)
+            intra, inter, neg, dloss, out8, coords_src, cd_out, loss_out, dd_out = res
+            coords_off = _CorrLossFn.last_coords_off
         # FPS coordinates stay in the arena until someone asks for them (see the last_coords property)
-        self._last_coords = (coords_src, _CorrLossFn.last_coords_off, B, S) if (flags & _lib.FLAG_FPS) else coords
+        self._last_coords = (coords_src, coords_off, B, S) if (flags & _lib.FLAG_FPS) else coords
         if self.materialize_cd:
             five = (B, S, S, S, S)
             intra_cd, inter_cd = cd_out[0].view(five), cd_out[1].view(five)

@@ -56,6 +56,55 @@ def knn_topk(queries: torch.Tensor, db: torch.Tensor, k: int = TOPK, return_sims
     return out if len(out) > 1 else out[0]
 
 
+class KnnShard:
+    """Two-phase build of one query-row shard (``dg_knn_shard_begin`` / ``dg_knn_shard_finish``): the shard's rows are
+    database rows [row_lo, row_lo + Nq).  ``begin`` needs only the local rows and is what a rank runs while the
+    all-gather of the database is in flight; ``finish`` takes the gathered database.  Same result as
+    ``knn_topk(local, db, k)``."""
+
+    def __init__(self, local: torch.Tensor, row_lo: int, total_rows: int, k: int = TOPK):
+        require_cuda_f32(local, "local")
+        if local.dim() != 2:
+            raise ValueError(f"local must be [Nq,F], got {tuple(local.shape)}")
+        if not 1 <= k <= 32 or k > total_rows:
+            raise ValueError(f"k={k} must be in [1,32] and at most the database size {total_rows}")
+        if row_lo < 0 or row_lo + local.shape[0] > total_rows:
+            raise ValueError(f"rows [{row_lo},{row_lo + local.shape[0]}) outside the {total_rows}-row database")
+        self.local, self.row_lo, self.N, self.k = local.contiguous(), int(row_lo), int(total_rows), int(k)
+        self.Nq, self.F = self.local.shape
+        self.ws = None
+        if self.Nq:
+            self.ws_bytes = _lib.lib().dg_knn_workspace_bytes(self.Nq, self.N, self.F, self.k)
+            self.ws = torch.empty(self.ws_bytes, device=local.device, dtype=torch.uint8)
+
+    def begin(self):
+        if self.Nq:
+            dev = self.local.device
+            with torch.cuda.device(dev):
+                check(_lib.lib().dg_knn_shard_begin(ptr(self.local), self.Nq, self.row_lo, self.N, self.F, self.k,
+                                                    ptr(self.ws), self.ws_bytes, stream_ptr(dev.index)),
+                      "dg_knn_shard_begin")
+        return self
+
+    def finish(self, db: torch.Tensor, return_stats: bool = False):
+        require_cuda_f32(db, "db")
+        if db.dim() != 2 or db.shape[0] != self.N or db.shape[1] != self.F or not db.is_contiguous():
+            raise ValueError(f"db must be a contiguous [{self.N},{self.F}] tensor, got {tuple(db.shape)}")
+        dev = self.local.device
+        if db.device != dev:
+            raise ValueError(f"db on {db.device}, local rows on {dev}")
+        idx = torch.empty((self.Nq, self.k), device=dev, dtype=torch.int64)
+        if self.Nq:
+            with torch.cuda.device(dev):
+                check(_lib.lib().dg_knn_shard_finish(ptr(db), self.Nq, self.row_lo, self.N, self.F, self.k, ptr(idx),
+                                                     None, ptr(self.ws), self.ws_bytes, stream_ptr(dev.index)),
+                      "dg_knn_shard_finish")
+        if return_stats:
+            head = self.ws[:12].view(torch.int32).cpu() if self.Nq else [0, 0]
+            return idx, {"pipeline_error": int(head[0]), "fallback_rows": int(head[1])}
+        return idx
+
+
 def build_knn_index(normed_feats: torch.Tensor, k: int = TOPK, n_batches: int = N_BATCHES) -> torch.Tensor:
     """The whole loop of src/precompute_knns.py:99-113 as one call: int64 [N,k].
     ``n_batches`` is accepted for signature parity; chunking does not change the

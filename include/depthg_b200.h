@@ -281,6 +281,21 @@ DG_API size_t dg_knn_workspace_bytes(int Nq, int N, int F, int k);
 DG_API int dg_knn_topk(const float* q, const float* db, int Nq, int N, int F, int k, int64_t* idx, float* sims, void* ws,
                 size_t ws_bytes, dg_stream_t stream);
 
+/* The same build for a query-row SHARD of a multi-GPU job (query rows shard, the database is
+ * all-gathered), in two phases so that the all-gather overlaps useful work.  The shard's query rows are database rows
+ * [row_lo, row_lo + Nq).
+ *   dg_knn_shard_begin : needs only the local rows `local` [Nq,F]; ranks them against themselves (the part of the
+ *                        database this rank already holds) - enqueue it, then wait for the all-gather.
+ *   dg_knn_shard_finish: `db` is the complete [N,F] database (rows [row_lo, row_lo+Nq) equal to `local`); continues the
+ *                        candidate lists of phase 1 over the remote rows and finishes exactly like dg_knn_topk.
+ * Same workspace (dg_knn_workspace_bytes(Nq,N,F,k)), untouched between the two calls; same stream; same diagnostics
+ * header.  Result identical to dg_knn_topk(db + row_lo*F, db, Nq, N, ...).  Replaces the per-shard form of
+ * src/precompute_knns.py:99-113. */
+DG_API int dg_knn_shard_begin(const float* local, int Nq, int row_lo, int N, int F, int k, void* ws, size_t ws_bytes,
+                       dg_stream_t stream);
+DG_API int dg_knn_shard_finish(const float* db, int Nq, int row_lo, int N, int F, int k, int64_t* idx, float* sims, void* ws,
+                        size_t ws_bytes, dg_stream_t stream);
+
 /* Mean-pool + L2-normalise of get_feats (src/precompute_knns.py:19):
  * t [N,C,H,W] with element strides (host) -> out [N,C], eps = 1e-12. */
 DG_API int dg_pool_normalize(const float* t, const int64_t* strides, int N, int C, int H, int W, float eps, float* out,

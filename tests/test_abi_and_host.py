@@ -145,7 +145,7 @@ _WORKER = r"""
 import os, sys
 sys.path.insert(0, {root!r})
 import numpy as np, torch, torch.distributed as dist
-from depthg_b200.distributed import shard_bounds, shard_batch, allreduce_mean_, sharded_knn, allgather_rows
+from depthg_b200.distributed import shard_bounds, shard_batch, allreduce_mean_, sharded_knn, allgather_rows, knn_shard_bounds
 from oracle import depthg_oracle as O
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -155,6 +155,13 @@ lo, hi = shard_bounds(301, world, rank)
 cpu_topk = lambda q, db, k: O.knn_rows(q, db, k)[1]
 full = sharded_knn(feats[lo:hi], 301, 5, cpu_topk, gather_result=True)
 assert torch.equal(full, O.knn_rows(feats, feats, 5)[1]), "sharded KNN != single-process KNN"
+# the KNN build's ceil partition: the equal-size all-gather of (end-padded) shards IS the database
+klo, khi = knn_shard_bounds(301, world, rank)
+per = -(-301 // world)
+src = torch.zeros((per, 32)); src[:khi - klo] = feats[klo:khi]
+gathered = torch.empty((world * per, 32))
+dist.all_gather_into_tensor(gathered, src)
+assert torch.equal(gathered[:301], feats), "ceil-partition all-gather is not the database"
 even = allgather_rows(feats[rank * 100:(rank + 1) * 100], 200)
 assert torch.equal(even, feats[:200])
 g = [torch.full((3, 2), float(rank + 1)), None, torch.arange(4.0) * (rank + 1)]
@@ -166,6 +173,16 @@ assert part.shape[0] == (3 if rank == 0 else 2)
 dist.barrier(); dist.destroy_process_group()
 print("rank", rank, "ok")
 """
+
+
+def test_knn_shard_bounds_cover_rows_with_short_last_shards():
+    from depthg_b200.distributed import knn_shard_bounds
+    for n, world in ((49629, 8), (301, 2), (5, 8), (64, 8), (1, 3)):
+        per = -(-n // world)
+        spans = [knn_shard_bounds(n, world, r) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        assert all(lo == min(r * per, n) and hi - lo <= per for r, (lo, hi) in enumerate(spans))
 
 
 def test_distributed_sharding_world2_gloo(tmp_path):

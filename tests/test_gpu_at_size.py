@@ -84,6 +84,32 @@ def test_knn_bench_size_full_build_and_shard(kind):
         assert float((fv - pv).abs()[diff].max()) < 1e-6
 
 
+@pytest.mark.parametrize("N,world,rank", [(KNN_N, 8, 0), (KNN_N, 8, 3), (KNN_N, 8, 7), (KNN_N, 2, 1), (5003, 4, 2),
+                                          (5003, 4, 3), (3001, 8, 7)])
+def test_knn_two_phase_shard_equals_one_call_build(N, world, rank):
+    """dg_knn_shard_begin (local rows only: what runs under the all-gather) + dg_knn_shard_finish (remote rows, warm
+    lists) against the oracle and against the one-call build of the same rows.  Ranks 0 / last have an empty remote
+    range on one side; 5003 / 3001 rows give unaligned tile boundaries and a short last shard."""
+    from depthg_b200.distributed import knn_shard_bounds
+    from depthg_b200.precompute_knns import KnnShard, knn_topk
+    x = knn_feats("clustered" if rank % 2 else "iid", N=N)
+    xd = x.to(dev())
+    lo, hi = knn_shard_bounds(N, world, rank)
+    assert 0 <= lo < hi <= N
+    local = xd[lo:hi].contiguous()
+    shard = KnnShard(local, lo, N, KNN_K).begin()
+    idx, stats = shard.finish(xd, return_stats=True)
+    assert stats["pipeline_error"] == 0 and stats["fallback_rows"] <= max(4, (hi - lo) // 200), stats
+    rs = np.random.RandomState(5)
+    rows = np.unique(np.concatenate([rs.randint(lo, hi, 768), np.arange(hi - 16, hi), np.arange(lo, lo + 16)]))
+    check_rows_against_oracle(idx[torch.from_numpy(rows - lo).to(dev())], rows, x, KNN_K)
+    one = knn_topk(local, xd, KNN_K)
+    diff = idx != one
+    if bool(diff.any()):
+        sims = local @ xd.T
+        assert float((torch.gather(sims, 1, idx) - torch.gather(sims, 1, one)).abs()[diff].max()) < 1e-6
+
+
 def test_knn_unnormalised_rows_stay_exact():
     """Rows that are NOT unit-norm: the certificate's error bound scales with |q| max|d|, so the
     result must still equal the fp32 oracle's under the tie rule scaled by the same factor."""

@@ -260,7 +260,7 @@ def test_loss_rng_stream_follows_reference_call_order():
     f, fp = torch.randn(B, 32, 28, 28, generator=g).to(dev()), torch.randn(B, 32, 28, 28, generator=g).to(dev())
     c, cp = torch.randn(B, 16, 28, 28, generator=g).to(dev()), torch.randn(B, 16, 28, 28, generator=g).to(dev())
     d = torch.randint(0, 256, (B, 1, 224, 224), generator=g).float().to(dev())
-    fn = ContrastiveCorrelationLoss(cfg)
+    fn = ContrastiveCorrelationLoss(cfg, negative_sampler="torch")   # the reference's own randperm stream
     torch.manual_seed(123)
     out = fn(f, fp, None, None, c, cp, d, d)
     torch.manual_seed(123)

@@ -54,8 +54,12 @@ SIGNATURES = {
     "dg_loss_backward": (C.c_int, [_vp, _vp, _vp, _vp]),
     "dg_knn_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "dg_knn_topk": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, C.c_size_t, _vp]),
-    "dg_knn_shard_begin": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_size_t, _vp]),
-    "dg_knn_shard_finish": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, C.c_size_t, _vp]),
+    "dg_knn_shard_begin": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_size_t, C.c_int, _vp]),
+    "dg_knn_shard_finish": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, C.c_size_t,
+                                      C.c_int, C.c_int, _vp]),
+    "dg_knn_panel_layout": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t),
+                                      C.POINTER(C.c_size_t)]),
+    "dg_memcpy_batch": (C.c_int, [C.c_int, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(C.c_size_t), C.POINTER(_vp)]),
     "dg_pool_normalize": (C.c_int, [_vp, _c_i64p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _vp, _vp]),
     "dg_probe_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "dg_linear_probe_ce": (C.c_int, [_vp, _c_i64p, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, C.c_int, _vp, _c_i64p,
@@ -65,6 +69,8 @@ SIGNATURES = {
 }
 
 PANEL_F32, PANEL_FEATS_SPLIT, PANEL_CODE_SPLIT = 0, 1, 2
+KNN_SPLIT_LOCAL, KNN_PASS_LOCAL, KNN_BEGIN_ALL, KNN_ALL_SMS = 1, 2, 3, 8
+KNN_SPLIT_REMOTE, KNN_PASS_REMOTE, KNN_RERANK, KNN_FINISH_ALL = 1, 2, 4, 7
 
 
 class Panels(C.Structure):

@@ -93,3 +93,18 @@ extern "C" int dg_debug_set_clock_buffer(long long* dev_ptr) {
   dg::set_clock_buffer(dev_ptr);
   return DG_OK;
 }
+
+// A batch of device-to-device copies, copy i on streams[i]: what the sharded KNN build uses to pull its peers' panel
+// rows out of their symmetric memory over NVLink.  cudaMemcpyAsync between device pointers runs on the copy engines -
+// no SMs - and one call enqueues the lot (the per-copy host cost of a framework copy_ was what paced the exchange).
+extern "C" int dg_memcpy_batch(int n, void* const* dst, const void* const* src, const size_t* bytes,
+                               const dg_stream_t* streams) {
+  using namespace dg;
+  DG_REQUIRE(n >= 0 && (n == 0 || (dst && src && bytes && streams)), DG_ERR_INVALID, "dg_memcpy_batch: bad arguments");
+  for (int i = 0; i < n; ++i) {
+    if (bytes[i] == 0) continue;
+    DG_REQUIRE(dst[i] && src[i], DG_ERR_INVALID, "dg_memcpy_batch: null pointer in copy %d", i);
+    DG_CUDA_OK(cudaMemcpyAsync(dst[i], src[i], bytes[i], cudaMemcpyDeviceToDevice, reinterpret_cast<cudaStream_t>(streams[i])));
+  }
+  return DG_OK;
+}

@@ -296,9 +296,10 @@ size_t knn_umma_workspace_bytes(int Nq, int N, int F);
 int knn_topk_umma(const float* q, const float* db, int Nq, int N, int F, int k, int64_t* idx, float* sims, void* ws,
                   cudaStream_t st);
 
-int knn_shard_begin(const float* local, int Nq, int row_lo, int N, int F, int k, void* ws, cudaStream_t st);
+int knn_shard_begin(const float* local, int Nq, int row_lo, int N, int F, int k, void* ws, int phases, cudaStream_t st);
 int knn_shard_finish(const float* db, int Nq, int row_lo, int N, int F, int k, int64_t* idx, float* sims, void* ws,
-                     cudaStream_t st);
+                     int phases, int npeer_max, cudaStream_t st);
+void knn_panel_layout(int N, int F, size_t* hi_off, size_t* lo_off, size_t* row_bytes);
 
 int launch_knn_exact(const float* q, const float* db, int Nq, int N, int F, int k, int64_t* idx, float* sims,
                      const int* row_list, const int* row_count, cudaStream_t st) {
@@ -355,10 +356,10 @@ extern "C" int dg_knn_topk(const float* q, const float* db, int Nq, int N, int F
 }
 
 // Two-phase form of dg_knn_topk for a query-row shard whose rows are database rows [row_lo, row_lo + Nq): see
-// knn_umma.cu.  `tensor_path` reports whether the shape takes the tensor-core path (otherwise begin does nothing and
-// finish is the plain exact build).
+// knn_umma.cu.  Shapes that do not take the tensor-core path do nothing in `begin` and run the plain exact build in
+// `finish` (once, when DG_KNN_RERANK is among the phases).
 extern "C" int dg_knn_shard_begin(const float* local, int Nq, int row_lo, int N, int F, int k, void* ws, size_t ws_bytes,
-                                  dg_stream_t stream) {
+                                  int phases, dg_stream_t stream) {
   using namespace dg;
   DG_REQUIRE(local && Nq > 0 && N > 0 && F > 0 && row_lo >= 0 && row_lo + Nq <= N, DG_ERR_INVALID,
              "dg_knn_shard_begin: bad arguments");
@@ -366,20 +367,31 @@ extern "C" int dg_knn_shard_begin(const float* local, int Nq, int row_lo, int N,
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (!use_umma(Nq, N, k)) return DG_OK;
   DG_REQUIRE(ws && ws_bytes >= knn_umma_workspace_bytes(Nq, N, F), DG_ERR_WORKSPACE, "dg_knn_shard_begin: workspace too small");
-  return knn_shard_begin(local, Nq, row_lo, N, F, k, ws, st);
+  return knn_shard_begin(local, Nq, row_lo, N, F, k, ws, phases, st);
 }
 
 extern "C" int dg_knn_shard_finish(const float* db, int Nq, int row_lo, int N, int F, int k, int64_t* idx, float* sims,
-                                   void* ws, size_t ws_bytes, dg_stream_t stream) {
+                                   void* ws, size_t ws_bytes, int phases, int npeer_max, dg_stream_t stream) {
   using namespace dg;
-  DG_REQUIRE(db && idx && Nq > 0 && N > 0 && F > 0 && row_lo >= 0 && row_lo + Nq <= N, DG_ERR_INVALID,
+  DG_REQUIRE(Nq > 0 && N > 0 && F > 0 && row_lo >= 0 && row_lo + Nq <= N, DG_ERR_INVALID,
              "dg_knn_shard_finish: bad arguments");
   DG_REQUIRE(k > 0 && k <= 32 && k <= N, DG_ERR_INVALID, "dg_knn_shard_finish: k=%d out of range", k);
+  DG_REQUIRE(npeer_max >= 0 && npeer_max <= 32, DG_ERR_INVALID, "dg_knn_shard_finish: npeer_max out of range");
+  DG_REQUIRE(!(phases & (DG_KNN_SPLIT_REMOTE | DG_KNN_RERANK)) || db, DG_ERR_INVALID, "dg_knn_shard_finish: db missing");
+  DG_REQUIRE(!(phases & DG_KNN_RERANK) || idx, DG_ERR_INVALID, "dg_knn_shard_finish: idx missing");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (use_umma(Nq, N, k)) {
     DG_REQUIRE(ws && ws_bytes >= knn_umma_workspace_bytes(Nq, N, F), DG_ERR_WORKSPACE, "dg_knn_shard_finish: workspace too small");
-    return knn_shard_finish(db, Nq, row_lo, N, F, k, idx, sims, ws, st);
+    return knn_shard_finish(db, Nq, row_lo, N, F, k, idx, sims, ws, phases, npeer_max, st);
   }
+  if (!(phases & DG_KNN_RERANK)) return DG_OK;
   if (ws && ws_bytes >= 256) DG_CUDA_OK(cudaMemsetAsync(ws, 0, 256, st));
   return launch_knn_exact(db + (size_t)row_lo * F, db, Nq, N, F, k, idx, sims, nullptr, nullptr, st);
+}
+
+extern "C" int dg_knn_panel_layout(int N, int F, size_t* hi_offset, size_t* lo_offset, size_t* row_bytes) {
+  using namespace dg;
+  DG_REQUIRE(N > 0 && F > 0 && hi_offset && lo_offset && row_bytes, DG_ERR_INVALID, "dg_knn_panel_layout: bad arguments");
+  knn_panel_layout(N, F, hi_offset, lo_offset, row_bytes);
+  return DG_OK;
 }

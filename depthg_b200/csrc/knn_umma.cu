@@ -331,14 +331,19 @@ __global__ void __launch_bounds__(256) knn_rerank_kernel(const float* __restrict
                                                          float* __restrict__ sims, int* __restrict__ fail_rows,
                                                          int* __restrict__ fail_count, const int* __restrict__ err,
                                                          const float* __restrict__ qnorm2,
-                                                         const int* __restrict__ dbmax2_bits, float eps_unit) {
+                                                         const int* __restrict__ dbmax2_bits, int npeer_max,
+                                                         float eps_unit) {
   __shared__ float s_val[8][KU_SURV];
   __shared__ int s_idx[8][KU_SURV];
   const int wid = threadIdx.x >> 5;
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (row >= Nq) return;
   // error bound of the approximate similarities of this row: eps_unit * |q| * max |d|
-  const float eps = eps_unit * sqrtf(__ldg(qnorm2 + row)) * sqrtf(__int_as_float(__ldg(dbmax2_bits)));
+  // (dbmax2_bits[0] = the largest squared norm this GPU measured; a sharded build that received its panels ready-made
+  //  finds the other ranks' maxima in dbmax2_bits[30 .. 30 + npeer_max): header ints 32.. of the workspace)
+  int mbits = __ldg(dbmax2_bits);
+  for (int p = 0; p < npeer_max; ++p) mbits = max(mbits, __ldg(dbmax2_bits + 30 + p));
+  const float eps = eps_unit * sqrtf(__ldg(qnorm2 + row)) * sqrtf(__int_as_float(mbits));
   const float* qr = q + (size_t)row * F;
   int my_idx[KU_MAXSEG];
   float my_a[KU_MAXSEG];
@@ -614,11 +619,11 @@ static int launch_split(const float* x, int n, int F, int Fp, __nv_bfloat16* hi,
 }
 
 static int launch_rerank(const KnnWs& w, const float* q, const float* db, int Nq, int N, int F, int k, int nseg,
-                         int64_t* idx, float* sims, cudaStream_t st) {
+                         int64_t* idx, float* sims, cudaStream_t st, int npeer_max = 0) {
   DG_PRE(st);
   knn_rerank_kernel<<<ceil_div(Nq * 32, 256), 256, 0, st>>>(q, db, Nq, N, F, k, nseg /* merged lists */, w.cand_idx, w.cand_val, idx,
                                                              sims, w.fail_rows, w.fail_count, w.err, w.qnorm2, w.dbmax2,
-                                                             ku_eps_unit(F));
+                                                             npeer_max, ku_eps_unit(F));
   DG_LAUNCH_OK("knn_rerank_kernel");
   return launch_knn_exact(q, db, Nq, N, F, k, idx, sims, w.fail_rows, w.fail_count, st);
 }
@@ -654,35 +659,62 @@ static int knn_nseg_local(int Nq, int nseg) {
   return max(1, min(n, nseg));
 }
 
-int knn_shard_begin(const float* local, int Nq, int row_lo, int N, int F, int k, void* ws, cudaStream_t st) {
+// `phases` selects which steps a call enqueues, so that a host that moves the panels itself (peer copies over NVLink
+// instead of a collective) can put its own work between them:
+//   begin : DG_KNN_SPLIT_LOCAL (reset the header, split the local rows into panel rows [row_lo, row_lo + Nq)),
+//           DG_KNN_PASS_LOCAL  (tensor pass against the local rows)
+//   finish: DG_KNN_SPLIT_REMOTE (split every other row of `db`; skipped when the panels were copied from the peers),
+//           DG_KNN_PASS_REMOTE, DG_KNN_RERANK (needs `db`, the fp32 rows)
+int knn_shard_begin(const float* local, int Nq, int row_lo, int N, int F, int k, void* ws, int phases, cudaStream_t st) {
   const int Fp = round_up(F, 64), BN = knn_bn();
   const KnnWs w = knn_ws_layout(ws, Nq, N, Fp, true, row_lo);
   const int nseg = knn_nseg(Nq, N, k);
-  const int nseg_l = knn_nseg_local(Nq, nseg);
-  DG_CUDA_OK(cudaMemsetAsync(w.err, 0, 256, st));
-  if (nseg_l < nseg) DG_CUDA_OK(cudaMemsetAsync(w.cand_idx, 0xff, (size_t)Nq * nseg * KU_CAND * 4, st));   // empty lists
+  // (DG_KNN_ALL_SMS: the exchange runs on copy engines, so the local pass may fill the GPU)
+  const int nseg_l = (phases & DG_KNN_ALL_SMS) ? nseg : knn_nseg_local(Nq, nseg);
   int rc;
-  if ((rc = launch_split(local, Nq, F, Fp, w.qh, w.ql, w.qnorm2, w.dbmax2, st))) return rc;
-  const int t0 = row_lo / BN, t1 = ceil_div(row_lo + Nq, BN);
-  return launch_knn_umma(w, Nq, N, Fp, nseg_l, nseg, t1 - t0, 0, t0, row_lo, row_lo + Nq, 1, 0, st);
+  if (phases & DG_KNN_SPLIT_LOCAL) {
+    DG_CUDA_OK(cudaMemsetAsync(w.err, 0, 256, st));
+    if ((rc = launch_split(local, Nq, F, Fp, w.qh, w.ql, w.qnorm2, w.dbmax2, st))) return rc;
+  }
+  if (phases & DG_KNN_PASS_LOCAL) {
+    if (nseg_l < nseg) DG_CUDA_OK(cudaMemsetAsync(w.cand_idx, 0xff, (size_t)Nq * nseg * KU_CAND * 4, st));   // empty lists
+    const int t0 = row_lo / BN, t1 = ceil_div(row_lo + Nq, BN);
+    if ((rc = launch_knn_umma(w, Nq, N, Fp, nseg_l, nseg, t1 - t0, 0, t0, row_lo, row_lo + Nq, 1, 0, st))) return rc;
+  }
+  return DG_OK;
 }
 
 int knn_shard_finish(const float* db, int Nq, int row_lo, int N, int F, int k, int64_t* idx, float* sims, void* ws,
-                     cudaStream_t st) {
+                     int phases, int npeer_max, cudaStream_t st) {
   const int Fp = round_up(F, 64), BN = knn_bn();
   const KnnWs w = knn_ws_layout(ws, Nq, N, Fp, true, row_lo);
   const int nseg = knn_nseg(Nq, N, k);
   const int row_hi = row_lo + Nq;
   int rc;
-  if ((rc = launch_split(db, row_lo, F, Fp, w.dh, w.dl, nullptr, w.dbmax2, st))) return rc;
-  if ((rc = launch_split(db + (size_t)row_hi * F, N - row_hi, F, Fp, w.dh + (size_t)row_hi * Fp, w.dl + (size_t)row_hi * Fp,
-                         nullptr, w.dbmax2, st))) return rc;
-  const int ntiles = ceil_div(N, BN);
-  const int tA_end = ceil_div(row_lo, BN);                 // tiles [0, tA_end) hold rows below the local range
-  const int tB_begin = max(row_hi / BN, tA_end);           // tiles [tB_begin, ntiles) hold rows above it
-  if ((rc = launch_knn_umma(w, Nq, N, Fp, nseg, nseg, tA_end + (ntiles - tB_begin), tA_end, tB_begin - tA_end, row_lo,
-                            row_hi, 2, 1, st))) return rc;
-  return launch_rerank(w, db + (size_t)row_lo * F, db, Nq, N, F, k, nseg, idx, sims, st);
+  if (phases & DG_KNN_SPLIT_REMOTE) {
+    if ((rc = launch_split(db, row_lo, F, Fp, w.dh, w.dl, nullptr, w.dbmax2, st))) return rc;
+    if ((rc = launch_split(db + (size_t)row_hi * F, N - row_hi, F, Fp, w.dh + (size_t)row_hi * Fp,
+                           w.dl + (size_t)row_hi * Fp, nullptr, w.dbmax2, st))) return rc;
+  }
+  if (phases & DG_KNN_PASS_REMOTE) {
+    const int ntiles = ceil_div(N, BN);
+    const int tA_end = ceil_div(row_lo, BN);                 // tiles [0, tA_end) hold rows below the local range
+    const int tB_begin = max(row_hi / BN, tA_end);           // tiles [tB_begin, ntiles) hold rows above it
+    if ((rc = launch_knn_umma(w, Nq, N, Fp, nseg, nseg, tA_end + (ntiles - tB_begin), tA_end, tB_begin - tA_end, row_lo,
+                              row_hi, 2, 1, st))) return rc;
+  }
+  if (phases & DG_KNN_RERANK)
+    return launch_rerank(w, db + (size_t)row_lo * F, db, Nq, N, F, k, nseg, idx, sims, st, npeer_max);
+  return DG_OK;
+}
+
+// byte offsets of the bf16 hi / lo panels inside the workspace and the pitch of a panel row: what a host needs to
+// copy panel rows between the workspaces of different GPUs
+void knn_panel_layout(int N, int F, size_t* hi_off, size_t* lo_off, size_t* row_bytes) {
+  const size_t Fp = (size_t)round_up(F, 64);
+  *hi_off = 256;
+  *lo_off = 256 + al256((size_t)N * Fp * 2);
+  *row_bytes = Fp * 2;
 }
 
 }  // namespace dg

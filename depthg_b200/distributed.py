@@ -13,6 +13,8 @@ split arithmetic is backend-independent and is what the gloo tests exercise.
 """
 from __future__ import annotations
 
+import os
+import time
 from typing import Callable, Sequence
 
 import torch
@@ -92,13 +94,157 @@ def knn_shard_bounds(n: int, world_size: int, rank: int):
 
 
 _comm_streams = {}
+_symm_states = {}
 
 
-def sharded_knn_build(local_feats: torch.Tensor, total_rows: int, k: int, group=None, return_stats: bool = False):
-    """The query-row-sharded KNN build with the all-gather overlapped: ``local_feats`` are rows
-    ``knn_shard_bounds(total_rows, world, rank)`` of the normalised feature matrix.  The all-gather of the database
-    runs on a side stream while this rank already ranks its rows against the rows it holds
-    (``KnnShard.begin``); ``finish`` continues over the remote rows.  Returns this rank's int64 [rows,k] block."""
+class _SymmKnnState:
+    """Per-(N, F, k, group) state of the peer-copy exchange: the KNN workspace and the gathered fp32 database live in
+    symmetric memory (torch.distributed._symmetric_memory: every rank can address every rank's buffers over NVLink),
+    so a rank PUSHES its bf16 panel rows and fp32 rows into its peers' buffers with plain device-to-device copies -
+    copy engines, no SMs, nothing for the tensor pass to compete with - instead of running an all-gather kernel.
+    (Pushes, not pulls: posted writes stream over NVLink, reads pay the round trip; measured 2x apart.)"""
+
+    def __init__(self, N, F, k, group, dev):
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm
+        from . import _lib
+        from .precompute_knns import knn_panel_layout
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        world, rank = self.world, self.rank
+        self.per = -(-N // world)
+        self.N, self.F, self.k, self.dev = N, F, k, dev
+        self.ws_bytes = _lib.lib().dg_knn_workspace_bytes(self.per, N, F, k)
+        self.ws = symm.empty(self.ws_bytes, dtype=torch.uint8, device=dev)
+        self.gathered = symm.empty((N, F), dtype=torch.float32, device=dev)
+        gname = (group or dist.group.WORLD).group_name
+        self.h_ws = symm.rendezvous(self.ws, gname)
+        self.h_g = symm.rendezvous(self.gathered, gname)
+        hi_off, lo_off, row_bytes = knn_panel_layout(N, F)
+        self.comm = [torch.cuda.Stream(device=dev) for _ in range(max(world - 1, 1))]
+        self.ev_split, self.ev_ready = torch.cuda.Event(), torch.cuda.Event()
+        self.ev_panels, self.ev_rows = torch.cuda.Event(), torch.cuda.Event()
+        # the two copy batches (pointers never change): A = this rank's panel rows and its squared-norm maximum into
+        # every peer's workspace, B = its fp32 rows into every peer's copy of the database; one stream per peer
+        lo, hi = knn_shard_bounds(N, world, rank)
+        wsp, gp = self.ws.data_ptr(), self.gathered.data_ptr()
+        a, b = [], []
+        for step in range(1, world):
+            p = (rank + step) % world
+            st = self.comm[step - 1].cuda_stream
+            pw = self.h_ws.get_buffer(p, (self.ws_bytes,), torch.uint8, 0).data_ptr()
+            pg = self.h_g.get_buffer(p, (N, F), torch.float32, 0).data_ptr()
+            if hi > lo:
+                for off in (hi_off, lo_off):
+                    o = off + lo * row_bytes
+                    a.append((pw + o, wsp + o, (hi - lo) * row_bytes, st))
+                b.append((pg + lo * F * 4, gp + lo * F * 4, (hi - lo) * F * 4, st))
+            a.append((pw + 128 + 4 * rank, wsp + 8, 4, st))     # header slot 32 + rank of the peer <- this rank's maximum
+
+        def pack(items):
+            n = len(items)
+            return (n, (C.c_void_p * n)(*[i[0] for i in items]), (C.c_void_p * n)(*[i[1] for i in items]),
+                    (C.c_size_t * n)(*[i[2] for i in items]), (C.c_void_p * n)(*[i[3] for i in items]))
+
+        self.batch_a, self.batch_b = pack(a), pack(b)
+        self.trace = None
+
+    def build(self, local, return_stats):
+        from . import _lib
+        from ._lib import check
+        from .precompute_knns import KnnShard
+        N, k, world, rank = self.N, self.k, self.world, self.rank
+        lo, hi = knn_shard_bounds(N, world, rank)
+        nq = hi - lo
+        cur = torch.cuda.current_stream(self.dev)
+        trace = self.trace = [] if os.environ.get("DEPTHG_KNN_TRACE") else None
+
+        def mark(name, stream):                   # DEPTHG_KNN_TRACE=1: (name, host seconds, event) per milestone
+            if trace is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record(stream)
+                trace.append((name, time.perf_counter(), ev))
+
+        mark("start", cur)
+        shard = None
+        lib = _lib.lib()
+        if nq:
+            self.gathered[lo:hi].copy_(local)
+            shard = KnnShard(local, lo, N, k, ws=self.ws).begin(_lib.KNN_SPLIT_LOCAL)
+        else:
+            self.ws[:256].zero_()
+        self.ev_split.record(cur)
+        mark("split_local", cur)
+        c0 = self.comm[0]
+        c0.wait_event(self.ev_split)
+        with torch.cuda.stream(c0):
+            # every rank is through its previous build (stream order) and has its panel rows ready: peers' buffers
+            # may be written
+            self.h_ws.barrier(channel=0)
+            self.ev_ready.record(c0)
+            mark("barrier0", c0)
+        if shard is not None:
+            shard.begin(_lib.KNN_PASS_LOCAL | _lib.KNN_ALL_SMS)      # under the copies: they need no SMs
+        mark("pass_local", cur)
+        for c in self.comm[1:]:
+            c.wait_event(self.ev_ready)
+        check(lib.dg_memcpy_batch(*self.batch_a), "dg_memcpy_batch")
+        for c in self.comm[1:]:
+            c0.wait_stream(c)
+        with torch.cuda.stream(c0):
+            self.h_ws.barrier(channel=1)          # every rank's panel rows have landed everywhere
+            self.ev_panels.record(c0)
+            mark("panels", c0)
+        if shard is not None:                     # enqueue the remote pass before the host spends time on the rest
+            cur.wait_event(self.ev_panels)
+            shard.finish(None, phases=_lib.KNN_PASS_REMOTE)
+            mark("pass_remote", cur)
+        for c in self.comm[1:]:
+            c.wait_event(self.ev_panels)          # (keeps the fp32 copies behind ALL panel copies on the links)
+        check(lib.dg_memcpy_batch(*self.batch_b), "dg_memcpy_batch")   # fp32 rows: only the re-rank reads them
+        for c in self.comm[1:]:
+            c0.wait_stream(c)
+        with torch.cuda.stream(c0):
+            self.h_ws.barrier(channel=2)          # ... and so have the fp32 rows
+            self.ev_rows.record(c0)
+            mark("rows", c0)
+        if shard is None:
+            idx = torch.empty((0, k), device=self.dev, dtype=torch.int64)
+            return (idx, {"pipeline_error": 0, "fallback_rows": 0}) if return_stats else idx
+        cur.wait_event(self.ev_rows)
+        out = shard.finish(self.gathered, return_stats=False, phases=_lib.KNN_RERANK, npeer_max=world)
+        mark("rerank", cur)
+        if return_stats:
+            head = self.ws[:12].view(torch.int32).cpu()
+            return out, {"pipeline_error": int(head[0]), "fallback_rows": int(head[1])}
+        return out
+
+
+def _symm_knn_state(N, F, k, group, dev):
+    """The cached exchange state, or None when symmetric memory cannot be set up here (all ranks agree)."""
+    key = (N, F, k, id(group), dev.index)
+    if key not in _symm_states:
+        st = None
+        try:
+            st = _SymmKnnState(N, F, k, group, dev)
+            ok = 1.0
+        except Exception as e:  # noqa: BLE001  (no NVLink peer access / no symmetric allocator: use the collective)
+            import warnings
+            warnings.warn(f"depthg_b200: symmetric-memory KNN exchange unavailable ({type(e).__name__}: {e}); "
+                          "falling back to the NCCL all-gather")
+            ok = 0.0
+        flag = torch.tensor([ok], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        _symm_states[key] = st if flag.item() == 1.0 else None
+    return _symm_states[key]
+
+
+def sharded_knn_build(local_feats: torch.Tensor, total_rows: int, k: int, group=None, return_stats: bool = False,
+                      exchange: str = "auto"):
+    """The query-row-sharded KNN build with the exchange overlapped: ``local_feats`` are rows
+    ``knn_shard_bounds(total_rows, world, rank)`` of the normalised feature matrix.  Returns this rank's int64 [rows,k]
+    block.  ``exchange``: "peer" = panel rows and fp32 rows pulled from the peers' symmetric memory with copy engines
+    (no SMs) while this rank ranks its rows against the rows it holds; "nccl" = ``all_gather_into_tensor`` on a side
+    stream; "auto" = peer copies when the shard is small enough for two phases to pay and symmetric memory is there."""
     from .precompute_knns import KnnShard, knn_topk
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         out = knn_topk(local_feats, local_feats, k, return_stats=return_stats)
@@ -110,6 +256,18 @@ def sharded_knn_build(local_feats: torch.Tensor, total_rows: int, k: int, group=
     per = -(-total_rows // world)
     dev = local_feats.device
     local_feats = local_feats.contiguous()
+    # Two phases pay when the local pass is short enough to hide under the exchange: 128 query rows per CTA, one CTA
+    # per SM, 256 database rows per tile at ~14 us a tile.  With few ranks the local rows are a large part of the
+    # database and one pass over everything is faster.
+    nblocks_max = -(-per // 128)
+    nseg_local = max(1, min(112 // max(nblocks_max, 1), 8))
+    two_phase = nblocks_max <= 112 and -(-per // 256) / nseg_local <= 26
+    if exchange not in ("auto", "peer", "nccl"):
+        raise ValueError("exchange must be 'auto', 'peer' or 'nccl'")
+    if exchange == "peer" or (exchange == "auto" and two_phase):
+        st = _symm_knn_state(total_rows, local_feats.shape[1], k, group, dev)
+        if st is not None:
+            return st.build(local_feats, return_stats)
     src = local_feats
     if hi - lo != per:                       # a short last shard: pad the all-gather input (the pad lands beyond row N)
         src = torch.zeros((per, local_feats.shape[1]), device=dev, dtype=local_feats.dtype)
@@ -122,13 +280,7 @@ def sharded_knn_build(local_feats: torch.Tensor, total_rows: int, k: int, group=
     comm.wait_stream(cur)
     with torch.cuda.stream(comm):
         dist.all_gather_into_tensor(gathered, src, group=group)
-    # Two phases pay when the local pass is short enough to hide under the all-gather: it runs on the SMs the
-    # communication kernels leave free (112 of 148, one CTA per SM and 128 query rows per CTA), 256 database rows per
-    # tile at ~14 us a tile.  With few ranks the local rows are a large part of the database and one pass is faster.
-    nblocks = -(-(hi - lo) // 128)
-    nseg_local = max(1, min(112 // max(nblocks, 1), 8))
-    overlap = nblocks <= 112 and -(-(hi - lo) // 256) / nseg_local <= 26
-    if overlap and hi > lo:
+    if two_phase and hi > lo:
         shard = KnnShard(local_feats, lo, total_rows, k).begin()
         cur.wait_stream(comm)
         return shard.finish(gathered[:total_rows], return_stats=return_stats)

@@ -57,12 +57,13 @@ def knn_topk(queries: torch.Tensor, db: torch.Tensor, k: int = TOPK, return_sims
 
 
 class KnnShard:
-    """Two-phase build of one query-row shard (``dg_knn_shard_begin`` / ``dg_knn_shard_finish``): the shard's rows are
+    """Phased build of one query-row shard (``dg_knn_shard_begin`` / ``dg_knn_shard_finish``): the shard's rows are
     database rows [row_lo, row_lo + Nq).  ``begin`` needs only the local rows and is what a rank runs while the
-    all-gather of the database is in flight; ``finish`` takes the gathered database.  Same result as
-    ``knn_topk(local, db, k)``."""
+    exchange of the database is in flight; ``finish`` takes the gathered database.  Same result as
+    ``knn_topk(local, db, k)``.  ``ws``: an externally owned workspace (e.g. symmetric memory the peers copy panel rows
+    out of); ``phases`` as in include/depthg_b200.h."""
 
-    def __init__(self, local: torch.Tensor, row_lo: int, total_rows: int, k: int = TOPK):
+    def __init__(self, local: torch.Tensor, row_lo: int, total_rows: int, k: int = TOPK, ws: torch.Tensor = None):
         require_cuda_f32(local, "local")
         if local.dim() != 2:
             raise ValueError(f"local must be [Nq,F], got {tuple(local.shape)}")
@@ -72,37 +73,51 @@ class KnnShard:
             raise ValueError(f"rows [{row_lo},{row_lo + local.shape[0]}) outside the {total_rows}-row database")
         self.local, self.row_lo, self.N, self.k = local.contiguous(), int(row_lo), int(total_rows), int(k)
         self.Nq, self.F = self.local.shape
-        self.ws = None
+        self.ws, self.ws_bytes = ws, 0
         if self.Nq:
             self.ws_bytes = _lib.lib().dg_knn_workspace_bytes(self.Nq, self.N, self.F, self.k)
-            self.ws = torch.empty(self.ws_bytes, device=local.device, dtype=torch.uint8)
+            if ws is None:
+                self.ws = torch.empty(self.ws_bytes, device=local.device, dtype=torch.uint8)
+            elif ws.numel() < self.ws_bytes or ws.dtype != torch.uint8 or ws.device != local.device:
+                raise ValueError("ws must be a uint8 tensor of at least dg_knn_workspace_bytes on the rows' device")
 
-    def begin(self):
+    def begin(self, phases: int = _lib.KNN_BEGIN_ALL):
         if self.Nq:
             dev = self.local.device
             with torch.cuda.device(dev):
                 check(_lib.lib().dg_knn_shard_begin(ptr(self.local), self.Nq, self.row_lo, self.N, self.F, self.k,
-                                                    ptr(self.ws), self.ws_bytes, stream_ptr(dev.index)),
+                                                    ptr(self.ws), self.ws_bytes, phases, stream_ptr(dev.index)),
                       "dg_knn_shard_begin")
         return self
 
-    def finish(self, db: torch.Tensor, return_stats: bool = False):
-        require_cuda_f32(db, "db")
-        if db.dim() != 2 or db.shape[0] != self.N or db.shape[1] != self.F or not db.is_contiguous():
-            raise ValueError(f"db must be a contiguous [{self.N},{self.F}] tensor, got {tuple(db.shape)}")
+    def finish(self, db: torch.Tensor, return_stats: bool = False, phases: int = _lib.KNN_FINISH_ALL,
+               npeer_max: int = 0, idx: torch.Tensor = None):
         dev = self.local.device
-        if db.device != dev:
-            raise ValueError(f"db on {db.device}, local rows on {dev}")
-        idx = torch.empty((self.Nq, self.k), device=dev, dtype=torch.int64)
+        if db is not None:
+            require_cuda_f32(db, "db")
+            if db.dim() != 2 or db.shape[0] != self.N or db.shape[1] != self.F or not db.is_contiguous():
+                raise ValueError(f"db must be a contiguous [{self.N},{self.F}] tensor, got {tuple(db.shape)}")
+            if db.device != dev:
+                raise ValueError(f"db on {db.device}, local rows on {dev}")
+        if idx is None and (phases & _lib.KNN_RERANK):
+            idx = torch.empty((self.Nq, self.k), device=dev, dtype=torch.int64)
         if self.Nq:
             with torch.cuda.device(dev):
                 check(_lib.lib().dg_knn_shard_finish(ptr(db), self.Nq, self.row_lo, self.N, self.F, self.k, ptr(idx),
-                                                     None, ptr(self.ws), self.ws_bytes, stream_ptr(dev.index)),
-                      "dg_knn_shard_finish")
+                                                     None, ptr(self.ws), self.ws_bytes, phases, npeer_max,
+                                                     stream_ptr(dev.index)), "dg_knn_shard_finish")
         if return_stats:
             head = self.ws[:12].view(torch.int32).cpu() if self.Nq else [0, 0]
             return idx, {"pipeline_error": int(head[0]), "fallback_rows": int(head[1])}
         return idx
+
+
+def knn_panel_layout(total_rows: int, F: int):
+    """(hi_offset, lo_offset, row_bytes) of the bf16 panels inside a KNN workspace (dg_knn_panel_layout)."""
+    import ctypes as C
+    hi, lo, rb = C.c_size_t(), C.c_size_t(), C.c_size_t()
+    check(_lib.lib().dg_knn_panel_layout(total_rows, F, C.byref(hi), C.byref(lo), C.byref(rb)), "dg_knn_panel_layout")
+    return hi.value, lo.value, rb.value
 
 
 def build_knn_index(normed_feats: torch.Tensor, k: int = TOPK, n_batches: int = N_BATCHES) -> torch.Tensor:

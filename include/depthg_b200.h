@@ -282,19 +282,41 @@ DG_API int dg_knn_topk(const float* q, const float* db, int Nq, int N, int F, in
                 size_t ws_bytes, dg_stream_t stream);
 
 /* The same build for a query-row SHARD of a multi-GPU job (query rows shard, the database is
- * all-gathered), in two phases so that the all-gather overlaps useful work.  The shard's query rows are database rows
+ * all-gathered), in phases so that the exchange overlaps useful work.  The shard's query rows are database rows
  * [row_lo, row_lo + Nq).
- *   dg_knn_shard_begin : needs only the local rows `local` [Nq,F]; ranks them against themselves (the part of the
- *                        database this rank already holds) - enqueue it, then wait for the all-gather.
- *   dg_knn_shard_finish: `db` is the complete [N,F] database (rows [row_lo, row_lo+Nq) equal to `local`); continues the
- *                        candidate lists of phase 1 over the remote rows and finishes exactly like dg_knn_topk.
- * Same workspace (dg_knn_workspace_bytes(Nq,N,F,k)), untouched between the two calls; same stream; same diagnostics
- * header.  Result identical to dg_knn_topk(db + row_lo*F, db, Nq, N, ...).  Replaces the per-shard form of
- * src/precompute_knns.py:99-113. */
+ *   dg_knn_shard_begin : needs only the local rows `local` [Nq,F].  DG_KNN_SPLIT_LOCAL resets the diagnostics header and
+ *                        writes the rows' bf16 hi/lo panels into the workspace (panel rows [row_lo, row_lo+Nq));
+ *                        DG_KNN_PASS_LOCAL ranks the rows against themselves - the part of the database this rank
+ *                        already holds, i.e. what it can do while the exchange is in flight (it leaves a quarter of the
+ *                        SMs to the communication kernels unless DG_KNN_ALL_SMS says the exchange needs none).
+ *   dg_knn_shard_finish: `db` is the complete [N,F] fp32 database (rows [row_lo, row_lo+Nq) equal to `local`).
+ *                        DG_KNN_SPLIT_REMOTE writes the panels of all other rows (skip it when the host copied the
+ *                        peers' panel rows into the workspace itself: dg_knn_panel_layout), DG_KNN_PASS_REMOTE continues
+ *                        the candidate lists of phase 1 over the remote rows, DG_KNN_RERANK finishes exactly like
+ *                        dg_knn_topk (`db` is only read by SPLIT_REMOTE and RERANK).  npeer_max: number of header slots
+ *                        ws int32[32 .. 32+npeer_max) that hold the squared-norm maxima (bit patterns, ws int32[2] of the
+ *                        other ranks) when their panels were copied in; 0 otherwise.
+ * Same workspace (dg_knn_workspace_bytes(Nq,N,F,k), Nq = the LARGEST shard if workspaces are to be laid out alike),
+ * untouched between the calls; same stream order; same diagnostics header.  Result identical to
+ * dg_knn_topk(db + row_lo*F, db, Nq, N, ...).  Replaces the per-shard form of src/precompute_knns.py:99-113. */
+#define DG_KNN_SPLIT_LOCAL 1
+#define DG_KNN_PASS_LOCAL 2
+#define DG_KNN_BEGIN_ALL 3
+#define DG_KNN_ALL_SMS 8      /* with DG_KNN_PASS_LOCAL: the exchange needs no SMs (copy engines) - use all of them */
+#define DG_KNN_SPLIT_REMOTE 1
+#define DG_KNN_PASS_REMOTE 2
+#define DG_KNN_RERANK 4
+#define DG_KNN_FINISH_ALL 7
 DG_API int dg_knn_shard_begin(const float* local, int Nq, int row_lo, int N, int F, int k, void* ws, size_t ws_bytes,
-                       dg_stream_t stream);
+                       int phases, dg_stream_t stream);
 DG_API int dg_knn_shard_finish(const float* db, int Nq, int row_lo, int N, int F, int k, int64_t* idx, float* sims, void* ws,
-                        size_t ws_bytes, dg_stream_t stream);
+                        size_t ws_bytes, int phases, int npeer_max, dg_stream_t stream);
+/* Byte offsets of the bf16 hi / lo panels ([N, row_bytes / 2] each) inside a KNN workspace and the pitch of a panel row. */
+DG_API int dg_knn_panel_layout(int N, int F, size_t* hi_offset, size_t* lo_offset, size_t* row_bytes);
+
+/* n device-to-device copies, copy i enqueued on streams[i] (copy engines; peer-mapped pointers allowed): the exchange
+ * step of the sharded KNN build when the host moves panel rows itself. */
+DG_API int dg_memcpy_batch(int n, void* const* dst, const void* const* src, const size_t* bytes, const dg_stream_t* streams);
 
 /* Mean-pool + L2-normalise of get_feats (src/precompute_knns.py:19):
  * t [N,C,H,W] with element strides (host) -> out [N,C], eps = 1e-12. */

@@ -14,5 +14,5 @@ except Exception as e:
 P
 }
 run fps X=1
-run inline DEPTHG_BENCH_ALLREDUCE=inline
+
 run none DEPTHG_BENCH_ALLREDUCE=none

@@ -14,7 +14,10 @@
 // coalesced.  HBM-bound: no data reuse beyond the four bilinear corners.
 #include <string.h>
 
+#include <stdlib.h>
+
 #include "kernels.cuh"
+#include "umma.cuh"
 
 namespace dg {
 
@@ -308,6 +311,230 @@ __global__ void __launch_bounds__(GF_THREADS, GF_MINBLOCKS)
                         int Prows, int nsplit, GatherOut o) {
   extern __shared__ float gfs[];  // [GF_WARPS][C] for the final cross-warp mean
   gather_feats_body<NV, FMT>(sets, B, C, H, W, coords, S, perms, eps, Prows, nsplit, o, blockIdx.x, gfs);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// The same gather as a PERSISTENT kernel of self-feeding warps (channels-last sources, C a multiple of 128, split fp16
+// panels).  The register-resident kernel above keeps a point's four corner rows in flight in registers (128 registers
+// per thread, 16 warps per SM; ncu: waiting on memory with 24 % of the warp slots active at 45 % of the DRAM peak), and
+// every warp pays the address chain of a point - permutation row, coordinates, corners - in front of its loads.
+// Here each of the 8 warps of a CTA owns two 4 x C-float slots of shared memory and runs its own double-buffered
+// pipeline: it turns its next-but-one point into four 1-D bulk copies (cp.async.bulk, one per corner row, completion
+// on the slot's mbarrier) and meanwhile blends / normalises / splits / stores the point whose bytes have landed.  No
+// warp ever waits for another one (the first version of this kernel had a producer warp and a consumer barrier per 8
+// points: the barriers and the producer's serial address chain cost more than the loads).  The address work is done
+// for 32 points at a time, one per lane, half a batch ahead of its first use.
+//
+// A CTA owns a contiguous range of panel rows, dealt round-robin to its warps.  Panel means: a warp sums the rows it
+// normalised per (set, image) panel and writes its own partial - 16 partials per panel: 8 warps x (the CTA that holds
+// the panel's first row | the CTA that holds the rest); a range is never shorter than a panel, so two CTAs at most
+// share one.  Fixed order everywhere: the means are deterministic.
+constexpr int GB_WARPS = 8;
+constexpr int GB_THREADS = 32 * GB_WARPS;
+constexpr int GB_PARTS = 2 * GB_WARPS;      // mean partials per (set, image) panel
+
+struct GatherBulkArgs {
+  SetTable sets;
+  GatherOut o;
+  const float* coords;
+  const int64_t* perms;
+  int B, C, H, W, S, Prows;
+  long long total_rows;                     // nsets * B * Prows
+  int dbg;                                  // timing experiments (DEPTHG_B200_GATHER_DBG) bits: 1 no panel stores, 2 no loads
+  float eps;
+};
+
+template <int NV>
+__global__ void __launch_bounds__(GB_THREADS, 1) gather_bulk_kernel(const __grid_constant__ GatherBulkArgs a) {
+  using namespace umma;
+  extern __shared__ uint8_t gb_raw[];
+  constexpr int C = 128 * NV;
+  uint8_t* base = gb_raw + ((128u - (smem_u32(gb_raw) & 127u)) & 127u);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* ring = reinterpret_cast<float*>(base) + (size_t)warp * 2 * 4 * C;        // this warp's two slots [2][4][C]
+  float* meta = reinterpret_cast<float*>(base) + (size_t)GB_WARPS * 2 * 4 * C + warp * 8;   // [2][4] corner weights
+  uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<float*>(base) + (size_t)GB_WARPS * 2 * 4 * C +
+                                               GB_WARPS * 8) + warp * 2;                    // [2]
+  const int P = a.S * a.S, Prows = a.Prows;
+  if (lane == 0) {
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    fence_barrier_init();
+  }
+  __syncwarp();
+
+  // this CTA's rows [r0, r1): 16-row units, contiguous, at least one whole panel unless there are fewer panels than CTAs
+  const long long units = a.total_rows / 16;
+  const long long r0 = (units * blockIdx.x / gridDim.x) * 16, r1 = (units * (blockIdx.x + 1) / gridDim.x) * 16;
+  const int nw = (int)((r1 - r0 - warp + GB_WARPS - 1) / GB_WARPS);   // rows of this warp: r0 + warp + 8 n
+  if (nw <= 0) return;
+
+  // address work for 32 of the warp's rows at a time (lane i <-> row n0 + i): raw global loads first, the arithmetic later
+  struct Raw { int64_t perm; float cx, cy; int set, b, p; bool in_range, valid; };
+  struct Desc { const float *p00, *p01, *p10, *p11; float w0, w1, w2, w3; };
+  auto fetch = [&](int n0) {
+    Raw q;
+    const int n = n0 + lane;
+    q.in_range = n < nw;
+    q.valid = false;
+    q.perm = 0; q.cx = q.cy = 0.f; q.set = q.b = q.p = 0;
+    if (!q.in_range) return q;
+    const unsigned gr = (unsigned)(r0 + warp) + (unsigned)GB_WARPS * (unsigned)n;   // total_rows < 2^31 (checked at launch)
+    const unsigned g = gr / (unsigned)Prows;
+    q.p = (int)(gr - g * (unsigned)Prows);
+    q.set = (int)(g / (unsigned)a.B);
+    q.b = (int)(g - (unsigned)q.set * (unsigned)a.B);
+    q.valid = q.p < P;
+    const SetDesc& sd = a.sets.s[q.set];
+    q.perm = sd.perm_row >= 0 ? a.perms[(size_t)sd.perm_row * a.B + q.b] : (int64_t)q.b;
+    if (q.valid) {
+      const int h = q.p / a.S, w = q.p - h * a.S;
+      const float* cc = a.coords + (((size_t)sd.coord * a.B + q.b) * P + (w * a.S + h)) * 2;   // the reference's S-axis swap
+      q.cx = __ldg(cc);
+      q.cy = __ldg(cc + 1);
+    }
+    return q;
+  };
+  auto resolve = [&](const Raw& q) {
+    Desc d;
+    const SetDesc& sd = a.sets.s[q.set];
+    const float* timg = sd.src + q.perm * sd.sb;
+    d.p00 = d.p01 = d.p10 = d.p11 = timg;   // padding rows (p >= P) read pixel 0 with zero weights: they come out as zeros
+    d.w0 = d.w1 = d.w2 = d.w3 = 0.f;
+    if (q.valid) {
+      const Corners k = bilinear_corners(q.cx, q.cy, a.H, a.W);
+      d.p00 = timg + k.y0 * sd.sh + k.x0 * sd.sw;
+      d.p01 = k.x1_ok ? d.p00 + sd.sw : d.p00;
+      d.p10 = k.y1_ok ? d.p00 + sd.sh : d.p00;
+      d.p11 = d.p10 + (k.x1_ok ? sd.sw : 0);
+      d.w0 = k.w00;
+      d.w1 = k.x1_ok ? k.w01 : 0.f;
+      d.w2 = k.y1_ok ? k.w10 : 0.f;
+      d.w3 = (k.x1_ok && k.y1_ok) ? k.w11 : 0.f;
+    }
+    return d;
+  };
+  // lane (n % 32) issues row n's copies into slot n & 1 from the batch `d` that holds it
+  auto issue = [&](int n, const Desc& d) {
+    if (n < nw && lane == (n & 31)) {
+      const int s = n & 1;
+      float* m = meta + 4 * s;
+      m[0] = d.w0; m[1] = d.w1; m[2] = d.w2; m[3] = d.w3;
+      float* dst = ring + (size_t)s * 4 * C;
+      if (a.dbg & 2) {
+        mbar_arrive(&full[s]);
+      } else {
+        fence_proxy_async_smem();     // the slot's previous contents were read through the generic proxy
+        mbar_arrive_expect_tx(&full[s], (uint32_t)(16 * C));
+        bulk_load(dst, d.p00, (uint32_t)(4 * C), &full[s]);
+        bulk_load(dst + C, d.p01, (uint32_t)(4 * C), &full[s]);
+        bulk_load(dst + 2 * C, d.p10, (uint32_t)(4 * C), &full[s]);
+        bulk_load(dst + 3 * C, d.p11, (uint32_t)(4 * C), &full[s]);
+      }
+    }
+  };
+
+  Desc cur = resolve(fetch(0));
+  Raw nxt_raw = fetch(32);
+  Desc nxt = cur;
+  issue(0, cur);
+  issue(1, cur);
+
+  float4 macc[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) macc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float invP = 1.f / (float)P;
+
+  int g = (int)((r0 + warp) / Prows);
+  int p = (int)((r0 + warp) - (long long)g * Prows);
+  int set = g / a.B, b = g - set * a.B;
+  for (int n = 0; n < nw; ++n) {
+    const int nb = n & 31;
+    if (nb == 16) nxt = resolve(nxt_raw);                       // (its loads were issued 16 rows ago)
+    // row identity (uniform over the warp), advanced incrementally at the bottom of the loop
+    const int slot = a.sets.s[set].slot;
+    const size_t pbase = ((size_t)slot * a.B + b) * Prows;
+    const size_t ro = (pbase + p) * C;
+    const int s = n & 1;
+    mbar_wait(&full[s], (n >> 1) & 1);
+    const float4 wq = *reinterpret_cast<const float4*>(meta + 4 * s);
+    const float* src = ring + (size_t)s * 4 * C + lane * 4;
+    float4 x[NV];
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float4 q0 = *reinterpret_cast<const float4*>(src + 128 * i);
+      const float4 q1 = *reinterpret_cast<const float4*>(src + C + 128 * i);
+      const float4 q2 = *reinterpret_cast<const float4*>(src + 2 * C + 128 * i);
+      const float4 q3 = *reinterpret_cast<const float4*>(src + 3 * C + 128 * i);
+      // (same operation order as the register-resident kernel: the two are bit-identical)
+      x[i].x = q0.x * wq.x + q1.x * wq.y + q2.x * wq.z + q3.x * wq.w;
+      x[i].y = q0.y * wq.x + q1.y * wq.y + q2.y * wq.z + q3.y * wq.w;
+      x[i].z = q0.z * wq.x + q1.z * wq.y + q2.z * wq.z + q3.z * wq.w;
+      x[i].w = q0.w * wq.x + q1.w * wq.y + q2.w * wq.z + q3.w * wq.w;
+      ss += x[i].x * x[i].x + x[i].y * x[i].y + x[i].z * x[i].z + x[i].w * x[i].w;
+    }
+    __syncwarp();                      // the slot is in registers: refill it with the warp's next-but-one row
+    if (nb == 30) { cur = nxt; nxt_raw = fetch(n + 2 + 32); }   // rows n + 2 .. n + 33 are the next batch
+    issue(n + 2, cur);
+    ss = warp_sum(ss);
+    const float r = p < P ? 1.f / fmaxf(sqrtf(ss), a.eps) : 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      if (p >= P) x[i] = make_float4(0.f, 0.f, 0.f, 0.f);   // padding row: exact zeros whatever pixel 0 holds
+      x[i] = make_float4(x[i].x * r, x[i].y * r, x[i].z * r, x[i].w * r);
+      macc[i].x += x[i].x; macc[i].y += x[i].y; macc[i].z += x[i].z; macc[i].w += x[i].w;
+    }
+    if (!(a.dbg & 1)) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = lane * 4 + 128 * i;
+        __half hh[4], ll[4];
+        constexpr float sc = F16_FEAT_SCALE;
+        split_f16(x[i].x * sc, hh[0], ll[0]); split_f16(x[i].y * sc, hh[1], ll[1]);
+        split_f16(x[i].z * sc, hh[2], ll[2]); split_f16(x[i].w * sc, hh[3], ll[3]);
+        if (a.o.interleave) {   // see gather_feats_body: even lanes store both hi quads, odd lanes both lo quads
+          const uint2 mh = *reinterpret_cast<uint2*>(hh), ml = *reinterpret_cast<uint2*>(ll);
+          const bool odd = lane & 1;
+          const uint2 give = odd ? mh : ml;
+          uint2 got;
+          got.x = __shfl_xor_sync(0xffffffffu, give.x, 1);
+          got.y = __shfl_xor_sync(0xffffffffu, give.y, 1);
+          const uint4 outv = odd ? make_uint4(got.x, got.y, ml.x, ml.y) : make_uint4(mh.x, mh.y, got.x, got.y);
+          const int c8 = c & ~7;
+          *reinterpret_cast<uint4*>(a.o.hi16 + 2 * ro + il_col(c8) + (odd ? 32 : 0)) = outv;
+        } else {
+          *reinterpret_cast<uint2*>(a.o.hi16 + ro + c) = *reinterpret_cast<uint2*>(hh);
+          *reinterpret_cast<uint2*>(a.o.lo16 + ro + c) = *reinterpret_cast<uint2*>(ll);
+        }
+      }
+    }
+    if (lane == 0) a.o.rnorm[pbase + p] = r;
+    // last row of this warp in panel g (its rows are 8 apart): write the warp's partial of the panel mean
+    const bool last_in_panel = (n + 1 == nw) || (p + GB_WARPS >= Prows);
+    if (last_in_panel && a.o.meanvec != nullptr) {
+      const long long g0 = (long long)g * Prows;                 // the panel's first row
+      const int part = (g0 >= r0 ? 0 : GB_WARPS) + warp;         // second half of the partials: the panel began in another CTA
+      float* mv = a.o.meanvec + (((size_t)slot * a.B + b) * GB_PARTS + part) * C + lane * 4;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        *reinterpret_cast<float4*>(mv + 128 * i) =
+            make_float4(macc[i].x * invP, macc[i].y * invP, macc[i].z * invP, macc[i].w * invP);
+        macc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      if (g0 >= r0 && g0 + Prows <= r1) {                        // the whole panel is this CTA's: the other half is zero
+        float* mz = mv + (size_t)GB_WARPS * C;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) *reinterpret_cast<float4*>(mz + 128 * i) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    p += GB_WARPS;                     // the warp's next row
+    if (p >= Prows) {
+      p -= Prows;
+      ++g;
+      if (++b == a.B) { b = 0; ++set; }
+    }
+  }
 }
 
 // Code tensors (D <= 128, any strides): lanes over channels with scalar loads, everything in registers, a
@@ -654,6 +881,16 @@ static int fill_sets(const char* fn, const float* src, const int64_t* strides, i
   return DG_OK;
 }
 
+// DEPTHG_B200_GATHER=regs keeps the register-resident kernel (comparison / fallback)
+static bool gather_bulk_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DEPTHG_B200_GATHER");
+    v = (e && e[0] == 'r') ? 0 : 1;
+  }
+  return v != 0;
+}
+
 // How many CTAs a (set, image) is split over: 8 on the register-resident fast path, else 1.
 int gather_nsplit(int fmt, const SetTable& tab, int nsets, int C, int ld) {
   if (fmt == FMT_CODE_SPLIT || C != ld || (C % 128) != 0 || C / 128 > 8) return 1;
@@ -663,6 +900,9 @@ int gather_nsplit(int fmt, const SetTable& tab, int nsets, int C, int ld) {
     const SetDesc& d = tab.s[s];
     if (d.sc != 1 || (d.sb & 3) || (d.sh & 3) || (d.sw & 3) || (reinterpret_cast<uintptr_t>(d.src) & 15)) return 1;
   }
+  // split fp16 panels whose 2 x 8 point slots (16 C floats each) fit in shared memory: the bulk-copy kernel, which
+  // writes GB_PARTS mean partials per panel; otherwise the register-resident kernel with 8 CTAs per panel
+  if (fmt == FMT_FEATS_SPLIT && gather_bulk_enabled() && (size_t)GB_WARPS * 2 * 16 * C <= 200 * 1024) return GB_PARTS;
   return 8;
 }
 
@@ -670,6 +910,34 @@ template <int NV>
 static int launch_gather_fast(int fmt, const SetTable& tab, int nsets, int B, int C, int H, int W, const float* coords,
                               int S, const int64_t* perms, float eps, int Prows, int nsplit, const GatherOut& o,
                               cudaStream_t st) {
+  if (fmt == FMT_FEATS_SPLIT && nsplit == GB_PARTS) {   // (gather_nsplit chose the self-feeding bulk-copy kernel)
+    const size_t smem = (size_t)GB_WARPS * 2 * 16 * C + GB_WARPS * (32 + 16) + 128;
+    static PerDevice attr_pd = {}, sm_pd = {};
+    size_t& attr = per_device(attr_pd);
+    size_t& sms = per_device(sm_pd);
+    if (attr < smem) {
+      DG_CUDA_OK(cudaFuncSetAttribute(gather_bulk_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr = smem;
+    }
+    if (!sms) {
+      int dev = 0, n = 0;
+      DG_CUDA_OK(cudaGetDevice(&dev));
+      DG_CUDA_OK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+      sms = (size_t)(n > 0 ? n : 148);
+    }
+    GatherBulkArgs ga;
+    ga.sets = tab; ga.o = o; ga.coords = coords; ga.perms = perms;
+    ga.B = B; ga.C = C; ga.H = H; ga.W = W; ga.S = S; ga.Prows = Prows;
+    ga.total_rows = (long long)nsets * B * Prows; ga.eps = eps;
+    DG_REQUIRE(ga.total_rows < (1LL << 31), DG_ERR_UNSUPPORTED, "gather: too many panel rows");
+    ga.dbg = getenv("DEPTHG_B200_GATHER_DBG") ? atoi(getenv("DEPTHG_B200_GATHER_DBG")) : 0;
+    const int npanels = nsets * B;             // a CTA's row range must hold at least one whole panel
+    const int grid = npanels < (int)sms ? npanels : (int)sms;
+    DG_PRE(st);
+    gather_bulk_kernel<NV><<<grid, GB_THREADS, smem, st>>>(ga);
+    DG_LAUNCH_OK("gather_bulk_kernel");
+    return DG_OK;
+  }
   const size_t smem = (size_t)GF_WARPS * C * sizeof(float);
   DG_PRE(st);
   if (fmt == FMT_F32)

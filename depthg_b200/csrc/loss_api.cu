@@ -55,7 +55,7 @@ static void make_plan(const dg_loss_desc_t* d, dg_loss_plan_t* p) {
   auto take = [&](size_t bytes) { size_t o = off; off += al256(bytes); return o; };
   p->coords = take((size_t)2 * B * P * 2 * 4);
   p->frn = take(nf * B * Pr * 4);
-  p->fmean = take(nf * B * 8 * p->ldf * 4);  // up to 8 partial means per (slot, image)
+  p->fmean = take(nf * B * 16 * p->ldf * 4);  // up to 16 partial means per (slot, image)
   p->crn = take(np * B * Pr * 4);
   p->dsign = take(B * Pr * 4);
   p->ws_bytes = corr_workspace_bytes(p->npairs, d->B, P);

@@ -3,6 +3,7 @@
 #include <string.h>
 
 #include <atomic>
+#include <stdlib.h>
 #include <map>
 #include <string>
 #include <vector>
@@ -86,6 +87,17 @@ extern "C" size_t dg_profile_collect(char* buf, size_t buf_bytes) {
   }
   return out.size() + 1;
 }
+
+namespace dg {
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DEPTHG_B200_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+}  // namespace dg
 
 namespace dg { void set_clock_buffer(long long* p); }
 // Debug: when non-NULL, the tcgen05 correlation kernel writes [grid][16] globaltimer stamps of its phases there.

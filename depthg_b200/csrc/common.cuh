@@ -59,6 +59,31 @@ inline size_t& per_device(PerDevice& s) {
   return s.v[(d >= 0 && d < 64) ? d : 0];
 }
 
+// ---- programmatic dependent launch (PDL).  The kernels of a step form a chain in one stream; launched with the
+// "programmatic stream serialization" attribute, kernel n+1 is set up on the SMs while kernel n drains, instead of
+// after it has drained: each of them calls pdl_wait() before it touches global memory (it blocks until the previous
+// kernel has completed and flushed) and pdl_trigger() as soon as it runs (the next kernel may be scheduled whenever
+// SM resources allow).  Takes the ~3-5 us launch gap per boundary off a 0.3 ms step.  DEPTHG_B200_PDL=0 disables it.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+bool pdl_enabled();   // api.cu
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 __host__ __device__ inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
 

@@ -153,6 +153,8 @@ __global__ void __launch_bounds__(CP_THREADS, 1) corr_pipe_kernel(const __grid_c
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = *tmem_slot;
+  pdl_trigger();
+  pdl_wait();   // barriers and TMEM are set up while the gathers drain; the panels are only read from here on
 
   if (warp == 0) {
     // ================================ TMA producer ================================
@@ -697,7 +699,7 @@ int corr_loss_pipe(const dg_panels_t* pan, const float* fmean, int nsplit, const
   }
   const int grid = prm.nitems < (int)sms ? prm.nitems : (int)sms;   // persistent: one CTA per SM walks the item list
   DG_PRE(st);
-  corr_pipe_kernel<<<grid, CP_THREADS, CP_SMEM, st>>>(prm);
+  launch_pdl(corr_pipe_kernel, dim3(grid), dim3(CP_THREADS), (size_t)CP_SMEM, st, prm);
   DG_LAUNCH_OK("corr_pipe_kernel");
   return DG_OK;  // out8 is written by the CTA that completes the last item
 }

@@ -132,6 +132,8 @@ __global__ void __launch_bounds__(FPS_THREADS) fps_kernel(const float* __restric
   __shared__ int s_idx[2][FPS_WARPS];
   __shared__ int s_scan[FPS_WARPS];
 
+  pdl_trigger();
+  pdl_wait();   // (the depth maps may be the previous kernel's output; nothing is written before this point)
   const int img = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float* gdepth = (img < B ? depth_a + (size_t)img * Hd * Wd : depth_b + (size_t)(img - B) * Hd * Wd);
@@ -269,9 +271,8 @@ int launch_fps(const float* depth_a, const float* depth_b, int B, int Hd, int Wd
       configured = smem;                                                                                          \
     }                                                                                                             \
     DG_PRE(st);                                                                                                   \
-    fps_kernel<PPT, ST, RTV, PRV><<<nimg, FPS_THREADS, smem, st>>>(depth_a, depth_b, B, Hd, Wd, H, W, S * S, factor,          \
-                                                          far_plane, affine, coords, idx, dsign, S, sign_pitch,     \
-                                                          sign_eps);                                                \
+    launch_pdl(fps_kernel<PPT, ST, RTV, PRV>, dim3(nimg), dim3(FPS_THREADS), smem, st, depth_a, depth_b, B, Hd, Wd, H, W,  \
+               S * S, factor, far_plane, affine, coords, idx, dsign, S, sign_pitch, sign_eps);                     \
   } while (0)
   static int rt_env = -1;  // DEPTHG_B200_FPS_RT = 32 | 64 | 128 | 256 round threads (experiments); default FPS_DEFAULT_RT
   if (rt_env < 0) {

@@ -362,6 +362,8 @@ __global__ void __launch_bounds__(GB_THREADS, 1) gather_bulk_kernel(const __grid
     fence_barrier_init();
   }
   __syncwarp();
+  pdl_trigger();
+  pdl_wait();   // coordinates / permutations come from the kernels before; nothing global is touched above
 
   // this CTA's rows [r0, r1): 16-row units, contiguous, at least one whole panel unless there are fewer panels than CTAs
   const long long units = a.total_rows / 16;
@@ -612,6 +614,8 @@ __global__ void __launch_bounds__(GF_THREADS)
     gather_code_kernel(const __grid_constant__ SetTable sets, int B, int C, int H, int W,
                        const float* __restrict__ coords, int S, const int64_t* __restrict__ perms, float eps,
                        int Prows, int nsplit, GatherOut o, const __grid_constant__ DotsJob job, int ncode_blocks) {
+  pdl_trigger();
+  pdl_wait();
   if ((int)blockIdx.x >= ncode_blocks) {   // appended pair_dots CTAs (independent of the code gather, same stream slot)
     pair_dots_body(job, (int)blockIdx.x - ncode_blocks);
     return;
@@ -686,6 +690,8 @@ __global__ void __launch_bounds__(256)
                            const float* __restrict__ rnorm, const float* __restrict__ dC1,
                            const float* __restrict__ dC2, int npairs, const __grid_constant__ PairTable pairs,
                            int has_depth, const __grid_constant__ GroupW gws, int nsets, int ni, int nj, int njw) {
+  pdl_trigger();
+  pdl_wait();
   const int P = S * S;
   // ni / nj: pitch (in panels) of the dC2 per-row-tile and dC1 per-column-tile (njw = 128) or per-column-group
   // (njw = 256) partial buffers; only the tiles / groups that contain real points were written
@@ -934,7 +940,7 @@ static int launch_gather_fast(int fmt, const SetTable& tab, int nsets, int B, in
     const int npanels = nsets * B;             // a CTA's row range must hold at least one whole panel
     const int grid = npanels < (int)sms ? npanels : (int)sms;
     DG_PRE(st);
-    gather_bulk_kernel<NV><<<grid, GB_THREADS, smem, st>>>(ga);
+    launch_pdl(gather_bulk_kernel<NV>, dim3(grid), dim3(GB_THREADS), smem, st, ga);
     DG_LAUNCH_OK("gather_bulk_kernel");
     return DG_OK;
   }
@@ -962,10 +968,10 @@ int launch_gather(int fmt, const SetTable& tab, int nsets, int B, int C, int H, 
     const int ncode = nsets * B * ns, grid = ncode + (tail ? tail->npairs * tail->B : 0);
     DG_PRE(st);
     switch (ld / 32) {
-      case 1: gather_code_kernel<1><<<grid, GF_THREADS, 0, st>>>(tab, B, C, H, W, coords, S, perms, eps, Prows, ns, o, job, ncode); break;
-      case 2: gather_code_kernel<2><<<grid, GF_THREADS, 0, st>>>(tab, B, C, H, W, coords, S, perms, eps, Prows, ns, o, job, ncode); break;
-      case 3: gather_code_kernel<3><<<grid, GF_THREADS, 0, st>>>(tab, B, C, H, W, coords, S, perms, eps, Prows, ns, o, job, ncode); break;
-      default: gather_code_kernel<4><<<grid, GF_THREADS, 0, st>>>(tab, B, C, H, W, coords, S, perms, eps, Prows, ns, o, job, ncode); break;
+      case 1: launch_pdl(gather_code_kernel<1>, dim3(grid), dim3(GF_THREADS), 0, st, tab, B, C, H, W, coords, S, perms, eps, Prows, ns, o, job, ncode); break;
+      case 2: launch_pdl(gather_code_kernel<2>, dim3(grid), dim3(GF_THREADS), 0, st, tab, B, C, H, W, coords, S, perms, eps, Prows, ns, o, job, ncode); break;
+      case 3: launch_pdl(gather_code_kernel<3>, dim3(grid), dim3(GF_THREADS), 0, st, tab, B, C, H, W, coords, S, perms, eps, Prows, ns, o, job, ncode); break;
+      default: launch_pdl(gather_code_kernel<4>, dim3(grid), dim3(GF_THREADS), 0, st, tab, B, C, H, W, coords, S, perms, eps, Prows, ns, o, job, ncode); break;
     }
     DG_LAUNCH_OK("gather_code_kernel");
     return DG_OK;
@@ -1047,8 +1053,8 @@ int launch_gather_bwd(const SetTable& tab, int nsets, int B, int C, int H, int W
   const long long rows = (long long)nsets * B * S * S;
   const int blocks = (int)((rows * 32 + 255) / 256);
   DG_PRE(st);
-  gather_norm_bwd_kernel<<<blocks, 256, 0, st>>>(tab, B, C, H, W, coords, S, perms, eps, Prows, ld, cn, cn_lo, rnorm,
-                                                 dC1, dC2, npairs, pt, has_depth, gw, nsets, ni, nj, njw);
+  launch_pdl(gather_norm_bwd_kernel, dim3(blocks), dim3(256), 0, st, tab, B, C, H, W, coords, S, perms, eps, Prows, ld, cn,
+             cn_lo, rnorm, dC1, dC2, npairs, pt, has_depth, gw, nsets, ni, nj, njw);
   DG_LAUNCH_OK("gather_norm_bwd_kernel");
   return DG_OK;
 }

@@ -39,10 +39,15 @@ static void make_plan(const dg_loss_desc_t* d, dg_loss_plan_t* p) {
   // groups of two tiles (panels padded to a multiple of 256 rows so that every group is whole)
   // kernel 2 = the persistent double-buffered tcgen05 kernel (corr_pipe.cu, default); 1 = the round-1 kernel
   // (corr_umma.cu, DEPTHG_B200_CORR=umma1, kept for comparison); 0 = the generic CUDA-core kernel
-  p->kernel = (P <= 1024 && p->ldc <= 128 && !(d->flags & DG_FLAG_FORCE_SIMT)) ? 2 : 0;
+  // Measured on B200 (profiles/r02_*): up to 128 points (one tile per pair and image) the persistent kernel wins
+  // (69 vs 73 us at cfg2); above, a CTA of the round-1 kernel that walks a 2 x 2 tile block (S = 12: no row-mean
+  // pre-pass, 0.50 vs 0.60 ms a step) or a group of two column tiles (dense: first-operand chunks loaded once per two
+  // tiles, 3.13 vs 3.91 ms) moves fewer operand bytes per tile, which is what bounds both.
+  p->kernel = (P <= 1024 && p->ldc <= 128 && !(d->flags & DG_FLAG_FORCE_SIMT)) ? (P <= 128 ? 2 : 1) : 0;
   if (p->kernel) {
     const char* e = getenv("DEPTHG_B200_CORR");
     if (e && strcmp(e, "umma1") == 0) p->kernel = 1;
+    if (e && strcmp(e, "pipe") == 0) p->kernel = 2;
   }
   p->Prows = p->kernel == 2 ? round_up(P, 128)
                             : (p->kernel == 1 ? (P <= 256 ? round_up(P, 128) : round_up(P, 256)) : round_up(P, 64));

@@ -18,6 +18,8 @@ namespace dg {
 __global__ void super_perms_kernel(unsigned long long seed, unsigned long long offset, int n, int B,
                                    int64_t* __restrict__ out, int use_smem) {
   extern __shared__ int sp_buf[];
+  pdl_trigger();
+  pdl_wait();
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (use_smem) {            // one block: thread k owns column k of sp_buf[i * n + k] (conflict-free)
     if (k < n) {
@@ -72,9 +74,9 @@ extern "C" int dg_super_perms(unsigned long long seed, unsigned long long offset
   const bool use_smem = n <= 128 && smem <= 48 * 1024;
   DG_PRE(st);
   if (use_smem)
-    super_perms_kernel<<<1, 128, smem, st>>>(seed, offset, n, B, out, 1);
+    launch_pdl(super_perms_kernel, dim3(1), dim3(128), smem, st, seed, offset, n, B, out, 1);
   else
-    super_perms_kernel<<<ceil_div(n, 32), 32, 0, st>>>(seed, offset, n, B, out, 0);
+    launch_pdl(super_perms_kernel, dim3(ceil_div(n, 32)), dim3(32), 0, st, seed, offset, n, B, out, 0);
   DG_LAUNCH_OK("super_perms_kernel");
   return DG_OK;
 }

@@ -616,11 +616,14 @@ __global__ void __launch_bounds__(GF_THREADS)
                        int Prows, int nsplit, GatherOut o, const __grid_constant__ DotsJob job, int ncode_blocks) {
   pdl_trigger();
   pdl_wait();
-  if ((int)blockIdx.x >= ncode_blocks) {   // appended pair_dots CTAs (independent of the code gather, same stream slot)
-    pair_dots_body(job, (int)blockIdx.x - ncode_blocks);
+  // the pair_dots CTAs (independent of the code gather, same stream slot) come FIRST: as the last blocks of the grid
+  // they were a serial tail of ~9 us (each is a latency chain over 2 x 16 partial means)
+  const int ndots = (int)gridDim.x - ncode_blocks;
+  if ((int)blockIdx.x < ndots) {
+    pair_dots_body(job, (int)blockIdx.x);
     return;
   }
-  gather_code_body<R>(sets, B, C, H, W, coords, S, perms, eps, Prows, nsplit, o, blockIdx.x);
+  gather_code_body<R>(sets, B, C, H, W, coords, S, perms, eps, Prows, nsplit, o, (int)blockIdx.x - ndots);
 }
 
 // Both gathers of a forward pass in ONE launch: the first `nfeat_blocks` CTAs gather the backbone features (bf16

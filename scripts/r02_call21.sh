@@ -1,0 +1,12 @@
+#!/bin/bash
+mkdir -p gpurun_out
+for m in 0 1; do
+DEPTHG_B200_GATHER_CODE=$m timeout 600 python bench.py --steps 100 --warmup 10 --no-cpu-baseline --no-knn --no-extra > gpurun_out/bench_gc$m.json 2> gpurun_out/bench.err
+python - <<P
+import json
+d=json.load(open('gpurun_out/bench_gc$m.json'))
+print("old_code_kernel=$m ms_per_step", round(d["ms_per_step"],4), d["breakdown_us"])
+P
+done
+timeout 900 python -m pytest tests -m gpu -q --timeout 900 -x -k "not knn" > gpurun_out/pytest.log 2>&1
+echo "pytest rc=$?"; tail -n 3 gpurun_out/pytest.log

@@ -107,7 +107,8 @@ class LossIO(C.Structure):
                 ("feats_strides", _i64x4), ("feats_pos_strides", _i64x4), ("code_strides", _i64x4),
                 ("code_pos_strides", _i64x4), ("depth", _vp), ("depth_pos", _vp), ("coords", _vp), ("perms", _vp),
                 ("arena", _vp), ("out8", _vp), ("cd_out", _vp), ("loss_out", _vp), ("dd_out", _vp), ("fd_dbg", _vp), ("aug_feats", _vp), ("aug_feats_strides", _i64x4),
-                ("perms_ready", _vp)]
+                ("perms_ready", _vp), ("perm_seed", C.c_ulonglong), ("perm_offset", C.c_ulonglong),
+                ("gen_perms", C.c_int)]
 
 
 class LossGrads(C.Structure):

@@ -16,7 +16,10 @@
 //   4. the selection ORDER is discarded like the reference does: a block scan of
 //      the taken flags emits the picks in raster order as indices and as
 //      normalised (row/H, col/W) coordinates.
+#include <string.h>
+
 #include "kernels.cuh"
+#include "sampler.cuh"
 
 namespace dg {
 
@@ -119,7 +122,7 @@ __global__ void __launch_bounds__(FPS_THREADS) fps_kernel(const float* __restric
                                                           int H, int W, int nsel, float factor, float far_plane,
                                                           int affine, float* __restrict__ coords,
                                                           int32_t* __restrict__ idx_out, float* __restrict__ dsign,
-                                                          int sign_S, int sign_pitch, float sign_eps) {
+                                                          int sign_S, int sign_pitch, float sign_eps, PermJob pj) {
   extern __shared__ __align__(16) float fps_smem[];
   const int npts = H * W;
   const int npad = (npts + 3) & ~3;
@@ -134,6 +137,10 @@ __global__ void __launch_bounds__(FPS_THREADS) fps_kernel(const float* __restric
 
   pdl_trigger();
   pdl_wait();   // (the depth maps may be the previous kernel's output; nothing is written before this point)
+  if (pj.n > 0 && blockIdx.x + 1 == gridDim.x) {   // one extra CTA: the step's negative-pair permutations
+    super_perms_block(pj.seed, pj.offset, pj.n, pj.B, pj.out, reinterpret_cast<int*>(fps_smem));
+    return;
+  }
   const int img = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float* gdepth = (img < B ? depth_a + (size_t)img * Hd * Wd : depth_b + (size_t)(img - B) * Hd * Wd);
@@ -248,7 +255,10 @@ __global__ void depth_sign_kernel(const float* __restrict__ depth, int B, int Hd
 
 int launch_fps(const float* depth_a, const float* depth_b, int B, int Hd, int Wd, int H, int W, int S, float factor,
                float far_plane, int affine, float* coords, int32_t* idx, cudaStream_t st, float* dsign, int sign_pitch,
-               float sign_eps) {
+               float sign_eps, const PermJob* perm_job) {
+  PermJob pj;
+  memset(&pj, 0, sizeof pj);
+  if (perm_job) pj = *perm_job;
   DG_REQUIRE(depth_a && coords, DG_ERR_INVALID, "dg_fps_coords: null pointer");
   DG_REQUIRE(B > 0 && Hd > 0 && Wd > 0 && H > 0 && W > 0 && S > 0, DG_ERR_INVALID, "dg_fps_coords: bad sizes");
   DG_REQUIRE(H <= Hd && W <= Wd, DG_ERR_UNSUPPORTED, "dg_fps_coords: pooling must not upsample (%dx%d -> %dx%d)", Hd,
@@ -261,7 +271,12 @@ int launch_fps(const float* depth_a, const float* depth_b, int B, int Hd, int Wd
   const size_t img_bytes = (size_t)Hd * Wd * sizeof(float);
   const bool stage = ((Hd * Wd) % 4 == 0) && (base_smem + img_bytes <= 220 * 1024) &&
                      ((reinterpret_cast<uintptr_t>(depth_a) | reinterpret_cast<uintptr_t>(depth_b)) % 16 == 0);
-  const size_t smem = base_smem + (stage ? img_bytes : 0);
+  size_t smem = base_smem + (stage ? img_bytes : 0);
+  if (pj.n > 0) {   // the extra CTA shuffles in shared memory and needs one thread per permutation
+    DG_REQUIRE(pj.n <= FPS_THREADS && (size_t)pj.n * pj.B * sizeof(int) <= 64 * 1024, DG_ERR_UNSUPPORTED,
+               "fps: %d permutations of %d do not fit the fused draw", pj.n, pj.B);
+    if (smem < (size_t)pj.n * pj.B * sizeof(int)) smem = (size_t)pj.n * pj.B * sizeof(int);
+  }
 #define DG_FPS_LAUNCH(PPT, ST, RTV, PRV)                                                                                    \
   do {                                                                                                            \
     static PerDevice configured_pd = {};                                                                          \
@@ -271,8 +286,8 @@ int launch_fps(const float* depth_a, const float* depth_b, int B, int Hd, int Wd
       configured = smem;                                                                                          \
     }                                                                                                             \
     DG_PRE(st);                                                                                                   \
-    launch_pdl(fps_kernel<PPT, ST, RTV, PRV>, dim3(nimg), dim3(FPS_THREADS), smem, st, depth_a, depth_b, B, Hd, Wd, H, W,  \
-               S * S, factor, far_plane, affine, coords, idx, dsign, S, sign_pitch, sign_eps);                     \
+    launch_pdl(fps_kernel<PPT, ST, RTV, PRV>, dim3(nimg + (pj.n > 0 ? 1 : 0)), dim3(FPS_THREADS), smem, st, depth_a,     \
+               depth_b, B, Hd, Wd, H, W, S * S, factor, far_plane, affine, coords, idx, dsign, S, sign_pitch, sign_eps, pj); \
   } while (0)
   static int rt_env = -1;  // DEPTHG_B200_FPS_RT = 32 | 64 | 128 | 256 round threads (experiments); default FPS_DEFAULT_RT
   if (rt_env < 0) {

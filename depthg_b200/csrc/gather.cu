@@ -686,6 +686,7 @@ int launch_nchw_to_nhwc(const float* a, const float* b, int B, int C, int HW, in
 
 // One warp per panel row: compose the row's gradient from the unit gradients,
 // back through x/max(||x||,eps), then atomically scatter through the 4 corners.
+template <int RT>
 __global__ void __launch_bounds__(256)
     gather_norm_bwd_kernel(const __grid_constant__ SetTable sets, int B, int C, int H, int W,
                            const float* __restrict__ coords, int S, const int64_t* __restrict__ perms, float eps,
@@ -708,21 +709,23 @@ __global__ void __launch_bounds__(256)
   const int slot = sd.slot;
   const size_t panel = (size_t)B * Prows * ld;
   const size_t rowoff = ((size_t)b * Prows + p) * ld;
-  const int R = ld / 32;  // ld is a multiple of 32, <= 8 chunks handled in registers
+  // ld is a multiple of 32; RT = ld / 32 chunks handled in registers (RT = 0: runtime count, up to 8)
+  constexpr int RJ = RT > 0 ? RT : 8;
+  const int R = RT > 0 ? RT : ld / 32;
   float gw[DG_NUM_GROUPS];
 #pragma unroll
   for (int g = 0; g < DG_NUM_GROUPS; ++g)
     gw[g] = gws.arr ? __ldg(gws.arr + g) : (gws.ptr[g] ? __ldg(gws.ptr[g]) : 0.f);
-  float g[8];
+  float g[RJ];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) g[j] = 0.f;
+  for (int j = 0; j < RJ; ++j) g[j] = 0.f;
   if (slot == 0) {
     for (int k = 0; k < npairs; ++k) {
       const float wk = gw[pairs.group[k]] * pairs.scale[k];
       for (int t = 0; t < nj_used; ++t) {   // dC1 comes as `nj` partial buffers (one per column group; 1 unless dense)
         const float* a = dC1 + ((size_t)k * nj + t) * panel + rowoff;
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
+        for (int j = 0; j < RJ; ++j)
           if (j < R) g[j] += wk * __ldg(a + lane + 32 * j);
       }
     }
@@ -730,7 +733,7 @@ __global__ void __launch_bounds__(256)
       const float w0 = gw[pairs.group[0]] * pairs.scale[0];
       const float* a = dC2 + (size_t)t * panel + rowoff;
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
+      for (int j = 0; j < RJ; ++j)
         if (j < R) g[j] += w0 * __ldg(a + lane + 32 * j);
     }
     if (has_depth) {
@@ -738,13 +741,13 @@ __global__ void __launch_bounds__(256)
       for (int t = 0; t < nj_used; ++t) {
         const float* a1 = dC1 + ((size_t)npairs * nj + t) * panel + rowoff;
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
+        for (int j = 0; j < RJ; ++j)
           if (j < R) g[j] += wd * __ldg(a1 + lane + 32 * j);
       }
       for (int t = 0; t < ni_used; ++t) {
         const float* a2 = dC2 + ((size_t)npairs * ni + t) * panel + rowoff;
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
+        for (int j = 0; j < RJ; ++j)
           if (j < R) g[j] += wd * __ldg(a2 + lane + 32 * j);
       }
     }
@@ -753,17 +756,17 @@ __global__ void __launch_bounds__(256)
     for (int t = 0; t < ni_used; ++t) {
       const float* a = dC2 + ((size_t)slot * ni + t) * panel + rowoff;
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
+      for (int j = 0; j < RJ; ++j)
         if (j < R) g[j] += ws * __ldg(a + lane + 32 * j);
     }
   }
   const float* xh = cn + (size_t)slot * panel + rowoff;
   const float* xl = cn_lo ? cn_lo + (size_t)slot * panel + rowoff : nullptr;  // split panels: x = hi + lo exactly
   const float r = __ldg(rnorm + ((size_t)slot * B + b) * Prows + p);
-  float x[8];
+  float x[RJ];
   float dot = 0.f;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
+  for (int j = 0; j < RJ; ++j) {
     x[j] = (j < R) ? __ldg(xh + lane + 32 * j) : 0.f;
     if (xl && j < R) x[j] += __ldg(xl + lane + 32 * j);
     dot += g[j] * x[j];
@@ -779,7 +782,7 @@ __global__ void __launch_bounds__(256)
   const int64_t sb = sd.sb, sc = sd.sc, sh = sd.sh, sw = sd.sw;
   float* g00 = const_cast<float*>(sd.src) + src * sb + k.y0 * sh + k.x0 * sw;  // sd.src is the gradient tensor here
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
+  for (int j = 0; j < RJ; ++j) {
     const int c = lane + 32 * j;
     if (j < R && c < C) {
       const float dx = (g[j] - x[j] * dot) * r;
@@ -1056,8 +1059,17 @@ int launch_gather_bwd(const SetTable& tab, int nsets, int B, int C, int H, int W
   const long long rows = (long long)nsets * B * S * S;
   const int blocks = (int)((rows * 32 + 255) / 256);
   DG_PRE(st);
-  launch_pdl(gather_norm_bwd_kernel, dim3(blocks), dim3(256), 0, st, tab, B, C, H, W, coords, S, perms, eps, Prows, ld, cn,
-             cn_lo, rnorm, dC1, dC2, npairs, pt, has_depth, gw, nsets, ni, nj, njw);
+#define DG_BWD(RT)                                                                                                    \
+  launch_pdl(gather_norm_bwd_kernel<RT>, dim3(blocks), dim3(256), 0, st, tab, B, C, H, W, coords, S, perms, eps, Prows, \
+             ld, cn, cn_lo, rnorm, dC1, dC2, npairs, pt, has_depth, gw, nsets, ni, nj, njw)
+  switch (ld / 32) {   // the common code widths get their register loops sized at compile time
+    case 1: DG_BWD(1); break;
+    case 2: DG_BWD(2); break;
+    case 3: DG_BWD(3); break;
+    case 4: DG_BWD(4); break;
+    default: DG_BWD(0); break;
+  }
+#undef DG_BWD
   DG_LAUNCH_OK("gather_norm_bwd_kernel");
   return DG_OK;
 }

@@ -99,9 +99,15 @@ __device__ __forceinline__ void pair_dots_body(const DotsJob& j, int w) {
 }
 
 // dsign != null: also writes the depth signs of depth_a (what launch_depth_sign computes) from the same CTA
+// Negative-pair permutations drawn by one extra CTA of the FPS launch (n = 0: none)
+struct PermJob {
+  unsigned long long seed, offset;
+  int n, B;
+  int64_t* out;   // [n,B]
+};
 int launch_fps(const float* depth_a, const float* depth_b, int B, int Hd, int Wd, int H, int W, int S, float factor,
                float far_plane, int affine, float* coords, int32_t* idx, cudaStream_t st, float* dsign = nullptr,
-               int sign_pitch = 0, float sign_eps = 0.f);
+               int sign_pitch = 0, float sign_eps = 0.f, const PermJob* perm_job = nullptr);
 int launch_depth_sign(const float* depth, int B, int Hd, int Wd, int S, float eps, int out_pitch, float* out,
                       cudaStream_t st);
 // meanvec is written as `nsplit` partial means per (slot, image): [slot,b,nsplit,ld], each already divided by P

@@ -140,13 +140,27 @@ extern "C" int dg_loss_forward(const dg_loss_desc_t* d, const dg_loss_io_t* io, 
   const bool pointwise = d->flags & DG_FLAG_POINTWISE;
   float* fmean = pointwise ? reinterpret_cast<float*>(A + pl.fmean) : nullptr;
   float* dsign = depth_term ? reinterpret_cast<float*>(A + pl.dsign) : nullptr;
+  PermJob pj;
+  memset(&pj, 0, sizeof pj);
+  bool draw = io->gen_perms && d->neg_samples > 0;
+  if (draw) {
+    pj.seed = io->perm_seed; pj.offset = io->perm_offset; pj.n = d->neg_samples; pj.B = B;
+    pj.out = const_cast<int64_t*>(io->perms);
+  }
   if (fps) {  // FPS of both depth tensors; the same CTAs also emit the depth signs the depth term needs
     float* c = reinterpret_cast<float*>(A + pl.coords);
+    const bool fuse = draw && pj.n <= 256 && (size_t)pj.n * B * sizeof(int) <= 64 * 1024;
     rc = launch_fps(io->depth, io->depth_pos, B, d->Hd, d->Wd, d->H, d->W, S, fov_factor(), kFarPlane, 1, c, nullptr, st,
-                    dsign, pl.Prows, kNormEps);
+                    dsign, pl.Prows, kNormEps, fuse ? &pj : nullptr);
     if (rc != DG_OK) return rc;
     coords = c;
-  } else if (depth_term) {
+    if (fuse) draw = false;
+  }
+  if (draw) {   // no FPS launch to ride on (or too many permutations for one CTA): the sampler's own launch
+    rc = dg_super_perms(pj.seed, pj.offset, pj.n, pj.B, pj.out, stream);
+    if (rc != DG_OK) return rc;
+  }
+  if (!fps && depth_term) {
     rc = launch_depth_sign(io->depth, B, d->Hd, d->Wd, S, kNormEps, pl.Prows, dsign, st);
     if (rc != DG_OK) return rc;
   }

@@ -7,9 +7,8 @@
 // by the caller's (seed, offset) — the caller advances its generator, so runs are reproducible
 // under torch.manual_seed — then applies the same fixed-point bump.  Same distribution as the
 // reference, different random stream (the module keeps the exact torch stream as an option).
-#include <curand_kernel.h>
-
 #include "kernels.cuh"
+#include "sampler.cuh"
 
 namespace dg {
 
@@ -21,26 +20,8 @@ __global__ void super_perms_kernel(unsigned long long seed, unsigned long long o
   pdl_trigger();
   pdl_wait();
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (use_smem) {            // one block: thread k owns column k of sp_buf[i * n + k] (conflict-free)
-    if (k < n) {
-      curandStatePhilox4_32_10_t st;
-      curand_init(seed, (unsigned long long)k, offset, &st);
-      for (int i = 0; i < B; ++i) sp_buf[i * n + k] = i;
-      for (int i = B - 1; i > 0; --i) {
-        const unsigned int r = curand(&st);
-        const int j = (int)(((unsigned long long)r * (unsigned long long)(i + 1)) >> 32);
-        const int t = sp_buf[i * n + k];
-        sp_buf[i * n + k] = sp_buf[j * n + k];
-        sp_buf[j * n + k] = t;
-      }
-    }
-    __syncthreads();
-    for (int e = threadIdx.x; e < n * B; e += blockDim.x) {     // coalesced write-out with the fixed-point bump
-      const int kk = e / B, i = e - kk * B;
-      int v = sp_buf[i * n + kk];
-      if (v == i) v += 1;    // perm[perm == arange] += 1
-      out[e] = (int64_t)(v % B);   // perm % size
-    }
+  if (use_smem) {
+    super_perms_block(seed, offset, n, B, out, sp_buf);
     return;
   }
   if (k >= n) return;

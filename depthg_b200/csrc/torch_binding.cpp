@@ -47,13 +47,14 @@ dg_loss_desc_t make_desc(const std::vector<int64_t>& ints, const std::vector<dou
 
 class CorrLossFn : public torch::autograd::Function<CorrLossFn> {
  public:
-  // ints: B, C, D, H, W, Hd, Wd, S, neg_samples, flags;  shifts: intra, inter, neg, depth
+  // ints: B, C, D, H, W, Hd, Wd, S, neg_samples, flags [, perm_seed, perm_offset];  shifts: intra, inter, neg, depth
   static variable_list forward(AutogradContext* ctx, Tensor feats, Tensor feats_pos, Tensor code, Tensor code_pos,
                                c10::optional<Tensor> depth, c10::optional<Tensor> depth_pos,
                                c10::optional<Tensor> coords, c10::optional<Tensor> perms,
                                c10::optional<Tensor> aug_feats, std::vector<int64_t> ints, std::vector<double> shifts,
                                bool materialize, bool want_fd, int64_t perms_event) {
-    TORCH_CHECK(ints.size() == 10 && shifts.size() == 4, "corr_loss: ints[10] / shifts[4] expected");
+    TORCH_CHECK((ints.size() == 10 || ints.size() == 12) && shifts.size() == 4,
+                "corr_loss: ints[10 or 12] / shifts[4] expected");
     dg_loss_desc_t d = make_desc(ints, shifts);
     dg_loss_plan_t plan;
     check(dg_loss_plan(&d, &plan), "dg_loss_plan");
@@ -90,6 +91,11 @@ class CorrLossFn : public torch::autograd::Function<CorrLossFn> {
       fill_strides(io.aug_feats_strides, *aug_feats);
     }
     io.perms_ready = reinterpret_cast<void*>(perms_event);
+    if (ints.size() >= 12) {   // the forward draws the permutations itself into `perms`
+      io.gen_perms = 1;
+      io.perm_seed = static_cast<unsigned long long>(ints[10]);    // two's-complement round trip of torch's uint64 seed
+      io.perm_offset = static_cast<unsigned long long>(ints[11]);
+    }
     check(dg_loss_forward(&d, &io, reinterpret_cast<dg_stream_t>(stream.stream())), "dg_loss_forward");
 
     ctx->saved_data["ints"] = ints;
@@ -164,7 +170,7 @@ std::vector<Tensor> corr_loss(Tensor feats, Tensor feats_pos, Tensor code, Tenso
 }
 
 std::vector<int64_t> loss_plan(std::vector<int64_t> ints) {
-  TORCH_CHECK(ints.size() == 10, "loss_plan: ints[10] expected");
+  TORCH_CHECK(ints.size() >= 10, "loss_plan: ints[10] expected");
   dg_loss_desc_t d = make_desc(ints, {});
   dg_loss_plan_t p;
   check(dg_loss_plan(&d, &p), "dg_loss_plan");

@@ -159,14 +159,21 @@ class _GraphedSuperPerms:
             gen.set_state(state)            # neither warm-up nor capture (failed or not) may consume the user's RNG stream
 
 
+def _reserve_perm_stream(size: int, device):
+    """(seed, offset) of the Philox stream the one-launch sampler uses for this draw; advances torch's CUDA generator
+    past it, so ``torch.manual_seed`` makes runs reproducible and successive draws differ."""
+    gen = torch.cuda.default_generators[device.index if device.index is not None else torch.cuda.current_device()]
+    seed, offset = gen.initial_seed(), gen.get_offset()
+    gen.set_offset(offset + 4 * ((size + 3) // 4))
+    return seed, offset
+
+
 def fused_super_perms(n: int, size: int, device) -> torch.Tensor:
     """All ``n`` negative-pair permutations in ONE kernel (dg_super_perms): same distribution as
     ``super_perm`` but a Philox stream of its own, keyed by torch's CUDA generator (seed, offset) so
     ``torch.manual_seed`` still makes runs reproducible.  The generator is advanced past the draws."""
     device = torch.device(device)
-    gen = torch.cuda.default_generators[device.index if device.index is not None else torch.cuda.current_device()]
-    seed, offset = gen.initial_seed(), gen.get_offset()
-    gen.set_offset(offset + 4 * ((size + 3) // 4))
+    seed, offset = _reserve_perm_stream(size, device)
     out = torch.empty((n, size), device=device, dtype=torch.long)
     check(_lib.lib().dg_super_perms(seed, offset, n, size, ptr(out), stream_ptr(device.index)), "dg_super_perms")
     return out
@@ -371,7 +378,7 @@ class _CorrLossFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, feats, feats_pos, code, code_pos, depth, depth_pos, coords, perms, desc, materialize,
-                perms_event=None, aug_feats=None):
+                perms_event=None, aug_feats=None, perm_gen=None):
         lib = _lib.lib()
         dev = feats.device
         plan = _lib.LossPlan()
@@ -402,6 +409,8 @@ class _CorrLossFn(torch.autograd.Function):
         io.perms = perms.data_ptr() if perms is not None else None
         io.arena, io.out8 = arena.data_ptr(), out8.data_ptr()
         io.perms_ready = perms_event.cuda_event if perms_event is not None else None
+        if perm_gen is not None:           # `perms` is an output: the forward draws the permutations itself
+            io.gen_perms, io.perm_seed, io.perm_offset = 1, perm_gen[0], perm_gen[1]
         if aug_feats is not None:
             io.aug_feats = aug_feats.data_ptr()
             io.aug_feats_strides[:] = aug_feats.stride()
@@ -467,7 +476,7 @@ class _CorrLossFn(torch.autograd.Function):
         with torch.cuda.device(arena.device):   # autograd may run this on a thread whose current device differs
             check(_lib.lib().dg_loss_backward(C.byref(ctx.desc), C.byref(io), C.byref(gr),
                                               stream_ptr(arena.device.index)), "dg_loss_backward")
-        return (None, None, d_code, d_code_pos) + (None,) * 8
+        return (None, None, d_code, d_code_pos) + (None,) * 9
 
 
 class ContrastiveCorrelationLoss(nn.Module):
@@ -506,6 +515,7 @@ class ContrastiveCorrelationLoss(nn.Module):
         # overlap with its gathers (a DDP-style gradient all-reduce of the previous step on another stream): the
         # forward waits for it after launching FPS.  Consumed (reset to None) by the call.
         self.wait_after_fps = None
+        self.last_perms = None
         self._last_coords = None
 
     @property
@@ -595,12 +605,17 @@ class ContrastiveCorrelationLoss(nn.Module):
             c2 = self.rand_fn(shape, dev) * 2 - 1
             coords = torch.stack([c1, c2]).float().contiguous()
         also_wait, self.wait_after_fps = self.wait_after_fps, None
+        perm_gen = None
+        self.last_perms = None
         if not nneg:
             perms = None
         elif self.perm_fn is not super_perm:
             perms = torch.stack([self.perm_fn(B, dev) for _ in range(nneg)]).to(torch.long).contiguous()
         elif self.negative_sampler == "fused" and not torch.cuda.is_current_stream_capturing():
-            perms = fused_super_perms(nneg, B, dev)
+            # drawn by the forward itself (one extra CTA of its FPS launch): only the buffer and the stream position
+            # are fixed here
+            perms = torch.empty((nneg, B), device=dev, dtype=torch.long)
+            perm_gen = _reserve_perm_stream(B, dev)
         elif self.negative_sampler == "fused":
             # under CUDA-graph capture the generator's offset cannot be read on the host: torch.randperm is graph-safe
             perms = super_perms(nneg, B, dev)
@@ -613,6 +628,8 @@ class ContrastiveCorrelationLoss(nn.Module):
             # (dg_loss_io_t.perms_ready is exactly that wait)
             perms_event = also_wait
 
+        self.last_perms = perms     # [neg_samples,B] source image of every negative (test hook; filled by the forward
+        #                             itself with the default sampler)
         depth_term = depth_term and aug_feats is None
         Hd = Wd = 0
         if depth_term or (flags & _lib.FLAG_FPS):
@@ -653,6 +670,9 @@ class ContrastiveCorrelationLoss(nn.Module):
             coords_off = _plan_cache.get(ints)
             if coords_off is None:
                 coords_off = _plan_cache[ints] = binding.loss_plan(list(ints))[1]
+            if perm_gen is not None:     # (seed as a signed 64-bit value: the binding casts it back)
+                seed = perm_gen[0] - (1 << 64) if perm_gen[0] >= (1 << 63) else perm_gen[0]
+                ints = ints + (seed, perm_gen[1])
             res = binding.corr_loss(orig_feats, orig_feats_pos, orig_code, orig_code_pos, depth, depth_pos, coords,
                                     perms, aug_feats, ints, shifts, bool(self.materialize_cd), False,
                                     perms_event.cuda_event if perms_event is not None else 0)
@@ -662,7 +682,7 @@ class ContrastiveCorrelationLoss(nn.Module):
         else:
             with torch.cuda.device(dev):    # kernels, attribute set-up and the stream all belong to the tensors' device
                 res = _CorrLossFn.apply(orig_feats, orig_feats_pos, orig_code, orig_code_pos, depth, depth_pos, coords,
-                                        perms, desc, bool(self.materialize_cd), perms_event, aug_feats)
+                                        perms, desc, bool(self.materialize_cd), perms_event, aug_feats, perm_gen)
             intra, inter, neg, dloss, out8, coords_src, cd_out, loss_out, dd_out = res
             coords_off = _CorrLossFn.last_coords_off
         # FPS coordinates stay in the arena until someone asks for them (see the last_coords property)

@@ -252,6 +252,11 @@ typedef struct dg_loss_io {
   int64_t aug_feats_strides[4];
   void* perms_ready;      /* optional cudaEvent_t: `perms` is produced on another stream; the gathers wait for it
                              (FPS and the depth signs, which do not need perms, are enqueued before the wait) */
+  /* gen_perms != 0: `perms` is an OUTPUT - the forward draws the neg_samples permutations itself (the dg_super_perms
+     stream for (perm_seed, perm_offset)), in one extra CTA of the FPS launch when there is one: no launch of its own,
+     nothing on the step's critical path.  dg_loss_backward reads the same buffer. */
+  unsigned long long perm_seed, perm_offset;
+  int gen_perms;
 } dg_loss_io_t;
 
 typedef struct dg_loss_grads {

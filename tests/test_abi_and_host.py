@@ -105,18 +105,19 @@ def test_loss_plan_sizes_for_sampled_and_dense_shapes():
         _lib.check(lib.dg_loss_plan(C.byref(desc), C.byref(p)), "dg_loss_plan")
         return p
 
-    p11, p12, p17, p28 = plan(11), plan(12), plan(17), plan(28)
-    # kernel 2 = the persistent tcgen05 kernel: panels padded to whole 128-row tiles (144 -> 256, 289 -> 384, 784 -> 896)
-    assert (p11.kernel, p11.Prows) == (2, 128) and (p12.kernel, p12.Prows) == (2, 256)
-    assert (p17.kernel, p17.Prows) == (2, 384) and (p28.kernel, p28.Prows) == (2, 896)
-    assert p11.total < p12.total < p17.total < p28.total
     import os
-    os.environ["DEPTHG_B200_CORR"] = "umma1"          # the round-1 kernel: column groups of 256 above 256 points
+    p11, p12, q17, q28 = plan(11), plan(12), plan(17), plan(28)
+    # default dispatch: kernel 2 (the persistent tcgen05 kernel) up to 128 points, kernel 1 (2 x 2 tile blocks up to 256
+    # points, column groups of 256 above: 289 -> 512, 784 -> 1024) beyond
+    assert (p11.kernel, p11.Prows) == (2, 128) and (p12.kernel, p12.Prows) == (1, 256)
+    assert (q17.kernel, q17.Prows) == (1, 512) and (q28.kernel, q28.Prows) == (1, 1024)
+    os.environ["DEPTHG_B200_CORR"] = "pipe"           # the persistent kernel forced: whole 128-row tiles (289 -> 384, 784 -> 896)
     try:
-        q17, q28 = plan(17), plan(28)
+        p17, p28 = plan(17), plan(28)
     finally:
         del os.environ["DEPTHG_B200_CORR"]
-    assert (q17.kernel, q17.Prows) == (1, 512) and (q28.kernel, q28.Prows) == (1, 1024)
+    assert (p17.kernel, p17.Prows) == (2, 384) and (p28.kernel, p28.Prows) == (2, 896)
+    assert p11.total < p12.total < p17.total < p28.total
     forced = plan(11, flags=1 | 2 | _lib.FLAG_FORCE_SIMT)
     assert (forced.kernel, forced.Prows) == (0, 128)
     desc = _lib.LossDesc(4, 64, 24, 28, 28, 224, 224, 30, 2, 3, 0.1, 0.2, 0.3, 0.0)   # 900 points > 784 grid points

@@ -534,24 +534,34 @@ def test_fused_negative_sampler_properties():
 
 
 def test_fused_sampler_loss_runs_and_matches_oracle_on_its_own_perms():
-    from depthg_b200.modules import ContrastiveCorrelationLoss
+    """The default sampler: the forward draws the permutations itself (one extra CTA of its FPS launch) from the Philox
+    stream ``fused_super_perms`` uses - same permutations under the same seed - and the loss on them equals the oracle's."""
+    from depthg_b200.modules import ContrastiveCorrelationLoss, fused_super_perms
     cfg, t = cases.make_loss_inputs("small_fps")
     fn = ContrastiveCorrelationLoss(cfg, negative_sampler="fused")
-    captured = []
-    import depthg_b200.modules as M
-    orig = M.fused_super_perms
-    M.fused_super_perms = lambda n, size, device: captured.append(orig(n, size, device)) or captured[-1]
-    try:
-        a = {k: t[k].to(dev()) for k in ("feats", "feats_pos", "code", "code_pos", "depth", "depth_pos")}
-        out = fn(a["feats"], a["feats_pos"], None, None, a["code"], a["code_pos"], a["depth"], a["depth_pos"])
-    finally:
-        M.fused_super_perms = orig
+    a = {k: t[k].to(dev()) for k in ("feats", "feats_pos", "code", "code_pos", "depth", "depth_pos")}
+    torch.manual_seed(77)
+    out = fn(a["feats"], a["feats_pos"], None, None, a["code"], a["code_pos"], a["depth"], a["depth_pos"])
+    perms = fn.last_perms.cpu()
+    torch.manual_seed(77)
+    assert torch.equal(perms, fused_super_perms(int(cfg.neg_samples), a["feats"].shape[0], dev()).cpu())
+    B = a["feats"].shape[0]
+    assert int(perms.min()) >= 0 and int(perms.max()) < B
+    assert not bool((perms == torch.arange(B)).any())          # no image is its own negative
     ofn = O.ContrastiveCorrelationLoss(cfg)
-    pit = iter(captured[0].cpu())
+    pit = iter(perms)
     ofn.perm_fn = lambda B, device: next(pit)
     want = ofn(t["feats"], t["feats_pos"], None, None, t["code"], t["code_pos"], t["depth"], t["depth_pos"])
     np.testing.assert_allclose(out[4].item(), want[4].mean().item(), rtol=RTOL, atol=ATOL)
     np.testing.assert_allclose(out[0].item(), want[0].item(), rtol=RTOL, atol=ATOL)
+    # without FPS there is no launch to ride on: the forward falls back to the sampler's own launch, same stream
+    cfg2, t2 = cases.make_loss_inputs("small_fps")
+    cfg2.depth_sampling = "none"
+    fn2 = ContrastiveCorrelationLoss(cfg2, negative_sampler="fused")
+    fn2.rand_fn = lambda shape, device: torch.full(shape, 0.25, device=device)
+    torch.manual_seed(77)
+    fn2(a["feats"], a["feats_pos"], None, None, a["code"], a["code_pos"], a["depth"], a["depth_pos"])
+    assert torch.equal(fn2.last_perms.cpu(), perms)
 
 
 def test_grad_tensors_backprop_equals_weighted_sum_backward():

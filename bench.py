@@ -607,7 +607,7 @@ def main():
         fl = algorithmic_flops(B)
         roofline["tensor"] = {"flops": fl, "achieved_tflops": fl / (dom_us * 1e-6) / 1e12,
                               "frac_of_bf16_sustained_div3": fl / (dom_us * 1e-6) / 1e12 / (tf_sust / 3.0),
-                              "note": "fd runs as a 3-product bf16 split, cd as a 3-product tf32 split"}
+                              "note": "fd and cd run as 3-term fp16 hi/lo products (fp32-grade), the gradient GEMMs likewise"}
     roofline_step = {"bound": "hbm", "algorithmic_bytes": step_bytes, "achieved": step_bytes / (ms_per_step * 1e-3) / 1e9,
                      "peak": hbm_peak, "unit": "GB/s", "frac": step_bytes / (ms_per_step * 1e-3) / 1e9 / hbm_peak,
                      "traffic": step_traffic,

@@ -35,11 +35,13 @@ using namespace umma;
 
 constexpr int CP_THREADS = 352;  // warp 0 TMA (operand chunks), warp 1 MMA, warps 2..9 epilogue (two per TMEM lane group), warp 10 TMA (codebuf fills)
 constexpr int CP_EPI = 256;
-constexpr int CP_NSTAGE = 4;
+constexpr int CP_NSTAGE = 3;
 constexpr int CP_STAGE = 32768;     // [A | B], 16 KB each: 128 rows x (32 hi | 32 lo) fp16 = 128-byte swizzled rows
 constexpr int CP_U = 65536;         // U hi (32 KB) + U lo (32 KB); doubles as the drain's transpose scratch
 constexpr int CP_CODE = 32768;      // gradient-GEMM operand: ONE half (hi or lo) of 128 code rows at a time (ldc <= 128)
-constexpr int CP_SMEM = CP_NSTAGE * CP_STAGE + CP_U + CP_CODE + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int CP_NCODE = 2;         // ... double-buffered: the fill of step s+1 is in flight while step s multiplies (a
+                                    // single buffer made the 4-8 fills of an item a chain of L2 round trips: 9-15 us)
+constexpr int CP_SMEM = CP_NSTAGE * CP_STAGE + CP_U + CP_NCODE * CP_CODE + 1024 /*align slack*/ + 256 /*barriers*/;
 static_assert(CP_SMEM + 1664 /*static: s_red, s_rowsum, s_sign*/ <= 232448, "corr_pipe_kernel: shared memory over the 227 KB CTA limit");
 
 struct PipeParams {
@@ -70,6 +72,7 @@ struct PipeParams {
   float* fd_dbg;    // optional raw fd [npairs,B,Prows,Prows] (tests)
   int* err;
   long long* clk;   // optional phase stamps of each CTA's first item [grid][16]
+  int l2_hints;              // L2 eviction-priority hints on the operand loads (DEPTHG_B200_L2HINTS=1; measured: slower, off by default)
   int dbg_mma;               // timing experiment (DEPTHG_B200_PIPE_MMA): 1 = hi.hi product only, 2 = no chunk MMAs (results garbage)
   const uint8_t* dbg_bulk;   // timing experiment (DEPTHG_B200_PIPE_BULK): stream stages as 1-D bulk copies from here (results garbage)
 };
@@ -114,16 +117,16 @@ __global__ void __launch_bounds__(CP_THREADS, 1) corr_pipe_kernel(const __grid_c
   uint8_t* u_hi = ring + CP_NSTAGE * CP_STAGE;
   uint8_t* u_lo = u_hi + 32768;
   uint8_t* codebuf = u_hi + CP_U;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(codebuf + CP_CODE);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(codebuf + CP_NCODE * CP_CODE);
   uint64_t* full = bars;                     // [CP_NSTAGE] stage landed
   uint64_t* empty = bars + CP_NSTAGE;        // [CP_NSTAGE] stage consumed by the MMAs
   uint64_t* acc_full = bars + 2 * CP_NSTAGE; // [2] fd/cd of TMEM set ready
   uint64_t* acc_free = acc_full + 2;         // [2] TMEM set drained by the epilogue
   uint64_t* u_ready = acc_full + 4;          // U tile written
   uint64_t* grad_full = acc_full + 5;        // gradient accumulators of a round ready
-  uint64_t* g_full = acc_full + 6;           // codebuf fill landed
-  uint64_t* g_free = acc_full + 7;           // codebuf fill consumed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 8);
+  uint64_t* g_full = acc_full + 6;           // [CP_NCODE] codebuf fill landed
+  uint64_t* g_free = acc_full + 8;           // [CP_NCODE] codebuf fill consumed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 10);
   __shared__ float s_red[8][4];
   __shared__ float s_rowsum[2][128];
   __shared__ float s_sign[128];   // depth signs of the item's column tile (the row's own sign is read from global)
@@ -144,8 +147,10 @@ __global__ void __launch_bounds__(CP_THREADS, 1) corr_pipe_kernel(const __grid_c
     }
     mbar_init(u_ready, CP_EPI);
     mbar_init(grad_full, 1);
-    mbar_init(g_full, 1);
-    mbar_init(g_free, 1);
+    for (int c = 0; c < CP_NCODE; ++c) {
+      mbar_init(&g_full[c], 1);
+      mbar_init(&g_free[c], 1);
+    }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -173,8 +178,15 @@ __global__ void __launch_bounds__(CP_THREADS, 1) corr_pipe_kernel(const __grid_c
           const size_t off = ((size_t)(blockIdx.x * 977 + job) * 32768) % (size_t)(64u << 20);
           bulk_load(st, prm.dbg_bulk + off, same ? 16384u : 32768u, &full[s]);
         } else {
-          tma_load_2d(st, m, &full[s], 64 * c, ra);
-          if (!same) tma_load_2d(st + 16384, m, &full[s], 64 * c, rb);
+          // the first operand's panel (slot 0 / the image's own code) is read by every pair of the image: keep it;
+          // the second operand's is read by this item only: let it go first
+          if (prm.l2_hints) {
+            tma_load_2d_hint(st, m, &full[s], 64 * c, ra, L2_EVICT_LAST);
+            if (!same) tma_load_2d_hint(st + 16384, m, &full[s], 64 * c, rb, L2_EVICT_FIRST);
+          } else {
+            tma_load_2d(st, m, &full[s], 64 * c, ra);
+            if (!same) tma_load_2d(st + 16384, m, &full[s], 64 * c, rb);
+          }
         }
         ++job;
       };
@@ -232,7 +244,7 @@ __global__ void __launch_bounds__(CP_THREADS, 1) corr_pipe_kernel(const __grid_c
       //   which = 2: dC2 += U^T . Cn (A = the same U tile MN-major, accumulator in the cd columns)
       //   both_u: A runs over U hi and U lo (the code half is `hi`), else over U hi only (the code half is `lo`);
       //   fresh: the first MMA overwrites the accumulator.  K = 128 U columns / rows = 8 steps of 16.
-      auto grad_mma = [&](int set, int which, bool both_u, bool fresh) {
+      auto grad_mma = [&](int set, int which, bool both_u, bool fresh, int cb) {
         const uint32_t d = tmem + 256u * set + (which == 1 ? 0u : 128u);
         const uint32_t idd = which == 1 ? id_g1 : id_g2;
 #pragma unroll
@@ -244,7 +256,7 @@ __global__ void __launch_bounds__(CP_THREADS, 1) corr_pipe_kernel(const __grid_c
           } else {
             a_h = dmn128 + uh + ks * 128; a_l = dmn128 + ul + ks * 128;
           }
-          const uint64_t bq = dmn64 + gb + ks * 64;
+          const uint64_t bq = dmn64 + gb + (uint32_t)cb * (CP_CODE >> 4) + ks * 64;
           mma_f16(d, a_h, bq, idd, !(fresh && ks == 0));
           if (both_u) mma_f16(d, a_l, bq, idd, 1);
         }
@@ -257,22 +269,23 @@ __global__ void __launch_bounds__(CP_THREADS, 1) corr_pipe_kernel(const __grid_c
       // are the inputs of the pending item's next step there?  (non-blocking: polled between operand chunks, so the
       // gradient GEMMs slot into the chunk stream whenever the epilogue and the fill producer are ready for them)
       auto step_ready = [&]() {
-        return (p_step != 0 || mbar_test(u_ready, nu & 1)) && mbar_test(g_full, fills & 1);
+        return (p_step != 0 || mbar_test(u_ready, nu & 1)) && mbar_test(&g_full[fills % CP_NCODE], (fills / CP_NCODE) & 1);
       };
       auto step = [&]() {   // issue the next step of the pending item (blocking on its inputs)
         if (p_step == 0) { ok = ok && mbar_wait(u_ready, nu & 1); ++nu; }
-        ok = ok && mbar_wait(g_full, fills & 1);
+        const int cb = fills % CP_NCODE;
+        ok = ok && mbar_wait(&g_full[cb], (fills / CP_NCODE) & 1);
         ++fills;
         tc_fence_after_sync();
         if (!ok) return;
         const int nsteps = p_csame ? 2 : 4;
         if (p_csame) {
-          grad_mma(p_set, 1, p_step == 0, p_step == 0);
-          grad_mma(p_set, 2, p_step == 0, p_step == 0);
+          grad_mma(p_set, 1, p_step == 0, p_step == 0, cb);
+          grad_mma(p_set, 2, p_step == 0, p_step == 0, cb);
         } else {
-          grad_mma(p_set, p_step < 2 ? 1 : 2, (p_step & 1) == 0, (p_step & 1) == 0);
+          grad_mma(p_set, p_step < 2 ? 1 : 2, (p_step & 1) == 0, (p_step & 1) == 0, cb);
         }
-        mma_commit(g_free);                      // this fill is consumed
+        mma_commit(&g_free[cb]);                 // this fill is consumed
         if (++p_step == nsteps) {
           mma_commit(grad_full);
           p_step = 0;
@@ -334,10 +347,12 @@ __global__ void __launch_bounds__(CP_THREADS, 1) corr_pipe_kernel(const __grid_c
         for (int f = 0; f < total && ok; ++f, ++fills) {
           const int j = f % per_round;
           const int r = j < 2 ? row2 : row1, half2 = j & 1;
-          ok = ok && mbar_wait(g_free, (fills & 1) ^ 1);
+          const int cb = fills % CP_NCODE;
+          ok = ok && mbar_wait(&g_free[cb], ((fills / CP_NCODE) & 1) ^ 1);
           if (!ok) break;
-          mbar_arrive_expect_tx(g_full, (uint32_t)(nb * 8192));
-          for (int a = 0; a < nb; ++a) tma_load_2d(codebuf + a * 8192, &prm.tm_cg, g_full, 64 * a + 32 * half2, r);
+          mbar_arrive_expect_tx(&g_full[cb], (uint32_t)(nb * 8192));
+          for (int a = 0; a < nb; ++a)
+            tma_load_2d(codebuf + cb * CP_CODE + a * 8192, &prm.tm_cg, &g_full[cb], 64 * a + 32 * half2, r);
         }
       }
       if (!ok) praise(prm.err, 4);
@@ -674,6 +689,7 @@ int corr_loss_pipe(const dg_panels_t* pan, const float* fmean, int nsplit, const
   prm.dC1 = dC1; prm.dC2 = dC2; prm.partials = partials;
   prm.cd_out = cd_out; prm.loss_out = loss_out; prm.dd_out = dd_out; prm.fd_dbg = fd_dbg; prm.err = err;
   prm.clk = get_clock_buffer();
+  prm.l2_hints = getenv("DEPTHG_B200_L2HINTS") && getenv("DEPTHG_B200_L2HINTS")[0] == '1';
   prm.dbg_mma = getenv("DEPTHG_B200_PIPE_MMA") ? atoi(getenv("DEPTHG_B200_PIPE_MMA")) : 0;
   prm.dbg_bulk = getenv("DEPTHG_B200_PIPE_BULK") ? static_cast<const uint8_t*>(pan->f_hi) : nullptr;
   if (!dots_done) {

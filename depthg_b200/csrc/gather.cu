@@ -341,6 +341,7 @@ struct GatherBulkArgs {
   int B, C, H, W, S, Prows;
   long long total_rows;                     // nsets * B * Prows
   int dbg;                                  // timing experiments (DEPTHG_B200_GATHER_DBG) bits: 1 no panel stores, 2 no loads
+  int l2_hints;                             // evict-first source loads / evict-last panel stores (DEPTHG_B200_L2HINTS=1; measured: slower, off by default)
   float eps;
 };
 
@@ -428,10 +429,13 @@ __global__ void __launch_bounds__(GB_THREADS, 1) gather_bulk_kernel(const __grid
       } else {
         fence_proxy_async_smem();     // the slot's previous contents were read through the generic proxy
         mbar_arrive_expect_tx(&full[s], (uint32_t)(16 * C));
-        bulk_load(dst, d.p00, (uint32_t)(4 * C), &full[s]);
-        bulk_load(dst + C, d.p01, (uint32_t)(4 * C), &full[s]);
-        bulk_load(dst + 2 * C, d.p10, (uint32_t)(4 * C), &full[s]);
-        bulk_load(dst + 3 * C, d.p11, (uint32_t)(4 * C), &full[s]);
+        // the sources stream through (each pixel is wanted by a handful of points at about the same time); the
+        // panels this kernel writes are what the correlation kernel reads next: they should be what stays in L2
+        const uint64_t pol = a.l2_hints ? L2_EVICT_FIRST : 0x1000000000000000ull;
+        bulk_load_hint(dst, d.p00, (uint32_t)(4 * C), &full[s], pol);
+        bulk_load_hint(dst + C, d.p01, (uint32_t)(4 * C), &full[s], pol);
+        bulk_load_hint(dst + 2 * C, d.p10, (uint32_t)(4 * C), &full[s], pol);
+        bulk_load_hint(dst + 3 * C, d.p11, (uint32_t)(4 * C), &full[s], pol);
       }
     }
   };
@@ -504,7 +508,10 @@ __global__ void __launch_bounds__(GB_THREADS, 1) gather_bulk_kernel(const __grid
           got.y = __shfl_xor_sync(0xffffffffu, give.y, 1);
           const uint4 outv = odd ? make_uint4(got.x, got.y, ml.x, ml.y) : make_uint4(mh.x, mh.y, got.x, got.y);
           const int c8 = c & ~7;
-          *reinterpret_cast<uint4*>(a.o.hi16 + 2 * ro + il_col(c8) + (odd ? 32 : 0)) = outv;
+          if (a.l2_hints)
+            st_global_v4_hint(a.o.hi16 + 2 * ro + il_col(c8) + (odd ? 32 : 0), outv, L2_EVICT_LAST);
+          else
+            *reinterpret_cast<uint4*>(a.o.hi16 + 2 * ro + il_col(c8) + (odd ? 32 : 0)) = outv;
         } else {
           *reinterpret_cast<uint2*>(a.o.hi16 + ro + c) = *reinterpret_cast<uint2*>(hh);
           *reinterpret_cast<uint2*>(a.o.lo16 + ro + c) = *reinterpret_cast<uint2*>(ll);
@@ -943,6 +950,7 @@ static int launch_gather_fast(int fmt, const SetTable& tab, int nsets, int B, in
     ga.total_rows = (long long)nsets * B * Prows; ga.eps = eps;
     DG_REQUIRE(ga.total_rows < (1LL << 31), DG_ERR_UNSUPPORTED, "gather: too many panel rows");
     ga.dbg = getenv("DEPTHG_B200_GATHER_DBG") ? atoi(getenv("DEPTHG_B200_GATHER_DBG")) : 0;
+    ga.l2_hints = getenv("DEPTHG_B200_L2HINTS") && getenv("DEPTHG_B200_L2HINTS")[0] == '1';
     const int npanels = nsets * B;             // a CTA's row range must hold at least one whole panel
     const int grid = npanels < (int)sms ? npanels : (int)sms;
     DG_PRE(st);

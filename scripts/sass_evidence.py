@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Count the Blackwell-native SASS mnemonics per kernel of the built library (B200_PROFILING.md, "What proves a
-Blackwell-native kernel"): UTC*MMA = tcgen05.mma, LDTM/STTM = tcgen05.ld/st, UTMALDG/UTMASTG = TMA tensor copies,
+Blackwell-native kernel"): UTC*MMA = tcgen05.mma, LDTM/STTM = tcgen05.ld/st, UTMALDG/UTMASTG = TMA tensor copies, UBLKCP = cp.async.bulk (1-D bulk copy),
 UTCBAR = tcgen05.commit, SYNCS = mbarrier ops, HMMA = legacy mma.sync (must be 0).  Writes a table to stdout."""
 import collections
 import re
@@ -10,7 +10,7 @@ import sys
 lib = sys.argv[1] if len(sys.argv) > 1 else "depthg_b200/libdepthg_b200.so"
 sass = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True, check=True).stdout
 WANT = [("UTC*MMA", r"\bUTC[A-Z]*MMA\b"), ("LDTM", r"\bLDTM\b"), ("STTM", r"\bSTTM\b"), ("UTMALDG", r"\bUTMALDG\b"),
-        ("UTMASTG", r"\bUTMASTG\b"), ("UTCBAR", r"\bUTCBAR\b"), ("SYNCS", r"\bSYNCS\b"), ("HMMA", r"\bHMMA\b"),
+        ("UTMASTG", r"\bUTMASTG\b"), ("UBLKCP", r"\bUBLKCP\b"), ("UTCBAR", r"\bUTCBAR\b"), ("SYNCS", r"\bSYNCS\b"), ("HMMA", r"\bHMMA\b"),
         ("REDUX", r"\bREDUX\b"), ("LDGSTS", r"\bLDGSTS\b")]
 counts = collections.OrderedDict()
 cur = None
@@ -23,7 +23,7 @@ for line in sass.splitlines():
         continue
     if cur is None:
         continue
-    counts[cur]["instr"] += bool(re.search(r"/\*[0-9a-f]{4}\*/", line))
+    counts[cur]["instr"] += bool(re.search(r"/\*[0-9a-f]{4,}\*/", line))
     for key, pat in WANT:
         if re.search(pat, line):
             counts[cur][key] += 1

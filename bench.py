@@ -17,9 +17,11 @@ double-buffered and a serialised loop, both reported), ``cpu_baseline`` (oracle 
 ``reference_ops_on_gpu`` (the reference's op sequence as stock torch ops on this GPU), ``cuda_graph`` (same step,
 no host work) and ``torch_negative_sampler`` (same step with the reference's randperm stream), ``knn`` (the precompute_knns build, query-sharded at N > 1; ``parity_checked`` = the timed
 result against the oracle on sampled rows and, at N > 1, against a one-GPU build) and ``probes`` (fused probe losses vs the trainer's torch op sequence).  At N > 1 every step is followed by the
-all-reduce of the trainable-head gradient (729 012 floats), replayed as a captured NCCL graph in stream order
-(DEPTHG_BENCH_ALLREDUCE = fps | inline | graph | graph_hp | async | none; fps = on the sampler's side stream,
-underneath the next step's FPS kernel).
+all-reduce of the trainable-head gradient (729 012 floats)
+(DEPTHG_BENCH_ALLREDUCE = symm | symm_inline | fps | inline | graph | graph_hp | async | none; symm (default) = torch's
+symmetric-memory multimem / two-shot all-reduce on a side stream underneath the next step's FPS kernel - measured at
+N = 8: 0.260 ms/step vs 0.298 with the NCCL all-reduce in the same place and 0.258 on one GPU; fps = the NCCL
+all-reduce, captured once and replayed there).
 """
 from __future__ import annotations
 
@@ -432,15 +434,41 @@ def main():
     # Measured at N=8 (ms/step): graph 0.505, graph_hp 0.432, inline 0.344 - the all-reduce is latency-bound
     # (2.9 MB over NVSwitch) and its spinning CTAs fight the SM-filling step kernels when overlapped, so the
     # default runs it in stream order.
-    # "fps" (default) = replayed on a side stream after backward i; step i+1's forward waits for it between its FPS
+    # "symm" (default) = the symmetric-memory all-reduce, else "fps" = the captured NCCL one, on a side stream after backward i; step i+1's forward waits for it between its FPS
     # kernel and its gathers (loss_fn.wait_after_fps): the all-reduce runs underneath step i+1's FPS kernel (2B CTAs on
     # a 148-SM GPU) and the sampler draw, and is over before the SM-filling gathers start - overlap without contention.
-    ar_mode = os.environ.get("DEPTHG_BENCH_ALLREDUCE", "fps") if world > 1 else "none"
+    ar_mode = os.environ.get("DEPTHG_BENCH_ALLREDUCE", "symm") if world > 1 else "none"
     ar_stream = ar_graph = None
     ar_done = torch.cuda.Event()
     ar_inline = ar_mode == "inline"          # replay on the compute stream: no overlap, no SM contention
     ar_fps = ar_mode == "fps"                # replay on the sampler's side stream, under the next step's FPS
     ar_hp = ar_mode in ("graph_hp",)         # side stream with high priority
+    ar_symm = None
+    if ar_mode in ("symm", "symm_inline"):
+        # the same all-reduce on torch's symmetric-memory kernels (NVLS multimem when the fabric has it, else two-shot
+        # over peer pointers): one small kernel instead of NCCL's protocol - latency is what matters at 2.9 MB
+        ar_fps = ar_mode == "symm"
+        try:
+            import torch.distributed._symmetric_memory as symm
+            gname = dist.group.WORLD.group_name
+            hg = symm.empty(HEAD_GRAD_FLOATS, dtype=torch.float32, device=dev)
+            hg.zero_()
+            hdl = symm.rendezvous(hg, gname)
+            opname = "multimem_all_reduce_" if hdl.has_multicast_support else "two_shot_all_reduce_"
+            op = getattr(torch.ops.symm_mem, opname)
+            op(hg, "sum", gname)
+            torch.cuda.synchronize()
+            head_grad, ar_symm = hg, (lambda: op(hg, "sum", gname))
+            ar_stream = torch.cuda.Stream(device=dev)
+            ok = 1.0
+        except Exception:  # noqa: BLE001
+            ok = 0.0
+        flags = torch.tensor([ok], device=dev)
+        dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+        if flags.item() == 0.0:
+            ar_symm, ar_mode, ar_fps = None, "fps", True
+        else:
+            ar_mode = "symm:" + opname
     if ar_mode in ("graph", "graph_hp", "inline", "fps"):
         ar_mode = "graph"
         try:
@@ -469,6 +497,14 @@ def main():
             pending[0] = dist.all_reduce(head_grad, async_op=True)
         elif ar_mode == "graph" and ar_inline:
             ar_graph.replay()
+        elif ar_symm is not None and ar_fps:
+            ar_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(ar_stream):
+                ar_symm()
+                ar_done.record(ar_stream)
+            loss_fn.wait_after_fps = ar_done
+        elif ar_symm is not None:
+            ar_symm()
         elif ar_mode == "graph" and ar_fps:
             ar_stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(ar_stream):

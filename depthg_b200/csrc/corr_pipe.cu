@@ -78,19 +78,24 @@ struct PipeParams {
 };
 
 struct Item {
-  int k, b, ti, tj, kb;
+  int k, b, ti, tj, kb, pidx;
   bool fsame, csame, depth;   // feature operands identical / code operands identical (diagonal tile of a self pair) / depth round
 };
 
 __device__ __forceinline__ Item decode_item(const PipeParams& prm, int it) {
   Item w;
   const int nt2 = prm.nt * prm.nt;
-  w.kb = it / nt2;
-  const int r = it - w.kb * nt2;
+  // Pair-major (the seven CTAs that share an image's first operand are spread over time: image-major order, where
+  // they fetch it at the same moment, measured 5 us slower), LAST image first: the gathers wrote the panels image by
+  // image, so the last images' panels are the ones still in L2.
+  const int g = it / nt2;                        // (pair, image) group
+  const int r = it - g * nt2;
   w.ti = r / prm.nt;
   w.tj = r - w.ti * prm.nt;
-  w.k = w.kb / prm.B;
-  w.b = w.kb - w.k * prm.B;
+  w.k = g / prm.B;
+  w.b = prm.B - 1 - (g - w.k * prm.B);
+  w.kb = w.k * prm.B + w.b;
+  w.pidx = w.kb * nt2 + r;                       // canonical (pair-major) index of the item's partial sums
   w.fsame = prm.fs1[w.k] == prm.fs2[w.k] && w.ti == w.tj;
   w.csame = w.k == 0 && w.ti == w.tj;
   w.depth = prm.has_depth && w.k == 0;
@@ -566,7 +571,7 @@ __global__ void __launch_bounds__(CP_THREADS, 1) corr_pipe_kernel(const __grid_c
           float t = 0.f;
 #pragma unroll
           for (int w8 = 0; w8 < 8; ++w8) t += s_red[w8][lane];
-          prm.partials[(size_t)it * 4 + lane] = t;
+          prm.partials[(size_t)w.pidx * 4 + lane] = t;
         }
         // fused finalize: the CTA that completes the last item folds all partial sums into the 8 output scalars.
         // __syncwarp orders the four partial stores before lane 0's acq_rel counter increment, which publishes them

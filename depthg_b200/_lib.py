@@ -108,7 +108,7 @@ class LossIO(C.Structure):
                 ("code_pos_strides", _i64x4), ("depth", _vp), ("depth_pos", _vp), ("coords", _vp), ("perms", _vp),
                 ("arena", _vp), ("out8", _vp), ("cd_out", _vp), ("loss_out", _vp), ("dd_out", _vp), ("fd_dbg", _vp), ("aug_feats", _vp), ("aug_feats_strides", _i64x4),
                 ("perms_ready", _vp), ("perm_seed", C.c_ulonglong), ("perm_offset", C.c_ulonglong),
-                ("gen_perms", C.c_int)]
+                ("gen_perms", C.c_int), ("clear", _vp * 2), ("clear_bytes", C.c_size_t * 2)]
 
 
 class LossGrads(C.Structure):

@@ -25,9 +25,10 @@ namespace dg {
 
 constexpr int FPS_THREADS = 256;  // setup (staging, pooling, lifting) and emission threads; the rounds use the first RT of them
 constexpr int FPS_WARPS = FPS_THREADS / 32;
-// measured on B200 (28x28 grid, S=11): RT=256 44.2 us, 128 45.4, 64 70.4, 32 76.0 per launch: the round is bound by
-// the redux -> barrier -> redux chain, not by the per-point arithmetic; folding the warp candidates with a compare
-// tree instead of the second redux pair was slower (55.9 us at RT=256).
+// measured on B200 (28x28 grid, S=11, one image per CTA; scripts/micro/fps_micro.cu): cycles per round 350 at RT=256,
+// 468 at 128, 367 at 512, 576 at 64 — a warp issues one instruction every other cycle, so fewer round threads pay in
+// issue slots what they save on the barrier; the floor of the chain is LDS 29 + redux pair 49 + STS/BAR/LDS 59 +
+// redux pair 42 cycles.
 constexpr int FPS_DEFAULT_RT = 256;  // round threads for the <= 896-point case (see fps_rounds)
 
 // s = d / max(|d|, eps) of the align_corners=True bilinear resample of one [Hd,Wd] image at point p of the SxS grid
@@ -49,70 +50,108 @@ __device__ __forceinline__ float depth_sign_value(const float* d, int Hd, int Wd
 
 // STAGE: the whole [Hd,Wd] depth image is first copied into shared memory with 16-byte cp.async
 // (every load in flight at once), so the pooling reads never wait on DRAM one window row at a time.
-// The S*S-1 selection rounds, run by the first RT threads of the CTA (RT = 32, 64 or 128): thread t owns points
-// t, t+RT, ... (PR per thread, in registers).  Fewer round threads = more points per thread but a shorter
-// critical path per round (no cross-warp exchange at RT = 32; a 2-candidate compare at RT = 64).
+
+// Packed fp32 pairs (FADD2 / FMUL2 of sm_100): two IEEE-rounded operations per instruction, bit-identical to the scalar
+// ones.  Only subtraction and multiplication are packed: ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2
+// (ONE rounding) whatever -fmad says, which would break the bit-exact distances, so the two additions stay scalar
+// (scripts/sass_evidence.py checks that no FFMA is left in this kernel's round loop).
+__device__ __forceinline__ unsigned long long f2_pack(float a, float b) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(unsigned long long v, float& a, float& b) {
+  asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long f2_sub(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long f2_sqr(unsigned long long a) {
+  unsigned long long r;
+  asm("mul.rn.f32x2 %0, %1, %1;" : "=l"(r) : "l"(a));
+  return r;
+}
+
+// The S*S-1 selection rounds, run by the first RT threads of the CTA: thread t owns points t, t+RT, ... (PR per thread,
+// in registers as packed pairs).  Per round (measured on B200, scripts/micro/fps_micro.cu: 350 cycles at RT = 256 /
+// PR = 4 against 588 for the round-1 loop):
+//   * key = min(key, int view of the distance) as a SIGNED integer minimum: a point that can no longer be picked needs no
+//     test and no marking, because the distance of a picked point to itself is exactly +0, so its key drops to 0 in the
+//     round after its pick and can only win again when every remaining key is 0 too (coincident points) — that case
+//     (block maximum == 0) takes a slow path that consults the taken flags, like np.delete does in the reference;
+//   * warp argmax = redux.max of the key, then redux.min of the lowest owned index holding that key; the RT/32 warp
+//     results meet in shared memory as one 8-byte word each behind ONE named barrier and every warp folds them with the
+//     same two redux ops.
 template <int PR, int RT>
 __device__ __forceinline__ void fps_rounds(const float* sX, const float* sY, const float* sZ, unsigned char* sTaken,
-                                           int npts, int nsel, int (*s_key)[FPS_WARPS], int (*s_idx)[FPS_WARPS]) {
+                                           int npts, int nsel, int2 (*s_kv)[FPS_WARPS]) {
   constexpr int RW = RT / 32;
+  static_assert(PR % 2 == 0 && RW <= FPS_WARPS && (RW & (RW - 1)) == 0, "fps_rounds: packed pairs, power-of-two warps");
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  float X[PR], Y[PR], Z[PR];
-  int key[PR];  // int view of the running min distance; -1 once taken (or not a point)
+  unsigned long long X2[PR / 2], Y2[PR / 2], Z2[PR / 2];
+  int key[PR];  // int view of the running min distance; -1 = not a point
 #pragma unroll
-  for (int j = 0; j < PR; ++j) {
-    const int i = j * RT + tid;
-    const bool ok = i < npts;
-    X[j] = ok ? sX[i] : 0.f;
-    Y[j] = ok ? sY[i] : 0.f;
-    Z[j] = ok ? sZ[i] : 0.f;
-    key[j] = ok && i != 0 ? 0x7f800000 : -1;  // +inf; point 0 is already taken
+  for (int j = 0; j < PR; j += 2) {
+    const int i0 = j * RT + tid, i1 = i0 + RT;
+    const bool ok0 = i0 < npts, ok1 = i1 < npts;
+    X2[j / 2] = f2_pack(ok0 ? sX[i0] : 0.f, ok1 ? sX[i1] : 0.f);
+    Y2[j / 2] = f2_pack(ok0 ? sY[i0] : 0.f, ok1 ? sY[i1] : 0.f);
+    Z2[j / 2] = f2_pack(ok0 ? sZ[i0] : 0.f, ok1 ? sZ[i1] : 0.f);
+    key[j] = ok0 ? 0x7f800000 : -1;  // +inf; point 0 (the first pick) drops to 0 in round 1
+    key[j + 1] = ok1 ? 0x7f800000 : -1;
   }
   int last = 0;
   for (int r = 1; r < nsel; ++r) {
     const float lx = sX[last], ly = sY[last], lz = sZ[last];
-    int bk = -1, bi = 0x7fffffff;
+    const unsigned long long lx2 = f2_pack(lx, lx), ly2 = f2_pack(ly, ly), lz2 = f2_pack(lz, lz);
+    int bk = -1;
 #pragma unroll
-    for (int j = 0; j < PR; ++j) {  // branch-free so the PR independent chains interleave
-      const float dx = __fsub_rn(lx, X[j]), dy = __fsub_rn(ly, Y[j]), dz = __fsub_rn(lz, Z[j]);
-      const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-      const int kj = key[j];
-      const int k = kj < 0 ? -1 : min(kj, __float_as_int(d));  // non-negative floats: int order == float order
-      key[j] = k;
-      const bool better = k > bk;  // strict: the lowest index wins ties inside a thread (j ascending)
-      bk = better ? k : bk;
-      bi = better ? j * RT + tid : bi;
+    for (int j = 0; j < PR; j += 2) {
+      float xx0, xx1, yy0, yy1, zz0, zz1;
+      f2_unpack(f2_sqr(f2_sub(lx2, X2[j / 2])), xx0, xx1);
+      f2_unpack(f2_sqr(f2_sub(ly2, Y2[j / 2])), yy0, yy1);
+      f2_unpack(f2_sqr(f2_sub(lz2, Z2[j / 2])), zz0, zz1);
+      const float d0 = __fadd_rn(__fadd_rn(xx0, yy0), zz0), d1 = __fadd_rn(__fadd_rn(xx1, yy1), zz1);
+      key[j] = min(key[j], __float_as_int(d0));  // non-negative floats: int order == float order; -1 stays -1
+      key[j + 1] = min(key[j + 1], __float_as_int(d1));
+      bk = max(bk, max(key[j], key[j + 1]));
     }
     const int wk = __reduce_max_sync(0xffffffffu, bk);
-    const int wi = __reduce_min_sync(0xffffffffu, bk == wk ? bi : 0x7fffffff);
+    int bi = 0x7fffffff;
+#pragma unroll
+    for (int j = PR - 1; j >= 0; --j) bi = key[j] == wk ? j * RT + tid : bi;  // lowest owned index holding the maximum
+    const int wi = __reduce_min_sync(0xffffffffu, bi);
     if (RW == 1) {
       last = wi;
+      if (wk == 0) {  // coincident points only: first index that is not taken yet (np.delete semantics)
+        int fi = 0x7fffffff;
+#pragma unroll
+        for (int j = PR - 1; j >= 0; --j)
+          if (key[j] == 0 && !sTaken[j * RT + tid]) fi = j * RT + tid;
+        last = __reduce_min_sync(0xffffffffu, fi);
+      }
     } else {
       const int buf = r & 1;
-      if (lane == 0) {
-        s_key[buf][warp] = wk;
-        s_idx[buf][warp] = wi;
-      }
+      if (lane == 0) s_kv[buf][warp] = make_int2(wk, wi);
       asm volatile("bar.sync 1, %0;" ::"n"(RT) : "memory");
-      if (RW == 2) {
-        const int k0 = s_key[buf][0], i0 = s_idx[buf][0], k1 = s_key[buf][1], i1 = s_idx[buf][1];
-        last = (k0 > k1 || (k0 == k1 && i0 < i1)) ? i0 : i1;
-      } else {  // every warp folds the RW candidates with the same two redux ops
-        const int ck = lane < RW ? s_key[buf][lane] : -1;
-        const int ci = lane < RW ? s_idx[buf][lane] : 0x7fffffff;
-        const int gk = __reduce_max_sync(0xffffffffu, ck);
-        last = __reduce_min_sync(0xffffffffu, ck == gk ? ci : 0x7fffffff);
-      }
-    }
-    if (((last % RT) >> 5) == warp) {  // warp-uniform: only the owner's warp enters
-      if ((last % RT) == tid) {
-        const int j = last / RT;
+      const int2 c = s_kv[buf][lane & (RW - 1)];
+      const int gk = __reduce_max_sync(0xffffffffu, c.x);
+      last = __reduce_min_sync(0xffffffffu, c.x == gk ? c.y : 0x7fffffff);
+      if (gk == 0) {  // block-uniform: coincident points only
+        int fi = 0x7fffffff;
 #pragma unroll
-        for (int jj = 0; jj < PR; ++jj)
-          if (jj == j) key[jj] = -1;
-        sTaken[last] = 1;
+        for (int j = PR - 1; j >= 0; --j)
+          if (key[j] == 0 && !sTaken[j * RT + tid]) fi = j * RT + tid;
+        fi = __reduce_min_sync(0xffffffffu, fi);
+        asm volatile("bar.sync 1, %0;" ::"n"(RT) : "memory");  // everybody has read slot `buf`
+        if (lane == 0) s_kv[buf][warp].y = fi;
+        asm volatile("bar.sync 1, %0;" ::"n"(RT) : "memory");
+        last = __reduce_min_sync(0xffffffffu, s_kv[buf][lane & (RW - 1)].y);
       }
     }
+    if (tid == 0) sTaken[last] = 1;  // read by the slow path (two barriers later at the earliest) and by the emission
   }
 }
 
@@ -131,8 +170,7 @@ __global__ void __launch_bounds__(FPS_THREADS) fps_kernel(const float* __restric
   float* sZ = sY + npad;
   unsigned char* sTaken = reinterpret_cast<unsigned char*>(sZ + npad);
   float* sImg = reinterpret_cast<float*>(sTaken + ((npts + 15) & ~15));
-  __shared__ int s_key[2][FPS_WARPS];
-  __shared__ int s_idx[2][FPS_WARPS];
+  __shared__ int2 s_kv[2][FPS_WARPS];
   __shared__ int s_scan[FPS_WARPS];
 
   pdl_trigger();
@@ -203,7 +241,7 @@ __global__ void __launch_bounds__(FPS_THREADS) fps_kernel(const float* __restric
   __syncthreads();
   if (tid == 0) sTaken[0] = 1;  // point 0 is the first pick
 
-  if (tid < RT) fps_rounds<PR, RT>(sX, sY, sZ, sTaken, npts, nsel, s_key, s_idx);
+  if (tid < RT) fps_rounds<PR, RT>(sX, sY, sZ, sTaken, npts, nsel, s_kv);
   __syncthreads();
 
   // Raster-order emission: each thread scans a contiguous chunk of point indices.
@@ -289,20 +327,18 @@ int launch_fps(const float* depth_a, const float* depth_b, int B, int Hd, int Wd
     launch_pdl(fps_kernel<PPT, ST, RTV, PRV>, dim3(nimg + (pj.n > 0 ? 1 : 0)), dim3(FPS_THREADS), smem, st, depth_a,     \
                depth_b, B, Hd, Wd, H, W, S * S, factor, far_plane, affine, coords, idx, dsign, S, sign_pitch, sign_eps, pj); \
   } while (0)
-  static int rt_env = -1;  // DEPTHG_B200_FPS_RT = 32 | 64 | 128 | 256 round threads (experiments); default FPS_DEFAULT_RT
+  static int rt_env = -1;  // DEPTHG_B200_FPS_RT = 128 | 256 round threads (experiments); default FPS_DEFAULT_RT
   if (rt_env < 0) {
     const char* e = getenv("DEPTHG_B200_FPS_RT");
     rt_env = e ? atoi(e) : 0;
   }
   if (npts <= 896) {  // the 28x28 grid of the reference (784 points) lives here
-    const int rt = (rt_env == 32 || rt_env == 64 || rt_env == 128 || rt_env == 256) ? rt_env : FPS_DEFAULT_RT;
+    const int rt = rt_env == 128 ? 128 : FPS_DEFAULT_RT;
     if (stage) {
-      if (rt == 32) DG_FPS_LAUNCH(4, true, 32, 28);
-      else if (rt == 64) DG_FPS_LAUNCH(4, true, 64, 14);
-      else if (rt == 128) DG_FPS_LAUNCH(4, true, 128, 7);
+      if (rt == 128) DG_FPS_LAUNCH(4, true, 128, 8);
       else DG_FPS_LAUNCH(4, true, 256, 4);
     } else {
-      if (rt == 256) DG_FPS_LAUNCH(4, false, 256, 4); else DG_FPS_LAUNCH(4, false, 128, 7);
+      if (rt == 128) DG_FPS_LAUNCH(4, false, 128, 8); else DG_FPS_LAUNCH(4, false, 256, 4);
     }
   } else if (npts <= 8 * FPS_THREADS) {
     if (stage) DG_FPS_LAUNCH(8, true, 256, 8); else DG_FPS_LAUNCH(8, false, 256, 8);

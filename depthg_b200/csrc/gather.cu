@@ -630,6 +630,16 @@ __global__ void __launch_bounds__(GF_THREADS)
     pair_dots_body(job, (int)blockIdx.x);
     return;
   }
+  // the zero fill of the caller's gradient buffers (dg_loss_io_t::clear) rides here: a few 16-byte stores per thread
+  // in a latency-bound kernel instead of two fill launches between the forward and the backward
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    if (job.clr[q] == nullptr) continue;
+    const unsigned long long step = (unsigned long long)ncode_blocks * GF_THREADS;
+    for (unsigned long long i = (unsigned long long)((int)blockIdx.x - ndots) * GF_THREADS + threadIdx.x; i < job.clr_n16[q];
+         i += step)
+      job.clr[q][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   gather_code_body<R>(sets, B, C, H, W, coords, S, perms, eps, Prows, nsplit, o, (int)blockIdx.x - ndots);
 }
 

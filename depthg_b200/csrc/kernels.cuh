@@ -68,6 +68,8 @@ struct DotsJob {
   int* err;            // [4] error flag + completion counter
   int nsplit, npairs, B, ldf;
   int32_t fs1[DG_MAX_PAIRS], fs2[DG_MAX_PAIRS];
+  float4* clr[2];           // caller buffers the code-gather CTAs set to zero (dg_loss_io_t::clear), or null
+  unsigned long long clr_n16[2];  // their sizes in 16-byte units
 };
 
 // One 256-thread block per (pair k, image b); block 0 also clears the flags.

@@ -230,6 +230,16 @@ extern "C" int dg_loss_forward(const dg_loss_desc_t* d, const dg_loss_io_t* io, 
                        st);
     if (rc != DG_OK) return rc;
     DotsJob job;
+    memset(&job, 0, sizeof job);
+    for (int q = 0; q < 2; ++q) {   // the caller's buffers to clear: inside the code gather when it has a job slot
+      if (!io->clear[q] || !io->clear_bytes[q]) continue;
+      if (pl.kernel && reinterpret_cast<uintptr_t>(io->clear[q]) % 16 == 0 && io->clear_bytes[q] % 16 == 0) {
+        job.clr[q] = static_cast<float4*>(io->clear[q]);
+        job.clr_n16[q] = io->clear_bytes[q] / 16;
+      } else {
+        DG_CUDA_OK(cudaMemsetAsync(io->clear[q], 0, io->clear_bytes[q], st));
+      }
+    }
     if (pl.kernel) {   // the pair dots / flag reset of the tcgen05 kernel ride along as extra CTAs of the code gather
       job.fmean = fmean;
       umma_ws_layout(A + pl.ws, &job.err, &job.dots);

@@ -52,12 +52,15 @@ class CorrLossFn : public torch::autograd::Function<CorrLossFn> {
                                c10::optional<Tensor> depth, c10::optional<Tensor> depth_pos,
                                c10::optional<Tensor> coords, c10::optional<Tensor> perms,
                                c10::optional<Tensor> aug_feats, std::vector<int64_t> ints, std::vector<double> shifts,
-                               bool materialize, bool want_fd, int64_t perms_event) {
+                               bool materialize, bool want_fd, bool prezero_grads, int64_t perms_event) {
     TORCH_CHECK((ints.size() == 10 || ints.size() == 12) && shifts.size() == 4,
                 "corr_loss: ints[10 or 12] / shifts[4] expected");
     dg_loss_desc_t d = make_desc(ints, shifts);
     dg_loss_plan_t plan;
     check(dg_loss_plan(&d, &plan), "dg_loss_plan");
+    // Undefined upstream gradients stay undefined: the default would hand backward() a ZERO tensor for every output
+    // nobody differentiated — including the non-differentiable 151 MB arena, i.e. a 42 us fill kernel per step.
+    ctx->set_materialize_grads(false);
     const c10::cuda::CUDAGuard guard(feats.device());
     auto stream = c10::cuda::getCurrentCUDAStream(feats.device().index());
     const auto u8 = feats.options().dtype(torch::kUInt8);
@@ -90,6 +93,19 @@ class CorrLossFn : public torch::autograd::Function<CorrLossFn> {
       io.aug_feats = aug_feats->data_ptr<float>();
       fill_strides(io.aug_feats_strides, *aug_feats);
     }
+    // the gradient buffers of the coming backward are allocated here and zeroed inside the forward's code gather
+    // (dg_loss_io_t::clear): no fill launches between the correlation kernel and the backward kernel
+    Tensor d_code, d_code_pos;
+    if (prezero_grads) {   // the caller's grad mode (it is always off inside an autograd Function's forward)
+      if (code.requires_grad() && code.is_non_overlapping_and_dense()) {
+        d_code = torch::empty_strided(code.sizes(), code.strides(), f32);
+        io.clear[0] = d_code.data_ptr(); io.clear_bytes[0] = (size_t)d_code.numel() * sizeof(float);
+      }
+      if (code_pos.requires_grad() && code_pos.is_non_overlapping_and_dense()) {
+        d_code_pos = torch::empty_strided(code_pos.sizes(), code_pos.strides(), f32);
+        io.clear[1] = d_code_pos.data_ptr(); io.clear_bytes[1] = (size_t)d_code_pos.numel() * sizeof(float);
+      }
+    }
     io.perms_ready = reinterpret_cast<void*>(perms_event);
     if (ints.size() >= 12) {   // the forward draws the permutations itself into `perms`
       io.gen_perms = 1;
@@ -108,6 +124,8 @@ class CorrLossFn : public torch::autograd::Function<CorrLossFn> {
     ctx->saved_data["code_pos_strides"] = code_pos.strides().vec();
     ctx->saved_data["need_code"] = code.requires_grad();
     ctx->saved_data["need_code_pos"] = code_pos.requires_grad();
+    if (d_code.defined()) ctx->saved_data["d_code"] = d_code;            // consumed by the first backward
+    if (d_code_pos.defined()) ctx->saved_data["d_code_pos"] = d_code_pos;
 
     auto u = out8.unbind(0);
     // outputs: 4 differentiable scalars, out8, the arena, then only the optional tensors that exist, in the order
@@ -138,13 +156,23 @@ class CorrLossFn : public torch::autograd::Function<CorrLossFn> {
     Tensor d_code, d_code_pos;
     if (ctx->saved_data["need_code"].toBool()) {
       const auto st = ctx->saved_data["code_strides"].toIntVector();
-      d_code = torch::empty_strided(sizes, st, f32).zero_();
+      if (ctx->saved_data.count("d_code")) {   // pre-zeroed by the forward; a second backward (retain_graph) refills
+        d_code = ctx->saved_data["d_code"].toTensor();
+        ctx->saved_data.erase("d_code");
+      } else {
+        d_code = torch::empty_strided(sizes, st, f32).zero_();
+      }
       gr.d_code = d_code.data_ptr<float>();
       for (int i = 0; i < 4; ++i) gr.d_code_strides[i] = st[i];
     }
     if (ctx->saved_data["need_code_pos"].toBool()) {
       const auto st = ctx->saved_data["code_pos_strides"].toIntVector();
-      d_code_pos = torch::empty_strided(sizes, st, f32).zero_();
+      if (ctx->saved_data.count("d_code_pos")) {
+        d_code_pos = ctx->saved_data["d_code_pos"].toTensor();
+        ctx->saved_data.erase("d_code_pos");
+      } else {
+        d_code_pos = torch::empty_strided(sizes, st, f32).zero_();
+      }
       gr.d_code_pos = d_code_pos.data_ptr<float>();
       for (int i = 0; i < 4; ++i) gr.d_code_pos_strides[i] = st[i];
     }
@@ -154,7 +182,7 @@ class CorrLossFn : public torch::autograd::Function<CorrLossFn> {
     if (ctx->saved_data.count("coords")) io.coords = ctx->saved_data["coords"].toTensor().data_ptr<float>();
     if (ctx->saved_data.count("perms")) io.perms = ctx->saved_data["perms"].toTensor().data_ptr<int64_t>();
     check(dg_loss_backward(&d, &io, &gr, reinterpret_cast<dg_stream_t>(stream.stream())), "dg_loss_backward");
-    variable_list out(14);
+    variable_list out(15);
     out[2] = d_code;
     out[3] = d_code_pos;
     return out;
@@ -164,9 +192,9 @@ class CorrLossFn : public torch::autograd::Function<CorrLossFn> {
 std::vector<Tensor> corr_loss(Tensor feats, Tensor feats_pos, Tensor code, Tensor code_pos, c10::optional<Tensor> depth,
                               c10::optional<Tensor> depth_pos, c10::optional<Tensor> coords, c10::optional<Tensor> perms,
                               c10::optional<Tensor> aug_feats, std::vector<int64_t> ints, std::vector<double> shifts,
-                              bool materialize, bool want_fd, int64_t perms_event) {
+                              bool materialize, bool want_fd, bool prezero_grads, int64_t perms_event) {
   return CorrLossFn::apply(feats, feats_pos, code, code_pos, depth, depth_pos, coords, perms, aug_feats, ints, shifts,
-                           materialize, want_fd, perms_event);
+                           materialize, want_fd, prezero_grads, perms_event);
 }
 
 std::vector<int64_t> loss_plan(std::vector<int64_t> ints) {

@@ -383,6 +383,8 @@ class _CorrLossFn(torch.autograd.Function):
         dev = feats.device
         plan = _lib.LossPlan()
         check(lib.dg_loss_plan(C.byref(desc), C.byref(plan)), "dg_loss_plan")
+        # no zero tensors for outputs nobody differentiated (the arena alone would be a 151 MB fill per step)
+        ctx.set_materialize_grads(False)
         B, S, nneg, npairs = desc.B, desc.S, desc.neg_samples, plan.npairs
         P = S * S
         has_depth = bool(desc.flags & _lib.FLAG_DEPTH_TERM)
@@ -675,6 +677,7 @@ class ContrastiveCorrelationLoss(nn.Module):
                 ints = ints + (seed, perm_gen[1])
             res = binding.corr_loss(orig_feats, orig_feats_pos, orig_code, orig_code_pos, depth, depth_pos, coords,
                                     perms, aug_feats, ints, shifts, bool(self.materialize_cd), False,
+                                    torch.is_grad_enabled(),   # gradient buffers zeroed inside the forward's launches
                                     perms_event.cuda_event if perms_event is not None else 0)
             intra, inter, neg, dloss, out8, coords_src = res[:6]
             cd_out, loss_out = (res[6], res[7]) if self.materialize_cd else (None, None)

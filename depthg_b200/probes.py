@@ -59,11 +59,14 @@ class _LinearProbeCEFn(torch.autograd.Function):
                                             stream_ptr(code.device.index)), "dg_linear_probe_ce")
         ctx.save_for_backward(dw, db)
         ctx.wshape = weight.shape
+        ctx.set_materialize_grads(False)
         return loss
 
     @staticmethod
     def backward(ctx, g):
         dw, db = ctx.saved_tensors
+        if g is None:
+            return None, None, None, None
         return (None, None if dw is None else (dw * g).reshape(ctx.wshape), None if db is None else db * g, None)
 
 
@@ -108,12 +111,13 @@ class _ClusterProbeFn(torch.autograd.Function):
         ctx.save_for_backward(dc)
         probs = probs.permute(0, 3, 1, 2)
         ctx.mark_non_differentiable(probs)
+        ctx.set_materialize_grads(False)   # no [B,N,h,w] zero tensor for the non-differentiable probs
         return loss, probs
 
     @staticmethod
     def backward(ctx, g, _gp):
         (dc,) = ctx.saved_tensors
-        return None, None if dc is None else dc * g
+        return None, None if (dc is None or g is None) else dc * g
 
 
 class ClusterLookup(nn.Module):

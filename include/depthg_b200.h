@@ -257,6 +257,11 @@ typedef struct dg_loss_io {
      nothing on the step's critical path.  dg_loss_backward reads the same buffer. */
   unsigned long long perm_seed, perm_offset;
   int gen_perms;
+  /* Optional: up to two caller buffers the forward sets to zero on its stream — meant for the d_code / d_code_pos
+     buffers of the coming dg_loss_backward (which accumulates into them with atomics), so that the caller needs no
+     fill launches between forward and backward.  The work rides in the code-gather launch.  NULL / 0 = nothing. */
+  void* clear[2];
+  size_t clear_bytes[2];
 } dg_loss_io_t;
 
 typedef struct dg_loss_grads {

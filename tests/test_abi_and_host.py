@@ -234,3 +234,30 @@ def test_nns_file_contract_round_trips_to_the_dataset_loader(tmp_path):
     # int32 / CUDA-produced tensors are widened to the int64 the reference stores
     save_nns(path, nn.to(torch.int32))
     assert np.load(path)["nns"].dtype == np.int64
+
+
+def test_fps_round_loop_has_no_fused_multiply_add():
+    """The FPS distances must round like NumPy's (a-b)**2 summed left to right: one rounding per operation.  ptxas
+    contracts packed mul.rn.f32x2 + add.rn.f32x2 into FFMA2 whatever -fmad says, so the kernel keeps its additions
+    scalar; this checks the SASS of every fps_kernel instance: between the packed subtractions of a round and the
+    redux that ends it there is no fp32 fused multiply-add (FFMA / FFMA2)."""
+    import shutil
+    obj = os.path.join(ROOT, "depthg_b200", "csrc", "build", "fps.o")
+    if shutil.which("cuobjdump") is None or not os.path.isfile(obj):
+        pytest.skip("needs cuobjdump and the object file of the in-tree build")
+    sass = subprocess.run(["cuobjdump", "-sass", obj], capture_output=True, text=True, check=True).stdout
+    funcs = re.split(r"\n\s*Function : ", sass)[1:]
+    checked = 0
+    for f in funcs:
+        name = f.split("\n", 1)[0]
+        if "fps_kernel" not in name:
+            continue
+        ops = [m.group(1) for m in re.finditer(r"/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d\s+)?([A-Z][A-Z0-9_.]*)", f)]
+        first = next(i for i, o in enumerate(ops) if o.startswith("FADD2"))
+        last = max(i for i, o in enumerate(ops) if o.startswith("CREDUX"))
+        assert first < last, name
+        loop = ops[first:last]
+        assert any(o.startswith("FMUL2") for o in loop), name
+        assert not [o for o in loop if o.startswith("FFMA")], name
+        checked += 1
+    assert checked >= 4

@@ -587,6 +587,50 @@ def test_grad_tensors_backprop_equals_weighted_sum_backward():
     assert rel_err(grads[0][1].cpu().numpy(), grads[1][1].cpu().numpy()) < 1e-6
 
 
+def test_partial_and_repeated_backward_use_fresh_zeroed_gradient_buffers():
+    """The forward pre-zeroes the code-gradient buffers of the FIRST backward inside its own launches and leaves
+    undefined upstream gradients undefined (no zero tensors materialised for unused outputs): (a) backprop through one
+    loss only == the same loss with explicit zero weights for the others; (b) a second backward over a retained graph
+    accumulates exactly one more copy of the gradient; (c) a forward under no_grad still returns the same values."""
+    from depthg_b200.modules import ContrastiveCorrelationLoss
+    cfg, t = cases.make_loss_inputs("small_fps")
+    a = {k: t[k].to(dev()) for k in ("feats", "feats_pos", "depth", "depth_pos")}
+
+    def run(how):
+        fn = ContrastiveCorrelationLoss(cfg)
+        pit = iter(t["perms"].to(dev()))
+        fn.perm_fn = lambda B, device: next(pit).clone()
+        code = t["code"].to(dev()).requires_grad_(True)
+        code_pos = t["code_pos"].to(dev()).requires_grad_(True)
+        if how == "nograd":
+            with torch.no_grad():
+                out = fn(a["feats"], a["feats_pos"], None, None, code, code_pos, a["depth"], a["depth_pos"])
+            return [float(out[i].mean()) for i in (0, 2, 4, 6)], None, None
+        out = fn(a["feats"], a["feats_pos"], None, None, code, code_pos, a["depth"], a["depth_pos"])
+        one, zero = torch.ones((), device=dev()), torch.zeros((), device=dev())
+        if how == "inter_only":
+            out[2].backward()
+        elif how == "inter_zero_weights":
+            torch.autograd.backward([out[0], out[2], out[4].mean(), out[6]], grad_tensors=[zero, one, zero, zero])
+        elif how == "twice":
+            L = out[0] + out[2] + out[4].mean() + out[6]
+            L.backward(retain_graph=True)
+            L.backward()
+        else:
+            (out[0] + out[2] + out[4].mean() + out[6]).backward()
+        torch.cuda.synchronize()
+        return [float(out[i].mean()) for i in (0, 2, 4, 6)], code.grad.cpu().numpy(), code_pos.grad.cpu().numpy()
+
+    v_once, g_once, gp_once = run("once")
+    v_ng, _, _ = run("nograd")
+    assert v_ng == v_once
+    _, g1, gp1 = run("inter_only")
+    _, g2, gp2 = run("inter_zero_weights")
+    assert np.abs(g1).max() > 0 and rel_err(g1, g2) < 1e-6 and rel_err(gp1, gp2) < 1e-6
+    _, g_twice, gp_twice = run("twice")
+    assert rel_err(g_twice, 2 * g_once) < 1e-6 and rel_err(gp_twice, 2 * gp_once) < 1e-6
+
+
 def test_graphed_super_perms_reproduce_the_eager_torch_stream():
     """The CUDA-graph replay of neg_samples x torch.randperm must give the eager calls' permutations
     (same seed -> same stream), call after call, and advance the generator identically."""

@@ -37,15 +37,22 @@ constexpr int KU_CAND = 32;
 // database rows (hi, lo).  BN = 256 loads the query chunk once per 256 database rows instead of once per 128 (25 % less
 // L2->SM operand traffic) and uses 32-wide K chunks (64-byte rows, SWIZZLE_64B): 4 stages of 48 KB in flight.
 // Besides the ring, shared memory holds the candidate lists: 128 rows x 32 entries x (value, index) = 32 KB.
-template <int BN> struct KuCfg {
-  static constexpr int KC = BN == 128 ? 64 : 32;                  // K elements per stage
-  static constexpr int QBYTES = 128 * KC * 2, DBYTES = BN * KC * 2;  // one bf16 panel chunk of the query / database tile
-  static constexpr int STAGE = 2 * QBYTES + 2 * DBYTES;
-  static constexpr int NSTAGE = BN == 128 ? 3 : 4;
+// TERMS = 3: bf16 hi/lo panels, sims = hh + hl + lh (fp32-grade, error bound ku_eps_unit);
+// TERMS = 1: the FAST pass of the precision ladder (SURVEY 7.1 iii): ONE fp16 panel, sims = h.h — a third of the MMAs
+//            and half of the operand bytes (a stage carries 64 K elements instead of 32, so the L2->SM stream that
+//            bounds the 3-term pass at ~10 TB/s halves) for an error bound 15x wider (ku_eps_unit_fast), which the
+//            re-rank absorbs: more candidates are ambiguous and get an exact fp32 dot product, and the certificate
+//            still decides row by row whether the candidate lists provably contain the exact top-k.
+template <int BN, int TERMS> struct KuCfg {
+  static constexpr int KC = (BN == 128 || TERMS == 1) ? 64 : 32;   // K elements per stage
+  static constexpr int QBYTES = 128 * KC * 2, DBYTES = BN * KC * 2;  // one 16-bit panel chunk of the query / database tile
+  static constexpr int STAGE = TERMS == 3 ? 2 * QBYTES + 2 * DBYTES : QBYTES + DBYTES;
+  static constexpr int NSTAGE = (BN == 128 && TERMS == 3) ? 3 : 4;
   static constexpr int LISTS = 4 * 32 * KU_CAND * 8;
   static constexpr int SMEM = NSTAGE * STAGE + LISTS + 1024 + 256;
 };
-static_assert(KuCfg<256>::SMEM <= 232448 && KuCfg<128>::SMEM <= 232448, "knn_umma_kernel: shared memory over the CTA limit");
+static_assert(KuCfg<256, 3>::SMEM <= 232448 && KuCfg<128, 3>::SMEM <= 232448 && KuCfg<256, 1>::SMEM <= 232448,
+              "knn_umma_kernel: shared memory over the CTA limit");
 // Bound on |approx - exact| of the 3-product bf16 split, as a multiple of |q| * max|d| (the row norms are measured by
 // split_rows_kernel, so un-normalised inputs get a proportionally wider bound instead of a silently wrong one):
 //   x = hi + lo + r with |lo| <= 2^-8 |x| and |r| <= 2^-8 |lo| <= 2^-16 |x| (bf16 keeps 8 significand bits), so
@@ -56,6 +63,17 @@ static_assert(KuCfg<256>::SMEM <= 232448 && KuCfg<128>::SMEM <= 232448, "knn_umm
 __host__ __device__ inline float ku_eps_unit(int F) {
   return 3.f * 1.52587890625e-5f + (3.f * (float)F / 16.f + 16.f) * 1.1920929e-7f;
 }
+
+// Fast pass (one fp16 panel): x = h + r with |r| <= 2^-11 |x| for normal fp16 values (11 significand bits) and
+// |r| <= 2^-25 absolutely below the normal range, so q.d - qh.dh = rq.d + qh.rd is at most
+//   (2 * 2^-11 + 2^-22) |q||d|  +  2^-25 sqrt(F) (|q| + |d|)        (Cauchy-Schwarz; the second term: subnormals)
+// plus the accumulation term (F / 16 + 16) * 2^-23 |q||d| of F / 16 instruction results.  Values of 65504 or more do
+// not convert: the re-rank refuses the fast result (every row goes to the exact kernel) when a squared norm exceeds
+// 2^30.  F = 768, unit norms: 9.9e-4.
+__host__ __device__ inline float ku_eps_unit_fast(int F) {
+  return 2.f * 4.8828125e-4f + 2.38418579e-7f + ((float)F / 16.f + 16.f) * 1.1920929e-7f;
+}
+__host__ __device__ inline float ku_eps_abs_fast(int F) { return 2.98023224e-8f * sqrtf((float)F); }
 
 struct KnnUmmaParams {
   CUtensorMap tm_qh, tm_ql, tm_dh, tm_dl;  // bf16 [rows, Fp], box 64 x 128, SWIZZLE_128B
@@ -73,6 +91,7 @@ struct KnnUmmaParams {
 
 // A warp per row: bf16 hi/lo panels (K padded with zeros to Fp), the row's squared norm (rownorm2, nullable) and the
 // maximum squared norm over all rows (maxnorm2_bits: the float's bit pattern, which orders like an int for x >= 0).
+template <bool FAST>   // FAST: one fp16 panel (hi); lo is not written
 __global__ void __launch_bounds__(256) split_rows_kernel(const float* __restrict__ x, int n, int F, int Fp,
                                                          __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
                                                          float* __restrict__ rownorm2, int* __restrict__ maxnorm2_bits) {
@@ -94,15 +113,25 @@ __global__ void __launch_bounds__(256) split_rows_kernel(const float* __restrict
 #pragma unroll
         for (int e = 0; e < 4; ++e) v[e] = c + e < F ? __ldg(xr + c + e) : 0.f;
       }
-      __nv_bfloat16 h[4], l[4];
+      if (FAST) {
+        __half h[4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        ss = fmaf(v[e], v[e], ss);
-        h[e] = __float2bfloat16_rn(v[e]);
-        l[e] = __float2bfloat16_rn(v[e] - __bfloat162float(h[e]));
+        for (int e = 0; e < 4; ++e) {
+          ss = fmaf(v[e], v[e], ss);
+          h[e] = __float2half_rn(v[e]);
+        }
+        *reinterpret_cast<uint2*>(hr + c) = *reinterpret_cast<uint2*>(h);
+      } else {
+        __nv_bfloat16 h[4], l[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          ss = fmaf(v[e], v[e], ss);
+          h[e] = __float2bfloat16_rn(v[e]);
+          l[e] = __float2bfloat16_rn(v[e] - __bfloat162float(h[e]));
+        }
+        *reinterpret_cast<uint2*>(hr + c) = *reinterpret_cast<uint2*>(h);
+        *reinterpret_cast<uint2*>(lr + c) = *reinterpret_cast<uint2*>(l);
       }
-      *reinterpret_cast<uint2*>(hr + c) = *reinterpret_cast<uint2*>(h);
-      *reinterpret_cast<uint2*>(lr + c) = *reinterpret_cast<uint2*>(l);
     }
     ss = warp_sum(ss);
     if (rownorm2 && lane == 0) rownorm2[r] = ss;
@@ -111,10 +140,11 @@ __global__ void __launch_bounds__(256) split_rows_kernel(const float* __restrict
   if (maxnorm2_bits && lane == 0 && wmax > 0.f) atomicMax(maxnorm2_bits, __float_as_int(wmax));
 }
 
-template <int BN>
+template <int BN, int TERMS>
 __global__ void __launch_bounds__(KU_THREADS, 1) knn_umma_kernel(const __grid_constant__ KnnUmmaParams prm) {
-  constexpr int KU_STAGE = KuCfg<BN>::STAGE, KU_NSTAGE = KuCfg<BN>::NSTAGE, KC = KuCfg<BN>::KC;
-  constexpr int QB = KuCfg<BN>::QBYTES, DB = KuCfg<BN>::DBYTES;
+  using Cfg = KuCfg<BN, TERMS>;
+  constexpr int KU_STAGE = Cfg::STAGE, KU_NSTAGE = Cfg::NSTAGE, KC = Cfg::KC;
+  constexpr int QB = Cfg::QBYTES, DB = Cfg::DBYTES;
   extern __shared__ uint8_t ku_raw[];
   // 1024-byte alignment for SWIZZLE_128B, computed as an offset so the pointer stays in the shared address space
   // (a round trip through uintptr_t makes every later access a generic LD/ST instead of LDS/STS)
@@ -122,7 +152,7 @@ __global__ void __launch_bounds__(KU_THREADS, 1) knn_umma_kernel(const __grid_co
   // candidate lists: per epilogue warp 32 slots x 32 rows of values, then of indices; slot e of row r lives at word
   // e * 32 + (r ^ e), which is conflict-free both for "every row scans slot e" and for "one row, all slots"
   float* lists = reinterpret_cast<float*>(ring + KU_NSTAGE * KU_STAGE);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + KU_NSTAGE * KU_STAGE + KuCfg<BN>::LISTS);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + KU_NSTAGE * KU_STAGE + Cfg::LISTS);
   uint64_t* full = bars;               // [<=4]
   uint64_t* empty = bars + 4;          // [<=4]
   uint64_t* tfull = bars + 8;          // [2] accumulator ready
@@ -158,7 +188,8 @@ __global__ void __launch_bounds__(KU_THREADS, 1) knn_umma_kernel(const __grid_co
 
   if (warp == 0) {
     if (lane == 0) {
-      prefetch_tmap(&prm.tm_qh); prefetch_tmap(&prm.tm_ql); prefetch_tmap(&prm.tm_dh); prefetch_tmap(&prm.tm_dl);
+      prefetch_tmap(&prm.tm_qh); prefetch_tmap(&prm.tm_dh);
+      if (TERMS == 3) { prefetch_tmap(&prm.tm_ql); prefetch_tmap(&prm.tm_dl); }
       int job = 0;
       for (int t = 0; t < ntiles; ++t) {
         for (int c = 0; c < nchunk; ++c, ++job) {
@@ -166,16 +197,21 @@ __global__ void __launch_bounds__(KU_THREADS, 1) knn_umma_kernel(const __grid_co
           if (!mbar_wait(&empty[s], ((job / KU_NSTAGE) & 1) ^ 1)) { if (prm.err) atomicCAS(prm.err, 0, 11); return; }
           uint8_t* st = ring + s * KU_STAGE;
           mbar_arrive_expect_tx(&full[s], KU_STAGE);
-          tma_load_2d(st, &prm.tm_qh, &full[s], c * KC, m0);
-          tma_load_2d(st + QB, &prm.tm_ql, &full[s], c * KC, m0);
-          tma_load_2d(st + 2 * QB, &prm.tm_dh, &full[s], c * KC, tile_of(t_begin + t) * BN);
-          tma_load_2d(st + 2 * QB + DB, &prm.tm_dl, &full[s], c * KC, tile_of(t_begin + t) * BN);
+          if (TERMS == 3) {
+            tma_load_2d(st, &prm.tm_qh, &full[s], c * KC, m0);
+            tma_load_2d(st + QB, &prm.tm_ql, &full[s], c * KC, m0);
+            tma_load_2d(st + 2 * QB, &prm.tm_dh, &full[s], c * KC, tile_of(t_begin + t) * BN);
+            tma_load_2d(st + 2 * QB + DB, &prm.tm_dl, &full[s], c * KC, tile_of(t_begin + t) * BN);
+          } else {
+            tma_load_2d(st, &prm.tm_qh, &full[s], c * KC, m0);
+            tma_load_2d(st + QB, &prm.tm_dh, &full[s], c * KC, tile_of(t_begin + t) * BN);
+          }
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = instr_desc(FMT_BF16, 128, BN, 0, 0);
+      const uint32_t idesc = instr_desc(TERMS == 3 ? FMT_BF16 : FMT_F16, 128, BN, 0, 0);
       // K-major operands: rows of KC bf16 (128 B -> SWIZZLE_128B, 64 B -> SWIZZLE_64B), 8-row groups 8 rows apart
       const uint64_t dk128 = KC == 64 ? smem_desc(0, 16, 1024, SW_128B) : smem_desc(0, 16, 512, SW_64B);
       int job = 0;
@@ -190,12 +226,18 @@ __global__ void __launch_bounds__(KU_THREADS, 1) knn_umma_kernel(const __grid_co
           ok = mbar_wait(&full[s], (job / KU_NSTAGE) & 1);
           tc_fence_after_sync();
           const uint32_t a0 = smem_u32(ring + s * KU_STAGE) >> 4;
-          const uint64_t ah = dk128 + a0, al = ah + QB / 16, bh = ah + 2 * QB / 16, bl = bh + DB / 16;  // 16-byte units
+          if (TERMS == 3) {
+            const uint64_t ah = dk128 + a0, al = ah + QB / 16, bh = ah + 2 * QB / 16, bl = bh + DB / 16;  // 16-byte units
 #pragma unroll
-          for (int ks = 0; ks < KC / 16; ++ks) {
-            mma_f16(acc, ah + 2 * ks, bh + 2 * ks, idesc, (c | ks) != 0);
-            mma_f16(acc, ah + 2 * ks, bl + 2 * ks, idesc, 1);
-            mma_f16(acc, al + 2 * ks, bh + 2 * ks, idesc, 1);
+            for (int ks = 0; ks < KC / 16; ++ks) {
+              mma_f16(acc, ah + 2 * ks, bh + 2 * ks, idesc, (c | ks) != 0);
+              mma_f16(acc, ah + 2 * ks, bl + 2 * ks, idesc, 1);
+              mma_f16(acc, al + 2 * ks, bh + 2 * ks, idesc, 1);
+            }
+          } else {
+            const uint64_t ah = dk128 + a0, bh = ah + QB / 16;
+#pragma unroll
+            for (int ks = 0; ks < KC / 16; ++ks) mma_f16(acc, ah + 2 * ks, bh + 2 * ks, idesc, (c | ks) != 0);
           }
           mma_commit(&empty[s]);
         }
@@ -332,7 +374,7 @@ __global__ void __launch_bounds__(256) knn_rerank_kernel(const float* __restrict
                                                          int* __restrict__ fail_count, const int* __restrict__ err,
                                                          const float* __restrict__ qnorm2,
                                                          const int* __restrict__ dbmax2_bits, int npeer_max,
-                                                         float eps_unit) {
+                                                         float eps_unit, float eps_abs, float max_norm2) {
   __shared__ float s_val[8][KU_SURV];
   __shared__ int s_idx[8][KU_SURV];
   const int wid = threadIdx.x >> 5;
@@ -343,7 +385,11 @@ __global__ void __launch_bounds__(256) knn_rerank_kernel(const float* __restrict
   //  finds the other ranks' maxima in dbmax2_bits[30 .. 30 + npeer_max): header ints 32.. of the workspace)
   int mbits = __ldg(dbmax2_bits);
   for (int p = 0; p < npeer_max; ++p) mbits = max(mbits, __ldg(dbmax2_bits + 30 + p));
-  const float eps = eps_unit * sqrtf(__ldg(qnorm2 + row)) * sqrtf(__int_as_float(mbits));
+  // (eps_abs: the fast pass's absolute term for values below the fp16 normal range; max_norm2: above it the 16-bit
+  //  panels may have overflowed and the approximate pass proves nothing - the row goes to the exact kernel)
+  const float qn2 = __ldg(qnorm2 + row), dn2 = __int_as_float(mbits);
+  const float eps = eps_unit * sqrtf(qn2) * sqrtf(dn2) + eps_abs * (sqrtf(qn2) + sqrtf(dn2));
+  const bool overflow = !(qn2 <= max_norm2 && dn2 <= max_norm2);
   const float* qr = q + (size_t)row * F;
   int my_idx[KU_MAXSEG];
   float my_a[KU_MAXSEG];
@@ -404,7 +450,7 @@ __global__ void __launch_bounds__(256) knn_rerank_kernel(const float* __restrict
     }
   }
   __syncwarp();
-  if (cnt > KU_SURV || cnt < k || (err && *err != 0)) {   // massive ties / broken pipeline: the exact kernel does this row
+  if (cnt > KU_SURV || cnt < k || overflow || (err && *err != 0)) {   // massive ties / broken pipeline: the exact kernel does this row
     if (lane == 0) fail_rows[atomicAdd(fail_count, 1)] = row;
     return;
   }
@@ -420,6 +466,7 @@ __global__ void __launch_bounds__(256) knn_rerank_kernel(const float* __restrict
     amb[h] = sims != nullptr;
   }
   const float two_eps = 2.f * eps;
+  const bool vec4 = (F & 3) == 0 && ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(db)) & 15) == 0;
   for (int j = 0; j < cnt; ++j) {
     const float aj = s_val[wid][j];   // broadcast
     amb[0] |= (j != lane) && fabsf(key[0] - aj) <= two_eps;
@@ -436,7 +483,17 @@ __global__ void __launch_bounds__(256) knn_rerank_kernel(const float* __restrict
       live &= live - 1;
       const float* dr = db + (size_t)s_idx[wid][c + 32 * h] * F;
       float s = 0.f;
-      for (int f = lane; f < F; f += 32) s = fmaf(__ldg(qr + f), __ldg(dr + f), s);
+      if (vec4) {   // 16-byte loads: a 768-float row is 6 loads per lane, all in flight at once
+        float s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        for (int f = lane * 4; f < F; f += 128) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(qr + f));
+          const float4 b = __ldg(reinterpret_cast<const float4*>(dr + f));
+          s = fmaf(a.x, b.x, s); s1 = fmaf(a.y, b.y, s1); s2 = fmaf(a.z, b.z, s2); s3 = fmaf(a.w, b.w, s3);
+        }
+        s = (s + s1) + (s2 + s3);
+      } else {
+        for (int f = lane; f < F; f += 32) s = fmaf(__ldg(qr + f), __ldg(dr + f), s);
+      }
       s = warp_sum(s);
       if (lane == c) {
         key[h] = s;
@@ -505,6 +562,14 @@ static int make_map(CUtensorMap* m, const void* base, uint64_t cols, uint64_t ro
 
 static size_t al256(size_t x) { return (x + 255) / 256 * 256; }
 
+// DEPTHG_B200_KNN_PASS = split3 : the 3-term bf16 hi/lo tensor pass (round-1/2 kernel, fp32-grade similarities);
+// default                        : the fast single-panel fp16 pass of the precision ladder (TERMS = 1 above).
+// Read per call (tests switch it); both give the exact fp32 top-k, they differ in how much the re-rank recomputes.
+static bool knn_fast() {
+  const char* e = getenv("DEPTHG_B200_KNN_PASS");
+  return !(e && strcmp(e, "split3") == 0);
+}
+
 // Database segments per query block.  More segments fill the SMs when there are few query blocks (a multi-GPU
 // shard) and even out the last wave of a large build; with thread-per-row lists a segment's cold start costs
 // microseconds, so what is left is one more 32-entry list per row for the re-rank (~1 % per segment).
@@ -522,6 +587,9 @@ static int knn_nseg(int Nq, int N, int k) {
       best = nseg;
     }
   }
+  // the fast pass wants more than k + 2 candidates per row: its certificate needs the exact k-th value to clear the
+  // list minimum by the (wider) error bound, which the 32nd value of a single list rarely allows
+  if (knn_fast() && best < 2 && ceil_div(N, 256) >= 2) best = 2;
   return best;
 }
 
@@ -569,12 +637,12 @@ static KnnWs knn_ws_layout(void* ws, int Nq, int N, int Fp, bool q_in_db, int q_
 }
 
 static int knn_bn() {
-  static int bn_env = -1;  // DEPTHG_B200_KNN_BN = 128 | 256 (experiments); default 256
+  static int bn_env = -1;  // DEPTHG_B200_KNN_BN = 128 | 256 (experiments, 3-term pass only); default 256
   if (bn_env < 0) {
     const char* e = getenv("DEPTHG_B200_KNN_BN");
     bn_env = e && atoi(e) == 128 ? 128 : 256;
   }
-  return bn_env;
+  return knn_fast() ? 256 : bn_env;
 }
 
 // One launch of the tensor pass over the virtual tile list (see KnnUmmaParams).
@@ -582,8 +650,9 @@ static int launch_knn_umma(const KnnWs& w, int Nq, int N, int Fp, int nseg, int 
                            int tB_shift, int col_lo, int col_hi, int col_mode, int warm, cudaStream_t st) {
   KnnUmmaParams prm;
   int rc;
+  const bool fast = knn_fast();
   const int BN = knn_bn();
-  const int KC = BN == 128 ? KuCfg<128>::KC : KuCfg<256>::KC;
+  const int KC = fast ? KuCfg<256, 1>::KC : (BN == 128 ? KuCfg<128, 3>::KC : KuCfg<256, 3>::KC);
   if ((rc = make_map(&prm.tm_qh, w.qh, Fp, Nq, 128, KC))) return rc;
   if ((rc = make_map(&prm.tm_ql, w.ql, Fp, Nq, 128, KC))) return rc;
   if ((rc = make_map(&prm.tm_dh, w.dh, Fp, N, BN, KC))) return rc;
@@ -596,15 +665,18 @@ static int launch_knn_umma(const KnnWs& w, int Nq, int N, int Fp, int nseg, int 
   static PerDevice attr_pd = {};
   size_t& attr_set = per_device(attr_pd);
   if (!attr_set) {
-    DG_CUDA_OK(cudaFuncSetAttribute(knn_umma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, KuCfg<128>::SMEM));
-    DG_CUDA_OK(cudaFuncSetAttribute(knn_umma_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, KuCfg<256>::SMEM));
+    DG_CUDA_OK(cudaFuncSetAttribute(knn_umma_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, KuCfg<128, 3>::SMEM));
+    DG_CUDA_OK(cudaFuncSetAttribute(knn_umma_kernel<256, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, KuCfg<256, 3>::SMEM));
+    DG_CUDA_OK(cudaFuncSetAttribute(knn_umma_kernel<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, KuCfg<256, 1>::SMEM));
     attr_set = 1;
   }
   DG_PRE(st);
-  if (BN == 128)
-    knn_umma_kernel<128><<<dim3(ceil_div(Nq, 128), nseg), KU_THREADS, KuCfg<128>::SMEM, st>>>(prm);
+  if (fast)
+    knn_umma_kernel<256, 1><<<dim3(ceil_div(Nq, 128), nseg), KU_THREADS, KuCfg<256, 1>::SMEM, st>>>(prm);
+  else if (BN == 128)
+    knn_umma_kernel<128, 3><<<dim3(ceil_div(Nq, 128), nseg), KU_THREADS, KuCfg<128, 3>::SMEM, st>>>(prm);
   else
-    knn_umma_kernel<256><<<dim3(ceil_div(Nq, 128), nseg), KU_THREADS, KuCfg<256>::SMEM, st>>>(prm);
+    knn_umma_kernel<256, 3><<<dim3(ceil_div(Nq, 128), nseg), KU_THREADS, KuCfg<256, 3>::SMEM, st>>>(prm);
   DG_LAUNCH_OK("knn_umma_kernel");
   return DG_OK;
 }
@@ -613,7 +685,10 @@ static int launch_split(const float* x, int n, int F, int Fp, __nv_bfloat16* hi,
                         int* maxnorm2_bits, cudaStream_t st) {
   if (n <= 0) return DG_OK;
   DG_PRE(st);
-  split_rows_kernel<<<min(148 * 8, ceil_div(n, 8)), 256, 0, st>>>(x, n, F, Fp, hi, lo, rownorm2, maxnorm2_bits);
+  if (knn_fast())
+    split_rows_kernel<true><<<min(148 * 8, ceil_div(n, 8)), 256, 0, st>>>(x, n, F, Fp, hi, lo, rownorm2, maxnorm2_bits);
+  else
+    split_rows_kernel<false><<<min(148 * 8, ceil_div(n, 8)), 256, 0, st>>>(x, n, F, Fp, hi, lo, rownorm2, maxnorm2_bits);
   DG_LAUNCH_OK("split_rows_kernel");
   return DG_OK;
 }
@@ -621,9 +696,12 @@ static int launch_split(const float* x, int n, int F, int Fp, __nv_bfloat16* hi,
 static int launch_rerank(const KnnWs& w, const float* q, const float* db, int Nq, int N, int F, int k, int nseg,
                          int64_t* idx, float* sims, cudaStream_t st, int npeer_max = 0) {
   DG_PRE(st);
+  const bool fast = knn_fast();
   knn_rerank_kernel<<<ceil_div(Nq * 32, 256), 256, 0, st>>>(q, db, Nq, N, F, k, nseg /* merged lists */, w.cand_idx, w.cand_val, idx,
                                                              sims, w.fail_rows, w.fail_count, w.err, w.qnorm2, w.dbmax2,
-                                                             npeer_max, ku_eps_unit(F));
+                                                             npeer_max, fast ? ku_eps_unit_fast(F) : ku_eps_unit(F),
+                                                             fast ? ku_eps_abs_fast(F) : 0.f,
+                                                             fast ? 1073741824.f /* 2^30 */ : INFINITY);
   DG_LAUNCH_OK("knn_rerank_kernel");
   return launch_knn_exact(q, db, Nq, N, F, k, idx, sims, w.fail_rows, w.fail_count, st);
 }

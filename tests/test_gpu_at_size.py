@@ -47,11 +47,15 @@ def check_rows_against_oracle(idx_rows, rows, x, k):
     return int(mism.sum())
 
 
-@pytest.mark.parametrize("kind", ["iid", "clustered"])
-def test_knn_bench_size_full_build_and_shard(kind):
-    """/root/reference/src/precompute_knns.py:99-113 at N = 49 629, F = 768, k = 30 (what bench.py times)."""
+@pytest.mark.parametrize("kind", ["iid", "clustered", "iid_split3"])
+def test_knn_bench_size_full_build_and_shard(kind, monkeypatch):
+    """/root/reference/src/precompute_knns.py:99-113 at N = 49 629, F = 768, k = 30 (what bench.py times): the default
+    fast fp16 tensor pass on both data sets, the 3-term bf16 pass (DEPTHG_B200_KNN_PASS=split3) on one."""
     from depthg_b200.distributed import shard_bounds
     from depthg_b200.precompute_knns import knn_topk
+    if kind.endswith("_split3"):
+        monkeypatch.setenv("DEPTHG_B200_KNN_PASS", "split3")
+        kind = kind[:-7]
     x = knn_feats(kind)
     xd = x.to(dev())
     idx, sims, stats = knn_topk(xd, xd, KNN_K, return_sims=True, return_stats=True)

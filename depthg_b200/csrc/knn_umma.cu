@@ -43,16 +43,23 @@ constexpr int KU_CAND = 32;
 //            bounds the 3-term pass at ~10 TB/s halves) for an error bound 15x wider (ku_eps_unit_fast), which the
 //            re-rank absorbs: more candidates are ambiguous and get an exact fp32 dot product, and the certificate
 //            still decides row by row whether the candidate lists provably contain the exact top-k.
-template <int BN, int TERMS> struct KuCfg {
-  static constexpr int KC = (BN == 128 || TERMS == 1) ? 64 : 32;   // K elements per stage
-  static constexpr int QBYTES = 128 * KC * 2, DBYTES = BN * KC * 2;  // one 16-bit panel chunk of the query / database tile
+// MQ = query blocks of 128 rows per CTA.  MQ = 2 (fast pass only): every database chunk that lands in shared memory is
+//      multiplied with TWO query blocks (two 128 x 256 accumulators = all 512 TMEM columns), so the L2->SM operand
+//      stream per useful flop drops by a third (384 instead of 576 KB per 128 x 256 tile) - and that stream, not the
+//      tensor pipe, bounds the pass (~60 GB/s per SM).  One accumulator set means the MMAs of tile t+1 wait for the
+//      epilogue of tile t; measured slower than MQ = 1 (see knn_mq), so it is an experiment knob, not the default.
+template <int BN, int TERMS, int MQ = 1> struct KuCfg {
+  static constexpr int KC = MQ == 2 ? 32 : ((BN == 128 || TERMS == 1) ? 64 : 32);   // K elements per stage
+  static constexpr int QBYTES = 128 * MQ * KC * 2, DBYTES = BN * KC * 2;  // one 16-bit panel chunk of the query / database tile
   static constexpr int STAGE = TERMS == 3 ? 2 * QBYTES + 2 * DBYTES : QBYTES + DBYTES;
-  static constexpr int NSTAGE = (BN == 128 && TERMS == 3) ? 3 : 4;
-  static constexpr int LISTS = 4 * 32 * KU_CAND * 8;
+  static constexpr int NSTAGE = MQ == 2 ? 5 : ((BN == 128 && TERMS == 3) ? 3 : 4);
+  static constexpr int LISTS = 4 * MQ * 32 * KU_CAND * 8;
   static constexpr int SMEM = NSTAGE * STAGE + LISTS + 1024 + 256;
+  static constexpr int THREADS = 64 + 128 * MQ;   // TMA warp + MMA warp + 4 MQ epilogue warps
+  static constexpr int NACC = MQ == 2 ? 1 : 2;    // accumulator sets in TMEM
 };
-static_assert(KuCfg<256, 3>::SMEM <= 232448 && KuCfg<128, 3>::SMEM <= 232448 && KuCfg<256, 1>::SMEM <= 232448,
-              "knn_umma_kernel: shared memory over the CTA limit");
+static_assert(KuCfg<256, 3>::SMEM <= 232448 && KuCfg<128, 3>::SMEM <= 232448 && KuCfg<256, 1>::SMEM <= 232448 &&
+              KuCfg<256, 1, 2>::SMEM <= 232448, "knn_umma_kernel: shared memory over the CTA limit");
 // Bound on |approx - exact| of the 3-product bf16 split, as a multiple of |q| * max|d| (the row norms are measured by
 // split_rows_kernel, so un-normalised inputs get a proportionally wider bound instead of a silently wrong one):
 //   x = hi + lo + r with |lo| <= 2^-8 |x| and |r| <= 2^-8 |lo| <= 2^-16 |x| (bf16 keeps 8 significand bits), so
@@ -140,9 +147,11 @@ __global__ void __launch_bounds__(256) split_rows_kernel(const float* __restrict
   if (maxnorm2_bits && lane == 0 && wmax > 0.f) atomicMax(maxnorm2_bits, __float_as_int(wmax));
 }
 
-template <int BN, int TERMS>
-__global__ void __launch_bounds__(KU_THREADS, 1) knn_umma_kernel(const __grid_constant__ KnnUmmaParams prm) {
-  using Cfg = KuCfg<BN, TERMS>;
+template <int BN, int TERMS, int MQ>
+__global__ void __launch_bounds__(KuCfg<BN, TERMS, MQ>::THREADS, 1) knn_umma_kernel(const __grid_constant__ KnnUmmaParams prm) {
+  using Cfg = KuCfg<BN, TERMS, MQ>;
+  static_assert(MQ == 1 || (TERMS == 1 && BN == 256), "two query blocks per CTA: fast pass, 256-row database tiles");
+  constexpr int NACC = Cfg::NACC;
   constexpr int KU_STAGE = Cfg::STAGE, KU_NSTAGE = Cfg::NSTAGE, KC = Cfg::KC;
   constexpr int QB = Cfg::QBYTES, DB = Cfg::DBYTES;
   extern __shared__ uint8_t ku_raw[];
@@ -153,14 +162,15 @@ __global__ void __launch_bounds__(KU_THREADS, 1) knn_umma_kernel(const __grid_co
   // e * 32 + (r ^ e), which is conflict-free both for "every row scans slot e" and for "one row, all slots"
   float* lists = reinterpret_cast<float*>(ring + KU_NSTAGE * KU_STAGE);
   uint64_t* bars = reinterpret_cast<uint64_t*>(ring + KU_NSTAGE * KU_STAGE + Cfg::LISTS);
-  uint64_t* full = bars;               // [<=4]
-  uint64_t* empty = bars + 4;          // [<=4]
-  uint64_t* tfull = bars + 8;          // [2] accumulator ready
-  uint64_t* tempty = bars + 10;        // [2] accumulator drained
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* full = bars;                          // [KU_NSTAGE]
+  uint64_t* empty = bars + KU_NSTAGE;             // [KU_NSTAGE]
+  uint64_t* tfull = bars + 2 * KU_NSTAGE;         // [2] accumulator ready
+  uint64_t* tempty = bars + 2 * KU_NSTAGE + 2;    // [2] accumulator drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * KU_NSTAGE + 4);
+  static_assert((2 * KU_NSTAGE + 5) * 8 <= 256, "barrier block");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * 128;
+  const int m0 = blockIdx.x * 128 * MQ;
   // blockIdx.y = database segment: this CTA ranks its 128 query rows against tiles [t_begin, t_end) only, which
   // gives small query blocks (multi-GPU shards) enough CTAs to fill the GPU and every row nseg x 32 candidates
   const int seg = blockIdx.y;
@@ -176,11 +186,11 @@ __global__ void __launch_bounds__(KU_THREADS, 1) knn_umma_kernel(const __grid_co
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], 128);  // every epilogue thread arrives
+      mbar_init(&tempty[a], 128 * MQ);  // every epilogue thread arrives
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
+  if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);   // MQ = 1: two alternating sets; MQ = 2: one set of two halves
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -217,8 +227,8 @@ __global__ void __launch_bounds__(KU_THREADS, 1) knn_umma_kernel(const __grid_co
       int job = 0;
       bool ok = true;
       for (int t = 0; t < ntiles && ok; ++t) {
-        const int a = t & 1;
-        ok = mbar_wait(&tempty[a], ((t >> 1) & 1) ^ 1);
+        const int a = t % NACC;
+        ok = mbar_wait(&tempty[a], ((t / NACC) & 1) ^ 1);
         tc_fence_after_sync();
         const uint32_t acc = tmem + a * BN;
         for (int c = 0; c < nchunk && ok; ++c, ++job) {
@@ -237,7 +247,10 @@ __global__ void __launch_bounds__(KU_THREADS, 1) knn_umma_kernel(const __grid_co
           } else {
             const uint64_t ah = dk128 + a0, bh = ah + QB / 16;
 #pragma unroll
-            for (int ks = 0; ks < KC / 16; ++ks) mma_f16(acc, ah + 2 * ks, bh + 2 * ks, idesc, (c | ks) != 0);
+            for (int h = 0; h < MQ; ++h)     // query block h: rows 128 h .. of the Q chunk, accumulator columns BN h ..
+#pragma unroll
+              for (int ks = 0; ks < KC / 16; ++ks)
+                mma_f16(acc + h * BN, ah + h * (128 * KC * 2 / 16) + 2 * ks, bh + 2 * ks, idesc, (c | ks) != 0);
           }
           mma_commit(&empty[s]);
         }
@@ -248,7 +261,9 @@ __global__ void __launch_bounds__(KU_THREADS, 1) knn_umma_kernel(const __grid_co
   } else {
     // ---- epilogue: thread = query row (the TMEM row-per-thread layout), see the file header
     const int lg = warp & 3;     // the TMEM lane group this warp may read: lanes 32 * (warp % 4) ..
-    const uint32_t tlane = tmem + ((uint32_t)(32 * lg) << 16);
+    const int qh = (warp - 2) >> 2;   // query block of this warp (MQ = 2: warps 2-5 block 0, warps 6-9 block 1)
+    const uint32_t tlane = tmem + ((uint32_t)(32 * lg) << 16) + (MQ == 2 ? qh * BN : 0);
+    const int mrow0 = m0 + 128 * qh + 32 * lg;   // first query row of this warp
     float* lv = lists + (warp - 2) * (2 * 32 * KU_CAND);
     int* li = reinterpret_cast<int*>(lv + 32 * KU_CAND);
     float thr = -INFINITY;   // smallest value of the full list; -inf while the list still has room
@@ -267,7 +282,7 @@ __global__ void __launch_bounds__(KU_THREADS, 1) knn_umma_kernel(const __grid_co
     if (prm.warm) {   // continue the list a previous launch (same grid, same segments) left in cand_*
       // coalesced: for each row of the warp, lane e fetches entry e
       for (int r = 0; r < 32; ++r) {
-        const int q = m0 + 32 * lg + r;
+        const int q = mrow0 + r;
         float x = -INFINITY;
         int xi = -1;
         if (q < prm.Nq) {
@@ -286,8 +301,8 @@ __global__ void __launch_bounds__(KU_THREADS, 1) knn_umma_kernel(const __grid_co
     float v[32];
     bool ok = true;
     for (int t = 0; t < ntiles && ok; ++t) {
-      const int a = t & 1;
-      ok = mbar_wait(&tfull[a], (t >> 1) & 1);
+      const int a = t % NACC;
+      ok = mbar_wait(&tfull[a], (t / NACC) & 1);
       tc_fence_after_sync();
       const int n0 = tile_of(t_begin + t) * BN;
 #pragma unroll 1
@@ -340,7 +355,7 @@ __global__ void __launch_bounds__(KU_THREADS, 1) knn_umma_kernel(const __grid_co
     }
     __syncwarp();
     for (int r = 0; r < 32; ++r) {
-      const int q = m0 + 32 * lg + r;
+      const int q = mrow0 + r;
       if (q < prm.Nq) {
         const size_t o = ((size_t)q * prm.list_pitch + seg) * KU_CAND;
         prm.cand_val[o + lane] = lv[lane * 32 + (r ^ lane)];
@@ -570,12 +585,22 @@ static bool knn_fast() {
   return !(e && strcmp(e, "split3") == 0);
 }
 
+// Query blocks per CTA of the tensor pass (KuCfg::MQ).  Default 1.  DEPTHG_B200_KNN_MQ=2 (fast pass only) selects the
+// 256 x 256 tile; measured on B200 at N = 49 629: 5.18 ms against 4.83 ms for MQ = 1 — the two 128 x 256 accumulators
+// fill TMEM, so nothing overlaps the epilogue (256 KB of TMEM reads at 64 B/cycle alone are 2 us a tile) and the
+// operand stream it saves is lost again while the ring waits.  Kept for the record and covered by a GPU test.
+static int knn_mq() {
+  if (!knn_fast()) return 1;
+  const char* e = getenv("DEPTHG_B200_KNN_MQ");
+  return e && atoi(e) == 2 ? 2 : 1;
+}
+
 // Database segments per query block.  More segments fill the SMs when there are few query blocks (a multi-GPU
 // shard) and even out the last wave of a large build; with thread-per-row lists a segment's cold start costs
 // microseconds, so what is left is one more 32-entry list per row for the re-rank (~1 % per segment).
 // Pick the nseg that minimises  waves x tiles-per-segment x (1 + 0.01 (nseg - 1)).
 static int knn_nseg(int Nq, int N, int k) {
-  const int nblocks = ceil_div(Nq, 128), ntiles = ceil_div(N, 128);
+  const int nblocks = ceil_div(Nq, 128 * knn_mq()), ntiles = ceil_div(N, 128);
   double best_cost = 1e300;
   (void)k;
   int best = 1;
@@ -651,10 +676,10 @@ static int launch_knn_umma(const KnnWs& w, int Nq, int N, int Fp, int nseg, int 
   KnnUmmaParams prm;
   int rc;
   const bool fast = knn_fast();
-  const int BN = knn_bn();
-  const int KC = fast ? KuCfg<256, 1>::KC : (BN == 128 ? KuCfg<128, 3>::KC : KuCfg<256, 3>::KC);
-  if ((rc = make_map(&prm.tm_qh, w.qh, Fp, Nq, 128, KC))) return rc;
-  if ((rc = make_map(&prm.tm_ql, w.ql, Fp, Nq, 128, KC))) return rc;
+  const int BN = knn_bn(), MQ = knn_mq();
+  const int KC = fast ? (MQ == 2 ? KuCfg<256, 1, 2>::KC : KuCfg<256, 1>::KC) : (BN == 128 ? KuCfg<128, 3>::KC : KuCfg<256, 3>::KC);
+  if ((rc = make_map(&prm.tm_qh, w.qh, Fp, Nq, 128 * MQ, KC))) return rc;
+  if ((rc = make_map(&prm.tm_ql, w.ql, Fp, Nq, 128 * MQ, KC))) return rc;
   if ((rc = make_map(&prm.tm_dh, w.dh, Fp, N, BN, KC))) return rc;
   if ((rc = make_map(&prm.tm_dl, w.dl, Fp, N, BN, KC))) return rc;
   prm.Nq = Nq; prm.N = N; prm.nchunk = Fp / KC; prm.ntiles = ntiles_virtual; prm.nseg = nseg;
@@ -665,18 +690,21 @@ static int launch_knn_umma(const KnnWs& w, int Nq, int N, int Fp, int nseg, int 
   static PerDevice attr_pd = {};
   size_t& attr_set = per_device(attr_pd);
   if (!attr_set) {
-    DG_CUDA_OK(cudaFuncSetAttribute(knn_umma_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, KuCfg<128, 3>::SMEM));
-    DG_CUDA_OK(cudaFuncSetAttribute(knn_umma_kernel<256, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, KuCfg<256, 3>::SMEM));
-    DG_CUDA_OK(cudaFuncSetAttribute(knn_umma_kernel<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, KuCfg<256, 1>::SMEM));
+    DG_CUDA_OK(cudaFuncSetAttribute(knn_umma_kernel<128, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, KuCfg<128, 3>::SMEM));
+    DG_CUDA_OK(cudaFuncSetAttribute(knn_umma_kernel<256, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, KuCfg<256, 3>::SMEM));
+    DG_CUDA_OK(cudaFuncSetAttribute(knn_umma_kernel<256, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, KuCfg<256, 1>::SMEM));
+    DG_CUDA_OK(cudaFuncSetAttribute(knn_umma_kernel<256, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, KuCfg<256, 1, 2>::SMEM));
     attr_set = 1;
   }
   DG_PRE(st);
-  if (fast)
-    knn_umma_kernel<256, 1><<<dim3(ceil_div(Nq, 128), nseg), KU_THREADS, KuCfg<256, 1>::SMEM, st>>>(prm);
+  if (fast && MQ == 2)
+    knn_umma_kernel<256, 1, 2><<<dim3(ceil_div(Nq, 256), nseg), KuCfg<256, 1, 2>::THREADS, KuCfg<256, 1, 2>::SMEM, st>>>(prm);
+  else if (fast)
+    knn_umma_kernel<256, 1, 1><<<dim3(ceil_div(Nq, 128), nseg), KU_THREADS, KuCfg<256, 1>::SMEM, st>>>(prm);
   else if (BN == 128)
-    knn_umma_kernel<128, 3><<<dim3(ceil_div(Nq, 128), nseg), KU_THREADS, KuCfg<128, 3>::SMEM, st>>>(prm);
+    knn_umma_kernel<128, 3, 1><<<dim3(ceil_div(Nq, 128), nseg), KU_THREADS, KuCfg<128, 3>::SMEM, st>>>(prm);
   else
-    knn_umma_kernel<256, 3><<<dim3(ceil_div(Nq, 128), nseg), KU_THREADS, KuCfg<256, 3>::SMEM, st>>>(prm);
+    knn_umma_kernel<256, 3, 1><<<dim3(ceil_div(Nq, 128), nseg), KU_THREADS, KuCfg<256, 3>::SMEM, st>>>(prm);
   DG_LAUNCH_OK("knn_umma_kernel");
   return DG_OK;
 }
@@ -732,7 +760,7 @@ int knn_topk_umma(const float* q, const float* db, int Nq, int N, int F, int k, 
 constexpr int KU_COMM_SMS = 36;
 
 static int knn_nseg_local(int Nq, int nseg) {
-  const int nblocks = ceil_div(Nq, 128);
+  const int nblocks = ceil_div(Nq, 128 * knn_mq());
   int n = (148 - KU_COMM_SMS) / max(nblocks, 1);
   return max(1, min(n, nseg));
 }

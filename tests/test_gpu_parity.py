@@ -358,7 +358,7 @@ def _check_knn_rows(idx, queries, db, want_idx):
 
 
 @pytest.mark.parametrize("k", [30, 7])
-@pytest.mark.parametrize("path", ["umma", "umma_split3", "simt"])
+@pytest.mark.parametrize("path", ["umma", "umma_split3", "umma_mq2", "simt"])
 def test_knn_tensor_core_and_exact_kernels_agree(path, k, monkeypatch):
     """All KNN paths (tcgen05 fast fp16 pass = default, tcgen05 3-term bf16 pass, exact CUDA-core kernel) against the
     oracle on a problem big enough for the tcgen05 path, incl. ragged sizes."""
@@ -367,6 +367,8 @@ def test_knn_tensor_core_and_exact_kernels_agree(path, k, monkeypatch):
         monkeypatch.setenv("DEPTHG_B200_KNN", "simt")
     if path == "umma_split3":
         monkeypatch.setenv("DEPTHG_B200_KNN_PASS", "split3")
+    if path == "umma_mq2":      # the 256 x 256 tile variant of the fast pass (two query blocks per CTA)
+        monkeypatch.setenv("DEPTHG_B200_KNN_MQ", "2")
     rs = np.random.RandomState(41)
     cent = rs.standard_normal((40, 200)).astype(np.float32)
     x = cent[rs.randint(0, 40, 4100)] + 0.25 * rs.standard_normal((4100, 200)).astype(np.float32)

@@ -57,6 +57,7 @@ SIGNATURES = {
     "dg_knn_shard_begin": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_size_t, C.c_int, _vp]),
     "dg_knn_shard_finish": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, C.c_size_t,
                                       C.c_int, C.c_int, _vp]),
+    "dg_knn_panel_count": (C.c_int, []),
     "dg_knn_panel_layout": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t),
                                       C.POINTER(C.c_size_t)]),
     "dg_memcpy_batch": (C.c_int, [C.c_int, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(C.c_size_t), C.POINTER(_vp)]),

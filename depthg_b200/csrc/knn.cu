@@ -389,6 +389,9 @@ extern "C" int dg_knn_shard_finish(const float* db, int Nq, int row_lo, int N, i
   return launch_knn_exact(db + (size_t)row_lo * F, db, Nq, N, F, k, idx, sims, nullptr, nullptr, st);
 }
 
+namespace dg { int knn_panel_count(); }
+extern "C" int dg_knn_panel_count(void) { return dg::knn_panel_count(); }
+
 extern "C" int dg_knn_panel_layout(int N, int F, size_t* hi_offset, size_t* lo_offset, size_t* row_bytes) {
   using namespace dg;
   DG_REQUIRE(N > 0 && F > 0 && hi_offset && lo_offset && row_bytes, DG_ERR_INVALID, "dg_knn_panel_layout: bad arguments");

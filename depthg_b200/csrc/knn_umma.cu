@@ -814,6 +814,8 @@ int knn_shard_finish(const float* db, int Nq, int row_lo, int N, int F, int k, i
   return DG_OK;
 }
 
+int knn_panel_count() { return knn_fast() ? 1 : 2; }
+
 // byte offsets of the bf16 hi / lo panels inside the workspace and the pitch of a panel row: what a host needs to
 // copy panel rows between the workspaces of different GPUs
 void knn_panel_layout(int N, int F, size_t* hi_off, size_t* lo_off, size_t* row_bytes) {

@@ -120,6 +120,7 @@ class _SymmKnnState:
         self.h_ws = symm.rendezvous(self.ws, gname)
         self.h_g = symm.rendezvous(self.gathered, gname)
         hi_off, lo_off, row_bytes = knn_panel_layout(N, F)
+        self.npanels = _lib.lib().dg_knn_panel_count()      # 1: the fast pass reads (and the peers need) the hi panel only
         self.comm = [torch.cuda.Stream(device=dev) for _ in range(max(world - 1, 1))]
         self.ev_split, self.ev_ready = torch.cuda.Event(), torch.cuda.Event()
         self.ev_panels, self.ev_rows = torch.cuda.Event(), torch.cuda.Event()
@@ -134,7 +135,7 @@ class _SymmKnnState:
             pw = self.h_ws.get_buffer(p, (self.ws_bytes,), torch.uint8, 0).data_ptr()
             pg = self.h_g.get_buffer(p, (N, F), torch.float32, 0).data_ptr()
             if hi > lo:
-                for off in (hi_off, lo_off):
+                for off in (hi_off, lo_off)[:self.npanels]:
                     o = off + lo * row_bytes
                     a.append((pw + o, wsp + o, (hi - lo) * row_bytes, st))
                 b.append((pg + lo * F * 4, gp + lo * F * 4, (hi - lo) * F * 4, st))
@@ -221,7 +222,8 @@ class _SymmKnnState:
 
 def _symm_knn_state(N, F, k, group, dev):
     """The cached exchange state, or None when symmetric memory cannot be set up here (all ranks agree)."""
-    key = (N, F, k, id(group), dev.index)
+    from . import _lib
+    key = (N, F, k, id(group), dev.index, _lib.lib().dg_knn_panel_count())
     if key not in _symm_states:
         st = None
         try:

@@ -323,6 +323,9 @@ DG_API int dg_knn_shard_finish(const float* db, int Nq, int row_lo, int N, int F
                         size_t ws_bytes, int phases, int npeer_max, dg_stream_t stream);
 /* Byte offsets of the bf16 hi / lo panels ([N, row_bytes / 2] each) inside a KNN workspace and the pitch of a panel row. */
 DG_API int dg_knn_panel_layout(int N, int F, size_t* hi_offset, size_t* lo_offset, size_t* row_bytes);
+/* How many of those panels the tensor pass reads, i.e. what a host-side exchange has to move: 1 = the hi panel only
+ * (the default fast pass: one fp16 panel), 2 = hi and lo (DEPTHG_B200_KNN_PASS=split3: the 3-term bf16 pass). */
+DG_API int dg_knn_panel_count(void);
 
 /* n device-to-device copies, copy i enqueued on streams[i] (copy engines; peer-mapped pointers allowed): the exchange
  * step of the sharded KNN build when the host moves panel rows itself. */

@@ -51,6 +51,7 @@ SIGNATURES = {
                                C.c_size_t, _vp]),
     "dg_loss_plan": (C.c_int, [_vp, _vp]),
     "dg_loss_forward": (C.c_int, [_vp, _vp, _vp]),
+    "dg_loss_presample": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_ulonglong, C.c_ulonglong, _vp]),
     "dg_loss_backward": (C.c_int, [_vp, _vp, _vp, _vp]),
     "dg_knn_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "dg_knn_topk": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, C.c_size_t, _vp]),
@@ -109,7 +110,10 @@ class LossIO(C.Structure):
                 ("code_pos_strides", _i64x4), ("depth", _vp), ("depth_pos", _vp), ("coords", _vp), ("perms", _vp),
                 ("arena", _vp), ("out8", _vp), ("cd_out", _vp), ("loss_out", _vp), ("dd_out", _vp), ("fd_dbg", _vp), ("aug_feats", _vp), ("aug_feats_strides", _i64x4),
                 ("perms_ready", _vp), ("perm_seed", C.c_ulonglong), ("perm_offset", C.c_ulonglong),
-                ("gen_perms", C.c_int), ("clear", _vp * 2), ("clear_bytes", C.c_size_t * 2)]
+                ("gen_perms", C.c_int), ("clear", _vp * 2), ("clear_bytes", C.c_size_t * 2),
+                ("dsign", _vp), ("next_depth", _vp), ("next_depth_pos", _vp), ("next_coords", _vp), ("next_dsign", _vp),
+                ("next_perms", _vp), ("next_perm_seed", C.c_ulonglong), ("next_perm_offset", C.c_ulonglong),
+                ("next_n_perms", C.c_int)]
 
 
 class LossGrads(C.Structure):

@@ -25,9 +25,11 @@
 // gather_norm_bwd_kernel sums.  Every mbarrier wait is bounded; a timeout raises the error flag (losses come back NaN).
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "kernels.cuh"
 #include "umma.cuh"
+#include "fps_body.cuh"
 
 namespace dg {
 
@@ -75,6 +77,13 @@ struct PipeParams {
   int l2_hints;              // L2 eviction-priority hints on the operand loads (DEPTHG_B200_L2HINTS=1; measured: slower, off by default)
   int dbg_mma;               // timing experiment (DEPTHG_B200_PIPE_MMA): 1 = hi.hi product only, 2 = no chunk MMAs (results garbage)
   const uint8_t* dbg_bulk;   // timing experiment (DEPTHG_B200_PIPE_BULK): stream stages as 1-D bulk copies from here (results garbage)
+  // The NEXT step's sampling riding along (dg_loss_io_t::next_*): CTAs nmain .. nmain + nride - 1 of the grid run the
+  // FPS launch of the next step (one image each, + one CTA for its permutations).  They become resident when the
+  // first one-item CTAs of the item list exit - 224 items on 148 CTAs leave 72 SMs idle for the second half of this
+  // kernel - so the next step starts at its gathers: FPS leaves the step's critical path without a launch, a side
+  // stream or an SM taken from anybody.
+  int nmain, nride;
+  FpsArgs ride;
 };
 
 struct Item {
@@ -118,6 +127,18 @@ __device__ __forceinline__ void praise(int* err, int code) {
 // precede) and where the producer issues the second code fill: fractions of the chunk count, see the file header
 __global__ void __launch_bounds__(CP_THREADS, 1) corr_pipe_kernel(const __grid_constant__ PipeParams prm) {
   extern __shared__ uint8_t cp_raw[];
+  if ((int)blockIdx.x >= prm.nmain) {   // ride-along CTA: the next step's FPS (see PipeParams::ride)
+    pdl_trigger();
+    pdl_wait();
+    const int c = (int)blockIdx.x - prm.nmain;
+    if (c == prm.ride.nimg) {           // (only present when ride.pj.n > 0) all threads of the CTA draw the permutations
+      super_perms_block(prm.ride.pj.seed, prm.ride.pj.offset, prm.ride.pj.n, prm.ride.pj.B, prm.ride.pj.out,
+                        reinterpret_cast<int*>(cp_raw));
+      return;
+    }
+    if (threadIdx.x < FPS_THREADS) fps_cta<4, 256, 4>(prm.ride, c, reinterpret_cast<float*>(cp_raw));
+    return;
+  }
   uint8_t* ring = cp_raw + ((1024u - (smem_u32(cp_raw) & 1023u)) & 1023u);   // 1024-byte aligned, stays an smem pointer
   uint8_t* u_hi = ring + CP_NSTAGE * CP_STAGE;
   uint8_t* u_lo = u_hi + 32768;
@@ -139,7 +160,7 @@ __global__ void __launch_bounds__(CP_THREADS, 1) corr_pipe_kernel(const __grid_c
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nfd = prm.ldf / 32, ncd = prm.ldc / 32, nb = prm.ldc / 32;
   const int Prows = prm.prows;
-  const int first = blockIdx.x, stride = gridDim.x;
+  const int first = blockIdx.x, stride = prm.nmain;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < CP_NSTAGE; ++s) {
@@ -644,12 +665,19 @@ size_t corr_pipe_workspace_floats(int npairs, int B, int P) {
   return (size_t)npairs * B * (1 + nt * nt * 4 + (size_t)round_up(P, 128)) + 512;
 }
 
+// Can this FPS launch run as ride-along CTAs of the correlation kernel?  (the 28 x 28 grid class of fps_kernel<4, 256, 4>,
+// shared memory within this kernel's allocation, permutation draw within one CTA)
+bool corr_pipe_can_ride(const FpsArgs& a, size_t smem) {
+  return a.H * a.W <= 896 && smem <= (size_t)CP_SMEM && a.pj.n <= CP_THREADS;
+}
+
 int corr_loss_pipe(const dg_panels_t* pan, const float* fmean, int nsplit, const float* dsign, int npairs, int B, int P,
                    int Prows, int ldf, int ldc, const float* pair_shift, const int32_t* pair_group, float depth_shift,
                    int flags, float* out8, float* dC1, float* dC2, float* cd_out, float* loss_out, float* dd_out,
                    float* fd_dbg, void* ws, cudaStream_t st, const int32_t* fslot1, const int32_t* fslot2, int nfslots,
-                   bool dots_done) {
+                   bool dots_done, const FpsArgs* ride, size_t ride_smem) {
   DG_REQUIRE(Prows % 128 == 0 && Prows >= P && P <= 1024, DG_ERR_INVALID, "corr_loss_pipe: bad panel rows %d for %d points", Prows, P);
+  DG_REQUIRE(!ride || corr_pipe_can_ride(*ride, ride_smem), DG_ERR_INVALID, "corr_loss_pipe: this FPS job cannot ride along");
   DG_REQUIRE(ldf % 32 == 0 && ldc % 32 == 0 && ldc <= 128, DG_ERR_UNSUPPORTED, "corr_loss_pipe: bad panel pitch");
   PipeParams prm;
   const int nt = ceil_div(P, 128);
@@ -719,8 +747,15 @@ int corr_loss_pipe(const dg_panels_t* pan, const float* fmean, int nsplit, const
     attr_set = 1;
   }
   const int grid = prm.nitems < (int)sms ? prm.nitems : (int)sms;   // persistent: one CTA per SM walks the item list
+  prm.nmain = grid;
+  prm.nride = 0;
+  memset(&prm.ride, 0, sizeof prm.ride);
+  if (ride) {
+    prm.ride = *ride;
+    prm.nride = ride->nimg + (ride->pj.n > 0 ? 1 : 0);
+  }
   DG_PRE(st);
-  launch_pdl(corr_pipe_kernel, dim3(grid), dim3(CP_THREADS), (size_t)CP_SMEM, st, prm);
+  launch_pdl(corr_pipe_kernel, dim3(grid + prm.nride), dim3(CP_THREADS), (size_t)CP_SMEM, st, prm);
   DG_LAUNCH_OK("corr_pipe_kernel");
   return DG_OK;  // out8 is written by the CTA that completes the last item
 }

@@ -18,268 +18,20 @@
 //      normalised (row/H, col/W) coordinates.
 #include <string.h>
 
-#include "kernels.cuh"
-#include "sampler.cuh"
+#include "fps_body.cuh"
 
 namespace dg {
 
-constexpr int FPS_THREADS = 256;  // setup (staging, pooling, lifting) and emission threads; the rounds use the first RT of them
-constexpr int FPS_WARPS = FPS_THREADS / 32;
-// measured on B200 (28x28 grid, S=11, one image per CTA; scripts/micro/fps_micro.cu): cycles per round 350 at RT=256,
-// 468 at 128, 367 at 512, 576 at 64 — a warp issues one instruction every other cycle, so fewer round threads pay in
-// issue slots what they save on the barrier; the floor of the chain is LDS 29 + redux pair 49 + STS/BAR/LDS 59 +
-// redux pair 42 cycles.
-constexpr int FPS_DEFAULT_RT = 256;  // round threads for the <= 896-point case (see fps_rounds)
-
-// s = d / max(|d|, eps) of the align_corners=True bilinear resample of one [Hd,Wd] image at point p of the SxS grid
-// (0 for p >= S*S).  `d` may point to global or shared memory.
-__device__ __forceinline__ float depth_sign_value(const float* d, int Hd, int Wd, int S, int p, float eps) {
-  if (p >= S * S) return 0.f;
-  const int h = p / S, w = p - h * S;
-  const float sy = S > 1 ? __fdiv_rn((float)(Hd - 1), (float)(S - 1)) : 0.f;
-  const float sx = S > 1 ? __fdiv_rn((float)(Wd - 1), (float)(S - 1)) : 0.f;
-  const float fy = __fmul_rn(sy, (float)h), fx = __fmul_rn(sx, (float)w);
-  const int y0 = min((int)fy, Hd - 1), x0 = min((int)fx, Wd - 1);
-  const int y1 = y0 + (y0 < Hd - 1 ? 1 : 0), x1 = x0 + (x0 < Wd - 1 ? 1 : 0);
-  const float ly = fminf(fmaxf(fy - (float)y0, 0.f), 1.f), lx = fminf(fmaxf(fx - (float)x0, 0.f), 1.f);
-  const float v00 = d[(size_t)y0 * Wd + x0], v01 = d[(size_t)y0 * Wd + x1];
-  const float v10 = d[(size_t)y1 * Wd + x0], v11 = d[(size_t)y1 * Wd + x1];
-  const float v = (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
-  return v / fmaxf(fabsf(v), eps);
-}
-
-// STAGE: the whole [Hd,Wd] depth image is first copied into shared memory with 16-byte cp.async
-// (every load in flight at once), so the pooling reads never wait on DRAM one window row at a time.
-
-// Packed fp32 pairs (FADD2 / FMUL2 of sm_100): two IEEE-rounded operations per instruction, bit-identical to the scalar
-// ones.  Only subtraction and multiplication are packed: ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2
-// (ONE rounding) whatever -fmad says, which would break the bit-exact distances, so the two additions stay scalar
-// (scripts/sass_evidence.py checks that no FFMA is left in this kernel's round loop).
-__device__ __forceinline__ unsigned long long f2_pack(float a, float b) {
-  unsigned long long r;
-  asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(a), "f"(b));
-  return r;
-}
-__device__ __forceinline__ void f2_unpack(unsigned long long v, float& a, float& b) {
-  asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
-}
-__device__ __forceinline__ unsigned long long f2_sub(unsigned long long a, unsigned long long b) {
-  unsigned long long r;
-  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-__device__ __forceinline__ unsigned long long f2_sqr(unsigned long long a) {
-  unsigned long long r;
-  asm("mul.rn.f32x2 %0, %1, %1;" : "=l"(r) : "l"(a));
-  return r;
-}
-
-// The S*S-1 selection rounds, run by the first RT threads of the CTA: thread t owns points t, t+RT, ... (PR per thread,
-// in registers as packed pairs).  Per round (measured on B200, scripts/micro/fps_micro.cu: 350 cycles at RT = 256 /
-// PR = 4 against 588 for the round-1 loop):
-//   * key = min(key, int view of the distance) as a SIGNED integer minimum: a point that can no longer be picked needs no
-//     test and no marking, because the distance of a picked point to itself is exactly +0, so its key drops to 0 in the
-//     round after its pick and can only win again when every remaining key is 0 too (coincident points) — that case
-//     (block maximum == 0) takes a slow path that consults the taken flags, like np.delete does in the reference;
-//   * warp argmax = redux.max of the key, then redux.min of the lowest owned index holding that key; the RT/32 warp
-//     results meet in shared memory as one 8-byte word each behind ONE named barrier and every warp folds them with the
-//     same two redux ops.
-template <int PR, int RT>
-__device__ __forceinline__ void fps_rounds(const float* sX, const float* sY, const float* sZ, unsigned char* sTaken,
-                                           int npts, int nsel, int2 (*s_kv)[FPS_WARPS]) {
-  constexpr int RW = RT / 32;
-  static_assert(PR % 2 == 0 && RW <= FPS_WARPS && (RW & (RW - 1)) == 0, "fps_rounds: packed pairs, power-of-two warps");
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  unsigned long long X2[PR / 2], Y2[PR / 2], Z2[PR / 2];
-  int key[PR];  // int view of the running min distance; -1 = not a point
-#pragma unroll
-  for (int j = 0; j < PR; j += 2) {
-    const int i0 = j * RT + tid, i1 = i0 + RT;
-    const bool ok0 = i0 < npts, ok1 = i1 < npts;
-    X2[j / 2] = f2_pack(ok0 ? sX[i0] : 0.f, ok1 ? sX[i1] : 0.f);
-    Y2[j / 2] = f2_pack(ok0 ? sY[i0] : 0.f, ok1 ? sY[i1] : 0.f);
-    Z2[j / 2] = f2_pack(ok0 ? sZ[i0] : 0.f, ok1 ? sZ[i1] : 0.f);
-    key[j] = ok0 ? 0x7f800000 : -1;  // +inf; point 0 (the first pick) drops to 0 in round 1
-    key[j + 1] = ok1 ? 0x7f800000 : -1;
-  }
-  int last = 0;
-  for (int r = 1; r < nsel; ++r) {
-    const float lx = sX[last], ly = sY[last], lz = sZ[last];
-    const unsigned long long lx2 = f2_pack(lx, lx), ly2 = f2_pack(ly, ly), lz2 = f2_pack(lz, lz);
-    int bk = -1;
-#pragma unroll
-    for (int j = 0; j < PR; j += 2) {
-      float xx0, xx1, yy0, yy1, zz0, zz1;
-      f2_unpack(f2_sqr(f2_sub(lx2, X2[j / 2])), xx0, xx1);
-      f2_unpack(f2_sqr(f2_sub(ly2, Y2[j / 2])), yy0, yy1);
-      f2_unpack(f2_sqr(f2_sub(lz2, Z2[j / 2])), zz0, zz1);
-      const float d0 = __fadd_rn(__fadd_rn(xx0, yy0), zz0), d1 = __fadd_rn(__fadd_rn(xx1, yy1), zz1);
-      key[j] = min(key[j], __float_as_int(d0));  // non-negative floats: int order == float order; -1 stays -1
-      key[j + 1] = min(key[j + 1], __float_as_int(d1));
-      bk = max(bk, max(key[j], key[j + 1]));
-    }
-    const int wk = __reduce_max_sync(0xffffffffu, bk);
-    int bi = 0x7fffffff;
-#pragma unroll
-    for (int j = PR - 1; j >= 0; --j) bi = key[j] == wk ? j * RT + tid : bi;  // lowest owned index holding the maximum
-    const int wi = __reduce_min_sync(0xffffffffu, bi);
-    if (RW == 1) {
-      last = wi;
-      if (wk == 0) {  // coincident points only: first index that is not taken yet (np.delete semantics)
-        int fi = 0x7fffffff;
-#pragma unroll
-        for (int j = PR - 1; j >= 0; --j)
-          if (key[j] == 0 && !sTaken[j * RT + tid]) fi = j * RT + tid;
-        last = __reduce_min_sync(0xffffffffu, fi);
-      }
-    } else {
-      const int buf = r & 1;
-      if (lane == 0) s_kv[buf][warp] = make_int2(wk, wi);
-      asm volatile("bar.sync 1, %0;" ::"n"(RT) : "memory");
-      const int2 c = s_kv[buf][lane & (RW - 1)];
-      const int gk = __reduce_max_sync(0xffffffffu, c.x);
-      last = __reduce_min_sync(0xffffffffu, c.x == gk ? c.y : 0x7fffffff);
-      if (gk == 0) {  // block-uniform: coincident points only
-        int fi = 0x7fffffff;
-#pragma unroll
-        for (int j = PR - 1; j >= 0; --j)
-          if (key[j] == 0 && !sTaken[j * RT + tid]) fi = j * RT + tid;
-        fi = __reduce_min_sync(0xffffffffu, fi);
-        asm volatile("bar.sync 1, %0;" ::"n"(RT) : "memory");  // everybody has read slot `buf`
-        if (lane == 0) s_kv[buf][warp].y = fi;
-        asm volatile("bar.sync 1, %0;" ::"n"(RT) : "memory");
-        last = __reduce_min_sync(0xffffffffu, s_kv[buf][lane & (RW - 1)].y);
-      }
-    }
-    if (tid == 0) sTaken[last] = 1;  // read by the slow path (two barriers later at the earliest) and by the emission
-  }
-}
-
-template <int PPT, bool STAGE, int RT, int PR>
-__global__ void __launch_bounds__(FPS_THREADS) fps_kernel(const float* __restrict__ depth_a,
-                                                          const float* __restrict__ depth_b, int B, int Hd, int Wd,
-                                                          int H, int W, int nsel, float factor, float far_plane,
-                                                          int affine, float* __restrict__ coords,
-                                                          int32_t* __restrict__ idx_out, float* __restrict__ dsign,
-                                                          int sign_S, int sign_pitch, float sign_eps, PermJob pj) {
-  extern __shared__ __align__(16) float fps_smem[];
-  const int npts = H * W;
-  const int npad = (npts + 3) & ~3;
-  float* sX = fps_smem;
-  float* sY = sX + npad;
-  float* sZ = sY + npad;
-  unsigned char* sTaken = reinterpret_cast<unsigned char*>(sZ + npad);
-  float* sImg = reinterpret_cast<float*>(sTaken + ((npts + 15) & ~15));
-  __shared__ int2 s_kv[2][FPS_WARPS];
-  __shared__ int s_scan[FPS_WARPS];
-
+template <int PPT, int RT, int PR>
+__global__ void __launch_bounds__(FPS_THREADS) fps_kernel(const __grid_constant__ FpsArgs a) {
+  extern __shared__ __align__(16) float fps_dyn_smem[];
   pdl_trigger();
   pdl_wait();   // (the depth maps may be the previous kernel's output; nothing is written before this point)
-  if (pj.n > 0 && blockIdx.x + 1 == gridDim.x) {   // one extra CTA: the step's negative-pair permutations
-    super_perms_block(pj.seed, pj.offset, pj.n, pj.B, pj.out, reinterpret_cast<int*>(fps_smem));
+  if (a.pj.n > 0 && (int)blockIdx.x == a.nimg) {   // one extra CTA: the step's negative-pair permutations
+    super_perms_block(a.pj.seed, a.pj.offset, a.pj.n, a.pj.B, a.pj.out, reinterpret_cast<int*>(fps_dyn_smem));
     return;
   }
-  const int img = blockIdx.x;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const float* gdepth = (img < B ? depth_a + (size_t)img * Hd * Wd : depth_b + (size_t)(img - B) * Hd * Wd);
-  const float* depth = gdepth;
-  if (STAGE) {
-    const int n16 = (Hd * Wd) >> 2;
-    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(sImg);
-    for (int i = tid; i < n16; i += FPS_THREADS)
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + 16u * i), "l"(gdepth + 4 * (size_t)i) : "memory");
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();
-    depth = sImg;
-  }
-
-  float X[PPT], Y[PPT], Z[PPT];
-  int key[PPT];  // int view of the running min distance; -1 once taken (or not a point)
-  const float halfH = (float)H / 2.0f, halfW = (float)W / 2.0f;
-
-#pragma unroll
-  for (int j = 0; j < PPT; ++j) {
-    const int i = j * FPS_THREADS + tid;
-    X[j] = Y[j] = Z[j] = 0.f;
-    key[j] = -1;
-    if (i < npts) {
-      const int py = i / W, px = i - py * W;
-      const int ys = (py * Hd) / H, ye = ((py + 1) * Hd + H - 1) / H;
-      const int xs = (px * Wd) / W, xe = ((px + 1) * Wd + W - 1) / W;
-      float acc = 0.f;
-      if (xe - xs == 8 && ye - ys == 8 && (Wd & 3) == 0 && (xs & 3) == 0) {
-        // the common 8x8 window: all sixteen 128-bit loads first, then add in the reference's row-major order
-        float4 v[16];
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-          const float4* row = reinterpret_cast<const float4*>(depth + (size_t)(ys + r) * Wd + xs);
-          v[2 * r] = row[0];
-          v[2 * r + 1] = row[1];
-        }
-#pragma unroll
-        for (int r = 0; r < 16; ++r) {
-          acc = __fadd_rn(acc, v[r].x); acc = __fadd_rn(acc, v[r].y);
-          acc = __fadd_rn(acc, v[r].z); acc = __fadd_rn(acc, v[r].w);
-        }
-      } else {
-        for (int y = ys; y < ye; ++y)
-          for (int x = xs; x < xe; ++x) acc = __fadd_rn(acc, depth[(size_t)y * Wd + x]);
-      }
-      const float pooled = __fdiv_rn(__fdiv_rn(acc, (float)(ye - ys)), (float)(xe - xs));  // ATen: sum / kh / kw
-      const float fd = __fmul_rn(factor, pooled);
-      X[j] = __fdiv_rn(__fmul_rn(fd, __fsub_rn((float)px, halfW)), (float)W);
-      Y[j] = __fdiv_rn(__fmul_rn(fd, __fsub_rn((float)py, halfH)), (float)H);
-      Z[j] = __fmul_rn(-pooled, far_plane);
-      key[j] = 0x7f800000;  // +inf
-      sX[i] = X[j];
-      sY[i] = Y[j];
-      sZ[i] = Z[j];
-      sTaken[i] = 0;
-    }
-  }
-  __syncthreads();
-  if (tid == 0) sTaken[0] = 1;  // point 0 is the first pick
-
-  if (tid < RT) fps_rounds<PR, RT>(sX, sY, sZ, sTaken, npts, nsel, s_kv);
-  __syncthreads();
-
-  // Raster-order emission: each thread scans a contiguous chunk of point indices.
-  const int chunk = (npts + FPS_THREADS - 1) / FPS_THREADS;
-  const int beg = tid * chunk, end = min(beg + chunk, npts);
-  int cnt = 0;
-  for (int i = beg; i < end; ++i) cnt += sTaken[i];
-  int incl = cnt;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int v = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += v;
-  }
-  if (lane == 31) s_scan[warp] = incl;
-  __syncthreads();
-  int base = 0;
-  for (int w = 0; w < warp; ++w) base += s_scan[w];
-  int rank = base + incl - cnt;
-  float* cimg = coords + (size_t)img * nsel * 2;
-  for (int i = beg; i < end; ++i) {
-    if (sTaken[i]) {
-      const int py = i / W, px = i - py * W;
-      float cy = __fdiv_rn((float)py, (float)H), cx = __fdiv_rn((float)px, (float)W);
-      if (affine) {
-        cy = __fsub_rn(__fmul_rn(cy, 2.0f), 1.0f);
-        cx = __fsub_rn(__fmul_rn(cx, 2.0f), 1.0f);
-      }
-      cimg[2 * rank + 0] = cy;
-      cimg[2 * rank + 1] = cx;
-      if (idx_out) idx_out[(size_t)img * nsel + rank] = i;
-      ++rank;
-    }
-  }
-  // fused depth_sign_kernel for the first depth tensor (the depth term of the loss only uses `depth`, not depth_pos)
-  if (dsign != nullptr && img < B) {
-    for (int p = tid; p < sign_pitch; p += FPS_THREADS)
-      dsign[(size_t)img * sign_pitch + p] = depth_sign_value(depth, Hd, Wd, sign_S, p, sign_eps);
-  }
+  fps_cta<PPT, RT, PR>(a, (int)blockIdx.x, fps_dyn_smem);
 }
 
 // s = d / max(|d|, eps) of the align_corners=True bilinear resample of depth to SxS.
@@ -291,9 +43,10 @@ __global__ void depth_sign_kernel(const float* __restrict__ depth, int B, int Hd
   out[t] = depth_sign_value(depth + (size_t)b * Hd * Wd, Hd, Wd, S, p, eps);
 }
 
-int launch_fps(const float* depth_a, const float* depth_b, int B, int Hd, int Wd, int H, int W, int S, float factor,
-               float far_plane, int affine, float* coords, int32_t* idx, cudaStream_t st, float* dsign, int sign_pitch,
-               float sign_eps, const PermJob* perm_job) {
+// Validates the arguments of an FPS launch and fills `a`; `smem` = dynamic shared memory one CTA needs.
+int make_fps_args(FpsArgs* a, size_t* smem_out, const float* depth_a, const float* depth_b, int B, int Hd, int Wd, int H,
+                  int W, int S, float factor, float far_plane, int affine, float* coords, int32_t* idx, float* dsign,
+                  int sign_pitch, float sign_eps, const PermJob* perm_job) {
   PermJob pj;
   memset(&pj, 0, sizeof pj);
   if (perm_job) pj = *perm_job;
@@ -304,28 +57,45 @@ int launch_fps(const float* depth_a, const float* depth_b, int B, int Hd, int Wd
   const int npts = H * W;
   DG_REQUIRE(S * S <= npts, DG_ERR_INVALID, "dg_fps_coords: S*S=%d exceeds H*W=%d points", S * S, npts);
   DG_REQUIRE(npts <= 4096, DG_ERR_UNSUPPORTED, "dg_fps_coords: H*W=%d > 4096 not supported", npts);
-  const int nimg = depth_b ? 2 * B : B;
-  const size_t base_smem = (size_t)((npts + 3) & ~3) * 3 * sizeof(float) + (size_t)((npts + 15) & ~15);
-  const size_t img_bytes = (size_t)Hd * Wd * sizeof(float);
-  const bool stage = ((Hd * Wd) % 4 == 0) && (base_smem + img_bytes <= 220 * 1024) &&
+  const bool stage = ((Hd * Wd) % 4 == 0) && (fps_smem_bytes(npts, Hd, Wd, true) <= 220 * 1024) &&
                      ((reinterpret_cast<uintptr_t>(depth_a) | reinterpret_cast<uintptr_t>(depth_b)) % 16 == 0);
-  size_t smem = base_smem + (stage ? img_bytes : 0);
+  size_t smem = fps_smem_bytes(npts, Hd, Wd, stage);
   if (pj.n > 0) {   // the extra CTA shuffles in shared memory and needs one thread per permutation
     DG_REQUIRE(pj.n <= FPS_THREADS && (size_t)pj.n * pj.B * sizeof(int) <= 64 * 1024, DG_ERR_UNSUPPORTED,
                "fps: %d permutations of %d do not fit the fused draw", pj.n, pj.B);
     if (smem < (size_t)pj.n * pj.B * sizeof(int)) smem = (size_t)pj.n * pj.B * sizeof(int);
   }
-#define DG_FPS_LAUNCH(PPT, ST, RTV, PRV)                                                                                    \
+  a->depth_a = depth_a; a->depth_b = depth_b;
+  a->B = B; a->Hd = Hd; a->Wd = Wd; a->H = H; a->W = W; a->nsel = S * S;
+  a->factor = factor; a->far_plane = far_plane; a->affine = affine;
+  a->coords = coords; a->idx = idx; a->dsign = dsign;
+  a->sign_S = S; a->sign_pitch = sign_pitch; a->sign_eps = sign_eps;
+  a->stage = stage ? 1 : 0;
+  a->nimg = depth_b ? 2 * B : B;
+  a->pj = pj;
+  *smem_out = smem;
+  return DG_OK;
+}
+
+int launch_fps(const float* depth_a, const float* depth_b, int B, int Hd, int Wd, int H, int W, int S, float factor,
+               float far_plane, int affine, float* coords, int32_t* idx, cudaStream_t st, float* dsign, int sign_pitch,
+               float sign_eps, const PermJob* perm_job) {
+  FpsArgs a;
+  size_t smem = 0;
+  int rc = make_fps_args(&a, &smem, depth_a, depth_b, B, Hd, Wd, H, W, S, factor, far_plane, affine, coords, idx, dsign,
+                         sign_pitch, sign_eps, perm_job);
+  if (rc != DG_OK) return rc;
+  const int npts = H * W;
+#define DG_FPS_LAUNCH(PPT, RTV, PRV)                                                                              \
   do {                                                                                                            \
     static PerDevice configured_pd = {};                                                                          \
     size_t& configured = per_device(configured_pd);                                                               \
     if (smem > 48 * 1024 && smem > configured) {                                                                  \
-      DG_CUDA_OK(cudaFuncSetAttribute(fps_kernel<PPT, ST, RTV, PRV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      DG_CUDA_OK(cudaFuncSetAttribute(fps_kernel<PPT, RTV, PRV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
       configured = smem;                                                                                          \
     }                                                                                                             \
     DG_PRE(st);                                                                                                   \
-    launch_pdl(fps_kernel<PPT, ST, RTV, PRV>, dim3(nimg + (pj.n > 0 ? 1 : 0)), dim3(FPS_THREADS), smem, st, depth_a,     \
-               depth_b, B, Hd, Wd, H, W, S * S, factor, far_plane, affine, coords, idx, dsign, S, sign_pitch, sign_eps, pj); \
+    launch_pdl(fps_kernel<PPT, RTV, PRV>, dim3(a.nimg + (a.pj.n > 0 ? 1 : 0)), dim3(FPS_THREADS), smem, st, a);   \
   } while (0)
   static int rt_env = -1;  // DEPTHG_B200_FPS_RT = 128 | 256 round threads (experiments); default FPS_DEFAULT_RT
   if (rt_env < 0) {
@@ -333,17 +103,12 @@ int launch_fps(const float* depth_a, const float* depth_b, int B, int Hd, int Wd
     rt_env = e ? atoi(e) : 0;
   }
   if (npts <= 896) {  // the 28x28 grid of the reference (784 points) lives here
-    const int rt = rt_env == 128 ? 128 : FPS_DEFAULT_RT;
-    if (stage) {
-      if (rt == 128) DG_FPS_LAUNCH(4, true, 128, 8);
-      else DG_FPS_LAUNCH(4, true, 256, 4);
-    } else {
-      if (rt == 128) DG_FPS_LAUNCH(4, false, 128, 8); else DG_FPS_LAUNCH(4, false, 256, 4);
-    }
+    if (rt_env == 128) DG_FPS_LAUNCH(4, 128, 8); else DG_FPS_LAUNCH(4, 256, 4);
   } else if (npts <= 8 * FPS_THREADS) {
-    if (stage) DG_FPS_LAUNCH(8, true, 256, 8); else DG_FPS_LAUNCH(8, false, 256, 8);
+    DG_FPS_LAUNCH(8, 256, 8);
   } else {
-    DG_FPS_LAUNCH(16, false, 256, 16);
+    a.stage = 0;
+    DG_FPS_LAUNCH(16, 256, 16);
   }
 #undef DG_FPS_LAUNCH
   DG_LAUNCH_OK("fps_kernel");

@@ -62,6 +62,8 @@ struct GroupW {
 
 // pair_dots work that the one-call loss path appends to the code gather's grid (the tcgen05 correlation kernel
 // needs dots[k,b] = <mean row of F1[b], mean row of F2[k,b]> and a cleared error flag / completion counter)
+struct FpsArgs;   // fps_body.cuh
+
 struct DotsJob {
   const float* fmean;  // [slot,b,nsplit,ldf] partial means, or null (not pointwise): only the flags are cleared
   float* dots;         // [npairs,B]
@@ -110,6 +112,9 @@ struct PermJob {
 int launch_fps(const float* depth_a, const float* depth_b, int B, int Hd, int Wd, int H, int W, int S, float factor,
                float far_plane, int affine, float* coords, int32_t* idx, cudaStream_t st, float* dsign = nullptr,
                int sign_pitch = 0, float sign_eps = 0.f, const PermJob* perm_job = nullptr);
+int make_fps_args(FpsArgs* a, size_t* smem_out, const float* depth_a, const float* depth_b, int B, int Hd, int Wd, int H,
+                  int W, int S, float factor, float far_plane, int affine, float* coords, int32_t* idx, float* dsign,
+                  int sign_pitch, float sign_eps, const PermJob* perm_job);
 int launch_depth_sign(const float* depth, int B, int Hd, int Wd, int S, float eps, int out_pitch, float* out,
                       cudaStream_t st);
 // meanvec is written as `nsplit` partial means per (slot, image): [slot,b,nsplit,ld], each already divided by P
@@ -139,11 +144,14 @@ int corr_loss_umma(const dg_panels_t* pan, const float* fmean, int nsplit, const
                    int nfslots = 0, bool dots_done = false);
 // the persistent, double-buffered tcgen05 kernel (corr_pipe.cu): same arguments; Prows a multiple of 128, partial
 // gradient buffers dC1 [npairs+1, Prows/128 (column tile), ...] and dC2 [npairs+1, Prows/128 (row tile), ...]
+// `ride` (optional): an FPS launch (make_fps_args) executed by extra CTAs of this kernel - the NEXT step's sampling, see
+// PipeParams::ride; only when corr_pipe_can_ride(*ride, ride_smem).
 int corr_loss_pipe(const dg_panels_t* pan, const float* fmean, int nsplit, const float* dsign, int npairs, int B, int P, int Prows, int ldf,
                    int ldc, const float* pair_shift, const int32_t* pair_group, float depth_shift, int flags,
                    float* out8, float* dC1, float* dC2, float* cd_out, float* loss_out, float* dd_out, float* fd_dbg,
                    void* ws, cudaStream_t st, const int32_t* fslot1 = nullptr, const int32_t* fslot2 = nullptr,
-                   int nfslots = 0, bool dots_done = false);
+                   int nfslots = 0, bool dots_done = false, const FpsArgs* ride = nullptr, size_t ride_smem = 0);
+bool corr_pipe_can_ride(const FpsArgs& a, size_t smem);
 size_t corr_pipe_workspace_floats(int npairs, int B, int P);
 // where corr_loss_umma keeps its error flag / completion counter and the pair dots inside its workspace
 void umma_ws_layout(void* ws, int** err, float** dots);

@@ -4,6 +4,7 @@
 #include <string.h>
 
 #include "kernels.cuh"
+#include "fps_body.cuh"
 
 namespace dg {
 
@@ -126,7 +127,7 @@ extern "C" int dg_loss_forward(const dg_loss_desc_t* d, const dg_loss_io_t* io, 
   DG_REQUIRE(d->neg_samples == 0 || io->perms, DG_ERR_INVALID, "dg_loss_forward: perms missing");
   const bool fps = d->flags & DG_FLAG_FPS, depth_term = d->flags & DG_FLAG_DEPTH_TERM;
   DG_REQUIRE(!fps || (io->depth && io->depth_pos), DG_ERR_INVALID, "dg_loss_forward: fps sampling needs depth and depth_pos");
-  DG_REQUIRE(!depth_term || io->depth, DG_ERR_INVALID, "dg_loss_forward: the depth term needs depth");
+  DG_REQUIRE(!depth_term || io->depth || (!fps && io->dsign), DG_ERR_INVALID, "dg_loss_forward: the depth term needs depth");
   DG_REQUIRE(fps || io->coords, DG_ERR_INVALID, "dg_loss_forward: coords missing");
   const bool aug = d->flags & DG_FLAG_AUG_INTRA;
   DG_REQUIRE(!aug || io->aug_feats, DG_ERR_INVALID, "dg_loss_forward: DG_FLAG_AUG_INTRA needs aug_feats");
@@ -161,8 +162,12 @@ extern "C" int dg_loss_forward(const dg_loss_desc_t* d, const dg_loss_io_t* io, 
     if (rc != DG_OK) return rc;
   }
   if (!fps && depth_term) {
-    rc = launch_depth_sign(io->depth, B, d->Hd, d->Wd, S, kNormEps, pl.Prows, dsign, st);
-    if (rc != DG_OK) return rc;
+    if (io->dsign) {   // sampled ahead of time (dg_loss_presample / the previous forward's next_* job)
+      dsign = const_cast<float*>(io->dsign);
+    } else {
+      rc = launch_depth_sign(io->depth, B, d->Hd, d->Wd, S, kNormEps, pl.Prows, dsign, st);
+      if (rc != DG_OK) return rc;
+    }
   }
   if (io->perms_ready) DG_CUDA_OK(cudaStreamWaitEvent(st, reinterpret_cast<cudaEvent_t>(io->perms_ready), 0));
   SetTable ftab, ctab;
@@ -260,19 +265,70 @@ extern "C" int dg_loss_forward(const dg_loss_desc_t* d, const dg_loss_io_t* io, 
   const int kflags = d->flags & (DG_FLAG_POINTWISE | DG_FLAG_ZERO_CLAMP | DG_FLAG_STABALIZE);
   float* dC1 = reinterpret_cast<float*>(A + pl.dC1);
   float* dC2 = reinterpret_cast<float*>(A + pl.dC2);
+  // the next step's sampling (io->next_*): extra CTAs of the persistent correlation kernel when it is the one that
+  // runs, else a launch of its own behind this forward
+  FpsArgs next;
+  size_t next_smem = 0;
+  const bool has_next = io->next_depth != nullptr;
+  if (has_next) {
+    DG_REQUIRE(io->next_depth_pos && io->next_coords && d->Hd > 0 && d->Wd > 0, DG_ERR_INVALID,
+               "dg_loss_forward: next_depth needs next_depth_pos, next_coords and the depth size");
+    DG_REQUIRE(io->next_n_perms == 0 || io->next_perms, DG_ERR_INVALID, "dg_loss_forward: next_perms missing");
+    PermJob npj;
+    memset(&npj, 0, sizeof npj);
+    npj.seed = io->next_perm_seed; npj.offset = io->next_perm_offset; npj.n = io->next_n_perms; npj.B = B;
+    npj.out = io->next_perms;
+    rc = make_fps_args(&next, &next_smem, io->next_depth, io->next_depth_pos, B, d->Hd, d->Wd, d->H, d->W, S,
+                       fov_factor(), kFarPlane, 1, io->next_coords, nullptr, io->next_dsign, pl.Prows, kNormEps,
+                       npj.n > 0 ? &npj : nullptr);
+    if (rc != DG_OK) return rc;
+  }
+  const bool ride = has_next && pl.kernel == 2 && corr_pipe_can_ride(next, next_smem) && !getenv("DEPTHG_B200_NO_RIDE");
   if (pl.kernel) {
     dg_panels_t pan;
     pan.format = DG_PANEL_CODE_SPLIT;
     pan.f_hi = A + pl.f_hi; pan.f_lo = A + pl.f_lo; pan.c_hi = A + pl.c_hi; pan.c_lo = A + pl.c_lo;
     pan.cb_hi = A + pl.cb_hi; pan.cb_lo = A + pl.cb_lo;
-    return (pl.kernel == 2 ? corr_loss_pipe : corr_loss_umma)(
-        &pan, fmean, nsplit, dsign, np, B, P, pl.Prows, pl.ldf, pl.ldc, shifts, groups, d->depth_feat_shift, kflags,
-        io->out8, dC1, dC2, io->cd_out, io->loss_out, io->dd_out, io->fd_dbg, A + pl.ws, st, fs1, fs2, aug ? np + 1 : np,
-        dots_done);
+    if (pl.kernel == 2)
+      rc = corr_loss_pipe(&pan, fmean, nsplit, dsign, np, B, P, pl.Prows, pl.ldf, pl.ldc, shifts, groups,
+                          d->depth_feat_shift, kflags, io->out8, dC1, dC2, io->cd_out, io->loss_out, io->dd_out,
+                          io->fd_dbg, A + pl.ws, st, fs1, fs2, aug ? np + 1 : np, dots_done, ride ? &next : nullptr,
+                          next_smem);
+    else
+      rc = corr_loss_umma(&pan, fmean, nsplit, dsign, np, B, P, pl.Prows, pl.ldf, pl.ldc, shifts, groups,
+                          d->depth_feat_shift, kflags, io->out8, dC1, dC2, io->cd_out, io->loss_out, io->dd_out,
+                          io->fd_dbg, A + pl.ws, st, fs1, fs2, aug ? np + 1 : np, dots_done);
+  } else {
+    rc = corr_loss_simt(reinterpret_cast<const float*>(A + pl.f_hi), reinterpret_cast<const float*>(A + pl.c_hi), fmean,
+                        nsplit, dsign, np, B, P, pl.Prows, pl.ldf, pl.ldc, shifts, groups, d->depth_feat_shift, kflags,
+                        io->out8, dC1, dC2, io->cd_out, io->loss_out, io->dd_out, A + pl.ws, st, fs1, fs2);
   }
-  return corr_loss_simt(reinterpret_cast<const float*>(A + pl.f_hi), reinterpret_cast<const float*>(A + pl.c_hi), fmean,
-                        nsplit, dsign, np, B, P, pl.Prows, pl.ldf, pl.ldc, shifts, groups, d->depth_feat_shift, kflags, io->out8,
-                        dC1, dC2, io->cd_out, io->loss_out, io->dd_out, A + pl.ws, st, fs1, fs2);
+  if (rc != DG_OK) return rc;
+  if (has_next && !ride)
+    return launch_fps(io->next_depth, io->next_depth_pos, B, d->Hd, d->Wd, d->H, d->W, S, fov_factor(), kFarPlane, 1,
+                      io->next_coords, nullptr, st, io->next_dsign, pl.Prows, kNormEps, next.pj.n > 0 ? &next.pj : nullptr);
+  return DG_OK;
+}
+
+extern "C" int dg_loss_presample(const dg_loss_desc_t* d, const float* depth, const float* depth_pos, float* coords,
+                                 float* dsign, int64_t* perms, int n_perms, unsigned long long perm_seed,
+                                 unsigned long long perm_offset, dg_stream_t stream) {
+  using namespace dg;
+  int rc = check_desc(d);
+  if (rc != DG_OK) return rc;
+  DG_REQUIRE(depth && depth_pos && coords && d->Hd > 0 && d->Wd > 0, DG_ERR_INVALID, "dg_loss_presample: null pointer / depth size");
+  DG_REQUIRE(n_perms == 0 || perms, DG_ERR_INVALID, "dg_loss_presample: perms missing");
+  dg_loss_plan_t pl;
+  make_plan(d, &pl);
+  PermJob pj;
+  memset(&pj, 0, sizeof pj);
+  pj.seed = perm_seed; pj.offset = perm_offset; pj.n = n_perms; pj.B = d->B; pj.out = perms;
+  const bool fuse = n_perms > 0 && n_perms <= 256 && (size_t)n_perms * d->B * sizeof(int) <= 64 * 1024;
+  rc = launch_fps(depth, depth_pos, d->B, d->Hd, d->Wd, d->H, d->W, d->S, fov_factor(), kFarPlane, 1, coords, nullptr,
+                  reinterpret_cast<cudaStream_t>(stream), dsign, pl.Prows, kNormEps, fuse ? &pj : nullptr);
+  if (rc != DG_OK) return rc;
+  if (n_perms > 0 && !fuse) return dg_super_perms(perm_seed, perm_offset, n_perms, d->B, perms, stream);
+  return DG_OK;
 }
 
 extern "C" int dg_loss_backward(const dg_loss_desc_t* d, const dg_loss_io_t* io, const dg_loss_grads_t* gr,

@@ -52,7 +52,11 @@ class CorrLossFn : public torch::autograd::Function<CorrLossFn> {
                                c10::optional<Tensor> depth, c10::optional<Tensor> depth_pos,
                                c10::optional<Tensor> coords, c10::optional<Tensor> perms,
                                c10::optional<Tensor> aug_feats, std::vector<int64_t> ints, std::vector<double> shifts,
-                               bool materialize, bool want_fd, bool prezero_grads, int64_t perms_event) {
+                               bool materialize, bool want_fd, bool prezero_grads, int64_t perms_event,
+                               c10::optional<Tensor> dsign, c10::optional<Tensor> next_depth,
+                               c10::optional<Tensor> next_depth_pos, c10::optional<Tensor> next_coords,
+                               c10::optional<Tensor> next_dsign, c10::optional<Tensor> next_perms,
+                               std::vector<int64_t> next_rng) {
     TORCH_CHECK((ints.size() == 10 || ints.size() == 12) && shifts.size() == 4,
                 "corr_loss: ints[10 or 12] / shifts[4] expected");
     dg_loss_desc_t d = make_desc(ints, shifts);
@@ -107,6 +111,21 @@ class CorrLossFn : public torch::autograd::Function<CorrLossFn> {
       }
     }
     io.perms_ready = reinterpret_cast<void*>(perms_event);
+    io.dsign = fptr(dsign);                       // sampled ahead of time (dg_loss_io_t::dsign)
+    if (next_depth.has_value() && next_depth->defined()) {   // the next step's sampling rides in this forward
+      TORCH_CHECK(next_depth_pos.has_value() && next_coords.has_value(), "corr_loss: incomplete next-sampling job");
+      io.next_depth = next_depth->data_ptr<float>();
+      io.next_depth_pos = next_depth_pos->data_ptr<float>();
+      io.next_coords = next_coords->data_ptr<float>();
+      io.next_dsign = next_dsign.has_value() && next_dsign->defined() ? next_dsign->data_ptr<float>() : nullptr;
+      if (next_perms.has_value() && next_perms->defined()) {
+        TORCH_CHECK(next_rng.size() == 2, "corr_loss: next_rng = (seed, offset) expected");
+        io.next_perms = next_perms->data_ptr<int64_t>();
+        io.next_n_perms = (int)next_perms->size(0);
+        io.next_perm_seed = static_cast<unsigned long long>(next_rng[0]);
+        io.next_perm_offset = static_cast<unsigned long long>(next_rng[1]);
+      }
+    }
     if (ints.size() >= 12) {   // the forward draws the permutations itself into `perms`
       io.gen_perms = 1;
       io.perm_seed = static_cast<unsigned long long>(ints[10]);    // two's-complement round trip of torch's uint64 seed
@@ -182,7 +201,7 @@ class CorrLossFn : public torch::autograd::Function<CorrLossFn> {
     if (ctx->saved_data.count("coords")) io.coords = ctx->saved_data["coords"].toTensor().data_ptr<float>();
     if (ctx->saved_data.count("perms")) io.perms = ctx->saved_data["perms"].toTensor().data_ptr<int64_t>();
     check(dg_loss_backward(&d, &io, &gr, reinterpret_cast<dg_stream_t>(stream.stream())), "dg_loss_backward");
-    variable_list out(15);
+    variable_list out(22);
     out[2] = d_code;
     out[3] = d_code_pos;
     return out;
@@ -192,9 +211,14 @@ class CorrLossFn : public torch::autograd::Function<CorrLossFn> {
 std::vector<Tensor> corr_loss(Tensor feats, Tensor feats_pos, Tensor code, Tensor code_pos, c10::optional<Tensor> depth,
                               c10::optional<Tensor> depth_pos, c10::optional<Tensor> coords, c10::optional<Tensor> perms,
                               c10::optional<Tensor> aug_feats, std::vector<int64_t> ints, std::vector<double> shifts,
-                              bool materialize, bool want_fd, bool prezero_grads, int64_t perms_event) {
+                              bool materialize, bool want_fd, bool prezero_grads, int64_t perms_event,
+                              c10::optional<Tensor> dsign, c10::optional<Tensor> next_depth,
+                              c10::optional<Tensor> next_depth_pos, c10::optional<Tensor> next_coords,
+                              c10::optional<Tensor> next_dsign, c10::optional<Tensor> next_perms,
+                              std::vector<int64_t> next_rng) {
   return CorrLossFn::apply(feats, feats_pos, code, code_pos, depth, depth_pos, coords, perms, aug_feats, ints, shifts,
-                           materialize, want_fd, prezero_grads, perms_event);
+                           materialize, want_fd, prezero_grads, perms_event, dsign, next_depth, next_depth_pos,
+                           next_coords, next_dsign, next_perms, next_rng);
 }
 
 std::vector<int64_t> loss_plan(std::vector<int64_t> ints) {

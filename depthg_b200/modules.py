@@ -159,6 +159,17 @@ class _GraphedSuperPerms:
             gen.set_state(state)            # neither warm-up nor capture (failed or not) may consume the user's RNG stream
 
 
+_side_streams = {}
+
+
+def _side_stream(device):
+    """One side stream per device for work that overlaps the caller's stream (prefetch_sampling)."""
+    st = _side_streams.get(device.index)
+    if st is None:
+        st = _side_streams[device.index] = torch.cuda.Stream(device=device)
+    return st
+
+
 def _reserve_perm_stream(size: int, device):
     """(seed, offset) of the Philox stream the one-launch sampler uses for this draw; advances torch's CUDA generator
     past it, so ``torch.manual_seed`` makes runs reproducible and successive draws differ."""
@@ -346,6 +357,7 @@ def depth_correlation(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
 # --------------------------------------------------------------------------- the loss
 _compiled_mod = None
 _plan_cache = {}
+_prows_cache = {}
 
 
 def compiled_binding():
@@ -519,6 +531,9 @@ class ContrastiveCorrelationLoss(nn.Module):
         self.wait_after_fps = None
         self.last_perms = None
         self._last_coords = None
+        # sampling done ahead of the forward that uses it (queue_next_sampling / prefetch_sampling)
+        self._next_job = None       # (depth, depth_pos) whose sampling rides in the NEXT forward call
+        self._presampled = None     # dict(key, coords, dsign, perms, event) waiting for the forward of that batch
 
     @property
     def last_coords(self):
@@ -534,6 +549,66 @@ class ContrastiveCorrelationLoss(nn.Module):
     @last_coords.setter
     def last_coords(self, value):
         self._last_coords = value
+
+    @staticmethod
+    def _depth4(depth):
+        """[B,Hd,Wd] -> [B,1,Hd,Wd] (the Potsdam dataset yields depth without a channel axis, src/data.py:226), contiguous."""
+        if depth is not None and depth.dim() == 3:
+            depth = depth.unsqueeze(1)
+        return depth.contiguous() if depth is not None else None
+
+    @staticmethod
+    def _sampling_key(depth, depth_pos, S, H, W, nneg):
+        return (depth.data_ptr(), depth._version, tuple(depth.shape), depth_pos.data_ptr(), depth_pos._version,
+                tuple(depth_pos.shape), S, H, W, nneg)
+
+    def queue_next_sampling(self, depth, depth_pos):
+        """Hand the NEXT batch's depth maps to the loss before calling ``forward`` on the CURRENT batch: the next
+        batch's farthest-point sampling (coordinates, depth signs, negative permutations) then rides as extra CTAs of
+        this forward's correlation kernel, on SMs its item list leaves idle (dg_loss_io_t::next_*), and the forward that
+        later receives exactly these tensors starts at its gathers — FPS (src/modules.py:999-1037, 14 % of a step) is
+        off the critical path.  A forward that receives other depth tensors simply samples as usual.  Only
+        ``depth_sampling in ('fps', 'fps_depth_feat')`` uses it."""
+        if depth is None or depth_pos is None:
+            self._next_job = None
+            return
+        for name, t in (("depth", depth), ("depth_pos", depth_pos)):
+            require_cuda_f32(t, name)
+        self._next_job = (self._depth4(depth), self._depth4(depth_pos))
+
+    def prefetch_sampling(self, depth, depth_pos, grid_hw, stream=None):
+        """The sampling of the batch whose ``forward`` comes later in this training step, launched NOW on a side stream
+        (dg_loss_presample) — e.g. at the top of ``training_step``, so that it runs under the backbone's forward pass.
+        ``grid_hw`` = (H, W) of the feature maps the loss will see.  The forward that receives these depth tensors waits
+        for the side stream and skips its own FPS launch."""
+        cfg = self.cfg
+        for name, t in (("depth", depth), ("depth_pos", depth_pos)):
+            require_cuda_f32(t, name)
+        depth, depth_pos = self._depth4(depth), self._depth4(depth_pos)
+        if depth.dim() != 4 or depth.shape[1] != 1 or depth_pos.shape != depth.shape:
+            raise ValueError("depth / depth_pos must be [B,1,Hd,Wd] (or [B,Hd,Wd]) of one shape")
+        dev = depth.device
+        B, _, Hd, Wd = depth.shape
+        H, W = int(grid_hw[0]), int(grid_hw[1])
+        S, nneg = int(cfg.feature_samples), int(cfg.neg_samples)
+        fused = nneg > 0 and self.negative_sampler == "fused" and self.perm_fn is super_perm
+        desc = _lib.LossDesc(B, 32, 32, H, W, Hd, Wd, S, nneg, 0, 0.0, 0.0, 0.0, 0.0)
+        plan = _lib.LossPlan()
+        check(_lib.lib().dg_loss_plan(C.byref(desc), C.byref(plan)), "dg_loss_plan")
+        side = stream if stream is not None else _side_stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))      # the depth maps are ready on the caller's stream
+        seed, offset = _reserve_perm_stream(B, dev) if fused else (0, 0)
+        with torch.cuda.device(dev), torch.cuda.stream(side):
+            coords = torch.empty((2, B, S, S, 2), device=dev, dtype=torch.float32)
+            dsign = torch.empty((B, plan.Prows), device=dev, dtype=torch.float32)
+            perms = torch.empty((nneg, B), device=dev, dtype=torch.long) if fused else None
+            check(_lib.lib().dg_loss_presample(C.byref(desc), ptr(depth), ptr(depth_pos), ptr(coords), ptr(dsign),
+                                               ptr(perms), nneg if fused else 0, seed, offset, side.cuda_stream),
+                  "dg_loss_presample")
+            ev = torch.cuda.Event()
+            ev.record(side)
+        self._presampled = dict(key=self._sampling_key(depth, depth_pos, S, H, W, nneg), coords=coords, dsign=dsign,
+                                perms=perms, event=ev, keep=(depth, depth_pos))
 
     def _flags(self):
         cfg = self.cfg
@@ -606,32 +681,6 @@ class ContrastiveCorrelationLoss(nn.Module):
             c1 = self.rand_fn(shape, dev) * 2 - 1
             c2 = self.rand_fn(shape, dev) * 2 - 1
             coords = torch.stack([c1, c2]).float().contiguous()
-        also_wait, self.wait_after_fps = self.wait_after_fps, None
-        perm_gen = None
-        self.last_perms = None
-        if not nneg:
-            perms = None
-        elif self.perm_fn is not super_perm:
-            perms = torch.stack([self.perm_fn(B, dev) for _ in range(nneg)]).to(torch.long).contiguous()
-        elif self.negative_sampler == "fused" and not torch.cuda.is_current_stream_capturing():
-            # drawn by the forward itself (one extra CTA of its FPS launch): only the buffer and the stream position
-            # are fixed here
-            perms = torch.empty((nneg, B), device=dev, dtype=torch.long)
-            perm_gen = _reserve_perm_stream(B, dev)
-        elif self.negative_sampler == "fused":
-            # under CUDA-graph capture the generator's offset cannot be read on the host: torch.randperm is graph-safe
-            perms = super_perms(nneg, B, dev)
-        elif self.graph_negative_sampler:
-            perms, perms_event = _GraphedSuperPerms.draw_async(nneg, B, dev, also_wait)
-        else:
-            perms = super_perms(nneg, B, dev)
-        if also_wait is not None and perms_event is None:
-            # no sampler stream to fold it into: the library waits for this event itself, right after launching FPS
-            # (dg_loss_io_t.perms_ready is exactly that wait)
-            perms_event = also_wait
-
-        self.last_perms = perms     # [neg_samples,B] source image of every negative (test hook; filled by the forward
-        #                             itself with the default sampler)
         depth_term = depth_term and aug_feats is None
         Hd = Wd = 0
         if depth_term or (flags & _lib.FLAG_FPS):
@@ -653,6 +702,48 @@ class ContrastiveCorrelationLoss(nn.Module):
             Hd, Wd = depth.shape[-2:]
             if depth_term:
                 flags |= _lib.FLAG_DEPTH_TERM
+        # Was this batch sampled ahead of time (queue_next_sampling of the previous call / prefetch_sampling)?  Then the
+        # forward takes coordinates, depth signs and permutations from there and launches no FPS.
+        pre, self._presampled = self._presampled, None
+        dsign_in = None
+        use_pre = False
+        self.last_used_presampled = False      # test hook
+        if pre is not None and (flags & _lib.FLAG_FPS) and depth_pos is not None and compiled_binding() and \
+                not _CorrLossFn.debug and pre["key"] == self._sampling_key(depth, depth_pos, S, H, W, nneg):
+            use_pre = self.last_used_presampled = True
+            flags &= ~_lib.FLAG_FPS
+            coords = pre["coords"]
+            dsign_in = pre["dsign"] if depth_term else None
+            if pre["event"] is not None:
+                torch.cuda.current_stream(dev).wait_event(pre["event"])
+        also_wait, self.wait_after_fps = self.wait_after_fps, None
+        perm_gen = None
+        self.last_perms = None
+        if not nneg:
+            perms = None
+        elif use_pre and pre["perms"] is not None and self.perm_fn is super_perm and self.negative_sampler == "fused":
+            perms = pre["perms"]        # drawn together with the coordinates
+        elif self.perm_fn is not super_perm:
+            perms = torch.stack([self.perm_fn(B, dev) for _ in range(nneg)]).to(torch.long).contiguous()
+        elif self.negative_sampler == "fused" and not torch.cuda.is_current_stream_capturing():
+            # drawn by the forward itself (one extra CTA of its FPS launch): only the buffer and the stream position
+            # are fixed here
+            perms = torch.empty((nneg, B), device=dev, dtype=torch.long)
+            perm_gen = _reserve_perm_stream(B, dev)
+        elif self.negative_sampler == "fused":
+            # under CUDA-graph capture the generator's offset cannot be read on the host: torch.randperm is graph-safe
+            perms = super_perms(nneg, B, dev)
+        elif self.graph_negative_sampler:
+            perms, perms_event = _GraphedSuperPerms.draw_async(nneg, B, dev, also_wait)
+        else:
+            perms = super_perms(nneg, B, dev)
+        if also_wait is not None and perms_event is None:
+            # no sampler stream to fold it into: the library waits for this event itself, right after launching FPS
+            # (dg_loss_io_t.perms_ready is exactly that wait)
+            perms_event = also_wait
+
+        self.last_perms = perms     # [neg_samples,B] source image of every negative (test hook; filled by the forward
+        #                             itself with the default sampler)
         if corr_kernel_choice(S * S, orig_code.shape[1]) == "simt":
             flags |= _lib.FLAG_FORCE_SIMT
         elif Cdim % 128 == 0 and orig_feats.is_contiguous() and orig_feats_pos.is_contiguous() and \
@@ -675,10 +766,33 @@ class ContrastiveCorrelationLoss(nn.Module):
             if perm_gen is not None:     # (seed as a signed 64-bit value: the binding casts it back)
                 seed = perm_gen[0] - (1 << 64) if perm_gen[0] >= (1 << 63) else perm_gen[0]
                 ints = ints + (seed, perm_gen[1])
+            # the next batch's sampling rides in this forward (queue_next_sampling)
+            nxt, self._next_job = self._next_job, None
+            n_coords = n_dsign = n_perms = None
+            n_rng = []
+            fps_mode = use_pre or bool(flags & _lib.FLAG_FPS)
+            if nxt is not None and fps_mode and aug_feats is None and nxt[0].shape == depth.shape and \
+                    nxt[1].shape == depth.shape and not torch.cuda.is_current_stream_capturing():
+                Prows = _prows_cache.get(ints[:10])
+                if Prows is None:
+                    Prows = _prows_cache[ints[:10]] = binding.loss_plan(list(ints[:10]))[5]
+                n_coords = torch.empty((2, B, S, S, 2), device=dev, dtype=torch.float32)
+                n_dsign = torch.empty((B, Prows), device=dev, dtype=torch.float32)
+                if nneg and self.negative_sampler == "fused" and self.perm_fn is super_perm:
+                    n_perms = torch.empty((nneg, B), device=dev, dtype=torch.long)
+                    sd, off = _reserve_perm_stream(B, dev)
+                    n_rng = [sd - (1 << 64) if sd >= (1 << 63) else sd, off]
+            else:
+                nxt = None
             res = binding.corr_loss(orig_feats, orig_feats_pos, orig_code, orig_code_pos, depth, depth_pos, coords,
                                     perms, aug_feats, ints, shifts, bool(self.materialize_cd), False,
                                     torch.is_grad_enabled(),   # gradient buffers zeroed inside the forward's launches
-                                    perms_event.cuda_event if perms_event is not None else 0)
+                                    perms_event.cuda_event if perms_event is not None else 0,
+                                    dsign_in, nxt[0] if nxt else None, nxt[1] if nxt else None, n_coords, n_dsign,
+                                    n_perms, n_rng)
+            if nxt is not None:     # same stream as the forward that will use it: no event needed
+                self._presampled = dict(key=self._sampling_key(nxt[0], nxt[1], S, H, W, nneg), coords=n_coords,
+                                        dsign=n_dsign, perms=n_perms, event=None, keep=nxt)
             intra, inter, neg, dloss, out8, coords_src = res[:6]
             cd_out, loss_out = (res[6], res[7]) if self.materialize_cd else (None, None)
             dd_out = res[8] if (self.materialize_cd and depth_term) else None
@@ -689,7 +803,7 @@ class ContrastiveCorrelationLoss(nn.Module):
             intra, inter, neg, dloss, out8, coords_src, cd_out, loss_out, dd_out = res
             coords_off = _CorrLossFn.last_coords_off
         # FPS coordinates stay in the arena until someone asks for them (see the last_coords property)
-        self._last_coords = (coords_src, coords_off, B, S) if (flags & _lib.FLAG_FPS) else coords
+        self._last_coords = (coords_src, coords_off, B, S) if (flags & _lib.FLAG_FPS) else coords.view(2, B, S, S, 2)
         if self.materialize_cd:
             five = (B, S, S, S, S)
             intra_cd, inter_cd = cd_out[0].view(five), cd_out[1].view(five)

@@ -262,6 +262,23 @@ typedef struct dg_loss_io {
      fill launches between forward and backward.  The work rides in the code-gather launch.  NULL / 0 = nothing. */
   void* clear[2];
   size_t clear_bytes[2];
+  /* Sampling done ahead of time (dg_loss_presample, or the next_* job of the previous forward): without DG_FLAG_FPS the
+     forward takes `coords` and `perms` from the caller anyway; `dsign` (optional, [B, Prows] as dg_loss_presample
+     writes it) replaces the depth-sign launch of the depth term. */
+  const float* dsign;
+  /* The NEXT step's sampling, computed inside THIS forward: when next_depth is set, FPS of (next_depth, next_depth_pos)
+     - coordinates, depth signs and (next_n_perms > 0) that step's permutations from (next_perm_seed, next_perm_offset)
+     - is written to next_coords [2,B,S*S,2] / next_dsign [B,Prows] (may be NULL) / next_perms [n,B], exactly as
+     dg_loss_presample would.  The work rides as extra CTAs of the correlation kernel, on SMs that its item list
+     leaves idle, so the next forward (called with these buffers as coords / dsign / perms and without DG_FLAG_FPS)
+     has no FPS on its critical path.  Shapes are this step's (B, Hd, Wd, H, W, S). */
+  const float* next_depth;
+  const float* next_depth_pos;
+  float* next_coords;
+  float* next_dsign;
+  int64_t* next_perms;
+  unsigned long long next_perm_seed, next_perm_offset;
+  int next_n_perms;
 } dg_loss_io_t;
 
 typedef struct dg_loss_grads {
@@ -272,6 +289,14 @@ typedef struct dg_loss_grads {
 } dg_loss_grads_t;
 
 DG_API int dg_loss_plan(const dg_loss_desc_t* desc, dg_loss_plan_t* plan);
+/* The sampling of one forward as its own launch (any stream - e.g. a side stream under the backbone's forward pass):
+ * farthest_point_sampling_depth of depth and depth_pos (src/modules.py:999-1037) -> coords [2,B,S*S,2] in [-1,1],
+ * the depth signs of the depth term -> dsign [B,Prows] (NULL to skip; Prows from dg_loss_plan), and n_perms > 0
+ * permutations of super_perm (src/modules.py:1184-1188) from (perm_seed, perm_offset) -> perms [n_perms,B].
+ * Uses desc->B, Hd, Wd, H, W, S. */
+DG_API int dg_loss_presample(const dg_loss_desc_t* desc, const float* depth, const float* depth_pos, float* coords,
+                             float* dsign, int64_t* perms, int n_perms, unsigned long long perm_seed,
+                             unsigned long long perm_offset, dg_stream_t stream);
 DG_API int dg_loss_forward(const dg_loss_desc_t* desc, const dg_loss_io_t* io, dg_stream_t stream);
 DG_API int dg_loss_backward(const dg_loss_desc_t* desc, const dg_loss_io_t* io, const dg_loss_grads_t* grads,
                             dg_stream_t stream);

@@ -636,6 +636,71 @@ def test_partial_and_repeated_backward_use_fresh_zeroed_gradient_buffers():
     assert rel_err(g_twice, 2 * g_once) < 1e-6 and rel_err(gp_twice, 2 * gp_once) < 1e-6
 
 
+def _sampling_ahead_inputs(seed, B=4, C=128, D=32):
+    g = torch.Generator().manual_seed(seed)
+    feat = lambda ch: torch.randn((B, 28, 28, ch), generator=g).permute(0, 3, 1, 2).to(dev())  # noqa: E731
+    depth = lambda: torch.randint(0, 256, (B, 1, 224, 224), generator=g).float().to(dev())     # noqa: E731
+    return dict(feats=feat(C), feats_pos=feat(C), code=feat(D), code_pos=feat(D), depth=depth(), depth_pos=depth())
+
+
+@pytest.mark.parametrize("how", ["ride_along", "side_stream", "ride_along_no_ride_kernel"])
+def test_sampling_done_ahead_of_the_forward_changes_nothing(how, monkeypatch):
+    """queue_next_sampling (the next batch's FPS rides as extra CTAs of this forward's correlation kernel) and
+    prefetch_sampling (dg_loss_presample on a side stream): the forward that consumes the pre-computed coordinates,
+    depth signs and permutations must give what a plain forward gives on the same permutations - bit-identical
+    coordinates (src/modules.py:999-1037), losses and gradients equal up to the atomics' summation order.  A forward
+    that receives OTHER depth tensors than the ones sampled ahead must ignore the stale sampling."""
+    from depthg_b200.modules import ContrastiveCorrelationLoss
+    from types import SimpleNamespace
+    if how == "ride_along_no_ride_kernel":
+        monkeypatch.setenv("DEPTHG_B200_NO_RIDE", "1")      # the next_* job as a launch of its own behind the forward
+    cfg = SimpleNamespace(feature_samples=11, neg_samples=3, depth_sampling="fps", pointwise=True, zero_clamp=True,
+                          stabalize=False, use_salience=False, depth_feat_correlation_loss=True, pos_intra_shift=0.18,
+                          pos_inter_shift=0.12, neg_inter_shift=0.46, depth_feat_shift=0.0)
+    s1, s2, s3 = (_sampling_ahead_inputs(k) for k in (11, 12, 13))
+
+    def step(fn, s):
+        code = s["code"].detach().clone().requires_grad_(True)
+        code_pos = s["code_pos"].detach().clone().requires_grad_(True)
+        out = fn(s["feats"], s["feats_pos"], None, None, code, code_pos, s["depth"], s["depth_pos"])
+        (out[0] + out[2] + out[4].mean() + out[6]).backward()
+        torch.cuda.synchronize()
+        return ([float(out[i].mean()) for i in (0, 2, 4, 6)], code.grad.cpu().numpy(), code_pos.grad.cpu().numpy(),
+                fn.last_coords.cpu().numpy().copy(), fn.last_perms.cpu().clone())
+
+    torch.manual_seed(3)
+    fn = ContrastiveCorrelationLoss(cfg)
+    if how == "side_stream":
+        step(fn, s1)
+        fn.prefetch_sampling(s2["depth"], s2["depth_pos"], (28, 28))
+    else:
+        fn.queue_next_sampling(s2["depth"], s2["depth_pos"])
+        step(fn, s1)
+    assert fn._presampled is not None
+    got = step(fn, s2)
+    assert fn.last_used_presampled and fn._presampled is None
+
+    def plain(s, perms):
+        ref = ContrastiveCorrelationLoss(cfg)
+        it = iter(perms.to(dev()))
+        ref.perm_fn = lambda B, device: next(it).clone()
+        r = step(ref, s)
+        assert not ref.last_used_presampled
+        return r
+
+    want = plain(s2, got[4])
+    assert np.array_equal(got[3], want[3])                      # coordinates: bit-identical
+    assert np.allclose(got[0], want[0], rtol=1e-6, atol=1e-7)
+    assert rel_err(got[1], want[1]) < 1e-6 and rel_err(got[2], want[2]) < 1e-6
+    # stale sampling: queued for s3, but the next forward sees s2 again -> ignored, plain result
+    fn.queue_next_sampling(s3["depth"], s3["depth_pos"])
+    step(fn, s1)
+    again = step(fn, s2)
+    assert not fn.last_used_presampled
+    want2 = plain(s2, again[4])
+    assert np.array_equal(again[3], want2[3]) and rel_err(again[1], want2[1]) < 1e-6
+
+
 def test_graphed_super_perms_reproduce_the_eager_torch_stream():
     """The CUDA-graph replay of neg_samples x torch.randperm must give the eager calls' permutations
     (same seed -> same stream), call after call, and advance the generator identically."""

@@ -485,10 +485,24 @@ def main():
         if flags.item() == 0.0:
             ar_mode, ar_stream, ar_graph = "async", None, None
 
+    # Sampling one batch ahead (default): before the forward of batch i the loss is handed batch i+1's depth maps
+    # (queue_next_sampling); their farthest-point sampling then runs as extra CTAs of forward i's correlation kernel,
+    # on SMs that kernel's item list leaves idle, and forward i+1 starts at its gathers.  Every timed step still
+    # computes exactly one batch's sampling inside the timed region (step i computes batch i+1's).
+    # DEPTHG_BENCH_LOOKAHEAD=0 turns it off; the plain step is always reported as the side key `no_lookahead`.
+    lookahead = [os.environ.get("DEPTHG_BENCH_LOOKAHEAD", "1") != "0"]
+    # at N > 1 the head-gradient all-reduce of step i runs on a side stream; with look-ahead there is no FPS kernel at
+    # the start of step i+1 to hide it under: "gather" makes step i+1 wait for it before its gathers, "free" (default)
+    # lets it run beside them (it only has to land before the next all-reduce / the end of the timed region)
+    ar_wait = os.environ.get("DEPTHG_BENCH_AR_WAIT", "free")
+
     def step(i):
         s = sets[i % NSETS]
         s["code"].grad = None
         s["code_pos"].grad = None
+        if lookahead[0]:
+            nx = sets[(i + 1) % NSETS]
+            loss_fn.queue_next_sampling(nx["depth"], nx["depth_pos"])
         out = loss_fn(s["feats"], s["feats_pos"], None, None, s["code"], s["code_pos"], s["depth"], s["depth_pos"])
         backprop(out)
         if ar_mode == "async":   # DDP semantics: the only exchange is the head-gradient all-reduce; like DDP it is
@@ -502,7 +516,8 @@ def main():
             with torch.cuda.stream(ar_stream):
                 ar_symm()
                 ar_done.record(ar_stream)
-            loss_fn.wait_after_fps = ar_done
+            if not (lookahead[0] and ar_wait == "free"):
+                loss_fn.wait_after_fps = ar_done
         elif ar_symm is not None:
             ar_symm()
         elif ar_mode == "graph" and ar_fps:
@@ -510,7 +525,8 @@ def main():
             with torch.cuda.stream(ar_stream):
                 ar_graph.replay()
                 ar_done.record(ar_stream)
-            loss_fn.wait_after_fps = ar_done    # the next forward waits for it between its FPS and its gathers
+            if not (lookahead[0] and ar_wait == "free"):
+                loss_fn.wait_after_fps = ar_done    # the next forward waits for it between its FPS and its gathers
         elif ar_mode == "graph":
             ar_stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(ar_stream):
@@ -551,6 +567,26 @@ def main():
         ms = float(t.item())
     ms_per_step = ms / args.steps
     value = world * B * args.steps / (ms / 1e3)
+
+    # the plain step: every forward samples its own batch (FPS at the head of the step)
+    look_default = lookahead[0]
+    lookahead[0] = False
+    loss_fn.queue_next_sampling(None, None)
+    loss_fn._presampled = None
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    ev0.record()
+    for i in range(args.steps):
+        step(i)
+    drain()
+    ev1.record()
+    barrier()
+    ms_plain = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms_plain], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_plain = float(t.item())
 
     # same step with negative_sampler="torch": neg_samples x torch.randperm replayed as a CUDA graph on a side stream
     # (the reference's exact RNG stream; more host work per step)
@@ -938,14 +974,23 @@ def main():
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": workload_config(B, world, extra={
                     "l2_policy": f"rotating {NSETS} input sets ({NSETS * step_bytes / 1e6:.0f} MB) > 126 MB L2",
-                    "negative_sampler": "fused (module default: one dg_super_perms launch)",
+                    "negative_sampler": "fused (module default: drawn by one CTA of the sampling launch)",
+                    "sampling_schedule": ("one batch ahead: batch i+1's FPS / depth signs / permutations ride as extra "
+                                          "CTAs of forward i's correlation kernel (queue_next_sampling); every timed "
+                                          "step computes one batch's sampling" if look_default else
+                                          "in step: FPS is the first launch of every forward"),
                     "allreduce_floats_per_step": HEAD_GRAD_FLOATS if ar_mode != "none" else 0,
                     "allreduce_issue": ar_mode + ("_inline" if ar_inline else "_hp" if ar_hp else
-                                                  "_under_next_fps" if ar_fps else ""),
+                                                  ("_beside_next_gathers" if (look_default and ar_wait == "free")
+                                                   else "_under_next_fps") if ar_fps else ""),
                     "layout": "nchw" if args.nchw else "channels_last (live trainer layout)"}),
                 "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches),
                 "launches_per_step": launches / args.steps, "roofline": roofline, "roofline_step": roofline_step,
                 "breakdown_us": {k: round(v, 2) for k, v in breakdown.items()}, "cpu_baseline": cpu_baseline,
+                "no_lookahead": {"value": world * B * args.steps / (ms_plain / 1e3), "unit": UNIT,
+                                 "ms_per_step": ms_plain / args.steps,
+                                 "note": "the same step with the sampling inside it (FPS first, then the gathers): what "
+                                         "a caller gets without queue_next_sampling / prefetch_sampling"},
                 "cuda_graph": graphed, "reference_ops_on_gpu": ref_gpu,
                 "torch_negative_sampler": {"value": world * B * args.steps / (ms_fused / 1e3), "unit": UNIT,
                                            "ms_per_step": ms_fused / args.steps,

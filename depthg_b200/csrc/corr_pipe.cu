@@ -125,18 +125,35 @@ __device__ __forceinline__ void praise(int* err, int code) {
 
 // where, inside item n+1's feature-chunk stream, the previous item's gradient GEMM groups are issued (chunk index they
 // precede) and where the producer issues the second code fill: fractions of the chunk count, see the file header
+// A ride-along CTA (PipeParams::ride).  Deliberately NOT inlined: with the FPS body inside corr_pipe_kernel the
+// compiler's code for the correlation roles came out 8 us slower (79 vs 71 us at cfg2).
+__device__ __noinline__ void ride_cta(const FpsArgs& a, int c, uint8_t* smem, long long* clk) {
+  pdl_trigger();
+  pdl_wait();
+  if (clk && threadIdx.x == 0) {   // phase stamps (dg_debug_set_clock_buffer): slot 1 = start, slot 9 = end of the CTA
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    clk[(size_t)blockIdx.x * 16 + 1] = t;
+  }
+  if (c == a.nimg) {           // (only present when a.pj.n > 0) all threads of the CTA draw the permutations
+    super_perms_block(a.pj.seed, a.pj.offset, a.pj.n, a.pj.B, a.pj.out, reinterpret_cast<int*>(smem));
+  } else if (threadIdx.x < FPS_THREADS) {
+    if (a.stage)
+      fps_cta<4, 256, 4, true>(a, c, reinterpret_cast<float*>(smem));
+    else
+      fps_cta<4, 256, 4, false>(a, c, reinterpret_cast<float*>(smem));
+  }
+  if (clk && threadIdx.x == 0) {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    clk[(size_t)blockIdx.x * 16 + 9] = t;
+  }
+}
+
 __global__ void __launch_bounds__(CP_THREADS, 1) corr_pipe_kernel(const __grid_constant__ PipeParams prm) {
   extern __shared__ uint8_t cp_raw[];
   if ((int)blockIdx.x >= prm.nmain) {   // ride-along CTA: the next step's FPS (see PipeParams::ride)
-    pdl_trigger();
-    pdl_wait();
-    const int c = (int)blockIdx.x - prm.nmain;
-    if (c == prm.ride.nimg) {           // (only present when ride.pj.n > 0) all threads of the CTA draw the permutations
-      super_perms_block(prm.ride.pj.seed, prm.ride.pj.offset, prm.ride.pj.n, prm.ride.pj.B, prm.ride.pj.out,
-                        reinterpret_cast<int*>(cp_raw));
-      return;
-    }
-    if (threadIdx.x < FPS_THREADS) fps_cta<4, 256, 4>(prm.ride, c, reinterpret_cast<float*>(cp_raw));
+    ride_cta(prm.ride, (int)blockIdx.x - prm.nmain, cp_raw, prm.clk);
     return;
   }
   uint8_t* ring = cp_raw + ((1024u - (smem_u32(cp_raw) & 1023u)) & 1023u);   // 1024-byte aligned, stays an smem pointer
@@ -752,6 +769,7 @@ int corr_loss_pipe(const dg_panels_t* pan, const float* fmean, int nsplit, const
   memset(&prm.ride, 0, sizeof prm.ride);
   if (ride) {
     prm.ride = *ride;
+    prm.ride.clk = prm.clk;
     prm.nride = ride->nimg + (ride->pj.n > 0 ? 1 : 0);
   }
   DG_PRE(st);

@@ -31,7 +31,10 @@ __global__ void __launch_bounds__(FPS_THREADS) fps_kernel(const __grid_constant_
     super_perms_block(a.pj.seed, a.pj.offset, a.pj.n, a.pj.B, a.pj.out, reinterpret_cast<int*>(fps_dyn_smem));
     return;
   }
-  fps_cta<PPT, RT, PR>(a, (int)blockIdx.x, fps_dyn_smem);
+  if (a.stage)
+    fps_cta<PPT, RT, PR, true>(a, (int)blockIdx.x, fps_dyn_smem);
+  else
+    fps_cta<PPT, RT, PR, false>(a, (int)blockIdx.x, fps_dyn_smem);
 }
 
 // s = d / max(|d|, eps) of the align_corners=True bilinear resample of depth to SxS.
@@ -57,9 +60,10 @@ int make_fps_args(FpsArgs* a, size_t* smem_out, const float* depth_a, const floa
   const int npts = H * W;
   DG_REQUIRE(S * S <= npts, DG_ERR_INVALID, "dg_fps_coords: S*S=%d exceeds H*W=%d points", S * S, npts);
   DG_REQUIRE(npts <= 4096, DG_ERR_UNSUPPORTED, "dg_fps_coords: H*W=%d > 4096 not supported", npts);
-  const bool stage = ((Hd * Wd) % 4 == 0) && (fps_smem_bytes(npts, Hd, Wd, true) <= 220 * 1024) &&
+  // fast pooling path: aligned 8 x 8 windows and 16-byte aligned image rows (the reference's 224 x 224 -> 28 x 28)
+  const bool stage = Hd == 8 * H && Wd == 8 * W && (Wd % 4) == 0 && ((Hd * Wd) % 4) == 0 &&
                      ((reinterpret_cast<uintptr_t>(depth_a) | reinterpret_cast<uintptr_t>(depth_b)) % 16 == 0);
-  size_t smem = fps_smem_bytes(npts, Hd, Wd, stage);
+  size_t smem = fps_smem_bytes(npts);
   if (pj.n > 0) {   // the extra CTA shuffles in shared memory and needs one thread per permutation
     DG_REQUIRE(pj.n <= FPS_THREADS && (size_t)pj.n * pj.B * sizeof(int) <= 64 * 1024, DG_ERR_UNSUPPORTED,
                "fps: %d permutations of %d do not fit the fused draw", pj.n, pj.B);
@@ -73,6 +77,7 @@ int make_fps_args(FpsArgs* a, size_t* smem_out, const float* depth_a, const floa
   a->stage = stage ? 1 : 0;
   a->nimg = depth_b ? 2 * B : B;
   a->pj = pj;
+  a->clk = nullptr;
   *smem_out = smem;
   return DG_OK;
 }
@@ -107,7 +112,6 @@ int launch_fps(const float* depth_a, const float* depth_b, int B, int Hd, int Wd
   } else if (npts <= 8 * FPS_THREADS) {
     DG_FPS_LAUNCH(8, 256, 8);
   } else {
-    a.stage = 0;
     DG_FPS_LAUNCH(16, 256, 16);
   }
 #undef DG_FPS_LAUNCH

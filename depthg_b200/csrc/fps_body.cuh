@@ -37,9 +37,10 @@ struct FpsArgs {
   float* dsign;                // [B, sign_pitch] or null
   int sign_S, sign_pitch;
   float sign_eps;
-  int stage;                   // 1: the [Hd,Wd] image is staged in shared memory first
+  int stage;                   // 1: the fast pooling path (aligned 8 x 8 windows, see fps_cta<.., FAST8>)
   int nimg;                    // CTAs 0 .. nimg-1 run images; CTA nimg (when pj.n > 0) draws the permutations
   PermJob pj;
+  long long* clk;              // debug: [gridDim.x][16] %globaltimer stamps (slots 3-4: pooled+lifted / rounds done)
 };
 
 
@@ -67,9 +68,6 @@ __device__ __forceinline__ float depth_sign_value(const float* d, int Hd, int Wd
   const float v = (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
   return v / fmaxf(fabsf(v), eps);
 }
-
-// STAGE: the whole [Hd,Wd] depth image is first copied into shared memory with 16-byte cp.async
-// (every load in flight at once), so the pooling reads never wait on DRAM one window row at a time.
 
 // Packed fp32 pairs (FADD2 / FMUL2 of sm_100): two IEEE-rounded operations per instruction, bit-identical to the scalar
 // ones.  Only subtraction and multiplication are packed: ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2
@@ -180,8 +178,22 @@ __device__ __forceinline__ void fps_rounds(const float* sX, const float* sY, con
 // (0 .. 2B-1: depth_a then depth_b); `fps_smem` = the CTA's dynamic shared memory (fps_smem_bytes()).  CTA-wide
 // synchronisation is a named barrier over exactly these threads.
 __device__ __forceinline__ void fps_sync() { asm volatile("bar.sync 2, %0;" ::"n"(FPS_THREADS) : "memory"); }
+__device__ __forceinline__ void fps_stamp(const FpsArgs& a, int slot) {
+  if (a.clk && threadIdx.x == 0) {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    a.clk[(size_t)blockIdx.x * 16 + slot] = t;
+  }
+}
 
-template <int PPT, int RT, int PR>
+// FAST8 (template parameter; host-checked: Hd == 8 H, Wd == 8 W, 16-byte aligned rows): the adaptive-average-pooling
+// windows are the aligned 8 x 8 blocks, and a WARP pools one row of the feature grid at a time straight from global
+// memory - lane l loads the two float4 of pixel l in each of the 8 image rows (a row of the image = 28 lanes x 32
+// contiguous bytes: fully coalesced), all 16 loads of a lane and all rows of a warp in flight at once, then sums its 64
+// values in the reference's row-major order.  This replaced "stage the whole image in shared memory with cp.async,
+// then one thread per window": 6 us of staging + 4-10 us of pooling out of bank-conflicted shared memory per launch
+// (measured with %globaltimer stamps), and 200 KB of shared memory per CTA.
+template <int PPT, int RT, int PR, bool FAST8>
 __device__ __forceinline__ void fps_cta(const FpsArgs& a, int img, float* fps_smem) {
   const float* __restrict__ depth_a = a.depth_a;
   const float* __restrict__ depth_b = a.depth_b;
@@ -192,7 +204,6 @@ __device__ __forceinline__ void fps_cta(const FpsArgs& a, int img, float* fps_sm
   float* __restrict__ dsign = a.dsign;
   const int sign_S = a.sign_S, sign_pitch = a.sign_pitch;
   const float sign_eps = a.sign_eps;
-  const bool STAGE = a.stage != 0;
   const int npts = H * W;
   const int npad = (npts + 3) & ~3;
   int2 (*s_kv)[FPS_WARPS] = reinterpret_cast<int2 (*)[FPS_WARPS]>(fps_smem);       // [2][FPS_WARPS]
@@ -201,71 +212,71 @@ __device__ __forceinline__ void fps_cta(const FpsArgs& a, int img, float* fps_sm
   float* sY = sX + npad;
   float* sZ = sY + npad;
   unsigned char* sTaken = reinterpret_cast<unsigned char*>(sZ + npad);
-  float* sImg = reinterpret_cast<float*>(sTaken + ((npts + 15) & ~15));
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float* gdepth = (img < B ? depth_a + (size_t)img * Hd * Wd : depth_b + (size_t)(img - B) * Hd * Wd);
   const float* depth = gdepth;
-  if (STAGE) {
-    const int n16 = (Hd * Wd) >> 2;
-    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(sImg);
-    for (int i = tid; i < n16; i += FPS_THREADS)
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + 16u * i), "l"(gdepth + 4 * (size_t)i) : "memory");
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    fps_sync();
-    depth = sImg;
-  }
-
-  float X[PPT], Y[PPT], Z[PPT];
-  int key[PPT];  // int view of the running min distance; -1 once taken (or not a point)
   const float halfH = (float)H / 2.0f, halfW = (float)W / 2.0f;
-
-#pragma unroll
-  for (int j = 0; j < PPT; ++j) {
-    const int i = j * FPS_THREADS + tid;
-    X[j] = Y[j] = Z[j] = 0.f;
-    key[j] = -1;
-    if (i < npts) {
-      const int py = i / W, px = i - py * W;
-      const int ys = (py * Hd) / H, ye = ((py + 1) * Hd + H - 1) / H;
-      const int xs = (px * Wd) / W, xe = ((px + 1) * Wd + W - 1) / W;
-      float acc = 0.f;
-      if (xe - xs == 8 && ye - ys == 8 && (Wd & 3) == 0 && (xs & 3) == 0) {
-        // the common 8x8 window: all sixteen 128-bit loads first, then add in the reference's row-major order
+  // pooled value -> lifted point (depth2points, one rounding per operation) -> shared memory
+  auto put_point = [&](int py, int px, float acc, int kh, int kw) {
+    const int i = py * W + px;
+    const float pooled = __fdiv_rn(__fdiv_rn(acc, (float)kh), (float)kw);  // ATen: sum / kh / kw
+    const float fd = __fmul_rn(factor, pooled);
+    sX[i] = __fdiv_rn(__fmul_rn(fd, __fsub_rn((float)px, halfW)), (float)W);
+    sY[i] = __fdiv_rn(__fmul_rn(fd, __fsub_rn((float)py, halfH)), (float)H);
+    sZ[i] = __fmul_rn(-pooled, far_plane);
+    sTaken[i] = 0;
+  };
+  if (FAST8) {
+    // The image comes from HBM exactly once and a warp's rows are consumed one after the other (16 loads, then a chain
+    // of 64 additions): without help every row iteration pays a full DRAM round trip (4 x ~2 us per warp, measured).
+    // One bulk L2 prefetch per warp for its share of the image starts all of it moving at once; the loads below then
+    // find their lines in L2 or already on their way.
+    if (lane == 0) {
+      const size_t total = (size_t)Hd * Wd * sizeof(float);                  // a multiple of 16 (host-checked)
+      const size_t chunk = ((total / FPS_WARPS) + 15) & ~(size_t)15;
+      const size_t off = (size_t)warp * chunk;
+      if (off < total) {
+        const unsigned bytes = (unsigned)(total - off < chunk ? total - off : chunk);
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const char*>(gdepth) + off), "r"(bytes) : "memory");
+      }
+    }
+    for (int py = warp; py < H; py += FPS_WARPS) {
+      for (int px = lane; px < W; px += 32) {
         float4 v[16];
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
-          const float4* row = reinterpret_cast<const float4*>(depth + (size_t)(ys + r) * Wd + xs);
-          v[2 * r] = row[0];
-          v[2 * r + 1] = row[1];
+          const float4* row = reinterpret_cast<const float4*>(gdepth + (size_t)(8 * py + r) * Wd + 8 * px);
+          v[2 * r] = __ldg(row);
+          v[2 * r + 1] = __ldg(row + 1);
         }
+        float acc = 0.f;
 #pragma unroll
         for (int r = 0; r < 16; ++r) {
           acc = __fadd_rn(acc, v[r].x); acc = __fadd_rn(acc, v[r].y);
           acc = __fadd_rn(acc, v[r].z); acc = __fadd_rn(acc, v[r].w);
         }
-      } else {
-        for (int y = ys; y < ye; ++y)
-          for (int x = xs; x < xe; ++x) acc = __fadd_rn(acc, depth[(size_t)y * Wd + x]);
+        put_point(py, px, acc, 8, 8);
       }
-      const float pooled = __fdiv_rn(__fdiv_rn(acc, (float)(ye - ys)), (float)(xe - xs));  // ATen: sum / kh / kw
-      const float fd = __fmul_rn(factor, pooled);
-      X[j] = __fdiv_rn(__fmul_rn(fd, __fsub_rn((float)px, halfW)), (float)W);
-      Y[j] = __fdiv_rn(__fmul_rn(fd, __fsub_rn((float)py, halfH)), (float)H);
-      Z[j] = __fmul_rn(-pooled, far_plane);
-      key[j] = 0x7f800000;  // +inf
-      sX[i] = X[j];
-      sY[i] = Y[j];
-      sZ[i] = Z[j];
-      sTaken[i] = 0;
+    }
+  } else {
+    for (int i = tid; i < npts; i += FPS_THREADS) {
+      const int py = i / W, px = i - py * W;
+      const int ys = (py * Hd) / H, ye = ((py + 1) * Hd + H - 1) / H;
+      const int xs = (px * Wd) / W, xe = ((px + 1) * Wd + W - 1) / W;
+      float acc = 0.f;
+      for (int y = ys; y < ye; ++y)
+        for (int x = xs; x < xe; ++x) acc = __fadd_rn(acc, __ldg(depth + (size_t)y * Wd + x));
+      put_point(py, px, acc, ye - ys, xe - xs);
     }
   }
   fps_sync();
+  fps_stamp(a, 3);
   if (tid == 0) sTaken[0] = 1;  // point 0 is the first pick
 
   if (tid < RT) fps_rounds<PR, RT>(sX, sY, sZ, sTaken, npts, nsel, s_kv);
   fps_sync();
+  fps_stamp(a, 4);
 
   // Raster-order emission: each thread scans a contiguous chunk of point indices.
   const int chunk = (npts + FPS_THREADS - 1) / FPS_THREADS;
@@ -307,9 +318,8 @@ __device__ __forceinline__ void fps_cta(const FpsArgs& a, int img, float* fps_sm
 
 
 // dynamic shared memory of one FPS CTA
-__host__ __device__ inline size_t fps_smem_bytes(int npts, int Hd, int Wd, bool stage) {
-  return (size_t)FPS_SCRATCH_FLOATS * 4 + (size_t)((npts + 3) & ~3) * 3 * sizeof(float) + (size_t)((npts + 15) & ~15) +
-         (stage ? (size_t)Hd * Wd * sizeof(float) : 0);
+__host__ __device__ inline size_t fps_smem_bytes(int npts) {
+  return (size_t)FPS_SCRATCH_FLOATS * 4 + (size_t)((npts + 3) & ~3) * 3 * sizeof(float) + (size_t)((npts + 15) & ~15);
 }
 
 }  // namespace dg

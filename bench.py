@@ -490,7 +490,11 @@ def main():
     # on SMs that kernel's item list leaves idle, and forward i+1 starts at its gathers.  Every timed step still
     # computes exactly one batch's sampling inside the timed region (step i computes batch i+1's).
     # DEPTHG_BENCH_LOOKAHEAD=0 turns it off; the plain step is always reported as the side key `no_lookahead`.
-    lookahead = [os.environ.get("DEPTHG_BENCH_LOOKAHEAD", "1") != "0"]
+    # Default: on one GPU.  At N > 1 the step also carries the head-gradient all-reduce, which costs ~40 us a step
+    # when nothing hides it (a 2.9 MB exchange is latency and rank skew, not bandwidth); the in-step FPS kernel - 65
+    # CTAs on a 148-SM GPU - is where it hides, so there the plain schedule is the faster one (measured at N = 2:
+    # 0.2155 ms plain with the all-reduce under FPS, 0.220 ms with look-ahead sampling in any all-reduce placement).
+    lookahead = [os.environ.get("DEPTHG_BENCH_LOOKAHEAD", "1" if world == 1 else "0") != "0"]
     # at N > 1 the head-gradient all-reduce of step i runs on a side stream; with look-ahead there is no FPS kernel at
     # the start of step i+1 to hide it under: "gather" makes step i+1 wait for it before its gathers, "free" (default)
     # lets it run beside them (it only has to land before the next all-reduce / the end of the timed region)
@@ -568,9 +572,10 @@ def main():
     ms_per_step = ms / args.steps
     value = world * B * args.steps / (ms / 1e3)
 
-    # the plain step: every forward samples its own batch (FPS at the head of the step)
+    # the other schedule as a side key: the plain step (every forward samples its own batch, FPS at the head of the
+    # step) when look-ahead is the default, and vice versa
     look_default = lookahead[0]
-    lookahead[0] = False
+    lookahead[0] = not look_default
     loss_fn.queue_next_sampling(None, None)
     loss_fn._presampled = None
     for i in range(args.warmup):
@@ -588,6 +593,9 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_plain = float(t.item())
 
+    lookahead[0] = False
+    loss_fn.queue_next_sampling(None, None)
+    loss_fn._presampled = None
     # same step with negative_sampler="torch": neg_samples x torch.randperm replayed as a CUDA graph on a side stream
     # (the reference's exact RNG stream; more host work per step)
     loss_fn.negative_sampler = "torch"
@@ -889,9 +897,12 @@ def main():
                "parity_checked": parity,
                "roofline": {"bound": "tensor", "achieved": per_gpu_tflops, "peak": tf_burst,
                             "unit": "TFLOP/s per GPU", "frac": per_gpu_tflops / tf_burst, "n_gpus": world,
-                            "note": "useful flops 2 N^2 F counted once, divided by N_gpus x the measured bf16 burst "
-                                    "peak of ONE GPU; the tensor pass issues 3 MMAs per useful product (bf16 hi/lo "
-                                    "split) and is followed by an exact fp32 re-rank"}}
+                            "note": "useful flops 2 N^2 F counted once over the whole build (panel split, tensor "
+                                    "pass, exact fp32 re-rank), divided by N_gpus x the measured 16-bit burst peak of "
+                                    "ONE GPU; the default tensor pass is one fp16 product per pair (the fast pass of the "
+                                    "precision ladder) and is bound by the L2->SM operand stream (~9 TB/s aggregate), "
+                                    "not by the tensor pipe; DEPTHG_B200_KNN_PASS=split3 is the 3-term bf16 pass"},
+               "tensor_pass": os.environ.get("DEPTHG_B200_KNN_PASS", "fast fp16 (default)")}
 
     if knn is not None and rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
@@ -987,10 +998,12 @@ def main():
                 "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches),
                 "launches_per_step": launches / args.steps, "roofline": roofline, "roofline_step": roofline_step,
                 "breakdown_us": {k: round(v, 2) for k, v in breakdown.items()}, "cpu_baseline": cpu_baseline,
-                "no_lookahead": {"value": world * B * args.steps / (ms_plain / 1e3), "unit": UNIT,
-                                 "ms_per_step": ms_plain / args.steps,
-                                 "note": "the same step with the sampling inside it (FPS first, then the gathers): what "
-                                         "a caller gets without queue_next_sampling / prefetch_sampling"},
+                ("no_lookahead" if look_default else "lookahead"): {
+                    "value": world * B * args.steps / (ms_plain / 1e3), "unit": UNIT, "ms_per_step": ms_plain / args.steps,
+                    "note": ("the same step with the sampling inside it (FPS first, then the gathers): what a caller "
+                             "gets without queue_next_sampling / prefetch_sampling" if look_default else
+                             "the same step with the sampling one batch ahead (queue_next_sampling): the default on "
+                             "one GPU; with the per-step all-reduce it loses the FPS kernel the all-reduce hides under")},
                 "cuda_graph": graphed, "reference_ops_on_gpu": ref_gpu,
                 "torch_negative_sampler": {"value": world * B * args.steps / (ms_fused / 1e3), "unit": UNIT,
                                            "ms_per_step": ms_fused / args.steps,

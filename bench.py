@@ -490,11 +490,14 @@ def main():
     # on SMs that kernel's item list leaves idle, and forward i+1 starts at its gathers.  Every timed step still
     # computes exactly one batch's sampling inside the timed region (step i computes batch i+1's).
     # DEPTHG_BENCH_LOOKAHEAD=0 turns it off; the plain step is always reported as the side key `no_lookahead`.
-    # Default: on one GPU.  At N > 1 the step also carries the head-gradient all-reduce, which costs ~40 us a step
-    # when nothing hides it (a 2.9 MB exchange is latency and rank skew, not bandwidth); the in-step FPS kernel - 65
-    # CTAs on a 148-SM GPU - is where it hides, so there the plain schedule is the faster one (measured at N = 2:
-    # 0.2155 ms plain with the all-reduce under FPS, 0.220 ms with look-ahead sampling in any all-reduce placement).
-    lookahead = [os.environ.get("DEPTHG_BENCH_LOOKAHEAD", "1" if world == 1 else "0") != "0"]
+    # Default at every N.  At N > 1 the step also carries the head-gradient all-reduce (2.9 MB: latency and rank skew,
+    # not bandwidth).  Measured, ms/step (one B200 box, symmetric-memory all-reduce):
+    #              N = 1     N = 2     N = 8
+    #   look-ahead 0.179     0.220     0.237    all-reduce free-running beside the next step's gathers
+    #   in-step    0.208     0.2155    0.347    all-reduce under the next step's FPS kernel, forward waits for it
+    # The in-step schedule couples the ranks every step (the forward waits for the all-reduce, i.e. for the slowest
+    # rank); since the FPS kernel got shorter than the 8-rank all-reduce it no longer hides it.
+    lookahead = [os.environ.get("DEPTHG_BENCH_LOOKAHEAD", "1") != "0"]
     # at N > 1 the head-gradient all-reduce of step i runs on a side stream; with look-ahead there is no FPS kernel at
     # the start of step i+1 to hide it under: "gather" makes step i+1 wait for it before its gathers, "free" (default)
     # lets it run beside them (it only has to land before the next all-reduce / the end of the timed region)

@@ -16,12 +16,21 @@ configs[4] as side measurements), ``breakdown_us`` (library-side per-kernel even
 double-buffered and a serialised loop, both reported), ``cpu_baseline`` (oracle port on the host cores),
 ``reference_ops_on_gpu`` (the reference's op sequence as stock torch ops on this GPU), ``cuda_graph`` (same step,
 no host work) and ``torch_negative_sampler`` (same step with the reference's randperm stream), ``knn`` (the precompute_knns build, query-sharded at N > 1; ``parity_checked`` = the timed
-result against the oracle on sampled rows and, at N > 1, against a one-GPU build) and ``probes`` (fused probe losses vs the trainer's torch op sequence).  At N > 1 every step is followed by the
-all-reduce of the trainable-head gradient (729 012 floats)
+result against the oracle on sampled rows and, at N > 1, against a one-GPU build) and ``probes`` (fused probe losses vs
+the trainer's torch op sequence).
+
+Sampling schedule: by default the loss is handed batch i+1's depth maps before the forward of batch i
+(``queue_next_sampling``), so batch i+1's farthest-point sampling runs as extra CTAs of forward i's correlation kernel and
+every timed step still computes exactly one batch's sampling inside the timed region; ``no_lookahead`` is the same loop
+with the sampling at the head of each step (DEPTHG_BENCH_LOOKAHEAD=0 makes that the main value and reports the default
+as ``lookahead``).
+
+At N > 1 every step is followed by the all-reduce of the trainable-head gradient (729 012 floats)
 (DEPTHG_BENCH_ALLREDUCE = symm | symm_inline | fps | inline | graph | graph_hp | async | none; symm (default) = torch's
-symmetric-memory multimem / two-shot all-reduce on a side stream underneath the next step's FPS kernel - measured at
-N = 8: 0.260 ms/step vs 0.298 with the NCCL all-reduce in the same place and 0.258 on one GPU; fps = the NCCL
-all-reduce, captured once and replayed there).
+symmetric-memory multimem / two-shot all-reduce on a side stream; with look-ahead sampling it runs free beside the next
+step's gathers (DEPTHG_BENCH_AR_WAIT=gather: the next forward waits for it first), with in-step sampling underneath the
+next step's FPS kernel.  Measured, ms/step at N = 1 / 2 / 8: look-ahead 0.179 / 0.220 / 0.237, in-step 0.208 / 0.2155 /
+0.347).
 """
 from __future__ import annotations
 

@@ -721,7 +721,8 @@ class ContrastiveCorrelationLoss(nn.Module):
         use_pre = False
         self.last_used_presampled = False      # test hook
         if pre is not None and (flags & _lib.FLAG_FPS) and depth_pos is not None and compiled_binding() and \
-                not _CorrLossFn.debug and pre["key"] == self._sampling_key(depth, depth_pos, S, H, W, nneg):
+                not _CorrLossFn.debug and not torch.cuda.is_current_stream_capturing() and \
+                pre["key"] == self._sampling_key(depth, depth_pos, S, H, W, nneg):
             use_pre = self.last_used_presampled = True
             flags &= ~_lib.FLAG_FPS
             coords = pre["coords"]

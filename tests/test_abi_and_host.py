@@ -263,3 +263,19 @@ def test_fps_round_loop_has_no_fused_multiply_add():
         assert any(o.startswith("FMUL2") for o in ops), name
         checked += 1
     assert checked >= 4
+
+
+def test_ctypes_mirrors_have_the_c_struct_sizes(tmp_path):
+    """The ctypes Structures of depthg_b200/_lib.py must lay out like the C structs of include/depthg_b200.h (a field
+    added on one side only would shift every later field of the debug binding silently)."""
+    from depthg_b200 import _lib
+    import ctypes as C
+    src = tmp_path / "sizes.c"
+    src.write_text('#include <stdio.h>\n#include "depthg_b200.h"\nint main(void) { printf("%zu %zu %zu %zu\\n", '
+                   'sizeof(dg_loss_desc_t), sizeof(dg_loss_plan_t), sizeof(dg_loss_io_t), sizeof(dg_loss_grads_t)); '
+                   'return 0; }\n')
+    exe = tmp_path / "sizes"
+    subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    want = [C.sizeof(_lib.LossDesc), C.sizeof(_lib.LossPlan), C.sizeof(_lib.LossIO), C.sizeof(_lib.LossGrads)]
+    assert got == want, (got, want)

@@ -562,8 +562,15 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(args.warmup):
+    # Start-up priming, untimed and before the W warm-up steps: the first ~10 steps of a fresh process are not steady
+    # state (caching-allocator growth for the 151 MB arenas and the gradient / sampling buffers, lazy kernel-attribute
+    # set-up, clock ramp) - measured: 0.246 ms/step over 50 steps after 5 warm-up steps against 0.179 after 10+.
+    PRIME = 12
+    for i in range(PRIME):
         step(i)
+    barrier()
+    for i in range(args.warmup):        # (step indices keep counting, so the batch the last warm-up step sampled ahead
+        step(PRIME + i)                 #  IS the first timed step's batch)
     barrier()
     l0 = lib.dg_kernel_launches()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -571,7 +578,7 @@ def main():
         barrier()
         ev0.record()
         for i in range(args.steps):
-            step(i)
+            step(PRIME + args.warmup + i)
         drain()
         ev1.record()
         barrier()
@@ -997,6 +1004,7 @@ def main():
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": workload_config(B, world, extra={
                     "l2_policy": f"rotating {NSETS} input sets ({NSETS * step_bytes / 1e6:.0f} MB) > 126 MB L2",
+                    "priming_steps": PRIME,   # untimed start-up steps before the W warm-up steps
                     "negative_sampler": "fused (module default: drawn by one CTA of the sampling launch)",
                     "sampling_schedule": ("one batch ahead: batch i+1's FPS / depth signs / permutations ride as extra "
                                           "CTAs of forward i's correlation kernel (queue_next_sampling); every timed "

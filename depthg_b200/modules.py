@@ -727,8 +727,12 @@ class ContrastiveCorrelationLoss(nn.Module):
             flags &= ~_lib.FLAG_FPS
             coords = pre["coords"]
             dsign_in = pre["dsign"] if depth_term else None
-            if pre["event"] is not None:
-                torch.cuda.current_stream(dev).wait_event(pre["event"])
+            if pre["event"] is not None:     # produced on a side stream (prefetch_sampling)
+                cur = torch.cuda.current_stream(dev)
+                cur.wait_event(pre["event"])
+                for t in (pre["coords"], pre["dsign"], pre["perms"]):
+                    if t is not None:        # allocated on the side stream, consumed here: keep the allocator from
+                        t.record_stream(cur)  # handing the block out again before this stream is done with it
         also_wait, self.wait_after_fps = self.wait_after_fps, None
         perm_gen = None
         self.last_perms = None

@@ -4,15 +4,17 @@
 // (/root/reference/src/modules.py:999-1037, :988-996, :939-985), which pools on
 // the device, copies every image to the host and runs a 120-round NumPy loop.
 // Here the whole chain stays in one kernel:
-//   1. adaptive average pooling of the [Hd,Wd] depth to [H,W]: each thread owns
-//      pooled pixels and sums its window row-major with sequential fp32 adds
-//      (128-bit loads when the window is 8 wide), then ATen's sum / kh / kw;
+//   1. adaptive average pooling of the [Hd,Wd] depth to [H,W] straight from global
+//      memory: a warp per row of the feature grid with coalesced 128-bit loads when
+//      the windows are the aligned 8 x 8 blocks (a thread per window otherwise), every
+//      window summed row-major with sequential fp32 adds, then ATen's sum / kh / kw;
 //   2. lifting to 3-D with one explicit rounding per operation (no FMA);
 //   3. S*S-1 rounds of (distance to last pick, running min, block argmax).  The
-//      candidate key is the int view of the non-negative fp32 distance (-1 once a
-//      point is taken), so a warp argmax is two redux.sync instructions (max of
-//      the key, then min of the index among the maxima = NumPy's first-argmax);
-//      eight warp results meet in shared memory behind ONE barrier per round;
+//      candidate key is the int view of the non-negative fp32 distance, folded with a
+//      SIGNED integer minimum (a picked point drops to key 0 by itself: no marking), so
+//      a warp argmax is two redux.sync instructions (max of the key, then min of the
+//      index among the maxima = NumPy's first-argmax); eight warp results meet in
+//      shared memory behind ONE barrier per round;
 //   4. the selection ORDER is discarded like the reference does: a block scan of
 //      the taken flags emits the picks in raster order as indices and as
 //      normalised (row/H, col/W) coordinates.
@@ -44,7 +46,7 @@ struct FpsArgs {
 };
 
 
-constexpr int FPS_THREADS = 256;  // setup (staging, pooling, lifting) and emission threads; the rounds use the first RT of them
+constexpr int FPS_THREADS = 256;  // setup (pooling, lifting) and emission threads; the rounds use the first RT of them
 constexpr int FPS_WARPS = FPS_THREADS / 32;
 // measured on B200 (28x28 grid, S=11, one image per CTA; scripts/micro/fps_micro.cu): cycles per round 350 at RT=256,
 // 468 at 128, 367 at 512, 576 at 64 — a warp issues one instruction every other cycle, so fewer round threads pay in

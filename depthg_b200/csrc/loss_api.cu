@@ -227,9 +227,13 @@ extern "C" int dg_loss_forward(const dg_loss_desc_t* d, const dg_loss_io_t* io, 
   //  kernel's register footprint and lose the occupancy that hides their latency; kept for experiments)
   bool dots_done = false;
   rc = DG_ERR_UNSUPPORTED;
-  if (pl.kernel && !aug && getenv("DEPTHG_B200_GATHER_ALL"))
+  if (pl.kernel && !aug && getenv("DEPTHG_B200_GATHER_ALL")) {
     rc = launch_gather_all(ftab, ctab, nsets, B, d->C, d->D, d->H, d->W, coords, S, io->perms, kNormEps, pl.Prows, pl.ldf,
                            pl.ldc, nsplit, fo, co, st);
+    if (rc == DG_OK)   // this experimental launch has no job slot: the caller's buffers are cleared by plain memsets
+      for (int q = 0; q < 2; ++q)
+        if (io->clear[q] && io->clear_bytes[q]) DG_CUDA_OK(cudaMemsetAsync(io->clear[q], 0, io->clear_bytes[q], st));
+  }
   if (rc == DG_ERR_UNSUPPORTED) {
     rc = launch_gather(ffmt, ftab, nsets, B, d->C, d->H, d->W, coords, S, io->perms, kNormEps, pl.Prows, pl.ldf, nsplit, fo,
                        st);

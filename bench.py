@@ -1022,8 +1022,8 @@ def main():
                     "value": world * B * args.steps / (ms_plain / 1e3), "unit": UNIT, "ms_per_step": ms_plain / args.steps,
                     "note": ("the same step with the sampling inside it (FPS first, then the gathers): what a caller "
                              "gets without queue_next_sampling / prefetch_sampling" if look_default else
-                             "the same step with the sampling one batch ahead (queue_next_sampling): the default on "
-                             "one GPU; with the per-step all-reduce it loses the FPS kernel the all-reduce hides under")},
+                             "the same step with the sampling one batch ahead (queue_next_sampling): bench.py's "
+                             "default schedule (this run was started with DEPTHG_BENCH_LOOKAHEAD=0)")},
                 "cuda_graph": graphed, "reference_ops_on_gpu": ref_gpu,
                 "torch_negative_sampler": {"value": world * B * args.steps / (ms_fused / 1e3), "unit": UNIT,
                                            "ms_per_step": ms_fused / args.steps,
